@@ -1,0 +1,213 @@
+/*
+ * ls2d.h -- C ABI of the B200-native projective 2D scan-to-local-map registration path.
+ *
+ * This is the drop-in boundary for ONE hot path of rvp-group/srrg2_laser_slam_2d: everything that runs
+ * inside one MultiAligner2D::compute() call with laser slices.  Each entry point
+ * names the reference interface it replaces.  Reference paths are relative to
+ * /root/reference/srrg2_laser_slam_2d/ ; R/ = src/srrg2_laser_slam_2d/ ;
+ * L0.json = /root/reference/configurations/stage_segway_double_config_LASER_0.json.
+ *
+ * Conventions
+ *  - plain C: opaque handle, plain pointers and sizes, no C++/torch types.
+ *  - every function returns LS2D_OK (0) or a negative ls2d_error; nothing throws.
+ *  - pointers are HOST pointers unless the parameter name ends in _dev.
+ *  - a point is 4 floats (x, y, nx, ny) == PointNormal2f coordinates() + normal()
+ *    (R/registration/correspondence_finder_normal_2f.h:9-12); a cloud set is a CSR batch:
+ *    points [total, 4] + offsets [n_clouds + 1].
+ *  - poses are (x, y, theta) == geometry2d::t2v(Isometry2f).
+ *  - one handle == one device + one CUDA stream; a handle is not re-entrant (the reference's modules
+ *    are not thread-safe either), different handles may be used from different threads.
+ *  - there is NO CPU fallback: without a CUDA device every compute call returns LS2D_ERR_CUDA.
+ */
+#ifndef LS2D_H
+#define LS2D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LS2D_VERSION 100
+
+typedef struct ls2d_handle ls2d_handle;
+
+typedef enum {
+  LS2D_OK               = 0,
+  LS2D_ERR_INVALID      = -1, /* bad argument (mis-wiring; the reference throws std::runtime_error) */
+  LS2D_ERR_CUDA         = -2, /* CUDA runtime/driver error, or no device */
+  LS2D_ERR_NOT_READY    = -3, /* clouds / params not set (the reference: "Missing fixed!") */
+  LS2D_ERR_UNSUPPORTED  = -4, /* size outside the compiled kernel table */
+  LS2D_ERR_NCCL         = -5
+} ls2d_error;
+
+/* All parameters of the path, with the reference's names and defaults. */
+typedef struct {
+  /* PointNormal2fProjectorPolar (L0.json:312-338) */
+  int32_t canvas_cols;   /* 721 */
+  float angle_col_min;   /* -3.14159 */
+  float angle_col_max;   /*  3.14159 */
+  float range_min;       /* 0.3 */
+  float range_max;       /* 20 */
+  /* CorrespondenceFinderProjective2f (R/registration/correspondence_finder_projective_2d.h:16-21) */
+  float point_distance;  /* 0.5 */
+  float normal_cos;      /* 0.8 */
+  /* RobustifierCauchy.chi_threshold (L0.json:76-81); <= 0: slice has no robustifier (#pointer -1) */
+  float cauchy_chi_threshold; /* 0.01 */
+  /* IterationAlgorithmGN.damping (L0.json:83-88) */
+  float damping;         /* 0 */
+  /* MultiAligner2D.max_iterations / min_num_inliers (L0.json:9-37, 487-517) */
+  int32_t max_iterations;          /* 10 */
+  int32_t min_num_correspondences; /* AlignerSliceProcessor*.min_num_correspondences, 0 (L0.json:134) */
+  int32_t min_num_inliers;         /* 10 */
+  /* AlignerSliceProcessorLaser2DWithSensor (R/registration/aligner_slice_processor_laser_2d.h:21-42):
+   * sensor_in_robot looked up from the tf tree by setupFactor()
+   * (R/registration/aligner_slice_processor_laser_2d_impl.cpp:7-10) */
+  int32_t with_sensor;             /* 0 = AlignerSliceProcessorLaser2D */
+  float sensor_in_robot[3];
+} ls2d_params;
+
+/* MultiAligner2D status (+ SINGULAR for a non positive definite H) */
+typedef enum {
+  LS2D_STATUS_SUCCESS                    = 0,
+  LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES = 1,
+  LS2D_STATUS_NOT_ENOUGH_INLIERS         = 2,
+  LS2D_STATUS_SINGULAR                   = 3
+} ls2d_status;
+
+/* One alignment's outcome (64 B): movingInFixed(), the last iterationStats() entry, the information
+ * matrix H (apps/visual_test_aligner_2d.cpp:145-156). */
+typedef struct {
+  float x, y, theta;
+  float chi_inliers;
+  float chi_kernelized;
+  int32_t n_inliers;
+  int32_t n_kernelized;
+  int32_t n_corr;
+  int32_t status;
+  int32_t iterations;
+  float H[6]; /* H00 H01 H02 H11 H12 H22 */
+} ls2d_result;
+
+/* iterationStats() record (32 B); the pose is the estimate after that iteration's update */
+typedef struct {
+  float x, y, theta;
+  float chi_inliers, chi_kernelized;
+  int32_t n_inliers, n_kernelized, n_corr;
+} ls2d_iter_stats;
+
+/* loop-closure acceptance gates: MultiLoopDetectorBruteForce2D relocalize_min_inliers /
+ * relocalize_max_chi_inliers / relocalize_min_inliers_ratio (L0.json:627-634) */
+typedef struct {
+  int32_t min_inliers;        /* 300 */
+  float max_chi_per_inlier;   /* 0.1 */
+  float min_inlier_ratio;     /* 0.8 */
+} ls2d_gates;
+
+/* best accepted candidate of a verification shard (32 B) -- the record the ranks all-gather */
+typedef struct {
+  float x, y, theta;
+  float chi_inliers;
+  int32_t n_inliers;
+  int32_t n_corr;
+  int32_t candidate;  /* global candidate id, -1 = nothing accepted */
+  int32_t guess;      /* index of the winning initial guess */
+} ls2d_best;
+
+enum { LS2D_FIXED = 0, LS2D_MOVING = 1 };
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+/* replaces: construction of the BOSS-registered modules (R/instances.cpp:27-36) */
+int ls2d_create(ls2d_handle** h, int device);
+int ls2d_destroy(ls2d_handle* h);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the handle's own */
+int ls2d_set_stream(ls2d_handle* h, void* cuda_stream);
+int ls2d_sync(ls2d_handle* h);
+const char* ls2d_strerror(int err);
+int ls2d_version(void);
+
+/* ---- configuration ---------------------------------------------------------------------------------
+ * replaces: PARAM() properties of CorrespondenceFinderProjective2f, PointNormal2fProjectorPolar,
+ * AlignerSliceProcessorLaser2D[WithSensor], MultiAligner2D, RobustifierCauchy, IterationAlgorithmGN */
+void ls2d_default_params(ls2d_params* p);
+int ls2d_set_params(ls2d_handle* h, const ls2d_params* p);
+int ls2d_get_params(const ls2d_handle* h, ls2d_params* p);
+
+/* ---- clouds ----------------------------------------------------------------------------------------
+ * replaces: MultiAligner2D::setFixed / setMoving(PropertyContainer*) and
+ * CorrespondenceFinder_::setFixed / setMoving(const PointNormal2fVectorCloud*)
+ * (apps/visual_test_aligner_2d.cpp:108-126, apps/visual_test_correspondence_finder_projective_2d.cpp:73-79) */
+int ls2d_upload_clouds(ls2d_handle* h, int which, const float* points_xynn, const int32_t* offsets,
+                       int32_t n_clouds);
+/* borrow device-resident clouds (no copy); max_points = largest cloud in the set */
+int ls2d_set_clouds_dev(ls2d_handle* h, int which, const void* points_dev, const int32_t* offsets_dev,
+                        int32_t n_clouds, int32_t max_points);
+
+/* ---- registration ----------------------------------------------------------------------------------
+ * replaces: MultiAligner2D::setMovingInFixed + compute + movingInFixed + iterationStats
+ * (apps/visual_test_aligner_2d.cpp:123-156), batched: pair p aligns moving cloud moving_id[p] onto fixed
+ * cloud fixed_id[p] from init_xyt[p].  NULL ids mean id == p.  iter_stats (nullable) holds
+ * n_pairs * max_iterations records. */
+int ls2d_align_batch(ls2d_handle* h, const int32_t* fixed_id, const int32_t* moving_id,
+                     const float* init_xyt, int32_t n_pairs, ls2d_result* out,
+                     ls2d_iter_stats* iter_stats);
+/* same, everything device-resident, asynchronous on the handle's stream */
+int ls2d_align_batch_dev(ls2d_handle* h, const int32_t* fixed_id_dev, const int32_t* moving_id_dev,
+                         const float* init_xyt_dev, int32_t n_pairs, ls2d_result* out_dev,
+                         ls2d_iter_stats* iter_stats_dev);
+/* one call from host buffers: upload both cloud sets, align pair p = (fixed p, moving p), download */
+int ls2d_align_pairs_host(ls2d_handle* h, const float* fixed_points, const int32_t* fixed_offsets,
+                          const float* moving_points, const int32_t* moving_offsets,
+                          const float* init_xyt, int32_t n_pairs, ls2d_result* out);
+/* linearise once at init_xyt without updating the pose (chi / inliers / H of a guess) */
+int ls2d_score_batch(ls2d_handle* h, const int32_t* fixed_id, const int32_t* moving_id,
+                     const float* xyt, int32_t n_pairs, ls2d_result* out);
+int ls2d_score_batch_dev(ls2d_handle* h, const int32_t* fixed_id_dev, const int32_t* moving_id_dev,
+                         const float* xyt_dev, int32_t n_pairs, ls2d_result* out_dev);
+
+/* ---- finder / projector (drop-in + parity) ---------------------------------------------------------
+ * replaces: CorrespondenceFinderProjective2f::compute()
+ * (R/registration/correspondence_finder_projective_2d.cpp:18-77): ordered (ascending column) list of
+ * Correspondence(fixed_idx, moving_idx); arrays must hold canvas_cols entries. */
+int ls2d_find_correspondences(ls2d_handle* h, int32_t fixed_id, int32_t moving_id,
+                              const float* local_map_in_sensor_xyt, int32_t* fixed_idx,
+                              int32_t* moving_idx, int32_t* n_correspondences);
+/* replaces: PointNormal2fProjectorPolar::setCameraPose + compute
+ * (R/registration/correspondence_finder_projective_2d.cpp:40-41,47-48): per column the winning
+ * source_idx (-1 empty) and its depth (FLT_MAX empty); arrays hold canvas_cols entries. */
+int ls2d_project(ls2d_handle* h, int which, int32_t cloud_id, const float* camera_pose_xyt,
+                 int32_t* source_idx, float* depth);
+
+/* ---- loop-closure verification ---------------------------------------------------------------------
+ * replaces: the per-candidate loop of MultiLoopDetectorBruteForce2D::compute (config L0.json:613-635):
+ * fixed cloud query_id against moving clouds candidate_ids[0..n_cand) from guesses_xyt
+ * [n_cand * n_guess * 3], acceptance gates, deterministic best-of (most inliers, then lowest chi per
+ * inlier, then lowest candidate/guess).  candidate_base is added to the local candidate index in the
+ * reported record so that shards report global ids.  all_results (nullable) receives every alignment. */
+int ls2d_verify(ls2d_handle* h, int32_t query_id, const int32_t* candidate_ids, int32_t n_cand,
+                const float* guesses_xyt, int32_t n_guess, const ls2d_gates* gates,
+                int32_t candidate_base, ls2d_best* best, ls2d_result* all_results);
+/* device-resident variant: best_dev receives the shard's record (ready for an NCCL all-gather) */
+int ls2d_verify_dev(ls2d_handle* h, int32_t query_id, const int32_t* candidate_ids_dev, int32_t n_cand,
+                    const float* guesses_xyt_dev, int32_t n_guess, const ls2d_gates* gates,
+                    int32_t candidate_base, ls2d_best* best_dev, ls2d_result* all_results_dev);
+/* best-of over gathered shard records (host), same ordering rule */
+int ls2d_reduce_best(const ls2d_best* records, int32_t n, ls2d_best* out);
+/* ls2d_verify_dev + all-gather of the 32-byte records over an existing NCCL communicator
+ * (ncclComm_t passed as void*; libnccl is resolved at run time) + ls2d_reduce_best on every rank */
+int ls2d_verify_sharded_nccl(ls2d_handle* h, int32_t query_id, const int32_t* candidate_ids_dev,
+                             int32_t n_cand, const float* guesses_xyt_dev, int32_t n_guess,
+                             const ls2d_gates* gates, int32_t candidate_base, void* nccl_comm,
+                             int32_t n_ranks, ls2d_best* best);
+
+/* ---- introspection ---------------------------------------------------------------------------------*/
+/* threads per pair the fused kernel uses for clouds of up to max_points points: fixes the shape of its
+ * H/b reduction tree (the oracle's ORC_SUM_TREE mode mirrors it) */
+int ls2d_reduction_threads(int32_t max_points);
+/* kernels launched by this handle since creation */
+int64_t ls2d_launch_count(const ls2d_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,549 @@
+/*
+ * ls2d_oracle.c -- CPU restatement of the reference's projective 2D registration path.
+ * TEST INFRASTRUCTURE ONLY (see ls2d_oracle.h).  PARITY UNPINNED (see ls2d_oracle.h).
+ *
+ * Reference paths are relative to /root/reference/srrg2_laser_slam_2d/ ; R/ abbreviates
+ * src/srrg2_laser_slam_2d/ ; L0.json = /root/reference/configurations/
+ * stage_segway_double_config_LASER_0.json.
+ *
+ * Decision points (result-affecting choices the in-repo sources do not pin):
+ *  D1  column index = lrintf(u) (round to nearest, ties to even) -- the unprojector puts beam i
+ *      exactly at u = i (R/sensor_processing/raw_data_preprocessor_projective_2d.cpp:87-90).
+ *  D2  K00 = (float)C / (angle_col_max - angle_col_min), K01 = (float)C * 0.5f, all binary32
+ *      (camera-matrix layout: apps/synthetic_scene_generator.cpp:60-66).
+ *  D2b range gate: reject rho < range_min || rho > range_max.
+ *  D3  z-buffer: strict "rho < cell.depth" => nearest wins, first in iteration order wins ties.
+ *  D4  empty cell: source_idx = -1, depth = FLT_MAX.
+ *  D5  all points are Valid (no status channel; invalid beams are encoded as far points by the
+ *      generators).
+ *  D6  Cauchy: chi < tau => inlier (w = 1); else kernelized: a = chi/tau + 1, rho = tau*ln a,
+ *      w = 1/a.  tau <= 0 => no robustifier.
+ *  D7  error order [point-to-line ; dn.x ; dn.y].
+ *  D8  information matrix Omega = I3.
+ *  D9  WithSensor: finder gets S^-1 * X; factor predicts S^-1 * (X * p_m), rotations S^-1 * R.
+ *  D10 sum order: sequential in correspondence order (reference) or the CUDA tree (debug).
+ *  D11 3x3 solve in binary64 Cholesky LL^T with reciprocal pivots (Cholmod is double).
+ *  D12 pose state = Isometry2f content (tx, ty, c, s); X <- X * v2t(dx) by plain products,
+ *      no re-orthonormalisation; theta reported as atan2f(s, c).
+ *  D13 the camera pose goes through TWO Isometry2f::inverse() calls before touching a point
+ *      (finder: setCameraPose(local_map_in_sensor.inverse()),
+ *      R/registration/correspondence_finder_projective_2d.cpp:47; projector applies the inverse
+ *      of its camera pose) -- restated literally, since inverse(inverse(T)) != T in binary32.
+ */
+#include "ls2d_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+void orc_default_params(orc_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->canvas_cols             = 721;      /* L0.json:328 */
+  p->angle_col_min           = -3.14159f; /* L0.json:319 */
+  p->angle_col_max           = 3.14159f;  /* L0.json:316 */
+  p->range_min               = 0.3f;     /* L0.json:337 */
+  p->range_max               = 20.f;     /* L0.json:334 */
+  p->point_distance          = 0.5f;     /* correspondence_finder_projective_2d.h:19 */
+  p->normal_cos              = 0.8f;     /* correspondence_finder_projective_2d.h:21 */
+  p->cauchy_chi_threshold    = 0.01f;    /* L0.json:80 */
+  p->damping                 = 0.f;      /* L0.json:87 */
+  p->max_iterations          = 10;       /* L0.json:498 */
+  p->min_num_correspondences = 0;        /* L0.json:134 */
+  p->min_num_inliers         = 10;       /* L0.json:501 */
+  p->with_sensor             = 0;
+}
+
+/* ---------------------------------------------------------------- A.0 geometry helpers */
+
+/* geometry2d::v2t [srrg2_core; used at apps/visual_test_correspondence_finder_projective_2d.cpp:71] */
+orc_iso orc_v2t(float x, float y, float theta) {
+  orc_iso T;
+  T.tx = x;
+  T.ty = y;
+  T.c  = cosf(theta);
+  T.s  = sinf(theta);
+  return T;
+}
+
+/* geometry2d::t2v [used at apps/visual_test_aligner_2d.cpp:145]: theta = atan2(R10, R00) */
+void orc_t2v(orc_iso T, float* xyt) {
+  xyt[0] = T.tx;
+  xyt[1] = T.ty;
+  xyt[2] = atan2f(T.s, T.c);
+}
+
+/* R * v for R = [c -s; s c]: Eigen evaluates row0 = R00*v0 + R01*v1 with R01 = -s */
+static inline void rot(orc_iso T, float vx, float vy, float* ox, float* oy) {
+  *ox = T.c * vx + (-T.s) * vy;
+  *oy = T.s * vx + T.c * vy;
+}
+
+/* Isometry2f * Vector2f = linear()*v + translation() */
+static inline void apply(orc_iso T, float vx, float vy, float* ox, float* oy) {
+  float rx, ry;
+  rot(T, vx, vy, &rx, &ry);
+  *ox = rx + T.tx;
+  *oy = ry + T.ty;
+}
+
+/* Eigen Transform::inverse(Isometry): linear = R^T, translation = -(R^T * t) */
+orc_iso orc_inverse(orc_iso T) {
+  orc_iso I;
+  I.c = T.c;
+  I.s = -T.s;
+  float rx, ry;
+  rot(I, T.tx, T.ty, &rx, &ry);
+  I.tx = -rx;
+  I.ty = -ry;
+  return I;
+}
+
+/* Isometry2f * Isometry2f: linear = Ra*Rb (first column kept; the second is its exact
+ * rotation by 90 degrees in binary32, see D12), translation = Ra*tb + ta */
+orc_iso orc_compose(orc_iso A, orc_iso B) {
+  orc_iso C;
+  C.c = A.c * B.c + (-A.s) * B.s;
+  C.s = A.s * B.c + A.c * B.s;
+  apply(A, B.tx, B.ty, &C.tx, &C.ty);
+  return C;
+}
+
+/* ---------------------------------------------------------------- A.1 polar projector */
+
+/* PointNormal2fProjectorPolar::compute [srrg2_core srrg_pcl/point_projector*.h; call sites
+ * R/registration/correspondence_finder_projective_2d.cpp:40-41,47-48] */
+void orc_project(const orc_params* prm, orc_iso camera_pose, const orc_point* pts, int32_t n,
+                 orc_cell* image) {
+  const int32_t C = prm->canvas_cols;
+  const float K00 = (float) C / (prm->angle_col_max - prm->angle_col_min); /* D2 */
+  const float K01 = (float) C * 0.5f;
+  const orc_iso W = orc_inverse(camera_pose); /* world -> camera (D13) */
+  for (int32_t k = 0; k < C; ++k) {
+    image[k].source_idx = -1; /* D4 */
+    image[k].depth      = FLT_MAX;
+    image[k].px = image[k].py = image[k].nx = image[k].ny = 0.f;
+  }
+  for (int32_t i = 0; i < n; ++i) {
+    float px, py, nx, ny;
+    apply(W, pts[i].x, pts[i].y, &px, &py);
+    rot(W, pts[i].nx, pts[i].ny, &nx, &ny);
+    const float rho = sqrtf(px * px + py * py);
+    if (rho < prm->range_min || rho > prm->range_max) { /* D2b */
+      continue;
+    }
+    const float theta = atan2f(py, px);
+    const float u     = K00 * theta + K01;
+    const long col    = lrintf(u); /* D1 */
+    if (col < 0 || col >= C) {
+      continue;
+    }
+    orc_cell* cell = &image[col];
+    if (rho < cell->depth) { /* D3 */
+      cell->source_idx = i;
+      cell->depth      = rho;
+      cell->px         = px;
+      cell->py         = py;
+      cell->nx         = nx;
+      cell->ny         = ny;
+    }
+  }
+}
+
+/* ---------------------------------------------------------------- A.2 correspondence finder */
+
+/* R/registration/correspondence_finder_projective_2d.cpp:46-76, line by line */
+int32_t orc_find_correspondences(const orc_params* prm, const orc_cell* fixed_image,
+                                 const orc_point* moving, int32_t n_moving,
+                                 orc_iso local_map_in_sensor, orc_cell* moving_image,
+                                 int32_t* fixed_idx, int32_t* moving_idx) {
+  /* :47-48  the camera sits on the fixed */
+  orc_project(prm, orc_inverse(local_map_in_sensor), moving, n_moving, moving_image);
+  int32_t k = 0;
+  for (int32_t col = 0; col < prm->canvas_cols; ++col) { /* :55-59 lock-step walk */
+    const orc_cell* m = &moving_image[col];
+    const orc_cell* f = &fixed_image[col];
+    if (m->source_idx < 0 || f->source_idx < 0) { /* :61 */
+      continue;
+    }
+    if (fabsf(f->depth - m->depth) > prm->point_distance) { /* :65 */
+      continue;
+    }
+    if (m->nx * f->nx + m->ny * f->ny < prm->normal_cos) { /* :69 */
+      continue;
+    }
+    fixed_idx[k]  = f->source_idx; /* :73 Correspondence(fixed, moving) */
+    moving_idx[k] = m->source_idx;
+    ++k;
+  }
+  return k; /* :76 */
+}
+
+/* ---------------------------------------------------------------- A.3 factor */
+
+typedef struct {
+  orc_iso X;      /* estimate (moving_in_fixed, robot frame) */
+  orc_iso Sinv;   /* sensor_in_robot^-1 (WithSensor) */
+  orc_iso RX;     /* rotation used by the Jacobian: R (plain) or Rs^-1 * R (WithSensor) */
+  int with_sensor;
+} factor_ctx;
+
+/* e, J entries of SE2Plane2PlaneErrorFactor [srrg2_solver types_2d/se2_plane2plane_error_factor;
+ * type bound at R/registration/aligner_slice_processor_laser_2d.h:8,23]; 2D reduction of
+ * octave/solver/nicp_post.m:13-25 with the post-multiplied increment of nicp_post.m:96.
+ * J = [ Ja Jb Jc ; 0 0 d0 ; 0 0 d1 ]. */
+static inline void factor_eval(const factor_ctx* f, orc_point pf, orc_point pm, float* e, float* Ja,
+                               float* Jb, float* Jc, float* d0, float* d1) {
+  float px, py, nx, ny;
+  apply(f->X, pm.x, pm.y, &px, &py); /* p_pred = X * p_moving */
+  if (f->with_sensor) {              /* D9 */
+    float qx, qy;
+    apply(f->Sinv, px, py, &qx, &qy);
+    px = qx;
+    py = qy;
+  }
+  rot(f->RX, pm.nx, pm.ny, &nx, &ny); /* n_pred = R * n_moving */
+  const float dx = px - pf.x;
+  const float dy = py - pf.y;
+  e[0] = dx * pf.nx + dy * pf.ny; /* nt * (p_pred - p_fixed)   nicp_post.m:20 */
+  e[1] = nx - pf.nx;              /* n_pred - n_fixed          nicp_post.m:21 */
+  e[2] = ny - pf.ny;
+  *Ja = pf.nx * f->RX.c + pf.ny * f->RX.s;    /* nt * R        nicp_post.m:23 */
+  *Jb = pf.nx * (-f->RX.s) + pf.ny * f->RX.c;
+  *Jc = *Ja * (-pm.y) + *Jb * pm.x;           /* nt * R * (-y, x)^T   nicp_post.m:24 */
+  rot(f->RX, -pm.ny, pm.nx, d0, d1);          /* R * (-n.y, n.x)^T    nicp_post.m:25 */
+}
+
+static factor_ctx make_factor(const orc_params* prm, orc_iso X) {
+  factor_ctx f;
+  f.X           = X;
+  f.with_sensor = prm->with_sensor;
+  f.RX          = X;
+  f.Sinv        = orc_v2t(0.f, 0.f, 0.f);
+  if (prm->with_sensor) {
+    f.Sinv = orc_inverse(
+      orc_v2t(prm->sensor_in_robot[0], prm->sensor_in_robot[1], prm->sensor_in_robot[2]));
+    f.RX = orc_compose(f.Sinv, X); /* only its rotation is used */
+  }
+  return f;
+}
+
+void orc_error_and_jacobian(const orc_params* prm, orc_iso X, orc_point fixed, orc_point moving,
+                            float* e, float* J) {
+  factor_ctx f = make_factor(prm, X);
+  float Ja, Jb, Jc, d0, d1;
+  factor_eval(&f, fixed, moving, e, &Ja, &Jb, &Jc, &d0, &d1);
+  J[0] = Ja;
+  J[1] = Jb;
+  J[2] = Jc;
+  J[3] = 0.f;
+  J[4] = 0.f;
+  J[5] = d0;
+  J[6] = 0.f;
+  J[7] = 0.f;
+  J[8] = d1;
+}
+
+/* ---------------------------------------------------------------- A.4 / A.5 linearisation */
+
+/* slots: 0..5 = H00 H01 H02 H11 H12 H22, 6..8 = b, 9 = chi_inliers, 10 = chi_kernelized */
+#define NSLOT 11
+
+/* one correspondence's contribution: robustifier (A.4) + J^T (w Omega) J, J^T (w Omega) e (A.5).
+ * returns 1 if inlier, 0 if kernelized */
+static inline int contribution(const orc_params* prm, const factor_ctx* f, orc_point pf,
+                               orc_point pm, float* v) {
+  float e[3], Ja, Jb, Jc, d0, d1;
+  factor_eval(f, pf, pm, e, &Ja, &Jb, &Jc, &d0, &d1);
+  const float chi = (e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]; /* e^T Omega e, Omega = I (D8) */
+  float w         = 1.f;
+  int inlier      = 1;
+  float chi_in = chi, chi_k = 0.f;
+  const float tau = prm->cauchy_chi_threshold;
+  if (tau > 0.f && !(chi < tau)) { /* D6 */
+    const float inv_tau = 1.f / tau;
+    const float aux     = chi * inv_tau + 1.f;
+    chi_k               = tau * logf(aux);
+    w                   = 1.f / aux;
+    chi_in              = 0.f;
+    inlier              = 0;
+  }
+  const float wa = Ja * w, wb = Jb * w, wc = Jc * w, wd0 = d0 * w, wd1 = d1 * w;
+  v[0]  = wa * Ja;
+  v[1]  = wa * Jb;
+  v[2]  = wa * Jc;
+  v[3]  = wb * Jb;
+  v[4]  = wb * Jc;
+  v[5]  = (wc * Jc + wd0 * d0) + wd1 * d1;
+  v[6]  = wa * e[0];
+  v[7]  = wb * e[0];
+  v[8]  = (wc * e[0] + wd0 * e[1]) + wd1 * e[2];
+  v[9]  = chi_in;
+  v[10] = chi_k;
+  return inlier;
+}
+
+typedef struct {
+  float v[NSLOT];
+  int32_t n_inliers, n_kernelized;
+} lin_sums;
+
+static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
+                      const orc_point* moving, int32_t n_moving, const int32_t* fixed_idx,
+                      const int32_t* moving_idx, int32_t n_corr, int32_t sum_mode,
+                      int32_t tree_threads, lin_sums* out) {
+  const factor_ctx f = make_factor(prm, X);
+  memset(out, 0, sizeof(*out));
+  if (sum_mode == ORC_SUM_SEQUENTIAL) {
+    for (int32_t k = 0; k < n_corr; ++k) {
+      float v[NSLOT];
+      const int inl = contribution(prm, &f, fixed[fixed_idx[k]], moving[moving_idx[k]], v);
+      for (int s = 0; s < NSLOT; ++s) {
+        out->v[s] = out->v[s] + v[s];
+      }
+      out->n_inliers += inl;
+      out->n_kernelized += !inl;
+    }
+    return;
+  }
+  /* ORC_SUM_TREE: the CUDA kernel's fixed reduction shape (D10) */
+  const int32_t T = tree_threads;
+  float* part     = (float*) calloc((size_t) T * NSLOT, sizeof(float));
+  int32_t* fx_of  = (int32_t*) malloc(sizeof(int32_t) * (size_t)(n_moving > 0 ? n_moving : 1));
+  for (int32_t i = 0; i < n_moving; ++i) {
+    fx_of[i] = -1;
+  }
+  for (int32_t k = 0; k < n_corr; ++k) {
+    fx_of[moving_idx[k]] = fixed_idx[k]; /* a moving point wins at most one column */
+  }
+  for (int32_t i = 0; i < n_moving; ++i) { /* ascending i == ascending slot within a thread */
+    if (fx_of[i] < 0) {
+      continue;
+    }
+    float v[NSLOT];
+    const int inl = contribution(prm, &f, fixed[fx_of[i]], moving[i], v);
+    float* p      = part + (size_t)(i % T) * NSLOT;
+    for (int s = 0; s < NSLOT; ++s) {
+      p[s] = p[s] + v[s];
+    }
+    out->n_inliers += inl;
+    out->n_kernelized += !inl;
+  }
+  for (int32_t w = 0; w < T / 32; ++w) {
+    float* lane = part + (size_t) w * 32 * NSLOT;
+    for (int off = 16; off >= 1; off >>= 1) { /* v[l] = v[l] + v[l ^ off] on all lanes */
+      for (int l = 0; l < 32; ++l) {
+        if (l & off) {
+          continue;
+        }
+        for (int s = 0; s < NSLOT; ++s) {
+          const float a             = lane[l * NSLOT + s];
+          const float b             = lane[(l ^ off) * NSLOT + s];
+          lane[l * NSLOT + s]         = a + b;
+          lane[(l ^ off) * NSLOT + s] = b + a;
+        }
+      }
+    }
+    for (int s = 0; s < NSLOT; ++s) { /* sequential over warps */
+      out->v[s] = (w == 0) ? lane[s] : out->v[s] + lane[s];
+    }
+  }
+  free(part);
+  free(fx_of);
+}
+
+/* ---------------------------------------------------------------- A.6 GN step */
+
+/* IterationAlgorithmGN + 3x3 Cholesky (D11). returns 0 on success, -1 if not positive definite */
+static int solve3(const float* v, float damping, float* dx) {
+  const double H00 = (double) v[0] + (double) damping, H01 = v[1], H02 = v[2];
+  const double H11 = (double) v[3] + (double) damping, H12 = v[4];
+  const double H22 = (double) v[5] + (double) damping;
+  const double r0 = -(double) v[6], r1 = -(double) v[7], r2 = -(double) v[8];
+  if (!(H00 > 0.0)) {
+    return -1;
+  }
+  const double l00 = sqrt(H00), i00 = 1.0 / l00;
+  const double l10 = H01 * i00, l20 = H02 * i00;
+  const double t11 = H11 - l10 * l10;
+  if (!(t11 > 0.0)) {
+    return -1;
+  }
+  const double l11 = sqrt(t11), i11 = 1.0 / l11;
+  const double l21 = (H12 - l20 * l10) * i11;
+  const double t22 = (H22 - l20 * l20) - l21 * l21;
+  if (!(t22 > 0.0)) {
+    return -1;
+  }
+  const double l22 = sqrt(t22), i22 = 1.0 / l22;
+  const double y0 = r0 * i00;
+  const double y1 = (r1 - l10 * y0) * i11;
+  const double y2 = ((r2 - l20 * y0) - l21 * y1) * i22;
+  const double x2 = y2 * i22;
+  const double x1 = (y1 - l21 * x2) * i11;
+  const double x0 = ((y0 - l10 * x1) - l20 * x2) * i00;
+  dx[0]           = (float) x0;
+  dx[1]           = (float) x1;
+  dx[2]           = (float) x2;
+  if (!isfinite(dx[0]) || !isfinite(dx[1]) || !isfinite(dx[2])) {
+    return -1;
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------- A.7 outer loop */
+
+void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
+               const orc_point* moving, int32_t n_moving, const float* init_xyt,
+               int32_t sum_mode, int32_t tree_threads, orc_result* out,
+               orc_iter_stats* iter_stats) {
+  const int32_t C      = prm->canvas_cols;
+  orc_cell* fixed_img  = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
+  orc_cell* moving_img = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
+  int32_t* fidx        = (int32_t*) malloc(sizeof(int32_t) * (size_t) C);
+  int32_t* midx        = (int32_t*) malloc(sizeof(int32_t) * (size_t) C);
+
+  /* correspondence_finder_projective_2d.cpp:37-44: fixed projected once, identity camera */
+  orc_project(prm, orc_v2t(0.f, 0.f, 0.f), fixed, n_fixed, fixed_img);
+
+  orc_iso X = orc_v2t(init_xyt[0], init_xyt[1], init_xyt[2]); /* setMovingInFixed */
+  orc_iso Sinv = orc_v2t(0.f, 0.f, 0.f);
+  if (prm->with_sensor) {
+    Sinv = orc_inverse(
+      orc_v2t(prm->sensor_in_robot[0], prm->sensor_in_robot[1], prm->sensor_in_robot[2]));
+  }
+  memset(out, 0, sizeof(*out));
+  if (iter_stats) {
+    memset(iter_stats, 0, sizeof(orc_iter_stats) * (size_t) prm->max_iterations);
+  }
+  lin_sums sums;
+  memset(&sums, 0, sizeof(sums));
+  int32_t n_corr = 0;
+  int32_t status = -1;
+  int32_t it     = 0;
+  for (; it < prm->max_iterations; ++it) {
+    /* slice->findCorrespondences(): local_map_in_sensor = sensor_in_robot^-1 * moving_in_fixed */
+    const orc_iso L = prm->with_sensor ? orc_compose(Sinv, X) : X;
+    n_corr = orc_find_correspondences(prm, fixed_img, moving, n_moving, L, moving_img, fidx, midx);
+    memset(&sums, 0, sizeof(sums));
+    if (n_corr <= prm->min_num_correspondences) {
+      status = ORC_STATUS_NOT_ENOUGH_CORRESPONDENCES;
+      break;
+    }
+    linearize(prm, X, fixed, moving, n_moving, fidx, midx, n_corr, sum_mode, tree_threads, &sums);
+    float dx[3];
+    if (solve3(sums.v, prm->damping, dx) != 0) {
+      status = ORC_STATUS_SINGULAR;
+      break;
+    }
+    X = orc_compose(X, orc_v2t(dx[0], dx[1], dx[2])); /* VariableSE2Right: X <- X * v2t(dx) */
+    if (iter_stats) {
+      orc_iter_stats* st = &iter_stats[it];
+      float xyt[3];
+      orc_t2v(X, xyt);
+      st->x              = xyt[0];
+      st->y              = xyt[1];
+      st->theta          = xyt[2];
+      st->chi_inliers    = sums.v[9];
+      st->chi_kernelized = sums.v[10];
+      st->n_inliers      = sums.n_inliers;
+      st->n_kernelized   = sums.n_kernelized;
+      st->n_corr         = n_corr;
+    }
+  }
+  if (status < 0) {
+    status = (sums.n_inliers < prm->min_num_inliers) ? ORC_STATUS_NOT_ENOUGH_INLIERS
+                                                     : ORC_STATUS_SUCCESS;
+  }
+  float xyt[3];
+  orc_t2v(X, xyt);
+  out->x              = xyt[0];
+  out->y              = xyt[1];
+  out->theta          = xyt[2];
+  out->chi_inliers    = sums.v[9];
+  out->chi_kernelized = sums.v[10];
+  out->n_inliers      = sums.n_inliers;
+  out->n_kernelized   = sums.n_kernelized;
+  out->n_corr         = n_corr;
+  out->status         = status;
+  out->iterations     = it;
+  for (int s = 0; s < 6; ++s) {
+    out->H[s] = sums.v[s];
+  }
+  free(fixed_img);
+  free(moving_img);
+  free(fidx);
+  free(midx);
+}
+
+void orc_align_batch(const orc_params* prm, const orc_point* fixed_pts, const int32_t* fixed_off,
+                     const orc_point* moving_pts, const int32_t* moving_off,
+                     const int32_t* fixed_id, const int32_t* moving_id, const float* init_xyt,
+                     int32_t n_pairs, int32_t sum_mode, int32_t tree_threads, int32_t n_threads,
+                     orc_result* out, orc_iter_stats* iter_stats) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8) num_threads(n_threads > 1 ? n_threads : 1)
+#endif
+  for (int32_t p = 0; p < n_pairs; ++p) {
+    const int32_t f = fixed_id ? fixed_id[p] : p;
+    const int32_t m = moving_id ? moving_id[p] : p;
+    orc_align(prm, fixed_pts + fixed_off[f], fixed_off[f + 1] - fixed_off[f],
+              moving_pts + moving_off[m], moving_off[m + 1] - moving_off[m], init_xyt + 3 * p,
+              sum_mode, tree_threads, out + p,
+              iter_stats ? iter_stats + (size_t) p * prm->max_iterations : NULL);
+  }
+}
+
+/* ---------------------------------------------------------------- A.8 verification gates */
+
+int32_t orc_accept(const orc_result* r, int32_t min_inliers, float max_chi_per_inlier,
+                   float min_inlier_ratio) {
+  if (r->status != ORC_STATUS_SUCCESS) {
+    return 0;
+  }
+  if (r->n_inliers < min_inliers) { /* relocalize_min_inliers  L0.json:627-634 */
+    return 0;
+  }
+  if (r->n_inliers <= 0 || r->n_corr <= 0) {
+    return 0;
+  }
+  if (r->chi_inliers / (float) r->n_inliers > max_chi_per_inlier) {
+    return 0;
+  }
+  if ((float) r->n_inliers / (float) r->n_corr < min_inlier_ratio) {
+    return 0;
+  }
+  return 1;
+}
+
+int32_t orc_best_of(const orc_result* r, int32_t n, int32_t min_inliers, float max_chi_per_inlier,
+                    float min_inlier_ratio) {
+  int32_t best = -1;
+  for (int32_t i = 0; i < n; ++i) {
+    if (!orc_accept(&r[i], min_inliers, max_chi_per_inlier, min_inlier_ratio)) {
+      continue;
+    }
+    if (best < 0) {
+      best = i;
+      continue;
+    }
+    const float ci = r[i].chi_inliers / (float) r[i].n_inliers;
+    const float cb = r[best].chi_inliers / (float) r[best].n_inliers;
+    if (r[i].n_inliers > r[best].n_inliers ||
+        (r[i].n_inliers == r[best].n_inliers && ci < cb)) {
+      best = i; /* ties keep the lowest id */
+    }
+  }
+  return best;
+}
+
+int32_t orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,150 @@
+/*
+ * ls2d_oracle.h -- CPU restatement ("oracle") of the srrg2_laser_slam_2d projective
+ * 2D scan-to-local-map registration path.
+ *
+ * THIS IS TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product library
+ * (libls2d.so) never links, loads or calls anything in this directory.
+ *
+ * PARITY UNPINNED: the reference cannot be built here (it needs Eigen3, srrg2_core,
+ * srrg2_solver, srrg2_slam_interfaces, catkin -- none present, none version-pinned:
+ * srrg2_laser_slam_2d/package.xml:14-21) and its own tests hold no golden vector for
+ * this path.  What is in-repo is followed line by line
+ * (correspondence_finder_projective_2d.cpp:18-77); what lives in the un-vendored
+ * dependencies is restated from their published behaviour, and every result-affecting
+ * choice is a numbered decision point D1..D13 documented in ls2d_oracle.c.
+ *
+ * Arithmetic contract: every floating-point operation below is ONE IEEE-754 binary32
+ * operation (no FMA contraction; build with -ffp-contract=off), in the order Eigen
+ * evaluates the reference's expressions; transcendental functions are glibc's
+ * (atan2f, sinf, cosf, logf, sqrtf).  The 3x3 solve is binary64 (Cholmod is double).
+ */
+#ifndef LS2D_ORACLE_H
+#define LS2D_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* PointNormal2f [srrg2_core, used at correspondence_finder_normal_2f.h:9-12] */
+typedef struct {
+  float x, y, nx, ny;
+} orc_point;
+
+/* SE(2) isometry kept as Eigen's Isometry2f content: R = [c -s; s c], t = (tx, ty) */
+typedef struct {
+  float tx, ty, c, s;
+} orc_iso;
+
+/* one cell of PointNormal2fProjectorPolar::TargetMatrixType
+ * (fields read at correspondence_finder_projective_2d.cpp:61-73) */
+typedef struct {
+  int32_t source_idx; /* -1 = empty */
+  float depth;        /* range rho [m]; FLT_MAX when empty (D4) */
+  float px, py, nx, ny; /* "transformed" point in the camera frame */
+} orc_cell;
+
+typedef struct {
+  /* PointNormal2fProjectorPolar params (LASER_0.json:312-338) */
+  int32_t canvas_cols;
+  float angle_col_min, angle_col_max;
+  float range_min, range_max;
+  /* CorrespondenceFinderProjective2f params (correspondence_finder_projective_2d.h:16-21) */
+  float point_distance, normal_cos;
+  /* RobustifierCauchy chi_threshold (LASER_0.json:76-81); <= 0 means "no robustifier" */
+  float cauchy_chi_threshold;
+  /* IterationAlgorithmGN damping (LASER_0.json:83-88) */
+  float damping;
+  /* MultiAligner2D (LASER_0.json:9-37) / slice (LASER_0.json:115-143) */
+  int32_t max_iterations;
+  int32_t min_num_correspondences;
+  int32_t min_num_inliers;
+  /* AlignerSliceProcessorLaser2DWithSensor: sensor_in_robot (x, y, theta) */
+  int32_t with_sensor;
+  float sensor_in_robot[3];
+} orc_params;
+
+enum {
+  ORC_STATUS_SUCCESS = 0,
+  ORC_STATUS_NOT_ENOUGH_CORRESPONDENCES = 1,
+  ORC_STATUS_NOT_ENOUGH_INLIERS = 2,
+  ORC_STATUS_SINGULAR = 3
+};
+
+/* 64-byte result record; same field order as ls2d_result in include/ls2d.h */
+typedef struct {
+  float x, y, theta;     /* movingInFixed() as t2v */
+  float chi_inliers;     /* last iteration's stats (linearisation point of that iteration) */
+  float chi_kernelized;
+  int32_t n_inliers;
+  int32_t n_kernelized;
+  int32_t n_corr;
+  int32_t status;
+  int32_t iterations;    /* iterations actually run */
+  float H[6];            /* H00 H01 H02 H11 H12 H22 of the last linearisation */
+} orc_result;
+
+/* per-iteration record (32 B); pose is the estimate AFTER that iteration's update */
+typedef struct {
+  float x, y, theta;
+  float chi_inliers, chi_kernelized;
+  int32_t n_inliers, n_kernelized, n_corr;
+} orc_iter_stats;
+
+/* accumulation order (D10): sequential in correspondence order (the reference's), or the
+ * fixed-shape tree of the CUDA kernel: thread t owns moving points t, t+T, ...; per-thread
+ * sequential, xor-butterfly inside each 32-lane warp, then sequential over warps. */
+enum { ORC_SUM_SEQUENTIAL = 0, ORC_SUM_TREE = 1 };
+
+void orc_default_params(orc_params* p);
+
+/* geometry2d::v2t / t2v, Isometry2f::inverse, operator* */
+orc_iso orc_v2t(float x, float y, float theta);
+void orc_t2v(orc_iso T, float* xyt);
+orc_iso orc_inverse(orc_iso T);
+orc_iso orc_compose(orc_iso A, orc_iso B);
+
+/* PointNormal2fProjectorPolar: setCameraPose(camera_pose) + compute(image, pts[0..n)) */
+void orc_project(const orc_params* prm, orc_iso camera_pose, const orc_point* pts, int32_t n,
+                 orc_cell* image /* canvas_cols cells */);
+
+/* CorrespondenceFinderProjective2f::compute() with an already projected fixed image.
+ * Returns the number of correspondences; fills moving_image (canvas_cols cells). */
+int32_t orc_find_correspondences(const orc_params* prm, const orc_cell* fixed_image,
+                                 const orc_point* moving, int32_t n_moving,
+                                 orc_iso local_map_in_sensor, orc_cell* moving_image,
+                                 int32_t* fixed_idx, int32_t* moving_idx);
+
+/* SE2Plane2PlaneErrorFactor::errorAndJacobian for one correspondence: e[3], J[9] row-major */
+void orc_error_and_jacobian(const orc_params* prm, orc_iso X, orc_point fixed, orc_point moving,
+                            float* e, float* J);
+
+/* MultiAligner2D::compute() for one pair */
+void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
+               const orc_point* moving, int32_t n_moving, const float* init_xyt,
+               int32_t sum_mode, int32_t tree_threads, orc_result* out,
+               orc_iter_stats* iter_stats /* max_iterations records or NULL */);
+
+/* batch over CSR clouds; n_threads <= 1 runs the reference's single-threaded model,
+ * otherwise an OpenMP parallel-for over the independent pairs */
+void orc_align_batch(const orc_params* prm, const orc_point* fixed_pts, const int32_t* fixed_off,
+                     const orc_point* moving_pts, const int32_t* moving_off,
+                     const int32_t* fixed_id, const int32_t* moving_id, const float* init_xyt,
+                     int32_t n_pairs, int32_t sum_mode, int32_t tree_threads, int32_t n_threads,
+                     orc_result* out, orc_iter_stats* iter_stats);
+
+/* loop-closure acceptance gates (MultiLoopDetectorBruteForce2D, LASER_0.json:627-634) and the
+ * deterministic best-of rule. Returns index of the best accepted result or -1. */
+int32_t orc_accept(const orc_result* r, int32_t min_inliers, float max_chi_per_inlier,
+                   float min_inlier_ratio);
+int32_t orc_best_of(const orc_result* r, int32_t n, int32_t min_inliers, float max_chi_per_inlier,
+                    float min_inlier_ratio);
+
+int32_t orc_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,266 @@
+"""ctypes binding of the C ABI in include/ls2d.h (libls2d.so).
+
+Thin plumbing for the Python test-suite and bench harness: every call goes straight to the CUDA
+library.  There is no Python or CPU implementation of the path here -- if the library is missing or
+no CUDA device is present the calls fail loudly (Ls2dError)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libls2d.so")
+MATHCHECK_PATH = os.path.join(_HERE, "libls2d_mathcheck.so")
+
+LS2D_FIXED, LS2D_MOVING = 0, 1
+STATUS_SUCCESS, STATUS_NOT_ENOUGH_CORRESPONDENCES, STATUS_NOT_ENOUGH_INLIERS, STATUS_SINGULAR = 0, 1, 2, 3
+
+
+class Ls2dError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """ls2d_params -- the reference's parameter names (include/ls2d.h)."""
+    _fields_ = [("canvas_cols", C.c_int32), ("angle_col_min", C.c_float), ("angle_col_max", C.c_float),
+                ("range_min", C.c_float), ("range_max", C.c_float), ("point_distance", C.c_float),
+                ("normal_cos", C.c_float), ("cauchy_chi_threshold", C.c_float), ("damping", C.c_float),
+                ("max_iterations", C.c_int32), ("min_num_correspondences", C.c_int32),
+                ("min_num_inliers", C.c_int32), ("with_sensor", C.c_int32),
+                ("sensor_in_robot", C.c_float * 3)]
+
+
+class Gates(C.Structure):
+    _fields_ = [("min_inliers", C.c_int32), ("max_chi_per_inlier", C.c_float), ("min_inlier_ratio", C.c_float)]
+
+
+RESULT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
+                         ("chi_kernelized", "<f4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"),
+                         ("n_corr", "<i4"), ("status", "<i4"), ("iterations", "<i4"), ("H", "<f4", (6,))])
+ITER_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
+                       ("chi_kernelized", "<f4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"),
+                       ("n_corr", "<i4")])
+BEST_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
+                       ("n_inliers", "<i4"), ("n_corr", "<i4"), ("candidate", "<i4"), ("guess", "<i4")])
+assert RESULT_DTYPE.itemsize == 64 and ITER_DTYPE.itemsize == 32 and BEST_DTYPE.itemsize == 32
+
+# every symbol include/ls2d.h declares (tests/test_abi_symbols.py checks the library exports them all)
+EXPORTS = [
+    "ls2d_create", "ls2d_destroy", "ls2d_set_stream", "ls2d_sync", "ls2d_strerror", "ls2d_version",
+    "ls2d_default_params", "ls2d_set_params", "ls2d_get_params", "ls2d_upload_clouds", "ls2d_set_clouds_dev",
+    "ls2d_align_batch", "ls2d_align_batch_dev", "ls2d_align_pairs_host", "ls2d_score_batch",
+    "ls2d_score_batch_dev", "ls2d_find_correspondences", "ls2d_project", "ls2d_verify", "ls2d_verify_dev",
+    "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_threads", "ls2d_launch_count",
+]
+
+_lib = None
+
+
+def load():
+    """dlopen libls2d.so and declare the prototypes.  Raises Ls2dError if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Ls2dError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback for this path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f32, i64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
+    PP, GP = C.POINTER(Params), C.POINTER(Gates)
+    L.ls2d_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.ls2d_destroy.argtypes = [vp]
+    L.ls2d_set_stream.argtypes = [vp, vp]
+    L.ls2d_sync.argtypes = [vp]
+    L.ls2d_strerror.argtypes, L.ls2d_strerror.restype = [C.c_int], C.c_char_p
+    L.ls2d_default_params.argtypes, L.ls2d_default_params.restype = [PP], None
+    L.ls2d_set_params.argtypes = [vp, PP]
+    L.ls2d_get_params.argtypes = [vp, PP]
+    L.ls2d_upload_clouds.argtypes = [vp, C.c_int, vp, vp, i32]
+    L.ls2d_set_clouds_dev.argtypes = [vp, C.c_int, vp, vp, i32, i32]
+    L.ls2d_align_batch.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    L.ls2d_align_batch_dev.argtypes = [vp, vp, vp, vp, i32, vp, vp]
+    L.ls2d_align_pairs_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    L.ls2d_score_batch.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ls2d_score_batch_dev.argtypes = [vp, vp, vp, vp, i32, vp]
+    L.ls2d_find_correspondences.argtypes = [vp, i32, i32, vp, vp, vp, C.POINTER(i32)]
+    L.ls2d_project.argtypes = [vp, C.c_int, i32, vp, vp, vp]
+    L.ls2d_verify.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]
+    L.ls2d_verify_dev.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]
+    L.ls2d_reduce_best.argtypes = [vp, i32, vp]
+    L.ls2d_verify_sharded_nccl.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, i32, vp]
+    L.ls2d_reduction_threads.argtypes = [i32]
+    L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
+    _lib = L
+    return L
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    load().ls2d_default_params(C.byref(p))
+    for k, v in kw.items():
+        if k == "sensor_in_robot":
+            p.sensor_in_robot = (C.c_float * 3)(*v)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def reduction_threads(max_points: int) -> int:
+    return load().ls2d_reduction_threads(max_points)
+
+
+def reduce_best(records: np.ndarray) -> np.ndarray:
+    records = np.ascontiguousarray(records, dtype=BEST_DTYPE)
+    out = np.zeros(1, BEST_DTYPE)
+    rc = load().ls2d_reduce_best(_ptr(records), len(records), _ptr(out))
+    if rc:
+        raise Ls2dError(load().ls2d_strerror(rc).decode())
+    return out[0]
+
+
+class Handle:
+    """One ls2d_handle: one device, one stream.  Host-array methods copy in/out; *_dev methods take raw
+    device addresses (ints, e.g. torch.Tensor.data_ptr()) and are asynchronous on the handle's stream."""
+
+    def __init__(self, device: int = 0, params: Params | None = None):
+        self._L = load()
+        self._h = C.c_void_p()
+        self._check(self._L.ls2d_create(C.byref(self._h), device))
+        self.params = params if params is not None else default_params()
+        self.set_params(self.params)
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise Ls2dError(f"ls2d error {rc}: {self._L.ls2d_strerror(rc).decode()}")
+
+    def close(self):
+        if self._h:
+            self._L.ls2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- configuration
+    def set_params(self, p: Params):
+        self._check(self._L.ls2d_set_params(self._h, C.byref(p)))
+        self.params = p
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._L.ls2d_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        self._check(self._L.ls2d_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.ls2d_launch_count(self._h))
+
+    # ---- clouds
+    def upload_clouds(self, which: int, points: np.ndarray, offsets: np.ndarray):
+        points, offsets = _f32(points), _i32(offsets)
+        assert points.ndim == 2 and points.shape[1] == 4 and offsets[-1] == len(points)
+        self._check(self._L.ls2d_upload_clouds(self._h, which, _ptr(points), _ptr(offsets), len(offsets) - 1))
+        self.sync()  # the numpy temporaries may die after this call
+
+    def set_clouds_dev(self, which: int, points_ptr: int, offsets_ptr: int, n_clouds: int, max_points: int):
+        self._check(self._L.ls2d_set_clouds_dev(self._h, which, C.c_void_p(points_ptr), C.c_void_p(offsets_ptr),
+                                                n_clouds, max_points))
+
+    # ---- registration
+    def align_batch(self, init_xyt, fixed_id=None, moving_id=None, want_iters: bool = False):
+        init = _f32(init_xyt).reshape(-1, 3)
+        fid, mid = _i32(fixed_id), _i32(moving_id)
+        n = len(init)
+        out = np.zeros(n, RESULT_DTYPE)
+        its = np.zeros((n, self.params.max_iterations), ITER_DTYPE) if want_iters else None
+        self._check(self._L.ls2d_align_batch(self._h, _ptr(fid), _ptr(mid), _ptr(init), n, _ptr(out), _ptr(its)))
+        return (out, its) if want_iters else out
+
+    def align_batch_dev(self, fixed_id_ptr, moving_id_ptr, init_ptr: int, n_pairs: int, out_ptr: int,
+                        iters_ptr: int | None = None):
+        self._check(self._L.ls2d_align_batch_dev(self._h, C.c_void_p(fixed_id_ptr or 0), C.c_void_p(moving_id_ptr or 0),
+                                                 C.c_void_p(init_ptr), n_pairs, C.c_void_p(out_ptr),
+                                                 C.c_void_p(iters_ptr or 0)))
+
+    def align_pairs_host(self, fixed_pts, fixed_off, moving_pts, moving_off, init_xyt, out=None):
+        """One call from host buffers (upload + align + download) -- the end-to-end path bench.py times."""
+        n = len(fixed_off) - 1
+        if out is None:
+            out = np.zeros(n, RESULT_DTYPE)
+        self._check(self._L.ls2d_align_pairs_host(self._h, _ptr(fixed_pts), _ptr(fixed_off), _ptr(moving_pts),
+                                                  _ptr(moving_off), _ptr(init_xyt), n, _ptr(out)))
+        return out
+
+    def score_batch(self, xyt, fixed_id=None, moving_id=None):
+        xyt = _f32(xyt).reshape(-1, 3)
+        fid, mid = _i32(fixed_id), _i32(moving_id)
+        out = np.zeros(len(xyt), RESULT_DTYPE)
+        self._check(self._L.ls2d_score_batch(self._h, _ptr(fid), _ptr(mid), _ptr(xyt), len(xyt), _ptr(out)))
+        return out
+
+    def score_batch_dev(self, fixed_id_ptr, moving_id_ptr, xyt_ptr: int, n_pairs: int, out_ptr: int):
+        self._check(self._L.ls2d_score_batch_dev(self._h, C.c_void_p(fixed_id_ptr or 0), C.c_void_p(moving_id_ptr or 0),
+                                                 C.c_void_p(xyt_ptr), n_pairs, C.c_void_p(out_ptr)))
+
+    # ---- finder / projector
+    def find_correspondences(self, fixed_id: int, moving_id: int, local_map_in_sensor_xyt):
+        xyt = _f32(local_map_in_sensor_xyt)
+        cols = self.params.canvas_cols
+        fi, mi = np.zeros(cols, np.int32), np.zeros(cols, np.int32)
+        n = C.c_int32(0)
+        self._check(self._L.ls2d_find_correspondences(self._h, fixed_id, moving_id, _ptr(xyt), _ptr(fi), _ptr(mi),
+                                                      C.byref(n)))
+        return fi[:n.value].copy(), mi[:n.value].copy()
+
+    def project(self, which: int, cloud_id: int, camera_pose_xyt):
+        xyt = _f32(camera_pose_xyt)
+        cols = self.params.canvas_cols
+        idx, depth = np.zeros(cols, np.int32), np.zeros(cols, np.float32)
+        self._check(self._L.ls2d_project(self._h, which, cloud_id, _ptr(xyt), _ptr(idx), _ptr(depth)))
+        return idx, depth
+
+    # ---- loop-closure verification
+    def verify(self, query_id: int, candidate_ids, guesses_xyt, gates: Gates, candidate_base: int = 0,
+               want_all: bool = False):
+        g = _f32(guesses_xyt)
+        n_cand, n_guess = g.shape[0], g.shape[1]
+        cand = _i32(candidate_ids)
+        best = np.zeros(1, BEST_DTYPE)
+        allr = np.zeros(n_cand * n_guess, RESULT_DTYPE) if want_all else None
+        self._check(self._L.ls2d_verify(self._h, query_id, _ptr(cand), n_cand, _ptr(g), n_guess, C.byref(gates),
+                                        candidate_base, _ptr(best), _ptr(allr)))
+        return (best[0], allr) if want_all else best[0]
+
+    def verify_dev(self, query_id: int, cand_ptr, n_cand: int, guesses_ptr: int, n_guess: int, gates: Gates,
+                   candidate_base: int, best_ptr: int, all_ptr: int | None = None):
+        self._check(self._L.ls2d_verify_dev(self._h, query_id, C.c_void_p(cand_ptr or 0), n_cand,
+                                            C.c_void_p(guesses_ptr), n_guess, C.byref(gates), candidate_base,
+                                            C.c_void_p(best_ptr), C.c_void_p(all_ptr or 0)))

@@ -1,0 +1,619 @@
+// ls2d_api.cu -- implementation of the C ABI declared in include/ls2d.h.
+// Host-side bookkeeping only: device buffers, parameter translation, kernel selection and launches.
+// There is deliberately no CPU implementation behind these entry points.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "ls2d_kernels.cuh"
+
+using namespace ls2d;
+
+namespace {
+
+struct cloud_set {
+  float4* pts     = nullptr;
+  int* off        = nullptr;
+  bool owned      = false;
+  size_t cap_pts  = 0;  // points
+  size_t cap_off  = 0;  // ints
+  int n_clouds    = 0;
+  int max_points  = 0;
+};
+
+struct scratch {
+  void* p    = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct ls2d_handle {
+  int device               = 0;
+  cudaStream_t own_stream  = nullptr;
+  cudaStream_t stream      = nullptr;
+  ls2d_params prm;
+  dev_params dp;
+  cloud_set sets[2];
+  scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc;
+  int64_t launches = 0;
+  int variant      = 0;  // LS2D_ICP_VARIANT: tuning knob for the 1081-point kernel shape
+  // NCCL, resolved lazily
+  void* nccl_lib                                                             = nullptr;
+  int (*nccl_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+};
+
+#define CU(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) {                                           \
+      set_last_cuda_error(e__, #call);                                  \
+      return LS2D_ERR_CUDA;                                             \
+    }                                                                   \
+  } while (0)
+
+namespace {
+
+thread_local char g_last_cuda[256] = "";
+
+void set_last_cuda_error(cudaError_t e, const char* what) {
+  snprintf(g_last_cuda, sizeof(g_last_cuda), "CUDA error: %s (%s)", cudaGetErrorString(e), what);
+}
+
+int reserve(scratch& s, size_t bytes) {
+  if (bytes <= s.cap) return LS2D_OK;
+  if (s.p) cudaFree(s.p);
+  s.p   = nullptr;
+  s.cap = 0;
+  const size_t want = bytes + bytes / 4 + 256;
+  CU(cudaMalloc(&s.p, want));
+  s.cap = want;
+  return LS2D_OK;
+}
+
+void release(scratch& s) {
+  if (s.p) cudaFree(s.p);
+  s.p   = nullptr;
+  s.cap = 0;
+}
+
+void release(cloud_set& c) {
+  if (c.owned) {
+    if (c.pts) cudaFree(c.pts);
+    if (c.off) cudaFree(c.off);
+  }
+  c = cloud_set();
+}
+
+bool params_valid(const ls2d_params& p) {
+  if (p.canvas_cols < 1 || p.canvas_cols > 7680) return false;
+  if (!(p.angle_col_max > p.angle_col_min)) return false;
+  if (!(p.range_max > p.range_min)) return false;
+  if (p.max_iterations < 0 || p.max_iterations > 100000) return false;
+  return true;
+}
+
+dev_params translate(const ls2d_params& p) {
+  dev_params d;
+  d.cam                     = make_polar_cam(p.canvas_cols, p.angle_col_min, p.angle_col_max);
+  d.range_min               = p.range_min;
+  d.range_max               = p.range_max;
+  d.point_distance          = p.point_distance;
+  d.normal_cos              = p.normal_cos;
+  d.tau                     = p.cauchy_chi_threshold;
+  d.inv_tau                 = p.cauchy_chi_threshold > 0.f ? 1.f / p.cauchy_chi_threshold : 0.f;
+  d.damping                 = p.damping;
+  d.max_iterations          = p.max_iterations;
+  d.min_num_correspondences = p.min_num_correspondences;
+  d.min_num_inliers         = p.min_num_inliers;
+  d.with_sensor             = p.with_sensor;
+  d.Sinv                    = iso_identity();
+  if (p.with_sensor)
+    d.Sinv = iso_inverse(iso_v2t(p.sensor_in_robot[0], p.sensor_in_robot[1], p.sensor_in_robot[2]));
+  return d;
+}
+
+// ---- kernel table: (threads, points per thread) by cloud size -------------------------------------
+struct shape {
+  int threads, ppt;
+};
+
+shape pick_shape(int max_points, int variant) {
+  if (max_points <= 256) return {128, 2};
+  if (max_points <= 512) return {128, 4};
+  if (max_points <= 768) return {256, 3};
+  if (max_points <= 1152) {
+    switch (variant) {
+      case 1: return {128, 9};
+      case 2: return {192, 6};
+      case 3: return {256, 5};
+      default: return {384, 3};
+    }
+  }
+  if (max_points <= 1536) return {256, 6};
+  if (max_points <= 2048) return {256, 8};
+  if (max_points <= 4096) return {512, 8};
+  return {0, 0};
+}
+
+template <int T, int PPT>
+int launch_icp_t(ls2d_handle* h, const align_args& a) {
+  const size_t smem = icp_smem_bytes(h->dp.cam.cols, T);
+  if (h->dp.with_sensor) {
+    CU(cudaFuncSetAttribute(icp_fused_kernel<T, PPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int) smem));
+    icp_fused_kernel<T, PPT, true><<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
+  } else {
+    CU(cudaFuncSetAttribute(icp_fused_kernel<T, PPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int) smem));
+    icp_fused_kernel<T, PPT, false><<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
+  }
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_icp(ls2d_handle* h, const align_args& a) {
+  if (a.n_pairs <= 0) return LS2D_OK;
+  const int maxp = h->sets[0].max_points > h->sets[1].max_points ? h->sets[0].max_points
+                                                                  : h->sets[1].max_points;
+  const shape s = pick_shape(maxp, h->variant);
+#define LS2D_CASE(T, P) \
+  if (s.threads == T && s.ppt == P) return launch_icp_t<T, P>(h, a);
+  LS2D_CASE(128, 2)
+  LS2D_CASE(128, 4)
+  LS2D_CASE(256, 3)
+  LS2D_CASE(384, 3)
+  LS2D_CASE(128, 9)
+  LS2D_CASE(192, 6)
+  LS2D_CASE(256, 5)
+  LS2D_CASE(256, 6)
+  LS2D_CASE(256, 8)
+  LS2D_CASE(512, 8)
+#undef LS2D_CASE
+  return LS2D_ERR_UNSUPPORTED;
+}
+
+bool ready(const ls2d_handle* h) { return h->sets[0].pts && h->sets[1].pts && h->sets[0].off && h->sets[1].off; }
+
+int h2d(ls2d_handle* h, scratch& s, const void* src, size_t bytes) {
+  int rc = reserve(s, bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(s.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return LS2D_OK;
+}
+
+align_args base_args(const ls2d_handle* h) {
+  align_args a;
+  memset(&a, 0, sizeof(a));
+  a.fixed_pts   = h->sets[0].pts;
+  a.fixed_off   = h->sets[0].off;
+  a.moving_pts  = h->sets[1].pts;
+  a.moving_off  = h->sets[1].off;
+  a.moving_div  = 1;
+  a.fixed_const = -1;
+  return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ls2d_version(void) { return LS2D_VERSION; }
+
+const char* ls2d_strerror(int err) {
+  switch (err) {
+    case LS2D_OK: return "ok";
+    case LS2D_ERR_INVALID: return "invalid argument";
+    case LS2D_ERR_CUDA: return g_last_cuda[0] ? g_last_cuda : "CUDA error";
+    case LS2D_ERR_NOT_READY: return "clouds or parameters not set";
+    case LS2D_ERR_UNSUPPORTED: return "size outside the compiled kernel table";
+    case LS2D_ERR_NCCL: return "NCCL error";
+    default: return "unknown error";
+  }
+}
+
+void ls2d_default_params(ls2d_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->canvas_cols             = 721;
+  p->angle_col_min           = -3.14159f;
+  p->angle_col_max           = 3.14159f;
+  p->range_min               = 0.3f;
+  p->range_max               = 20.f;
+  p->point_distance          = 0.5f;
+  p->normal_cos              = 0.8f;
+  p->cauchy_chi_threshold    = 0.01f;
+  p->damping                 = 0.f;
+  p->max_iterations          = 10;
+  p->min_num_correspondences = 0;
+  p->min_num_inliers         = 10;
+  p->with_sensor             = 0;
+}
+
+int ls2d_create(ls2d_handle** out, int device) {
+  if (!out) return LS2D_ERR_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  CU(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(device));
+  ls2d_handle* h = new (std::nothrow) ls2d_handle();
+  if (!h) return LS2D_ERR_INVALID;
+  h->device = device;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return LS2D_ERR_CUDA;
+  }
+  h->stream = h->own_stream;
+  ls2d_default_params(&h->prm);
+  h->dp = translate(h->prm);
+  if (const char* v = getenv("LS2D_ICP_VARIANT")) h->variant = atoi(v);
+  *out = h;
+  return LS2D_OK;
+}
+
+int ls2d_destroy(ls2d_handle* h) {
+  if (!h) return LS2D_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  release(h->sets[0]);
+  release(h->sets[1]);
+  release(h->d_fid);
+  release(h->d_mid);
+  release(h->d_init);
+  release(h->d_out);
+  release(h->d_iters);
+  release(h->d_best);
+  release(h->d_misc);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->nccl_lib) dlclose(h->nccl_lib);
+  delete h;
+  return LS2D_OK;
+}
+
+int ls2d_set_stream(ls2d_handle* h, void* s) {
+  if (!h) return LS2D_ERR_INVALID;
+  h->stream = s ? (cudaStream_t) s : h->own_stream;
+  return LS2D_OK;
+}
+
+int ls2d_sync(ls2d_handle* h) {
+  if (!h) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
+}
+
+int ls2d_set_params(ls2d_handle* h, const ls2d_params* p) {
+  if (!h || !p || !params_valid(*p)) return LS2D_ERR_INVALID;
+  h->prm = *p;
+  h->dp  = translate(*p);
+  return LS2D_OK;
+}
+
+int ls2d_get_params(const ls2d_handle* h, ls2d_params* p) {
+  if (!h || !p) return LS2D_ERR_INVALID;
+  *p = h->prm;
+  return LS2D_OK;
+}
+
+int ls2d_upload_clouds(ls2d_handle* h, int which, const float* pts, const int32_t* off, int32_t n_clouds) {
+  if (!h || (which != 0 && which != 1) || !off || n_clouds < 0 || (!pts && n_clouds > 0 && off[n_clouds] > 0))
+    return LS2D_ERR_INVALID;
+  if (off[0] != 0) return LS2D_ERR_INVALID;
+  int maxp = 0;
+  for (int i = 0; i < n_clouds; ++i) {
+    const int n = off[i + 1] - off[i];
+    if (n < 0) return LS2D_ERR_INVALID;
+    if (n > maxp) maxp = n;
+  }
+  CU(cudaSetDevice(h->device));
+  cloud_set& c = h->sets[which];
+  if (!c.owned) c = cloud_set();
+  c.owned              = true;
+  const size_t total   = (size_t) off[n_clouds];
+  const size_t n_off   = (size_t) n_clouds + 1;
+  if (total > c.cap_pts || !c.pts) {
+    if (c.pts) cudaFree(c.pts);
+    c.pts     = nullptr;
+    c.cap_pts = 0;
+    CU(cudaMalloc((void**) &c.pts, (total + total / 8 + 16) * sizeof(float4)));
+    c.cap_pts = total + total / 8 + 16;
+  }
+  if (n_off > c.cap_off || !c.off) {
+    if (c.off) cudaFree(c.off);
+    c.off     = nullptr;
+    c.cap_off = 0;
+    CU(cudaMalloc((void**) &c.off, (n_off + n_off / 8 + 16) * sizeof(int)));
+    c.cap_off = n_off + n_off / 8 + 16;
+  }
+  if (total) CU(cudaMemcpyAsync(c.pts, pts, total * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(c.off, off, n_off * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  c.n_clouds   = n_clouds;
+  c.max_points = maxp;
+  return LS2D_OK;
+}
+
+int ls2d_set_clouds_dev(ls2d_handle* h, int which, const void* pts_dev, const int32_t* off_dev,
+                        int32_t n_clouds, int32_t max_points) {
+  if (!h || (which != 0 && which != 1) || !pts_dev || !off_dev || n_clouds < 0 || max_points < 0)
+    return LS2D_ERR_INVALID;
+  if (((uintptr_t) pts_dev) & 15) return LS2D_ERR_INVALID;
+  release(h->sets[which]);
+  cloud_set& c = h->sets[which];
+  c.pts        = (float4*) pts_dev;
+  c.off        = (int*) off_dev;
+  c.owned      = false;
+  c.n_clouds   = n_clouds;
+  c.max_points = max_points;
+  return LS2D_OK;
+}
+
+static int align_dev_impl(ls2d_handle* h, const int32_t* fid, const int32_t* mid, const float* init,
+                          int32_t n_pairs, ls2d_result* out, ls2d_iter_stats* iters, int score_only) {
+  if (!h || !init || !out || n_pairs < 0) return LS2D_ERR_INVALID;
+  if (!ready(h)) return LS2D_ERR_NOT_READY;
+  CU(cudaSetDevice(h->device));
+  align_args a = base_args(h);
+  a.fixed_id   = fid;
+  a.moving_id  = mid;
+  a.init_xyt   = init;
+  a.out        = out;
+  a.iters      = iters;
+  a.n_pairs    = n_pairs;
+  a.score_only = score_only;
+  return launch_icp(h, a);
+}
+
+static int check_ids(const ls2d_handle* h, const int32_t* fid, const int32_t* mid, int32_t n) {
+  for (int i = 0; i < n; ++i) {
+    const int f = fid ? fid[i] : i, m = mid ? mid[i] : i;
+    if (f < 0 || f >= h->sets[0].n_clouds || m < 0 || m >= h->sets[1].n_clouds) return LS2D_ERR_INVALID;
+  }
+  return LS2D_OK;
+}
+
+static int align_host_impl(ls2d_handle* h, const int32_t* fid, const int32_t* mid, const float* init,
+                           int32_t n_pairs, ls2d_result* out, ls2d_iter_stats* iters, int score_only) {
+  if (!h || !init || !out || n_pairs < 0) return LS2D_ERR_INVALID;
+  if (!ready(h)) return LS2D_ERR_NOT_READY;
+  if (n_pairs == 0) return LS2D_OK;
+  int rc = check_ids(h, fid, mid, n_pairs);
+  if (rc) return rc;
+  CU(cudaSetDevice(h->device));
+  if (fid && (rc = h2d(h, h->d_fid, fid, sizeof(int) * (size_t) n_pairs))) return rc;
+  if (mid && (rc = h2d(h, h->d_mid, mid, sizeof(int) * (size_t) n_pairs))) return rc;
+  if ((rc = h2d(h, h->d_init, init, sizeof(float) * 3 * (size_t) n_pairs))) return rc;
+  if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) n_pairs))) return rc;
+  const size_t iter_bytes = sizeof(ls2d_iter_stats) * (size_t) n_pairs * (size_t) h->prm.max_iterations;
+  if (iters && iter_bytes) {
+    if ((rc = reserve(h->d_iters, iter_bytes))) return rc;
+    CU(cudaMemsetAsync(h->d_iters.p, 0, iter_bytes, h->stream));
+  }
+  rc = align_dev_impl(h, fid ? (const int*) h->d_fid.p : nullptr, mid ? (const int*) h->d_mid.p : nullptr,
+                      (const float*) h->d_init.p, n_pairs, (ls2d_result*) h->d_out.p,
+                      (iters && iter_bytes) ? (ls2d_iter_stats*) h->d_iters.p : nullptr, score_only);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, h->d_out.p, sizeof(ls2d_result) * (size_t) n_pairs, cudaMemcpyDeviceToHost, h->stream));
+  if (iters && iter_bytes) CU(cudaMemcpyAsync(iters, h->d_iters.p, iter_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
+}
+
+int ls2d_align_batch(ls2d_handle* h, const int32_t* fid, const int32_t* mid, const float* init,
+                     int32_t n_pairs, ls2d_result* out, ls2d_iter_stats* iters) {
+  return align_host_impl(h, fid, mid, init, n_pairs, out, iters, 0);
+}
+
+int ls2d_align_batch_dev(ls2d_handle* h, const int32_t* fid, const int32_t* mid, const float* init,
+                         int32_t n_pairs, ls2d_result* out, ls2d_iter_stats* iters) {
+  return align_dev_impl(h, fid, mid, init, n_pairs, out, iters, 0);
+}
+
+int ls2d_score_batch(ls2d_handle* h, const int32_t* fid, const int32_t* mid, const float* xyt,
+                     int32_t n_pairs, ls2d_result* out) {
+  return align_host_impl(h, fid, mid, xyt, n_pairs, out, nullptr, 1);
+}
+
+int ls2d_score_batch_dev(ls2d_handle* h, const int32_t* fid, const int32_t* mid, const float* xyt,
+                         int32_t n_pairs, ls2d_result* out) {
+  return align_dev_impl(h, fid, mid, xyt, n_pairs, out, nullptr, 1);
+}
+
+int ls2d_align_pairs_host(ls2d_handle* h, const float* fpts, const int32_t* foff, const float* mpts,
+                          const int32_t* moff, const float* init, int32_t n_pairs, ls2d_result* out) {
+  int rc;
+  if ((rc = ls2d_upload_clouds(h, LS2D_FIXED, fpts, foff, n_pairs))) return rc;
+  if ((rc = ls2d_upload_clouds(h, LS2D_MOVING, mpts, moff, n_pairs))) return rc;
+  return align_host_impl(h, nullptr, nullptr, init, n_pairs, out, nullptr, 0);
+}
+
+int ls2d_find_correspondences(ls2d_handle* h, int32_t fixed_id, int32_t moving_id, const float* xyt,
+                              int32_t* fixed_idx, int32_t* moving_idx, int32_t* n_out) {
+  if (!h || !xyt || !fixed_idx || !moving_idx || !n_out) return LS2D_ERR_INVALID;
+  if (!ready(h)) return LS2D_ERR_NOT_READY;
+  if (fixed_id < 0 || fixed_id >= h->sets[0].n_clouds || moving_id < 0 || moving_id >= h->sets[1].n_clouds)
+    return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  const int C = h->dp.cam.cols;
+  int rc      = reserve(h->d_misc, sizeof(int) * (2 * (size_t) C + 1));
+  if (rc) return rc;
+  correspond_args a;
+  a.fixed_pts    = h->sets[0].pts;
+  a.fixed_off    = h->sets[0].off;
+  a.moving_pts   = h->sets[1].pts;
+  a.moving_off   = h->sets[1].off;
+  a.fixed_cloud  = fixed_id;
+  a.moving_cloud = moving_id;
+  memcpy(a.lmis_xyt, xyt, sizeof(float) * 3);
+  a.fixed_idx  = (int*) h->d_misc.p;
+  a.moving_idx = a.fixed_idx + C;
+  a.count      = a.moving_idx + C;
+  const size_t smem = sizeof(unsigned) * 4 * (size_t) C;
+  CU(cudaFuncSetAttribute(correspond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  correspond_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  int n = 0;
+  CU(cudaMemcpyAsync(&n, a.count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (n < 0 || n > C) return LS2D_ERR_CUDA;
+  if (n) {
+    CU(cudaMemcpyAsync(fixed_idx, a.fixed_idx, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(moving_idx, a.moving_idx, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  *n_out = n;
+  return LS2D_OK;
+}
+
+int ls2d_project(ls2d_handle* h, int which, int32_t cloud_id, const float* cam_xyt, int32_t* source_idx,
+                 float* depth) {
+  if (!h || (which != 0 && which != 1) || !cam_xyt || !source_idx || !depth) return LS2D_ERR_INVALID;
+  const cloud_set& c = h->sets[which];
+  if (!c.pts || !c.off) return LS2D_ERR_NOT_READY;
+  if (cloud_id < 0 || cloud_id >= c.n_clouds) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  const int C = h->dp.cam.cols;
+  int rc      = reserve(h->d_misc, sizeof(int) * (2 * (size_t) C + 1));
+  if (rc) return rc;
+  project_args a;
+  a.pts   = c.pts;
+  a.off   = c.off;
+  a.cloud = cloud_id;
+  memcpy(a.cam_xyt, cam_xyt, sizeof(float) * 3);
+  a.source_idx = (int*) h->d_misc.p;
+  a.depth      = (float*) (a.source_idx + C);
+  const size_t smem = sizeof(unsigned) * 2 * (size_t) C;
+  CU(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  project_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  CU(cudaMemcpyAsync(source_idx, a.source_idx, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(depth, a.depth, sizeof(float) * C, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
+}
+
+int ls2d_verify_dev(ls2d_handle* h, int32_t query_id, const int32_t* cand_dev, int32_t n_cand,
+                    const float* guesses_dev, int32_t n_guess, const ls2d_gates* gates, int32_t cand_base,
+                    ls2d_best* best_dev, ls2d_result* all_dev) {
+  if (!h || !guesses_dev || !gates || !best_dev || n_cand < 0 || n_guess < 1) return LS2D_ERR_INVALID;
+  if (!ready(h)) return LS2D_ERR_NOT_READY;
+  if (query_id < 0 || query_id >= h->sets[0].n_clouds) return LS2D_ERR_INVALID;
+  if ((int64_t) n_cand * n_guess > 0x7fffffff) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  const int n = n_cand * n_guess;
+  int rc;
+  if (!all_dev) {
+    if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) (n > 0 ? n : 1)))) return rc;
+    all_dev = (ls2d_result*) h->d_out.p;
+  }
+  align_args a  = base_args(h);
+  a.fixed_const = query_id;
+  a.moving_id   = cand_dev;
+  a.moving_div  = n_guess;
+  a.init_xyt    = guesses_dev;
+  a.out         = all_dev;
+  a.n_pairs     = n;
+  if ((rc = launch_icp(h, a))) return rc;
+  best_of_kernel<<<1, 1024, 0, h->stream>>>(all_dev, n, n_guess, *gates, cand_base, best_dev);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int ls2d_verify(ls2d_handle* h, int32_t query_id, const int32_t* cand, int32_t n_cand, const float* guesses,
+                int32_t n_guess, const ls2d_gates* gates, int32_t cand_base, ls2d_best* best,
+                ls2d_result* all) {
+  if (!h || !guesses || !gates || !best || n_cand < 0 || n_guess < 1) return LS2D_ERR_INVALID;
+  if (!ready(h)) return LS2D_ERR_NOT_READY;
+  if ((int64_t) n_cand * n_guess > 0x7fffffff) return LS2D_ERR_INVALID;
+  if (cand)
+    for (int i = 0; i < n_cand; ++i)
+      if (cand[i] < 0 || cand[i] >= h->sets[1].n_clouds) return LS2D_ERR_INVALID;
+  if (!cand && n_cand > h->sets[1].n_clouds) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  const size_t n = (size_t) n_cand * n_guess;
+  int rc;
+  if (cand && n_cand && (rc = h2d(h, h->d_mid, cand, sizeof(int) * (size_t) n_cand))) return rc;
+  if ((rc = h2d(h, h->d_init, guesses, sizeof(float) * 3 * (n ? n : 1)))) return rc;
+  if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (n ? n : 1)))) return rc;
+  if ((rc = reserve(h->d_best, sizeof(ls2d_best)))) return rc;
+  rc = ls2d_verify_dev(h, query_id, cand ? (const int*) h->d_mid.p : nullptr, n_cand, (const float*) h->d_init.p,
+                       n_guess, gates, cand_base, (ls2d_best*) h->d_best.p, (ls2d_result*) h->d_out.p);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(best, h->d_best.p, sizeof(ls2d_best), cudaMemcpyDeviceToHost, h->stream));
+  if (all && n) CU(cudaMemcpyAsync(all, h->d_out.p, sizeof(ls2d_result) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
+}
+
+int ls2d_reduce_best(const ls2d_best* rec, int32_t n, ls2d_best* out) {
+  if (!rec || !out || n < 0) return LS2D_ERR_INVALID;
+  ls2d_best b;
+  memset(&b, 0, sizeof(b));
+  b.candidate = -1;
+  b.guess     = -1;
+  for (int i = 0; i < n; ++i) {
+    const ls2d_best& r = rec[i];
+    if (r.candidate < 0 || r.n_inliers <= 0) continue;
+    if (b.candidate < 0) {
+      b = r;
+      continue;
+    }
+    const float cr = r.chi_inliers / (float) r.n_inliers, cb = b.chi_inliers / (float) b.n_inliers;
+    bool take      = false;
+    if (r.n_inliers != b.n_inliers)
+      take = r.n_inliers > b.n_inliers;
+    else if (cr != cb)
+      take = cr < cb;
+    else if (r.candidate != b.candidate)
+      take = r.candidate < b.candidate;
+    else
+      take = r.guess < b.guess;
+    if (take) b = r;
+  }
+  *out = b;
+  return LS2D_OK;
+}
+
+int ls2d_verify_sharded_nccl(ls2d_handle* h, int32_t query_id, const int32_t* cand_dev, int32_t n_cand,
+                             const float* guesses_dev, int32_t n_guess, const ls2d_gates* gates,
+                             int32_t cand_base, void* comm, int32_t n_ranks, ls2d_best* best) {
+  if (!h || !comm || !best || n_ranks < 1) return LS2D_ERR_INVALID;
+  if (!h->nccl_all_gather) {
+    h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h->nccl_lib) h->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h->nccl_lib) return LS2D_ERR_NCCL;
+    h->nccl_all_gather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t)) dlsym(h->nccl_lib, "ncclAllGather");
+    if (!h->nccl_all_gather) return LS2D_ERR_NCCL;
+  }
+  int rc;
+  if ((rc = reserve(h->d_best, sizeof(ls2d_best) * (size_t) (n_ranks + 1)))) return rc;
+  ls2d_best* mine   = (ls2d_best*) h->d_best.p;
+  ls2d_best* gather = mine + 1;
+  if ((rc = ls2d_verify_dev(h, query_id, cand_dev, n_cand, guesses_dev, n_guess, gates, cand_base, mine, nullptr)))
+    return rc;
+  if (h->nccl_all_gather(mine, gather, sizeof(ls2d_best), /*ncclInt8*/ 0, comm, h->stream) != 0) return LS2D_ERR_NCCL;
+  std::vector<ls2d_best> host((size_t) n_ranks);
+  CU(cudaMemcpyAsync(host.data(), gather, sizeof(ls2d_best) * (size_t) n_ranks, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return ls2d_reduce_best(host.data(), n_ranks, best);
+}
+
+int ls2d_reduction_threads(int32_t max_points) {
+  int variant = 0;
+  if (const char* v = getenv("LS2D_ICP_VARIANT")) variant = atoi(v);
+  return pick_shape(max_points, variant).threads;
+}
+
+int64_t ls2d_launch_count(const ls2d_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,573 @@
+// ls2d_kernels.cuh -- sm_100a kernels of the projective 2D registration path.
+//
+//  icp_fused_kernel   one CTA per scan pair; the whole MultiAligner2D::compute() loop on chip:
+//                     fixed range image built once in shared memory, the moving cloud lives in
+//                     REGISTERS for all iterations (owner-computes: the thread that owns a moving point
+//                     projects it, fights for its column with two 32-bit shared-memory atomicMin passes,
+//                     and -- if it won -- evaluates the correspondence itself), 11 sums + 2 counts reduced
+//                     by a recursive-halving warp shuffle + one shared-memory stage, 3x3 solve and SE(2)
+//                     update by thread 0.  HBM traffic = the compulsory bytes (each cloud read once,
+//                     64 B written).
+//  project_kernel     PointNormal2fProjectorPolar::compute for the drop-in projector API / parity.
+//  correspond_kernel  CorrespondenceFinderProjective2f::compute for the drop-in finder API / parity.
+//  best_of_kernel     acceptance gates + deterministic arg-best of a verification shard.
+//
+// Reference paths: R/ = /root/reference/srrg2_laser_slam_2d/src/srrg2_laser_slam_2d/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <float.h>
+
+#include "../../include/ls2d.h"
+#include "ls2d_math.cuh"
+
+namespace ls2d {
+
+struct dev_params {
+  polar_cam cam;
+  float range_min, range_max;
+  float point_distance, normal_cos;
+  float tau, inv_tau;  // Cauchy threshold (<= 0: none) and 1/tau
+  float damping;
+  int max_iterations, min_num_correspondences, min_num_inliers;
+  int with_sensor;
+  iso Sinv;  // sensor_in_robot^-1
+};
+
+struct align_args {
+  const float4* fixed_pts;
+  const int* fixed_off;
+  const float4* moving_pts;
+  const int* moving_off;
+  const int* fixed_id;   // nullable: pair index
+  const int* moving_id;  // nullable: pair index
+  int moving_div;        // moving_id == nullptr: moving cloud = pair / moving_div (verification: guesses)
+  int fixed_const;       // >= 0: every pair uses this fixed cloud (verification: the query)
+  const float* init_xyt;
+  ls2d_result* out;
+  ls2d_iter_stats* iters;  // nullable
+  int n_pairs;
+  int score_only;  // 1: one linearisation, no update
+};
+
+constexpr unsigned Z_EMPTY_DEPTH = 0xFFFFFFFFu;
+constexpr unsigned Z_EMPTY_IDX   = 0x7FFFFFFFu;
+constexpr int NSUM               = 11;  // H00 H01 H02 H11 H12 H22 b0 b1 b2 chi_inliers chi_kernelized
+constexpr int RED_STRIDE         = 12;  // + packed counts
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ---------------------------------------------------------------------------------------------------
+// recursive-halving warp reduction of 11 floats: the value of slot s ends up on lane 2*s.  Every slot is
+// summed along the xor-butterfly tree (offsets 16, 8, 4, 2, 1), so the result is the one a full butterfly
+// gives (binary32 addition is commutative) at 16 shuffles instead of 55.
+__device__ __forceinline__ float warp_reduce_slots(float (&v)[16], int lane) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool up    = lane & 16;
+    const float send = up ? v[k] : v[k + 8];
+    const float keep = up ? v[k + 8] : v[k];
+    v[k]             = fadd(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool up    = lane & 8;
+    const float send = up ? v[k] : v[k + 4];
+    const float keep = up ? v[k + 4] : v[k];
+    v[k]             = fadd(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool up    = lane & 4;
+    const float send = up ? v[k] : v[k + 2];
+    const float keep = up ? v[k + 2] : v[k];
+    v[k]             = fadd(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+  {
+    const bool up    = lane & 2;
+    const float send = up ? v[0] : v[1];
+    const float keep = up ? v[1] : v[0];
+    v[0]             = fadd(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+  }
+  v[0] = fadd(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1));
+  return v[0];
+}
+
+// 3x3 Cholesky in binary64, operation order of oracle/ls2d_oracle.c solve3() (decision D11)
+__device__ __forceinline__ bool solve3(const float* v, float damping, float* dx) {
+  const double H00 = dadd((double) v[0], (double) damping), H01 = v[1], H02 = v[2];
+  const double H11 = dadd((double) v[3], (double) damping), H12 = v[4];
+  const double H22 = dadd((double) v[5], (double) damping);
+  const double r0 = -(double) v[6], r1 = -(double) v[7], r2 = -(double) v[8];
+  if (!(H00 > 0.0)) return false;
+  const double l00 = dsqrt(H00), i00 = ddiv(1.0, l00);
+  const double l10 = dmul(H01, i00), l20 = dmul(H02, i00);
+  const double t11 = dsub(H11, dmul(l10, l10));
+  if (!(t11 > 0.0)) return false;
+  const double l11 = dsqrt(t11), i11 = ddiv(1.0, l11);
+  const double l21 = dmul(dsub(H12, dmul(l20, l10)), i11);
+  const double t22 = dsub(dsub(H22, dmul(l20, l20)), dmul(l21, l21));
+  if (!(t22 > 0.0)) return false;
+  const double l22 = dsqrt(t22), i22 = ddiv(1.0, l22);
+  const double y0 = dmul(r0, i00);
+  const double y1 = dmul(dsub(r1, dmul(l10, y0)), i11);
+  const double y2 = dmul(dsub(dsub(r2, dmul(l20, y0)), dmul(l21, y1)), i22);
+  const double x2 = dmul(y2, i22);
+  const double x1 = dmul(dsub(y1, dmul(l21, x2)), i11);
+  const double x0 = dmul(dsub(dsub(y0, dmul(l10, x1)), dmul(l20, x2)), i00);
+  dx[0]           = (float) x0;
+  dx[1]           = (float) x1;
+  dx[2]           = (float) x2;
+  return isfinite(dx[0]) && isfinite(dx[1]) && isfinite(dx[2]);
+}
+
+// pose block broadcast through shared memory once per iteration
+struct pose_bc {
+  float Xtx, Xty, Xc, Xs;  // estimate X = moving_in_fixed
+  float Lc, Ls;            // rotation of local_map_in_sensor (= X, or Sinv * X)
+  float Wtx, Wty;          // translation of inverse(inverse(local_map_in_sensor))  (decision D13)
+  int stop;
+};
+
+__device__ __forceinline__ void publish_pose(pose_bc* bc, const dev_params& P, const iso& X,
+                                             bool with_sensor, int stop) {
+  const iso L = with_sensor ? iso_compose(P.Sinv, X) : X;
+  const iso W = iso_inverse(iso_inverse(L));
+  bc->Xtx = X.tx, bc->Xty = X.ty, bc->Xc = X.c, bc->Xs = X.s;
+  bc->Lc = W.c, bc->Ls = W.s;
+  bc->Wtx = W.tx, bc->Wty = W.ty;
+  bc->stop = stop;
+}
+
+constexpr size_t icp_smem_bytes(int cols, int threads) {
+  return (size_t) cols * (16 + 4 + 4 + 4) + (size_t)(threads / 32) * RED_STRIDE * 4 + sizeof(pose_bc) + 16;
+}
+
+template <int T, int PPT, bool SENSOR>
+__global__ void __launch_bounds__(T) icp_fused_kernel(const dev_params P, const align_args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C      = P.cam.cols;
+  float4* fimg     = reinterpret_cast<float4*>(smem_raw);           // fixed image: x y nx ny per column
+  float* fdepth    = reinterpret_cast<float*>(fimg + C);            // fixed image: rho, < 0 = empty
+  unsigned* zdepth = reinterpret_cast<unsigned*>(fdepth + C);       // z-buffer pass 1: min rho bits
+  unsigned* zidx   = zdepth + C;                                    // z-buffer pass 2: min index among ties
+  float* red       = reinterpret_cast<float*>(zidx + C);            // [T/32][RED_STRIDE]
+  pose_bc* bc      = reinterpret_cast<pose_bc*>(red + (T / 32) * RED_STRIDE);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = blockIdx.x;
+  const int fcl  = A.fixed_const >= 0 ? A.fixed_const : (A.fixed_id ? A.fixed_id[pair] : pair);
+  const int mcl  = A.moving_id ? A.moving_id[pair / A.moving_div] : pair / A.moving_div;
+  const int f0 = A.fixed_off[fcl], nf = A.fixed_off[fcl + 1] - f0;
+  const int m0 = A.moving_off[mcl], nm = A.moving_off[mcl + 1] - m0;
+
+  for (int k = tid; k < C; k += T) {
+    fdepth[k] = -1.f;
+    zdepth[k] = Z_EMPTY_DEPTH;
+    zidx[k]   = Z_EMPTY_IDX;
+  }
+  // moving cloud -> registers (issued early; consumed after the fixed image is built)
+  float4 mp[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int i = tid + j * T;
+    mp[j]       = i < nm ? ldg4(A.moving_pts + m0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid == 0) {
+    const iso X = iso_v2t(A.init_xyt[3 * pair], A.init_xyt[3 * pair + 1], A.init_xyt[3 * pair + 2]);
+    publish_pose(bc, P, X, SENSOR, 0);
+  }
+  __syncthreads();
+
+  // ---- fixed range image: identity camera (R/registration/correspondence_finder_projective_2d.cpp:37-44)
+  {
+    float4 fp[PPT];
+    int col[PPT];
+    unsigned rb[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      const int i = tid + j * T;
+      col[j]      = -1;
+      rb[j]       = 0;
+      if (i < nf) {
+        fp[j]           = ldg4(A.fixed_pts + f0 + i);
+        const float rho = fsqrt(fadd(fmul(fp[j].x, fp[j].x), fmul(fp[j].y, fp[j].y)));
+        if (!(rho < P.range_min || rho > P.range_max)) {
+          col[j] = polar_column(P.cam, fp[j].y, fp[j].x);
+          rb[j]  = f2u(rho);
+          if (col[j] >= 0) atomicMin(&zdepth[col[j]], rb[j]);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+      if (col[j] >= 0 && zdepth[col[j]] == rb[j]) atomicMin(&zidx[col[j]], (unsigned) (tid + j * T));
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+      if (col[j] >= 0 && zidx[col[j]] == (unsigned) (tid + j * T)) {
+        fimg[col[j]]   = fp[j];
+        fdepth[col[j]] = u2f(rb[j]);
+        zdepth[col[j]] = Z_EMPTY_DEPTH;
+        zidx[col[j]]   = Z_EMPTY_IDX;
+      }
+    __syncthreads();
+  }
+
+  // ---- ICP loop (MultiAligner2D::compute; L0.json:487-517)
+  const int max_it = A.score_only ? 1 : P.max_iterations;
+  int it           = 0;
+  int status       = -1;
+  float tot        = 0.f;  // lane s of warp 0: total of slot s for the last linearisation
+  unsigned tot_cnt = 0;
+  for (; it < max_it; ++it) {
+    const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
+    int col[PPT];
+    unsigned rb[PPT];
+    // phase 1: project the moving cloud (camera = local_map_in_sensor^-1, .cpp:47-48), z-buffer pass 1
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      col[j] = -1;
+      rb[j]  = 0;
+      if (tid + j * T < nm) {
+        const float rx  = fadd(fmul(Lc, mp[j].x), fmul(-Ls, mp[j].y));
+        const float ry  = fadd(fmul(Ls, mp[j].x), fmul(Lc, mp[j].y));
+        const float px  = fadd(rx, Wtx);
+        const float py  = fadd(ry, Wty);
+        const float rho = fsqrt(fadd(fmul(px, px), fmul(py, py)));
+        if (!(rho < P.range_min || rho > P.range_max)) {
+          col[j] = polar_column(P.cam, py, px);
+          rb[j]  = f2u(rho);
+          if (col[j] >= 0) atomicMin(&zdepth[col[j]], rb[j]);
+        }
+      }
+    }
+    __syncthreads();
+    // z-buffer pass 2: lowest index among equal depths (first in iteration order wins, decision D3)
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+      if (col[j] >= 0 && zdepth[col[j]] == rb[j]) atomicMin(&zidx[col[j]], (unsigned) (tid + j * T));
+    __syncthreads();
+    // phase 2: winners gate against the fixed column (.cpp:61-73) and linearise their correspondence
+    float acc[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) acc[s] = 0.f;
+    unsigned cnt = 0;  // n_inliers | n_kernelized << 16
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      if (col[j] < 0 || zidx[col[j]] != (unsigned) (tid + j * T)) continue;
+      const int c = col[j];
+      zdepth[c]   = Z_EMPTY_DEPTH;  // the winner hands the cell back for the next iteration
+      zidx[c]     = Z_EMPTY_IDX;
+      const float fd = fdepth[c];
+      if (fd < 0.f) continue;  // fcell.source_idx < 0
+      const float rho = u2f(rb[j]);
+      if (fabsf(fsub(fd, rho)) > P.point_distance) continue;
+      const float4 F = fimg[c];
+      const float4 M = mp[j];
+      const float nx = fadd(fmul(Lc, M.z), fmul(-Ls, M.w));  // transformed normal
+      const float ny = fadd(fmul(Ls, M.z), fmul(Lc, M.w));
+      if (fadd(fmul(nx, F.z), fmul(ny, F.w)) < P.normal_cos) continue;
+      // SE2Plane2PlaneErrorFactor (R/registration/aligner_slice_processor_laser_2d.h:8,23)
+      float px, py;
+      if (SENSOR) {
+        const float qx = fadd(fadd(fmul(bc->Xc, M.x), fmul(-bc->Xs, M.y)), Xtx);
+        const float qy = fadd(fadd(fmul(bc->Xs, M.x), fmul(bc->Xc, M.y)), Xty);
+        iso_apply(P.Sinv, qx, qy, px, py);
+      } else {
+        px = fadd(fadd(fmul(Lc, M.x), fmul(-Ls, M.y)), Xtx);
+        py = fadd(fadd(fmul(Ls, M.x), fmul(Lc, M.y)), Xty);
+      }
+      const float dx = fsub(px, F.x), dy = fsub(py, F.y);
+      const float e0 = fadd(fmul(dx, F.z), fmul(dy, F.w));
+      const float e1 = fsub(nx, F.z), e2 = fsub(ny, F.w);
+      const float Ja = fadd(fmul(F.z, Lc), fmul(F.w, Ls));
+      const float Jb = fadd(fmul(F.z, -Ls), fmul(F.w, Lc));
+      const float Jc = fadd(fmul(Ja, -M.y), fmul(Jb, M.x));
+      const float d0 = -ny, d1 = nx;  // R * (-n.y, n.x)^T, exact in binary32
+      const float chi = fadd(fadd(fmul(e0, e0), fmul(e1, e1)), fmul(e2, e2));
+      float w = 1.f, chi_in = chi, chi_k = 0.f;
+      if (P.tau > 0.f && !(chi < P.tau)) {  // RobustifierCauchy (L0.json:76-81)
+        const float aux = fadd(fmul(chi, P.inv_tau), 1.f);
+        chi_k           = fmul(P.tau, logf(aux));
+        w               = fdiv(1.f, aux);
+        chi_in          = 0.f;
+        cnt += 1u << 16;
+      } else {
+        cnt += 1u;
+      }
+      const float wa = fmul(Ja, w), wb = fmul(Jb, w), wc = fmul(Jc, w);
+      const float wd0 = fmul(d0, w), wd1 = fmul(d1, w);
+      acc[0]  = fadd(acc[0], fmul(wa, Ja));
+      acc[1]  = fadd(acc[1], fmul(wa, Jb));
+      acc[2]  = fadd(acc[2], fmul(wa, Jc));
+      acc[3]  = fadd(acc[3], fmul(wb, Jb));
+      acc[4]  = fadd(acc[4], fmul(wb, Jc));
+      acc[5]  = fadd(acc[5], fadd(fadd(fmul(wc, Jc), fmul(wd0, d0)), fmul(wd1, d1)));
+      acc[6]  = fadd(acc[6], fmul(wa, e0));
+      acc[7]  = fadd(acc[7], fmul(wb, e0));
+      acc[8]  = fadd(acc[8], fadd(fadd(fmul(wc, e0), fmul(wd0, e1)), fmul(wd1, e2)));
+      acc[9]  = fadd(acc[9], chi_in);
+      acc[10] = fadd(acc[10], chi_k);
+    }
+    // reduction: warp shuffle tree, then one shared-memory stage over the warps
+    const float wsum    = warp_reduce_slots(acc, lane);
+    const unsigned wcnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (!(lane & 1) && lane < 2 * NSUM) red[warp * RED_STRIDE + (lane >> 1)] = wsum;
+    if (lane == 0) red[warp * RED_STRIDE + NSUM] = __uint_as_float(wcnt);
+    __syncthreads();
+    if (warp == 0) {
+      if (lane < NSUM) {
+        tot = red[lane];
+#pragma unroll
+        for (int w = 1; w < T / 32; ++w) tot = fadd(tot, red[w * RED_STRIDE + lane]);
+      } else if (lane == NSUM) {
+        tot_cnt = 0;
+#pragma unroll
+        for (int w = 0; w < T / 32; ++w) tot_cnt += __float_as_uint(red[w * RED_STRIDE + NSUM]);
+      }
+      float v[NSUM];
+#pragma unroll
+      for (int s = 0; s < NSUM; ++s) v[s] = __shfl_sync(0xffffffffu, tot, s);
+      const unsigned c2 = __shfl_sync(0xffffffffu, tot_cnt, NSUM);
+      if (lane == 0) {
+        const int n_in = c2 & 0xffff, n_k = c2 >> 16, n_corr = n_in + n_k;
+        iso X;
+        X.tx = Xtx, X.ty = Xty, X.c = bc->Xc, X.s = bc->Xs;
+        int stop = 0;
+        float dx[3];
+        if (n_corr <= P.min_num_correspondences) {
+          stop = 1 + LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES;
+        } else if (!A.score_only) {
+          if (!solve3(v, P.damping, dx)) {
+            stop = 1 + LS2D_STATUS_SINGULAR;
+          } else {
+            X = iso_compose(X, iso_v2t(dx[0], dx[1], dx[2]));  // VariableSE2Right: X <- X * v2t(dx)
+            if (A.iters) {
+              ls2d_iter_stats st;
+              st.x = X.tx, st.y = X.ty, st.theta = atan2f_fdlibm(X.s, X.c);
+              st.chi_inliers = v[9], st.chi_kernelized = v[10];
+              st.n_inliers = n_in, st.n_kernelized = n_k, st.n_corr = n_corr;
+              A.iters[(size_t) pair * P.max_iterations + it] = st;
+            }
+          }
+        }
+        publish_pose(bc, P, X, SENSOR, stop);
+      }
+    }
+    __syncthreads();
+    if (bc->stop) {
+      status = bc->stop - 1;
+      break;
+    }
+  }
+
+  if (tid < 32) {
+    float v[NSUM];
+#pragma unroll
+    for (int s = 0; s < NSUM; ++s) v[s] = __shfl_sync(0xffffffffu, tot, s);
+    const unsigned c2 = __shfl_sync(0xffffffffu, tot_cnt, NSUM);
+    if (tid == 0) {
+      int n_in = c2 & 0xffff, n_k = c2 >> 16;
+      const int n_corr = n_in + n_k;
+      if (status == LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES) {  // the oracle reports empty sums here
+#pragma unroll
+        for (int s = 0; s < NSUM; ++s) v[s] = 0.f;
+        n_in = n_k = 0;
+      }
+      if (status < 0)
+        status = n_in < P.min_num_inliers ? LS2D_STATUS_NOT_ENOUGH_INLIERS : LS2D_STATUS_SUCCESS;
+      ls2d_result r;
+      r.x = bc->Xtx, r.y = bc->Xty, r.theta = atan2f_fdlibm(bc->Xs, bc->Xc);
+      r.chi_inliers = v[9], r.chi_kernelized = v[10];
+      r.n_inliers = n_in, r.n_kernelized = n_k, r.n_corr = n_corr;
+      r.status = status, r.iterations = it;
+#pragma unroll
+      for (int s = 0; s < 6; ++s) r.H[s] = v[s];
+      A.out[pair] = r;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// z-buffer projection of an arbitrary-size cloud with strided loops (API / parity kernels).
+// W = world -> camera isometry.  On return (after the trailing barrier) zidx[c] holds the winner of
+// column c (Z_EMPTY_IDX if none) and zdepth[c] its rho bits.
+template <bool IDENTITY>
+__device__ __forceinline__ void zbuffer_project(const dev_params& P, const iso& W, const float4* pts, int n,
+                                                unsigned* zdepth, unsigned* zidx) {
+  const int C = P.cam.cols;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    zdepth[k] = Z_EMPTY_DEPTH;
+    zidx[k]   = Z_EMPTY_IDX;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float4 p = ldg4(pts + i);
+      float px = p.x, py = p.y;
+      if (!IDENTITY) iso_apply(W, p.x, p.y, px, py);
+      const float rho = fsqrt(fadd(fmul(px, px), fmul(py, py)));
+      if (rho < P.range_min || rho > P.range_max) continue;
+      const int col = polar_column(P.cam, py, px);
+      if (col < 0) continue;
+      if (pass == 0)
+        atomicMin(&zdepth[col], f2u(rho));
+      else if (zdepth[col] == f2u(rho))
+        atomicMin(&zidx[col], (unsigned) i);
+    }
+    __syncthreads();
+  }
+}
+
+struct project_args {
+  const float4* pts;
+  const int* off;
+  int cloud;
+  float cam_xyt[3];
+  int* source_idx;  // [C]
+  float* depth;     // [C]
+};
+
+__global__ void project_kernel(const dev_params P, const project_args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C      = P.cam.cols;
+  unsigned* zdepth = reinterpret_cast<unsigned*>(smem_raw);
+  unsigned* zidx   = zdepth + C;
+  const int p0 = A.off[A.cloud], n = A.off[A.cloud + 1] - p0;
+  const iso W = iso_inverse(iso_v2t(A.cam_xyt[0], A.cam_xyt[1], A.cam_xyt[2]));
+  zbuffer_project<false>(P, W, A.pts + p0, n, zdepth, zidx);
+  for (int k = threadIdx.x; k < C; k += blockDim.x) {
+    const bool empty = zidx[k] == Z_EMPTY_IDX;
+    A.source_idx[k]  = empty ? -1 : (int) zidx[k];
+    A.depth[k]       = empty ? FLT_MAX : u2f(zdepth[k]);
+  }
+}
+
+struct correspond_args {
+  const float4* fixed_pts;
+  const int* fixed_off;
+  const float4* moving_pts;
+  const int* moving_off;
+  int fixed_cloud, moving_cloud;
+  float lmis_xyt[3];  // local_map_in_sensor
+  int* fixed_idx;     // [C]
+  int* moving_idx;    // [C]
+  int* count;
+};
+
+// CorrespondenceFinderProjective2f::compute (R/registration/correspondence_finder_projective_2d.cpp:18-77)
+__global__ void correspond_kernel(const dev_params P, const correspond_args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C   = P.cam.cols;
+  unsigned* zdf = reinterpret_cast<unsigned*>(smem_raw);
+  unsigned* zif = zdf + C;
+  unsigned* zdm = zif + C;
+  unsigned* zim = zdm + C;
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const int f0 = A.fixed_off[A.fixed_cloud], nf = A.fixed_off[A.fixed_cloud + 1] - f0;
+  const int m0 = A.moving_off[A.moving_cloud], nm = A.moving_off[A.moving_cloud + 1] - m0;
+  const iso L = iso_v2t(A.lmis_xyt[0], A.lmis_xyt[1], A.lmis_xyt[2]);
+  const iso W = iso_inverse(iso_inverse(L));  // .cpp:47 + the projector's own inverse (decision D13)
+  zbuffer_project<true>(P, W, A.fixed_pts + f0, nf, zdf, zif);
+  zbuffer_project<false>(P, W, A.moving_pts + m0, nm, zdm, zim);
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int k0 = 0; k0 < C; k0 += blockDim.x) {  // ascending columns, ordered compaction (.cpp:55-74)
+    const int k = k0 + threadIdx.x;
+    bool ok     = false;
+    int fi = -1, mi = -1;
+    if (k < C && zif[k] != Z_EMPTY_IDX && zim[k] != Z_EMPTY_IDX) {
+      fi = (int) zif[k], mi = (int) zim[k];
+      ok = !(fabsf(fsub(u2f(zdf[k]), u2f(zdm[k]))) > P.point_distance);
+      if (ok) {
+        const float4 F = ldg4(A.fixed_pts + f0 + fi);
+        const float4 M = ldg4(A.moving_pts + m0 + mi);
+        float nx, ny;
+        iso_rot(W, M.z, M.w, nx, ny);
+        ok = !(fadd(fmul(nx, F.z), fmul(ny, F.w)) < P.normal_cos);
+      }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) warp_tot[warp] = __popc(ballot);
+    __syncthreads();
+    int before = base;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (ok) {
+      const int dst     = before + __popc(ballot & ((1u << lane) - 1u));
+      A.fixed_idx[dst]  = fi;
+      A.moving_idx[dst] = mi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = base;
+      for (int w = 0; w < nwarp; ++w) t += warp_tot[w];
+      base = t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *A.count = base;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// acceptance gates (L0.json:627-634) + deterministic best-of, one CTA.
+__device__ __forceinline__ bool accepts(const ls2d_result& r, const ls2d_gates& g) {
+  if (r.status != LS2D_STATUS_SUCCESS) return false;
+  if (r.n_inliers < g.min_inliers || r.n_inliers <= 0 || r.n_corr <= 0) return false;
+  if (fdiv(r.chi_inliers, (float) r.n_inliers) > g.max_chi_per_inlier) return false;
+  if (fdiv((float) r.n_inliers, (float) r.n_corr) < g.min_inlier_ratio) return false;
+  return true;
+}
+// strict "a better than b": more inliers, then lower chi per inlier, then lower id
+__device__ __forceinline__ bool better(int na, float ca, int ia, int nb, float cb, int ib) {
+  if (ib < 0) return ia >= 0;
+  if (ia < 0) return false;
+  if (na != nb) return na > nb;
+  if (ca != cb) return ca < cb;
+  return ia < ib;
+}
+
+__global__ void best_of_kernel(const ls2d_result* res, int n, int n_guess, ls2d_gates g, int candidate_base,
+                               ls2d_best* out) {
+  __shared__ int s_n[32], s_i[32];
+  __shared__ float s_c[32];
+  int bn = 0, bi = -1;
+  float bcpi = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const ls2d_result r = res[i];
+    if (!accepts(r, g)) continue;
+    const float c = fdiv(r.chi_inliers, (float) r.n_inliers);
+    if (better(r.n_inliers, c, i, bn, bcpi, bi)) bn = r.n_inliers, bcpi = c, bi = i;
+  }
+  for (int off = 16; off >= 1; off >>= 1) {
+    const int on   = __shfl_xor_sync(0xffffffffu, bn, off);
+    const float oc = __shfl_xor_sync(0xffffffffu, bcpi, off);
+    const int oi   = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (better(on, oc, oi, bn, bcpi, bi)) bn = on, bcpi = oc, bi = oi;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_n[warp] = bn, s_c[warp] = bcpi, s_i[warp] = bi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int) (blockDim.x >> 5); ++w)
+      if (better(s_n[w], s_c[w], s_i[w], bn, bcpi, bi)) bn = s_n[w], bcpi = s_c[w], bi = s_i[w];
+    ls2d_best b;
+    if (bi < 0) {
+      b.x = b.y = b.theta = b.chi_inliers = 0.f;
+      b.n_inliers = b.n_corr = 0;
+      b.candidate = -1, b.guess = -1;
+    } else {
+      const ls2d_result r = res[bi];
+      b.x = r.x, b.y = r.y, b.theta = r.theta, b.chi_inliers = r.chi_inliers;
+      b.n_inliers = r.n_inliers, b.n_corr = r.n_corr;
+      b.candidate = candidate_base + bi / n_guess;
+      b.guess     = bi % n_guess;
+    }
+    *out = b;
+  }
+}
+
+}  // namespace ls2d

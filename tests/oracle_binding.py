@@ -1,0 +1,158 @@
+"""ctypes binding of the CPU oracle (oracle/ls2d_oracle.h).  Test infrastructure: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "_build", "libls2d_oracle.so")
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("canvas_cols", C.c_int32), ("angle_col_min", C.c_float), ("angle_col_max", C.c_float),
+                ("range_min", C.c_float), ("range_max", C.c_float), ("point_distance", C.c_float),
+                ("normal_cos", C.c_float), ("cauchy_chi_threshold", C.c_float), ("damping", C.c_float),
+                ("max_iterations", C.c_int32), ("min_num_correspondences", C.c_int32),
+                ("min_num_inliers", C.c_int32), ("with_sensor", C.c_int32),
+                ("sensor_in_robot", C.c_float * 3)]
+
+
+class OrcIso(C.Structure):
+    _fields_ = [("tx", C.c_float), ("ty", C.c_float), ("c", C.c_float), ("s", C.c_float)]
+
+
+CELL_DTYPE = np.dtype([("source_idx", "<i4"), ("depth", "<f4"), ("px", "<f4"), ("py", "<f4"),
+                       ("nx", "<f4"), ("ny", "<f4")])
+RESULT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
+                         ("chi_kernelized", "<f4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"),
+                         ("n_corr", "<i4"), ("status", "<i4"), ("iterations", "<i4"), ("H", "<f4", (6,))])
+ITER_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
+                       ("chi_kernelized", "<f4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"),
+                       ("n_corr", "<i4")])
+assert RESULT_DTYPE.itemsize == 64 and ITER_DTYPE.itemsize == 32 and CELL_DTYPE.itemsize == 24
+
+SUM_SEQUENTIAL, SUM_TREE = 0, 1
+_lib = None
+
+
+def build() -> str:
+    subprocess.run(["make", "-s", "-C", os.path.join(_ROOT, "oracle")], check=True)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+        L.orc_default_params.argtypes = [C.POINTER(OrcParams)]
+        L.orc_v2t.argtypes, L.orc_v2t.restype = [f32, f32, f32], OrcIso
+        L.orc_inverse.argtypes, L.orc_inverse.restype = [OrcIso], OrcIso
+        L.orc_compose.argtypes, L.orc_compose.restype = [OrcIso, OrcIso], OrcIso
+        L.orc_t2v.argtypes = [OrcIso, vp]
+        L.orc_project.argtypes = [C.POINTER(OrcParams), OrcIso, vp, i32, vp]
+        L.orc_find_correspondences.argtypes = [C.POINTER(OrcParams), vp, vp, i32, OrcIso, vp, vp, vp]
+        L.orc_find_correspondences.restype = i32
+        L.orc_error_and_jacobian.argtypes = [C.POINTER(OrcParams), OrcIso, C.c_float * 4, C.c_float * 4, vp, vp]
+        L.orc_align.argtypes = [C.POINTER(OrcParams), vp, i32, vp, i32, vp, i32, i32, vp, vp]
+        L.orc_align_batch.argtypes = [C.POINTER(OrcParams), vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
+        L.orc_best_of.argtypes = [vp, i32, i32, f32, f32]
+        L.orc_best_of.restype = i32
+        L.orc_accept.argtypes = [vp, i32, f32, f32]
+        L.orc_accept.restype = i32
+        L.orc_max_threads.restype = i32
+        _lib = L
+    return _lib
+
+
+def default_params(**kw) -> OrcParams:
+    p = OrcParams()
+    lib().orc_default_params(C.byref(p))
+    for k, v in kw.items():
+        if k == "sensor_in_robot":
+            p.sensor_in_robot = (C.c_float * 3)(*v)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def v2t(x, y, theta) -> OrcIso:
+    return lib().orc_v2t(x, y, theta)
+
+
+def project(prm: OrcParams, camera_pose_xyt, pts: np.ndarray) -> np.ndarray:
+    """PointNormal2fProjectorPolar with setCameraPose(v2t(camera_pose_xyt)); returns canvas_cols cells."""
+    pts = _f32(pts)
+    img = np.zeros(prm.canvas_cols, CELL_DTYPE)
+    lib().orc_project(C.byref(prm), v2t(*camera_pose_xyt), _ptr(pts), len(pts), _ptr(img))
+    return img
+
+
+def find_correspondences(prm: OrcParams, fixed: np.ndarray, moving: np.ndarray, local_map_in_sensor_xyt):
+    """CorrespondenceFinderProjective2f::compute(); returns (fixed_idx, moving_idx, fixed_img, moving_img)."""
+    fixed, moving = _f32(fixed), _f32(moving)
+    fimg = project(prm, (0.0, 0.0, 0.0), fixed)
+    mimg = np.zeros(prm.canvas_cols, CELL_DTYPE)
+    fi = np.zeros(prm.canvas_cols, np.int32)
+    mi = np.zeros(prm.canvas_cols, np.int32)
+    k = lib().orc_find_correspondences(C.byref(prm), _ptr(fimg), _ptr(moving), len(moving),
+                                       v2t(*local_map_in_sensor_xyt), _ptr(mimg), _ptr(fi), _ptr(mi))
+    return fi[:k].copy(), mi[:k].copy(), fimg, mimg
+
+
+def error_and_jacobian(prm: OrcParams, X_xyt, fixed_pt, moving_pt):
+    e = np.zeros(3, np.float32)
+    J = np.zeros(9, np.float32)
+    lib().orc_error_and_jacobian(C.byref(prm), v2t(*X_xyt), (C.c_float * 4)(*fixed_pt),
+                                 (C.c_float * 4)(*moving_pt), _ptr(e), _ptr(J))
+    return e, J.reshape(3, 3)
+
+
+def align(prm: OrcParams, fixed, moving, init_xyt, sum_mode=SUM_SEQUENTIAL, tree_threads=256):
+    fixed, moving, init = _f32(fixed), _f32(moving), _f32(init_xyt)
+    out = np.zeros(1, RESULT_DTYPE)
+    its = np.zeros(prm.max_iterations, ITER_DTYPE)
+    lib().orc_align(C.byref(prm), _ptr(fixed), len(fixed), _ptr(moving), len(moving), _ptr(init),
+                    sum_mode, tree_threads, _ptr(out), _ptr(its))
+    return out[0], its
+
+
+def align_batch(prm: OrcParams, fixed_pts, fixed_off, moving_pts, moving_off, init_xyt, fixed_id=None,
+                moving_id=None, sum_mode=SUM_SEQUENTIAL, tree_threads=256, n_threads=1, want_iters=True):
+    fixed_pts, moving_pts, init = _f32(fixed_pts), _f32(moving_pts), _f32(init_xyt)
+    fixed_off, moving_off = _i32(fixed_off), _i32(moving_off)
+    fixed_id, moving_id = _i32(fixed_id), _i32(moving_id)
+    n = len(init)
+    out = np.zeros(n, RESULT_DTYPE)
+    its = np.zeros((n, prm.max_iterations), ITER_DTYPE) if want_iters else None
+    lib().orc_align_batch(C.byref(prm), _ptr(fixed_pts), _ptr(fixed_off), _ptr(moving_pts), _ptr(moving_off),
+                          _ptr(fixed_id), _ptr(moving_id), _ptr(init), n, sum_mode, tree_threads, n_threads,
+                          _ptr(out), _ptr(its))
+    return out, its
+
+
+def best_of(results: np.ndarray, min_inliers: int, max_chi_per_inlier: float, min_inlier_ratio: float) -> int:
+    results = np.ascontiguousarray(results)
+    return lib().orc_best_of(_ptr(results), len(results), min_inliers, max_chi_per_inlier, min_inlier_ratio)
+
+
+def max_threads() -> int:
+    return lib().orc_max_threads()
