@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- aligned scan-pairs/s of the batched projective 2D registration path on B200.
+
+Workload (BASELINE.json configs[2], "config 3" of SURVEY.md 8d): 4096 scan pairs x 1081 beams (Hokuyo
+UTM-30LX shape), 10 Gauss-Newton/ICP iterations, the reference's tracking parameter set
+(point_distance 0.5, normal_cos 0.9, Cauchy 0.01; LASER_0.json:598-611,76-81,498), canvas 1081 columns
+over +-3.14159 rad.  A "step" is one pass of the hot path over the whole batch.
+
+  value      device-resident throughput: clouds already in HBM, one fused-ICP launch per step, CUDA events
+             on the launching stream.  The 142 MB of clouds exceed the 126 MB L2, so every step re-reads
+             them from HBM (config.l2: "inputs_larger_than_l2").
+  e2e        the same metric through the C ABI with HOST buffers (ls2d_align_pairs_host): pinned-memory
+             H2D of both cloud sets and the initial guesses, the kernel, D2H of the 64-byte results, all
+             inside the timed region.
+  roofline   achieved = 34,672 algorithmic bytes per pair (16*1081 + 16*1081 + 16 + 64) x pairs
+             per launch / mean launch duration, against the measured HBM copy bandwidth.
+  cpu_baseline  the CPU oracle (oracle/ls2d_oracle.c, the restatement of the reference's aligner -- the
+             reference itself cannot be built here) on the box's host cores.
+
+N > 1 (torchrun): one process per GPU, every rank aligns its own 4096-pair batch (independent pairs, no
+data-path collective: weak scaling); time = max over ranks.   --impl reference times the oracle only.
+--workload verify runs the sharded loop-closure verification (config 4 shape) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+A_PAIR_BYTES = 16 * 1081 + 16 * 1081 + 16 + 64  # compulsory bytes per aligned pair
+TRACK = dict(canvas_cols=1081, point_distance=0.5, normal_cos=0.9, cauchy_chi_threshold=0.01, max_iterations=10)
+LOOP = dict(canvas_cols=1081, point_distance=1.414, normal_cos=0.8, cauchy_chi_threshold=0.05, max_iterations=30)
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(kernel: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    return rank, int(os.environ.get("LOCAL_RANK", rank)), world
+
+
+def make_workload(n_pairs: int, seed: int, device: str, loop: bool = False):
+    from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
+    if loop:
+        return make_scan_pairs(n_pairs, seed=seed, device=device, motion_xy=0.4, motion_theta=0.2,
+                               init_noise_xy=0.2, init_noise_theta=0.08)
+    return make_scan_pairs(n_pairs, seed=seed, device=device)
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  It cannot be compiled here (needs Eigen3 and three
+    un-vendored srrg2 packages), so this arm times the oracle port of it with every host thread."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    prm = ob.default_params(**TRACK)
+    cores = ob.max_threads()
+    sample_pairs = min(args.pairs, 4096)
+    sp = make_workload(sample_pairs, 0xC0FFEE, "cpu")
+    run = lambda: ob.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
+                                 n_threads=cores, want_iters=False)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    value = sample_pairs * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "aligned scan-pairs/sec (1081 beams, 10 GN iters)", "value": value,
+        "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batched scan-to-local-map registration: %d pairs x 1081 beams, 10 GN iterations, "
+                               "tracking parameter set" % sample_pairs, "pairs_per_step": sample_pairs},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "%d pairs per step, OpenMP over pairs on %d threads" % (sample_pairs, cores)},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from srrg2_laser_slam_2d_b200 import Handle, default_params
+    from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING, RESULT_DTYPE
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_pairs = args.pairs
+    sp = make_workload(n_pairs, 0xC0FFEE + rank, str(dev))
+    h = Handle(local_rank, default_params(**TRACK))
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+
+    # ---- device-resident: clouds live in HBM, one launch per step
+    fp, fo = torch.from_numpy(sp.fixed_pts).to(dev), torch.from_numpy(sp.fixed_off).to(dev)
+    mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
+    init = torch.from_numpy(sp.init_xyt).to(dev)
+    out = torch.zeros(n_pairs * 16, dtype=torch.int32, device=dev)
+    h.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), n_pairs, 1081)
+    h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), n_pairs, 1081)
+
+    def step():
+        h.align_batch_dev(None, None, init.data_ptr(), n_pairs, out.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = h.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    launches = h.launch_count - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    res = np.frombuffer(out.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+    ok_rate = float((res["status"] == 0).mean())
+
+    # ---- end to end: host buffers (pinned) -> C ABI -> host results
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hfp, hfo, hmp, hmo, hin = pin(sp.fixed_pts), pin(sp.fixed_off), pin(sp.moving_pts), pin(sp.moving_off), pin(sp.init_xyt)
+    hout = torch.zeros(n_pairs * 64, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
+    he = Handle(local_rank, default_params(**TRACK))
+    for _ in range(args.warmup):
+        he.align_pairs_host(hfp, hfo, hmp, hmo, hin, hout)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        he.align_pairs_host(hfp, hfo, hmp, hmo, hin, hout)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = he.launch_count
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    assert hout.tobytes() == res.tobytes(), "end-to-end results differ from the device-resident run"
+
+    # ---- max over ranks
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        value = world * n_pairs * args.steps / (total_ms * 1e-3)
+        e2e_value = world * n_pairs * args.steps / (e2e_ms * 1e-3)
+        peak, peak_src = hbm_peak()
+        mean_launch_s = float(np.mean(per_launch_ms)) * 1e-3
+        achieved = A_PAIR_BYTES * n_pairs / mean_launch_s / 1e9
+        h2d = hfp.nbytes + hfo.nbytes + hmp.nbytes + hmo.nbytes + hin.nbytes
+        line = {
+            "metric": "aligned scan-pairs/sec (1081 beams, 10 GN iters)", "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "batched scan-to-local-map registration: %d pairs x 1081 beams, 10 GN iterations, "
+                                   "tracking parameter set (config 3)" % n_pairs,
+                       "pairs_per_gpu_per_step": n_pairs, "canvas_cols": 1081, "l2": "inputs_larger_than_l2 (142 MB)",
+                       "success_rate": ok_rate},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(hout.nbytes), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": recorded_traffic("icp_fused_kernel"), "peak_source": peak_src,
+                         "kernel": "icp_fused_kernel", "algorithmic_bytes_per_launch": A_PAIR_BYTES * n_pairs,
+                         "mean_launch_ms": mean_launch_s * 1e3,
+                         "note": "10 fused iterations per pair make this kernel issue-bound, not HBM-bound "
+                                 "(SURVEY.md 8d); see DESIGN.md for the instruction-issue roofline"},
+            "clocks": clk,
+            "e2e_gpu_launches": int(e2e_launches),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sp)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sp):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    prm = ob.default_params(**TRACK)
+    cores = ob.max_threads()
+    n = sp.n_pairs
+    best = float("inf")
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ob.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt, n_threads=cores,
+                       want_iters=False)
+        best = min(best, time.perf_counter() - t0)
+    m = min(n, 256)
+    t0 = time.perf_counter()
+    ob.align_batch(prm, sp.fixed_pts, sp.fixed_off[:m + 1], sp.moving_pts, sp.moving_off[:m + 1], sp.init_xyt[:m],
+                   n_threads=1, want_iters=False)
+    single = m / (time.perf_counter() - t0)
+    return {"value": n / best, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": "the same %d pairs, OpenMP over pairs on %d threads, best of 3" % (n, cores),
+            "single_thread_pairs_per_s": single}
+
+
+# ----------------------------------------------------------------------------------------------- verification
+def run_verify(args):
+    """Sharded loop-closure verification (config 4 shape): one query local map against n_cand candidate local
+    maps x n_guess initial guesses, candidates split contiguously over the ranks, one all-gather of the 32-byte
+    per-shard best records (torch.distributed / NCCL), deterministic best-of on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    from srrg2_laser_slam_2d_b200 import Gates, Handle, default_params
+    from srrg2_laser_slam_2d_b200._abi import BEST_DTYPE, LS2D_FIXED, LS2D_MOVING, reduce_best
+    from srrg2_laser_slam_2d_b200.sharding import shard_range
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_cand, n_guess = args.candidates, args.guesses
+    lo, hi = shard_range(n_cand, rank, world)
+    # every rank builds the same candidate set from the same seed and keeps its slice (a real deployment
+    # would hold its shard of the local maps resident); unique clouds are tiled to reach n_cand
+    uniq = min(n_cand, args.unique)
+    sp = make_workload(uniq, 0xBEEF, str(dev), loop=True)
+    rng = np.random.default_rng(1)
+    guesses = (sp.gt_xyt[0][None, None, :] + rng.uniform(-0.15, 0.15, (n_cand, n_guess, 3))).astype(np.float32)
+    cand_ids = (np.arange(n_cand) % uniq).astype(np.int32)
+    h = Handle(local_rank, default_params(**LOOP))
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    fp, fo = torch.from_numpy(sp.fixed_pts).to(dev), torch.from_numpy(sp.fixed_off).to(dev)
+    mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
+    h.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), uniq, 1081)
+    h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), uniq, 1081)
+    cand = torch.from_numpy(cand_ids[lo:hi].copy()).to(dev)
+    gs = torch.from_numpy(guesses[lo:hi].copy()).to(dev)
+    best = torch.zeros(8, dtype=torch.int32, device=dev)
+    gathered = torch.zeros(8 * world, dtype=torch.int32, device=dev)
+    gates = Gates(300, 0.1, 0.8)
+
+    def step():
+        h.verify_dev(0, cand.data_ptr(), hi - lo, gs.data_ptr(), n_guess, gates, lo, best.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, best)
+        else:
+            gathered.copy_(best)
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rec = np.frombuffer(gathered.cpu().numpy().tobytes(), dtype=BEST_DTYPE)
+    winner = reduce_best(rec)
+    if rank == 0:
+        n_align = n_cand * n_guess
+        print(json.dumps({
+            "metric": "verified candidate alignments/sec (1081 beams, 30 GN iters)",
+            "value": n_align * args.steps / (float(ms[0]) * 1e-3), "unit": "alignments/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms[0]) / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "loop-closure verification: 1 query x %d candidates x %d guesses, 30 GN iterations, "
+                                   "loop-closure parameter set (config 4 shape)" % (n_cand, n_guess),
+                       "unique_candidate_clouds": uniq, "collective": "all_gather of %d x 32 B" % world},
+            "winner": {"candidate": int(winner["candidate"]), "guess": int(winner["guess"]),
+                       "n_inliers": int(winner["n_inliers"])},
+            "gpu_launches": int(h.launch_count),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["align", "verify"], default="align")
+    ap.add_argument("--pairs", type=int, default=4096)
+    ap.add_argument("--candidates", type=int, default=65536)
+    ap.add_argument("--guesses", type=int, default=8)
+    ap.add_argument("--unique", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.workload == "verify":
+        run_verify(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -547,3 +547,31 @@ int32_t orc_max_threads(void) {
   return 1;
 #endif
 }
+
+/* ---------------------------------------------------------------- host libm bulk drivers
+ * (tests/test_math_host.py compares the kernels' own libm copies against these; numpy's float32
+ * ufuncs may dispatch to SIMD implementations that are NOT the libm the reference links) */
+void orc_libm_atan2f_n(const float* y, const float* x, float* out, long n) {
+  for (long i = 0; i < n; ++i) {
+    out[i] = atan2f(y[i], x[i]);
+  }
+}
+
+void orc_libm_sincosf_n(const float* x, float* s, float* c, long n) {
+  for (long i = 0; i < n; ++i) {
+    s[i] = sinf(x[i]);
+    c[i] = cosf(x[i]);
+  }
+}
+
+/* lrintf(K00 * atan2f(y, x) + K01) with the projector's gating: -1 outside [0, C) */
+void orc_column_n(const orc_params* prm, const float* y, const float* x, int32_t* col, long n) {
+  const int32_t C = prm->canvas_cols;
+  const float K00 = (float) C / (prm->angle_col_max - prm->angle_col_min);
+  const float K01 = (float) C * 0.5f;
+  for (long i = 0; i < n; ++i) {
+    const float u = K00 * atan2f(y[i], x[i]) + K01;
+    const long c  = lrintf(u);
+    col[i]        = (c < 0 || c >= C) ? -1 : (int32_t) c;
+  }
+}

@@ -144,6 +144,11 @@ int32_t orc_best_of(const orc_result* r, int32_t n, int32_t min_inliers, float m
 
 int32_t orc_max_threads(void);
 
+/* host libm bulk drivers for tests/test_math_host.py */
+void orc_libm_atan2f_n(const float* y, const float* x, float* out, long n);
+void orc_libm_sincosf_n(const float* x, float* s, float* c, long n);
+void orc_column_n(const orc_params* prm, const float* y, const float* x, int32_t* col, long n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,10 @@ class OrcIso(C.Structure):
     _fields_ = [("tx", C.c_float), ("ty", C.c_float), ("c", C.c_float), ("s", C.c_float)]
 
 
+class OrcPoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("nx", C.c_float), ("ny", C.c_float)]
+
+
 CELL_DTYPE = np.dtype([("source_idx", "<i4"), ("depth", "<f4"), ("px", "<f4"), ("py", "<f4"),
                        ("nx", "<f4"), ("ny", "<f4")])
 RESULT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
@@ -59,7 +63,7 @@ def lib():
         L.orc_project.argtypes = [C.POINTER(OrcParams), OrcIso, vp, i32, vp]
         L.orc_find_correspondences.argtypes = [C.POINTER(OrcParams), vp, vp, i32, OrcIso, vp, vp, vp]
         L.orc_find_correspondences.restype = i32
-        L.orc_error_and_jacobian.argtypes = [C.POINTER(OrcParams), OrcIso, C.c_float * 4, C.c_float * 4, vp, vp]
+        L.orc_error_and_jacobian.argtypes = [C.POINTER(OrcParams), OrcIso, OrcPoint, OrcPoint, vp, vp]
         L.orc_align.argtypes = [C.POINTER(OrcParams), vp, i32, vp, i32, vp, i32, i32, vp, vp]
         L.orc_align_batch.argtypes = [C.POINTER(OrcParams), vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
         L.orc_best_of.argtypes = [vp, i32, i32, f32, f32]
@@ -67,6 +71,9 @@ def lib():
         L.orc_accept.argtypes = [vp, i32, f32, f32]
         L.orc_accept.restype = i32
         L.orc_max_threads.restype = i32
+        L.orc_libm_atan2f_n.argtypes = [vp, vp, vp, C.c_long]
+        L.orc_libm_sincosf_n.argtypes = [vp, vp, vp, C.c_long]
+        L.orc_column_n.argtypes = [C.POINTER(OrcParams), vp, vp, vp, C.c_long]
         _lib = L
     return _lib
 
@@ -121,8 +128,8 @@ def find_correspondences(prm: OrcParams, fixed: np.ndarray, moving: np.ndarray, 
 def error_and_jacobian(prm: OrcParams, X_xyt, fixed_pt, moving_pt):
     e = np.zeros(3, np.float32)
     J = np.zeros(9, np.float32)
-    lib().orc_error_and_jacobian(C.byref(prm), v2t(*X_xyt), (C.c_float * 4)(*fixed_pt),
-                                 (C.c_float * 4)(*moving_pt), _ptr(e), _ptr(J))
+    lib().orc_error_and_jacobian(C.byref(prm), v2t(*X_xyt), OrcPoint(*[float(v) for v in fixed_pt]),
+                                 OrcPoint(*[float(v) for v in moving_pt]), _ptr(e), _ptr(J))
     return e, J.reshape(3, 3)
 
 
@@ -156,3 +163,24 @@ def best_of(results: np.ndarray, min_inliers: int, max_chi_per_inlier: float, mi
 
 def max_threads() -> int:
     return lib().orc_max_threads()
+
+
+def libm_atan2f(y: np.ndarray, x: np.ndarray) -> np.ndarray:
+    y, x = _f32(y), _f32(x)
+    out = np.zeros(len(x), np.float32)
+    lib().orc_libm_atan2f_n(_ptr(y), _ptr(x), _ptr(out), len(x))
+    return out
+
+
+def libm_sincosf(x: np.ndarray):
+    x = _f32(x)
+    s, c = np.zeros(len(x), np.float32), np.zeros(len(x), np.float32)
+    lib().orc_libm_sincosf_n(_ptr(x), _ptr(s), _ptr(c), len(x))
+    return s, c
+
+
+def column(prm: OrcParams, y: np.ndarray, x: np.ndarray) -> np.ndarray:
+    y, x = _f32(y), _f32(x)
+    col = np.zeros(len(x), np.int32)
+    lib().orc_column_n(C.byref(prm), _ptr(y), _ptr(x), _ptr(col), len(x))
+    return col

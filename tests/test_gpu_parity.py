@@ -1,0 +1,346 @@
+"""GPU parity: the CUDA path, called through the C ABI (libls2d.so), against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * pixel indices, z-buffer winners and correspondence sets: bit-exact;
+  * with the oracle summing H/b in the kernel's tree order (ORC_SUM_TREE) the whole ICP trajectory --
+    every iteration's pose, chi2, H -- is bit-exact (chi_kernelized within 2 ulp: CUDA logf vs glibc);
+  * against the reference's sequential sum order: poses within 1e-5 m / 1e-6 rad, chi2 within 1e-4
+    relative, on >= 95 % of the pairs (tolerances from BASELINE.json).
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from srrg2_laser_slam_2d_b200 import Gates, default_params
+from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING, reduction_threads
+from srrg2_laser_slam_2d_b200.synthetic import FAR_POINT, make_scan_pairs
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M, POSE_TOL_RAD, CHI_RTOL = 1e-5, 1e-6, 1e-4      # BASELINE.json north_star
+INT_FIELDS = ("status", "iterations", "n_corr", "n_inliers", "n_kernelized")
+
+
+def upload(h, sp_or_dict):
+    d = sp_or_dict if isinstance(sp_or_dict, dict) else sp_or_dict.__dict__
+    h.upload_clouds(LS2D_FIXED, d["fixed_pts"], d["fixed_off"])
+    h.upload_clouds(LS2D_MOVING, d["moving_pts"], d["moving_off"])
+
+
+def max_points(d):
+    return int(max(np.diff(d["fixed_off"]).max(initial=0), np.diff(d["moving_off"]).max(initial=0)))
+
+
+def assert_bit_exact(g, o, gi=None, oi=None, chi_k_ulp=4):
+    for f in INT_FIELDS:
+        assert np.array_equal(g[f], o[f]), f
+    for f in ("x", "y", "theta", "chi_inliers"):
+        assert np.array_equal(gu.bits(g[f]), gu.bits(o[f])), f
+    assert np.array_equal(gu.bits(g["H"]), gu.bits(o["H"]))
+    ulp = np.abs(gu.bits(g["chi_kernelized"]).astype(np.int64) - gu.bits(o["chi_kernelized"]).astype(np.int64))
+    assert ulp.max(initial=0) <= chi_k_ulp * max(1, g["n_kernelized"].max(initial=1))
+    if gi is not None:
+        for f in ("n_corr", "n_inliers", "n_kernelized"):
+            assert np.array_equal(gi[f], oi[f]), f
+        for f in ("x", "y", "theta", "chi_inliers"):
+            assert np.array_equal(gu.bits(gi[f]), gu.bits(oi[f])), f
+
+
+def tolerance_rate(g, o):
+    same = np.ones(len(g), bool)
+    for f in INT_FIELDS:
+        same &= g[f] == o[f]
+    pose = (np.abs(g["x"] - o["x"]) <= POSE_TOL_M) & (np.abs(g["y"] - o["y"]) <= POSE_TOL_M) & \
+           (np.abs(g["theta"] - o["theta"]) <= POSE_TOL_RAD)
+    chi = np.abs(g["chi_inliers"] - o["chi_inliers"]) <= CHI_RTOL * np.abs(o["chi_inliers"]) + 1e-12
+    return float((same & pose & chi).mean()), float(same.mean())
+
+
+# ------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("name", gu.ALIGN_CASES)
+def test_golden_alignment(handle_factory, oracle, name):
+    d = gu.load(name)
+    h = handle_factory(gu.make_params(default_params, d))
+    upload(h, d)
+    g, gi = h.align_batch(d["init_xyt"], want_iters=True)
+    # (1) bit-exact against the oracle run in the kernel's summation order
+    prm = gu.make_params(oracle.default_params, d)
+    o, oi = oracle.align_batch(prm, d["fixed_pts"], d["fixed_off"], d["moving_pts"], d["moving_off"], d["init_xyt"],
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(max_points(d)))
+    assert_bit_exact(g, o, gi, oi)
+    # (2) within tolerance of the frozen fixture (the reference's sequential summation order)
+    ref = d["results"]
+    for f in INT_FIELDS:
+        assert np.array_equal(g[f], ref[f]), f
+    assert np.abs(g["x"] - ref["x"]).max() <= POSE_TOL_M and np.abs(g["y"] - ref["y"]).max() <= POSE_TOL_M
+    assert np.abs(g["theta"] - ref["theta"]).max() <= 5 * POSE_TOL_RAD
+    assert np.allclose(g["chi_inliers"], ref["chi_inliers"], rtol=10 * CHI_RTOL)
+    assert np.array_equal(gi["n_corr"], d["iters"]["n_corr"])
+
+
+@pytest.mark.parametrize("name", gu.ALIGN_CASES)
+def test_golden_correspondences_and_pixel_indices(handle_factory, oracle, name):
+    d = gu.load(name)
+    prm_o = gu.make_params(oracle.default_params, d)
+    h = handle_factory(gu.make_params(default_params, d))
+    upload(h, d)
+    for p in range(len(d["init_xyt"])):
+        lmis = d["init_xyt"][p]
+        if d["params"]["with_sensor"]:
+            S = oracle.lib().orc_inverse(oracle.v2t(*d["params"]["sensor_in_robot"]))
+            L = oracle.lib().orc_compose(S, oracle.v2t(*lmis))
+            lmis = np.zeros(3, np.float32)
+            oracle.lib().orc_t2v(L, lmis.ctypes.data)
+        fi, mi = h.find_correspondences(p, p, lmis)
+        n = int(d["corr_n"][p])
+        assert len(fi) == n
+        assert np.array_equal(fi, d["corr_fixed_idx"][p, :n]) and np.array_equal(mi, d["corr_moving_idx"][p, :n])
+        idx, depth = h.project(LS2D_FIXED, p, (0.0, 0.0, 0.0))
+        assert np.array_equal(idx, d["fixed_source_idx"][p])
+        assert np.array_equal(gu.bits(depth), gu.bits(d["fixed_depth"][p]))
+        # moving image: camera = local_map_in_sensor^-1 (correspondence_finder_projective_2d.cpp:47)
+        cam = np.zeros(3, np.float32)
+        oracle.lib().orc_t2v(oracle.lib().orc_inverse(oracle.v2t(*lmis)), cam.ctypes.data)
+        img = oracle.project(prm_o, cam, d["moving_pts"][d["moving_off"][p]:d["moving_off"][p + 1]])
+        idx, depth = h.project(LS2D_MOVING, p, cam)
+        assert np.array_equal(idx, img["source_idx"]) and np.array_equal(gu.bits(depth), gu.bits(img["depth"]))
+
+
+def test_demo_scene_projection(handle_factory):
+    d = gu.load("demo_scene_projection")
+    h = handle_factory(gu.make_params(default_params, d))
+    h.upload_clouds(LS2D_FIXED, d["scene"], np.array([0, len(d["scene"])], np.int32))
+    idx, depth = h.project(LS2D_FIXED, 0, d["camera_pose"])
+    assert np.array_equal(idx, d["source_idx"]) and np.array_equal(gu.bits(depth), gu.bits(d["depth"]))
+
+
+# ------------------------------------------------------------------ seeded batches vs the oracle
+@pytest.mark.parametrize("n_beams,cols,n_pairs", [(1081, 1081, 192), (721, 721, 96), (361, 361, 64), (181, 90, 32),
+                                                  (1500, 1081, 24), (2000, 721, 16), (4000, 1081, 8)])
+def test_seeded_batch_tree_bit_exact_and_sequential_tolerance(handle_factory, oracle, n_beams, cols, n_pairs):
+    sp = make_scan_pairs(n_pairs, n_beams=n_beams, seed=1000 + n_beams)
+    kw = dict(canvas_cols=cols, normal_cos=0.9)
+    h = handle_factory(default_params(**kw))
+    upload(h, sp)
+    g, gi = h.align_batch(sp.init_xyt, want_iters=True)
+    prm = oracle.default_params(**kw)
+    nt = oracle.max_threads()
+    o, oi = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(n_beams), n_threads=nt)
+    assert_bit_exact(g, o, gi, oi)
+    s, _ = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt, n_threads=nt)
+    rate, int_rate = tolerance_rate(g, s)
+    assert int_rate >= 0.95 and rate >= 0.95, (rate, int_rate)     # target of BASELINE.json
+    # first-iteration correspondences never depend on the summation order
+    assert np.array_equal(gi["n_corr"][:, 0], s_first_n_corr(oracle, prm, sp))
+
+
+def s_first_n_corr(oracle, prm, sp):
+    out = []
+    for p in range(sp.n_pairs):
+        f = sp.fixed_pts[sp.fixed_off[p]:sp.fixed_off[p + 1]]
+        m = sp.moving_pts[sp.moving_off[p]:sp.moving_off[p + 1]]
+        out.append(len(oracle.find_correspondences(prm, f, m, sp.init_xyt[p])[0]))
+    return np.array(out)
+
+
+def test_loop_closure_parameters_30_iterations(handle_factory, oracle):
+    sp = make_scan_pairs(48, n_beams=1081, seed=77, motion_xy=0.4, motion_theta=0.2, init_noise_xy=0.2,
+                         init_noise_theta=0.08)
+    kw = dict(canvas_cols=1081, point_distance=1.414, normal_cos=0.8, cauchy_chi_threshold=0.05, max_iterations=30)
+    h = handle_factory(default_params(**kw))
+    upload(h, sp)
+    g, gi = h.align_batch(sp.init_xyt, want_iters=True)
+    o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
+                               sp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1081),
+                               n_threads=oracle.max_threads())
+    assert_bit_exact(g, o, gi, oi)
+
+
+@pytest.mark.parametrize("with_sensor,tau", [(1, 0.01), (0, -1.0), (1, -1.0)])
+def test_sensor_offset_and_no_robustifier(handle_factory, oracle, with_sensor, tau):
+    sp = make_scan_pairs(32, n_beams=721, seed=31)
+    kw = dict(canvas_cols=721, normal_cos=0.9, with_sensor=with_sensor, sensor_in_robot=(0.15, -0.1, 0.2),
+              cauchy_chi_threshold=tau, min_num_correspondences=5)
+    h = handle_factory(default_params(**kw))
+    upload(h, sp)
+    g, gi = h.align_batch(sp.init_xyt, want_iters=True)
+    o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
+                               sp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(721))
+    assert_bit_exact(g, o, gi, oi)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_ragged_empty_and_degenerate_clouds(handle_factory, oracle):
+    """ragged CSR batch: an empty moving cloud, an empty fixed cloud, all-invalid beams, a 1-point cloud,
+    clouds of very different sizes, pairs addressed through id arrays (with repeats)."""
+    sp = make_scan_pairs(6, n_beams=500, seed=5)
+    clouds_f = [sp.fixed_pts[sp.fixed_off[i]:sp.fixed_off[i + 1]] for i in range(6)]
+    clouds_m = [sp.moving_pts[sp.moving_off[i]:sp.moving_off[i + 1]] for i in range(6)]
+    far = np.tile(np.array(FAR_POINT, np.float32), (50, 1))
+    fixed = [clouds_f[0], clouds_f[1][:0], clouds_f[2], far, clouds_f[4][:137], clouds_f[5]]
+    moving = [clouds_m[0][:0], clouds_m[1], far, clouds_m[3], clouds_m[4][:1], clouds_m[5][:333]]
+    f_off = np.concatenate([[0], np.cumsum([len(c) for c in fixed])]).astype(np.int32)
+    m_off = np.concatenate([[0], np.cumsum([len(c) for c in moving])]).astype(np.int32)
+    f_pts, m_pts = np.concatenate(fixed), np.concatenate(moving)
+    fid = np.array([0, 1, 2, 3, 4, 5, 5, 0, 2], np.int32)
+    mid = np.array([0, 1, 2, 3, 4, 5, 1, 5, 3], np.int32)
+    init = np.zeros((len(fid), 3), np.float32)
+    kw = dict(canvas_cols=500, normal_cos=0.9, max_iterations=6)
+    h = handle_factory(default_params(**kw))
+    h.upload_clouds(LS2D_FIXED, f_pts, f_off)
+    h.upload_clouds(LS2D_MOVING, m_pts, m_off)
+    g, gi = h.align_batch(init, fid, mid, want_iters=True)
+    o, oi = oracle.align_batch(oracle.default_params(**kw), f_pts, f_off, m_pts, m_off, init, fid, mid,
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(500))
+    assert_bit_exact(g, o, gi, oi)
+    assert (g["status"][:5] != 0).all() and g["status"][5] == 0
+    for p in (0, 1, 3, 4):
+        fi, mi = h.find_correspondences(int(fid[p]), int(mid[p]), (0, 0, 0))
+        assert len(fi) == len(oracle.find_correspondences(oracle.default_params(**kw), fixed[fid[p]], moving[mid[p]],
+                                                          (0, 0, 0))[0])
+
+
+def test_zero_pairs_and_bad_arguments(handle_factory):
+    from srrg2_laser_slam_2d_b200 import Ls2dError
+    sp = make_scan_pairs(2, n_beams=181, seed=6)
+    h = handle_factory(default_params(canvas_cols=181))
+    with pytest.raises(Ls2dError):                      # clouds not set: "Missing fixed!"
+        h.align_batch(np.zeros((1, 3), np.float32))
+    upload(h, sp)
+    assert len(h.align_batch(np.zeros((0, 3), np.float32))) == 0
+    with pytest.raises(Ls2dError):                      # cloud id out of range
+        h.align_batch(np.zeros((1, 3), np.float32), fixed_id=[7], moving_id=[0])
+    with pytest.raises(Ls2dError):
+        h.set_params(default_params(canvas_cols=0))
+    big = np.zeros((5000, 4), np.float32)
+    h.upload_clouds(LS2D_MOVING, big, np.array([0, 5000], np.int32))
+    with pytest.raises(Ls2dError):                      # beyond the compiled kernel table: loud, no fallback
+        h.align_batch(np.zeros((1, 3), np.float32), fixed_id=[0], moving_id=[0])
+
+
+def test_status_codes_match_the_oracle(handle_factory, oracle):
+    sp = make_scan_pairs(4, n_beams=361, seed=8)
+    for kw in (dict(min_num_inliers=100000), dict(min_num_correspondences=100000), dict(max_iterations=0),
+               dict(normal_cos=1.5)):
+        kw = dict(canvas_cols=361, **kw)
+        h = handle_factory(default_params(**kw))
+        upload(h, sp)
+        g = h.align_batch(sp.init_xyt)
+        o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts,
+                                  sp.moving_off, sp.init_xyt, sum_mode=oracle.SUM_TREE,
+                                  tree_threads=reduction_threads(361))
+        assert_bit_exact(g, o)
+        assert (g["status"] != 0).all()
+    # zero normals -> H has an empty diagonal -> SINGULAR, pose untouched
+    flat = sp.fixed_pts.copy()
+    flat[:, 2:] = 0
+    kw = dict(canvas_cols=361, normal_cos=-1.0)
+    h = handle_factory(default_params(**kw))
+    h.upload_clouds(LS2D_FIXED, flat, sp.fixed_off)
+    h.upload_clouds(LS2D_MOVING, flat, sp.fixed_off)
+    g = h.align_batch(sp.init_xyt)
+    assert (g["status"] == 3).all() and (g["iterations"] == 0).all() and (g["x"] == 0).all()
+
+
+def test_score_batch_is_the_first_linearisation(handle_factory, oracle):
+    sp = make_scan_pairs(16, n_beams=721, seed=12)
+    kw = dict(canvas_cols=721, normal_cos=0.9)
+    h = handle_factory(default_params(**kw))
+    upload(h, sp)
+    s = h.score_batch(sp.gt_xyt)
+    prm = oracle.default_params(max_iterations=1, **kw)
+    o, oi = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.gt_xyt,
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(721))
+    for f in ("n_corr", "n_inliers", "n_kernelized"):
+        assert np.array_equal(s[f], o[f])
+    assert np.array_equal(gu.bits(s["chi_inliers"]), gu.bits(o["chi_inliers"]))
+    assert np.array_equal(gu.bits(s["H"]), gu.bits(o["H"]))
+    assert np.array_equal(s["x"], sp.gt_xyt[:, 0]) and np.array_equal(s["y"], sp.gt_xyt[:, 1])   # pose untouched
+
+
+# ------------------------------------------------------------------ loop-closure verification
+def test_verify_gates_and_best_of_match_the_oracle(handle_factory, oracle):
+    n_cand, n_guess = 24, 4
+    sp = make_scan_pairs(n_cand, n_beams=721, seed=21, motion_xy=0.3, motion_theta=0.15)
+    # one query (fixed cloud 0) against candidates; candidate 0's moving cloud is the true match, others are
+    # scans of other rooms; guesses are perturbations of candidate 0's ground truth
+    rng = np.random.default_rng(4)
+    guesses = (sp.gt_xyt[0][None, None, :] + rng.uniform(-0.1, 0.1, (n_cand, n_guess, 3))).astype(np.float32)
+    kw = dict(canvas_cols=721, point_distance=1.414, normal_cos=0.8, cauchy_chi_threshold=0.05, max_iterations=30)
+    h = handle_factory(default_params(**kw))
+    upload(h, sp)
+    gates = Gates(300, 0.1, 0.8)
+    cand = np.arange(n_cand, dtype=np.int32)[::-1].copy()        # permuted candidate list
+    best, allr = h.verify(0, cand, guesses, gates, candidate_base=1000, want_all=True)
+    fid = np.zeros(n_cand * n_guess, np.int32)
+    mid = np.repeat(cand, n_guess)
+    o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
+                              guesses.reshape(-1, 3), fid, mid, sum_mode=oracle.SUM_TREE,
+                              tree_threads=reduction_threads(721), n_threads=oracle.max_threads())
+    assert_bit_exact(allr, o)
+    ob = oracle.best_of(o, 300, 0.1, 0.8)
+    assert ob >= 0 and cand[ob // n_guess] == 0                  # the true match wins
+    assert best["candidate"] == 1000 + ob // n_guess and best["guess"] == ob % n_guess
+    assert best["n_inliers"] == o["n_inliers"][ob] and best["x"] == o["x"][ob]
+    # impossible gates: nothing accepted
+    none = h.verify(0, cand, guesses, Gates(100000, 0.1, 0.8))
+    assert none["candidate"] == -1
+
+
+# ------------------------------------------------------------------ full-size properties (config 3 shape)
+def test_full_size_batch_properties(handle_factory, oracle):
+    """4096 pairs x 1081 beams x 10 iterations (BASELINE.json config 3) through size-independent properties:
+    run-to-run determinism, invariance to pair order, duplicates agree, a converged pose is a fixed point,
+    plus the oracle on a random sample."""
+    n = 4096
+    sp = make_scan_pairs(512, seed=0xC0FFEE)              # 512 distinct pairs, addressed 8x through id arrays
+    kw = dict(canvas_cols=1081, normal_cos=0.9)
+    h = handle_factory(default_params(**kw))
+    upload(h, sp)
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, 512, n).astype(np.int32)
+    init = np.zeros((n, 3), np.float32)
+    a = h.align_batch(init, ids, ids)
+    b = h.align_batch(init, ids, ids)
+    assert a.tobytes() == b.tobytes()                                       # deterministic
+    perm = rng.permutation(n)
+    c = h.align_batch(init[perm], ids[perm], ids[perm])
+    assert c.tobytes() == a[perm].tobytes()                                 # order-invariant
+    first = {int(i): k for k, i in reversed(list(enumerate(ids)))}
+    dup = np.array([first[int(i)] for i in ids])
+    assert a.tobytes() == a[dup].tobytes()                                  # duplicates agree
+    assert (a["status"] == 0).mean() > 0.99
+    err = np.abs(np.stack([a["x"], a["y"], a["theta"]], 1) - sp.gt_xyt[ids])
+    assert np.median(err[:, :2]) < 2e-3 and np.median(err[:, 2]) < 1e-3     # converges to ground truth
+    again = h.align_batch(np.stack([a["x"], a["y"], a["theta"]], 1), ids, ids)
+    d = np.abs(np.stack([again["x"] - a["x"], again["y"] - a["y"], again["theta"] - a["theta"]], 1))
+    assert np.percentile(d, 95) < 1e-5                                      # fixed point
+    sample = rng.choice(n, 64, replace=False)
+    o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
+                              init[sample], ids[sample], ids[sample], sum_mode=oracle.SUM_TREE,
+                              tree_threads=reduction_threads(1081), n_threads=oracle.max_threads())
+    assert_bit_exact(a[sample], o)
+
+
+def test_device_resident_path_matches_host_path(handle_factory):
+    import torch
+    sp = make_scan_pairs(64, n_beams=1081, seed=3)
+    h = handle_factory(default_params(canvas_cols=1081, normal_cos=0.9))
+    upload(h, sp)
+    ref = h.align_batch(sp.init_xyt)
+    dev = torch.device("cuda:0")
+    fp, fo = torch.from_numpy(sp.fixed_pts).to(dev), torch.from_numpy(sp.fixed_off).to(dev)
+    mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
+    init = torch.from_numpy(sp.init_xyt).to(dev)
+    out = torch.zeros(64 * 16, dtype=torch.int32, device=dev)
+    h2 = handle_factory(default_params(canvas_cols=1081, normal_cos=0.9))
+    h2.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), 64, 1081)
+    h2.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), 64, 1081)
+    h2.set_stream(torch.cuda.current_stream().cuda_stream)
+    h2.align_batch_dev(None, None, init.data_ptr(), 64, out.data_ptr())
+    torch.cuda.synchronize()
+    got = np.frombuffer(out.cpu().numpy().tobytes(), dtype=ref.dtype)
+    assert got.tobytes() == ref.tobytes()
+    one = h2.align_pairs_host(sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt)
+    assert one.tobytes() == ref.tobytes()

@@ -1,0 +1,94 @@
+"""Generates tests/golden/*.npz: small seeded inputs plus the ORACLE's outputs for them.
+
+The reference holds no golden vectors for this path and cannot be built here, so these
+fixtures freeze the oracle restatement (oracle/ls2d_oracle.c) instead: the CPU suite checks that the
+oracle still reproduces them, the GPU suite checks the CUDA path against them.  Re-run only when a
+decision point of the oracle changes on purpose:   python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_binding as ob  # noqa: E402
+from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs, reference_demo_scene  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# name -> (generator kwargs, oracle params)
+CASES = {
+    "track_1081": (dict(n_pairs=4, n_beams=1081, seed=101),
+                   dict(canvas_cols=1081, normal_cos=0.9, max_iterations=10)),
+    "track_721_l0": (dict(n_pairs=6, n_beams=721, seed=102),   # LASER_0.json tracking aligner values
+                     dict(canvas_cols=721, normal_cos=0.9, point_distance=0.5, cauchy_chi_threshold=0.01,
+                          max_iterations=10)),
+    "loop_721_l0": (dict(n_pairs=6, n_beams=721, seed=103, motion_xy=0.3, motion_theta=0.15,
+                         init_noise_xy=0.15, init_noise_theta=0.05),  # LASER_0.json loop-closure aligner values
+                    dict(canvas_cols=721, normal_cos=0.8, point_distance=1.414, cauchy_chi_threshold=0.05,
+                         max_iterations=30)),
+    "sensor_361": (dict(n_pairs=6, n_beams=361, seed=104),
+                   dict(canvas_cols=361, normal_cos=0.9, max_iterations=8, with_sensor=1,
+                        sensor_in_robot=(0.2, 0.2, 0.1))),          # synthetic_scene_generator.cpp:77
+    "norobust_361": (dict(n_pairs=6, n_beams=361, seed=105),
+                     dict(canvas_cols=361, normal_cos=0.8, cauchy_chi_threshold=-1.0, max_iterations=6,
+                          min_num_correspondences=5)),              # MULTI.json laser_1 slice: no robustifier
+}
+
+
+def params_dict(p):
+    d = {k: getattr(p, k) for k, _ in p._fields_ if k != "sensor_in_robot"}
+    d["sensor_in_robot"] = list(p.sensor_in_robot)
+    return d
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, (gen, prm_kw) in CASES.items():
+        sp = make_scan_pairs(**gen)
+        prm = ob.default_params(**prm_kw)
+        res, its = ob.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt)
+        fidx, midx, ncorr, f_src, f_depth, m_src, m_depth = [], [], [], [], [], [], []
+        for p in range(sp.n_pairs):
+            f = sp.fixed_pts[sp.fixed_off[p]:sp.fixed_off[p + 1]]
+            m = sp.moving_pts[sp.moving_off[p]:sp.moving_off[p + 1]]
+            lmis = sp.init_xyt[p]
+            if prm.with_sensor:
+                S = ob.lib().orc_inverse(ob.v2t(*prm.sensor_in_robot))
+                L = ob.lib().orc_compose(S, ob.v2t(*lmis))
+                xyt = np.zeros(3, np.float32)
+                ob.lib().orc_t2v(L, xyt.ctypes.data)
+                lmis = xyt
+            fi, mi, fimg, mimg = ob.find_correspondences(prm, f, m, lmis)
+            pad = np.full(prm.canvas_cols, -1, np.int32)
+            a, b = pad.copy(), pad.copy()
+            a[:len(fi)], b[:len(mi)] = fi, mi
+            fidx.append(a), midx.append(b), ncorr.append(len(fi))
+            f_src.append(fimg["source_idx"]), f_depth.append(fimg["depth"])
+            m_src.append(mimg["source_idx"]), m_depth.append(mimg["depth"])
+        np.savez_compressed(
+            os.path.join(OUT, name + ".npz"), fixed_pts=sp.fixed_pts, fixed_off=sp.fixed_off,
+            moving_pts=sp.moving_pts, moving_off=sp.moving_off, init_xyt=sp.init_xyt, gt_xyt=sp.gt_xyt,
+            params=np.array(repr(params_dict(prm))), results=res, iters=its,
+            corr_fixed_idx=np.stack(fidx), corr_moving_idx=np.stack(midx), corr_n=np.array(ncorr, np.int32),
+            fixed_source_idx=np.stack(f_src), fixed_depth=np.stack(f_depth),
+            moving_source_idx=np.stack(m_src), moving_depth=np.stack(m_depth), lmis_is_init=np.array(1))
+        print(name, "status", res["status"], "n_corr", res["n_corr"], "n_inl", res["n_inliers"])
+
+    # the reference's own deterministic demo world (apps/synthetic_scene_generator.cpp:36-88):
+    # 1024 bins over +-0.4 pi, range_min 0.01, projector at (0.2, 0.2, 0.1) in the robot, robot at identity
+    scene = reference_demo_scene()
+    prm = ob.default_params(canvas_cols=1024, angle_col_min=np.float32(-np.pi * 0.4), angle_col_max=np.float32(np.pi * 0.4),
+                            range_min=0.01)
+    img = ob.project(prm, (0.2, 0.2, 0.1), scene)
+    np.savez_compressed(os.path.join(OUT, "demo_scene_projection.npz"), scene=scene,
+                        params=np.array(repr(params_dict(prm))), camera_pose=np.array([0.2, 0.2, 0.1], np.float32),
+                        source_idx=img["source_idx"], depth=img["depth"])
+    print("demo scene: %d / 1024 bins hit, depth range %.3f..%.3f" % ((img["source_idx"] >= 0).sum(),
+          img["depth"][img["source_idx"] >= 0].min(), img["depth"][img["source_idx"] >= 0].max()))
+
+
+if __name__ == "__main__":
+    main()
