@@ -168,7 +168,9 @@ def run_ours(args):
     n_pairs = args.pairs
     sp = make_workload(n_pairs, 0xC0FFEE + rank, str(dev))
     h = Handle(local_rank, default_params(**TRACK))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)   # kernels and timing events share this (non-default) stream
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
 
     # ---- device-resident: clouds live in HBM, one launch per step
@@ -308,7 +310,9 @@ def run_verify(args):
     guesses = (sp.gt_xyt[0][None, None, :] + rng.uniform(-0.15, 0.15, (n_cand, n_guess, 3))).astype(np.float32)
     cand_ids = (np.arange(n_cand) % uniq).astype(np.int32)
     h = Handle(local_rank, default_params(**LOOP))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
     fp, fo = torch.from_numpy(sp.fixed_pts).to(dev), torch.from_numpy(sp.fixed_off).to(dev)
     mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)

@@ -120,42 +120,48 @@ dev_params translate(const ls2d_params& p) {
 
 // ---- kernel table: (threads, points per thread) by cloud size -------------------------------------
 struct shape {
-  int threads, ppt;
+  int threads, ppt, minb;
 };
 
 shape pick_shape(int max_points, int variant) {
-  if (max_points <= 256) return {128, 2};
-  if (max_points <= 512) return {128, 4};
-  if (max_points <= 768) return {256, 3};
+  if (max_points <= 256) return {128, 2, 6};
+  if (max_points <= 512) return {128, 4, 6};
+  if (max_points <= 768) return {256, 3, 3};
   if (max_points <= 1152) {
     switch (variant) {
-      case 1: return {128, 9};
-      case 2: return {192, 6};
-      case 3: return {256, 5};
-      default: return {384, 3};
+      case 1: return {128, 9, 4};
+      case 2: return {384, 3, 2};
+      case 3: return {256, 5, 3};
+      case 4: return {192, 6, 5};
+      case 5: return {256, 5, 4};
+      case 6: return {192, 6, 4};
+      case 7: return {128, 9, 5};
+      case 8: return {128, 9, 6};
+      default: return {384, 3, 3};  // measured best on B200 (profiles/r01_variant_sweep.md)
     }
   }
-  if (max_points <= 1536) return {256, 6};
-  if (max_points <= 2048) return {256, 8};
-  if (max_points <= 4096) return {512, 8};
-  return {0, 0};
+  if (max_points <= 1536) return {256, 6, 2};
+  if (max_points <= 2048) return {256, 8, 2};
+  if (max_points <= 4096) return {512, 8, 1};
+  return {0, 0, 0};
 }
 
-template <int T, int PPT>
-int launch_icp_t(ls2d_handle* h, const align_args& a) {
+template <int T, int PPT, bool SENSOR, int MINB>
+int launch_icp_k(ls2d_handle* h, const align_args& a) {
   const size_t smem = icp_smem_bytes(h->dp.cam.cols, T);
-  if (h->dp.with_sensor) {
-    CU(cudaFuncSetAttribute(icp_fused_kernel<T, PPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int) smem));
-    icp_fused_kernel<T, PPT, true><<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
-  } else {
-    CU(cudaFuncSetAttribute(icp_fused_kernel<T, PPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int) smem));
-    icp_fused_kernel<T, PPT, false><<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
-  }
+  auto kern         = icp_fused_kernel<T, PPT, SENSOR, MINB>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  // the kernel keeps its working set in shared memory and registers; give it the whole carve-out
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
   return LS2D_OK;
+}
+
+template <int T, int PPT, int MINB>
+int launch_icp_t(ls2d_handle* h, const align_args& a) {
+  return h->dp.with_sensor ? launch_icp_k<T, PPT, true, MINB>(h, a) : launch_icp_k<T, PPT, false, MINB>(h, a);
 }
 
 int launch_icp(ls2d_handle* h, const align_args& a) {
@@ -163,18 +169,23 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   const int maxp = h->sets[0].max_points > h->sets[1].max_points ? h->sets[0].max_points
                                                                   : h->sets[1].max_points;
   const shape s = pick_shape(maxp, h->variant);
-#define LS2D_CASE(T, P) \
-  if (s.threads == T && s.ppt == P) return launch_icp_t<T, P>(h, a);
-  LS2D_CASE(128, 2)
-  LS2D_CASE(128, 4)
-  LS2D_CASE(256, 3)
-  LS2D_CASE(384, 3)
-  LS2D_CASE(128, 9)
-  LS2D_CASE(192, 6)
-  LS2D_CASE(256, 5)
-  LS2D_CASE(256, 6)
-  LS2D_CASE(256, 8)
-  LS2D_CASE(512, 8)
+#define LS2D_CASE(T, P, B) \
+  if (s.threads == T && s.ppt == P && s.minb == B) return launch_icp_t<T, P, B>(h, a);
+  LS2D_CASE(128, 2, 6)
+  LS2D_CASE(128, 4, 6)
+  LS2D_CASE(256, 3, 3)
+  LS2D_CASE(192, 6, 4)
+  LS2D_CASE(128, 9, 4)
+  LS2D_CASE(384, 3, 2)
+  LS2D_CASE(256, 5, 3)
+  LS2D_CASE(192, 6, 5)
+  LS2D_CASE(256, 5, 4)
+  LS2D_CASE(384, 3, 3)
+  LS2D_CASE(128, 9, 5)
+  LS2D_CASE(128, 9, 6)
+  LS2D_CASE(256, 6, 2)
+  LS2D_CASE(256, 8, 2)
+  LS2D_CASE(512, 8, 1)
 #undef LS2D_CASE
   return LS2D_ERR_UNSUPPORTED;
 }

@@ -143,8 +143,8 @@ constexpr size_t icp_smem_bytes(int cols, int threads) {
   return (size_t) cols * (16 + 4 + 4 + 4) + (size_t)(threads / 32) * RED_STRIDE * 4 + sizeof(pose_bc) + 16;
 }
 
-template <int T, int PPT, bool SENSOR>
-__global__ void __launch_bounds__(T) icp_fused_kernel(const dev_params P, const align_args A) {
+template <int T, int PPT, bool SENSOR, int MINB>
+__global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, const align_args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C      = P.cam.cols;
   float4* fimg     = reinterpret_cast<float4*>(smem_raw);           // fixed image: x y nx ny per column
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(T) icp_fused_kernel(const dev_params P, const 
       float w = 1.f, chi_in = chi, chi_k = 0.f;
       if (P.tau > 0.f && !(chi < P.tau)) {  // RobustifierCauchy (L0.json:76-81)
         const float aux = fadd(fmul(chi, P.inv_tau), 1.f);
-        chi_k           = fmul(P.tau, logf(aux));
+        chi_k           = fmul(P.tau, __logf(aux));  // statistics only (tolerance parity)
         w               = fdiv(1.f, aux);
         chi_in          = 0.f;
         cnt += 1u << 16;
