@@ -1,0 +1,423 @@
+// ls2d_modules.cpp -- host logic of the CUDA-backed drop-in modules (see ls2d_modules.h).
+// Parameter gathering, argument checks with the reference's exception messages, staging of clouds, and
+// calls into the C ABI.  No arithmetic of the path is done here.
+#include "ls2d_modules.h"
+
+#include <cfloat>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+namespace srrg2_core {
+
+  Ls2dDevice::~Ls2dDevice() {
+    if (_h) ls2d_destroy(_h);
+  }
+
+  void Ls2dDevice::check(int rc, const char* where) {
+    if (rc != LS2D_OK) throw std::runtime_error(std::string(where) + "| " + ls2d_strerror(rc));
+  }
+
+  ls2d_handle* Ls2dDevice::handle() {
+    if (!_h) {
+      int device = 0;
+      if (const char* d = std::getenv("LS2D_DEVICE")) device = std::atoi(d);
+      check(ls2d_create(&_h, device), "Ls2dDevice::handle");
+    }
+    return _h;
+  }
+
+  void flattenCloud(const PointNormal2fVectorCloud& cloud, std::vector<float>& out) {
+    out.resize(cloud.size() * 4);
+    for (size_t i = 0; i < cloud.size(); ++i) {
+      const PointNormal2f& p = cloud[i];
+      if (p.status == Valid) {
+        out[4 * i + 0] = p.coordinates().x();
+        out[4 * i + 1] = p.coordinates().y();
+        out[4 * i + 2] = p.normal().x();
+        out[4 * i + 3] = p.normal().y();
+      } else {  // non-Valid points never project: encode them beyond any range_max
+        out[4 * i + 0] = 1.0e6f;
+        out[4 * i + 1] = out[4 * i + 2] = out[4 * i + 3] = 0.f;
+      }
+    }
+  }
+
+  void PointNormal2fProjectorPolar::cameraMatrix(float& K00, float& K01) const {
+    const ls2d::polar_cam k = ls2d::make_polar_cam((int) param_canvas_cols.value(), param_angle_col_min.value(),
+                                                   param_angle_col_max.value());
+    K00 = k.K00, K01 = k.K01;
+  }
+
+  void PointNormal2fProjectorPolar::fillParams(ls2d_params& p) const {
+    p.canvas_cols   = (int32_t) param_canvas_cols.value();
+    p.angle_col_min = param_angle_col_min.value();
+    p.angle_col_max = param_angle_col_max.value();
+    p.range_min     = param_range_min.value();
+    p.range_max     = param_range_max.value();
+  }
+
+  size_t PointNormal2fProjectorPolar::compute(TargetMatrixType& target, const PointNormal2f* begin,
+                                              const PointNormal2f* end) {
+    const size_t n    = (size_t)(end - begin);
+    const size_t cols = param_canvas_cols.value();
+    ls2d_params p;
+    ls2d_default_params(&p);
+    fillParams(p);
+    ls2d_handle* h = _device.handle();
+    Ls2dDevice::check(ls2d_set_params(h, &p), "PointNormal2fProjectorPolar::compute");
+    PointNormal2fVectorCloud cloud(begin, end);
+    std::vector<float> flat;
+    flattenCloud(cloud, flat);
+    const int32_t off[2] = {0, (int32_t) n};
+    Ls2dDevice::check(ls2d_upload_clouds(h, LS2D_FIXED, flat.data(), off, 1), "PointNormal2fProjectorPolar::compute");
+    const Vector3f cam = geometry2d::t2v(_camera_pose);
+    std::vector<int32_t> idx(cols);
+    std::vector<float> depth(cols);
+    Ls2dDevice::check(ls2d_project(h, LS2D_FIXED, 0, cam.v, idx.data(), depth.data()),
+                      "PointNormal2fProjectorPolar::compute");
+    target.resize(1, cols);
+    // `transformed` of the winners: same isometry, same single-rounding arithmetic as the device
+    const Isometry2f W = geometry2d::v2t(cam).inverse();
+    size_t filled      = 0;
+    for (size_t c = 0; c < cols; ++c) {
+      ProjectedEntry& e = target.at(0, c);
+      e.source_idx      = idx[c];
+      e.depth           = depth[c];
+      if (idx[c] >= 0) {
+        e.transformed.coordinates() = W * cloud[idx[c]].coordinates();
+        e.transformed.normal()      = W.rotate(cloud[idx[c]].normal());
+        ++filled;
+      }
+    }
+    return filled;
+  }
+
+}  // namespace srrg2_core
+
+namespace srrg2_solver {
+  std::ostream& operator<<(std::ostream& os, const IterationStatsVector& stats) {
+    for (const auto& s : stats)
+      os << "it= " << s.iteration << "; chi_in= " << s.chi_inliers << "; chi_k= " << s.chi_kernelized
+         << "; #in= " << s.num_inliers << "; #out= " << s.num_outliers << "; #corr= " << s.num_correspondences
+         << "\n";
+    return os;
+  }
+}  // namespace srrg2_solver
+
+namespace srrg2_laser_slam_2d {
+
+  void CorrespondenceFinderProjective2f::fillParams(ls2d_params& p) const {
+    if (param_projector.value()) param_projector->fillParams(p);
+    p.point_distance = param_point_distance.value();
+    p.normal_cos     = param_normal_cos.value();
+  }
+
+  // same checks, same messages, same caching and the same side effect on the shared projector as
+  // R/registration/correspondence_finder_projective_2d.cpp:18-77
+  void CorrespondenceFinderProjective2f::compute() {
+    PointNormal2fProjectorPolarPtr projector = param_projector.value();
+    if (!projector) throw std::runtime_error("CorrespondenceFinderProjective2f::compute| Missing Projector");
+    if (!_fixed) throw std::runtime_error("CorrespondenceFinderProjective2f::compute| Missing fixed!");
+    if (!_moving) throw std::runtime_error("CorrespondenceFinderProjective2f::compute| Missing moving!");
+    if (!_correspondences)
+      throw std::runtime_error("CorrespondenceFinderProjective2f::compute| Missing correspondences!");
+    const int num_beams = (int) projector->param_canvas_cols.value();
+    ls2d_handle* h      = _device.handle();
+    ls2d_params p;
+    ls2d_default_params(&p);
+    fillParams(p);
+    Ls2dDevice::check(ls2d_set_params(h, &p), "CorrespondenceFinderProjective2f::compute");
+    if (_fixed_changed_flag || _projector_changed_flag) {  // .cpp:37-44: the fixed image is cached
+      flattenCloud(*_fixed, _staging);
+      const int32_t off[2] = {0, (int32_t) _fixed->size()};
+      Ls2dDevice::check(ls2d_upload_clouds(h, LS2D_FIXED, _staging.data(), off, 1),
+                        "CorrespondenceFinderProjective2f::compute");
+      _fixed_changed_flag     = false;
+      _projector_changed_flag = false;
+    }
+    projector->setCameraPose(_local_map_in_sensor.inverse());  // .cpp:47 (visible to whoever shares the projector)
+    flattenCloud(*_moving, _staging);
+    const int32_t off[2] = {0, (int32_t) _moving->size()};
+    Ls2dDevice::check(ls2d_upload_clouds(h, LS2D_MOVING, _staging.data(), off, 1),
+                      "CorrespondenceFinderProjective2f::compute");
+    std::vector<int32_t> fi(num_beams), mi(num_beams);
+    int32_t n          = 0;
+    const Vector3f xyt = geometry2d::t2v(_local_map_in_sensor);
+    Ls2dDevice::check(ls2d_find_correspondences(h, 0, 0, xyt.v, fi.data(), mi.data(), &n),
+                      "CorrespondenceFinderProjective2f::compute");
+    _correspondences->resize(n);
+    for (int k = 0; k < n; ++k) (*_correspondences)[k] = Correspondence(fi[k], mi[k]);
+  }
+
+  void AlignerSliceProcessorLaser2DWithSensor::setupFactor() {
+    (void) sensorInRobot();  // throws when the tf lookup fails, like setupFactorWithSensor
+  }
+
+  void srrg2_laser_slam_2d_registerTypes() {
+    using namespace srrg2_core;
+    using namespace srrg2_solver;
+    using namespace srrg2_slam_interfaces;
+    // upstream *_registerTypes() of R/instances.cpp:21-25, reduced to the classes on the hot path
+    BOSS_REGISTER_CLASS(PointNormal2fProjectorPolar);
+    BOSS_REGISTER_CLASS(RobustifierCauchy);
+    BOSS_REGISTER_CLASS(IterationAlgorithmGN);
+    BOSS_REGISTER_CLASS(SparseBlockLinearSolverCholmodFull);
+    BOSS_REGISTER_CLASS(SparseBlockLinearSolverCholeskyCSparse);
+    BOSS_REGISTER_CLASS(SimpleTerminationCriteria);
+    BOSS_REGISTER_CLASS(Solver);
+    BOSS_REGISTER_CLASS(AlignerSliceOdom2DPrior);
+    BOSS_REGISTER_CLASS(MultiAligner2D);
+    BOSS_REGISTER_CLASS(MultiLoopDetectorBruteForce2D);
+    // R/instances.cpp:27,34,35
+    BOSS_REGISTER_CLASS(CorrespondenceFinderProjective2f);
+    BOSS_REGISTER_CLASS(AlignerSliceProcessorLaser2D);
+    BOSS_REGISTER_CLASS(AlignerSliceProcessorLaser2DWithSensor);
+    // explicit CUDA names, for configurations that want to say so
+    BOSS_REGISTER_CLASS_AS(CorrespondenceFinderProjective2f, "CorrespondenceFinderProjective2fCUDA");
+    BOSS_REGISTER_CLASS_AS(AlignerSliceProcessorLaser2D, "AlignerSliceProcessorLaser2DCUDA");
+    BOSS_REGISTER_CLASS_AS(AlignerSliceProcessorLaser2DWithSensor, "AlignerSliceProcessorLaser2DWithSensorCUDA");
+    BOSS_REGISTER_CLASS_AS(MultiAligner2D, "MultiAligner2DCUDA");
+  }
+
+}  // namespace srrg2_laser_slam_2d
+
+namespace srrg2_slam_interfaces {
+  using srrg2_laser_slam_2d::CorrespondenceFinderProjective2f;
+
+  Isometry2f AlignerSliceProcessorLaserBase::sensorInRobot() const {
+    if (!withSensor()) return Isometry2f::Identity();
+    if (!_platform) throw std::runtime_error("AlignerSliceProcessor::setupFactorWithSensor| no platform set");
+    Isometry2f S;
+    if (!_platform->getTransform(S, param_frame_id.value(), param_base_frame_id.value()))
+      throw std::runtime_error("AlignerSliceProcessor::setupFactorWithSensor| unable to find transform [" +
+                               param_frame_id.value() + "] in [" + param_base_frame_id.value() + "]");
+    return S;
+  }
+
+  std::shared_ptr<AlignerSliceProcessorLaserBase> MultiAligner2D::laserSlice() {
+    std::shared_ptr<AlignerSliceProcessorLaserBase> laser;
+    for (size_t i = 0; i < param_slice_processors.size(); ++i) {
+      const AlignerSliceProcessorBasePtr& s = param_slice_processors.value(i);
+      if (!s) continue;
+      if (s->isLaserSlice()) {
+        if (laser)
+          throw std::runtime_error("MultiAligner2D::compute| more than one laser slice is not supported by the "
+                                   "CUDA aligner yet (multi-slice fused solve: SURVEY.md 8f-4)");
+        laser = std::dynamic_pointer_cast<AlignerSliceProcessorLaserBase>(s);
+      } else {
+        // a prior slice contributes only if its data is present in both scenes
+        const bool bound = _fixed_scene && _moving_scene && _fixed_scene->cloud(s->param_fixed_slice_name.value()) &&
+                           _moving_scene->cloud(s->param_moving_slice_name.value());
+        if (bound)
+          throw std::runtime_error("MultiAligner2D::compute| slice \"" + s->className() +
+                                   "\" is not supported by the CUDA aligner yet (SURVEY.md 8f-4)");
+      }
+    }
+    if (!laser) throw std::runtime_error("MultiAligner2D::compute| no slice processor set");
+    return laser;
+  }
+
+  void MultiAligner2D::fillParams(ls2d_params& p) {
+    ls2d_default_params(&p);
+    std::shared_ptr<AlignerSliceProcessorLaserBase> slice = laserSlice();
+    auto finder = std::dynamic_pointer_cast<CorrespondenceFinderProjective2f>(slice->param_finder.value());
+    if (!finder)
+      throw std::runtime_error("MultiAligner2D::compute| the CUDA aligner needs a CorrespondenceFinderProjective2f "
+                               "finder on its laser slice");
+    if (!finder->param_projector.value())
+      throw std::runtime_error("CorrespondenceFinderProjective2f::compute| Missing Projector");
+    finder->fillParams(p);
+    auto cauchy = std::dynamic_pointer_cast<srrg2_solver::RobustifierCauchy>(slice->param_robustifier.value());
+    if (slice->param_robustifier.value() && !cauchy)
+      throw std::runtime_error("MultiAligner2D::compute| only RobustifierCauchy is supported");
+    p.cauchy_chi_threshold    = cauchy ? cauchy->param_chi_threshold.value() : -1.f;
+    p.min_num_correspondences = slice->param_min_num_correspondences.value();
+    p.max_iterations          = param_max_iterations.value();
+    p.min_num_inliers         = param_min_num_inliers.value();
+    p.damping                 = 0.f;
+    if (auto solver = param_solver.value()) {
+      if (solver->param_max_iterations.size() && solver->param_max_iterations.value(0) != 1)
+        throw std::runtime_error("MultiAligner2D::compute| the inner solver must run 1 iteration per ICP round "
+                                 "(both shipped configurations do)");
+      if (auto gn = std::dynamic_pointer_cast<srrg2_solver::IterationAlgorithmGN>(solver->param_algorithm.value()))
+        p.damping = gn->param_damping.value();
+      else if (solver->param_algorithm.value())
+        throw std::runtime_error("MultiAligner2D::compute| only IterationAlgorithmGN is supported");
+    }
+    if (param_enable_inlier_only_runs.value() || param_keep_only_inlier_correspondences.value())
+      throw std::runtime_error("MultiAligner2D::compute| inlier-only runs are not supported (both shipped "
+                               "configurations disable them)");
+    if (param_termination_criteria.value())
+      throw std::runtime_error("MultiAligner2D::compute| aligner termination criteria are not supported (both "
+                               "shipped configurations leave them unset)");
+    p.with_sensor = slice->withSensor() ? 1 : 0;
+    if (p.with_sensor) {
+      slice->setupFactor();
+      const Vector3f s = geometry2d::t2v(slice->sensorInRobot());
+      std::memcpy(p.sensor_in_robot, s.v, sizeof(float) * 3);
+    }
+  }
+
+  static AlignmentResult toResult(const ls2d_result& r) {
+    AlignmentResult a;
+    a.estimate        = Vector3f(r.x, r.y, r.theta);
+    a.moving_in_fixed = geometry2d::v2t(a.estimate);
+    a.status          = r.status;
+    a.iterations      = r.iterations;
+    a.last.iteration           = r.iterations - 1;
+    a.last.chi_inliers         = r.chi_inliers;
+    a.last.chi_kernelized      = r.chi_kernelized;
+    a.last.num_inliers         = r.n_inliers;
+    a.last.num_outliers        = r.n_kernelized;
+    a.last.num_correspondences = r.n_corr;
+    a.last.estimate            = a.estimate;
+    const int map[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) a.information_matrix.m[i][j] = r.H[map[i][j]];
+    return a;
+  }
+
+  static void uploadSet(ls2d_handle* h, int which, const std::vector<const PointNormal2fVectorCloud*>& clouds,
+                        const char* where) {
+    std::vector<int32_t> off(clouds.size() + 1, 0);
+    for (size_t i = 0; i < clouds.size(); ++i) {
+      if (!clouds[i]) throw std::runtime_error(std::string(where) + "| null cloud in batch");
+      off[i + 1] = off[i] + (int32_t) clouds[i]->size();
+    }
+    std::vector<float> flat((size_t) off.back() * 4), one;
+    for (size_t i = 0; i < clouds.size(); ++i) {
+      flattenCloud(*clouds[i], one);
+      if (!one.empty()) std::memcpy(flat.data() + (size_t) off[i] * 4, one.data(), one.size() * sizeof(float));
+    }
+    Ls2dDevice::check(ls2d_upload_clouds(h, which, flat.data(), off.data(), (int32_t) clouds.size()), where);
+  }
+
+  void MultiAligner2D::compute() {
+    _status = Fail;
+    _iteration_stats.clear();
+    if (!_fixed_scene) throw std::runtime_error("MultiAligner2D::compute| Missing fixed!");
+    if (!_moving_scene) throw std::runtime_error("MultiAligner2D::compute| Missing moving!");
+    ls2d_params p;
+    fillParams(p);
+    std::shared_ptr<AlignerSliceProcessorLaserBase> slice = laserSlice();
+    PointNormal2fVectorCloud* fixed  = _fixed_scene->cloud(slice->param_fixed_slice_name.value());
+    PointNormal2fVectorCloud* moving = _moving_scene->cloud(slice->param_moving_slice_name.value());
+    if (!fixed) throw std::runtime_error("MultiAligner2D::compute| fixed scene has no slice \"" +
+                                         slice->param_fixed_slice_name.value() + "\"");
+    if (!moving) throw std::runtime_error("MultiAligner2D::compute| moving scene has no slice \"" +
+                                          slice->param_moving_slice_name.value() + "\"");
+    slice->_fixed  = fixed;
+    slice->_moving = moving;
+    ls2d_handle* h = _device.handle();
+    Ls2dDevice::check(ls2d_set_params(h, &p), "MultiAligner2D::compute");
+    uploadSet(h, LS2D_FIXED, {fixed}, "MultiAligner2D::compute");
+    uploadSet(h, LS2D_MOVING, {moving}, "MultiAligner2D::compute");
+    const Vector3f init = geometry2d::t2v(_moving_in_fixed);
+    ls2d_result r;
+    std::vector<ls2d_iter_stats> its((size_t) (p.max_iterations > 0 ? p.max_iterations : 1));
+    Ls2dDevice::check(ls2d_align_batch(h, nullptr, nullptr, init.v, 1, &r, its.data()), "MultiAligner2D::compute");
+    const AlignmentResult a = toResult(r);
+    _moving_in_fixed        = a.moving_in_fixed;
+    _information_matrix     = a.information_matrix;
+    _status                 = r.status == LS2D_STATUS_SUCCESS ? Success
+                              : r.status == LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES ? NotEnoughCorrespondences
+                              : r.status == LS2D_STATUS_NOT_ENOUGH_INLIERS ? NotEnoughInliers : Fail;
+    for (int i = 0; i < r.iterations; ++i) {
+      srrg2_solver::IterationStats s;
+      s.iteration           = i;
+      s.chi_inliers         = its[i].chi_inliers;
+      s.chi_kernelized      = its[i].chi_kernelized;
+      s.num_inliers         = its[i].n_inliers;
+      s.num_outliers        = its[i].n_kernelized;
+      s.num_correspondences = its[i].n_corr;
+      s.estimate            = Vector3f(its[i].x, its[i].y, its[i].theta);
+      _iteration_stats.push_back(s);
+    }
+    // slice->correspondences(): those of the last iteration, i.e. found at the estimate before its update
+    Vector3f before = init;
+    if (r.iterations >= 2) before = _iteration_stats[r.iterations - 2].estimate;
+    Isometry2f lmis = geometry2d::v2t(before);
+    if (p.with_sensor) lmis = slice->sensorInRobot().inverse() * lmis;
+    const Vector3f lv = geometry2d::t2v(lmis);
+    std::vector<int32_t> fi(p.canvas_cols), mi(p.canvas_cols);
+    int32_t n = 0;
+    Ls2dDevice::check(ls2d_find_correspondences(h, 0, 0, lv.v, fi.data(), mi.data(), &n), "MultiAligner2D::compute");
+    slice->_correspondences.resize(n);
+    for (int k = 0; k < n; ++k) slice->_correspondences[k] = Correspondence(fi[k], mi[k]);
+  }
+
+  void MultiAligner2D::computeBatch(const std::vector<const PointNormal2fVectorCloud*>& fixed,
+                                    const std::vector<const PointNormal2fVectorCloud*>& moving,
+                                    const std::vector<Isometry2f>& guesses, std::vector<AlignmentResult>& results) {
+    if (fixed.size() != moving.size() || fixed.size() != guesses.size())
+      throw std::runtime_error("MultiAligner2D::computeBatch| fixed, moving and guesses differ in size");
+    ls2d_params p;
+    fillParams(p);
+    ls2d_handle* h = _device.handle();
+    Ls2dDevice::check(ls2d_set_params(h, &p), "MultiAligner2D::computeBatch");
+    uploadSet(h, LS2D_FIXED, fixed, "MultiAligner2D::computeBatch");
+    uploadSet(h, LS2D_MOVING, moving, "MultiAligner2D::computeBatch");
+    std::vector<float> init(guesses.size() * 3);
+    for (size_t i = 0; i < guesses.size(); ++i) {
+      const Vector3f v = geometry2d::t2v(guesses[i]);
+      std::memcpy(&init[3 * i], v.v, sizeof(float) * 3);
+    }
+    std::vector<ls2d_result> out(guesses.size());
+    Ls2dDevice::check(ls2d_align_batch(h, nullptr, nullptr, init.data(), (int32_t) guesses.size(), out.data(), nullptr),
+                      "MultiAligner2D::computeBatch");
+    results.clear();
+    for (const auto& r : out) results.push_back(toResult(r));
+  }
+
+  LoopClosure2D MultiLoopDetectorBruteForce2D::verify(const PointNormal2fVectorCloud& query,
+                                                      const std::vector<const PointNormal2fVectorCloud*>& candidates,
+                                                      const std::vector<std::vector<Isometry2f>>& guesses,
+                                                      std::vector<AlignmentResult>* all) {
+    MultiAligner2DPtr aligner = param_relocalize_aligner.value();
+    if (!aligner) throw std::runtime_error("MultiLoopDetectorBruteForce2D::compute| relocalize_aligner not set");
+    if (candidates.size() != guesses.size() || candidates.empty())
+      throw std::runtime_error("MultiLoopDetectorBruteForce2D::compute| candidates and guesses differ in size");
+    const size_t n_guess = guesses[0].size();
+    for (const auto& g : guesses)
+      if (g.size() != n_guess || n_guess == 0)
+        throw std::runtime_error("MultiLoopDetectorBruteForce2D::compute| every candidate needs the same, non-zero, "
+                                 "number of initial guesses");
+    ls2d_params p;
+    aligner->fillParams(p);
+    ls2d_handle* h = aligner->device().handle();
+    Ls2dDevice::check(ls2d_set_params(h, &p), "MultiLoopDetectorBruteForce2D::compute");
+    uploadSet(h, LS2D_FIXED, {&query}, "MultiLoopDetectorBruteForce2D::compute");
+    uploadSet(h, LS2D_MOVING, candidates, "MultiLoopDetectorBruteForce2D::compute");
+    std::vector<float> init(candidates.size() * n_guess * 3);
+    for (size_t c = 0; c < candidates.size(); ++c)
+      for (size_t g = 0; g < n_guess; ++g) {
+        const Vector3f v = geometry2d::t2v(guesses[c][g]);
+        std::memcpy(&init[3 * (c * n_guess + g)], v.v, sizeof(float) * 3);
+      }
+    ls2d_gates gates;
+    gates.min_inliers        = param_relocalize_min_inliers.value();
+    gates.max_chi_per_inlier = param_relocalize_max_chi_inliers.value();
+    gates.min_inlier_ratio   = param_relocalize_min_inliers_ratio.value();
+    ls2d_best best;
+    std::vector<ls2d_result> out(all ? candidates.size() * n_guess : 0);
+    Ls2dDevice::check(ls2d_verify(h, 0, nullptr, (int32_t) candidates.size(), init.data(), (int32_t) n_guess, &gates, 0,
+                                  &best, all ? out.data() : nullptr),
+                      "MultiLoopDetectorBruteForce2D::compute");
+    if (all) {
+      all->clear();
+      for (const auto& r : out) all->push_back(toResult(r));
+    }
+    LoopClosure2D lc;
+    lc.candidate = best.candidate;
+    lc.guess     = best.guess;
+    if (best.candidate >= 0) {
+      lc.moving_in_fixed     = geometry2d::v2t(Vector3f(best.x, best.y, best.theta));
+      lc.chi_inliers         = best.chi_inliers;
+      lc.num_inliers         = best.n_inliers;
+      lc.num_correspondences = best.n_corr;
+    }
+    return lc;
+  }
+
+}  // namespace srrg2_slam_interfaces

@@ -1,0 +1,365 @@
+// ls2d_modules.h -- CUDA-backed drop-ins for the reference's hot-path modules, with the reference's class
+// names, PARAM names, method names, ownership and error behaviour, so that the reference's configuration
+// files instantiate THESE classes unchanged.  Every compute() forwards to the C ABI of include/ls2d.h;
+// there is no host implementation of the path in here.
+//
+// Reference interfaces mirrored (R/ = /root/reference/srrg2_laser_slam_2d/src/srrg2_laser_slam_2d/):
+//   PointNormal2fProjectorPolar            params L0.json:312-338; use R/registration/correspondence_finder_projective_2d.cpp:35-48
+//   CorrespondenceFinderProjective2f       R/registration/correspondence_finder_projective_2d.{h,cpp}
+//   AlignerSliceProcessorLaser2D[WithSensor]  R/registration/aligner_slice_processor_laser_2d.h:7-45, _impl.cpp:7-10
+//   MultiAligner2D                         driven at apps/visual_test_aligner_2d.cpp:123-156; params L0.json:9-37
+//   RobustifierCauchy / IterationAlgorithmGN / Solver / ...   parameter holders, L0.json:76-88,193-289
+//   MultiLoopDetectorBruteForce2D          gates L0.json:613-635
+#pragma once
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ls2d.h"
+#include "ls2d_boss.h"
+#include "ls2d_types.h"
+
+namespace srrg2_core {
+
+  // owns one ls2d_handle; created on first use (device from $LS2D_DEVICE, default 0); throws
+  // std::runtime_error when the CUDA library reports an error -- there is no CPU fallback
+  class Ls2dDevice {
+  public:
+    Ls2dDevice() {}
+    ~Ls2dDevice();
+    Ls2dDevice(const Ls2dDevice&)            = delete;
+    Ls2dDevice& operator=(const Ls2dDevice&) = delete;
+    ls2d_handle* handle();
+    static void check(int rc, const char* where);
+
+  private:
+    ls2d_handle* _h = nullptr;
+  };
+
+  // flat (x, y, nx, ny) staging of a cloud for ls2d_upload_clouds
+  void flattenCloud(const PointNormal2fVectorCloud& cloud, std::vector<float>& out);
+
+  // 1 x cols image of {source_idx, depth, transformed}  (PointNormal2fProjectorPolar::TargetMatrixType)
+  struct ProjectedEntry {
+    int source_idx = -1;
+    float depth    = 0.f;
+    PointNormal2f transformed;
+  };
+  class ProjectedMatrix {
+  public:
+    void resize(size_t rows, size_t cols) {
+      _rows = rows, _cols = cols;
+      _data.assign(rows * cols, ProjectedEntry());
+    }
+    void clear() { _data.clear(), _rows = _cols = 0; }
+    size_t rows() const { return _rows; }
+    size_t cols() const { return _cols; }
+    ProjectedEntry& at(size_t r, size_t c) { return _data.at(r * _cols + c); }
+    const ProjectedEntry& at(size_t r, size_t c) const { return _data.at(r * _cols + c); }
+    std::vector<ProjectedEntry>::iterator begin() { return _data.begin(); }
+    std::vector<ProjectedEntry>::iterator end() { return _data.end(); }
+
+  private:
+    size_t _rows = 0, _cols = 0;
+    std::vector<ProjectedEntry> _data;
+  };
+
+  class PointNormal2fProjectorPolar : public Configurable {
+  public:
+    using TargetMatrixType = ProjectedMatrix;
+    PARAM(PropertyFloat, angle_col_max, "end col angle    [rad]", 3.14159f, &_config_changed);
+    PARAM(PropertyFloat, angle_col_min, "start col angle  [rad]", -3.14159f, &_config_changed);
+    PARAM(PropertyFloat, angle_row_max, "end row angle    [rad]", 1.5708f, 0);
+    PARAM(PropertyFloat, angle_row_min, "start row angle  [rad]", -1.5708f, 0);
+    PARAM(PropertyUnsignedInt, canvas_cols, "cols of the canvas", 721, &_config_changed);
+    PARAM(PropertyUnsignedInt, canvas_rows, "rows of the canvas", 1, 0);
+    PARAM(PropertyFloat, range_max, "maximum range [m]", 20.f, &_config_changed);
+    PARAM(PropertyFloat, range_min, "minimum range [m]", 0.3f, &_config_changed);
+    PointNormal2fProjectorPolar() { _class_name = "PointNormal2fProjectorPolar"; }
+
+    void setCameraPose(const Isometry2f& camera_pose) { _camera_pose = camera_pose; }
+    const Isometry2f& cameraPose() const { return _camera_pose; }
+    void initCameraMatrix() {}
+    // [[K00, K01], [0, 1]] with K00 = cols / (angle_col_max - angle_col_min), K01 = cols / 2
+    void cameraMatrix(float& K00, float& K01) const;
+    // project [begin, end) into `target` (resized to 1 x canvas_cols); returns the number of filled cells
+    size_t compute(TargetMatrixType& target, const PointNormal2f* begin, const PointNormal2f* end);
+    size_t compute(TargetMatrixType& target, PointNormal2fVectorCloud::const_iterator begin,
+                   PointNormal2fVectorCloud::const_iterator end) {
+      return compute(target, begin == end ? nullptr : &*begin, begin == end ? nullptr : &*begin + (end - begin));
+    }
+    void fillParams(ls2d_params& p) const;
+
+  protected:
+    bool _config_changed = true;
+    Isometry2f _camera_pose;
+    Ls2dDevice _device;
+  };
+  using PointNormal2fProjectorPolarPtr = std::shared_ptr<PointNormal2fProjectorPolar>;
+
+}  // namespace srrg2_core
+
+namespace srrg2_solver {
+  using namespace srrg2_core;
+
+  class RobustifierBase : public Configurable {};
+  class RobustifierCauchy : public RobustifierBase {
+  public:
+    PARAM(PropertyFloat, chi_threshold, "threshold of chi after which the kernel is active", 1.f, 0);
+    RobustifierCauchy() { _class_name = "RobustifierCauchy"; }
+  };
+  class IterationAlgorithmBase : public Configurable {};
+  class IterationAlgorithmGN : public IterationAlgorithmBase {
+  public:
+    PARAM(PropertyFloat, damping, "damping factor, the higher the closer to gradient descend. Default:0", 0.f, 0);
+    IterationAlgorithmGN() { _class_name = "IterationAlgorithmGN"; }
+  };
+  class SparseBlockLinearSolver : public Configurable {};
+  class SparseBlockLinearSolverCholmodFull : public SparseBlockLinearSolver {
+  public:
+    SparseBlockLinearSolverCholmodFull() { _class_name = "SparseBlockLinearSolverCholmodFull"; }
+  };
+  class SparseBlockLinearSolverCholeskyCSparse : public SparseBlockLinearSolver {
+  public:
+    SparseBlockLinearSolverCholeskyCSparse() { _class_name = "SparseBlockLinearSolverCholeskyCSparse"; }
+  };
+  class TerminationCriteria : public Configurable {};
+  class SimpleTerminationCriteria : public TerminationCriteria {
+  public:
+    PARAM(PropertyFloat, epsilon, "ratio of decay of chi2 between iteration", 1e-3f, 0);
+    SimpleTerminationCriteria() { _class_name = "SimpleTerminationCriteria"; }
+  };
+  class Solver : public Configurable {
+  public:
+    PARAM(PropertyConfigurable_<IterationAlgorithmBase>, algorithm,
+          "pointer to the optimization algorithm (GN/LM or others)", nullptr, 0);
+    PARAM(PropertyConfigurable_<SparseBlockLinearSolver>, linear_solver,
+          "pointer to linear solver used to compute Hx=b", nullptr, 0);
+    PARAM_VECTOR(PropertyVector_<int>, max_iterations, "maximum iterations if no stopping criteria is set", 0);
+    PARAM(PropertyFloat, mse_threshold, "Minimum mean square error variation to perform global optimization", -1.f, 0);
+    PARAM(PropertyConfigurable_<TerminationCriteria>, termination_criteria,
+          "term criteria ptr, if 0 solver will do max iterations", nullptr, 0);
+    Solver() { _class_name = "Solver"; }
+  };
+
+  // one entry of MultiAligner2D::iterationStats() (apps/visual_test_aligner_2d.cpp:156)
+  struct IterationStats {
+    int iteration        = 0;
+    float chi_inliers    = 0.f;
+    float chi_kernelized = 0.f;
+    int num_inliers      = 0;
+    int num_outliers     = 0;  // kernelized factors
+    int num_correspondences = 0;
+    Vector3f estimate;         // t2v of the estimate after this iteration
+  };
+  using IterationStatsVector = std::vector<IterationStats>;
+  std::ostream& operator<<(std::ostream& os, const IterationStatsVector& stats);
+
+}  // namespace srrg2_solver
+
+namespace srrg2_laser_slam_2d {
+  using namespace srrg2_core;
+
+  // CorrespondenceFinder_<Isometry2f, PointNormal2fVectorCloud, PointNormal2fVectorCloud>
+  // (R/registration/correspondence_finder_normal_2f.h:9-12)
+  class CorrespondenceFinderNormal2f : public Configurable {
+  public:
+    void setFixed(const PointNormal2fVectorCloud* fixed) {
+      _fixed              = fixed;
+      _fixed_changed_flag = true;
+    }
+    void setMoving(const PointNormal2fVectorCloud* moving) { _moving = moving; }
+    void setLocalMapInSensor(const Isometry2f& T) { _local_map_in_sensor = T; }
+    void setCorrespondences(CorrespondenceVector* c) { _correspondences = c; }
+    virtual void compute() = 0;
+
+  protected:
+    const PointNormal2fVectorCloud* _fixed  = nullptr;
+    const PointNormal2fVectorCloud* _moving = nullptr;
+    Isometry2f _local_map_in_sensor;
+    CorrespondenceVector* _correspondences = nullptr;
+    bool _fixed_changed_flag               = true;
+  };
+  using CorrespondenceFinderNormal2fPtr = std::shared_ptr<CorrespondenceFinderNormal2f>;
+
+  class CorrespondenceFinderProjective2f : public CorrespondenceFinderNormal2f {
+  public:
+    PARAM(PropertyFloat, point_distance, "max distance between corresponding points", 0.5f, 0);
+    PARAM(PropertyFloat, normal_cos, "min cosinus between normals", 0.8f, 0);
+    PARAM(PropertyConfigurable_<PointNormal2fProjectorPolar>, projector, "projector to compute correspondences",
+          PointNormal2fProjectorPolarPtr(new PointNormal2fProjectorPolar), &_projector_changed_flag);
+    CorrespondenceFinderProjective2f() { _class_name = "CorrespondenceFinderProjective2f"; }
+    void compute() override;
+    void fillParams(ls2d_params& p) const;
+
+  protected:
+    bool _projector_changed_flag = true;
+    Ls2dDevice _device;
+    std::vector<float> _staging;
+  };
+  using CorrespondenceFinderProjective2DPtr = std::shared_ptr<CorrespondenceFinderProjective2f>;
+
+}  // namespace srrg2_laser_slam_2d
+
+namespace srrg2_slam_interfaces {
+  using namespace srrg2_core;
+
+  // common part of AlignerSliceProcessor_<Factor, Fixed, Moving> (params L0.json:115-143)
+  class AlignerSliceProcessorBase : public Configurable {
+  public:
+    PARAM(PropertyString, base_frame_id, "name of the base frame in the tf tree", "", 0);
+    PARAM(PropertyString, fixed_slice_name, "name of the slice in the fixed scene", "", 0);
+    PARAM(PropertyString, frame_id, "name of the sensor's frame in the tf tree", "", 0);
+    PARAM(PropertyString, moving_slice_name, "name of the slice in the moving scene", "", 0);
+    PARAM(PropertyConfigurable_<srrg2_solver::RobustifierBase>, robustifier, "robustifier used on this slice",
+          nullptr, 0);
+    void setPlatform(const PlatformPtr& platform) { _platform = platform; }
+    virtual bool isLaserSlice() const { return false; }
+
+  protected:
+    PlatformPtr _platform;
+  };
+  using AlignerSliceProcessorBasePtr = std::shared_ptr<AlignerSliceProcessorBase>;
+
+  // prior slices are parameter holders in this build
+  class AlignerSliceOdom2DPrior : public AlignerSliceProcessorBase {
+  public:
+    AlignerSliceOdom2DPrior() { _class_name = "AlignerSliceOdom2DPrior"; }
+  };
+
+  class AlignerSliceProcessorLaserBase : public AlignerSliceProcessorBase {
+  public:
+    PARAM(PropertyConfigurable_<srrg2_laser_slam_2d::CorrespondenceFinderNormal2f>, finder,
+          "correspondence finder used in this cue", nullptr, 0);
+    PARAM(PropertyInt, min_num_correspondences, "minimum number of correspondences in this slice", 0, 0);
+    bool isLaserSlice() const override { return true; }
+    virtual bool withSensor() const { return false; }
+    // sensor_in_robot of this slice (identity unless WithSensor); throws if the tf lookup fails
+    Isometry2f sensorInRobot() const;
+    const CorrespondenceVector& correspondences() const { return _correspondences; }
+    const PointNormal2fVectorCloud* fixed() const { return _fixed; }
+    const PointNormal2fVectorCloud* moving() const { return _moving; }
+
+  protected:
+    friend class MultiAligner2D;
+    virtual void setupFactor() {}
+    CorrespondenceVector _correspondences;
+    const PointNormal2fVectorCloud* _fixed  = nullptr;
+    const PointNormal2fVectorCloud* _moving = nullptr;
+  };
+
+  struct AlignmentResult {
+    Isometry2f moving_in_fixed;
+    Vector3f estimate;  // t2v(moving_in_fixed)
+    int status = 0;
+    srrg2_solver::IterationStats last;
+    Matrix3f information_matrix;
+    int iterations = 0;
+  };
+
+  class MultiAligner2D : public Configurable {
+  public:
+    enum Status { Success = 0, NotEnoughCorrespondences = 1, NotEnoughInliers = 2, Fail = 3 };
+    PARAM(PropertyBool, enable_inlier_only_runs,
+          "toggles additional inlier only runs if sufficient inliers are available", false, 0);
+    PARAM(PropertyBool, keep_only_inlier_correspondences,
+          "toggles removal of correspondences which factors are not inliers in the last iteration", false, 0);
+    PARAM(PropertyInt, max_iterations, "maximum number of iterations", 10, 0);
+    PARAM(PropertyInt, min_num_inliers, "minimum number ofinliers", 10, 0);
+    PARAM_VECTOR(PropertyConfigurableVector_<AlignerSliceProcessorBase>, slice_processors, "slices", 0);
+    PARAM(PropertyConfigurable_<srrg2_solver::Solver>, solver, "this solver", nullptr, 0);
+    PARAM(PropertyConfigurable_<srrg2_solver::TerminationCriteria>, termination_criteria,
+          "termination criteria, not set=max iterations", nullptr, 0);
+    MultiAligner2D() { _class_name = "MultiAligner2D"; }
+
+    void setFixed(PropertyContainerDynamic* fixed) { _fixed_scene = fixed; }
+    void setMoving(PropertyContainerDynamic* moving) { _moving_scene = moving; }
+    void setMovingInFixed(const Isometry2f& T) { _moving_in_fixed = T; }
+    void compute();
+    const Isometry2f& movingInFixed() const { return _moving_in_fixed; }
+    Status status() const { return _status; }
+    int numInliers() const { return _iteration_stats.empty() ? 0 : _iteration_stats.back().num_inliers; }
+    const srrg2_solver::IterationStatsVector& iterationStats() const { return _iteration_stats; }
+    const Matrix3f& informationMatrix() const { return _information_matrix; }
+
+    // ---- batched extension: pair p aligns *moving[p] onto *fixed[p] from guesses[p] in ONE launch
+    void computeBatch(const std::vector<const PointNormal2fVectorCloud*>& fixed,
+                      const std::vector<const PointNormal2fVectorCloud*>& moving,
+                      const std::vector<Isometry2f>& guesses, std::vector<AlignmentResult>& results);
+
+    // the complete parameter set this aligner hands to the C ABI (public for tests / tools)
+    void fillParams(ls2d_params& p);
+    Ls2dDevice& device() { return _device; }
+
+  protected:
+    std::shared_ptr<AlignerSliceProcessorLaserBase> laserSlice();
+    PropertyContainerDynamic* _fixed_scene  = nullptr;
+    PropertyContainerDynamic* _moving_scene = nullptr;
+    Isometry2f _moving_in_fixed;
+    Status _status = Fail;
+    srrg2_solver::IterationStatsVector _iteration_stats;
+    Matrix3f _information_matrix;
+    Ls2dDevice _device;
+  };
+  using MultiAligner2DPtr = std::shared_ptr<MultiAligner2D>;
+
+  // result of a verified loop closure
+  struct LoopClosure2D {
+    int candidate = -1;  // index into the candidate list, -1: nothing accepted
+    int guess     = -1;
+    Isometry2f moving_in_fixed;
+    float chi_inliers = 0.f;
+    int num_inliers = 0, num_correspondences = 0;
+  };
+
+  // the candidate-verification part of MultiLoopDetectorBruteForce2D (L0.json:613-635): aligns the query
+  // local map against every candidate from every initial guess in one batched launch and applies the
+  // relocalize_* acceptance gates.  (The pose-graph search that proposes candidates is out of scope.)
+  class MultiLoopDetectorBruteForce2D : public Configurable {
+  public:
+    PARAM(PropertyConfigurable_<Configurable>, local_map_selector, "module used to figure out which local maps should be checked", nullptr, 0);
+    PARAM(PropertyConfigurable_<MultiAligner2D>, relocalize_aligner, "aligner used to register loop closures", nullptr, 0);
+    PARAM(PropertyFloat, relocalize_max_chi_inliers, "maximum chi per inlier for success [chi]", 0.05f, 0);
+    PARAM(PropertyInt, relocalize_min_inliers, "minimum number of inliers for success [int]", 500, 0);
+    PARAM(PropertyFloat, relocalize_min_inliers_ratio, "minimum fraction of inliers over total correspondences [num_inliers/num_correspondences]", 0.7f, 0);
+    MultiLoopDetectorBruteForce2D() { _class_name = "MultiLoopDetectorBruteForce2D"; }
+
+    LoopClosure2D verify(const PointNormal2fVectorCloud& query,
+                         const std::vector<const PointNormal2fVectorCloud*>& candidates,
+                         const std::vector<std::vector<Isometry2f>>& guesses,
+                         std::vector<AlignmentResult>* all = nullptr);
+  };
+
+}  // namespace srrg2_slam_interfaces
+
+namespace srrg2_laser_slam_2d {
+
+  // R/registration/aligner_slice_processor_laser_2d.h:7-17
+  class AlignerSliceProcessorLaser2D : public srrg2_slam_interfaces::AlignerSliceProcessorLaserBase {
+  public:
+    AlignerSliceProcessorLaser2D() {
+      _class_name = "AlignerSliceProcessorLaser2D";
+      param_finder.setValue(CorrespondenceFinderProjective2DPtr(new CorrespondenceFinderProjective2f));
+    }
+  };
+  using AlignerSliceProcessorLaser2DPtr = std::shared_ptr<AlignerSliceProcessorLaser2D>;
+
+  // R/registration/aligner_slice_processor_laser_2d.h:21-42
+  class AlignerSliceProcessorLaser2DWithSensor : public srrg2_slam_interfaces::AlignerSliceProcessorLaserBase {
+  public:
+    AlignerSliceProcessorLaser2DWithSensor() {
+      _class_name = "AlignerSliceProcessorLaser2DWithSensor";
+      param_finder.setValue(CorrespondenceFinderProjective2DPtr(new CorrespondenceFinderProjective2f));
+    }
+    bool withSensor() const override { return true; }
+
+  protected:
+    void setupFactor() override;  // R/registration/aligner_slice_processor_laser_2d_impl.cpp:7-10
+  };
+  using AlignerSliceProcessorLaser2DWithSensorPtr = std::shared_ptr<AlignerSliceProcessorLaser2DWithSensor>;
+
+  // ELF-constructor registration, like R/instances.h:14
+  void srrg2_laser_slam_2d_registerTypes() __attribute__((constructor));
+
+}  // namespace srrg2_laser_slam_2d

@@ -1,0 +1,337 @@
+// plugin_test.cpp -- driver used by tests/test_plugin_*.py.
+//   plugin_test selftest                          config system + mis-wiring behaviour (no GPU needed)
+//   plugin_test parse <config>                    load a BOSS-text configuration, print the hot-path objects
+//   plugin_test align <config> <aligner> <in.bin> <out.bin>     (GPU) single-pair compute(), computeBatch(), finder
+//   plugin_test verify <config> <detector> <in.bin> <out.bin>   (GPU) loop-closure candidate verification
+// Binary layout of <in.bin>: int32 n_pairs, int32 n_guess, float sensor_in_robot[3]; then per pair:
+//   int32 n_fixed, n_moving; float fixed[n_fixed*4]; float moving[n_moving*4]; float init[n_guess*3].
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "ls2d_modules.h"
+
+using namespace srrg2_core;
+using namespace srrg2_solver;
+using namespace srrg2_slam_interfaces;
+using namespace srrg2_laser_slam_2d;
+
+#define REQUIRE(cond)                                                             \
+  do {                                                                            \
+    if (!(cond)) {                                                                \
+      std::fprintf(stderr, "REQUIRE failed at %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+      std::exit(1);                                                               \
+    }                                                                             \
+  } while (0)
+
+template <typename F>
+static std::string thrown(F f) {
+  try {
+    f();
+  } catch (const std::runtime_error& e) {
+    return e.what();
+  }
+  return "";
+}
+
+static const char* kEmbedded = R"BOSS(
+// two finders sharing one projector, an aligner, an unknown class and a null link
+"PointNormal2fProjectorPolar" { "#id" : 31, "angle_col_max" : 3.14159, "angle_col_min" : -3.14159,
+  "canvas_cols" : 721, "canvas_rows" : 1, "range_max" : 20, "range_min" : 0.3 }
+"CorrespondenceFinderProjective2f" { "#id" : 17, "normal_cos" : 0.9, "point_distance" : 0.5,
+  "projector" : { "#pointer" : 31 } }
+"CorrespondenceFinderProjective2f" { "#id" : 42, "name" : "ld_finder", "normal_cos" : 0.8, "point_distance" : 1.414,
+  "projector" : { "#pointer" : 31 } }
+"RobustifierCauchy" { "#id" : 24, // threshold of chi after which the kernel is active
+  "chi_threshold" : 0.05 }
+"AlignerSliceProcessorLaser2D" { "#id" : 3, "name" : "al_sl_ld_laser_0", "base_frame_id" : "b", "frame_id" : "f",
+  "finder" : { "#pointer" : 42 }, "fixed_slice_name" : "points", "moving_slice_name" : "points",
+  "min_num_correspondences" : 0, "robustifier" : { "#pointer" : 24 } }
+"SomethingOutsideTheHotPath" { "#id" : 99, "name" : "slam", "whatever" : [ 1, 2, 3 ], "link" : { "#pointer" : 3 } }
+"MultiAligner2D" { "#id" : 2, "name" : "multi_aligner_ld", "enable_inlier_only_runs" : 0,
+  "keep_only_inlier_correspondences" : 0, "max_iterations" : 30, "min_num_inliers" : 10,
+  "slice_processors" : [ { "#pointer" : 3 } ], "solver" : { "#pointer" : -1 },
+  "termination_criteria" : { "#pointer" : -1 } }
+)BOSS";
+
+static int selftest() {
+  // registration happened in the ELF constructor (R/instances.h:14)
+  for (const char* c : {"CorrespondenceFinderProjective2f", "AlignerSliceProcessorLaser2D",
+                        "AlignerSliceProcessorLaser2DWithSensor", "MultiAligner2D", "PointNormal2fProjectorPolar",
+                        "RobustifierCauchy", "IterationAlgorithmGN", "Solver", "MultiLoopDetectorBruteForce2D"})
+    REQUIRE(ClassRegistry::instance().has(c));
+
+  ConfigurableManager m;
+  m.readString(kEmbedded);
+  REQUIRE(m.objects().size() == 7);
+  auto aligner = m.getByName<MultiAligner2D>("multi_aligner_ld");
+  REQUIRE(aligner && aligner->param_max_iterations.value() == 30 && aligner->param_min_num_inliers.value() == 10);
+  REQUIRE(aligner->param_slice_processors.size() == 1 && !aligner->param_solver.value());
+  auto slice = std::dynamic_pointer_cast<AlignerSliceProcessorLaser2D>(aligner->param_slice_processors.value(0));
+  REQUIRE(slice && slice->name() == "al_sl_ld_laser_0");
+  auto f42 = m.getByName<CorrespondenceFinderProjective2f>("ld_finder");
+  auto f17 = m.getById<CorrespondenceFinderProjective2f>(17);
+  REQUIRE(f42 && f17 && slice->param_finder.value() == f42);
+  REQUIRE(f42->param_projector.value() == f17->param_projector.value());  // nested modules are shared
+  REQUIRE(f42->param_point_distance.value() == 1.414f && f17->param_normal_cos.value() == 0.9f);
+  REQUIRE(m.getByName<GenericConfigurable>("slam") && m.getByName<GenericConfigurable>("slam")->className() ==
+                                                        "SomethingOutsideTheHotPath");
+  ls2d_params p;
+  aligner->fillParams(p);
+  REQUIRE(p.canvas_cols == 721 && p.max_iterations == 30 && p.cauchy_chi_threshold == 0.05f && p.with_sensor == 0);
+  REQUIRE(p.point_distance == 1.414f && p.normal_cos == 0.8f && p.range_min == 0.3f && p.range_max == 20.f);
+
+  // write -> read round trip keeps parameters, links and unknown objects
+  ConfigurableManager m2;
+  m2.readString(m.writeString());
+  REQUIRE(m2.objects().size() == 7);
+  ls2d_params p2;
+  m2.getByName<MultiAligner2D>("multi_aligner_ld")->fillParams(p2);
+  REQUIRE(std::memcmp(&p, &p2, sizeof(p)) == 0);
+  REQUIRE(m2.getByName<GenericConfigurable>("slam")->unknown_fields.size() == 2);
+
+  // programmatic construction as apps/slam_app.cpp:87-167 does
+  ConfigurableManager m3;
+  auto a3 = m3.create<MultiAligner2D>("tracker_aligner");
+  auto s3 = m3.create<AlignerSliceProcessorLaser2DWithSensor>("slice");
+  s3->param_fixed_slice_name.setValue("points");
+  s3->param_moving_slice_name.setValue("points");
+  s3->param_frame_id.setValue("scan");
+  s3->param_base_frame_id.setValue("base_frame");
+  a3->param_slice_processors.pushBack(s3);
+  a3->param_max_iterations.setValue(10);
+  REQUIRE(s3->param_finder.value());  // default finder set by the slice constructor (aligner_slice_processor_laser_2d.h:13-16)
+  REQUIRE(thrown([&] { ls2d_params q; a3->fillParams(q); }).find("no platform set") != std::string::npos);
+  PlatformPtr platform(new Platform);
+  s3->setPlatform(platform);
+  REQUIRE(thrown([&] { ls2d_params q; a3->fillParams(q); }).find("unable to find transform") != std::string::npos);
+  platform->addTransform("scan", "base_frame", geometry2d::v2t(Vector3f(0.2f, 0.2f, 0.1f)));
+  ls2d_params q;
+  a3->fillParams(q);
+  REQUIRE(q.with_sensor == 1 && q.sensor_in_robot[0] == 0.2f && std::fabs(q.sensor_in_robot[2] - 0.1f) < 1e-6f);
+  REQUIRE(q.cauchy_chi_threshold < 0.f);  // no robustifier on the slice
+
+  // mis-wiring throws std::runtime_error with the reference's messages (correspondence_finder_projective_2d.cpp:20-31)
+  CorrespondenceFinderProjective2f finder;
+  CorrespondenceVector corr;
+  PointNormal2fVectorCloud cloud(3);
+  REQUIRE(thrown([&] { finder.compute(); }) == "CorrespondenceFinderProjective2f::compute| Missing fixed!");
+  finder.setFixed(&cloud);
+  REQUIRE(thrown([&] { finder.compute(); }) == "CorrespondenceFinderProjective2f::compute| Missing moving!");
+  finder.param_projector.setValue(nullptr);
+  REQUIRE(thrown([&] { finder.compute(); }) == "CorrespondenceFinderProjective2f::compute| Missing Projector");
+  MultiAligner2D bare;
+  REQUIRE(thrown([&] { bare.compute(); }) == "MultiAligner2D::compute| Missing fixed!");
+  PropertyContainerDynamic scene;
+  bare.setFixed(&scene);
+  bare.setMoving(&scene);
+  REQUIRE(thrown([&] { bare.compute(); }) == "MultiAligner2D::compute| no slice processor set");
+  REQUIRE(thrown([&] { ConfigurableManager bad; bad.readString("\"Solver\" { \"#id\" : 1, \"algorithm\" : { \"#pointer\" : 5 } }"); })
+            .find("dangling #pointer 5") != std::string::npos);
+  REQUIRE(thrown([&] { ConfigurableManager bad; bad.readString("\"MultiAligner2D\" { \"#id\" : 1, \"solver\" : { \"#pointer\" : 2 } }\n"
+                                                               "\"RobustifierCauchy\" { \"#id\" : 2 }"); })
+            .find("wrong class") != std::string::npos);
+
+  // geometry helpers agree with their definition
+  const Isometry2f T = geometry2d::v2t(Vector3f(1.f, -2.f, 0.5f));
+  const Vector3f back = geometry2d::t2v(T * T.inverse());
+  REQUIRE(std::fabs(back.x()) < 1e-6f && std::fabs(back.y()) < 1e-6f && std::fabs(back.z()) < 1e-6f);
+  std::printf("SELFTEST OK\n");
+  return 0;
+}
+
+static PlatformPtr identityPlatformFor(ConfigurableManager& m, const Isometry2f& S) {
+  PlatformPtr platform(new Platform);
+  for (auto& s : m.getAll<AlignerSliceProcessorBase>()) {
+    platform->addTransform(s->param_frame_id.value(), s->param_base_frame_id.value(), S);
+    s->setPlatform(platform);
+  }
+  return platform;
+}
+
+static int parse(const std::string& file) {
+  ConfigurableManager m;
+  m.read(file);
+  identityPlatformFor(m, Isometry2f::Identity());
+  std::printf("{\"objects\": %zu, \"aligners\": [", m.objects().size());
+  bool first = true;
+  for (auto& a : m.getAll<MultiAligner2D>()) {
+    ls2d_params p;
+    const std::string why = thrown([&] { a->fillParams(p); });
+    if (!why.empty()) {  // e.g. MULTI.json's two-laser tracking aligner (multi-slice solve: SURVEY.md 8f-4)
+      std::printf("%s{\"id\": %d, \"name\": \"%s\", \"slices\": %zu, \"unsupported\": \"%s\"}", first ? "" : ", ",
+                  m.idOf(a.get()), a->name().c_str(), a->param_slice_processors.size(), why.c_str());
+      first = false;
+      continue;
+    }
+    std::printf("%s{\"id\": %d, \"name\": \"%s\", \"slices\": %zu, \"canvas_cols\": %d, \"angle_col_min\": %.6f, "
+                "\"angle_col_max\": %.6f, \"range_min\": %.4f, \"range_max\": %.4f, \"point_distance\": %.4f, "
+                "\"normal_cos\": %.4f, \"cauchy_chi_threshold\": %.4f, \"damping\": %.4f, \"max_iterations\": %d, "
+                "\"min_num_correspondences\": %d, \"min_num_inliers\": %d, \"with_sensor\": %d}",
+                first ? "" : ", ", m.idOf(a.get()), a->name().c_str(), a->param_slice_processors.size(), p.canvas_cols,
+                p.angle_col_min, p.angle_col_max, p.range_min, p.range_max, p.point_distance, p.normal_cos,
+                p.cauchy_chi_threshold, p.damping, p.max_iterations, p.min_num_correspondences, p.min_num_inliers,
+                p.with_sensor);
+    first = false;
+  }
+  std::printf("], \"loop_detectors\": [");
+  first = true;
+  for (auto& d : m.getAll<MultiLoopDetectorBruteForce2D>()) {
+    std::printf("%s{\"name\": \"%s\", \"min_inliers\": %d, \"max_chi\": %.4f, \"min_ratio\": %.4f, \"aligner\": %d}",
+                first ? "" : ", ", d->name().c_str(), d->param_relocalize_min_inliers.value(),
+                d->param_relocalize_max_chi_inliers.value(), d->param_relocalize_min_inliers_ratio.value(),
+                d->param_relocalize_aligner.value() ? m.idOf(d->param_relocalize_aligner.value().get()) : -1);
+    first = false;
+  }
+  std::printf("], \"finders\": %zu, \"projectors\": %zu}\n", m.getAll<CorrespondenceFinderProjective2f>().size(),
+              m.getAll<PointNormal2fProjectorPolar>().size());
+  return 0;
+}
+
+struct PairsFile {
+  int32_t n_pairs = 0, n_guess = 0;
+  float sensor[3] = {0, 0, 0};
+  std::vector<PointNormal2fVectorCloud> fixed, moving;
+  std::vector<std::vector<Isometry2f>> guesses;
+};
+
+static PointNormal2fVectorCloud readCloud(std::ifstream& is, int n) {
+  std::vector<float> buf((size_t) n * 4);
+  is.read((char*) buf.data(), (std::streamsize)(buf.size() * sizeof(float)));
+  PointNormal2fVectorCloud c((size_t) n);
+  for (int i = 0; i < n; ++i) {
+    c[i].coordinates() = Vector2f(buf[4 * i], buf[4 * i + 1]);
+    c[i].normal()      = Vector2f(buf[4 * i + 2], buf[4 * i + 3]);
+  }
+  return c;
+}
+
+static PairsFile readPairs(const std::string& file) {
+  std::ifstream is(file, std::ios::binary);
+  if (!is.good()) throw std::runtime_error("cannot open " + file);
+  PairsFile f;
+  is.read((char*) &f.n_pairs, 4);
+  is.read((char*) &f.n_guess, 4);
+  is.read((char*) f.sensor, 12);
+  for (int p = 0; p < f.n_pairs; ++p) {
+    int32_t nf, nm;
+    is.read((char*) &nf, 4);
+    is.read((char*) &nm, 4);
+    f.fixed.push_back(readCloud(is, nf));
+    f.moving.push_back(readCloud(is, nm));
+    std::vector<float> g((size_t) f.n_guess * 3);
+    is.read((char*) g.data(), (std::streamsize)(g.size() * sizeof(float)));
+    std::vector<Isometry2f> gs;
+    for (int k = 0; k < f.n_guess; ++k) gs.push_back(geometry2d::v2t(Vector3f(g[3 * k], g[3 * k + 1], g[3 * k + 2])));
+    f.guesses.push_back(gs);
+  }
+  if (!is.good()) throw std::runtime_error("short read on " + file);
+  return f;
+}
+
+static void writeResult(std::ofstream& os, const Vector3f& est, int status, float chi_in, float chi_k, int n_in, int n_out,
+                        int n_corr, int iterations) {
+  const float f[5]   = {est.x(), est.y(), est.z(), chi_in, chi_k};
+  const int32_t i[5] = {status, n_in, n_out, n_corr, iterations};
+  os.write((const char*) f, sizeof(f));
+  os.write((const char*) i, sizeof(i));
+}
+
+static int align(const std::string& config, const std::string& name, const std::string& in, const std::string& out) {
+  ConfigurableManager m;
+  m.read(config);
+  PairsFile f = readPairs(in);
+  identityPlatformFor(m, geometry2d::v2t(Vector3f(f.sensor[0], f.sensor[1], f.sensor[2])));
+  MultiAligner2DPtr aligner = m.getByName<MultiAligner2D>(name);
+  if (!aligner) throw std::runtime_error("no MultiAligner2D named " + name);
+  std::ofstream os(out, std::ios::binary);
+  // (1) the reference's single-pair call sequence (apps/visual_test_aligner_2d.cpp:108-156)
+  for (int p = 0; p < f.n_pairs; ++p) {
+    PropertyContainerDynamic fixed_scene, moving_scene;
+    fixed_scene.setCloud("points", &f.fixed[p]);
+    moving_scene.setCloud("points", &f.moving[p]);
+    aligner->setFixed(&fixed_scene);
+    aligner->setMoving(&moving_scene);
+    aligner->setMovingInFixed(f.guesses[p][0]);
+    aligner->compute();
+    const auto& st = aligner->iterationStats();
+    const IterationStats last = st.empty() ? IterationStats() : st.back();
+    writeResult(os, geometry2d::t2v(aligner->movingInFixed()), (int) aligner->status(), last.chi_inliers,
+                last.chi_kernelized, last.num_inliers, last.num_outliers, last.num_correspondences, (int) st.size());
+    if (p == 0) {  // slice->correspondences() after compute()
+      auto slice = std::dynamic_pointer_cast<AlignerSliceProcessorLaserBase>(aligner->param_slice_processors.value(0));
+      const int32_t n = (int32_t) slice->correspondences().size();
+      os.write((const char*) &n, 4);
+      for (const auto& c : slice->correspondences()) {
+        os.write((const char*) &c.fixed_idx, 4);
+        os.write((const char*) &c.moving_idx, 4);
+      }
+    }
+  }
+  // (2) the batched extension: one launch for all pairs
+  std::vector<const PointNormal2fVectorCloud*> fx, mv;
+  std::vector<Isometry2f> gs;
+  for (int p = 0; p < f.n_pairs; ++p) fx.push_back(&f.fixed[p]), mv.push_back(&f.moving[p]), gs.push_back(f.guesses[p][0]);
+  std::vector<AlignmentResult> res;
+  aligner->computeBatch(fx, mv, gs, res);
+  for (const auto& r : res)
+    writeResult(os, r.estimate, r.status, r.last.chi_inliers, r.last.chi_kernelized, r.last.num_inliers,
+                r.last.num_outliers, r.last.num_correspondences, r.iterations);
+  // (3) the finder on its own (apps/visual_test_correspondence_finder_projective_2d.cpp:73-79), pair 0 at its guess
+  auto slice  = std::dynamic_pointer_cast<AlignerSliceProcessorLaserBase>(aligner->param_slice_processors.value(0));
+  auto finder = slice->param_finder.value();
+  CorrespondenceVector corr;
+  finder->setFixed(&f.fixed[0]);
+  finder->setMoving(&f.moving[0]);
+  finder->setLocalMapInSensor(f.guesses[0][0]);
+  finder->setCorrespondences(&corr);
+  finder->compute();
+  finder->compute();  // second call reuses the cached fixed image
+  const int32_t n = (int32_t) corr.size();
+  os.write((const char*) &n, 4);
+  for (const auto& c : corr) {
+    os.write((const char*) &c.fixed_idx, 4);
+    os.write((const char*) &c.moving_idx, 4);
+  }
+  std::printf("ALIGN OK %d pairs\n", f.n_pairs);
+  return 0;
+}
+
+static int verify(const std::string& config, const std::string& name, const std::string& in, const std::string& out) {
+  ConfigurableManager m;
+  m.read(config);
+  PairsFile f = readPairs(in);
+  identityPlatformFor(m, Isometry2f::Identity());
+  auto det = m.getByName<MultiLoopDetectorBruteForce2D>(name);
+  if (!det) throw std::runtime_error("no MultiLoopDetectorBruteForce2D named " + name);
+  std::vector<const PointNormal2fVectorCloud*> cands;
+  for (int p = 0; p < f.n_pairs; ++p) cands.push_back(&f.moving[p]);
+  std::vector<AlignmentResult> all;
+  const LoopClosure2D lc = det->verify(f.fixed[0], cands, f.guesses, &all);
+  std::ofstream os(out, std::ios::binary);
+  const int32_t head[4] = {lc.candidate, lc.guess, lc.num_inliers, lc.num_correspondences};
+  os.write((const char*) head, sizeof(head));
+  const Vector3f est = geometry2d::t2v(lc.moving_in_fixed);
+  os.write((const char*) est.v, 12);
+  for (const auto& r : all)
+    writeResult(os, r.estimate, r.status, r.last.chi_inliers, r.last.chi_kernelized, r.last.num_inliers,
+                r.last.num_outliers, r.last.num_correspondences, r.iterations);
+  std::printf("VERIFY OK candidate %d guess %d\n", lc.candidate, lc.guess);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  try {
+    const std::string cmd = argc > 1 ? argv[1] : "";
+    if (cmd == "selftest") return selftest();
+    if (cmd == "parse" && argc == 3) return parse(argv[2]);
+    if (cmd == "align" && argc == 6) return align(argv[2], argv[3], argv[4], argv[5]);
+    if (cmd == "verify" && argc == 6) return verify(argv[2], argv[3], argv[4], argv[5]);
+    std::fprintf(stderr, "usage: plugin_test selftest | parse <config> | align|verify <config> <name> <in> <out>\n");
+    return 2;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "plugin_test: %s\n", e.what());
+    return 1;
+  }
+}

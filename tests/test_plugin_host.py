@@ -1,0 +1,170 @@
+"""C++ host shim (srrg2_laser_slam_2d_b200/plugin): the reference's config-driven plugin surface.
+CPU part: class registry, BOSS-text reader/writer, parameter resolution, mis-wiring exceptions.
+GPU part: the reference's own call sequences (apps/visual_test_aligner_2d.cpp:108-156,
+apps/visual_test_correspondence_finder_projective_2d.cpp:73-79) through the plugin classes, compared
+with the C ABI called directly and with the oracle."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "srrg2_laser_slam_2d_b200", "plugin_test")
+OWN_CONFIG = os.path.join(ROOT, "configs", "laser_aligner_b200.json")
+REF_CONFIGS = "/root/reference/configurations"
+
+
+@pytest.fixture(scope="module")
+def exe():
+    if not os.path.exists(EXE):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "srrg2_laser_slam_2d_b200", "plugin")], check=True)
+    return EXE
+
+
+def run(exe, *args):
+    r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def test_selftest(exe):
+    assert "SELFTEST OK" in run(exe, "selftest")
+
+
+def test_own_config_resolves_to_the_shipped_parameter_values(exe):
+    d = json.loads(run(exe, "parse", OWN_CONFIG))
+    a = {x["name"]: x for x in d["aligners"]}
+    t, l = a["aligner_tracking"], a["aligner_loop"]
+    assert (t["max_iterations"], t["point_distance"], t["normal_cos"], t["cauchy_chi_threshold"], t["with_sensor"]) == \
+           (10, 0.5, 0.9, 0.01, 1)
+    assert (l["max_iterations"], l["point_distance"], l["normal_cos"], l["cauchy_chi_threshold"], l["with_sensor"]) == \
+           (30, 1.414, 0.8, 0.05, 0)
+    assert t["canvas_cols"] == l["canvas_cols"] == 1081 and d["projectors"] == 1          # shared projector
+    assert d["loop_detectors"] == [{"name": "loop_detector", "min_inliers": 300, "max_chi": 0.1, "min_ratio": 0.8,
+                                    "aligner": 12}]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CONFIGS), reason="reference checkout not present on this machine")
+def test_reference_configurations_load_unchanged(exe):
+    """both shipped files instantiate the CUDA-backed classes by their reference names."""
+    d = json.loads(run(exe, "parse", os.path.join(REF_CONFIGS, "stage_segway_double_config_LASER_0.json")))
+    assert d["objects"] == 45
+    a = {x["name"]: x for x in d["aligners"]}
+    ld, tr = a["multi_aligner_ld"], a["multi_aligner"]
+    assert (ld["max_iterations"], ld["min_num_inliers"], ld["point_distance"], ld["normal_cos"],
+            ld["cauchy_chi_threshold"], ld["canvas_cols"], ld["with_sensor"], ld["min_num_correspondences"]) == \
+           (30, 10, 1.414, 0.8, 0.05, 721, 0, 0)
+    assert (tr["max_iterations"], tr["point_distance"], tr["normal_cos"], tr["cauchy_chi_threshold"],
+            tr["with_sensor"], tr["slices"]) == (10, 0.5, 0.9, 0.01, 1, 2)
+    assert (tr["range_min"], tr["range_max"], tr["damping"]) == (0.3, 20.0, 0.0)
+    assert d["loop_detectors"][0]["min_inliers"] == 300 and d["loop_detectors"][0]["aligner"] == ld["id"]
+    m = json.loads(run(exe, "parse", os.path.join(REF_CONFIGS, "stage_segway_double_config_MULTI.json")))
+    assert m["objects"] == 56
+    am = {x["name"]: x for x in m["aligners"]}
+    assert am["multi_aligner_ld"]["min_num_correspondences"] == 10 and am["multi_aligner_ld"]["max_iterations"] == 30
+    assert "more than one laser slice" in am["multi_aligner"]["unsupported"]   # two rangefinders: SURVEY.md 8f-4
+    assert m["loop_detectors"][0]["min_inliers"] == 500
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+def write_pairs(path, sp, guesses, sensor=(0.0, 0.0, 0.0)):
+    n, g = len(guesses), guesses.shape[1]
+    with open(path, "wb") as f:
+        f.write(struct.pack("<ii3f", n, g, *sensor))
+        for p in range(n):
+            fx = sp.fixed_pts[sp.fixed_off[p]:sp.fixed_off[p + 1]]
+            mv = sp.moving_pts[sp.moving_off[p]:sp.moving_off[p + 1]]
+            f.write(struct.pack("<ii", len(fx), len(mv)))
+            f.write(np.ascontiguousarray(fx, np.float32).tobytes())
+            f.write(np.ascontiguousarray(mv, np.float32).tobytes())
+            f.write(np.ascontiguousarray(guesses[p], np.float32).tobytes())
+
+
+REC = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"), ("chi_kernelized", "<f4"),
+                ("status", "<i4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"), ("n_corr", "<i4"),
+                ("iterations", "<i4")])
+
+
+def same(rec, res):
+    for f in REC.names:
+        if not np.array_equal(rec[f], res[f]):
+            return f
+    return None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("aligner,sensor", [("aligner_tracking", (0.2, 0.2, 0.1)), ("aligner_loop", (0.0, 0.0, 0.0))])
+def test_plugin_aligner_matches_abi_and_oracle(exe, tmp_path, handle_factory, oracle, aligner, sensor):
+    from srrg2_laser_slam_2d_b200 import default_params
+    from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING, reduction_threads
+    from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
+    n = 6
+    sp = make_scan_pairs(n, seed=55)
+    guesses = sp.init_xyt[:, None, :].copy()
+    inp, out = str(tmp_path / "pairs.bin"), str(tmp_path / "out.bin")
+    write_pairs(inp, sp, guesses, sensor)
+    assert "ALIGN OK" in run(exe, "align", OWN_CONFIG, aligner, inp, out)
+    raw = open(out, "rb").read()
+    pos = 0
+    single = []
+    for p in range(n):
+        single.append(np.frombuffer(raw, REC, 1, pos)[0])
+        pos += REC.itemsize
+        if p == 0:
+            k = struct.unpack_from("<i", raw, pos)[0]
+            last_corr = np.frombuffer(raw, np.int32, 2 * k, pos + 4).reshape(k, 2)
+            pos += 4 + 8 * k
+    single = np.array(single, REC)
+    batch = np.frombuffer(raw, REC, n, pos)
+    pos += n * REC.itemsize
+    k = struct.unpack_from("<i", raw, pos)[0]
+    finder_corr = np.frombuffer(raw, np.int32, 2 * k, pos + 4).reshape(k, 2)
+    track = aligner == "aligner_tracking"
+    kw = dict(canvas_cols=1081, point_distance=0.5 if track else 1.414, normal_cos=0.9 if track else 0.8,
+              cauchy_chi_threshold=0.01 if track else 0.05, max_iterations=10 if track else 30,
+              with_sensor=1 if track else 0, sensor_in_robot=sensor)
+    # the plugin is a thin layer: identical to the C ABI called directly ...
+    h = handle_factory(default_params(**kw))
+    h.upload_clouds(LS2D_FIXED, sp.fixed_pts, sp.fixed_off)
+    h.upload_clouds(LS2D_MOVING, sp.moving_pts, sp.moving_off)
+    g, gi = h.align_batch(sp.init_xyt, want_iters=True)
+    assert same(batch, g) is None and same(single, g) is None
+    # ... and therefore bit-identical to the oracle in the kernel's summation order
+    o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
+                               sp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1081))
+    for f in ("x", "y", "theta", "chi_inliers", "status", "n_inliers", "n_corr", "iterations"):
+        assert np.array_equal(batch[f], o[f]), f
+    # slice->correspondences() after compute(): the last iteration's list
+    assert len(last_corr) == g["n_corr"][0]
+    # the finder on its own == oracle finder at the same local_map_in_sensor
+    fi, mi, _, _ = oracle.find_correspondences(oracle.default_params(**kw), sp.fixed_pts[:1081], sp.moving_pts[:1081],
+                                               sp.init_xyt[0])
+    assert np.array_equal(finder_corr[:, 0], fi) and np.array_equal(finder_corr[:, 1], mi)
+
+
+@pytest.mark.gpu
+def test_plugin_loop_detector_verification(exe, tmp_path, handle_factory):
+    from srrg2_laser_slam_2d_b200 import Gates, default_params
+    from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING
+    from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
+    n_cand, n_guess = 10, 3
+    sp = make_scan_pairs(n_cand, seed=91, motion_xy=0.3, motion_theta=0.15)
+    rng = np.random.default_rng(2)
+    guesses = (sp.gt_xyt[0][None, None, :] + rng.uniform(-0.1, 0.1, (n_cand, n_guess, 3))).astype(np.float32)
+    inp, out = str(tmp_path / "cands.bin"), str(tmp_path / "out.bin")
+    write_pairs(inp, sp, guesses)
+    assert "VERIFY OK" in run(exe, "verify", OWN_CONFIG, "loop_detector", inp, out)
+    raw = open(out, "rb").read()
+    cand, guess, n_inl, n_corr = struct.unpack_from("<4i", raw, 0)
+    allr = np.frombuffer(raw, REC, n_cand * n_guess, 16 + 12)
+    kw = dict(canvas_cols=1081, point_distance=1.414, normal_cos=0.8, cauchy_chi_threshold=0.05, max_iterations=30)
+    h = handle_factory(default_params(**kw))
+    h.upload_clouds(LS2D_FIXED, sp.fixed_pts, sp.fixed_off)
+    h.upload_clouds(LS2D_MOVING, sp.moving_pts, sp.moving_off)
+    best, ref = h.verify(0, None, guesses, Gates(300, 0.1, 0.8), want_all=True)
+    assert same(allr, ref) is None
+    assert (cand, guess, n_inl) == (int(best["candidate"]), int(best["guess"]), int(best["n_inliers"]))
+    assert cand == 0                                       # the true match
