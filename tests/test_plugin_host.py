@@ -123,6 +123,10 @@ def test_plugin_aligner_matches_abi_and_oracle(exe, tmp_path, handle_factory, or
     k = struct.unpack_from("<i", raw, pos)[0]
     finder_corr = np.frombuffer(raw, np.int32, 2 * k, pos + 4).reshape(k, 2)
     track = aligner == "aligner_tracking"
+    # the slice reads sensor_in_robot from the tf tree as an isometry; it crosses the C ABI as t2v(isometry)
+    srt = np.zeros(3, np.float32)
+    oracle.lib().orc_t2v(oracle.v2t(*sensor), srt.ctypes.data)
+    sensor = tuple(float(v) for v in srt)
     kw = dict(canvas_cols=1081, point_distance=0.5 if track else 1.414, normal_cos=0.9 if track else 0.8,
               cauchy_chi_threshold=0.01 if track else 0.05, max_iterations=10 if track else 30,
               with_sensor=1 if track else 0, sensor_in_robot=sensor)
