@@ -22,7 +22,8 @@
  *  D8  information matrix Omega = I3.
  *  D9  WithSensor: finder gets S^-1 * X; factor predicts S^-1 * (X * p_m), rotations S^-1 * R.
  *  D10 sum order: sequential in correspondence order (reference) or the CUDA tree (debug).
- *  D11 3x3 solve in binary64 Cholesky LL^T with reciprocal pivots (Cholmod is double).
+ *  D11 3x3 solve in binary64 LDL^T with reciprocal pivots (Cholmod is double; its simplicial
+ *      factorisation is LDL^T); a pivot <= 0 means "not positive definite" => status SINGULAR.
  *  D12 pose state = Isometry2f content (tx, ty, c, s); X <- X * v2t(dx) by plain products,
  *      no re-orthonormalisation; theta reported as atan2f(s, c).
  *  D13 the camera pose goes through TWO Isometry2f::inverse() calls before touching a point
@@ -357,34 +358,35 @@ static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
 
 /* ---------------------------------------------------------------- A.6 GN step */
 
-/* IterationAlgorithmGN + 3x3 Cholesky (D11). returns 0 on success, -1 if not positive definite */
+/* IterationAlgorithmGN + 3x3 LDL^T (D11). returns 0 on success, -1 if not positive definite */
 static int solve3(const float* v, float damping, float* dx) {
   const double H00 = (double) v[0] + (double) damping, H01 = v[1], H02 = v[2];
   const double H11 = (double) v[3] + (double) damping, H12 = v[4];
   const double H22 = (double) v[5] + (double) damping;
   const double r0 = -(double) v[6], r1 = -(double) v[7], r2 = -(double) v[8];
-  if (!(H00 > 0.0)) {
+  if (!(H00 > 0.0)) { /* d0 */
     return -1;
   }
-  const double l00 = sqrt(H00), i00 = 1.0 / l00;
-  const double l10 = H01 * i00, l20 = H02 * i00;
-  const double t11 = H11 - l10 * l10;
-  if (!(t11 > 0.0)) {
+  const double i0  = 1.0 / H00;
+  const double l10 = H01 * i0, l20 = H02 * i0;
+  const double d1  = H11 - l10 * H01;
+  if (!(d1 > 0.0)) {
     return -1;
   }
-  const double l11 = sqrt(t11), i11 = 1.0 / l11;
-  const double l21 = (H12 - l20 * l10) * i11;
-  const double t22 = (H22 - l20 * l20) - l21 * l21;
-  if (!(t22 > 0.0)) {
+  const double i1  = 1.0 / d1;
+  const double t21 = H12 - l20 * H01; /* = l21 * d1 */
+  const double l21 = t21 * i1;
+  const double d2  = (H22 - l20 * H02) - l21 * t21;
+  if (!(d2 > 0.0)) {
     return -1;
   }
-  const double l22 = sqrt(t22), i22 = 1.0 / l22;
-  const double y0 = r0 * i00;
-  const double y1 = (r1 - l10 * y0) * i11;
-  const double y2 = ((r2 - l20 * y0) - l21 * y1) * i22;
-  const double x2 = y2 * i22;
-  const double x1 = (y1 - l21 * x2) * i11;
-  const double x0 = ((y0 - l10 * x1) - l20 * x2) * i00;
+  const double i2 = 1.0 / d2;
+  /* L z = r, D y = z, L^T x = y */
+  const double z1 = r1 - l10 * r0;
+  const double z2 = (r2 - l20 * r0) - l21 * z1;
+  const double y0 = r0 * i0, y1 = z1 * i1, x2 = z2 * i2;
+  const double x1 = y1 - l21 * x2;
+  const double x0 = (y0 - l10 * x1) - l20 * x2;
   dx[0]           = (float) x0;
   dx[1]           = (float) x1;
   dx[2]           = (float) x2;

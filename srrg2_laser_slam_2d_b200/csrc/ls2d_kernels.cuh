@@ -93,28 +93,28 @@ __device__ __forceinline__ float warp_reduce_slots(float (&v)[16], int lane) {
   return v[0];
 }
 
-// 3x3 Cholesky in binary64, operation order of oracle/ls2d_oracle.c solve3() (decision D11)
+// 3x3 LDL^T in binary64, operation order of oracle/ls2d_oracle.c solve3() (decision D11)
 __device__ __forceinline__ bool solve3(const float* v, float damping, float* dx) {
   const double H00 = dadd((double) v[0], (double) damping), H01 = v[1], H02 = v[2];
   const double H11 = dadd((double) v[3], (double) damping), H12 = v[4];
   const double H22 = dadd((double) v[5], (double) damping);
   const double r0 = -(double) v[6], r1 = -(double) v[7], r2 = -(double) v[8];
   if (!(H00 > 0.0)) return false;
-  const double l00 = dsqrt(H00), i00 = ddiv(1.0, l00);
-  const double l10 = dmul(H01, i00), l20 = dmul(H02, i00);
-  const double t11 = dsub(H11, dmul(l10, l10));
-  if (!(t11 > 0.0)) return false;
-  const double l11 = dsqrt(t11), i11 = ddiv(1.0, l11);
-  const double l21 = dmul(dsub(H12, dmul(l20, l10)), i11);
-  const double t22 = dsub(dsub(H22, dmul(l20, l20)), dmul(l21, l21));
-  if (!(t22 > 0.0)) return false;
-  const double l22 = dsqrt(t22), i22 = ddiv(1.0, l22);
-  const double y0 = dmul(r0, i00);
-  const double y1 = dmul(dsub(r1, dmul(l10, y0)), i11);
-  const double y2 = dmul(dsub(dsub(r2, dmul(l20, y0)), dmul(l21, y1)), i22);
-  const double x2 = dmul(y2, i22);
-  const double x1 = dmul(dsub(y1, dmul(l21, x2)), i11);
-  const double x0 = dmul(dsub(dsub(y0, dmul(l10, x1)), dmul(l20, x2)), i00);
+  const double i0  = ddiv(1.0, H00);
+  const double l10 = dmul(H01, i0), l20 = dmul(H02, i0);
+  const double d1  = dsub(H11, dmul(l10, H01));
+  if (!(d1 > 0.0)) return false;
+  const double i1  = ddiv(1.0, d1);
+  const double t21 = dsub(H12, dmul(l20, H01));
+  const double l21 = dmul(t21, i1);
+  const double d2  = dsub(dsub(H22, dmul(l20, H02)), dmul(l21, t21));
+  if (!(d2 > 0.0)) return false;
+  const double i2 = ddiv(1.0, d2);
+  const double z1 = dsub(r1, dmul(l10, r0));
+  const double z2 = dsub(dsub(r2, dmul(l20, r0)), dmul(l21, z1));
+  const double y0 = dmul(r0, i0), y1 = dmul(z1, i1), x2 = dmul(z2, i2);
+  const double x1 = dsub(y1, dmul(l21, x2));
+  const double x0 = dsub(dsub(y0, dmul(l10, x1)), dmul(l20, x2));
   dx[0]           = (float) x0;
   dx[1]           = (float) x1;
   dx[2]           = (float) x2;
@@ -127,6 +127,7 @@ struct pose_bc {
   float Lc, Ls;            // rotation of local_map_in_sensor (= X, or Sinv * X)
   float Wtx, Wty;          // translation of inverse(inverse(local_map_in_sensor))  (decision D13)
   int stop;
+  int tie;                 // set by a failed optimistic z-buffer claim
 };
 
 __device__ __forceinline__ void publish_pose(pose_bc* bc, const dev_params& P, const iso& X,
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
   if (tid == 0) {
     const iso X = iso_v2t(A.init_xyt[3 * pair], A.init_xyt[3 * pair + 1], A.init_xyt[3 * pair + 2]);
     publish_pose(bc, P, X, SENSOR, 0);
+    bc->tie = 0;
   }
   __syncthreads();
 
@@ -221,8 +223,14 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
   int status       = -1;
   float tot        = 0.f;  // lane s of warp 0: total of slot s for the last linearisation
   unsigned tot_cnt = 0;
+  // z-buffer winner = lowest index among the points of minimal rho (decision D3).  Equal rho bits in one
+  // column are rare, so an iteration first runs OPTIMISTIC: one atomicMin pass, then every minimal-rho point
+  // claims its cell with a CAS; a failed claim means a tie, and the whole iteration is redone EXACT with the
+  // index tie-break pass (one more barrier).  `exact` is uniform over the CTA.
+  bool exact = false;
   for (; it < max_it; ++it) {
     const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
+    if (exact) __syncthreads();  // redo pass: tie flag cleared and all cells handed back
     int col[PPT];
     unsigned rb[PPT];
     // phase 1: project the moving cloud (camera = local_map_in_sensor^-1, .cpp:47-48), z-buffer pass 1
@@ -244,11 +252,12 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
       }
     }
     __syncthreads();
-    // z-buffer pass 2: lowest index among equal depths (first in iteration order wins, decision D3)
+    if (exact) {  // z-buffer pass 2: lowest index among equal depths
 #pragma unroll
-    for (int j = 0; j < PPT; ++j)
-      if (col[j] >= 0 && zdepth[col[j]] == rb[j]) atomicMin(&zidx[col[j]], (unsigned) (tid + j * T));
-    __syncthreads();
+      for (int j = 0; j < PPT; ++j)
+        if (col[j] >= 0 && zdepth[col[j]] == rb[j]) atomicMin(&zidx[col[j]], (unsigned) (tid + j * T));
+      __syncthreads();
+    }
     // phase 2: winners gate against the fixed column (.cpp:61-73) and linearise their correspondence
     float acc[16];
 #pragma unroll
@@ -256,10 +265,14 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
     unsigned cnt = 0;  // n_inliers | n_kernelized << 16
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      if (col[j] < 0 || zidx[col[j]] != (unsigned) (tid + j * T)) continue;
+      if (col[j] < 0 || zdepth[col[j]] != rb[j]) continue;
       const int c = col[j];
-      zdepth[c]   = Z_EMPTY_DEPTH;  // the winner hands the cell back for the next iteration
-      zidx[c]     = Z_EMPTY_IDX;
+      if (exact) {
+        if (zidx[c] != (unsigned) (tid + j * T)) continue;
+      } else if (atomicCAS(&zidx[c], Z_EMPTY_IDX, (unsigned) (tid + j * T)) != Z_EMPTY_IDX) {
+        bc->tie = 1;  // two points of equal minimal rho in one column: redo this iteration exactly
+        continue;
+      }
       const float fd = fdepth[c];
       if (fd < 0.f) continue;  // fcell.source_idx < 0
       const float rho = u2f(rb[j]);
@@ -317,6 +330,21 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
     if (!(lane & 1) && lane < 2 * NSUM) red[warp * RED_STRIDE + (lane >> 1)] = wsum;
     if (lane == 0) red[warp * RED_STRIDE + NSUM] = __uint_as_float(wcnt);
     __syncthreads();
+    // hand the touched cells back for the next pass (every toucher writes the same EMPTY values)
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+      if (col[j] >= 0) {
+        zdepth[col[j]] = Z_EMPTY_DEPTH;
+        zidx[col[j]]   = Z_EMPTY_IDX;
+      }
+    if (!exact && bc->tie) {  // uniform: bc->tie was written before the barrier above
+      __syncthreads();        // every thread has read the flag and handed its cells back
+      if (tid == 0) bc->tie = 0;
+      exact = true;
+      --it;
+      continue;               // the next pass starts after the barrier at the loop head
+    }
+    exact = false;
     if (warp == 0) {
       if (lane < NSUM) {
         tot = red[lane];

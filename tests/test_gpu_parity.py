@@ -346,3 +346,30 @@ def test_device_resident_path_matches_host_path(handle_factory):
     assert got.tobytes() == ref.tobytes()
     one = h2.align_pairs_host(sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt)
     assert one.tobytes() == ref.tobytes()
+
+
+def test_zbuffer_ties_first_index_wins(handle_factory, oracle):
+    """Equal rho bits in one column (duplicated points): the lowest index must win (decision D3).  This is the
+    kernel's rare exact-redo path (optimistic CAS claim fails -> iteration redone with the index tie-break)."""
+    sp = make_scan_pairs(12, n_beams=500, seed=17)
+    f = sp.fixed_pts.reshape(12, 500, 4)
+    m = sp.moving_pts.reshape(12, 500, 4)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(1000)
+    fixed = np.concatenate([f, f], 1)[:, perm]                     # every point twice, shuffled
+    moving = np.concatenate([m, m[:, ::-1]], 1)                    # every point twice, mirrored order
+    off = (np.arange(13) * 1000).astype(np.int32)
+    kw = dict(canvas_cols=721, normal_cos=0.9, max_iterations=8)
+    h = handle_factory(default_params(**kw))
+    h.upload_clouds(LS2D_FIXED, fixed.reshape(-1, 4), off)
+    h.upload_clouds(LS2D_MOVING, moving.reshape(-1, 4), off)
+    g, gi = h.align_batch(sp.init_xyt, want_iters=True)
+    prm = oracle.default_params(**kw)
+    o, oi = oracle.align_batch(prm, fixed.reshape(-1, 4), off, moving.reshape(-1, 4), off, sp.init_xyt,
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1000))
+    assert_bit_exact(g, o, gi, oi)
+    for p in range(3):
+        fi, mi, _, _ = oracle.find_correspondences(prm, fixed[p], moving[p], sp.init_xyt[p])
+        gfi, gmi = h.find_correspondences(p, p, sp.init_xyt[p])
+        assert np.array_equal(fi, gfi) and np.array_equal(mi, gmi)
+        assert (mi < 500).all()                                     # of each duplicated pair the first copy wins
