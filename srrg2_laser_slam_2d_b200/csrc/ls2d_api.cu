@@ -121,29 +121,34 @@ dev_params translate(const ls2d_params& p) {
 // ---- kernel table: (threads, points per thread) by cloud size -------------------------------------
 struct shape {
   int threads, ppt, minb;
+  int kind;  // 0: points in registers (icp_fused_kernel); 1: streamed from global/L2; 2: staged in shared memory
 };
 
 shape pick_shape(int max_points, int variant) {
-  if (max_points <= 256) return {128, 2, 6};
-  if (max_points <= 512) return {128, 4, 6};
-  if (max_points <= 768) return {256, 3, 3};
+  if (max_points <= 256) return {128, 2, 6, 0};
+  if (max_points <= 512) return {128, 4, 6, 0};
+  if (max_points <= 768) return {256, 3, 3, 0};
   if (max_points <= 1152) {
-    switch (variant) {
-      case 1: return {128, 9, 4};
-      case 2: return {384, 3, 2};
-      case 3: return {256, 5, 3};
-      case 4: return {192, 6, 5};
-      case 5: return {256, 5, 4};
-      case 6: return {192, 6, 4};
-      case 7: return {128, 9, 5};
-      case 8: return {128, 9, 6};
-      default: return {384, 3, 3};  // measured best on B200 (profiles/r01_variant_sweep.md)
+    switch (variant) {  // LS2D_ICP_VARIANT: tuning knob, see profiles/r01_variant_sweep.md
+      case 1: return {128, 9, 4, 0};
+      case 2: return {384, 3, 2, 0};
+      case 3: return {256, 5, 3, 0};
+      case 4: return {192, 6, 5, 0};
+      case 5: return {256, 5, 4, 0};
+      case 6: return {192, 6, 4, 0};
+      case 7: return {128, 9, 5, 0};
+      case 10: return {384, 0, 4, 2};
+      case 11: return {384, 0, 4, 1};
+      case 12: return {256, 0, 6, 2};
+      case 13: return {512, 0, 3, 2};
+      default: return {384, 3, 3, 0};  // measured best on B200 (profiles/r01_variant_sweep.md)
     }
   }
-  if (max_points <= 1536) return {256, 6, 2};
-  if (max_points <= 2048) return {256, 8, 2};
-  if (max_points <= 4096) return {512, 8, 1};
-  return {0, 0, 0};
+  if (max_points <= 1536) return {256, 6, 2, 0};
+  if (max_points <= 2048) return {256, 8, 2, 0};
+  if (max_points <= 4096) return {512, 8, 1, 0};
+  if (max_points <= 65535) return {512, 0, 2, 1};  // streaming kernel, any size the shared-memory stash can hold
+  return {0, 0, 0, 0};
 }
 
 template <int T, int PPT, bool SENSOR, int MINB>
@@ -164,13 +169,37 @@ int launch_icp_t(ls2d_handle* h, const align_args& a) {
   return h->dp.with_sensor ? launch_icp_k<T, PPT, true, MINB>(h, a) : launch_icp_k<T, PPT, false, MINB>(h, a);
 }
 
+template <int T, bool SENSOR, bool MP_SMEM, int MINB>
+int launch_stream_k(ls2d_handle* h, const align_args& a, int maxp) {
+  const size_t smem = icp_stream_smem_bytes(h->dp.cam.cols, T, maxp, MP_SMEM);
+  if (smem > 227 * 1024) return LS2D_ERR_UNSUPPORTED;
+  auto kern = icp_stream_kernel<T, SENSOR, MP_SMEM, MINB>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a, maxp);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+template <int T, bool MP_SMEM, int MINB>
+int launch_stream_t(ls2d_handle* h, const align_args& a, int maxp) {
+  return h->dp.with_sensor ? launch_stream_k<T, true, MP_SMEM, MINB>(h, a, maxp)
+                           : launch_stream_k<T, false, MP_SMEM, MINB>(h, a, maxp);
+}
+
 int launch_icp(ls2d_handle* h, const align_args& a) {
   if (a.n_pairs <= 0) return LS2D_OK;
   const int maxp = h->sets[0].max_points > h->sets[1].max_points ? h->sets[0].max_points
                                                                   : h->sets[1].max_points;
   const shape s = pick_shape(maxp, h->variant);
+  if (s.kind == 1 && s.threads == 512) return launch_stream_t<512, false, 2>(h, a, maxp);
+  if (s.kind == 1 && s.threads == 384) return launch_stream_t<384, false, 4>(h, a, maxp);
+  if (s.kind == 2 && s.threads == 384) return launch_stream_t<384, true, 4>(h, a, maxp);
+  if (s.kind == 2 && s.threads == 256) return launch_stream_t<256, true, 6>(h, a, maxp);
+  if (s.kind == 2 && s.threads == 512) return launch_stream_t<512, true, 3>(h, a, maxp);
 #define LS2D_CASE(T, P, B) \
-  if (s.threads == T && s.ppt == P && s.minb == B) return launch_icp_t<T, P, B>(h, a);
+  if (s.kind == 0 && s.threads == T && s.ppt == P && s.minb == B) return launch_icp_t<T, P, B>(h, a);
   LS2D_CASE(128, 2, 6)
   LS2D_CASE(128, 4, 6)
   LS2D_CASE(256, 3, 3)
@@ -182,7 +211,6 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   LS2D_CASE(256, 5, 4)
   LS2D_CASE(384, 3, 3)
   LS2D_CASE(128, 9, 5)
-  LS2D_CASE(128, 9, 6)
   LS2D_CASE(256, 6, 2)
   LS2D_CASE(256, 8, 2)
   LS2D_CASE(512, 8, 1)

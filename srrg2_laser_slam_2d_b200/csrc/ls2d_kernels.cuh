@@ -140,6 +140,142 @@ __device__ __forceinline__ void publish_pose(pose_bc* bc, const dev_params& P, c
   bc->stop = stop;
 }
 
+// gates of CorrespondenceFinderProjective2f (.cpp:61-73) + SE2Plane2PlaneErrorFactor + Cauchy + H/b terms for the
+// winner M of one column against the fixed cell (F, fd); adds into the thread's partial sums.
+template <bool SENSOR>
+__device__ __forceinline__ void linearize_point(const dev_params& P, const pose_bc* bc, float fd, const float4 F,
+                                                const float4 M, float rho, float Xtx, float Xty, float Lc, float Ls,
+                                                float (&acc)[16], unsigned& cnt) {
+  do {
+      if (fd < 0.f) break;  // fcell.source_idx < 0
+      if (fabsf(fsub(fd, rho)) > P.point_distance) break;
+      const float nx = fadd(fmul(Lc, M.z), fmul(-Ls, M.w));  // transformed normal
+      const float ny = fadd(fmul(Ls, M.z), fmul(Lc, M.w));
+      if (fadd(fmul(nx, F.z), fmul(ny, F.w)) < P.normal_cos) break;
+      // SE2Plane2PlaneErrorFactor (R/registration/aligner_slice_processor_laser_2d.h:8,23)
+      float px, py;
+      if (SENSOR) {
+        const float qx = fadd(fadd(fmul(bc->Xc, M.x), fmul(-bc->Xs, M.y)), Xtx);
+        const float qy = fadd(fadd(fmul(bc->Xs, M.x), fmul(bc->Xc, M.y)), Xty);
+        iso_apply(P.Sinv, qx, qy, px, py);
+      } else {
+        px = fadd(fadd(fmul(Lc, M.x), fmul(-Ls, M.y)), Xtx);
+        py = fadd(fadd(fmul(Ls, M.x), fmul(Lc, M.y)), Xty);
+      }
+      const float dx = fsub(px, F.x), dy = fsub(py, F.y);
+      const float e0 = fadd(fmul(dx, F.z), fmul(dy, F.w));
+      const float e1 = fsub(nx, F.z), e2 = fsub(ny, F.w);
+      const float Ja = fadd(fmul(F.z, Lc), fmul(F.w, Ls));
+      const float Jb = fadd(fmul(F.z, -Ls), fmul(F.w, Lc));
+      const float Jc = fadd(fmul(Ja, -M.y), fmul(Jb, M.x));
+      const float d0 = -ny, d1 = nx;  // R * (-n.y, n.x)^T, exact in binary32
+      const float chi = fadd(fadd(fmul(e0, e0), fmul(e1, e1)), fmul(e2, e2));
+      float w = 1.f, chi_in = chi, chi_k = 0.f;
+      if (P.tau > 0.f && !(chi < P.tau)) {  // RobustifierCauchy (L0.json:76-81)
+        const float aux = fadd(fmul(chi, P.inv_tau), 1.f);
+        chi_k           = fmul(P.tau, __logf(aux));  // statistics only (tolerance parity)
+        w               = fdiv(1.f, aux);
+        chi_in          = 0.f;
+        cnt += 1u << 16;
+      } else {
+        cnt += 1u;
+      }
+      const float wa = fmul(Ja, w), wb = fmul(Jb, w), wc = fmul(Jc, w);
+      const float wd0 = fmul(d0, w), wd1 = fmul(d1, w);
+      acc[0]  = fadd(acc[0], fmul(wa, Ja));
+      acc[1]  = fadd(acc[1], fmul(wa, Jb));
+      acc[2]  = fadd(acc[2], fmul(wa, Jc));
+      acc[3]  = fadd(acc[3], fmul(wb, Jb));
+      acc[4]  = fadd(acc[4], fmul(wb, Jc));
+      acc[5]  = fadd(acc[5], fadd(fadd(fmul(wc, Jc), fmul(wd0, d0)), fmul(wd1, d1)));
+      acc[6]  = fadd(acc[6], fmul(wa, e0));
+      acc[7]  = fadd(acc[7], fmul(wb, e0));
+      acc[8]  = fadd(acc[8], fadd(fadd(fmul(wc, e0), fmul(wd0, e1)), fmul(wd1, e2)));
+      acc[9]  = fadd(acc[9], chi_in);
+      acc[10] = fadd(acc[10], chi_k);
+  } while (false);
+}
+
+// reduction stage 1: warp shuffle tree, one partial row per warp in shared memory
+__device__ __forceinline__ void store_partials(float (&acc)[16], unsigned cnt, float* red, int lane, int warp) {
+  const float wsum    = warp_reduce_slots(acc, lane);
+  const unsigned wcnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (!(lane & 1) && lane < 2 * NSUM) red[warp * RED_STRIDE + (lane >> 1)] = wsum;
+  if (lane == 0) red[warp * RED_STRIDE + NSUM] = __uint_as_float(wcnt);
+}
+
+// reduction stage 2 + Gauss-Newton step, executed by warp 0 after the barrier: lanes 0..10 add the warps' partials in
+// warp order, lane 0 checks the correspondence gate, solves the 3x3 system in binary64, applies X <- X * v2t(dx)
+// (VariableSE2Right) and publishes the next pose.
+template <int T, bool SENSOR>
+__device__ __forceinline__ void warp0_update(const dev_params& P, const align_args& A, pose_bc* bc, const float* red,
+                                             int pair, int it, int lane, float& tot, unsigned& tot_cnt) {
+  if (lane < NSUM) {
+    tot = red[lane];
+#pragma unroll
+    for (int w = 1; w < T / 32; ++w) tot = fadd(tot, red[w * RED_STRIDE + lane]);
+  } else if (lane == NSUM) {
+    tot_cnt = 0;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) tot_cnt += __float_as_uint(red[w * RED_STRIDE + NSUM]);
+  }
+  float v[NSUM];
+#pragma unroll
+  for (int s = 0; s < NSUM; ++s) v[s] = __shfl_sync(0xffffffffu, tot, s);
+  const unsigned c2 = __shfl_sync(0xffffffffu, tot_cnt, NSUM);
+  if (lane == 0) {
+    const int n_in = c2 & 0xffff, n_k = c2 >> 16, n_corr = n_in + n_k;
+    iso X;
+    X.tx = bc->Xtx, X.ty = bc->Xty, X.c = bc->Xc, X.s = bc->Xs;
+    int stop = 0;
+    float dx[3];
+    if (n_corr <= P.min_num_correspondences) {
+      stop = 1 + LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES;
+    } else if (!A.score_only) {
+      if (!solve3(v, P.damping, dx)) {
+        stop = 1 + LS2D_STATUS_SINGULAR;
+      } else {
+        X = iso_compose(X, iso_v2t(dx[0], dx[1], dx[2]));
+        if (A.iters) {
+          ls2d_iter_stats st;
+          st.x = X.tx, st.y = X.ty, st.theta = atan2f_fdlibm(X.s, X.c);
+          st.chi_inliers = v[9], st.chi_kernelized = v[10];
+          st.n_inliers = n_in, st.n_kernelized = n_k, st.n_corr = n_corr;
+          A.iters[(size_t) pair * P.max_iterations + it] = st;
+        }
+      }
+    }
+    publish_pose(bc, P, X, SENSOR, stop);
+  }
+}
+
+// final record of a pair, written by thread 0 (called by the whole warp 0)
+__device__ __forceinline__ void write_result(const dev_params& P, const align_args& A, const pose_bc* bc, int pair,
+                                             int it, int status, float tot, unsigned tot_cnt) {
+  float v[NSUM];
+#pragma unroll
+  for (int s = 0; s < NSUM; ++s) v[s] = __shfl_sync(0xffffffffu, tot, s);
+  const unsigned c2 = __shfl_sync(0xffffffffu, tot_cnt, NSUM);
+  if (threadIdx.x == 0) {
+    int n_in = c2 & 0xffff, n_k = c2 >> 16;
+    const int n_corr = n_in + n_k;
+    if (status == LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES) {  // the oracle reports empty sums here
+#pragma unroll
+      for (int s = 0; s < NSUM; ++s) v[s] = 0.f;
+      n_in = n_k = 0;
+    }
+    if (status < 0) status = n_in < P.min_num_inliers ? LS2D_STATUS_NOT_ENOUGH_INLIERS : LS2D_STATUS_SUCCESS;
+    ls2d_result r;
+    r.x = bc->Xtx, r.y = bc->Xty, r.theta = atan2f_fdlibm(bc->Xs, bc->Xc);
+    r.chi_inliers = v[9], r.chi_kernelized = v[10];
+    r.n_inliers = n_in, r.n_kernelized = n_k, r.n_corr = n_corr;
+    r.status = status, r.iterations = it;
+#pragma unroll
+    for (int s = 0; s < 6; ++s) r.H[s] = v[s];
+    A.out[pair] = r;
+  }
+}
+
 constexpr size_t icp_smem_bytes(int cols, int threads) {
   return (size_t) cols * (16 + 4 + 4 + 4) + (size_t)(threads / 32) * RED_STRIDE * 4 + sizeof(pose_bc) + 16;
 }
@@ -273,62 +409,9 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
         bc->tie = 1;  // two points of equal minimal rho in one column: redo this iteration exactly
         continue;
       }
-      const float fd = fdepth[c];
-      if (fd < 0.f) continue;  // fcell.source_idx < 0
-      const float rho = u2f(rb[j]);
-      if (fabsf(fsub(fd, rho)) > P.point_distance) continue;
-      const float4 F = fimg[c];
-      const float4 M = mp[j];
-      const float nx = fadd(fmul(Lc, M.z), fmul(-Ls, M.w));  // transformed normal
-      const float ny = fadd(fmul(Ls, M.z), fmul(Lc, M.w));
-      if (fadd(fmul(nx, F.z), fmul(ny, F.w)) < P.normal_cos) continue;
-      // SE2Plane2PlaneErrorFactor (R/registration/aligner_slice_processor_laser_2d.h:8,23)
-      float px, py;
-      if (SENSOR) {
-        const float qx = fadd(fadd(fmul(bc->Xc, M.x), fmul(-bc->Xs, M.y)), Xtx);
-        const float qy = fadd(fadd(fmul(bc->Xs, M.x), fmul(bc->Xc, M.y)), Xty);
-        iso_apply(P.Sinv, qx, qy, px, py);
-      } else {
-        px = fadd(fadd(fmul(Lc, M.x), fmul(-Ls, M.y)), Xtx);
-        py = fadd(fadd(fmul(Ls, M.x), fmul(Lc, M.y)), Xty);
-      }
-      const float dx = fsub(px, F.x), dy = fsub(py, F.y);
-      const float e0 = fadd(fmul(dx, F.z), fmul(dy, F.w));
-      const float e1 = fsub(nx, F.z), e2 = fsub(ny, F.w);
-      const float Ja = fadd(fmul(F.z, Lc), fmul(F.w, Ls));
-      const float Jb = fadd(fmul(F.z, -Ls), fmul(F.w, Lc));
-      const float Jc = fadd(fmul(Ja, -M.y), fmul(Jb, M.x));
-      const float d0 = -ny, d1 = nx;  // R * (-n.y, n.x)^T, exact in binary32
-      const float chi = fadd(fadd(fmul(e0, e0), fmul(e1, e1)), fmul(e2, e2));
-      float w = 1.f, chi_in = chi, chi_k = 0.f;
-      if (P.tau > 0.f && !(chi < P.tau)) {  // RobustifierCauchy (L0.json:76-81)
-        const float aux = fadd(fmul(chi, P.inv_tau), 1.f);
-        chi_k           = fmul(P.tau, __logf(aux));  // statistics only (tolerance parity)
-        w               = fdiv(1.f, aux);
-        chi_in          = 0.f;
-        cnt += 1u << 16;
-      } else {
-        cnt += 1u;
-      }
-      const float wa = fmul(Ja, w), wb = fmul(Jb, w), wc = fmul(Jc, w);
-      const float wd0 = fmul(d0, w), wd1 = fmul(d1, w);
-      acc[0]  = fadd(acc[0], fmul(wa, Ja));
-      acc[1]  = fadd(acc[1], fmul(wa, Jb));
-      acc[2]  = fadd(acc[2], fmul(wa, Jc));
-      acc[3]  = fadd(acc[3], fmul(wb, Jb));
-      acc[4]  = fadd(acc[4], fmul(wb, Jc));
-      acc[5]  = fadd(acc[5], fadd(fadd(fmul(wc, Jc), fmul(wd0, d0)), fmul(wd1, d1)));
-      acc[6]  = fadd(acc[6], fmul(wa, e0));
-      acc[7]  = fadd(acc[7], fmul(wb, e0));
-      acc[8]  = fadd(acc[8], fadd(fadd(fmul(wc, e0), fmul(wd0, e1)), fmul(wd1, e2)));
-      acc[9]  = fadd(acc[9], chi_in);
-      acc[10] = fadd(acc[10], chi_k);
+      linearize_point<SENSOR>(P, bc, fdepth[c], fimg[c], mp[j], u2f(rb[j]), Xtx, Xty, Lc, Ls, acc, cnt);
     }
-    // reduction: warp shuffle tree, then one shared-memory stage over the warps
-    const float wsum    = warp_reduce_slots(acc, lane);
-    const unsigned wcnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (!(lane & 1) && lane < 2 * NSUM) red[warp * RED_STRIDE + (lane >> 1)] = wsum;
-    if (lane == 0) red[warp * RED_STRIDE + NSUM] = __uint_as_float(wcnt);
+    store_partials(acc, cnt, red, lane, warp);
     __syncthreads();
     // hand the touched cells back for the next pass (every toucher writes the same EMPTY values)
 #pragma unroll
@@ -345,45 +428,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
       continue;               // the next pass starts after the barrier at the loop head
     }
     exact = false;
-    if (warp == 0) {
-      if (lane < NSUM) {
-        tot = red[lane];
-#pragma unroll
-        for (int w = 1; w < T / 32; ++w) tot = fadd(tot, red[w * RED_STRIDE + lane]);
-      } else if (lane == NSUM) {
-        tot_cnt = 0;
-#pragma unroll
-        for (int w = 0; w < T / 32; ++w) tot_cnt += __float_as_uint(red[w * RED_STRIDE + NSUM]);
-      }
-      float v[NSUM];
-#pragma unroll
-      for (int s = 0; s < NSUM; ++s) v[s] = __shfl_sync(0xffffffffu, tot, s);
-      const unsigned c2 = __shfl_sync(0xffffffffu, tot_cnt, NSUM);
-      if (lane == 0) {
-        const int n_in = c2 & 0xffff, n_k = c2 >> 16, n_corr = n_in + n_k;
-        iso X;
-        X.tx = Xtx, X.ty = Xty, X.c = bc->Xc, X.s = bc->Xs;
-        int stop = 0;
-        float dx[3];
-        if (n_corr <= P.min_num_correspondences) {
-          stop = 1 + LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES;
-        } else if (!A.score_only) {
-          if (!solve3(v, P.damping, dx)) {
-            stop = 1 + LS2D_STATUS_SINGULAR;
-          } else {
-            X = iso_compose(X, iso_v2t(dx[0], dx[1], dx[2]));  // VariableSE2Right: X <- X * v2t(dx)
-            if (A.iters) {
-              ls2d_iter_stats st;
-              st.x = X.tx, st.y = X.ty, st.theta = atan2f_fdlibm(X.s, X.c);
-              st.chi_inliers = v[9], st.chi_kernelized = v[10];
-              st.n_inliers = n_in, st.n_kernelized = n_k, st.n_corr = n_corr;
-              A.iters[(size_t) pair * P.max_iterations + it] = st;
-            }
-          }
-        }
-        publish_pose(bc, P, X, SENSOR, stop);
-      }
-    }
+    if (warp == 0) warp0_update<T, SENSOR>(P, A, bc, red, pair, it, lane, tot, tot_cnt);
     __syncthreads();
     if (bc->stop) {
       status = bc->stop - 1;
@@ -391,31 +436,154 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
     }
   }
 
-  if (tid < 32) {
-    float v[NSUM];
-#pragma unroll
-    for (int s = 0; s < NSUM; ++s) v[s] = __shfl_sync(0xffffffffu, tot, s);
-    const unsigned c2 = __shfl_sync(0xffffffffu, tot_cnt, NSUM);
-    if (tid == 0) {
-      int n_in = c2 & 0xffff, n_k = c2 >> 16;
-      const int n_corr = n_in + n_k;
-      if (status == LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES) {  // the oracle reports empty sums here
-#pragma unroll
-        for (int s = 0; s < NSUM; ++s) v[s] = 0.f;
-        n_in = n_k = 0;
-      }
-      if (status < 0)
-        status = n_in < P.min_num_inliers ? LS2D_STATUS_NOT_ENOUGH_INLIERS : LS2D_STATUS_SUCCESS;
-      ls2d_result r;
-      r.x = bc->Xtx, r.y = bc->Xty, r.theta = atan2f_fdlibm(bc->Xs, bc->Xc);
-      r.chi_inliers = v[9], r.chi_kernelized = v[10];
-      r.n_inliers = n_in, r.n_kernelized = n_k, r.n_corr = n_corr;
-      r.status = status, r.iterations = it;
-#pragma unroll
-      for (int s = 0; s < 6; ++s) r.H[s] = v[s];
-      A.out[pair] = r;
+  if (tid < 32) write_result(P, A, bc, pair, it, status, tot, tot_cnt);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// icp_stream_kernel: same algorithm and the same reduction shape (thread t owns points t, t+T, ...; ascending) for
+// clouds of any size.  Per-point state does not live in registers: column and rho of every point are stashed in
+// shared memory (6 B/point) by the projection pass and re-read by the later passes; the points themselves are
+// either staged in shared memory once (MP_SMEM, 16 B/point) or re-read from global memory / L2 every pass.
+constexpr size_t icp_stream_smem_bytes(int cols, int threads, int max_points, bool mp_smem) {
+  return (size_t) cols * (16 + 4 + 4 + 4) + (size_t)(threads / 32) * RED_STRIDE * 4 + sizeof(pose_bc) + 16 +
+         (size_t) max_points * 4 + (size_t)((max_points + 1) / 2) * 4 + 16 + (mp_smem ? (size_t) max_points * 16 : 0);
+}
+
+template <int T, bool SENSOR, bool MP_SMEM, int MINB>
+__global__ void __launch_bounds__(T, MINB) icp_stream_kernel(const dev_params P, const align_args A, int max_points) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C          = P.cam.cols;
+  float4* fimg         = reinterpret_cast<float4*>(smem_raw);
+  float4* smp          = fimg + C;                                            // MP_SMEM: the moving cloud
+  float* fdepth        = reinterpret_cast<float*>(smp + (MP_SMEM ? max_points : 0));
+  unsigned* zdepth     = reinterpret_cast<unsigned*>(fdepth + C);
+  unsigned* zidx       = zdepth + C;
+  unsigned* srho       = zidx + C;                                            // [max_points] rho bits
+  unsigned short* scol = reinterpret_cast<unsigned short*>(srho + max_points);  // [max_points] column, 0xFFFF = none
+  float* red           = reinterpret_cast<float*>(scol + 2 * ((max_points + 1) / 2));
+  pose_bc* bc          = reinterpret_cast<pose_bc*>(red + (T / 32) * RED_STRIDE);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair = blockIdx.x;
+  const int fcl  = A.fixed_const >= 0 ? A.fixed_const : (A.fixed_id ? A.fixed_id[pair] : pair);
+  const int mcl  = A.moving_id ? A.moving_id[pair / A.moving_div] : pair / A.moving_div;
+  const int f0 = A.fixed_off[fcl], nf = A.fixed_off[fcl + 1] - f0;
+  const int m0 = A.moving_off[mcl], nm = A.moving_off[mcl + 1] - m0;
+  const float4* fpts = A.fixed_pts + f0;
+  const float4* mpts = A.moving_pts + m0;
+
+  for (int k = tid; k < C; k += T) {
+    fdepth[k] = -1.f;
+    zdepth[k] = Z_EMPTY_DEPTH;
+    zidx[k]   = Z_EMPTY_IDX;
+  }
+  if (MP_SMEM)
+    for (int i = tid; i < nm; i += T) smp[i] = ldg4(mpts + i);
+  if (tid == 0) {
+    const iso X = iso_v2t(A.init_xyt[3 * pair], A.init_xyt[3 * pair + 1], A.init_xyt[3 * pair + 2]);
+    publish_pose(bc, P, X, SENSOR, 0);
+    bc->tie = 0;
+  }
+  __syncthreads();
+
+  // ---- fixed range image (identity camera), exact two-pass z-buffer
+  for (int i = tid; i < nf; i += T) {
+    const float4 p  = ldg4(fpts + i);
+    const float rho = fsqrt(fadd(fmul(p.x, p.x), fmul(p.y, p.y)));
+    int col         = -1;
+    if (!(rho < P.range_min || rho > P.range_max)) col = polar_column(P.cam, p.y, p.x);
+    scol[i] = (unsigned short) (col < 0 ? 0xFFFF : col);
+    srho[i] = f2u(rho);
+    if (col >= 0) atomicMin(&zdepth[col], f2u(rho));
+  }
+  __syncthreads();
+  for (int i = tid; i < nf; i += T) {
+    const unsigned c = scol[i];
+    if (c != 0xFFFF && zdepth[c] == srho[i]) atomicMin(&zidx[c], (unsigned) i);
+  }
+  __syncthreads();
+  for (int i = tid; i < nf; i += T) {
+    const unsigned c = scol[i];
+    if (c != 0xFFFF && zidx[c] == (unsigned) i) {
+      fimg[c]   = ldg4(fpts + i);
+      fdepth[c] = u2f(srho[i]);
     }
   }
+  __syncthreads();
+  for (int i = tid; i < nf; i += T) {
+    const unsigned c = scol[i];
+    if (c != 0xFFFF) zdepth[c] = Z_EMPTY_DEPTH, zidx[c] = Z_EMPTY_IDX;
+  }
+  __syncthreads();
+
+  const int max_it = A.score_only ? 1 : P.max_iterations;
+  int it           = 0;
+  int status       = -1;
+  float tot        = 0.f;
+  unsigned tot_cnt = 0;
+  bool exact       = false;
+  for (; it < max_it; ++it) {
+    const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
+    if (exact) __syncthreads();
+    for (int i = tid; i < nm; i += T) {
+      const float4 M  = MP_SMEM ? smp[i] : ldg4(mpts + i);
+      const float rx  = fadd(fmul(Lc, M.x), fmul(-Ls, M.y));
+      const float ry  = fadd(fmul(Ls, M.x), fmul(Lc, M.y));
+      const float px  = fadd(rx, Wtx);
+      const float py  = fadd(ry, Wty);
+      const float rho = fsqrt(fadd(fmul(px, px), fmul(py, py)));
+      int col         = -1;
+      if (!(rho < P.range_min || rho > P.range_max)) col = polar_column(P.cam, py, px);
+      scol[i] = (unsigned short) (col < 0 ? 0xFFFF : col);
+      srho[i] = f2u(rho);
+      if (col >= 0) atomicMin(&zdepth[col], f2u(rho));
+    }
+    __syncthreads();
+    if (exact) {
+      for (int i = tid; i < nm; i += T) {
+        const unsigned c = scol[i];
+        if (c != 0xFFFF && zdepth[c] == srho[i]) atomicMin(&zidx[c], (unsigned) i);
+      }
+      __syncthreads();
+    }
+    float acc[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) acc[s] = 0.f;
+    unsigned cnt = 0;
+    for (int i = tid; i < nm; i += T) {
+      const unsigned c = scol[i];
+      if (c == 0xFFFF || zdepth[c] != srho[i]) continue;
+      if (exact) {
+        if (zidx[c] != (unsigned) i) continue;
+      } else if (atomicCAS(&zidx[c], Z_EMPTY_IDX, (unsigned) i) != Z_EMPTY_IDX) {
+        bc->tie = 1;
+        continue;
+      }
+      const float4 M = MP_SMEM ? smp[i] : ldg4(mpts + i);
+      linearize_point<SENSOR>(P, bc, fdepth[c], fimg[c], M, u2f(srho[i]), Xtx, Xty, Lc, Ls, acc, cnt);
+    }
+    store_partials(acc, cnt, red, lane, warp);
+    __syncthreads();
+    for (int i = tid; i < nm; i += T) {
+      const unsigned c = scol[i];
+      if (c != 0xFFFF) zdepth[c] = Z_EMPTY_DEPTH, zidx[c] = Z_EMPTY_IDX;
+    }
+    if (!exact && bc->tie) {
+      __syncthreads();
+      if (tid == 0) bc->tie = 0;
+      exact = true;
+      --it;
+      continue;
+    }
+    exact = false;
+    if (warp == 0) warp0_update<T, SENSOR>(P, A, bc, red, pair, it, lane, tot, tot_cnt);
+    __syncthreads();
+    if (bc->stop) {
+      status = bc->stop - 1;
+      break;
+    }
+  }
+  if (tid < 32) write_result(P, A, bc, pair, it, status, tot, tot_cnt);
 }
 
 // ---------------------------------------------------------------------------------------------------

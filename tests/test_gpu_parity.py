@@ -116,7 +116,8 @@ def test_demo_scene_projection(handle_factory):
 
 # ------------------------------------------------------------------ seeded batches vs the oracle
 @pytest.mark.parametrize("n_beams,cols,n_pairs", [(1081, 1081, 192), (721, 721, 96), (361, 361, 64), (181, 90, 32),
-                                                  (1500, 1081, 24), (2000, 721, 16), (4000, 1081, 8)])
+                                                  (1500, 1081, 24), (2000, 721, 16), (4000, 1081, 8),
+                                                  (6000, 1081, 6), (8192, 721, 6)])
 def test_seeded_batch_tree_bit_exact_and_sequential_tolerance(handle_factory, oracle, n_beams, cols, n_pairs):
     sp = make_scan_pairs(n_pairs, n_beams=n_beams, seed=1000 + n_beams)
     kw = dict(canvas_cols=cols, normal_cos=0.9)
@@ -213,9 +214,9 @@ def test_zero_pairs_and_bad_arguments(handle_factory):
         h.align_batch(np.zeros((1, 3), np.float32), fixed_id=[7], moving_id=[0])
     with pytest.raises(Ls2dError):
         h.set_params(default_params(canvas_cols=0))
-    big = np.zeros((5000, 4), np.float32)
-    h.upload_clouds(LS2D_MOVING, big, np.array([0, 5000], np.int32))
-    with pytest.raises(Ls2dError):                      # beyond the compiled kernel table: loud, no fallback
+    big = np.zeros((70000, 4), np.float32)
+    h.upload_clouds(LS2D_MOVING, big, np.array([0, 70000], np.int32))
+    with pytest.raises(Ls2dError):                      # beyond what the kernels can hold on chip: loud, no fallback
         h.align_batch(np.zeros((1, 3), np.float32), fixed_id=[0], moving_id=[0])
 
 
@@ -373,3 +374,20 @@ def test_zbuffer_ties_first_index_wins(handle_factory, oracle):
         gfi, gmi = h.find_correspondences(p, p, sp.init_xyt[p])
         assert np.array_equal(fi, gfi) and np.array_equal(mi, gmi)
         assert (mi < 500).all()                                     # of each duplicated pair the first copy wins
+
+
+@pytest.mark.parametrize("variant", ["10", "11", "12", "13"])
+def test_streaming_kernel_variants_are_bit_exact(oracle, variant, monkeypatch):
+    """The shared-memory / L2-streaming kernel (the path of clouds > 4096 points) forced onto 1081-point clouds:
+    same algorithm, same reduction shape, so the same bit-exact parity bar."""
+    from srrg2_laser_slam_2d_b200 import Handle
+    monkeypatch.setenv("LS2D_ICP_VARIANT", variant)
+    sp = make_scan_pairs(48, n_beams=1081, seed=404)
+    kw = dict(canvas_cols=1081, normal_cos=0.9)
+    with Handle(0, default_params(**kw)) as h:
+        upload(h, sp)
+        g, gi = h.align_batch(sp.init_xyt, want_iters=True)
+        o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts,
+                                   sp.moving_off, sp.init_xyt, sum_mode=oracle.SUM_TREE,
+                                   tree_threads=reduction_threads(1081), n_threads=oracle.max_threads())
+    assert_bit_exact(g, o, gi, oi)
