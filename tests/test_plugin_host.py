@@ -154,7 +154,7 @@ def test_plugin_aligner_matches_abi_and_oracle(exe, tmp_path, handle_factory, or
 
 
 @pytest.mark.gpu
-def test_plugin_loop_detector_verification(exe, tmp_path, handle_factory):
+def test_plugin_loop_detector_verification(exe, tmp_path, handle_factory, oracle):
     from srrg2_laser_slam_2d_b200 import Gates, default_params
     from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING
     from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
@@ -172,7 +172,11 @@ def test_plugin_loop_detector_verification(exe, tmp_path, handle_factory):
     h = handle_factory(default_params(**kw))
     h.upload_clouds(LS2D_FIXED, sp.fixed_pts, sp.fixed_off)
     h.upload_clouds(LS2D_MOVING, sp.moving_pts, sp.moving_off)
-    best, ref = h.verify(0, None, guesses, Gates(300, 0.1, 0.8), want_all=True)
+    # the detector takes its initial guesses as Isometry2f; they cross the C ABI as t2v(isometry)
+    rt = guesses.copy().reshape(-1, 3)
+    for k in range(len(rt)):
+        oracle.lib().orc_t2v(oracle.v2t(*rt[k]), rt[k:k + 1].ctypes.data)
+    best, ref = h.verify(0, None, rt.reshape(guesses.shape), Gates(300, 0.1, 0.8), want_all=True)
     assert same(allr, ref) is None
     assert (cand, guess, n_inl) == (int(best["candidate"]), int(best["guess"]), int(best["n_inliers"]))
     assert cand == 0                                       # the true match
