@@ -200,6 +200,27 @@ int ls2d_verify_sharded_nccl(ls2d_handle* h, int32_t query_id, const int32_t* ca
                              const ls2d_gates* gates, int32_t candidate_base, void* nccl_comm,
                              int32_t n_ranks, ls2d_best* best);
 
+/* ---- local-map maintenance around the aligner -------------------------------
+ * replaces: SceneClipperProjective2D::compute with voxelize_resolution == 0, the value both shipped
+ * configurations use (R/mapping/scene_clipper_projective_2d.cpp:11-65): for request r the scene cloud
+ * cloud_ids[r] of set `which` is seen from robot_in_local_map[r] * sensor_in_robot; the z-buffer winners, in
+ * column order, come back as points in the ROBOT frame: out_points [n * canvas_cols * 4], out_counts [n]. */
+int ls2d_clip_scenes(ls2d_handle* h, int which, const int32_t* cloud_ids, const float* robot_in_local_map_xyt,
+                     const float* sensor_in_robot_xyt, int32_t n, float* out_points, int32_t* out_counts);
+/* replaces: MergerProjective2D::compute (R/mapping/merger_projective_2d.cpp:9-100): merges a measurement cloud
+ * into a scene IN PLACE (add / average+renormalise / replace / ordered append per column, merge_threshold
+ * as the reference's PARAM).  scene_points holds `capacity` points of which *scene_size are valid; the call
+ * needs capacity >= *scene_size + canvas_cols, else LS2D_ERR_INVALID.  counters (nullable) = {new, merged,
+ * replaced}. */
+int ls2d_merge_scene(ls2d_handle* h, float* scene_points, int32_t* scene_size, int32_t capacity,
+                     const float* measurement_points, int32_t n_measurement,
+                     const float* measurement_in_scene_xyt, float merge_threshold, int32_t* counters);
+/* device-resident variant, asynchronous: scene_size_dev and counters_dev (4 ints: new, merged, replaced,
+ * overflow) live on the device */
+int ls2d_merge_scene_dev(ls2d_handle* h, void* scene_points_dev, int32_t* scene_size_dev, int32_t capacity,
+                         const void* measurement_points_dev, int32_t n_measurement,
+                         const float* measurement_in_scene_xyt, float merge_threshold, int32_t* counters_dev);
+
 /* ---- introspection ---------------------------------------------------------------------------------*/
 /* threads per pair the fused kernel uses for clouds of up to max_points points: fixes the shape of its
  * H/b reduction tree (the oracle's ORC_SUM_TREE mode mirrors it) */

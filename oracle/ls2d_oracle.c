@@ -577,3 +577,108 @@ void orc_column_n(const orc_params* prm, const float* y, const float* x, int32_t
     col[i]        = (c < 0 || c >= C) ? -1 : (int32_t) c;
   }
 }
+
+/* ---------------------------------------------------------------- next rows
+ *
+ * D14 PointNormal2f arithmetic in the merger (merger_projective_2d.cpp:72-74): "+=" and "*= 0.5f" act on all
+ *     four fields, normalize() renormalises the normal only, with Eigen's rule (divide by sqrt(squaredNorm)
+ *     when squaredNorm > 0). */
+
+static int iso_is_identity(orc_iso T) {
+  return T.c == 1.f && T.s == 0.f && T.tx == 0.f && T.ty == 0.f;
+}
+
+/* SceneClipperProjective2D::compute with voxelize_resolution == 0 (both shipped configurations)
+ * R/mapping/scene_clipper_projective_2d.cpp:22-62.  out holds canvas_cols points; returns the count. */
+int32_t orc_clip_scene(const orc_params* prm, const orc_point* scene, int32_t n_scene,
+                       orc_iso robot_in_local_map, orc_iso sensor_in_robot, orc_point* out) {
+  const int32_t C = prm->canvas_cols;
+  orc_cell* img   = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
+  const orc_iso sensor_in_local_map = orc_compose(robot_in_local_map, sensor_in_robot); /* :29 */
+  orc_project(prm, sensor_in_local_map, scene, n_scene, img);                             /* :31-32 */
+  int32_t k = 0;
+  for (int32_t c = 0; c < C; ++c) { /* :50-56 */
+    if (img[c].source_idx < 0) {
+      continue;
+    }
+    out[k].x  = img[c].px;
+    out[k].y  = img[c].py;
+    out[k].nx = img[c].nx;
+    out[k].ny = img[c].ny;
+    ++k;
+  }
+  if (!iso_is_identity(sensor_in_robot)) { /* :60-62 move the local scene in robot's coords */
+    for (int32_t i = 0; i < k; ++i) {
+      float x, y, nx, ny;
+      apply(sensor_in_robot, out[i].x, out[i].y, &x, &y);
+      rot(sensor_in_robot, out[i].nx, out[i].ny, &nx, &ny);
+      out[i].x = x, out[i].y = y, out[i].nx = nx, out[i].ny = ny;
+    }
+  }
+  free(img);
+  return k;
+}
+
+/* MergerProjective2D::compute, R/mapping/merger_projective_2d.cpp:9-100.  `scene` must have room for
+ * n_scene + canvas_cols points.  counters = {new, merged, replaced}.  Returns the new scene size. */
+int32_t orc_merge(const orc_params* prm, float merge_threshold, orc_point* scene, int32_t n_scene,
+                  const orc_point* measurement, int32_t n_measurement, orc_iso measurement_in_scene,
+                  int32_t* counters) {
+  const int32_t C  = prm->canvas_cols;
+  orc_cell* simg   = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
+  orc_cell* mimg   = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
+  orc_point* tmeas = (orc_point*) malloc(sizeof(orc_point) * (size_t)(n_measurement > 0 ? n_measurement : 1));
+  orc_project(prm, measurement_in_scene, scene, n_scene, simg); /* :19-20 */
+  for (int32_t i = 0; i < n_measurement; ++i) {                 /* :22-23 transformInPlace */
+    apply(measurement_in_scene, measurement[i].x, measurement[i].y, &tmeas[i].x, &tmeas[i].y);
+    rot(measurement_in_scene, measurement[i].nx, measurement[i].ny, &tmeas[i].nx, &tmeas[i].ny);
+  }
+  orc_project(prm, measurement_in_scene, tmeas, n_measurement, mimg); /* :24-25 */
+  int32_t scene_size = n_scene;
+  int32_t n_new = 0, n_merged = 0, n_replaced = 0;
+  for (int32_t c = 0; c < C; ++c) { /* :39-89 */
+    orc_cell* s = &simg[c];
+    orc_cell* m = &mimg[c];
+    if (m->depth > .9f * prm->range_max) { /* :46 */
+      m->source_idx = -1;
+    }
+    if (m->source_idx < 0) { /* :51 */
+      continue;
+    }
+    const orc_point mp = tmeas[m->source_idx];
+    if (s->source_idx < 0) { /* :57 */
+      scene[scene_size++] = mp;
+      ++n_new;
+      continue;
+    }
+    orc_point* sp      = &scene[s->source_idx];
+    const float dr     = m->depth - s->depth; /* :66 */
+    const float abs_dr = fabsf(dr);
+    if (abs_dr < merge_threshold) { /* :71-76, D14 */
+      float x = sp->x + mp.x, y = sp->y + mp.y, nx = sp->nx + mp.nx, ny = sp->ny + mp.ny;
+      x *= 0.5f, y *= 0.5f, nx *= 0.5f, ny *= 0.5f;
+      const float z = nx * nx + ny * ny;
+      if (z > 0.f) {
+        const float nrm = sqrtf(z);
+        nx = nx / nrm;
+        ny = ny / nrm;
+      }
+      sp->x = x, sp->y = y, sp->nx = nx, sp->ny = ny;
+      ++n_merged;
+      continue;
+    }
+    if (dr > 0) { /* :80-84 measure is behind: replace */
+      *sp = mp;
+      ++n_replaced;
+      continue;
+    }
+    scene[scene_size++] = mp; /* :87-88 */
+  }
+  if (counters) {
+    counters[0] = n_new, counters[1] = n_merged, counters[2] = n_replaced;
+  }
+  free(simg);
+  free(mimg);
+  free(tmeas);
+  return scene_size;
+}

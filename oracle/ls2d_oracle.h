@@ -144,6 +144,17 @@ int32_t orc_best_of(const orc_result* r, int32_t n, int32_t min_inliers, float m
 
 int32_t orc_max_threads(void);
 
+/* SceneClipperProjective2D::compute (voxelize_resolution == 0): visibility clip of a scene seen from
+ * robot_in_local_map * sensor_in_robot; `out` holds canvas_cols points; returns the count */
+int32_t orc_clip_scene(const orc_params* prm, const orc_point* scene, int32_t n_scene,
+                       orc_iso robot_in_local_map, orc_iso sensor_in_robot, orc_point* out);
+
+/* MergerProjective2D::compute: merges `measurement` into `scene` (room for n_scene + canvas_cols points
+ * required); counters = {new, merged, replaced} (nullable); returns the new scene size */
+int32_t orc_merge(const orc_params* prm, float merge_threshold, orc_point* scene, int32_t n_scene,
+                  const orc_point* measurement, int32_t n_measurement, orc_iso measurement_in_scene,
+                  int32_t* counters);
+
 /* host libm bulk drivers for tests/test_math_host.py */
 void orc_libm_atan2f_n(const float* y, const float* x, float* out, long n);
 void orc_libm_sincosf_n(const float* x, float* s, float* c, long n);

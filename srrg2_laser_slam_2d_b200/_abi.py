@@ -53,6 +53,7 @@ EXPORTS = [
     "ls2d_align_batch", "ls2d_align_batch_dev", "ls2d_align_pairs_host", "ls2d_score_batch",
     "ls2d_score_batch_dev", "ls2d_find_correspondences", "ls2d_project", "ls2d_verify", "ls2d_verify_dev",
     "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_threads", "ls2d_launch_count",
+    "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev",
 ]
 
 _lib = None
@@ -90,6 +91,9 @@ def load():
     L.ls2d_verify_dev.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]
     L.ls2d_reduce_best.argtypes = [vp, i32, vp]
     L.ls2d_verify_sharded_nccl.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, i32, vp]
+    L.ls2d_clip_scenes.argtypes = [vp, C.c_int, vp, vp, vp, i32, vp, vp]
+    L.ls2d_merge_scene.argtypes = [vp, vp, C.POINTER(i32), i32, vp, i32, vp, f32, vp]
+    L.ls2d_merge_scene_dev.argtypes = [vp, vp, vp, i32, vp, i32, vp, f32, vp]
     L.ls2d_reduction_threads.argtypes = [i32]
     L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
     _lib = L
@@ -246,6 +250,31 @@ class Handle:
         idx, depth = np.zeros(cols, np.int32), np.zeros(cols, np.float32)
         self._check(self._L.ls2d_project(self._h, which, cloud_id, _ptr(xyt), _ptr(idx), _ptr(depth)))
         return idx, depth
+
+    # ---- local-map maintenance
+    def clip_scenes(self, which: int, cloud_ids, robot_in_local_map_xyt, sensor_in_robot_xyt=(0.0, 0.0, 0.0)):
+        """SceneClipperProjective2D (voxelize off): returns a list of clipped clouds [k_r, 4] in the robot frame."""
+        ids = _i32(cloud_ids)
+        rob = _f32(robot_in_local_map_xyt).reshape(-1, 3)
+        sen = _f32(sensor_in_robot_xyt)
+        n, cols = len(ids), self.params.canvas_cols
+        out = np.zeros((n, cols, 4), np.float32)
+        cnt = np.zeros(n, np.int32)
+        self._check(self._L.ls2d_clip_scenes(self._h, which, _ptr(ids), _ptr(rob), _ptr(sen), n, _ptr(out), _ptr(cnt)))
+        return [out[r, :cnt[r]].copy() for r in range(n)]
+
+    def merge_scene(self, scene: np.ndarray, measurement: np.ndarray, measurement_in_scene_xyt, merge_threshold: float = 0.2):
+        """MergerProjective2D: returns (new scene [n, 4], counters [new, merged, replaced])."""
+        scene, measurement = _f32(scene), _f32(measurement)
+        cap = len(scene) + self.params.canvas_cols
+        buf = np.zeros((cap, 4), np.float32)
+        buf[:len(scene)] = scene
+        size = C.c_int32(len(scene))
+        counters = np.zeros(3, np.int32)
+        xyt = _f32(measurement_in_scene_xyt)
+        self._check(self._L.ls2d_merge_scene(self._h, _ptr(buf), C.byref(size), cap, _ptr(measurement), len(measurement),
+                                             _ptr(xyt), merge_threshold, _ptr(counters)))
+        return buf[:size.value].copy(), counters
 
     # ---- loop-closure verification
     def verify(self, query_id: int, candidate_ids, guesses_xyt, gates: Gates, candidate_base: int = 0,

@@ -647,6 +647,93 @@ int ls2d_verify_sharded_nccl(ls2d_handle* h, int32_t query_id, const int32_t* ca
   return ls2d_reduce_best(host.data(), n_ranks, best);
 }
 
+int ls2d_clip_scenes(ls2d_handle* h, int which, const int32_t* cloud_ids, const float* robot_xyt,
+                     const float* sensor_xyt, int32_t n, float* out_points, int32_t* out_counts) {
+  if (!h || (which != 0 && which != 1) || !cloud_ids || !robot_xyt || !sensor_xyt || !out_points || !out_counts || n < 0)
+    return LS2D_ERR_INVALID;
+  const cloud_set& c = h->sets[which];
+  if (!c.pts || !c.off) return LS2D_ERR_NOT_READY;
+  if (n == 0) return LS2D_OK;
+  for (int i = 0; i < n; ++i)
+    if (cloud_ids[i] < 0 || cloud_ids[i] >= c.n_clouds) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  const int C = h->dp.cam.cols;
+  int rc;
+  if ((rc = h2d(h, h->d_mid, cloud_ids, sizeof(int) * (size_t) n))) return rc;
+  if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * 3 * (size_t) n))) return rc;
+  const size_t out_bytes = sizeof(float4) * (size_t) n * C;
+  if ((rc = reserve(h->d_misc, out_bytes + sizeof(int) * (size_t) n))) return rc;
+  clip_args a;
+  a.pts       = c.pts;
+  a.off       = c.off;
+  a.cloud_ids = (const int*) h->d_mid.p;
+  a.robot_xyt = (const float*) h->d_init.p;
+  memcpy(a.sensor_xyt, sensor_xyt, sizeof(float) * 3);
+  a.out    = (float4*) h->d_misc.p;
+  a.counts = (int*) ((char*) h->d_misc.p + out_bytes);
+  const size_t smem = sizeof(unsigned) * 2 * (size_t) C;
+  CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  clip_kernel<<<n, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  CU(cudaMemcpyAsync(out_points, a.out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(out_counts, a.counts, sizeof(int) * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
+}
+
+int ls2d_merge_scene_dev(ls2d_handle* h, void* scene_dev, int32_t* scene_size_dev, int32_t capacity,
+                         const void* meas_dev, int32_t n_meas, const float* mis_xyt, float merge_threshold,
+                         int32_t* counters_dev) {
+  if (!h || !scene_dev || !scene_size_dev || capacity < 0 || (!meas_dev && n_meas > 0) || n_meas < 0 || !mis_xyt)
+    return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  merge_args a;
+  a.scene      = (float4*) scene_dev;
+  a.scene_size = scene_size_dev;
+  a.capacity   = capacity;
+  a.meas       = (const float4*) meas_dev;
+  a.n_meas     = n_meas;
+  memcpy(a.mis_xyt, mis_xyt, sizeof(float) * 3);
+  a.merge_threshold = merge_threshold;
+  a.counters        = counters_dev;
+  const size_t smem = sizeof(unsigned) * 4 * (size_t) h->dp.cam.cols;
+  CU(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  merge_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int ls2d_merge_scene(ls2d_handle* h, float* scene, int32_t* scene_size, int32_t capacity, const float* meas,
+                     int32_t n_meas, const float* mis_xyt, float merge_threshold, int32_t* counters) {
+  if (!h || !scene || !scene_size || !mis_xyt || n_meas < 0 || (!meas && n_meas > 0)) return LS2D_ERR_INVALID;
+  if (*scene_size < 0 || capacity < *scene_size + h->dp.cam.cols) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  const size_t scene_bytes = sizeof(float4) * (size_t) capacity;
+  const size_t meas_bytes  = sizeof(float4) * (size_t) n_meas;
+  if ((rc = reserve(h->d_misc, scene_bytes + meas_bytes + 64))) return rc;
+  char* base     = (char*) h->d_misc.p;
+  float4* d_scene = (float4*) base;
+  float4* d_meas  = (float4*) (base + scene_bytes);
+  int* d_ints     = (int*) (base + scene_bytes + meas_bytes);  // [0] = size, [1..4] = counters
+  CU(cudaMemcpyAsync(d_scene, scene, sizeof(float4) * (size_t) *scene_size, cudaMemcpyHostToDevice, h->stream));
+  if (n_meas) CU(cudaMemcpyAsync(d_meas, meas, meas_bytes, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_ints, scene_size, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = ls2d_merge_scene_dev(h, d_scene, d_ints, capacity, d_meas, n_meas, mis_xyt, merge_threshold, d_ints + 1)))
+    return rc;
+  int ints[5];
+  CU(cudaMemcpyAsync(ints, d_ints, sizeof(ints), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (ints[4]) return LS2D_ERR_INVALID;  // cannot happen with the capacity check above
+  CU(cudaMemcpyAsync(scene, d_scene, sizeof(float4) * (size_t) ints[0], cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *scene_size = ints[0];
+  if (counters) counters[0] = ints[1], counters[1] = ints[2], counters[2] = ints[3];
+  return LS2D_OK;
+}
+
 int ls2d_reduction_threads(int32_t max_points) {
   int variant = 0;
   if (const char* v = getenv("LS2D_ICP_VARIANT")) variant = atoi(v);

@@ -100,16 +100,16 @@ __device__ __forceinline__ bool solve3(const float* v, float damping, float* dx)
   const double H22 = dadd((double) v[5], (double) damping);
   const double r0 = -(double) v[6], r1 = -(double) v[7], r2 = -(double) v[8];
   if (!(H00 > 0.0)) return false;
-  const double i0  = ddiv(1.0, H00);
+  const double i0  = drcp(H00);
   const double l10 = dmul(H01, i0), l20 = dmul(H02, i0);
   const double d1  = dsub(H11, dmul(l10, H01));
   if (!(d1 > 0.0)) return false;
-  const double i1  = ddiv(1.0, d1);
+  const double i1  = drcp(d1);
   const double t21 = dsub(H12, dmul(l20, H01));
   const double l21 = dmul(t21, i1);
   const double d2  = dsub(dsub(H22, dmul(l20, H02)), dmul(l21, t21));
   if (!(d2 > 0.0)) return false;
-  const double i2 = ddiv(1.0, d2);
+  const double i2 = drcp(d2);
   const double z1 = dsub(r1, dmul(l10, r0));
   const double z2 = dsub(dsub(r2, dmul(l20, r0)), dmul(l21, z1));
   const double y0 = dmul(r0, i0), y1 = dmul(z1, i1), x2 = dmul(z2, i2);
@@ -174,7 +174,7 @@ __device__ __forceinline__ void linearize_point(const dev_params& P, const pose_
       if (P.tau > 0.f && !(chi < P.tau)) {  // RobustifierCauchy (L0.json:76-81)
         const float aux = fadd(fmul(chi, P.inv_tau), 1.f);
         chi_k           = fmul(P.tau, __logf(aux));  // statistics only (tolerance parity)
-        w               = fdiv(1.f, aux);
+        w               = frcp(aux);
         chi_in          = 0.f;
         cnt += 1u << 16;
       } else {
@@ -586,13 +586,33 @@ __global__ void __launch_bounds__(T, MINB) icp_stream_kernel(const dev_params P,
   if (tid < 32) write_result(P, A, bc, pair, it, status, tot, tot_cnt);
 }
 
+// ordered block-wide compaction step: every thread calls it with its flag for column k0 + threadIdx.x; returns the
+// output slot of flagged threads (ascending column order) and advances *base.  warp_tot: 32 ints of shared memory.
+__device__ __forceinline__ int ordered_slot(bool ok, int* warp_tot, int* base) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const unsigned ballot = __ballot_sync(0xffffffffu, ok);
+  if (lane == 0) warp_tot[warp] = __popc(ballot);
+  __syncthreads();
+  int before = *base;
+  for (int w = 0; w < warp; ++w) before += warp_tot[w];
+  const int dst = before + __popc(ballot & ((1u << lane) - 1u));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = *base;
+    for (int w = 0; w < nwarp; ++w) t += warp_tot[w];
+    *base = t;
+  }
+  __syncthreads();
+  return dst;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // z-buffer projection of an arbitrary-size cloud with strided loops (API / parity kernels).
 // W = world -> camera isometry.  On return (after the trailing barrier) zidx[c] holds the winner of
 // column c (Z_EMPTY_IDX if none) and zdepth[c] its rho bits.
-template <bool IDENTITY>
+template <bool IDENTITY, bool PLAIN_LOAD = false>
 __device__ __forceinline__ void zbuffer_project(const dev_params& P, const iso& W, const float4* pts, int n,
-                                                unsigned* zdepth, unsigned* zidx) {
+                                                unsigned* zdepth, unsigned* zidx, const iso* pre = nullptr) {
   const int C = P.cam.cols;
   for (int k = threadIdx.x; k < C; k += blockDim.x) {
     zdepth[k] = Z_EMPTY_DEPTH;
@@ -601,9 +621,15 @@ __device__ __forceinline__ void zbuffer_project(const dev_params& P, const iso& 
   __syncthreads();
   for (int pass = 0; pass < 2; ++pass) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float4 p = ldg4(pts + i);
+      const float4 p = PLAIN_LOAD ? pts[i] : ldg4(pts + i);  // PLAIN_LOAD: the buffer is written later in this kernel
       float px = p.x, py = p.y;
-      if (!IDENTITY) iso_apply(W, p.x, p.y, px, py);
+      if (pre) {  // the cloud is first moved by *pre (merger: measurement -> scene frame), then seen from the camera
+        float qx, qy;
+        iso_apply(*pre, p.x, p.y, qx, qy);
+        iso_apply(W, qx, qy, px, py);
+      } else if (!IDENTITY) {
+        iso_apply(W, p.x, p.y, px, py);
+      }
       const float rho = fsqrt(fadd(fmul(px, px), fmul(py, py)));
       if (rho < P.range_min || rho > P.range_max) continue;
       const int col = polar_column(P.cam, py, px);
@@ -671,7 +697,6 @@ __global__ void correspond_kernel(const dev_params P, const correspond_args A) {
   zbuffer_project<false>(P, W, A.moving_pts + m0, nm, zdm, zim);
   if (threadIdx.x == 0) base = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int k0 = 0; k0 < C; k0 += blockDim.x) {  // ascending columns, ordered compaction (.cpp:55-74)
     const int k = k0 + threadIdx.x;
     bool ok     = false;
@@ -687,25 +712,147 @@ __global__ void correspond_kernel(const dev_params P, const correspond_args A) {
         ok = !(fadd(fmul(nx, F.z), fmul(ny, F.w)) < P.normal_cos);
       }
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) warp_tot[warp] = __popc(ballot);
-    __syncthreads();
-    int before = base;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    const int dst = ordered_slot(ok, warp_tot, &base);
     if (ok) {
-      const int dst     = before + __popc(ballot & ((1u << lane) - 1u));
       A.fixed_idx[dst]  = fi;
       A.moving_idx[dst] = mi;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int t = base;
-      for (int w = 0; w < nwarp; ++w) t += warp_tot[w];
-      base = t;
-    }
-    __syncthreads();
   }
   if (threadIdx.x == 0) *A.count = base;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SceneClipperProjective2D::compute with voxelize_resolution == 0 (R/mapping/scene_clipper_projective_2d.cpp:22-62):
+// the z-buffer winners of the scene seen from robot_in_local_map * sensor_in_robot, in column order, as points in
+// the sensor frame, then moved into the robot frame.  One CTA per request.
+struct clip_args {
+  const float4* pts;
+  const int* off;
+  const int* cloud_ids;     // [n]
+  const float* robot_xyt;   // [n * 3] robot_in_local_map
+  float sensor_xyt[3];      // sensor_in_robot
+  float4* out;              // [n * C]
+  int* counts;              // [n]
+};
+
+__global__ void clip_kernel(const dev_params P, const clip_args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C      = P.cam.cols;
+  unsigned* zdepth = reinterpret_cast<unsigned*>(smem_raw);
+  unsigned* zidx   = zdepth + C;
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const int r      = blockIdx.x;
+  const int cloud  = A.cloud_ids[r];
+  const int p0 = A.off[cloud], n = A.off[cloud + 1] - p0;
+  const iso S   = iso_v2t(A.sensor_xyt[0], A.sensor_xyt[1], A.sensor_xyt[2]);
+  const iso cam = iso_compose(iso_v2t(A.robot_xyt[3 * r], A.robot_xyt[3 * r + 1], A.robot_xyt[3 * r + 2]), S);
+  const iso W   = iso_inverse(cam);
+  const bool move = !(S.c == 1.f && S.s == 0.f && S.tx == 0.f && S.ty == 0.f);  // .cpp:60
+  zbuffer_project<false>(P, W, A.pts + p0, n, zdepth, zidx);
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < C; k0 += blockDim.x) {
+    const int k   = k0 + threadIdx.x;
+    const bool ok = k < C && zidx[k] != Z_EMPTY_IDX;
+    float4 o      = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      const float4 p = ldg4(A.pts + p0 + zidx[k]);
+      iso_apply(W, p.x, p.y, o.x, o.y);
+      iso_rot(W, p.z, p.w, o.z, o.w);
+      if (move) {
+        float x, y, nx, ny;
+        iso_apply(S, o.x, o.y, x, y);
+        iso_rot(S, o.z, o.w, nx, ny);
+        o = make_float4(x, y, nx, ny);
+      }
+    }
+    const int dst = ordered_slot(ok, warp_tot, &base);
+    if (ok) A.out[(size_t) r * C + dst] = o;
+  }
+  if (threadIdx.x == 0) A.counts[r] = base;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MergerProjective2D::compute (R/mapping/merger_projective_2d.cpp:9-100): both clouds projected from
+// measurement_in_scene, per-column add / average+renormalise / replace / append; the scene is updated in place
+// and grows by an ordered append.  One CTA per (scene, measurement) request.
+struct merge_args {
+  float4* scene;        // in/out, `capacity` points
+  int* scene_size;      // in/out
+  int capacity;
+  const float4* meas;
+  int n_meas;
+  float mis_xyt[3];     // measurement_in_scene
+  float merge_threshold;
+  int* counters;        // [4]: new, merged, replaced, overflow flag
+};
+
+__global__ void merge_kernel(const dev_params P, const merge_args A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C   = P.cam.cols;
+  unsigned* zds = reinterpret_cast<unsigned*>(smem_raw);
+  unsigned* zis = zds + C;
+  unsigned* zdm = zis + C;
+  unsigned* zim = zdm + C;
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  __shared__ int cnt[4];
+  const int n_scene = *A.scene_size;
+  const iso M = iso_v2t(A.mis_xyt[0], A.mis_xyt[1], A.mis_xyt[2]);
+  const iso W = iso_inverse(M);
+  zbuffer_project<false, true>(P, W, A.scene, n_scene, zds, zis, nullptr);   // .cpp:19-20 (plain loads: scene is written below)
+  zbuffer_project<false, true>(P, W, A.meas, A.n_meas, zdm, zim, &M);        // .cpp:22-25
+  if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const float far_limit = fmul(.9f, P.range_max);
+  for (int k0 = 0; k0 < C; k0 += blockDim.x) {
+    const int k  = k0 + threadIdx.x;
+    bool append  = false;
+    float4 mp    = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < C && zim[k] != Z_EMPTY_IDX && !(u2f(zdm[k]) > far_limit)) {      // .cpp:46-53
+      const float4 m = A.meas[zim[k]];
+      iso_apply(M, m.x, m.y, mp.x, mp.y);
+      iso_rot(M, m.z, m.w, mp.z, mp.w);
+      if (zis[k] == Z_EMPTY_IDX) {                                           // .cpp:57-62
+        append = true;
+        atomicAdd(&cnt[0], 1);
+      } else {
+        float4* sp     = A.scene + zis[k];
+        const float dr = fsub(u2f(zdm[k]), u2f(zds[k]));                     // .cpp:66
+        if (fabsf(dr) < A.merge_threshold) {                                 // .cpp:71-76
+          const float4 s = *sp;
+          float x = fmul(fadd(s.x, mp.x), 0.5f), y = fmul(fadd(s.y, mp.y), 0.5f);
+          float nx = fmul(fadd(s.z, mp.z), 0.5f), ny = fmul(fadd(s.w, mp.w), 0.5f);
+          const float z = fadd(fmul(nx, nx), fmul(ny, ny));
+          if (z > 0.f) {
+            const float nrm = fsqrt(z);
+            nx = fdiv(nx, nrm), ny = fdiv(ny, nrm);
+          }
+          *sp = make_float4(x, y, nx, ny);
+          atomicAdd(&cnt[1], 1);
+        } else if (dr > 0.f) {                                               // .cpp:80-84
+          *sp = mp;
+          atomicAdd(&cnt[2], 1);
+        } else {                                                             // .cpp:87-88
+          append = true;
+        }
+      }
+    }
+    const int dst = ordered_slot(append, warp_tot, &base);
+    if (append) {
+      if (n_scene + dst < A.capacity)
+        A.scene[n_scene + dst] = mp;
+      else
+        cnt[3] = 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *A.scene_size = n_scene + base < A.capacity ? n_scene + base : A.capacity;
+    if (A.counters) A.counters[0] = cnt[0], A.counters[1] = cnt[1], A.counters[2] = cnt[2], A.counters[3] = cnt[3];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -71,6 +71,9 @@ def lib():
         L.orc_accept.argtypes = [vp, i32, f32, f32]
         L.orc_accept.restype = i32
         L.orc_max_threads.restype = i32
+        L.orc_clip_scene.argtypes, L.orc_clip_scene.restype = [C.POINTER(OrcParams), vp, i32, OrcIso, OrcIso, vp], i32
+        L.orc_merge.argtypes = [C.POINTER(OrcParams), f32, vp, i32, vp, i32, OrcIso, vp]
+        L.orc_merge.restype = i32
         L.orc_libm_atan2f_n.argtypes = [vp, vp, vp, C.c_long]
         L.orc_libm_sincosf_n.argtypes = [vp, vp, vp, C.c_long]
         L.orc_column_n.argtypes = [C.POINTER(OrcParams), vp, vp, vp, C.c_long]
@@ -184,3 +187,23 @@ def column(prm: OrcParams, y: np.ndarray, x: np.ndarray) -> np.ndarray:
     col = np.zeros(len(x), np.int32)
     lib().orc_column_n(C.byref(prm), _ptr(y), _ptr(x), _ptr(col), len(x))
     return col
+
+
+def clip_scene(prm: OrcParams, scene: np.ndarray, robot_in_local_map_xyt, sensor_in_robot_xyt) -> np.ndarray:
+    """SceneClipperProjective2D::compute (voxelize off): returns the clipped cloud [k, 4] in the robot frame."""
+    scene = _f32(scene)
+    out = np.zeros((prm.canvas_cols, 4), np.float32)
+    k = lib().orc_clip_scene(C.byref(prm), _ptr(scene), len(scene), v2t(*robot_in_local_map_xyt),
+                             v2t(*sensor_in_robot_xyt), _ptr(out))
+    return out[:k].copy()
+
+
+def merge(prm: OrcParams, merge_threshold: float, scene: np.ndarray, measurement: np.ndarray, measurement_in_scene_xyt):
+    """MergerProjective2D::compute: returns (new scene [n, 4], counters [new, merged, replaced])."""
+    scene, measurement = _f32(scene), _f32(measurement)
+    buf = np.zeros((len(scene) + prm.canvas_cols, 4), np.float32)
+    buf[:len(scene)] = scene
+    counters = np.zeros(3, np.int32)
+    n = lib().orc_merge(C.byref(prm), merge_threshold, _ptr(buf), len(scene), _ptr(measurement), len(measurement),
+                        v2t(*measurement_in_scene_xyt), _ptr(counters))
+    return buf[:n].copy(), counters
