@@ -150,6 +150,70 @@ namespace srrg2_laser_slam_2d {
     for (int k = 0; k < n; ++k) (*_correspondences)[k] = Correspondence(fi[k], mi[k]);
   }
 
+  static void unflatten(const float* flat, size_t n, PointNormal2fVectorCloud& cloud) {
+    cloud.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      cloud[i].coordinates() = Vector2f(flat[4 * i], flat[4 * i + 1]);
+      cloud[i].normal()      = Vector2f(flat[4 * i + 2], flat[4 * i + 3]);
+      cloud[i].status        = Valid;
+    }
+  }
+
+  // R/mapping/scene_clipper_projective_2d.cpp:11-65
+  void SceneClipperProjective2D::compute() {
+    if (!_clipped_scene_in_robot || !_full_scene) {
+      _status = Error;
+      std::cerr << "SceneClipperProjective2D::compute| missing local OR global scene" << std::endl;
+      return;
+    }
+    if (!param_projector.value()) throw std::runtime_error("SceneClipperProjective2D::compute| Missing Projector");
+    if (param_voxelize_resolution.value() > 0)
+      throw std::runtime_error("SceneClipperProjective2D::compute| voxelize_resolution > 0 is not supported by the "
+                               "CUDA clipper (both shipped configurations set 0)");
+    ls2d_params p;
+    ls2d_default_params(&p);
+    param_projector->fillParams(p);
+    ls2d_handle* h = _device.handle();
+    Ls2dDevice::check(ls2d_set_params(h, &p), "SceneClipperProjective2D::compute");
+    std::vector<float> flat;
+    flattenCloud(*_full_scene, flat);
+    const int32_t off[2] = {0, (int32_t) _full_scene->size()};
+    Ls2dDevice::check(ls2d_upload_clouds(h, LS2D_FIXED, flat.data(), off, 1), "SceneClipperProjective2D::compute");
+    param_projector->setCameraPose(_robot_in_local_map * _sensor_in_robot);  // .cpp:29-31, visible to sharers
+    const Vector3f robot = geometry2d::t2v(_robot_in_local_map), sensor = geometry2d::t2v(_sensor_in_robot);
+    std::vector<float> out((size_t) p.canvas_cols * 4);
+    int32_t n        = 0;
+    const int32_t id = 0;
+    Ls2dDevice::check(ls2d_clip_scenes(h, LS2D_FIXED, &id, robot.v, sensor.v, 1, out.data(), &n),
+                      "SceneClipperProjective2D::compute");
+    unflatten(out.data(), (size_t) n, *_clipped_scene_in_robot);
+    _status = Successful;
+  }
+
+  // R/mapping/merger_projective_2d.cpp:9-100
+  void MergerProjective2D::compute() {
+    if (!param_projector.value()) throw std::runtime_error("MergerProjective2D::compute| Missing Projector");
+    if (!_scene || !_measurement) throw std::runtime_error("MergerProjective2D::compute| Missing scene or measurement");
+    ls2d_params p;
+    ls2d_default_params(&p);
+    param_projector->fillParams(p);
+    ls2d_handle* h = _device.handle();
+    Ls2dDevice::check(ls2d_set_params(h, &p), "MergerProjective2D::compute");
+    param_projector->setCameraPose(_measurement_in_scene);  // .cpp:19
+    std::vector<float> scene, meas;
+    flattenCloud(*_scene, scene);
+    flattenCloud(*_measurement, meas);
+    int32_t size           = (int32_t) _scene->size();
+    const int32_t capacity = size + p.canvas_cols;  // .cpp:31
+    scene.resize((size_t) capacity * 4);
+    const Vector3f xyt = geometry2d::t2v(_measurement_in_scene);
+    Ls2dDevice::check(ls2d_merge_scene(h, scene.data(), &size, capacity, meas.data(), (int32_t) _measurement->size(),
+                                       xyt.v, param_merge_threshold.value(), nullptr),
+                      "MergerProjective2D::compute");
+    unflatten(scene.data(), (size_t) size, *_scene);
+    _status = Success;
+  }
+
   void AlignerSliceProcessorLaser2DWithSensor::setupFactor() {
     (void) sensorInRobot();  // throws when the tf lookup fails, like setupFactorWithSensor
   }
@@ -173,6 +237,9 @@ namespace srrg2_laser_slam_2d {
     BOSS_REGISTER_CLASS(CorrespondenceFinderProjective2f);
     BOSS_REGISTER_CLASS(AlignerSliceProcessorLaser2D);
     BOSS_REGISTER_CLASS(AlignerSliceProcessorLaser2DWithSensor);
+    // R/instances.cpp:30,32
+    BOSS_REGISTER_CLASS(MergerProjective2D);
+    BOSS_REGISTER_CLASS(SceneClipperProjective2D);
     // explicit CUDA names, for configurations that want to say so
     BOSS_REGISTER_CLASS_AS(CorrespondenceFinderProjective2f, "CorrespondenceFinderProjective2fCUDA");
     BOSS_REGISTER_CLASS_AS(AlignerSliceProcessorLaser2D, "AlignerSliceProcessorLaser2DCUDA");

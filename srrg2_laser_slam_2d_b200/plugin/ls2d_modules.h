@@ -359,6 +359,56 @@ namespace srrg2_laser_slam_2d {
   };
   using AlignerSliceProcessorLaser2DWithSensorPtr = std::shared_ptr<AlignerSliceProcessorLaser2DWithSensor>;
 
+  // R/mapping/scene_clipper_projective_2d.{h,cpp}: visibility clip of the local map (the tracker's moving cloud).
+  // Driven as apps/visual_test_scene_clipper_projective_2d.cpp:103-114.
+  class SceneClipperProjective2D : public Configurable {
+  public:
+    enum Status { Error = 0, Ready = 1, Successful = 2 };
+    PARAM(PropertyConfigurable_<PointNormal2fProjectorPolar>, projector, "projector used to remap the points",
+          PointNormal2fProjectorPolarPtr(new PointNormal2fProjectorPolar), 0);
+    PARAM(PropertyFloat, voxelize_resolution, "resolution used to decimate the points in the scan on a grid [meters]",
+          0.1f, 0);
+    SceneClipperProjective2D() { _class_name = "SceneClipperProjective2D"; }
+    void setFullScene(PointNormal2fVectorCloud* scene) { _full_scene = scene; }
+    void setClippedSceneInRobot(PointNormal2fVectorCloud* scene) { _clipped_scene_in_robot = scene; }
+    void setRobotInLocalMap(const Isometry2f& T) { _robot_in_local_map = T; }
+    void setSensorInRobot(const Isometry2f& T) { _sensor_in_robot = T; }
+    void compute();
+    Status status() const { return _status; }
+
+  protected:
+    PointNormal2fVectorCloud* _full_scene             = nullptr;
+    PointNormal2fVectorCloud* _clipped_scene_in_robot = nullptr;
+    Isometry2f _robot_in_local_map, _sensor_in_robot;
+    Status _status = Error;
+    Ls2dDevice _device;
+  };
+  using SceneClipperProjective2DPtr = std::shared_ptr<SceneClipperProjective2D>;
+
+  // R/mapping/merger_projective_2d.{h,cpp}: merges an aligned measurement into the local map, in place.
+  // Driven as apps/visual_test_merger_projective_2d.cpp:120-123.
+  class MergerProjective2D : public Configurable {
+  public:
+    enum Status { Error = 0, Success = 1 };
+    PARAM(PropertyFloat, merge_threshold, "max distance for merging the points in the scene and the moving", 0.2f, 0);
+    PARAM(PropertyConfigurable_<PointNormal2fProjectorPolar>, projector, "projector to compute correspondences",
+          PointNormal2fProjectorPolarPtr(new PointNormal2fProjectorPolar), 0);
+    MergerProjective2D() { _class_name = "MergerProjective2D"; }
+    void setScene(PointNormal2fVectorCloud* scene) { _scene = scene; }
+    void setMeasurement(const PointNormal2fVectorCloud* m) { _measurement = m; }
+    void setMeasurementInScene(const Isometry2f& T) { _measurement_in_scene = T; }
+    void compute();
+    Status status() const { return _status; }
+
+  protected:
+    PointNormal2fVectorCloud* _scene             = nullptr;
+    const PointNormal2fVectorCloud* _measurement = nullptr;
+    Isometry2f _measurement_in_scene;
+    Status _status = Error;
+    Ls2dDevice _device;
+  };
+  using MergerProjective2DPtr = std::shared_ptr<MergerProjective2D>;
+
   // ELF-constructor registration, like R/instances.h:14
   void srrg2_laser_slam_2d_registerTypes() __attribute__((constructor));
 

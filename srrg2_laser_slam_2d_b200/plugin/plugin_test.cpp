@@ -59,7 +59,8 @@ static int selftest() {
   // registration happened in the ELF constructor (R/instances.h:14)
   for (const char* c : {"CorrespondenceFinderProjective2f", "AlignerSliceProcessorLaser2D",
                         "AlignerSliceProcessorLaser2DWithSensor", "MultiAligner2D", "PointNormal2fProjectorPolar",
-                        "RobustifierCauchy", "IterationAlgorithmGN", "Solver", "MultiLoopDetectorBruteForce2D"})
+                        "RobustifierCauchy", "IterationAlgorithmGN", "Solver", "MultiLoopDetectorBruteForce2D",
+                        "SceneClipperProjective2D", "MergerProjective2D"})
     REQUIRE(ClassRegistry::instance().has(c));
 
   ConfigurableManager m;
@@ -321,6 +322,51 @@ static int verify(const std::string& config, const std::string& name, const std:
   return 0;
 }
 
+static void writeCloud(std::ofstream& os, const PointNormal2fVectorCloud& c) {
+  const int32_t n = (int32_t) c.size();
+  os.write((const char*) &n, 4);
+  for (const auto& p : c) {
+    const float f[4] = {p.coordinates().x(), p.coordinates().y(), p.normal().x(), p.normal().y()};
+    os.write((const char*) f, sizeof(f));
+  }
+}
+
+// (GPU) the reference's clipper / merger call sequences (apps/visual_test_merger_projective_2d.cpp:103-123)
+// through the plugin classes, canvas = cols columns over the full circle
+static int map(int cols, const std::string& in, const std::string& out) {
+  PairsFile f = readPairs(in);
+  SceneClipperProjective2DPtr clipper(new SceneClipperProjective2D);
+  clipper->param_projector->param_canvas_cols.setValue((unsigned) cols);
+  clipper->param_voxelize_resolution.setValue(0.f);
+  MergerProjective2DPtr merger(new MergerProjective2D);
+  merger->param_projector->param_canvas_cols.setValue((unsigned) cols);
+  const Isometry2f sensor = geometry2d::v2t(Vector3f(f.sensor[0], f.sensor[1], f.sensor[2]));
+  std::ofstream os(out, std::ios::binary);
+  for (int p = 0; p < f.n_pairs; ++p) {
+    PointNormal2fVectorCloud clipped;
+    clipper->setFullScene(&f.fixed[p]);
+    clipper->setClippedSceneInRobot(&clipped);
+    clipper->setRobotInLocalMap(f.guesses[p][0]);
+    clipper->setSensorInRobot(sensor);
+    clipper->compute();
+    if (clipper->status() != SceneClipperProjective2D::Successful) return 1;
+    writeCloud(os, clipped);
+    PointNormal2fVectorCloud scene = f.fixed[p];
+    merger->setScene(&scene);
+    merger->setMeasurement(&f.moving[p]);
+    merger->setMeasurementInScene(f.guesses[p][0]);
+    merger->compute();
+    writeCloud(os, scene);
+  }
+  SceneClipperProjective2D unwired;
+  if (thrown([&] { unwired.param_projector.setValue(nullptr); PointNormal2fVectorCloud a, b; unwired.setFullScene(&a);
+                   unwired.setClippedSceneInRobot(&b); unwired.compute(); }) !=
+      "SceneClipperProjective2D::compute| Missing Projector")
+    return 1;
+  std::printf("MAP OK %d\n", f.n_pairs);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   try {
     const std::string cmd = argc > 1 ? argv[1] : "";
@@ -328,6 +374,7 @@ int main(int argc, char** argv) {
     if (cmd == "parse" && argc == 3) return parse(argv[2]);
     if (cmd == "align" && argc == 6) return align(argv[2], argv[3], argv[4], argv[5]);
     if (cmd == "verify" && argc == 6) return verify(argv[2], argv[3], argv[4], argv[5]);
+    if (cmd == "map" && argc == 5) return map(std::atoi(argv[2]), argv[3], argv[4]);
     std::fprintf(stderr, "usage: plugin_test selftest | parse <config> | align|verify <config> <name> <in> <out>\n");
     return 2;
   } catch (const std::exception& e) {

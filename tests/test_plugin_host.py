@@ -180,3 +180,37 @@ def test_plugin_loop_detector_verification(exe, tmp_path, handle_factory, oracle
     assert same(allr, ref) is None
     assert (cand, guess, n_inl) == (int(best["candidate"]), int(best["guess"]), int(best["n_inliers"]))
     assert cand == 0                                       # the true match
+
+
+@pytest.mark.gpu
+def test_plugin_clipper_and_merger_match_the_oracle(exe, tmp_path, oracle):
+    """SceneClipperProjective2D / MergerProjective2D through the plugin classes (the reference's call sequence,
+    apps/visual_test_merger_projective_2d.cpp:103-123) vs the oracle, bit for bit."""
+    from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
+    n, cols, sensor = 4, 721, (0.2, 0.1, 0.3)
+    sp = make_scan_pairs(n, n_beams=721, seed=33)
+    poses = (sp.gt_xyt + np.float32(0.02)).astype(np.float32)
+    inp, out = str(tmp_path / "map.bin"), str(tmp_path / "map_out.bin")
+    write_pairs(inp, sp, poses[:, None, :], sensor)
+    assert "MAP OK" in run(exe, "map", str(cols), inp, out)
+    raw = open(out, "rb").read()
+    pos = 0
+
+    def cloud():
+        nonlocal pos
+        k = struct.unpack_from("<i", raw, pos)[0]
+        c = np.frombuffer(raw, np.float32, 4 * k, pos + 4).reshape(k, 4)
+        pos += 4 + 16 * k
+        return c
+
+    prm = oracle.default_params(canvas_cols=cols)
+    rt = lambda v: (lambda a: (oracle.lib().orc_t2v(oracle.v2t(*v), a.ctypes.data), a)[1])(np.zeros(3, np.float32))
+    for p in range(n):
+        scene = sp.fixed_pts[sp.fixed_off[p]:sp.fixed_off[p + 1]]
+        meas = sp.moving_pts[sp.moving_off[p]:sp.moving_off[p + 1]]
+        pose, sen = rt(poses[p]), rt(sensor)          # isometries cross the C ABI as t2v(isometry)
+        clipped, merged = cloud(), cloud()
+        ref_c = oracle.clip_scene(prm, scene, pose, sen)
+        ref_m, _ = oracle.merge(prm, 0.2, scene, meas, pose)
+        assert clipped.shape == ref_c.shape and np.array_equal(clipped.view(np.uint32), ref_c.view(np.uint32))
+        assert merged.shape == ref_m.shape and np.array_equal(merged.view(np.uint32), ref_m.view(np.uint32))
