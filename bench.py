@@ -97,6 +97,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def dist_env():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     return rank, int(os.environ.get("LOCAL_RANK", rank)), world
@@ -120,7 +127,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     prm = ob.default_params(**TRACK)
-    cores = ob.max_threads()
+    cores = host_cores()  # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     sample_pairs = min(args.pairs, 4096)
     sp = make_workload(sample_pairs, 0xC0FFEE, "cpu")
     run = lambda: ob.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
@@ -265,7 +272,7 @@ def cpu_baseline(sp):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     prm = ob.default_params(**TRACK)
-    cores = ob.max_threads()
+    cores = host_cores()  # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     n = sp.n_pairs
     best = float("inf")
     for _ in range(3):
