@@ -30,6 +30,19 @@
  *      (finder: setCameraPose(local_map_in_sensor.inverse()),
  *      R/registration/correspondence_finder_projective_2d.cpp:47; projector applies the inverse
  *      of its camera pose) -- restated literally, since inverse(inverse(T)) != T in binary32.
+ *  Multi-slice aligner (MultiAligner2D with several slice processors; MULTI.json:700-730):
+ *  D14 every laser slice finds its correspondences with its own projector / finder / sensor_in_robot
+ *      and linearises with its own robustifier; a slice with n_corr <= min_num_correspondences is
+ *      skipped in that iteration (no H/b/statistics contribution); if no laser slice contributes the
+ *      aligner stops with NotEnoughCorrespondences.  n_corr reports the contributing slices' total
+ *      (on that failure: everything the finders produced).
+ *  D15 AlignerSliceOdom2DPrior = SE2PriorErrorFactor on VariableSE2Right: e = t2v(Z^-1 * X),
+ *      J = blockdiag(R(Z^-1 * X), 1) (exact derivative of e for X <- X * v2t(dx)), Omega as given;
+ *      chi = e^T (Omega e); Cauchy as D6 when the slice has a robustifier (the configurations: none).
+ *      The factor counts as ONE inlier (or one kernelized factor) in the statistics, not as a
+ *      correspondence.
+ *  D16 H and b are the binary32 sums of the slices' totals in slice order, the prior last.
+ *  D17 max_iterations, min_num_inliers and damping are aligner-level (read from slice 0's record).
  */
 #include "ls2d_oracle.h"
 
@@ -496,6 +509,212 @@ void orc_align_batch(const orc_params* prm, const orc_point* fixed_pts, const in
               moving_pts + moving_off[m], moving_off[m + 1] - moving_off[m], init_xyt + 3 * p,
               sum_mode, tree_threads, out + p,
               iter_stats ? iter_stats + (size_t) p * prm->max_iterations : NULL);
+  }
+}
+
+
+/* ---------------------------------------------------------------- multi-slice aligner (D14-D17) */
+
+/* SE2PriorErrorFactor [srrg2_solver types_2d/se2_prior_error_factor; slice class named at
+ * L0.json:291-310, MULTI.json:400-422] -- D15 */
+static void prior_eval(const orc_prior* pr, orc_iso X, float* e, orc_iso* P_out) {
+  const orc_iso Zinv = orc_inverse(orc_v2t(pr->z[0], pr->z[1], pr->z[2]));
+  const orc_iso P    = orc_compose(Zinv, X);
+  e[0]               = P.tx;
+  e[1]               = P.ty;
+  e[2]               = atan2f(P.s, P.c);
+  *P_out             = P;
+}
+
+void orc_prior_error_and_jacobian(const orc_prior* prior, orc_iso X, float* e, float* J) {
+  orc_iso P;
+  prior_eval(prior, X, e, &P);
+  J[0] = P.c, J[1] = -P.s, J[2] = 0.f;
+  J[3] = P.s, J[4] = P.c, J[5] = 0.f;
+  J[6] = 0.f, J[7] = 0.f, J[8] = 1.f;
+}
+
+/* the prior's H/b/chi contribution; returns 1 if inlier, 0 if kernelized */
+static int prior_contribution(const orc_prior* pr, orc_iso X, float* v) {
+  float e[3];
+  orc_iso P;
+  prior_eval(pr, X, e, &P);
+  const float* O = pr->information; /* O00 O01 O02 O11 O12 O22 */
+  const float Om[3][3] = {{O[0], O[1], O[2]}, {O[1], O[3], O[4]}, {O[2], O[4], O[5]}};
+  float Oe[3];
+  for (int i = 0; i < 3; ++i) {
+    Oe[i] = (Om[i][0] * e[0] + Om[i][1] * e[1]) + Om[i][2] * e[2];
+  }
+  const float chi = (e[0] * Oe[0] + e[1] * Oe[1]) + e[2] * Oe[2];
+  float w = 1.f, chi_in = chi, chi_k = 0.f;
+  int inlier      = 1;
+  const float tau = pr->cauchy_chi_threshold;
+  if (tau > 0.f && !(chi < tau)) { /* D6 */
+    const float aux = chi * (1.f / tau) + 1.f;
+    chi_k           = tau * logf(aux);
+    w               = 1.f / aux;
+    chi_in          = 0.f;
+    inlier          = 0;
+  }
+  /* A = J^T Omega (zeros of J skipped), scaled by w */
+  float A[3][3];
+  for (int j = 0; j < 3; ++j) {
+    A[0][j] = (P.c * Om[0][j] + P.s * Om[1][j]) * w;
+    A[1][j] = ((-P.s) * Om[0][j] + P.c * Om[1][j]) * w;
+    A[2][j] = Om[2][j] * w;
+  }
+  float H[3][3], b[3];
+  for (int i = 0; i < 3; ++i) {
+    H[i][0] = A[i][0] * P.c + A[i][1] * P.s;
+    H[i][1] = A[i][0] * (-P.s) + A[i][1] * P.c;
+    H[i][2] = A[i][2];
+    b[i]    = (A[i][0] * e[0] + A[i][1] * e[1]) + A[i][2] * e[2];
+  }
+  v[0] = H[0][0], v[1] = H[0][1], v[2] = H[0][2], v[3] = H[1][1], v[4] = H[1][2], v[5] = H[2][2];
+  v[6] = b[0], v[7] = b[1], v[8] = b[2];
+  v[9]  = chi_in;
+  v[10] = chi_k;
+  return inlier;
+}
+
+void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point* const* fixed,
+                     const int32_t* n_fixed, const orc_point* const* moving, const int32_t* n_moving,
+                     const orc_prior* prior, const float* init_xyt, int32_t sum_mode, int32_t tree_threads,
+                     orc_result* out, orc_iter_stats* iter_stats) {
+  const int32_t max_it = slices[0].max_iterations; /* D17 */
+  orc_cell* fixed_img[ORC_MAX_SLICES];
+  orc_iso Sinv[ORC_MAX_SLICES];
+  int32_t Cmax = 1;
+  for (int32_t s = 0; s < n_slices; ++s) {
+    const int32_t C = slices[s].canvas_cols;
+    Cmax            = C > Cmax ? C : Cmax;
+    fixed_img[s]    = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
+    orc_project(&slices[s], orc_v2t(0.f, 0.f, 0.f), fixed[s], n_fixed[s], fixed_img[s]);
+    Sinv[s] = orc_v2t(0.f, 0.f, 0.f);
+    if (slices[s].with_sensor) {
+      Sinv[s] = orc_inverse(orc_v2t(slices[s].sensor_in_robot[0], slices[s].sensor_in_robot[1],
+                                    slices[s].sensor_in_robot[2]));
+    }
+  }
+  orc_cell* moving_img = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) Cmax);
+  int32_t* fidx        = (int32_t*) malloc(sizeof(int32_t) * (size_t) Cmax);
+  int32_t* midx        = (int32_t*) malloc(sizeof(int32_t) * (size_t) Cmax);
+  orc_iso X            = orc_v2t(init_xyt[0], init_xyt[1], init_xyt[2]);
+  memset(out, 0, sizeof(*out));
+  if (iter_stats) {
+    memset(iter_stats, 0, sizeof(orc_iter_stats) * (size_t) max_it);
+  }
+  lin_sums tot;
+  memset(&tot, 0, sizeof(tot));
+  int32_t n_corr = 0, status = -1, it = 0;
+  for (; it < max_it; ++it) {
+    memset(&tot, 0, sizeof(tot));
+    n_corr          = 0;
+    int contributed = 0;
+    int32_t n_found = 0;
+    for (int32_t s = 0; s < n_slices; ++s) { /* D14 */
+      const orc_iso L  = slices[s].with_sensor ? orc_compose(Sinv[s], X) : X;
+      const int32_t nc = orc_find_correspondences(&slices[s], fixed_img[s], moving[s], n_moving[s], L, moving_img,
+                                                  fidx, midx);
+      n_found += nc;
+      if (nc <= slices[s].min_num_correspondences) {
+        continue;
+      }
+      lin_sums ss;
+      linearize(&slices[s], X, fixed[s], moving[s], n_moving[s], fidx, midx, nc, sum_mode, tree_threads, &ss);
+      for (int k = 0; k < NSLOT; ++k) { /* D16 */
+        tot.v[k] = contributed ? tot.v[k] + ss.v[k] : ss.v[k];
+      }
+      tot.n_inliers += ss.n_inliers;
+      tot.n_kernelized += ss.n_kernelized;
+      n_corr += nc;
+      contributed = 1;
+    }
+    if (!contributed) {
+      memset(&tot, 0, sizeof(tot));
+      n_corr = n_found; /* what the finders produced, as orc_align reports it */
+      status = ORC_STATUS_NOT_ENOUGH_CORRESPONDENCES;
+      break;
+    }
+    if (prior) {
+      float pv[NSLOT];
+      const int inl = prior_contribution(prior, X, pv);
+      for (int k = 0; k < NSLOT; ++k) {
+        tot.v[k] = tot.v[k] + pv[k];
+      }
+      tot.n_inliers += inl;
+      tot.n_kernelized += !inl;
+    }
+    float dx[3];
+    if (solve3(tot.v, slices[0].damping, dx) != 0) {
+      status = ORC_STATUS_SINGULAR;
+      break;
+    }
+    X = orc_compose(X, orc_v2t(dx[0], dx[1], dx[2]));
+    if (iter_stats) {
+      orc_iter_stats* st = &iter_stats[it];
+      float xyt[3];
+      orc_t2v(X, xyt);
+      st->x = xyt[0], st->y = xyt[1], st->theta = xyt[2];
+      st->chi_inliers    = tot.v[9];
+      st->chi_kernelized = tot.v[10];
+      st->n_inliers      = tot.n_inliers;
+      st->n_kernelized   = tot.n_kernelized;
+      st->n_corr         = n_corr;
+    }
+  }
+  if (status < 0) {
+    status = (tot.n_inliers < slices[0].min_num_inliers) ? ORC_STATUS_NOT_ENOUGH_INLIERS : ORC_STATUS_SUCCESS;
+  }
+  float xyt[3];
+  orc_t2v(X, xyt);
+  out->x = xyt[0], out->y = xyt[1], out->theta = xyt[2];
+  out->chi_inliers    = tot.v[9];
+  out->chi_kernelized = tot.v[10];
+  out->n_inliers      = tot.n_inliers;
+  out->n_kernelized   = tot.n_kernelized;
+  out->n_corr         = n_corr;
+  out->status         = status;
+  out->iterations     = it;
+  for (int k = 0; k < 6; ++k) {
+    out->H[k] = tot.v[k];
+  }
+  for (int32_t s = 0; s < n_slices; ++s) {
+    free(fixed_img[s]);
+  }
+  free(moving_img);
+  free(fidx);
+  free(midx);
+}
+
+void orc_align_multi_batch(const orc_params* slices, int32_t n_slices, const orc_point* const* fixed_pts,
+                           const int32_t* const* fixed_off, const orc_point* const* moving_pts,
+                           const int32_t* const* moving_off, const int32_t* fixed_id, const int32_t* moving_id,
+                           const orc_prior* prior, const float* prior_z, const float* init_xyt, int32_t n_pairs,
+                           int32_t sum_mode, int32_t tree_threads, int32_t n_threads, orc_result* out,
+                           orc_iter_stats* iter_stats) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8) num_threads(n_threads > 1 ? n_threads : 1)
+#endif
+  for (int32_t p = 0; p < n_pairs; ++p) {
+    const int32_t f = fixed_id ? fixed_id[p] : p;
+    const int32_t m = moving_id ? moving_id[p] : p;
+    const orc_point* fx[ORC_MAX_SLICES];
+    const orc_point* mv[ORC_MAX_SLICES];
+    int32_t nf[ORC_MAX_SLICES], nm[ORC_MAX_SLICES];
+    for (int32_t s = 0; s < n_slices; ++s) {
+      fx[s] = fixed_pts[s] + fixed_off[s][f];
+      nf[s] = fixed_off[s][f + 1] - fixed_off[s][f];
+      mv[s] = moving_pts[s] + moving_off[s][m];
+      nm[s] = moving_off[s][m + 1] - moving_off[s][m];
+    }
+    orc_prior pr;
+    if (prior && prior_z) {
+      pr = *prior;
+      memcpy(pr.z, prior_z + 3 * (size_t) p, sizeof(float) * 3);
+    }
+    orc_align_multi(slices, n_slices, fx, nf, mv, nm, (prior && prior_z) ? &pr : NULL, init_xyt + 3 * p, sum_mode,
+                    tree_threads, out + p, iter_stats ? iter_stats + (size_t) p * slices[0].max_iterations : NULL);
   }
 }
 

@@ -12,7 +12,7 @@
  * this path.  What is in-repo is followed line by line
  * (correspondence_finder_projective_2d.cpp:18-77); what lives in the un-vendored
  * dependencies is restated from their published behaviour, and every result-affecting
- * choice is a numbered decision point D1..D13 documented in ls2d_oracle.c.
+ * choice is a numbered decision point D1..D17 documented in ls2d_oracle.c.
  *
  * Arithmetic contract: every floating-point operation below is ONE IEEE-754 binary32
  * operation (no FMA contraction; build with -ffp-contract=off), in the order Eigen
@@ -134,6 +134,40 @@ void orc_align_batch(const orc_params* prm, const orc_point* fixed_pts, const in
                      const int32_t* fixed_id, const int32_t* moving_id, const float* init_xyt,
                      int32_t n_pairs, int32_t sum_mode, int32_t tree_threads, int32_t n_threads,
                      orc_result* out, orc_iter_stats* iter_stats);
+
+
+/* ---- multi-slice aligner (MULTI.json:700-730: laser_0 + odometry prior + laser_1 in one 3x3 system) ----
+ * A laser slice is described by an orc_params (its projector, finder, robustifier, min_num_correspondences and
+ * sensor_in_robot); max_iterations / min_num_inliers / damping are read from slice 0. */
+#define ORC_MAX_SLICES 4
+
+/* AlignerSliceOdom2DPrior -> SE2PriorErrorFactor (LASER_0.json:291-310, MULTI.json:400-422): the odometry's
+ * prediction z of moving_in_fixed with information matrix Omega (upper triangle O00 O01 O02 O11 O12 O22);
+ * cauchy_chi_threshold <= 0: no robustifier (both configurations: "#pointer" -1) */
+typedef struct {
+  float z[3];
+  float information[6];
+  float cauchy_chi_threshold;
+} orc_prior;
+
+/* e[3] and J[9] (row-major) of the prior factor at estimate X (decision D15) */
+void orc_prior_error_and_jacobian(const orc_prior* prior, orc_iso X, float* e, float* J);
+
+/* MultiAligner2D::compute() with n_slices laser slices (slice s aligns moving[s] onto fixed[s]) and an
+ * optional prior (NULL: none) */
+void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point* const* fixed,
+                     const int32_t* n_fixed, const orc_point* const* moving, const int32_t* n_moving,
+                     const orc_prior* prior, const float* init_xyt, int32_t sum_mode, int32_t tree_threads,
+                     orc_result* out, orc_iter_stats* iter_stats);
+
+/* batch: slice s reads clouds fixed_id[p] / moving_id[p] (NULL: p) of its own CSR sets; prior_z [n_pairs * 3]
+ * (NULL: no prior) shares information / threshold of `prior` */
+void orc_align_multi_batch(const orc_params* slices, int32_t n_slices, const orc_point* const* fixed_pts,
+                           const int32_t* const* fixed_off, const orc_point* const* moving_pts,
+                           const int32_t* const* moving_off, const int32_t* fixed_id, const int32_t* moving_id,
+                           const orc_prior* prior, const float* prior_z, const float* init_xyt, int32_t n_pairs,
+                           int32_t sum_mode, int32_t tree_threads, int32_t n_threads, orc_result* out,
+                           orc_iter_stats* iter_stats);
 
 /* loop-closure acceptance gates (MultiLoopDetectorBruteForce2D, LASER_0.json:627-634) and the
  * deterministic best-of rule. Returns index of the best accepted result or -1. */

@@ -224,3 +224,79 @@ def reference_demo_scene(n_points: int = 1024) -> np.ndarray:
     ny = s * corner[:, 2] + c * corner[:, 3]
     corner = np.stack([x, y, nx, ny], -1).astype(np.float32)
     return np.concatenate([circle, corner]).astype(np.float32)
+
+
+@dataclass
+class MultiSensorPairs:
+    """MULTI.json-shaped batch: one robot with several rangefinders.  Slice s aligns the shared moving cloud
+    (local-map surrogate, robot frame) onto fixed set s (the scan of sensor s, SENSOR frame)."""
+
+    fixed_pts: list            # per sensor [n_pairs * n_beams, 4] float32
+    fixed_off: list            # per sensor [n_pairs + 1] int32
+    moving_pts: np.ndarray     # [n_pairs * n_sensors * n_beams, 4] float32 (robot frame of the moving pose)
+    moving_off: np.ndarray     # [n_pairs + 1] int32
+    sensors: np.ndarray        # [n_sensors, 3] sensor_in_robot
+    gt_xyt: np.ndarray         # [n_pairs, 3] ground-truth moving_in_fixed
+    init_xyt: np.ndarray       # [n_pairs, 3]
+    odom_xyt: np.ndarray       # [n_pairs, 3] odometry's (noisy) prediction of moving_in_fixed: the prior slice's z
+
+    @property
+    def n_pairs(self) -> int:
+        return len(self.moving_off) - 1
+
+
+def make_multi_sensor_pairs(n_pairs: int, sensors=((0.2, 0.0, 0.0), (-0.2, 0.0, math.pi)), n_beams: int = 721,
+                            seed: int = 0xD0C, fov: float = HOKUYO_FOV, motion_xy: float = 0.05,
+                            motion_theta: float = 0.05, odom_noise_xy: float = 0.01, odom_noise_theta: float = 0.01,
+                            range_noise: float = 0.01, dropout: float = 0.02, range_max: float = 20.0,
+                            device: str = "cpu", chunk: int = 128) -> MultiSensorPairs:
+    """Two (or more) rangefinders on one robot (MULTI.json:160-188,372-422): fixed set s = scan of sensor s at robot
+    pose P in the sensor frame; moving = the scans of all sensors at robot pose P*delta moved into that robot
+    frame (what the scene clipper hands the aligner); ground truth moving_in_fixed = delta; initial guess =
+    identity; odom = delta with noise (the odometry prior's measurement)."""
+    rng = np.random.default_rng(seed)
+    S = np.asarray(sensors, np.float64)
+    n_s = len(S)
+    segs_np, circ_np = _make_worlds(rng, n_pairs)
+    P = np.stack([rng.uniform(-1.0, 1.0, n_pairs), rng.uniform(-1.0, 1.0, n_pairs),
+                  rng.uniform(-math.pi, math.pi, n_pairs)], -1)
+    delta = np.stack([rng.uniform(-motion_xy, motion_xy, n_pairs), rng.uniform(-motion_xy, motion_xy, n_pairs),
+                      rng.uniform(-motion_theta, motion_theta, n_pairs)], -1)
+    odom = delta + np.stack([rng.uniform(-odom_noise_xy, odom_noise_xy, n_pairs),
+                             rng.uniform(-odom_noise_xy, odom_noise_xy, n_pairs),
+                             rng.uniform(-odom_noise_theta, odom_noise_theta, n_pairs)], -1)
+    Pm = _t2v(_v2t(P) @ _v2t(delta))
+    noise = rng.normal(0.0, range_noise, (2, n_s, n_pairs, n_beams))
+    drop = rng.uniform(0.0, 1.0, (2, n_s, n_pairs, n_beams)) < dropout
+    beam = np.linspace(-0.5 * fov, 0.5 * fov, n_beams)
+    dev = torch.device(device)
+    beam_t = torch.from_numpy(beam).to(dev)
+    fixed = [np.empty((n_pairs, n_beams, 4), np.float32) for _ in range(n_s)]
+    moving = np.empty((n_pairs, n_s, n_beams, 4), np.float32)
+    for lo in range(0, n_pairs, chunk):
+        hi = min(n_pairs, lo + chunk)
+        segs = torch.from_numpy(segs_np[lo:hi]).to(dev)
+        circ = torch.from_numpy(circ_np[lo:hi]).to(dev)
+        for s in range(n_s):
+            for which, poses in ((0, P), (1, Pm)):
+                sensor_pose = _t2v(_v2t(poses[lo:hi]) @ _v2t(S[s]))
+                cloud = _scan_clouds(torch.from_numpy(sensor_pose).to(dev), segs, circ, beam_t,
+                                     torch.from_numpy(noise[which, s, lo:hi]).to(dev),
+                                     torch.from_numpy(drop[which, s, lo:hi]).to(dev), range_max).cpu().numpy()
+                if which == 0:
+                    fixed[s][lo:hi] = cloud.astype(np.float32)
+                else:  # sensor frame -> robot frame
+                    c, sn = math.cos(S[s, 2]), math.sin(S[s, 2])
+                    far = cloud[..., 0] > 1.0e5
+                    out = np.empty_like(cloud)
+                    out[..., 0] = c * cloud[..., 0] - sn * cloud[..., 1] + S[s, 0]
+                    out[..., 1] = sn * cloud[..., 0] + c * cloud[..., 1] + S[s, 1]
+                    out[..., 2] = c * cloud[..., 2] - sn * cloud[..., 3]
+                    out[..., 3] = sn * cloud[..., 2] + c * cloud[..., 3]
+                    out[far] = np.asarray(FAR_POINT)
+                    moving[lo:hi, s] = out.astype(np.float32)
+    off = (np.arange(n_pairs + 1, dtype=np.int64) * n_beams).astype(np.int32)
+    moff = (np.arange(n_pairs + 1, dtype=np.int64) * n_beams * n_s).astype(np.int32)
+    return MultiSensorPairs([f.reshape(-1, 4) for f in fixed], [off.copy() for _ in range(n_s)],
+                            moving.reshape(-1, 4), moff, S.astype(np.float32), delta.astype(np.float32),
+                            np.zeros_like(delta, dtype=np.float32), odom.astype(np.float32))

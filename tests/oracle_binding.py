@@ -21,6 +21,10 @@ class OrcParams(C.Structure):
                 ("sensor_in_robot", C.c_float * 3)]
 
 
+class OrcPrior(C.Structure):
+    _fields_ = [("z", C.c_float * 3), ("information", C.c_float * 6), ("cauchy_chi_threshold", C.c_float)]
+
+
 class OrcIso(C.Structure):
     _fields_ = [("tx", C.c_float), ("ty", C.c_float), ("c", C.c_float), ("s", C.c_float)]
 
@@ -66,6 +70,8 @@ def lib():
         L.orc_error_and_jacobian.argtypes = [C.POINTER(OrcParams), OrcIso, OrcPoint, OrcPoint, vp, vp]
         L.orc_align.argtypes = [C.POINTER(OrcParams), vp, i32, vp, i32, vp, i32, i32, vp, vp]
         L.orc_align_batch.argtypes = [C.POINTER(OrcParams), vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
+        L.orc_prior_error_and_jacobian.argtypes = [C.POINTER(OrcPrior), OrcIso, vp, vp]
+        L.orc_align_multi_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
         L.orc_best_of.argtypes = [vp, i32, i32, f32, f32]
         L.orc_best_of.restype = i32
         L.orc_accept.argtypes = [vp, i32, f32, f32]
@@ -156,6 +162,54 @@ def align_batch(prm: OrcParams, fixed_pts, fixed_off, moving_pts, moving_off, in
     lib().orc_align_batch(C.byref(prm), _ptr(fixed_pts), _ptr(fixed_off), _ptr(moving_pts), _ptr(moving_off),
                           _ptr(fixed_id), _ptr(moving_id), _ptr(init), n, sum_mode, tree_threads, n_threads,
                           _ptr(out), _ptr(its))
+    return out, its
+
+
+def make_prior(information, cauchy_chi_threshold=-1.0, z=(0.0, 0.0, 0.0)) -> OrcPrior:
+    """information: 6 floats (upper triangle O00 O01 O02 O11 O12 O22) or a 3x3 symmetric matrix"""
+    info = np.asarray(information, np.float32)
+    if info.shape == (3, 3):
+        info = info[np.triu_indices(3)]
+    pr = OrcPrior()
+    pr.z = (C.c_float * 3)(*[float(v) for v in z])
+    pr.information = (C.c_float * 6)(*[float(v) for v in info])
+    pr.cauchy_chi_threshold = cauchy_chi_threshold
+    return pr
+
+
+def prior_error_and_jacobian(prior: OrcPrior, X_xyt):
+    e, J = np.zeros(3, np.float32), np.zeros(9, np.float32)
+    lib().orc_prior_error_and_jacobian(C.byref(prior), v2t(*X_xyt), _ptr(e), _ptr(J))
+    return e, J.reshape(3, 3)
+
+
+def align_multi_batch(slices, fixed_sets, moving_sets, init_xyt, prior=None, prior_z=None, fixed_id=None,
+                      moving_id=None, sum_mode=SUM_SEQUENTIAL, tree_threads=256, n_threads=1, want_iters=True):
+    """MultiAligner2D with several laser slices (+ optional odometry prior).  slices: list of OrcParams;
+    fixed_sets / moving_sets: per slice a (points [n, 4], offsets) CSR pair; prior_z: [n_pairs, 3]."""
+    n_s = len(slices)
+    arr = (OrcParams * n_s)(*slices)
+    keep = []
+
+    def ptr_array(items):
+        a = (C.c_void_p * n_s)(*[it.ctypes.data for it in items])
+        keep.append(items)
+        return a
+
+    fp = ptr_array([_f32(f[0]) for f in fixed_sets])
+    fo = ptr_array([_i32(f[1]) for f in fixed_sets])
+    mp = ptr_array([_f32(m[0]) for m in moving_sets])
+    mo = ptr_array([_i32(m[1]) for m in moving_sets])
+    init = _f32(init_xyt)
+    fixed_id, moving_id = _i32(fixed_id), _i32(moving_id)
+    pz = None if prior_z is None else _f32(prior_z)
+    n = len(init)
+    out = np.zeros(n, RESULT_DTYPE)
+    its = np.zeros((n, slices[0].max_iterations), ITER_DTYPE) if want_iters else None
+    lib().orc_align_multi_batch(C.cast(arr, C.c_void_p), n_s, C.cast(fp, C.c_void_p), C.cast(fo, C.c_void_p),
+                                C.cast(mp, C.c_void_p), C.cast(mo, C.c_void_p), _ptr(fixed_id), _ptr(moving_id),
+                                C.byref(prior) if prior is not None and pz is not None else None, _ptr(pz),
+                                _ptr(init), n, sum_mode, tree_threads, n_threads, _ptr(out), _ptr(its))
     return out, its
 
 
