@@ -114,7 +114,19 @@ typedef struct {
   int32_t guess;      /* index of the winning initial guess */
 } ls2d_best;
 
+/* cloud sets of a handle: ids 0 .. LS2D_MAX_CLOUD_SETS-1.  The single-slice entry points read LS2D_FIXED and
+ * LS2D_MOVING; the multi-slice aligner names a (fixed, moving) set per slice. */
 enum { LS2D_FIXED = 0, LS2D_MOVING = 1 };
+#define LS2D_MAX_CLOUD_SETS 8
+#define LS2D_MAX_SLICES 4
+
+/* AlignerSliceOdom2DPrior (L0.json:291-310, MULTI.json:400-422) -> SE2PriorErrorFactor: information matrix
+ * (upper triangle O00 O01 O02 O11 O12 O22) of the odometry's prediction of moving_in_fixed; the prediction
+ * itself is per pair.  cauchy_chi_threshold <= 0: the slice has no robustifier (both configurations). */
+typedef struct {
+  float information[6];
+  float cauchy_chi_threshold;
+} ls2d_prior;
 
 /* ---- lifetime ------------------------------------------------------------------------------------- */
 /* replaces: construction of the BOSS-registered modules (R/instances.cpp:27-36) */
@@ -137,7 +149,7 @@ int ls2d_get_params(const ls2d_handle* h, ls2d_params* p);
  * replaces: MultiAligner2D::setFixed / setMoving(PropertyContainer*) and
  * CorrespondenceFinder_::setFixed / setMoving(const PointNormal2fVectorCloud*)
  * (apps/visual_test_aligner_2d.cpp:108-126, apps/visual_test_correspondence_finder_projective_2d.cpp:73-79) */
-int ls2d_upload_clouds(ls2d_handle* h, int which, const float* points_xynn, const int32_t* offsets,
+int ls2d_upload_clouds(ls2d_handle* h, int which /* set id */, const float* points_xynn, const int32_t* offsets,
                        int32_t n_clouds);
 /* borrow device-resident clouds (no copy); max_points = largest cloud in the set */
 int ls2d_set_clouds_dev(ls2d_handle* h, int which, const void* points_dev, const int32_t* offsets_dev,
@@ -164,6 +176,26 @@ int ls2d_score_batch(ls2d_handle* h, const int32_t* fixed_id, const int32_t* mov
                      const float* xyt, int32_t n_pairs, ls2d_result* out);
 int ls2d_score_batch_dev(ls2d_handle* h, const int32_t* fixed_id_dev, const int32_t* moving_id_dev,
                          const float* xyt_dev, int32_t n_pairs, ls2d_result* out_dev);
+
+/* ---- multi-slice registration ------------------------------------------------------------------------
+ * replaces: MultiAligner2D::compute with several slice processors (MULTI.json:700-730: al_sl_laser_0 +
+ * ad_sl_odom + al_sl_laser_1; LASER_0.json:502-506: laser + odom): n_slices laser slices
+ * (AlignerSliceProcessorLaser2D[WithSensor], R/registration/aligner_slice_processor_laser_2d.h:7-42), slice s
+ * described by slices[s] (its projector, finder, robustifier, min_num_correspondences, sensor_in_robot) and
+ * aligning cloud moving_id[p] of set moving_set[s] onto cloud fixed_id[p] of set fixed_set[s]; their H and b
+ * are summed with the odometry prior's (prior / prior_z_xyt [n_pairs * 3], both NULL: no prior slice) and
+ * solved once per iteration.  max_iterations / min_num_inliers / damping are read from slices[0].  A slice
+ * with n_corr <= min_num_correspondences is skipped in that iteration. */
+int ls2d_align_multi(ls2d_handle* h, const ls2d_params* slices, const int32_t* fixed_set,
+                     const int32_t* moving_set, int32_t n_slices, const ls2d_prior* prior,
+                     const float* prior_z_xyt, const int32_t* fixed_id, const int32_t* moving_id,
+                     const float* init_xyt, int32_t n_pairs, ls2d_result* out, ls2d_iter_stats* iter_stats);
+/* same, per-pair arrays device-resident, asynchronous on the handle's stream */
+int ls2d_align_multi_dev(ls2d_handle* h, const ls2d_params* slices, const int32_t* fixed_set,
+                         const int32_t* moving_set, int32_t n_slices, const ls2d_prior* prior,
+                         const float* prior_z_xyt_dev, const int32_t* fixed_id_dev, const int32_t* moving_id_dev,
+                         const float* init_xyt_dev, int32_t n_pairs, ls2d_result* out_dev,
+                         ls2d_iter_stats* iter_stats_dev);
 
 /* ---- finder / projector (drop-in + parity) ---------------------------------------------------------
  * replaces: CorrespondenceFinderProjective2f::compute()

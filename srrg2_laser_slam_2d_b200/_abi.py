@@ -32,6 +32,21 @@ class Params(C.Structure):
                 ("sensor_in_robot", C.c_float * 3)]
 
 
+class Prior(C.Structure):
+    """ls2d_prior -- information matrix (upper triangle) and robustifier threshold of the odometry prior slice."""
+    _fields_ = [("information", C.c_float * 6), ("cauchy_chi_threshold", C.c_float)]
+
+
+def make_prior(information, cauchy_chi_threshold: float = -1.0) -> Prior:
+    info = np.asarray(information, np.float32)
+    if info.shape == (3, 3):
+        info = info[np.triu_indices(3)]
+    pr = Prior()
+    pr.information = (C.c_float * 6)(*[float(v) for v in info])
+    pr.cauchy_chi_threshold = cauchy_chi_threshold
+    return pr
+
+
 class Gates(C.Structure):
     _fields_ = [("min_inliers", C.c_int32), ("max_chi_per_inlier", C.c_float), ("min_inlier_ratio", C.c_float)]
 
@@ -53,7 +68,7 @@ EXPORTS = [
     "ls2d_align_batch", "ls2d_align_batch_dev", "ls2d_align_pairs_host", "ls2d_score_batch",
     "ls2d_score_batch_dev", "ls2d_find_correspondences", "ls2d_project", "ls2d_verify", "ls2d_verify_dev",
     "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_threads", "ls2d_launch_count",
-    "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev",
+    "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev", "ls2d_align_multi", "ls2d_align_multi_dev",
 ]
 
 _lib = None
@@ -94,6 +109,8 @@ def load():
     L.ls2d_clip_scenes.argtypes = [vp, C.c_int, vp, vp, vp, i32, vp, vp]
     L.ls2d_merge_scene.argtypes = [vp, vp, C.POINTER(i32), i32, vp, i32, vp, f32, vp]
     L.ls2d_merge_scene_dev.argtypes = [vp, vp, vp, i32, vp, i32, vp, f32, vp]
+    L.ls2d_align_multi.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.ls2d_align_multi_dev.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp]
     L.ls2d_reduction_threads.argtypes = [i32]
     L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
     _lib = L
@@ -222,6 +239,34 @@ class Handle:
         self._check(self._L.ls2d_align_pairs_host(self._h, _ptr(fixed_pts), _ptr(fixed_off), _ptr(moving_pts),
                                                   _ptr(moving_off), _ptr(init_xyt), n, _ptr(out)))
         return out
+
+    def align_multi(self, slices, fixed_sets, moving_sets, init_xyt, prior: Prior | None = None, prior_z=None,
+                    fixed_id=None, moving_id=None, want_iters: bool = False):
+        """MultiAligner2D with several laser slices (+ odometry prior): slices = list of Params, fixed_sets /
+        moving_sets = cloud-set ids per slice (uploaded with upload_clouds), prior_z = [n_pairs, 3]."""
+        n_s = len(slices)
+        arr = (Params * n_s)(*slices)
+        fs, ms = _i32(fixed_sets), _i32(moving_sets)
+        init = _f32(init_xyt).reshape(-1, 3)
+        pz = None if prior_z is None else _f32(prior_z).reshape(-1, 3)
+        fid, mid = _i32(fixed_id), _i32(moving_id)
+        n = len(init)
+        out = np.zeros(n, RESULT_DTYPE)
+        its = np.zeros((n, slices[0].max_iterations), ITER_DTYPE) if want_iters else None
+        self._check(self._L.ls2d_align_multi(self._h, C.cast(arr, C.c_void_p), _ptr(fs), _ptr(ms), n_s,
+                                             C.cast(C.pointer(prior), C.c_void_p) if prior is not None else None,
+                                             _ptr(pz), _ptr(fid), _ptr(mid), _ptr(init), n, _ptr(out), _ptr(its)))
+        return (out, its) if want_iters else out
+
+    def align_multi_dev(self, slices, fixed_sets, moving_sets, init_ptr: int, n_pairs: int, out_ptr: int,
+                        prior: Prior | None = None, prior_z_ptr: int | None = None, iters_ptr: int | None = None):
+        n_s = len(slices)
+        arr = (Params * n_s)(*slices)
+        fs, ms = _i32(fixed_sets), _i32(moving_sets)
+        self._check(self._L.ls2d_align_multi_dev(self._h, C.cast(arr, C.c_void_p), _ptr(fs), _ptr(ms), n_s,
+                                                 C.cast(C.pointer(prior), C.c_void_p) if prior is not None else None,
+                                                 C.c_void_p(prior_z_ptr or 0), None, None, C.c_void_p(init_ptr),
+                                                 n_pairs, C.c_void_p(out_ptr), C.c_void_p(iters_ptr or 0)))
 
     def score_batch(self, xyt, fixed_id=None, moving_id=None):
         xyt = _f32(xyt).reshape(-1, 3)

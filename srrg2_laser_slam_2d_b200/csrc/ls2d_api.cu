@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ls2d_kernels.cuh"
+#include "ls2d_multi.cuh"
 
 using namespace ls2d;
 
@@ -39,8 +40,8 @@ struct ls2d_handle {
   cudaStream_t stream      = nullptr;
   ls2d_params prm;
   dev_params dp;
-  cloud_set sets[2];
-  scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc;
+  cloud_set sets[LS2D_MAX_CLOUD_SETS];
+  scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior;
   int64_t launches = 0;
   int variant      = 0;  // LS2D_ICP_VARIANT: tuning knob for the 1081-point kernel shape
   // NCCL, resolved lazily
@@ -301,8 +302,8 @@ int ls2d_destroy(ls2d_handle* h) {
   if (!h) return LS2D_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  release(h->sets[0]);
-  release(h->sets[1]);
+  for (cloud_set& c : h->sets) release(c);
+  release(h->d_prior);
   release(h->d_fid);
   release(h->d_mid);
   release(h->d_init);
@@ -343,7 +344,7 @@ int ls2d_get_params(const ls2d_handle* h, ls2d_params* p) {
 }
 
 int ls2d_upload_clouds(ls2d_handle* h, int which, const float* pts, const int32_t* off, int32_t n_clouds) {
-  if (!h || (which != 0 && which != 1) || !off || n_clouds < 0 || (!pts && n_clouds > 0 && off[n_clouds] > 0))
+  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !off || n_clouds < 0 || (!pts && n_clouds > 0 && off[n_clouds] > 0))
     return LS2D_ERR_INVALID;
   if (off[0] != 0) return LS2D_ERR_INVALID;
   int maxp = 0;
@@ -381,7 +382,7 @@ int ls2d_upload_clouds(ls2d_handle* h, int which, const float* pts, const int32_
 
 int ls2d_set_clouds_dev(ls2d_handle* h, int which, const void* pts_dev, const int32_t* off_dev,
                         int32_t n_clouds, int32_t max_points) {
-  if (!h || (which != 0 && which != 1) || !pts_dev || !off_dev || n_clouds < 0 || max_points < 0)
+  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !pts_dev || !off_dev || n_clouds < 0 || max_points < 0)
     return LS2D_ERR_INVALID;
   if (((uintptr_t) pts_dev) & 15) return LS2D_ERR_INVALID;
   release(h->sets[which]);
@@ -471,6 +472,108 @@ int ls2d_align_pairs_host(ls2d_handle* h, const float* fpts, const int32_t* foff
   if ((rc = ls2d_upload_clouds(h, LS2D_FIXED, fpts, foff, n_pairs))) return rc;
   if ((rc = ls2d_upload_clouds(h, LS2D_MOVING, mpts, moff, n_pairs))) return rc;
   return align_host_impl(h, nullptr, nullptr, init, n_pairs, out, nullptr, 0);
+}
+
+// ---- multi-slice aligner ---------------------------------------------------------------------------
+static int multi_dev_impl(ls2d_handle* h, const ls2d_params* slices, const int32_t* fset, const int32_t* mset,
+                          int32_t n_slices, const ls2d_prior* prior, const float* prior_z, const int32_t* fid,
+                          const int32_t* mid, const float* init, int32_t n_pairs, ls2d_result* out,
+                          ls2d_iter_stats* iters) {
+  if (!h || !slices || !fset || !mset || n_slices < 1 || n_slices > LS2D_MAX_SLICES || !init || !out || n_pairs < 0)
+    return LS2D_ERR_INVALID;
+  if ((prior == nullptr) != (prior_z == nullptr)) return LS2D_ERR_INVALID;
+  multi_args a;
+  memset(&a, 0, sizeof(a));
+  int cols[LS2D_MAX_SLICES];
+  for (int s = 0; s < n_slices; ++s) {
+    if (!params_valid(slices[s])) return LS2D_ERR_INVALID;
+    if (fset[s] < 0 || fset[s] >= LS2D_MAX_CLOUD_SETS || mset[s] < 0 || mset[s] >= LS2D_MAX_CLOUD_SETS)
+      return LS2D_ERR_INVALID;
+    const cloud_set& f = h->sets[fset[s]];
+    const cloud_set& m = h->sets[mset[s]];
+    if (!f.pts || !f.off || !m.pts || !m.off) return LS2D_ERR_NOT_READY;
+    a.sl[s].P          = translate(slices[s]);
+    a.sl[s].fixed_pts  = f.pts;
+    a.sl[s].fixed_off  = f.off;
+    a.sl[s].moving_pts = m.pts;
+    a.sl[s].moving_off = m.off;
+    cols[s]            = slices[s].canvas_cols;
+    if (cols[s] > a.max_cols) a.max_cols = cols[s];
+    if (f.max_points > a.max_points) a.max_points = f.max_points;
+    if (m.max_points > a.max_points) a.max_points = m.max_points;
+  }
+  if (a.max_cols > 0xFFFE) return LS2D_ERR_UNSUPPORTED;
+  a.n_slices   = n_slices;
+  a.fixed_id   = fid;
+  a.moving_id  = mid;
+  a.init_xyt   = init;
+  a.prior_z    = prior_z;
+  if (prior) {
+    memcpy(a.prior_info, prior->information, sizeof(float) * 6);
+    a.prior_tau     = prior->cauchy_chi_threshold;
+    a.prior_inv_tau = prior->cauchy_chi_threshold > 0.f ? 1.f / prior->cauchy_chi_threshold : 0.f;
+  }
+  a.out        = out;
+  a.iters      = iters;
+  a.n_pairs    = n_pairs;
+  a.score_only = 0;
+  if (n_pairs == 0) return LS2D_OK;
+  CU(cudaSetDevice(h->device));
+  constexpr int T   = 512;
+  const size_t smem = multi_smem_bytes(cols, n_slices, a.max_cols, a.max_points, T);
+  if (smem > 227 * 1024) return LS2D_ERR_UNSUPPORTED;
+  auto kern = icp_multi_kernel<T, 2>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<n_pairs, T, smem, h->stream>>>(a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int ls2d_align_multi_dev(ls2d_handle* h, const ls2d_params* slices, const int32_t* fset, const int32_t* mset,
+                         int32_t n_slices, const ls2d_prior* prior, const float* prior_z, const int32_t* fid,
+                         const int32_t* mid, const float* init, int32_t n_pairs, ls2d_result* out,
+                         ls2d_iter_stats* iters) {
+  return multi_dev_impl(h, slices, fset, mset, n_slices, prior, prior_z, fid, mid, init, n_pairs, out, iters);
+}
+
+int ls2d_align_multi(ls2d_handle* h, const ls2d_params* slices, const int32_t* fset, const int32_t* mset,
+                     int32_t n_slices, const ls2d_prior* prior, const float* prior_z, const int32_t* fid,
+                     const int32_t* mid, const float* init, int32_t n_pairs, ls2d_result* out,
+                     ls2d_iter_stats* iters) {
+  if (!h || !slices || !fset || !mset || n_slices < 1 || n_slices > LS2D_MAX_SLICES || !init || !out || n_pairs < 0)
+    return LS2D_ERR_INVALID;
+  if (n_pairs == 0) return LS2D_OK;
+  for (int s = 0; s < n_slices; ++s) {
+    if (fset[s] < 0 || fset[s] >= LS2D_MAX_CLOUD_SETS || mset[s] < 0 || mset[s] >= LS2D_MAX_CLOUD_SETS)
+      return LS2D_ERR_INVALID;
+    for (int i = 0; i < n_pairs; ++i) {
+      const int f = fid ? fid[i] : i, m = mid ? mid[i] : i;
+      if (f < 0 || f >= h->sets[fset[s]].n_clouds || m < 0 || m >= h->sets[mset[s]].n_clouds) return LS2D_ERR_INVALID;
+    }
+  }
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if (fid && (rc = h2d(h, h->d_fid, fid, sizeof(int) * (size_t) n_pairs))) return rc;
+  if (mid && (rc = h2d(h, h->d_mid, mid, sizeof(int) * (size_t) n_pairs))) return rc;
+  if ((rc = h2d(h, h->d_init, init, sizeof(float) * 3 * (size_t) n_pairs))) return rc;
+  if (prior_z && (rc = h2d(h, h->d_prior, prior_z, sizeof(float) * 3 * (size_t) n_pairs))) return rc;
+  if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) n_pairs))) return rc;
+  const size_t iter_bytes = sizeof(ls2d_iter_stats) * (size_t) n_pairs * (size_t) slices[0].max_iterations;
+  if (iters && iter_bytes) {
+    if ((rc = reserve(h->d_iters, iter_bytes))) return rc;
+    CU(cudaMemsetAsync(h->d_iters.p, 0, iter_bytes, h->stream));
+  }
+  rc = multi_dev_impl(h, slices, fset, mset, n_slices, prior, prior_z ? (const float*) h->d_prior.p : nullptr,
+                      fid ? (const int*) h->d_fid.p : nullptr, mid ? (const int*) h->d_mid.p : nullptr,
+                      (const float*) h->d_init.p, n_pairs, (ls2d_result*) h->d_out.p,
+                      (iters && iter_bytes) ? (ls2d_iter_stats*) h->d_iters.p : nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, h->d_out.p, sizeof(ls2d_result) * (size_t) n_pairs, cudaMemcpyDeviceToHost, h->stream));
+  if (iters && iter_bytes) CU(cudaMemcpyAsync(iters, h->d_iters.p, iter_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
 }
 
 int ls2d_find_correspondences(ls2d_handle* h, int32_t fixed_id, int32_t moving_id, const float* xyt,

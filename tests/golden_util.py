@@ -15,6 +15,11 @@ def load(name):
     return d
 
 
+def load_raw(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
 def make_params(factory, d):
     """factory = oracle_binding.default_params or srrg2_laser_slam_2d_b200.default_params"""
     return factory(**d["params"])

@@ -44,3 +44,23 @@ def test_oracle_reproduces_demo_scene_projection(oracle):
     img = oracle.project(prm, d["camera_pose"], d["scene"])
     assert np.array_equal(img["source_idx"], d["source_idx"])
     assert np.array_equal(gu.bits(img["depth"]), gu.bits(d["depth"]))
+
+
+def test_oracle_reproduces_multi_slice_golden(oracle):
+    """MULTI.json-shaped aligner: two laser slices with their own sensor_in_robot + the odometry prior"""
+    from test_oracle_multi import sets_of  # noqa: F401  (same slice recipe as tools/make_golden.py)
+    d = gu.load_raw("multi_721_mu")
+    base = dict(canvas_cols=721, max_iterations=10, min_num_correspondences=5, with_sensor=1, point_distance=0.5)
+    sl = [oracle.default_params(normal_cos=0.9, cauchy_chi_threshold=0.01,
+                                sensor_in_robot=tuple(float(v) for v in d["sensors"][0]), **base),
+          oracle.default_params(normal_cos=0.8, cauchy_chi_threshold=-1.0,
+                                sensor_in_robot=tuple(float(v) for v in d["sensors"][1]), **base)]
+    fixed = [(d["fixed_pts_0"], d["fixed_off"]), (d["fixed_pts_1"], d["fixed_off"])]
+    moving = [(d["moving_pts"], d["moving_off"])] * 2
+    res, its = oracle.align_multi_batch(sl, fixed, moving, d["init_xyt"], prior=oracle.make_prior(d["prior_info"]),
+                                        prior_z=d["odom_xyt"])
+    assert res.tobytes() == d["results"].tobytes() and its.tobytes() == d["iters"].tobytes()
+    res, its = oracle.align_multi_batch(sl, fixed, moving, d["init_xyt"])
+    assert res.tobytes() == d["results_no_prior"].tobytes() and its.tobytes() == d["iters_no_prior"].tobytes()
+    assert (d["results"]["status"] == 0).all()
+    assert np.abs(np.stack([d["results"][k] for k in ("x", "y", "theta")], 1) - d["gt_xyt"]).max() < 5e-3

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_binding as ob  # noqa: E402
-from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs, reference_demo_scene  # noqa: E402
+from srrg2_laser_slam_2d_b200.synthetic import make_multi_sensor_pairs, make_scan_pairs, reference_demo_scene  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -44,8 +44,40 @@ def params_dict(p):
     return d
 
 
+# MULTI.json tracking aligner (:700-730): al_sl_laser_0 (Cauchy 0.01, finder 0.5 / 0.9), ad_sl_odom, al_sl_laser_1
+# (no robustifier, finder 0.5 / 0.8), min_num_correspondences 5, 721 columns, 10 iterations
+MULTI_SENSORS = ((0.2, 0.05, 0.1), (-0.2, 0.0, 3.1415927))
+MULTI_PRIOR_INFO = (100.0, 0.0, 0.0, 100.0, 0.0, 400.0)
+
+
+def multi_slices(factory, sensors):
+    base = dict(canvas_cols=721, max_iterations=10, min_num_correspondences=5, with_sensor=1, point_distance=0.5)
+    return [factory(normal_cos=0.9, cauchy_chi_threshold=0.01, sensor_in_robot=tuple(float(v) for v in sensors[0]), **base),
+            factory(normal_cos=0.8, cauchy_chi_threshold=-1.0, sensor_in_robot=tuple(float(v) for v in sensors[1]), **base)]
+
+
+def make_multi():
+    msp = make_multi_sensor_pairs(4, sensors=MULTI_SENSORS, n_beams=721, seed=106)
+    sl = multi_slices(ob.default_params, msp.sensors)
+    fixed = [(msp.fixed_pts[s], msp.fixed_off[s]) for s in range(2)]
+    moving = [(msp.moving_pts, msp.moving_off)] * 2
+    res, its = ob.align_multi_batch(sl, fixed, moving, msp.init_xyt, prior=ob.make_prior(MULTI_PRIOR_INFO),
+                                    prior_z=msp.odom_xyt)
+    res_np, its_np = ob.align_multi_batch(sl, fixed, moving, msp.init_xyt)
+    np.savez_compressed(os.path.join(OUT, "multi_721_mu.npz"), fixed_pts_0=msp.fixed_pts[0], fixed_pts_1=msp.fixed_pts[1],
+                        fixed_off=msp.fixed_off[0], moving_pts=msp.moving_pts, moving_off=msp.moving_off,
+                        sensors=msp.sensors, init_xyt=msp.init_xyt, gt_xyt=msp.gt_xyt, odom_xyt=msp.odom_xyt,
+                        prior_info=np.array(MULTI_PRIOR_INFO, np.float32), results=res, iters=its,
+                        results_no_prior=res_np, iters_no_prior=its_np)
+    print("multi_721_mu status", res["status"], "n_corr", res["n_corr"], "n_inl", res["n_inliers"],
+          "err", np.abs(np.stack([res["x"], res["y"], res["theta"]], 1) - msp.gt_xyt).max())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--multi-only" in sys.argv:
+        return make_multi()
+    make_multi()
     for name, (gen, prm_kw) in CASES.items():
         sp = make_scan_pairs(**gen)
         prm = ob.default_params(**prm_kw)
