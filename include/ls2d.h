@@ -204,6 +204,11 @@ int ls2d_align_multi_dev(ls2d_handle* h, const ls2d_params* slices, const int32_
 int ls2d_find_correspondences(ls2d_handle* h, int32_t fixed_id, int32_t moving_id,
                               const float* local_map_in_sensor_xyt, int32_t* fixed_idx,
                               int32_t* moving_idx, int32_t* n_correspondences);
+/* same, between cloud fixed_id of set fixed_set and cloud moving_id of set moving_set (a slice of the
+ * multi-slice aligner), with the handle's current parameters */
+int ls2d_find_correspondences_in(ls2d_handle* h, int32_t fixed_set, int32_t moving_set, int32_t fixed_id,
+                                 int32_t moving_id, const float* local_map_in_sensor_xyt, int32_t* fixed_idx,
+                                 int32_t* moving_idx, int32_t* n_correspondences);
 /* replaces: PointNormal2fProjectorPolar::setCameraPose + compute
  * (R/registration/correspondence_finder_projective_2d.cpp:40-41,47-48): per column the winning
  * source_idx (-1 empty) and its depth (FLT_MAX empty); arrays hold canvas_cols entries. */

@@ -69,6 +69,7 @@ EXPORTS = [
     "ls2d_score_batch_dev", "ls2d_find_correspondences", "ls2d_project", "ls2d_verify", "ls2d_verify_dev",
     "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_threads", "ls2d_launch_count",
     "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev", "ls2d_align_multi", "ls2d_align_multi_dev",
+    "ls2d_find_correspondences_in",
 ]
 
 _lib = None
@@ -101,6 +102,7 @@ def load():
     L.ls2d_score_batch.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ls2d_score_batch_dev.argtypes = [vp, vp, vp, vp, i32, vp]
     L.ls2d_find_correspondences.argtypes = [vp, i32, i32, vp, vp, vp, C.POINTER(i32)]
+    L.ls2d_find_correspondences_in.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, C.POINTER(i32)]
     L.ls2d_project.argtypes = [vp, C.c_int, i32, vp, vp, vp]
     L.ls2d_verify.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]
     L.ls2d_verify_dev.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]

@@ -578,19 +578,28 @@ int ls2d_align_multi(ls2d_handle* h, const ls2d_params* slices, const int32_t* f
 
 int ls2d_find_correspondences(ls2d_handle* h, int32_t fixed_id, int32_t moving_id, const float* xyt,
                               int32_t* fixed_idx, int32_t* moving_idx, int32_t* n_out) {
+  return ls2d_find_correspondences_in(h, LS2D_FIXED, LS2D_MOVING, fixed_id, moving_id, xyt, fixed_idx, moving_idx, n_out);
+}
+
+int ls2d_find_correspondences_in(ls2d_handle* h, int32_t fixed_set, int32_t moving_set, int32_t fixed_id,
+                                 int32_t moving_id, const float* xyt, int32_t* fixed_idx, int32_t* moving_idx,
+                                 int32_t* n_out) {
   if (!h || !xyt || !fixed_idx || !moving_idx || !n_out) return LS2D_ERR_INVALID;
-  if (!ready(h)) return LS2D_ERR_NOT_READY;
-  if (fixed_id < 0 || fixed_id >= h->sets[0].n_clouds || moving_id < 0 || moving_id >= h->sets[1].n_clouds)
+  if (fixed_set < 0 || fixed_set >= LS2D_MAX_CLOUD_SETS || moving_set < 0 || moving_set >= LS2D_MAX_CLOUD_SETS)
     return LS2D_ERR_INVALID;
+  const cloud_set& fs = h->sets[fixed_set];
+  const cloud_set& ms = h->sets[moving_set];
+  if (!fs.pts || !fs.off || !ms.pts || !ms.off) return LS2D_ERR_NOT_READY;
+  if (fixed_id < 0 || fixed_id >= fs.n_clouds || moving_id < 0 || moving_id >= ms.n_clouds) return LS2D_ERR_INVALID;
   CU(cudaSetDevice(h->device));
   const int C = h->dp.cam.cols;
   int rc      = reserve(h->d_misc, sizeof(int) * (2 * (size_t) C + 1));
   if (rc) return rc;
   correspond_args a;
-  a.fixed_pts    = h->sets[0].pts;
-  a.fixed_off    = h->sets[0].off;
-  a.moving_pts   = h->sets[1].pts;
-  a.moving_off   = h->sets[1].off;
+  a.fixed_pts    = fs.pts;
+  a.fixed_off    = fs.off;
+  a.moving_pts   = ms.pts;
+  a.moving_off   = ms.off;
   a.fixed_cloud  = fixed_id;
   a.moving_cloud = moving_id;
   memcpy(a.lmis_xyt, xyt, sizeof(float) * 3);
@@ -617,7 +626,7 @@ int ls2d_find_correspondences(ls2d_handle* h, int32_t fixed_id, int32_t moving_i
 
 int ls2d_project(ls2d_handle* h, int which, int32_t cloud_id, const float* cam_xyt, int32_t* source_idx,
                  float* depth) {
-  if (!h || (which != 0 && which != 1) || !cam_xyt || !source_idx || !depth) return LS2D_ERR_INVALID;
+  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !cam_xyt || !source_idx || !depth) return LS2D_ERR_INVALID;
   const cloud_set& c = h->sets[which];
   if (!c.pts || !c.off) return LS2D_ERR_NOT_READY;
   if (cloud_id < 0 || cloud_id >= c.n_clouds) return LS2D_ERR_INVALID;
@@ -752,7 +761,7 @@ int ls2d_verify_sharded_nccl(ls2d_handle* h, int32_t query_id, const int32_t* ca
 
 int ls2d_clip_scenes(ls2d_handle* h, int which, const int32_t* cloud_ids, const float* robot_xyt,
                      const float* sensor_xyt, int32_t n, float* out_points, int32_t* out_counts) {
-  if (!h || (which != 0 && which != 1) || !cloud_ids || !robot_xyt || !sensor_xyt || !out_points || !out_counts || n < 0)
+  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !cloud_ids || !robot_xyt || !sensor_xyt || !out_points || !out_counts || n < 0)
     return LS2D_ERR_INVALID;
   const cloud_set& c = h->sets[which];
   if (!c.pts || !c.off) return LS2D_ERR_NOT_READY;

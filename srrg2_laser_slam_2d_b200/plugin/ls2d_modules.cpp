@@ -262,32 +262,42 @@ namespace srrg2_slam_interfaces {
     return S;
   }
 
-  std::shared_ptr<AlignerSliceProcessorLaserBase> MultiAligner2D::laserSlice() {
-    std::shared_ptr<AlignerSliceProcessorLaserBase> laser;
+  std::vector<std::shared_ptr<AlignerSliceProcessorLaserBase>> MultiAligner2D::laserSlices() {
+    std::vector<std::shared_ptr<AlignerSliceProcessorLaserBase>> out;
     for (size_t i = 0; i < param_slice_processors.size(); ++i) {
       const AlignerSliceProcessorBasePtr& s = param_slice_processors.value(i);
       if (!s) continue;
       if (s->isLaserSlice()) {
-        if (laser)
-          throw std::runtime_error("MultiAligner2D::compute| more than one laser slice is not supported by the "
-                                   "CUDA aligner yet (multi-slice fused solve: SURVEY.md 8f-4)");
-        laser = std::dynamic_pointer_cast<AlignerSliceProcessorLaserBase>(s);
-      } else {
-        // a prior slice contributes only if its data is present in both scenes
-        const bool bound = _fixed_scene && _moving_scene && _fixed_scene->cloud(s->param_fixed_slice_name.value()) &&
-                           _moving_scene->cloud(s->param_moving_slice_name.value());
-        if (bound)
-          throw std::runtime_error("MultiAligner2D::compute| slice \"" + s->className() +
-                                   "\" is not supported by the CUDA aligner yet (SURVEY.md 8f-4)");
+        out.push_back(std::dynamic_pointer_cast<AlignerSliceProcessorLaserBase>(s));
+      } else if (!std::dynamic_pointer_cast<AlignerSliceOdom2DPrior>(s)) {
+        throw std::runtime_error("MultiAligner2D::compute| slice \"" + s->className() +
+                                 "\" is not supported by the CUDA aligner");
       }
     }
-    if (!laser) throw std::runtime_error("MultiAligner2D::compute| no slice processor set");
-    return laser;
+    if (out.empty()) throw std::runtime_error("MultiAligner2D::compute| no slice processor set");
+    if (out.size() > LS2D_MAX_SLICES)
+      throw std::runtime_error("MultiAligner2D::compute| more than " + std::to_string(LS2D_MAX_SLICES) +
+                               " laser slices");
+    return out;
   }
 
-  void MultiAligner2D::fillParams(ls2d_params& p) {
+  std::shared_ptr<AlignerSliceProcessorLaserBase> MultiAligner2D::laserSlice() { return laserSlices().front(); }
+
+  // the odometry prior takes part only if its pose slice is present in both scenes (a scene without odometry,
+  // e.g. the loop detector's local maps, simply drops the factor)
+  std::shared_ptr<AlignerSliceOdom2DPrior> MultiAligner2D::boundPrior() {
+    std::shared_ptr<AlignerSliceOdom2DPrior> prior;
+    for (size_t i = 0; i < param_slice_processors.size(); ++i) {
+      auto p = std::dynamic_pointer_cast<AlignerSliceOdom2DPrior>(param_slice_processors.value(i));
+      if (!p || !p->bound(_fixed_scene, _moving_scene)) continue;
+      if (prior) throw std::runtime_error("MultiAligner2D::compute| more than one bound prior slice");
+      prior = p;
+    }
+    return prior;
+  }
+
+  void MultiAligner2D::fillOne(ls2d_params& p, const std::shared_ptr<AlignerSliceProcessorLaserBase>& slice) {
     ls2d_default_params(&p);
-    std::shared_ptr<AlignerSliceProcessorLaserBase> slice = laserSlice();
     auto finder = std::dynamic_pointer_cast<CorrespondenceFinderProjective2f>(slice->param_finder.value());
     if (!finder)
       throw std::runtime_error("MultiAligner2D::compute| the CUDA aligner needs a CorrespondenceFinderProjective2f "
@@ -326,6 +336,14 @@ namespace srrg2_slam_interfaces {
     }
   }
 
+  void MultiAligner2D::fillParams(ls2d_params& p) { fillOne(p, laserSlice()); }
+
+  void MultiAligner2D::fillSliceParams(std::vector<ls2d_params>& p) {
+    const auto slices = laserSlices();
+    p.resize(slices.size());
+    for (size_t i = 0; i < slices.size(); ++i) fillOne(p[i], slices[i]);
+  }
+
   static AlignmentResult toResult(const ls2d_result& r) {
     AlignmentResult a;
     a.estimate        = Vector3f(r.x, r.y, r.theta);
@@ -360,30 +378,7 @@ namespace srrg2_slam_interfaces {
     Ls2dDevice::check(ls2d_upload_clouds(h, which, flat.data(), off.data(), (int32_t) clouds.size()), where);
   }
 
-  void MultiAligner2D::compute() {
-    _status = Fail;
-    _iteration_stats.clear();
-    if (!_fixed_scene) throw std::runtime_error("MultiAligner2D::compute| Missing fixed!");
-    if (!_moving_scene) throw std::runtime_error("MultiAligner2D::compute| Missing moving!");
-    ls2d_params p;
-    fillParams(p);
-    std::shared_ptr<AlignerSliceProcessorLaserBase> slice = laserSlice();
-    PointNormal2fVectorCloud* fixed  = _fixed_scene->cloud(slice->param_fixed_slice_name.value());
-    PointNormal2fVectorCloud* moving = _moving_scene->cloud(slice->param_moving_slice_name.value());
-    if (!fixed) throw std::runtime_error("MultiAligner2D::compute| fixed scene has no slice \"" +
-                                         slice->param_fixed_slice_name.value() + "\"");
-    if (!moving) throw std::runtime_error("MultiAligner2D::compute| moving scene has no slice \"" +
-                                          slice->param_moving_slice_name.value() + "\"");
-    slice->_fixed  = fixed;
-    slice->_moving = moving;
-    ls2d_handle* h = _device.handle();
-    Ls2dDevice::check(ls2d_set_params(h, &p), "MultiAligner2D::compute");
-    uploadSet(h, LS2D_FIXED, {fixed}, "MultiAligner2D::compute");
-    uploadSet(h, LS2D_MOVING, {moving}, "MultiAligner2D::compute");
-    const Vector3f init = geometry2d::t2v(_moving_in_fixed);
-    ls2d_result r;
-    std::vector<ls2d_iter_stats> its((size_t) (p.max_iterations > 0 ? p.max_iterations : 1));
-    Ls2dDevice::check(ls2d_align_batch(h, nullptr, nullptr, init.v, 1, &r, its.data()), "MultiAligner2D::compute");
+  void MultiAligner2D::storeOutcome(const ls2d_result& r, const std::vector<ls2d_iter_stats>& its) {
     const AlignmentResult a = toResult(r);
     _moving_in_fixed        = a.moving_in_fixed;
     _information_matrix     = a.information_matrix;
@@ -401,6 +396,38 @@ namespace srrg2_slam_interfaces {
       s.estimate            = Vector3f(its[i].x, its[i].y, its[i].theta);
       _iteration_stats.push_back(s);
     }
+  }
+
+  static PointNormal2fVectorCloud* sliceCloud(PropertyContainerDynamic* scene, const std::string& name, const char* which) {
+    PointNormal2fVectorCloud* c = scene->cloud(name);
+    if (!c) throw std::runtime_error(std::string("MultiAligner2D::compute| ") + which + " scene has no slice \"" + name + "\"");
+    return c;
+  }
+
+  void MultiAligner2D::compute() {
+    _status = Fail;
+    _iteration_stats.clear();
+    if (!_fixed_scene) throw std::runtime_error("MultiAligner2D::compute| Missing fixed!");
+    if (!_moving_scene) throw std::runtime_error("MultiAligner2D::compute| Missing moving!");
+    const auto slices = laserSlices();
+    const auto prior  = boundPrior();
+    if (slices.size() > 1 || prior) return computeMulti(slices, prior);
+    ls2d_params p;
+    fillParams(p);
+    std::shared_ptr<AlignerSliceProcessorLaserBase> slice = slices.front();
+    PointNormal2fVectorCloud* fixed  = sliceCloud(_fixed_scene, slice->param_fixed_slice_name.value(), "fixed");
+    PointNormal2fVectorCloud* moving = sliceCloud(_moving_scene, slice->param_moving_slice_name.value(), "moving");
+    slice->_fixed  = fixed;
+    slice->_moving = moving;
+    ls2d_handle* h = _device.handle();
+    Ls2dDevice::check(ls2d_set_params(h, &p), "MultiAligner2D::compute");
+    uploadSet(h, LS2D_FIXED, {fixed}, "MultiAligner2D::compute");
+    uploadSet(h, LS2D_MOVING, {moving}, "MultiAligner2D::compute");
+    const Vector3f init = geometry2d::t2v(_moving_in_fixed);
+    ls2d_result r;
+    std::vector<ls2d_iter_stats> its((size_t) (p.max_iterations > 0 ? p.max_iterations : 1));
+    Ls2dDevice::check(ls2d_align_batch(h, nullptr, nullptr, init.v, 1, &r, its.data()), "MultiAligner2D::compute");
+    storeOutcome(r, its);
     // slice->correspondences(): those of the last iteration, i.e. found at the estimate before its update
     Vector3f before = init;
     if (r.iterations >= 2) before = _iteration_stats[r.iterations - 2].estimate;
@@ -412,6 +439,62 @@ namespace srrg2_slam_interfaces {
     Ls2dDevice::check(ls2d_find_correspondences(h, 0, 0, lv.v, fi.data(), mi.data(), &n), "MultiAligner2D::compute");
     slice->_correspondences.resize(n);
     for (int k = 0; k < n; ++k) slice->_correspondences[k] = Correspondence(fi[k], mi[k]);
+  }
+
+  // several laser slices and / or a bound odometry prior: one fused 3x3 system per iteration (MULTI.json:700-730,
+  // LASER_0.json:502-506).  Fixed cloud of slice s -> cloud set s, its moving cloud -> set LS2D_MAX_SLICES + s
+  // (slices that share a moving cloud share the set).
+  void MultiAligner2D::computeMulti(const std::vector<std::shared_ptr<AlignerSliceProcessorLaserBase>>& slices,
+                                    const std::shared_ptr<AlignerSliceOdom2DPrior>& prior) {
+    std::vector<ls2d_params> p;
+    fillSliceParams(p);
+    ls2d_handle* h = _device.handle();
+    std::vector<int32_t> fset(slices.size()), mset(slices.size());
+    for (size_t s = 0; s < slices.size(); ++s) {
+      slices[s]->_fixed  = sliceCloud(_fixed_scene, slices[s]->param_fixed_slice_name.value(), "fixed");
+      slices[s]->_moving = sliceCloud(_moving_scene, slices[s]->param_moving_slice_name.value(), "moving");
+      fset[s] = (int32_t) s;
+      mset[s] = LS2D_MAX_SLICES + (int32_t) s;
+      uploadSet(h, fset[s], {slices[s]->_fixed}, "MultiAligner2D::compute");
+      bool shared = false;
+      for (size_t t = 0; t < s && !shared; ++t)
+        if (slices[t]->_moving == slices[s]->_moving) mset[s] = mset[t], shared = true;
+      if (!shared) uploadSet(h, mset[s], {slices[s]->_moving}, "MultiAligner2D::compute");
+    }
+    ls2d_prior pr;
+    Vector3f z;
+    if (prior) {
+      const Matrix3f& O = prior->informationMatrix();
+      const float info[6] = {O.m[0][0], O.m[0][1], O.m[0][2], O.m[1][1], O.m[1][2], O.m[2][2]};
+      std::memcpy(pr.information, info, sizeof(info));
+      auto cauchy = std::dynamic_pointer_cast<srrg2_solver::RobustifierCauchy>(prior->param_robustifier.value());
+      if (prior->param_robustifier.value() && !cauchy)
+        throw std::runtime_error("MultiAligner2D::compute| only RobustifierCauchy is supported");
+      pr.cauchy_chi_threshold = cauchy ? cauchy->param_chi_threshold.value() : -1.f;
+      z = geometry2d::t2v(prior->measurement(_fixed_scene, _moving_scene));
+    }
+    const Vector3f init = geometry2d::t2v(_moving_in_fixed);
+    ls2d_result r;
+    std::vector<ls2d_iter_stats> its((size_t) (p[0].max_iterations > 0 ? p[0].max_iterations : 1));
+    Ls2dDevice::check(ls2d_align_multi(h, p.data(), fset.data(), mset.data(), (int32_t) slices.size(), prior ? &pr : nullptr,
+                                       prior ? z.v : nullptr, nullptr, nullptr, init.v, 1, &r, its.data()),
+                      "MultiAligner2D::compute");
+    storeOutcome(r, its);
+    // every slice's correspondences(): found at the estimate before the last iteration's update
+    Vector3f before = init;
+    if (r.iterations >= 2) before = _iteration_stats[r.iterations - 2].estimate;
+    for (size_t s = 0; s < slices.size(); ++s) {
+      Isometry2f lmis = geometry2d::v2t(before);
+      if (p[s].with_sensor) lmis = slices[s]->sensorInRobot().inverse() * lmis;
+      const Vector3f lv = geometry2d::t2v(lmis);
+      Ls2dDevice::check(ls2d_set_params(h, &p[s]), "MultiAligner2D::compute");
+      std::vector<int32_t> fi(p[s].canvas_cols), mi(p[s].canvas_cols);
+      int32_t n = 0;
+      Ls2dDevice::check(ls2d_find_correspondences_in(h, fset[s], mset[s], 0, 0, lv.v, fi.data(), mi.data(), &n),
+                        "MultiAligner2D::compute");
+      slices[s]->_correspondences.resize(n);
+      for (int k = 0; k < n; ++k) slices[s]->_correspondences[k] = Correspondence(fi[k], mi[k]);
+    }
   }
 
   void MultiAligner2D::computeBatch(const std::vector<const PointNormal2fVectorCloud*>& fixed,

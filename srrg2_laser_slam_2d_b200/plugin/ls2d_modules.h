@@ -222,10 +222,30 @@ namespace srrg2_slam_interfaces {
   };
   using AlignerSliceProcessorBasePtr = std::shared_ptr<AlignerSliceProcessorBase>;
 
-  // prior slices are parameter holders in this build
+  // AlignerSliceProcessorPrior_<SE2PriorErrorFactor, Isometry2f, Isometry2f> (L0.json:291-310,
+  // apps/visual_test_tracker_2d.cpp:88-93): both scenes carry a pose-valued slice ("odom"); the factor's
+  // measurement is the odometry's prediction of moving_in_fixed, Z = fixed_pose^-1 * moving_pose (both poses
+  // live in the odometry frame), its information matrix the SE2PriorErrorFactor default (identity) unless
+  // setInformationMatrix() is called (oracle decision D15).
   class AlignerSliceOdom2DPrior : public AlignerSliceProcessorBase {
   public:
-    AlignerSliceOdom2DPrior() { _class_name = "AlignerSliceOdom2DPrior"; }
+    AlignerSliceOdom2DPrior() {
+      _class_name = "AlignerSliceOdom2DPrior";
+      for (int i = 0; i < 3; ++i) _information.m[i][i] = 1.f;
+    }
+    void setInformationMatrix(const Matrix3f& omega) { _information = omega; }
+    const Matrix3f& informationMatrix() const { return _information; }
+    // true if both scenes hold this slice's pose
+    bool bound(const PropertyContainerDynamic* fixed, const PropertyContainerDynamic* moving) const {
+      return fixed && moving && fixed->pose(param_fixed_slice_name.value()) &&
+             moving->pose(param_moving_slice_name.value());
+    }
+    Isometry2f measurement(const PropertyContainerDynamic* fixed, const PropertyContainerDynamic* moving) const {
+      return fixed->pose(param_fixed_slice_name.value())->inverse() * *moving->pose(param_moving_slice_name.value());
+    }
+
+  protected:
+    Matrix3f _information;
   };
 
   class AlignerSliceProcessorLaserBase : public AlignerSliceProcessorBase {
@@ -288,12 +308,20 @@ namespace srrg2_slam_interfaces {
                       const std::vector<const PointNormal2fVectorCloud*>& moving,
                       const std::vector<Isometry2f>& guesses, std::vector<AlignmentResult>& results);
 
-    // the complete parameter set this aligner hands to the C ABI (public for tests / tools)
+    // the complete parameter set this aligner hands to the C ABI (public for tests / tools): slice 0's record
     void fillParams(ls2d_params& p);
+    // every laser slice's record (aligner-level fields repeated), in slice_processors order
+    void fillSliceParams(std::vector<ls2d_params>& p);
     Ls2dDevice& device() { return _device; }
 
   protected:
     std::shared_ptr<AlignerSliceProcessorLaserBase> laserSlice();
+    std::vector<std::shared_ptr<AlignerSliceProcessorLaserBase>> laserSlices();
+    std::shared_ptr<AlignerSliceOdom2DPrior> boundPrior();
+    void fillOne(ls2d_params& p, const std::shared_ptr<AlignerSliceProcessorLaserBase>& slice);
+    void computeMulti(const std::vector<std::shared_ptr<AlignerSliceProcessorLaserBase>>& slices,
+                      const std::shared_ptr<AlignerSliceOdom2DPrior>& prior);
+    void storeOutcome(const ls2d_result& r, const std::vector<ls2d_iter_stats>& its);
     PropertyContainerDynamic* _fixed_scene  = nullptr;
     PropertyContainerDynamic* _moving_scene = nullptr;
     Isometry2f _moving_in_fixed;

@@ -124,9 +124,16 @@ namespace srrg2_core {
       auto it = _clouds.find(name);
       return it == _clouds.end() ? nullptr : it->second;
     }
+    // pose-valued slices (the "odom" slice of AlignerSliceOdom2DPrior, L0.json:291-310)
+    void setPose(const std::string& name, Isometry2f* pose) { _poses[name] = pose; }
+    Isometry2f* pose(const std::string& name) const {
+      auto it = _poses.find(name);
+      return it == _poses.end() ? nullptr : it->second;
+    }
 
   private:
     std::map<std::string, PointNormal2fVectorCloud*> _clouds;
+    std::map<std::string, Isometry2f*> _poses;
   };
 
   // the part of srrg2_core::Platform the WithSensor slice uses: a static transform per sensor frame

@@ -3,6 +3,7 @@
 //   plugin_test parse <config>                    load a BOSS-text configuration, print the hot-path objects
 //   plugin_test align <config> <aligner> <in.bin> <out.bin>     (GPU) single-pair compute(), computeBatch(), finder
 //   plugin_test verify <config> <detector> <in.bin> <out.bin>   (GPU) loop-closure candidate verification
+//   plugin_test multi <config> <aligner> <in.bin> <out.bin>     (GPU) two laser slices + odometry prior, compute()
 // Binary layout of <in.bin>: int32 n_pairs, int32 n_guess, float sensor_in_robot[3]; then per pair:
 //   int32 n_fixed, n_moving; float fixed[n_fixed*4]; float moving[n_moving*4]; float init[n_guess*3].
 #include <cstdio>
@@ -160,7 +161,7 @@ static int parse(const std::string& file) {
   for (auto& a : m.getAll<MultiAligner2D>()) {
     ls2d_params p;
     const std::string why = thrown([&] { a->fillParams(p); });
-    if (!why.empty()) {  // e.g. MULTI.json's two-laser tracking aligner (multi-slice solve: SURVEY.md 8f-4)
+    if (!why.empty()) {
       std::printf("%s{\"id\": %d, \"name\": \"%s\", \"slices\": %zu, \"unsupported\": \"%s\"}", first ? "" : ", ",
                   m.idOf(a.get()), a->name().c_str(), a->param_slice_processors.size(), why.c_str());
       first = false;
@@ -169,11 +170,22 @@ static int parse(const std::string& file) {
     std::printf("%s{\"id\": %d, \"name\": \"%s\", \"slices\": %zu, \"canvas_cols\": %d, \"angle_col_min\": %.6f, "
                 "\"angle_col_max\": %.6f, \"range_min\": %.4f, \"range_max\": %.4f, \"point_distance\": %.4f, "
                 "\"normal_cos\": %.4f, \"cauchy_chi_threshold\": %.4f, \"damping\": %.4f, \"max_iterations\": %d, "
-                "\"min_num_correspondences\": %d, \"min_num_inliers\": %d, \"with_sensor\": %d}",
+                "\"min_num_correspondences\": %d, \"min_num_inliers\": %d, \"with_sensor\": %d, \"laser_slices\": [",
                 first ? "" : ", ", m.idOf(a.get()), a->name().c_str(), a->param_slice_processors.size(), p.canvas_cols,
                 p.angle_col_min, p.angle_col_max, p.range_min, p.range_max, p.point_distance, p.normal_cos,
                 p.cauchy_chi_threshold, p.damping, p.max_iterations, p.min_num_correspondences, p.min_num_inliers,
                 p.with_sensor);
+    std::vector<ls2d_params> all;
+    a->fillSliceParams(all);  // every laser slice of the aligner (MULTI.json: two rangefinders)
+    for (size_t k = 0; k < all.size(); ++k)
+      std::printf("%s{\"point_distance\": %.4f, \"normal_cos\": %.4f, \"cauchy_chi_threshold\": %.4f, "
+                  "\"min_num_correspondences\": %d, \"with_sensor\": %d, \"canvas_cols\": %d}",
+                  k ? ", " : "", all[k].point_distance, all[k].normal_cos, all[k].cauchy_chi_threshold,
+                  all[k].min_num_correspondences, all[k].with_sensor, all[k].canvas_cols);
+    int priors = 0;
+    for (size_t k = 0; k < a->param_slice_processors.size(); ++k)
+      if (std::dynamic_pointer_cast<AlignerSliceOdom2DPrior>(a->param_slice_processors.value(k))) ++priors;
+    std::printf("], \"prior_slices\": %d}", priors);
     first = false;
   }
   std::printf("], \"loop_detectors\": [");
@@ -322,6 +334,82 @@ static int verify(const std::string& config, const std::string& name, const std:
   return 0;
 }
 
+// Binary layout of the multi-slice input: int32 n_pairs; float sensor0[3], sensor1[3]; float information[6]; then per
+// pair: int32 n_fixed0, n_fixed1, n_moving; the three clouds; float init[3], odom_fixed[3], odom_moving[3].
+static int multi(const std::string& config, const std::string& name, const std::string& in, const std::string& out) {
+  ConfigurableManager m;
+  m.read(config);
+  MultiAligner2DPtr aligner = m.getByName<MultiAligner2D>(name);
+  if (!aligner) throw std::runtime_error("no MultiAligner2D named " + name);
+  std::ifstream is(in, std::ios::binary);
+  if (!is.good()) throw std::runtime_error("cannot open " + in);
+  int32_t n_pairs = 0;
+  float sensors[2][3], info[6];
+  is.read((char*) &n_pairs, 4);
+  is.read((char*) sensors, sizeof(sensors));
+  is.read((char*) info, sizeof(info));
+  // tf tree: every laser slice finds its own sensor_in_robot by frame_id (aligner_slice_processor_laser_2d_impl.cpp:7-10)
+  PlatformPtr platform(new Platform);
+  std::vector<std::shared_ptr<AlignerSliceProcessorLaserBase>> lasers;
+  std::shared_ptr<AlignerSliceOdom2DPrior> prior;
+  for (size_t k = 0; k < aligner->param_slice_processors.size(); ++k) {
+    auto s = aligner->param_slice_processors.value(k);
+    s->setPlatform(platform);
+    if (auto l = std::dynamic_pointer_cast<AlignerSliceProcessorLaserBase>(s)) {
+      const float* v = sensors[lasers.size() < 2 ? lasers.size() : 1];
+      platform->addTransform(l->param_frame_id.value(), l->param_base_frame_id.value(),
+                             geometry2d::v2t(Vector3f(v[0], v[1], v[2])));
+      lasers.push_back(l);
+    } else if (auto p = std::dynamic_pointer_cast<AlignerSliceOdom2DPrior>(s)) {
+      prior = p;
+    }
+  }
+  REQUIRE(lasers.size() == 2 && prior);
+  Matrix3f O;
+  const int map[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) O.m[i][j] = info[map[i][j]];
+  prior->setInformationMatrix(O);
+  std::ofstream os(out, std::ios::binary);
+  for (int p = 0; p < n_pairs; ++p) {
+    int32_t n[3];
+    is.read((char*) n, sizeof(n));
+    PointNormal2fVectorCloud f0 = readCloud(is, n[0]), f1 = readCloud(is, n[1]), mv = readCloud(is, n[2]);
+    float v[9];
+    is.read((char*) v, sizeof(v));
+    if (!is.good()) throw std::runtime_error("short read on " + in);
+    Isometry2f odom_fixed  = geometry2d::v2t(Vector3f(v[3], v[4], v[5]));
+    Isometry2f odom_moving = geometry2d::v2t(Vector3f(v[6], v[7], v[8]));
+    PropertyContainerDynamic fixed_scene, moving_scene;
+    fixed_scene.setCloud(lasers[0]->param_fixed_slice_name.value(), &f0);
+    fixed_scene.setCloud(lasers[1]->param_fixed_slice_name.value(), &f1);
+    moving_scene.setCloud(lasers[0]->param_moving_slice_name.value(), &mv);
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0: with the odometry slice bound, pass 1: scenes without odometry
+      if (pass == 0) {
+        fixed_scene.setPose(prior->param_fixed_slice_name.value(), &odom_fixed);
+        moving_scene.setPose(prior->param_moving_slice_name.value(), &odom_moving);
+      } else {
+        fixed_scene.setPose(prior->param_fixed_slice_name.value(), nullptr);
+      }
+      aligner->setFixed(&fixed_scene);
+      aligner->setMoving(&moving_scene);
+      aligner->setMovingInFixed(geometry2d::v2t(Vector3f(v[0], v[1], v[2])));
+      aligner->compute();
+      const auto& st = aligner->iterationStats();
+      const IterationStats last = st.empty() ? IterationStats() : st.back();
+      writeResult(os, geometry2d::t2v(aligner->movingInFixed()), (int) aligner->status(), last.chi_inliers,
+                  last.chi_kernelized, last.num_inliers, last.num_outliers, last.num_correspondences, (int) st.size());
+      const int32_t nc[2] = {(int32_t) lasers[0]->correspondences().size(), (int32_t) lasers[1]->correspondences().size()};
+      os.write((const char*) nc, sizeof(nc));
+      const Matrix3f& H = aligner->informationMatrix();
+      const float h6[6] = {H.m[0][0], H.m[0][1], H.m[0][2], H.m[1][1], H.m[1][2], H.m[2][2]};
+      os.write((const char*) h6, sizeof(h6));
+    }
+  }
+  std::printf("MULTI OK %d pairs\n", n_pairs);
+  return 0;
+}
+
 static void writeCloud(std::ofstream& os, const PointNormal2fVectorCloud& c) {
   const int32_t n = (int32_t) c.size();
   os.write((const char*) &n, 4);
@@ -374,6 +462,7 @@ int main(int argc, char** argv) {
     if (cmd == "parse" && argc == 3) return parse(argv[2]);
     if (cmd == "align" && argc == 6) return align(argv[2], argv[3], argv[4], argv[5]);
     if (cmd == "verify" && argc == 6) return verify(argv[2], argv[3], argv[4], argv[5]);
+    if (cmd == "multi" && argc == 6) return multi(argv[2], argv[3], argv[4], argv[5]);
     if (cmd == "map" && argc == 5) return map(std::atoi(argv[2]), argv[3], argv[4]);
     std::fprintf(stderr, "usage: plugin_test selftest | parse <config> | align|verify <config> <name> <in> <out>\n");
     return 2;

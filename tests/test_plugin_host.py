@@ -14,6 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "srrg2_laser_slam_2d_b200", "plugin_test")
 OWN_CONFIG = os.path.join(ROOT, "configs", "laser_aligner_b200.json")
+MULTI_CONFIG = os.path.join(ROOT, "configs", "multi_laser_aligner_b200.json")
 REF_CONFIGS = "/root/reference/configurations"
 
 
@@ -65,8 +66,20 @@ def test_reference_configurations_load_unchanged(exe):
     assert m["objects"] == 56
     am = {x["name"]: x for x in m["aligners"]}
     assert am["multi_aligner_ld"]["min_num_correspondences"] == 10 and am["multi_aligner_ld"]["max_iterations"] == 30
-    assert "more than one laser slice" in am["multi_aligner"]["unsupported"]   # two rangefinders: SURVEY.md 8f-4
+    tr = am["multi_aligner"]                              # two rangefinders + odometry prior in one aligner (:700-730)
+    assert (tr["slices"], tr["prior_slices"], len(tr["laser_slices"])) == (3, 1, 2)
+    assert [(x["normal_cos"], x["cauchy_chi_threshold"], x["min_num_correspondences"], x["with_sensor"])
+            for x in tr["laser_slices"]] == [(0.9, 0.01, 5, 1), (0.8, -1.0, 5, 1)]
     assert m["loop_detectors"][0]["min_inliers"] == 500
+
+
+def test_own_multi_config_mirrors_the_reference_multi_aligner(exe):
+    d = json.loads(run(exe, "parse", MULTI_CONFIG))
+    tr = d["aligners"][0]
+    assert (tr["name"], tr["slices"], tr["prior_slices"], tr["max_iterations"], tr["canvas_cols"]) == \
+           ("multi_aligner", 3, 1, 10, 721)
+    assert [(x["point_distance"], x["normal_cos"], x["cauchy_chi_threshold"], x["min_num_correspondences"])
+            for x in tr["laser_slices"]] == [(0.5, 0.9, 0.01, 5), (0.5, 0.8, -1.0, 5)]
 
 
 # ---------------------------------------------------------------------------------------------- GPU
@@ -214,3 +227,71 @@ def test_plugin_clipper_and_merger_match_the_oracle(exe, tmp_path, oracle):
         ref_m, _ = oracle.merge(prm, 0.2, scene, meas, pose)
         assert clipped.shape == ref_c.shape and np.array_equal(clipped.view(np.uint32), ref_c.view(np.uint32))
         assert merged.shape == ref_m.shape and np.array_equal(merged.view(np.uint32), ref_m.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_plugin_multi_slice_aligner_with_odometry_prior(exe, tmp_path, handle_factory, oracle):
+    """MULTI.json-shaped MultiAligner2D (two WithSensor laser slices + AlignerSliceOdom2DPrior) through the plugin
+    classes: scenes carry "points_0" / "points_1" / "points" clouds and "odom" poses; compared with the C ABI called
+    directly and with the oracle (kernel summation order), bit for bit."""
+    from srrg2_laser_slam_2d_b200 import default_params
+    from srrg2_laser_slam_2d_b200._abi import make_prior
+    from srrg2_laser_slam_2d_b200.synthetic import make_multi_sensor_pairs
+    n = 4
+    sensors = ((0.2, 0.05, 0.1), (-0.2, 0.0, 3.0))
+    msp = make_multi_sensor_pairs(n, sensors=sensors, n_beams=721, seed=77)
+    info = np.array([80.0, 2.0, 0.5, 90.0, -1.0, 300.0], np.float32)
+    rng = np.random.default_rng(5)
+    odom_fixed = rng.uniform(-2, 2, (n, 3)).astype(np.float32)       # robot pose in the odometry frame now ...
+    inp, out = str(tmp_path / "multi.bin"), str(tmp_path / "multi_out.bin")
+    rt = lambda v: (lambda a: (oracle.lib().orc_t2v(oracle.v2t(*v), a.ctypes.data), a)[1])(np.zeros(3, np.float32))
+    odom_moving = np.zeros((n, 3), np.float32)
+    z = np.zeros((n, 3), np.float32)
+    L = oracle.lib()
+    for p in range(n):                                               # ... and the moving scene's: fixed * odometry delta
+        M = L.orc_compose(oracle.v2t(*odom_fixed[p]), oracle.v2t(*msp.odom_xyt[p]))
+        L.orc_t2v(M, odom_moving[p:p + 1].ctypes.data)
+        # what the slice computes: Z = fixed^-1 * moving, handed to the C ABI as t2v(Z)
+        Z = L.orc_compose(L.orc_inverse(oracle.v2t(*odom_fixed[p])), oracle.v2t(*odom_moving[p]))
+        L.orc_t2v(Z, z[p:p + 1].ctypes.data)
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<i6f6f", n, *sensors[0], *sensors[1], *info))
+        for p in range(n):
+            f0 = msp.fixed_pts[0][msp.fixed_off[0][p]:msp.fixed_off[0][p + 1]]
+            f1 = msp.fixed_pts[1][msp.fixed_off[1][p]:msp.fixed_off[1][p + 1]]
+            mv = msp.moving_pts[msp.moving_off[p]:msp.moving_off[p + 1]]
+            f.write(struct.pack("<3i", len(f0), len(f1), len(mv)))
+            for c in (f0, f1, mv):
+                f.write(np.ascontiguousarray(c, np.float32).tobytes())
+            f.write(np.concatenate([msp.init_xyt[p], odom_fixed[p], odom_moving[p]]).astype(np.float32).tobytes())
+    assert "MULTI OK" in run(exe, "multi", MULTI_CONFIG, "multi_aligner", inp, out)
+    item = np.dtype([("rec", REC), ("nc", "<i4", (2,)), ("H", "<f4", (6,))])
+    got = np.frombuffer(open(out, "rb").read(), item).reshape(n, 2)
+    # reference run: the C ABI directly, sensor_in_robot as t2v(isometry)
+    base = dict(canvas_cols=721, max_iterations=10, min_num_correspondences=5, with_sensor=1, point_distance=0.5)
+    mk = lambda fac: [fac(normal_cos=0.9, cauchy_chi_threshold=0.01, sensor_in_robot=tuple(map(float, rt(sensors[0]))), **base),
+                      fac(normal_cos=0.8, cauchy_chi_threshold=-1.0, sensor_in_robot=tuple(map(float, rt(sensors[1]))), **base)]
+    h = handle_factory()
+    h.upload_clouds(0, msp.fixed_pts[0], msp.fixed_off[0])
+    h.upload_clouds(2, msp.fixed_pts[1], msp.fixed_off[1])
+    h.upload_clouds(1, msp.moving_pts, msp.moving_off)
+    fixed = [(msp.fixed_pts[s], msp.fixed_off[s]) for s in range(2)]
+    moving = [(msp.moving_pts, msp.moving_off)] * 2
+    exact = [f for f in REC.names if f != "theta"]
+    for pass_, kw, okw in ((0, dict(prior=make_prior(info), prior_z=z), dict(prior=oracle.make_prior(info), prior_z=z)),
+                           (1, {}, {})):
+        g = h.align_multi(mk(default_params), [0, 2], [1, 1], msp.init_xyt, **kw)
+        o, _ = oracle.align_multi_batch(mk(oracle.default_params), fixed, moving, msp.init_xyt, sum_mode=oracle.SUM_TREE,
+                                        tree_threads=512, **okw)
+        rec = got[:, pass_]["rec"]
+        assert same(rec[exact], g[exact]) is None
+        assert np.abs(rec["theta"] - g["theta"]).max() <= 2.4e-7     # movingInFixed() is an Isometry2f: v2t -> t2v
+        assert np.array_equal(got[:, pass_]["H"].view(np.uint32), g["H"].view(np.uint32))   # informationMatrix()
+        for f in ("x", "y", "theta", "chi_inliers", "status", "n_inliers", "n_corr", "iterations"):
+            assert np.array_equal(g[f], o[f]), f
+        assert (g["status"] == 0).all()
+        # slice->correspondences() of both slices: the last iteration's lists
+        assert np.array_equal(got[:, pass_]["nc"].sum(1), g["n_corr"])
+    # the bound prior changes the answer and is one more inlier factor
+    assert not np.array_equal(got[:, 0]["rec"]["x"], got[:, 1]["rec"]["x"])
+    assert np.array_equal(got[:, 0]["rec"]["n_inliers"] + got[:, 0]["rec"]["n_kernelized"], got[:, 0]["rec"]["n_corr"] + 1)
