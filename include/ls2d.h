@@ -258,6 +258,37 @@ int ls2d_merge_scene_dev(ls2d_handle* h, void* scene_points_dev, int32_t* scene_
                          const void* measurement_points_dev, int32_t n_measurement,
                          const float* measurement_in_scene_xyt, float merge_threshold, int32_t* counters_dev);
 
+/* ---- raw scans as the wire format --------------------------------------------------
+ * replaces: RawDataPreprocessorProjective2D::setRawData + compute
+ * (R/sensor_processing/raw_data_preprocessor_projective_2d.cpp:13-51, 53-104): LaserMessage ranges -> polar
+ * unprojection with the sensor matrix [1/res, n/2] (.cpp:87-90) -> sliding-window normals
+ * (NormalComputator1DSlidingWindow, L0.json:711-719) -> voxelize(res, res, 1, 1) (.cpp:38-42) or the valid points
+ * in beam order (.cpp:44-48).  4 B per beam cross the bus instead of 16 B per point. */
+typedef struct ls2d_scan_params {
+  float angle_min, angle_max;         /* LaserMessage::angle_min / angle_max (.cpp:85-86) */
+  float msg_range_min, msg_range_max; /* LaserMessage::range_min / range_max (.cpp:83-84) */
+  float range_min, range_max;         /* PARAM range_min / range_max (raw_data_preprocessor_projective_2d.h:39-40) */
+  float voxelize_resolution;          /* PARAM voxelize_resolution (.h:41-45, default 0.02); <= 0: valid-only copy */
+  float normal_point_distance;        /* NormalComputator1DSlidingWindow::normal_point_distance (L0.json:718) */
+  int32_t normal_min_points;          /* NormalComputator1DSlidingWindow::normal_min_points (L0.json:715) */
+} ls2d_scan_params;
+void ls2d_default_scan_params(ls2d_scan_params* p);
+/* n_scans scans of n_beams ranges each (host, row-major) -> out_points [n_scans * n_beams * 4] (scan s starts at
+ * s * n_beams * 4; out_counts[s] points are valid), the cloud each RawDataPreprocessorProjective2D::compute would
+ * hand to setMeas().  n_beams <= 8192. */
+int ls2d_preprocess_scans(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges, int32_t n_beams,
+                          int32_t n_scans, float* out_points, int32_t* out_counts);
+/* same, but the clouds stay on the device as cloud set `which` (packed CSR), ready for ls2d_align_batch & co.;
+ * asynchronous on the handle's stream */
+int ls2d_preprocess_scans_to_set(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges,
+                                 int32_t n_beams, int32_t n_scans);
+int ls2d_preprocess_scans_to_set_dev(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges_dev,
+                                     int32_t n_beams, int32_t n_scans);
+/* copies cloud set `which` back: offsets [n_clouds + 1], points [offsets[n_clouds] * 4] (capacity_points is the
+ * room in `points`); n_clouds must match the set */
+int ls2d_download_clouds(ls2d_handle* h, int which, float* points, int32_t* offsets, int32_t n_clouds,
+                         int64_t capacity_points);
+
 /* ---- introspection ---------------------------------------------------------------------------------*/
 /* threads per pair the fused kernel uses for clouds of up to max_points points: fixes the shape of its
  * H/b reduction tree (the oracle's ORC_SUM_TREE mode mirrors it) */

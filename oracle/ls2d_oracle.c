@@ -901,3 +901,228 @@ int32_t orc_merge(const orc_params* prm, float merge_threshold, orc_point* scene
   free(tmeas);
   return scene_size;
 }
+
+/* ---------------------------------------------------------------- next row
+ * RawDataPreprocessorProjective2D: LaserMessage ranges -> PointNormal2fVectorCloud
+ * (R/sensor_processing/raw_data_preprocessor_projective_2d.cpp:13-51, 77-104).  The in-repo part (range limits,
+ * sensor matrix, voxelize / valid-only branch) is followed line by line; the unprojector, the sliding-window normal
+ * computator and PointCloud::voxelize live in srrg2_core (un-vendored) and are restated with decision points:
+ *  P1 PointNormal2fUnprojectorPolar reads only fx = K(0,0) and cx = K(0,1) of the sensor matrix (its second row is
+ *     zero, .cpp:89-90, so no matrix inverse can be involved): azimuth = (1/fx) * (c - cx); a beam is skipped when
+ *     range < range_min || range > range_max; point = (range * cosf(azimuth), range * sinf(azimuth)), normal 0.
+ *     The cloud handed to the normal computator holds the accepted beams only, in beam order (.cpp:29-31 uses the
+ *     unorganised back-inserter overload).
+ *  P2 NormalComputator1DSlidingWindow: the window of point i is the maximal run of consecutive points j around i
+ *     with |p_j - p_i|^2 < normal_point_distance^2 (scan outwards from i, stop at the first violation).
+ *  P3 fewer than normal_min_points points in the window (i included) => the point is Invalid (dropped by both
+ *     branches of .cpp:37-48).
+ *  P4 mean = sum / n; covariance = sum (p - mean)(p - mean)^T / n, sums sequential in ascending index.
+ *  P5 normal = eigenvector of the smallest eigenvalue by Eigen's closed-form 2x2
+ *     SelfAdjointEigenSolver::computeDirect (shift by trace/2, scale by max|coeff|, roots t1 -/+ t0, eigenvector of
+ *     the larger root from the better-conditioned row, the other by unitOrthogonal()); degenerate (equal roots):
+ *     identity => normal (1, 0).
+ *  P6 the normal is flipped to face the sensor: n <- -n when n . p > 0.
+ *  P7 voxelize(res_coeffs = (res, res, 1, 1)) (.cpp:40-42): key = trunc-toward-zero of the plain vector
+ *     (x, y, nx, ny) * (1/res, 1/res, 1, 1) as int; entries sorted by key (lexicographic), equal keys keep cloud
+ *     order; each run of equal keys emits ONE point: the sequential sum of the run times (1 / count), normal
+ *     renormalised with Eigen's rule; only Valid points take part; output in sorted order.
+ *  P8 voxelize_resolution <= 0: the Valid points in cloud order (.cpp:44-48).
+ */
+
+typedef struct {
+  int32_t k[4];
+  int32_t idx;
+} vox_entry;
+
+static int vox_cmp(const void* a, const void* b) {
+  const vox_entry* x = (const vox_entry*) a;
+  const vox_entry* y = (const vox_entry*) b;
+  for (int d = 0; d < 4; ++d) {
+    if (x->k[d] != y->k[d]) {
+      return x->k[d] < y->k[d] ? -1 : 1;
+    }
+  }
+  return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+void orc_default_scan_params(orc_scan_params* p) {
+  p->angle_min             = -2.34747f; /* L0.json:411 (the message carries the sensor's own values) */
+  p->angle_max             = 2.35619f;  /* L0.json:408 */
+  p->msg_range_min         = 0.f;
+  p->msg_range_max         = 30.f;      /* L0.json:429 */
+  p->range_min             = 0.f;       /* raw_data_preprocessor_projective_2d.h:39 */
+  p->range_max             = 1000.f;    /* raw_data_preprocessor_projective_2d.h:40 */
+  p->voxelize_resolution   = 0.02f;     /* raw_data_preprocessor_projective_2d.h:41-45 */
+  p->normal_point_distance = 0.3f;      /* L0.json:718 */
+  p->normal_min_points     = 5;         /* L0.json:715 */
+}
+
+/* Eigen 3.3 SelfAdjointEigenSolver<Matrix2f>::computeDirect, eigenvector of the smallest eigenvalue (P5) */
+static void smallest_eigenvector_2x2(float m00, float m10, float m11, float* vx, float* vy) {
+  const float shift = (m00 + m11) / 2.f;
+  float a = m00 - shift, b = m10, c = m11 - shift;
+  float scale = fabsf(a);
+  if (fabsf(b) > scale) {
+    scale = fabsf(b);
+  }
+  if (fabsf(c) > scale) {
+    scale = fabsf(c);
+  }
+  if (scale > 0.f) {
+    a = a / scale, b = b / scale, c = c / scale;
+  }
+  const float d  = a - c;
+  const float t0 = 0.5f * sqrtf(d * d + 4.f * (b * b));
+  const float t1 = 0.5f * (a + c);
+  const float r0 = t1 - t0, r1 = t1 + t0;
+  if ((r1 - r0) <= fabsf(r1) * FLT_EPSILON) {
+    *vx = 1.f, *vy = 0.f; /* eivecs.setIdentity(): column 0 */
+    return;
+  }
+  const float a1 = a - r1, c1 = c - r1;
+  const float a2 = a1 * a1, c2 = c1 * c1, b2 = b * b;
+  float ux, uy; /* eigenvector of the larger root */
+  if (a2 > c2) {
+    const float n = sqrtf(a2 + b2);
+    ux = -b / n, uy = a1 / n;
+  } else {
+    const float n = sqrtf(c2 + b2);
+    ux = -c1 / n, uy = b / n;
+  }
+  /* unitOrthogonal(): (-y, x).normalized() */
+  const float ox = -uy, oy = ux;
+  const float z  = ox * ox + oy * oy;
+  if (z > 0.f) {
+    const float n = sqrtf(z);
+    *vx = ox / n, *vy = oy / n;
+  } else {
+    *vx = ox, *vy = oy;
+  }
+}
+
+int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int32_t n_beams, orc_point* out) {
+  if (n_beams <= 0) {
+    return 0;
+  }
+  /* _processLaserMessage, .cpp:83-90 */
+  const float range_max  = sp->msg_range_max < sp->range_max ? sp->msg_range_max : sp->range_max;
+  const float range_min  = sp->msg_range_min > sp->range_min ? sp->msg_range_min : sp->range_min;
+  const float sensor_res = (sp->angle_max - sp->angle_min) / (float) n_beams;
+  const float fx = 1.f / sensor_res, cx = (float) n_beams / 2.f;
+  const float ifx = 1.f / fx; /* P1 */
+  orc_point* pts   = (orc_point*) malloc(sizeof(orc_point) * (size_t) n_beams);
+  uint8_t* valid   = (uint8_t*) malloc((size_t) n_beams);
+  int32_t n = 0;
+  for (int32_t c = 0; c < n_beams; ++c) { /* unprojector, P1 */
+    const float r = ranges[c];
+    if (r < range_min || r > range_max) {
+      continue;
+    }
+    const float az = ifx * ((float) c - cx);
+    pts[n].x  = r * cosf(az);
+    pts[n].y  = r * sinf(az);
+    pts[n].nx = 0.f;
+    pts[n].ny = 0.f;
+    ++n;
+  }
+  /* NormalComputator1DSlidingWindow::computeNormals (P2..P6) */
+  const float d2 = sp->normal_point_distance * sp->normal_point_distance;
+  for (int32_t i = 0; i < n; ++i) {
+    int32_t lo = i, hi = i;
+    while (lo > 0) {
+      const float dx = pts[lo - 1].x - pts[i].x, dy = pts[lo - 1].y - pts[i].y;
+      if (!(dx * dx + dy * dy < d2)) {
+        break;
+      }
+      --lo;
+    }
+    while (hi + 1 < n) {
+      const float dx = pts[hi + 1].x - pts[i].x, dy = pts[hi + 1].y - pts[i].y;
+      if (!(dx * dx + dy * dy < d2)) {
+        break;
+      }
+      ++hi;
+    }
+    const int32_t cnt = hi - lo + 1;
+    valid[i] = cnt >= sp->normal_min_points; /* P3 */
+    if (!valid[i]) {
+      continue;
+    }
+    float sx = 0.f, sy = 0.f;
+    for (int32_t j = lo; j <= hi; ++j) {
+      sx = sx + pts[j].x, sy = sy + pts[j].y;
+    }
+    const float mx = sx / (float) cnt, my = sy / (float) cnt; /* P4 */
+    float cxx = 0.f, cxy = 0.f, cyy = 0.f;
+    for (int32_t j = lo; j <= hi; ++j) {
+      const float dx = pts[j].x - mx, dy = pts[j].y - my;
+      cxx = cxx + dx * dx, cxy = cxy + dx * dy, cyy = cyy + dy * dy;
+    }
+    cxx = cxx / (float) cnt, cxy = cxy / (float) cnt, cyy = cyy / (float) cnt;
+    float nx, ny;
+    smallest_eigenvector_2x2(cxx, cxy, cyy, &nx, &ny); /* P5 */
+    if (nx * pts[i].x + ny * pts[i].y > 0.f) {          /* P6 */
+      nx = -nx, ny = -ny;
+    }
+    pts[i].nx = nx, pts[i].ny = ny;
+  }
+  int32_t k = 0;
+  if (sp->voxelize_resolution > 0.f) { /* .cpp:38-42, P7 */
+    const float inv = 1.f / sp->voxelize_resolution;
+    vox_entry* e    = (vox_entry*) malloc(sizeof(vox_entry) * (size_t)(n > 0 ? n : 1));
+    int32_t m = 0;
+    for (int32_t i = 0; i < n; ++i) {
+      if (!valid[i]) {
+        continue;
+      }
+      e[m].k[0] = (int32_t)(pts[i].x * inv);
+      e[m].k[1] = (int32_t)(pts[i].y * inv);
+      e[m].k[2] = (int32_t)(pts[i].nx * 1.f);
+      e[m].k[3] = (int32_t)(pts[i].ny * 1.f);
+      e[m].idx  = i;
+      ++m;
+    }
+    qsort(e, (size_t) m, sizeof(vox_entry), vox_cmp);
+    int32_t s = 0;
+    while (s < m) {
+      int32_t t = s;
+      float ax = 0.f, ay = 0.f, anx = 0.f, any = 0.f;
+      while (t < m && e[t].k[0] == e[s].k[0] && e[t].k[1] == e[s].k[1] && e[t].k[2] == e[s].k[2] &&
+             e[t].k[3] == e[s].k[3]) {
+        const orc_point* p = &pts[e[t].idx];
+        ax = ax + p->x, ay = ay + p->y, anx = anx + p->nx, any = any + p->ny;
+        ++t;
+      }
+      const float w = 1.f / (float) (t - s);
+      ax = ax * w, ay = ay * w, anx = anx * w, any = any * w;
+      const float z = anx * anx + any * any;
+      if (z > 0.f) {
+        const float nrm = sqrtf(z);
+        anx = anx / nrm, any = any / nrm;
+      }
+      out[k].x = ax, out[k].y = ay, out[k].nx = anx, out[k].ny = any;
+      ++k;
+      s = t;
+    }
+    free(e);
+  } else { /* .cpp:44-48, P8 */
+    for (int32_t i = 0; i < n; ++i) {
+      if (valid[i]) {
+        out[k++] = pts[i];
+      }
+    }
+  }
+  free(pts);
+  free(valid);
+  return k;
+}
+
+void orc_preprocess_scans(const orc_scan_params* sp, const float* ranges, int32_t n_beams, int32_t n_scans,
+                          int32_t n_threads, orc_point* out, int32_t* counts) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) num_threads(n_threads > 1 ? n_threads : 1)
+#endif
+  for (int32_t s = 0; s < n_scans; ++s) {
+    counts[s] = orc_preprocess_scan(sp, ranges + (size_t) s * n_beams, n_beams, out + (size_t) s * n_beams);
+  }
+}

@@ -189,6 +189,26 @@ int32_t orc_merge(const orc_params* prm, float merge_threshold, orc_point* scene
                   const orc_point* measurement, int32_t n_measurement, orc_iso measurement_in_scene,
                   int32_t* counters);
 
+/* ---- RawDataPreprocessorProjective2D: LaserMessage ranges -> PointNormal2f cloud
+ * R/sensor_processing/raw_data_preprocessor_projective_2d.cpp:13-51,77-104; decision points P1..P8 in the .c */
+typedef struct {
+  float angle_min, angle_max;         /* LaserMessage angle_min / angle_max (.cpp:85-86) */
+  float msg_range_min, msg_range_max; /* LaserMessage range_min / range_max (.cpp:83-84) */
+  float range_min, range_max;         /* PARAMs range_min / range_max (.h:39-40) */
+  float voxelize_resolution;          /* PARAM (.h:41-45); <= 0: valid-only copy */
+  float normal_point_distance;        /* NormalComputator1DSlidingWindow (L0.json:711-719) */
+  int32_t normal_min_points;
+} orc_scan_params;
+
+void orc_default_scan_params(orc_scan_params* p);
+
+/* one scan; `out` holds n_beams points; returns the number of points produced */
+int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int32_t n_beams, orc_point* out);
+
+/* batch: scan s reads ranges[s * n_beams ..], writes out[s * n_beams ..] and counts[s] */
+void orc_preprocess_scans(const orc_scan_params* sp, const float* ranges, int32_t n_beams, int32_t n_scans,
+                          int32_t n_threads, orc_point* out, int32_t* counts);
+
 /* host libm bulk drivers for tests/test_math_host.py */
 void orc_libm_atan2f_n(const float* y, const float* x, float* out, long n);
 void orc_libm_sincosf_n(const float* x, float* s, float* c, long n);

@@ -47,6 +47,14 @@ def make_prior(information, cauchy_chi_threshold: float = -1.0) -> Prior:
     return pr
 
 
+class ScanParams(C.Structure):
+    """ls2d_scan_params -- LaserMessage fields + RawDataPreprocessorProjective2D / normal computator PARAMs."""
+    _fields_ = [("angle_min", C.c_float), ("angle_max", C.c_float), ("msg_range_min", C.c_float),
+                ("msg_range_max", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float),
+                ("voxelize_resolution", C.c_float), ("normal_point_distance", C.c_float),
+                ("normal_min_points", C.c_int32)]
+
+
 class Gates(C.Structure):
     _fields_ = [("min_inliers", C.c_int32), ("max_chi_per_inlier", C.c_float), ("min_inlier_ratio", C.c_float)]
 
@@ -69,7 +77,8 @@ EXPORTS = [
     "ls2d_score_batch_dev", "ls2d_find_correspondences", "ls2d_project", "ls2d_verify", "ls2d_verify_dev",
     "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_threads", "ls2d_launch_count",
     "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev", "ls2d_align_multi", "ls2d_align_multi_dev",
-    "ls2d_find_correspondences_in",
+    "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
+    "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
 ]
 
 _lib = None
@@ -113,6 +122,12 @@ def load():
     L.ls2d_merge_scene_dev.argtypes = [vp, vp, vp, i32, vp, i32, vp, f32, vp]
     L.ls2d_align_multi.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp]
     L.ls2d_align_multi_dev.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, vp, vp]
+    SP = C.POINTER(ScanParams)
+    L.ls2d_default_scan_params.argtypes, L.ls2d_default_scan_params.restype = [SP], None
+    L.ls2d_preprocess_scans.argtypes = [vp, SP, vp, i32, i32, vp, vp]
+    L.ls2d_preprocess_scans_to_set.argtypes = [vp, C.c_int, SP, vp, i32, i32]
+    L.ls2d_preprocess_scans_to_set_dev.argtypes = [vp, C.c_int, SP, vp, i32, i32]
+    L.ls2d_download_clouds.argtypes = [vp, C.c_int, vp, vp, i32, i64]
     L.ls2d_reduction_threads.argtypes = [i32]
     L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
     _lib = L
@@ -127,6 +142,14 @@ def default_params(**kw) -> Params:
             p.sensor_in_robot = (C.c_float * 3)(*v)
         else:
             setattr(p, k, v)
+    return p
+
+
+def default_scan_params(**kw) -> ScanParams:
+    p = ScanParams()
+    load().ls2d_default_scan_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
     return p
 
 
@@ -322,6 +345,34 @@ class Handle:
         self._check(self._L.ls2d_merge_scene(self._h, _ptr(buf), C.byref(size), cap, _ptr(measurement), len(measurement),
                                              _ptr(xyt), merge_threshold, _ptr(counters)))
         return buf[:size.value].copy(), counters
+
+    # ---- raw scans (RawDataPreprocessorProjective2D)
+    def preprocess_scans(self, sp: ScanParams, ranges: np.ndarray):
+        """ranges [n_scans, n_beams] -> (points [n_scans, n_beams, 4], counts [n_scans])"""
+        ranges = _f32(ranges)
+        n_scans, n_beams = ranges.shape
+        out = np.zeros((n_scans, n_beams, 4), np.float32)
+        cnt = np.zeros(n_scans, np.int32)
+        self._check(self._L.ls2d_preprocess_scans(self._h, C.byref(sp), _ptr(ranges), n_beams, n_scans, _ptr(out),
+                                                  _ptr(cnt)))
+        return out, cnt
+
+    def preprocess_scans_to_set(self, which: int, sp: ScanParams, ranges: np.ndarray):
+        """raw ranges [n_scans, n_beams] become the resident cloud set `which`"""
+        ranges = _f32(ranges)
+        n_scans, n_beams = ranges.shape
+        self._check(self._L.ls2d_preprocess_scans_to_set(self._h, which, C.byref(sp), _ptr(ranges), n_beams, n_scans))
+        self.sync()
+
+    def preprocess_scans_to_set_dev(self, which: int, sp: ScanParams, ranges_ptr: int, n_beams: int, n_scans: int):
+        self._check(self._L.ls2d_preprocess_scans_to_set_dev(self._h, which, C.byref(sp), C.c_void_p(ranges_ptr),
+                                                             n_beams, n_scans))
+
+    def download_clouds(self, which: int, n_clouds: int, capacity_points: int):
+        pts = np.zeros((capacity_points, 4), np.float32)
+        off = np.zeros(n_clouds + 1, np.int32)
+        self._check(self._L.ls2d_download_clouds(self._h, which, _ptr(pts), _ptr(off), n_clouds, capacity_points))
+        return pts[:off[-1]].copy(), off
 
     # ---- loop-closure verification
     def verify(self, query_id: int, candidate_ids, guesses_xyt, gates: Gates, candidate_base: int = 0,

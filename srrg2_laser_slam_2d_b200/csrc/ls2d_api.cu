@@ -12,6 +12,7 @@
 
 #include "ls2d_kernels.cuh"
 #include "ls2d_multi.cuh"
+#include "ls2d_scan.cuh"
 
 using namespace ls2d;
 
@@ -41,7 +42,7 @@ struct ls2d_handle {
   ls2d_params prm;
   dev_params dp;
   cloud_set sets[LS2D_MAX_CLOUD_SETS];
-  scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior;
+  scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior, d_ranges;
   int64_t launches = 0;
   int variant      = 0;  // LS2D_ICP_VARIANT: tuning knob for the 1081-point kernel shape
   // NCCL, resolved lazily
@@ -311,6 +312,7 @@ int ls2d_destroy(ls2d_handle* h) {
   release(h->d_iters);
   release(h->d_best);
   release(h->d_misc);
+  release(h->d_ranges);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->nccl_lib) dlclose(h->nccl_lib);
   delete h;
@@ -843,6 +845,150 @@ int ls2d_merge_scene(ls2d_handle* h, float* scene, int32_t* scene_size, int32_t 
   CU(cudaStreamSynchronize(h->stream));
   *scene_size = ints[0];
   if (counters) counters[0] = ints[1], counters[1] = ints[2], counters[2] = ints[3];
+  return LS2D_OK;
+}
+
+// ---- RawDataPreprocessorProjective2D ------------------------------------------------
+void ls2d_default_scan_params(ls2d_scan_params* p) {
+  if (!p) return;
+  p->angle_min             = -2.34747f;
+  p->angle_max             = 2.35619f;
+  p->msg_range_min         = 0.f;
+  p->msg_range_max         = 30.f;
+  p->range_min             = 0.f;
+  p->range_max             = 1000.f;
+  p->voxelize_resolution   = 0.02f;
+  p->normal_point_distance = 0.3f;
+  p->normal_min_points     = 5;
+}
+
+// ranges_dev -> strided points + counts on the device (asynchronous)
+static int preprocess_dev(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges_dev, int32_t n_beams,
+                          int32_t n_scans, float4* out_dev, int* counts_dev) {
+  if (n_beams < 1 || n_beams > 8192 || !(sp->angle_max > sp->angle_min)) return LS2D_ERR_INVALID;
+  scan_dev_params P;
+  // _processLaserMessage, raw_data_preprocessor_projective_2d.cpp:83-90 (single binary32 operations)
+  P.range_max            = sp->msg_range_max < sp->range_max ? sp->msg_range_max : sp->range_max;
+  P.range_min            = sp->msg_range_min > sp->range_min ? sp->msg_range_min : sp->range_min;
+  const float sensor_res = (sp->angle_max - sp->angle_min) / (float) n_beams;
+  const float fx         = 1.f / sensor_res;
+  P.ifx                  = 1.f / fx;
+  P.cx                   = (float) n_beams / 2.f;
+  P.d2                   = sp->normal_point_distance * sp->normal_point_distance;
+  P.inv_res              = sp->voxelize_resolution > 0.f ? 1.f / sp->voxelize_resolution : 0.f;
+  P.min_points           = sp->normal_min_points;
+  P.n_beams              = n_beams;
+  P.sort_cap             = 0;
+  if (P.inv_res != 0.f) {
+    P.sort_cap = 1;
+    while (P.sort_cap < n_beams) P.sort_cap <<= 1;
+  }
+  scan_args a;
+  a.ranges  = ranges_dev;
+  a.out     = out_dev;
+  a.counts  = counts_dev;
+  a.n_scans = n_scans;
+  const size_t smem = scan_smem_bytes(n_beams, P.sort_cap);
+  if (smem > 227 * 1024) return LS2D_ERR_UNSUPPORTED;
+  CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  preprocess_kernel<<<n_scans, 256, smem, h->stream>>>(P, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int ls2d_preprocess_scans(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges, int32_t n_beams,
+                          int32_t n_scans, float* out_points, int32_t* out_counts) {
+  if (!h || !sp || n_scans < 0 || n_beams < 1 || (n_scans > 0 && (!ranges || !out_points || !out_counts)))
+    return LS2D_ERR_INVALID;
+  if (n_scans == 0) return LS2D_OK;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  const size_t n_pts = (size_t) n_scans * n_beams;
+  if ((rc = h2d(h, h->d_ranges, ranges, sizeof(float) * n_pts))) return rc;
+  if ((rc = reserve(h->d_misc, sizeof(float4) * n_pts + sizeof(int) * (size_t) n_scans))) return rc;
+  float4* d_out = (float4*) h->d_misc.p;
+  int* d_cnt    = (int*) ((char*) h->d_misc.p + sizeof(float4) * n_pts);
+  if ((rc = preprocess_dev(h, sp, (const float*) h->d_ranges.p, n_beams, n_scans, d_out, d_cnt))) return rc;
+  CU(cudaMemcpyAsync(out_points, d_out, sizeof(float4) * n_pts, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(out_counts, d_cnt, sizeof(int) * (size_t) n_scans, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
+}
+
+static int scans_to_set_impl(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges_dev,
+                             int32_t n_beams, int32_t n_scans) {
+  int rc;
+  const size_t n_pts = (size_t) n_scans * n_beams;
+  if ((rc = reserve(h->d_misc, sizeof(float4) * n_pts + sizeof(int) * (size_t) n_scans))) return rc;
+  float4* d_tmp = (float4*) h->d_misc.p;
+  int* d_cnt    = (int*) ((char*) h->d_misc.p + sizeof(float4) * n_pts);
+  cloud_set& c  = h->sets[which];
+  if (!c.owned) c = cloud_set();
+  c.owned            = true;
+  const size_t n_off = (size_t) n_scans + 1;
+  if (n_pts > c.cap_pts || !c.pts) {
+    if (c.pts) cudaFree(c.pts);
+    c.pts     = nullptr;
+    c.cap_pts = 0;
+    CU(cudaMalloc((void**) &c.pts, (n_pts + 16) * sizeof(float4)));
+    c.cap_pts = n_pts + 16;
+  }
+  if (n_off > c.cap_off || !c.off) {
+    if (c.off) cudaFree(c.off);
+    c.off     = nullptr;
+    c.cap_off = 0;
+    CU(cudaMalloc((void**) &c.off, (n_off + 16) * sizeof(int)));
+    c.cap_off = n_off + 16;
+  }
+  if (n_scans > 0) {
+    if ((rc = preprocess_dev(h, sp, ranges_dev, n_beams, n_scans, d_tmp, d_cnt))) return rc;
+    scan_offsets_kernel<<<1, 1024, 0, h->stream>>>(d_cnt, n_scans, c.off);
+    CU(cudaGetLastError());
+    scan_pack_kernel<<<n_scans, 128, 0, h->stream>>>(d_tmp, c.off, n_beams, c.pts);
+    CU(cudaGetLastError());
+    h->launches += 2;
+  } else {
+    CU(cudaMemsetAsync(c.off, 0, sizeof(int), h->stream));
+  }
+  c.n_clouds   = n_scans;
+  c.max_points = n_beams;  // upper bound: the counts stay on the device
+  return LS2D_OK;
+}
+
+int ls2d_preprocess_scans_to_set(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges,
+                                 int32_t n_beams, int32_t n_scans) {
+  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !sp || n_scans < 0 || n_beams < 1 || (n_scans > 0 && !ranges))
+    return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if (n_scans > 0 && (rc = h2d(h, h->d_ranges, ranges, sizeof(float) * (size_t) n_scans * n_beams))) return rc;
+  return scans_to_set_impl(h, which, sp, (const float*) h->d_ranges.p, n_beams, n_scans);
+}
+
+int ls2d_preprocess_scans_to_set_dev(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges_dev,
+                                     int32_t n_beams, int32_t n_scans) {
+  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !sp || n_scans < 0 || n_beams < 1 || (n_scans > 0 && !ranges_dev))
+    return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  return scans_to_set_impl(h, which, sp, ranges_dev, n_beams, n_scans);
+}
+
+int ls2d_download_clouds(ls2d_handle* h, int which, float* points, int32_t* offsets, int32_t n_clouds,
+                         int64_t capacity_points) {
+  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !offsets) return LS2D_ERR_INVALID;
+  const cloud_set& c = h->sets[which];
+  if (!c.pts || !c.off) return LS2D_ERR_NOT_READY;
+  if (n_clouds != c.n_clouds) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(offsets, c.off, sizeof(int) * ((size_t) n_clouds + 1), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const int64_t total = offsets[n_clouds];
+  if (total > capacity_points || (total > 0 && !points)) return LS2D_ERR_INVALID;
+  if (total > 0) {
+    CU(cudaMemcpyAsync(points, c.pts, sizeof(float4) * (size_t) total, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   return LS2D_OK;
 }
 

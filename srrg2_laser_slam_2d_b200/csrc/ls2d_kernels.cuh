@@ -347,6 +347,13 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
       if (col[j] >= 0 && zidx[col[j]] == (unsigned) (tid + j * T)) {
         fimg[col[j]]   = fp[j];
         fdepth[col[j]] = u2f(rb[j]);
+      }
+    __syncthreads();
+    // hand the z-buffer back empty for the moving cloud (a separate pass: the losers of a column were still
+    // reading zidx above; every toucher writes the same EMPTY values)
+#pragma unroll
+    for (int j = 0; j < PPT; ++j)
+      if (col[j] >= 0) {
         zdepth[col[j]] = Z_EMPTY_DEPTH;
         zidx[col[j]]   = Z_EMPTY_IDX;
       }

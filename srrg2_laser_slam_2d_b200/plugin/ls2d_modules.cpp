@@ -218,6 +218,85 @@ namespace srrg2_laser_slam_2d {
     (void) sensorInRobot();  // throws when the tf lookup fails, like setupFactorWithSensor
   }
 
+  // ---- RawDataPreprocessorProjective2D (R/sensor_processing/raw_data_preprocessor_projective_2d.cpp)
+  bool RawDataPreprocessorProjective2D::setRawData(BaseSensorMessagePtr msg) {
+    if (!msg) throw std::runtime_error("RawDataPreprocessorProjective2D::setMeasurement|measurement is not set");  // .cpp:54-57
+    _raw_data = msg;
+    _status   = Error;
+    // extractMessage<LaserMessage>(msg, scan_topic): the message itself when type and topic match (.cpp:62-63)
+    LaserMessagePtr laser = std::dynamic_pointer_cast<LaserMessage>(msg);
+    if (laser && laser->topic.value() != param_scan_topic.value()) laser.reset();
+    if (!laser) {
+      std::cerr << "RawDataPreprocessorProjective2D::setMeasurement|measurement does not contain a laser message"
+                << std::endl;  // .cpp:64-68
+      return false;
+    }
+    _processLaserMessage(laser);
+    _status = Ready;
+    return true;
+  }
+
+  void RawDataPreprocessorProjective2D::_processLaserMessage(LaserMessagePtr message) {
+    _laser  = message;
+    _ranges = &message->ranges.value();
+    if (!param_unprojector.value())
+      throw std::runtime_error("RawDataPreprocessorProjective2D::_processLaserMessage|missing unprojector");  // .cpp:94-97
+    ls2d_scan_params sp;
+    fillScanParams(sp);
+    // .cpp:83-102: the unprojector takes the message's limits and the sensor matrix [1/res, n/2]
+    PointNormal2fUnprojectorPolarPtr unprojector = param_unprojector.value();
+    unprojector->param_range_min.setValue(sp.msg_range_min > sp.range_min ? sp.msg_range_min : sp.range_min);
+    unprojector->param_range_max.setValue(sp.msg_range_max < sp.range_max ? sp.msg_range_max : sp.range_max);
+    unprojector->param_angle_max.setValue(sp.angle_max);
+    unprojector->param_angle_min.setValue(sp.angle_min);
+    const float n = (float) _ranges->size();
+    if (n > 0.f) unprojector->setCameraMatrix(1.f / ((sp.angle_max - sp.angle_min) / n), n / 2.f);
+  }
+
+  void RawDataPreprocessorProjective2D::fillScanParams(ls2d_scan_params& sp) const {
+    ls2d_default_scan_params(&sp);
+    if (_laser) {
+      sp.angle_min     = _laser->angle_min.value();
+      sp.angle_max     = _laser->angle_max.value();
+      sp.msg_range_min = _laser->range_min.value();
+      sp.msg_range_max = _laser->range_max.value();
+    }
+    sp.range_min           = param_range_min.value();
+    sp.range_max           = param_range_max.value();
+    sp.voxelize_resolution = param_voxelize_resolution.value();
+    if (param_normal_computator_sliding.value()) {
+      sp.normal_point_distance = param_normal_computator_sliding->param_normal_point_distance.value();
+      sp.normal_min_points     = param_normal_computator_sliding->param_normal_min_points.value();
+    }
+  }
+
+  void RawDataPreprocessorProjective2D::compute() {
+    if (!_meas || !_raw_data) {  // .cpp:14-17
+      _status = Error;
+      return;
+    }
+    if (!param_unprojector.value())
+      throw std::runtime_error("RawDataPreprocessorProjective2D::compute| missing unprojector");  // .cpp:19-21
+    if (!param_normal_computator_sliding.value())
+      throw std::runtime_error("RawDataPreprocessorProjective2D::compute| missing normal computator");
+    if (!_ranges) {
+      _status = Error;
+      return;
+    }
+    _meas->clear();
+    const int32_t n_beams = (int32_t) _ranges->size();
+    if (n_beams > 0) {
+      ls2d_scan_params sp;
+      fillScanParams(sp);
+      std::vector<float> out((size_t) n_beams * 4);
+      int32_t n = 0;
+      Ls2dDevice::check(ls2d_preprocess_scans(_device.handle(), &sp, _ranges->data(), n_beams, 1, out.data(), &n),
+                        "RawDataPreprocessorProjective2D::compute");
+      unflatten(out.data(), (size_t) n, *_meas);
+    }
+    _status = Ready;
+  }
+
   void srrg2_laser_slam_2d_registerTypes() {
     using namespace srrg2_core;
     using namespace srrg2_solver;
@@ -240,6 +319,10 @@ namespace srrg2_laser_slam_2d {
     // R/instances.cpp:30,32
     BOSS_REGISTER_CLASS(MergerProjective2D);
     BOSS_REGISTER_CLASS(SceneClipperProjective2D);
+    // R/instances.cpp:28 and the srrg2_core classes its parameters point at
+    BOSS_REGISTER_CLASS(RawDataPreprocessorProjective2D);
+    BOSS_REGISTER_CLASS(PointNormal2fUnprojectorPolar);
+    BOSS_REGISTER_CLASS(NormalComputator1DSlidingWindowNormal);
     // explicit CUDA names, for configurations that want to say so
     BOSS_REGISTER_CLASS_AS(CorrespondenceFinderProjective2f, "CorrespondenceFinderProjective2fCUDA");
     BOSS_REGISTER_CLASS_AS(AlignerSliceProcessorLaser2D, "AlignerSliceProcessorLaser2DCUDA");

@@ -98,6 +98,61 @@ namespace srrg2_core {
   };
   using PointNormal2fProjectorPolarPtr = std::shared_ptr<PointNormal2fProjectorPolar>;
 
+  // srrg2_core::LaserMessage, reduced to the fields RawDataPreprocessorProjective2D reads
+  // (R/sensor_processing/raw_data_preprocessor_projective_2d.cpp:78-86; built in tests/fixtures.hpp:25-35)
+  template <typename T>
+  struct MessageField {
+    T _v = T();
+    void setValue(const T& v) { _v = v; }
+    const T& value() const { return _v; }
+    T& value() { return _v; }
+  };
+  struct BaseSensorMessage {
+    explicit BaseSensorMessage(const std::string& topic_ = "") { topic.setValue(topic_); }
+    virtual ~BaseSensorMessage() {}
+    MessageField<std::string> topic;
+  };
+  using BaseSensorMessagePtr = std::shared_ptr<BaseSensorMessage>;
+  struct LaserMessage : public BaseSensorMessage {
+    using BaseSensorMessage::BaseSensorMessage;
+    MessageField<float> angle_min, angle_max, angle_increment, time_increment, scan_time, range_min, range_max;
+    MessageField<std::vector<float>> ranges, intensities;
+  };
+  using LaserMessagePtr = std::shared_ptr<LaserMessage>;
+
+  // parameter holder of PointNormal2fUnprojectorPolar (L0.json:405-434); the pre-processor overwrites its
+  // range / angle limits from every message (raw_data_preprocessor_projective_2d.cpp:98-102)
+  class PointNormal2fUnprojectorPolar : public Configurable {
+  public:
+    PARAM(PropertyFloat, angle_max, "end angle    [rad]", 3.14159f, 0);
+    PARAM(PropertyFloat, angle_min, "start angle  [rad]", -3.14159f, 0);
+    PARAM(PropertyUnsignedInt, canvas_cols, "cols of the canvas", 721, 0);
+    PARAM(PropertyUnsignedInt, canvas_rows, "rows of the canvas", 1, 0);
+    PARAM(PropertyInt, normal_min_points, "minimum number of points in ball when computing a valid normal", 5, 0);
+    PARAM(PropertyFloat, normal_point_distance, "range of points considered while computing normal", 0.2f, 0);
+    PARAM(PropertyInt, num_ranges, "number of laser beams", 721, 0);
+    PARAM(PropertyFloat, range_max, "max laser range [m]", 20.f, 0);
+    PARAM(PropertyFloat, range_min, "min laser range [m]", 0.3f, 0);
+    PointNormal2fUnprojectorPolar() { _class_name = "PointNormal2fUnprojectorPolar"; }
+    // sensor matrix [[fx, cx], [0, 0]] (.cpp:89-90)
+    void setCameraMatrix(float fx, float cx) { _fx = fx, _cx = cx; }
+    float fx() const { return _fx; }
+    float cx() const { return _cx; }
+
+  protected:
+    float _fx = 1.f, _cx = 0.f;
+  };
+  using PointNormal2fUnprojectorPolarPtr = std::shared_ptr<PointNormal2fUnprojectorPolar>;
+
+  // parameter holder of NormalComputator1DSlidingWindow<PointNormal2fVectorCloud, 1> (L0.json:711-719)
+  class NormalComputator1DSlidingWindowNormal : public Configurable {
+  public:
+    PARAM(PropertyInt, normal_min_points, "min number of points to compute a normal", 5, 0);
+    PARAM(PropertyFloat, normal_point_distance, "max normal point distance", 0.3f, 0);
+    NormalComputator1DSlidingWindowNormal() { _class_name = "NormalComputator1DSlidingWindowNormal"; }
+  };
+  using NormalComputator1DSlidingWindowNormalPtr = std::shared_ptr<NormalComputator1DSlidingWindowNormal>;
+
 }  // namespace srrg2_core
 
 namespace srrg2_solver {
@@ -436,6 +491,41 @@ namespace srrg2_laser_slam_2d {
     Ls2dDevice _device;
   };
   using MergerProjective2DPtr = std::shared_ptr<MergerProjective2D>;
+
+  // R/sensor_processing/raw_data_preprocessor_projective_2d.{h,cpp}: LaserMessage -> PointNormal2fVectorCloud on
+  // the device (unprojection, sliding-window normals, voxelisation).  Driven as tests/test_measurement_adaptor.cpp:12-33.
+  class RawDataPreprocessorProjective2D : public Configurable {
+  public:
+    enum Status { Error = 0, Ready = 1 };
+    using MeasurementType      = PointNormal2fVectorCloud;
+    using NormalComputatorType = NormalComputator1DSlidingWindowNormal;
+    PARAM(PropertyConfigurable_<PointNormal2fUnprojectorPolar>, unprojector,
+          "un-projector used to compute the scan from the cloud",
+          PointNormal2fUnprojectorPolarPtr(new PointNormal2fUnprojectorPolar), 0);
+    PARAM(PropertyConfigurable_<NormalComputatorType>, normal_computator_sliding, "normal computator object",
+          NormalComputator1DSlidingWindowNormalPtr(new NormalComputator1DSlidingWindowNormal), 0);
+    PARAM(PropertyFloat, range_min, "range_min [meters]", 0.f, 0);
+    PARAM(PropertyFloat, range_max, "range_max [meters]", 1000.f, 0);
+    PARAM(PropertyFloat, voxelize_resolution, "unproject voxelization resolution", 0.02f, 0);
+    PARAM(PropertyString, scan_topic, "topic of the scan", "/scan", 0);
+    RawDataPreprocessorProjective2D() { _class_name = "RawDataPreprocessorProjective2D"; }
+    void setMeas(MeasurementType* meas) { _meas = meas; }
+    bool setRawData(BaseSensorMessagePtr msg);
+    void compute();
+    Status status() const { return _status; }
+    // the record handed to the C ABI for the current message (public for tests)
+    void fillScanParams(ls2d_scan_params& sp) const;
+
+  protected:
+    void _processLaserMessage(LaserMessagePtr message);
+    MeasurementType* _meas = nullptr;
+    BaseSensorMessagePtr _raw_data;
+    LaserMessagePtr _laser;
+    std::vector<float>* _ranges = nullptr;
+    Status _status              = Error;
+    Ls2dDevice _device;
+  };
+  using RawDataPreprocessorProjective2DPtr = std::shared_ptr<RawDataPreprocessorProjective2D>;
 
   // ELF-constructor registration, like R/instances.h:14
   void srrg2_laser_slam_2d_registerTypes() __attribute__((constructor));

@@ -4,6 +4,8 @@
 //   plugin_test align <config> <aligner> <in.bin> <out.bin>     (GPU) single-pair compute(), computeBatch(), finder
 //   plugin_test verify <config> <detector> <in.bin> <out.bin>   (GPU) loop-closure candidate verification
 //   plugin_test multi <config> <aligner> <in.bin> <out.bin>     (GPU) two laser slices + odometry prior, compute()
+//   plugin_test scan <voxel_res> <in.bin> <out.bin>             (GPU) RawDataPreprocessorProjective2D; <in.bin>: int32
+//                                                 n_scans, n_beams; float angle_min, angle_max; float ranges[]
 // Binary layout of <in.bin>: int32 n_pairs, int32 n_guess, float sensor_in_robot[3]; then per pair:
 //   int32 n_fixed, n_moving; float fixed[n_fixed*4]; float moving[n_moving*4]; float init[n_guess*3].
 #include <cstdio>
@@ -61,7 +63,8 @@ static int selftest() {
   for (const char* c : {"CorrespondenceFinderProjective2f", "AlignerSliceProcessorLaser2D",
                         "AlignerSliceProcessorLaser2DWithSensor", "MultiAligner2D", "PointNormal2fProjectorPolar",
                         "RobustifierCauchy", "IterationAlgorithmGN", "Solver", "MultiLoopDetectorBruteForce2D",
-                        "SceneClipperProjective2D", "MergerProjective2D"})
+                        "SceneClipperProjective2D", "MergerProjective2D", "RawDataPreprocessorProjective2D",
+                        "PointNormal2fUnprojectorPolar", "NormalComputator1DSlidingWindowNormal"})
     REQUIRE(ClassRegistry::instance().has(c));
 
   ConfigurableManager m;
@@ -135,6 +138,27 @@ static int selftest() {
                                                                "\"RobustifierCauchy\" { \"#id\" : 2 }"); })
             .find("wrong class") != std::string::npos);
 
+  // RawDataPreprocessorProjective2D: the reference's error behaviour (raw_data_preprocessor_projective_2d.cpp:14-21,54-69)
+  RawDataPreprocessorProjective2D adaptor;
+  REQUIRE(adaptor.param_normal_computator_sliding.value() && adaptor.param_unprojector.value());  // test_measurement_adaptor.cpp:13-14
+  REQUIRE(adaptor.param_voxelize_resolution.value() == 0.02f && adaptor.param_scan_topic.value() == "/scan");
+  REQUIRE(thrown([&] { adaptor.setRawData(nullptr); }) ==
+          "RawDataPreprocessorProjective2D::setMeasurement|measurement is not set");
+  LaserMessagePtr other(new LaserMessage("/other_scan"));
+  REQUIRE(!adaptor.setRawData(other) && adaptor.status() == RawDataPreprocessorProjective2D::Error);
+  adaptor.compute();  // no measurement cloud set: status Error, no throw
+  REQUIRE(adaptor.status() == RawDataPreprocessorProjective2D::Error);
+  LaserMessagePtr scan(new LaserMessage("/scan"));
+  scan->angle_min.setValue(-1.f), scan->angle_max.setValue(1.f), scan->range_min.setValue(0.f), scan->range_max.setValue(30.f);
+  scan->ranges.setValue(std::vector<float>(100, 1.f));
+  REQUIRE(adaptor.setRawData(scan) && adaptor.status() == RawDataPreprocessorProjective2D::Ready);
+  REQUIRE(adaptor.param_unprojector->param_range_max.value() == 30.f);  // the tighter of message and PARAM (.cpp:83)
+  REQUIRE(std::fabs(adaptor.param_unprojector->fx() - 50.f) < 1e-3f && adaptor.param_unprojector->cx() == 50.f);  // .cpp:89-90
+  adaptor.param_unprojector.setValue(nullptr);
+  PointNormal2fVectorCloud meas;
+  adaptor.setMeas(&meas);
+  REQUIRE(thrown([&] { adaptor.compute(); }) == "RawDataPreprocessorProjective2D::compute| missing unprojector");
+
   // geometry helpers agree with their definition
   const Isometry2f T = geometry2d::v2t(Vector3f(1.f, -2.f, 0.5f));
   const Vector3f back = geometry2d::t2v(T * T.inverse());
@@ -195,6 +219,18 @@ static int parse(const std::string& file) {
                 first ? "" : ", ", d->name().c_str(), d->param_relocalize_min_inliers.value(),
                 d->param_relocalize_max_chi_inliers.value(), d->param_relocalize_min_inliers_ratio.value(),
                 d->param_relocalize_aligner.value() ? m.idOf(d->param_relocalize_aligner.value().get()) : -1);
+    first = false;
+  }
+  std::printf("], \"preprocessors\": [");
+  first = true;
+  for (auto& r : m.getAll<RawDataPreprocessorProjective2D>()) {
+    ls2d_scan_params sp;
+    r->fillScanParams(sp);
+    std::printf("%s{\"name\": \"%s\", \"scan_topic\": \"%s\", \"voxelize_resolution\": %.4f, \"range_min\": %.4f, "
+                "\"range_max\": %.4f, \"normal_point_distance\": %.4f, \"normal_min_points\": %d, \"num_ranges\": %d}",
+                first ? "" : ", ", r->name().c_str(), r->param_scan_topic.value().c_str(), sp.voxelize_resolution,
+                sp.range_min, sp.range_max, sp.normal_point_distance, sp.normal_min_points,
+                r->param_unprojector.value() ? r->param_unprojector->param_num_ranges.value() : -1);
     first = false;
   }
   std::printf("], \"finders\": %zu, \"projectors\": %zu}\n", m.getAll<CorrespondenceFinderProjective2f>().size(),
@@ -455,6 +491,33 @@ static int map(int cols, const std::string& in, const std::string& out) {
   return 0;
 }
 
+// (GPU) the reference's adaptor call sequence (tests/test_measurement_adaptor.cpp:12-33) for every scan of the file
+static int scan(float voxel_res, const std::string& in, const std::string& out) {
+  std::ifstream is(in, std::ios::binary);
+  if (!is.good()) throw std::runtime_error("cannot open " + in);
+  int32_t n_scans = 0, n_beams = 0;
+  float amin = 0.f, amax = 0.f;
+  is.read((char*) &n_scans, 4), is.read((char*) &n_beams, 4), is.read((char*) &amin, 4), is.read((char*) &amax, 4);
+  RawDataPreprocessorProjective2D adaptor;
+  adaptor.param_voxelize_resolution.setValue(voxel_res);
+  std::ofstream os(out, std::ios::binary);
+  for (int s = 0; s < n_scans; ++s) {
+    LaserMessagePtr msg(new LaserMessage("/scan"));
+    msg->angle_min.setValue(amin), msg->angle_max.setValue(amax);
+    msg->range_min.setValue(0.f), msg->range_max.setValue(30.f);
+    msg->ranges.value().resize((size_t) n_beams);
+    is.read((char*) msg->ranges.value().data(), (std::streamsize)(sizeof(float) * (size_t) n_beams));
+    PointNormal2fVectorCloud points;
+    adaptor.setMeas(&points);
+    if (!adaptor.setRawData(msg)) return 1;
+    adaptor.compute();
+    if (adaptor.status() != RawDataPreprocessorProjective2D::Ready) return 1;
+    writeCloud(os, points);
+  }
+  std::printf("SCAN OK %d\n", n_scans);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   try {
     const std::string cmd = argc > 1 ? argv[1] : "";
@@ -464,6 +527,7 @@ int main(int argc, char** argv) {
     if (cmd == "verify" && argc == 6) return verify(argv[2], argv[3], argv[4], argv[5]);
     if (cmd == "multi" && argc == 6) return multi(argv[2], argv[3], argv[4], argv[5]);
     if (cmd == "map" && argc == 5) return map(std::atoi(argv[2]), argv[3], argv[4]);
+    if (cmd == "scan" && argc == 5) return scan((float) std::atof(argv[2]), argv[3], argv[4]);
     std::fprintf(stderr, "usage: plugin_test selftest | parse <config> | align|verify <config> <name> <in> <out>\n");
     return 2;
   } catch (const std::exception& e) {

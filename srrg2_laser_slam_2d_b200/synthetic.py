@@ -202,6 +202,53 @@ def make_scan_pairs(n_pairs: int, n_beams: int = HOKUYO_BEAMS, seed: int = 0xC0F
                      delta.astype(np.float32), init.astype(np.float32))
 
 
+@dataclass
+class RawScanPairs:
+    """Raw LaserMessage-shaped input: ranges of the scan at pose P (fixed) and at pose P*delta (moving)."""
+
+    fixed_ranges: np.ndarray   # [n_pairs, n_beams] float32; no-return / dropped beams read `no_return`
+    moving_ranges: np.ndarray  # [n_pairs, n_beams] float32
+    angle_min: float           # LaserMessage::angle_min / angle_max for the symmetric sensor matrix [1/res, n/2]
+    angle_max: float
+    gt_xyt: np.ndarray         # [n_pairs, 3] float32 ground-truth moving_in_fixed
+    init_xyt: np.ndarray       # [n_pairs, 3] float32
+
+
+def make_raw_scans(n_pairs: int, n_beams: int = HOKUYO_BEAMS, seed: int = 0xC0FFEE, fov: float = HOKUYO_FOV,
+                   motion_xy: float = 0.05, motion_theta: float = 0.05, range_noise: float = 0.01,
+                   dropout: float = 0.02, range_max: float = 20.0, no_return: float = 65.0,
+                   device: str = "cpu", chunk: int = 128) -> RawScanPairs:
+    """The same worlds / poses / noise model as make_scan_pairs, but stopping at the sensor: float32 ranges, the
+    input of RawDataPreprocessorProjective2D.  Beam c looks along (c - n/2) * fov / n, the direction the
+    reference's sensor matrix assigns to it (raw_data_preprocessor_projective_2d.cpp:87-90)."""
+    rng = np.random.default_rng(seed)
+    segs_np, circ_np = _make_worlds(rng, n_pairs)
+    P = np.stack([rng.uniform(-1.0, 1.0, n_pairs), rng.uniform(-1.0, 1.0, n_pairs),
+                  rng.uniform(-math.pi, math.pi, n_pairs)], -1)
+    delta = np.stack([rng.uniform(-motion_xy, motion_xy, n_pairs),
+                      rng.uniform(-motion_xy, motion_xy, n_pairs),
+                      rng.uniform(-motion_theta, motion_theta, n_pairs)], -1)
+    Pm = _t2v(_v2t(P) @ _v2t(delta))
+    noise = rng.normal(0.0, range_noise, (2, n_pairs, n_beams))
+    drop = rng.uniform(0.0, 1.0, (2, n_pairs, n_beams)) < dropout
+    beam = (np.arange(n_beams) - 0.5 * n_beams) * (fov / n_beams)
+    dev = torch.device(device)
+    beam_t = torch.from_numpy(beam).to(dev)
+    out = np.empty((2, n_pairs, n_beams), np.float32)
+    for lo in range(0, n_pairs, chunk):
+        hi = min(n_pairs, lo + chunk)
+        segs = torch.from_numpy(segs_np[lo:hi]).to(dev)
+        circ = torch.from_numpy(circ_np[lo:hi]).to(dev)
+        for which, poses in ((0, P), (1, Pm)):
+            r = _raycast(torch.from_numpy(poses[lo:hi]).to(dev), beam_t, segs, circ)
+            r = r + torch.from_numpy(noise[which, lo:hi]).to(dev)
+            bad = ~torch.isfinite(r) | (r <= 0.05) | (r >= range_max) | torch.from_numpy(drop[which, lo:hi]).to(dev)
+            r = torch.where(bad, torch.full_like(r, no_return), r)
+            out[which, lo:hi] = r.to(torch.float32).cpu().numpy()
+    return RawScanPairs(out[0], out[1], -0.5 * fov, 0.5 * fov, delta.astype(np.float32),
+                        np.zeros_like(delta, dtype=np.float32))
+
+
 def reference_demo_scene(n_points: int = 1024) -> np.ndarray:
     """The deterministic world of apps/synthetic_scene_generator.cpp:36-56: a circle (r = 3.5 m,
     2*n_points points) plus a 2 m + 3 m corner placed at (2, 0, pi/4).  The reference leaves the

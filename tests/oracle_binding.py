@@ -25,6 +25,13 @@ class OrcPrior(C.Structure):
     _fields_ = [("z", C.c_float * 3), ("information", C.c_float * 6), ("cauchy_chi_threshold", C.c_float)]
 
 
+class OrcScanParams(C.Structure):
+    _fields_ = [("angle_min", C.c_float), ("angle_max", C.c_float), ("msg_range_min", C.c_float),
+                ("msg_range_max", C.c_float), ("range_min", C.c_float), ("range_max", C.c_float),
+                ("voxelize_resolution", C.c_float), ("normal_point_distance", C.c_float),
+                ("normal_min_points", C.c_int32)]
+
+
 class OrcIso(C.Structure):
     _fields_ = [("tx", C.c_float), ("ty", C.c_float), ("c", C.c_float), ("s", C.c_float)]
 
@@ -80,6 +87,9 @@ def lib():
         L.orc_clip_scene.argtypes, L.orc_clip_scene.restype = [C.POINTER(OrcParams), vp, i32, OrcIso, OrcIso, vp], i32
         L.orc_merge.argtypes = [C.POINTER(OrcParams), f32, vp, i32, vp, i32, OrcIso, vp]
         L.orc_merge.restype = i32
+        L.orc_default_scan_params.argtypes = [C.POINTER(OrcScanParams)]
+        L.orc_preprocess_scan.argtypes, L.orc_preprocess_scan.restype = [C.POINTER(OrcScanParams), vp, i32, vp], i32
+        L.orc_preprocess_scans.argtypes = [C.POINTER(OrcScanParams), vp, i32, i32, i32, vp, vp]
         L.orc_libm_atan2f_n.argtypes = [vp, vp, vp, C.c_long]
         L.orc_libm_sincosf_n.argtypes = [vp, vp, vp, C.c_long]
         L.orc_column_n.argtypes = [C.POINTER(OrcParams), vp, vp, vp, C.c_long]
@@ -261,3 +271,29 @@ def merge(prm: OrcParams, merge_threshold: float, scene: np.ndarray, measurement
     n = lib().orc_merge(C.byref(prm), merge_threshold, _ptr(buf), len(scene), _ptr(measurement), len(measurement),
                         v2t(*measurement_in_scene_xyt), _ptr(counters))
     return buf[:n].copy(), counters
+
+
+def default_scan_params(**kw) -> OrcScanParams:
+    p = OrcScanParams()
+    lib().orc_default_scan_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def preprocess_scan(sp: OrcScanParams, ranges: np.ndarray) -> np.ndarray:
+    """RawDataPreprocessorProjective2D::compute for one LaserMessage: returns the cloud [k, 4]."""
+    ranges = _f32(ranges)
+    out = np.zeros((max(len(ranges), 1), 4), np.float32)
+    k = lib().orc_preprocess_scan(C.byref(sp), _ptr(ranges), len(ranges), _ptr(out))
+    return out[:k].copy()
+
+
+def preprocess_scans(sp: OrcScanParams, ranges: np.ndarray, n_threads=1):
+    """batch of scans [n_scans, n_beams]: returns (points [n_scans, n_beams, 4], counts [n_scans])."""
+    ranges = _f32(ranges)
+    n_scans, n_beams = ranges.shape
+    out = np.zeros((n_scans, n_beams, 4), np.float32)
+    counts = np.zeros(n_scans, np.int32)
+    lib().orc_preprocess_scans(C.byref(sp), _ptr(ranges), n_beams, n_scans, n_threads, _ptr(out), _ptr(counts))
+    return out, counts

@@ -1,0 +1,94 @@
+"""GPU parity of the raw-scan pre-processor (RawDataPreprocessorProjective2D,
+R/sensor_processing/raw_data_preprocessor_projective_2d.cpp) through the C ABI: bit-exact against the oracle."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from srrg2_laser_slam_2d_b200 import default_params
+from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING, default_scan_params
+from srrg2_laser_slam_2d_b200.synthetic import make_raw_scans
+
+pytestmark = pytest.mark.gpu
+
+
+def both_params(oracle, **kw):
+    return default_scan_params(**kw), oracle.default_scan_params(**kw)
+
+
+def check(h, oracle, kw, ranges):
+    sp, osp = both_params(oracle, **kw)
+    got, cnt = h.preprocess_scans(sp, ranges)
+    ref, rcnt = oracle.preprocess_scans(osp, ranges, n_threads=4)
+    assert np.array_equal(cnt, rcnt)
+    for s in range(len(ranges)):
+        assert np.array_equal(gu.bits(got[s, :cnt[s]]), gu.bits(ref[s, :cnt[s]])), s
+    return cnt
+
+
+def test_reference_synthetic_fixture(handle_factory, oracle):
+    # /root/reference/srrg2_laser_slam_2d/tests/fixtures.hpp:38-47 + test_measurement_adaptor.cpp:36 -> 100 points
+    h = handle_factory(default_params())
+    kw = dict(angle_min=-1.0, angle_max=1.0, msg_range_min=0.0, msg_range_max=1000.0, range_min=0.0,
+              range_max=1000.0, voxelize_resolution=0.01)
+    cnt = check(h, oracle, kw, np.full((1, 100), 1.0, np.float32))
+    assert cnt[0] == 100
+
+
+@pytest.mark.parametrize("n_beams,res", [(1081, 0.02), (1081, 0.0), (721, 0.02), (721, 0.05), (360, 0.0), (2048, 0.1)])
+def test_preprocess_bit_exact(handle_factory, oracle, n_beams, res):
+    raw = make_raw_scans(24, n_beams=n_beams, seed=91 + n_beams)
+    h = handle_factory(default_params())
+    kw = dict(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=res)
+    cnt = check(h, oracle, kw, np.concatenate([raw.fixed_ranges, raw.moving_ranges]))
+    assert cnt.min() > 20 and cnt.max() <= n_beams
+
+
+def test_preprocess_edge_cases(handle_factory, oracle):
+    h = handle_factory(default_params())
+    rng = np.random.default_rng(3)
+    n = 300
+    ranges = np.stack([
+        np.full(n, 65.0, np.float32),                                   # nothing in range
+        np.full(n, 25.0, np.float32),                                   # too sparse for any normal
+        np.where(np.arange(n) % 7 == 0, 2.0, 65.0).astype(np.float32),  # isolated beams
+        np.full(n, 0.0, np.float32),                                    # all points at the origin (range_min 0 accepts them)
+        rng.uniform(0.5, 0.6, n).astype(np.float32),
+        np.full(n, 1.0, np.float32),
+    ])
+    kw = dict(angle_min=-2.0, angle_max=2.0)
+    cnt = check(h, oracle, kw, ranges)
+    assert cnt[0] == 0 and cnt[1] == 0 and cnt[2] == 0
+    check(h, oracle, dict(kw, voxelize_resolution=0.0), ranges)
+    check(h, oracle, dict(kw, normal_min_points=1, voxelize_resolution=0.3), ranges)
+    got, c0 = h.preprocess_scans(default_scan_params(), np.zeros((0, 64), np.float32))
+    assert len(c0) == 0
+
+
+def test_raw_scans_to_resident_set_and_align(handle_factory, oracle):
+    """raw ranges -> resident cloud sets -> aligner: same result as aligning the oracle's pre-processed clouds"""
+    raw = make_raw_scans(16, n_beams=1081, seed=7)
+    kw = dict(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=0.0)
+    sp, osp = both_params(oracle, **kw)
+    akw = dict(canvas_cols=1081, normal_cos=0.9, max_iterations=10)
+    h = handle_factory(default_params(**akw))
+    h.preprocess_scans_to_set(LS2D_FIXED, sp, raw.fixed_ranges)
+    h.preprocess_scans_to_set(LS2D_MOVING, sp, raw.moving_ranges)
+    fpts, foff = h.download_clouds(LS2D_FIXED, 16, 16 * 1081)
+    rf, cf = oracle.preprocess_scans(osp, raw.fixed_ranges)
+    rm, cm = oracle.preprocess_scans(osp, raw.moving_ranges)
+    assert np.array_equal(np.diff(foff), cf)
+    ref_f = np.concatenate([rf[s, :cf[s]] for s in range(16)])
+    ref_m = np.concatenate([rm[s, :cm[s]] for s in range(16)])
+    assert np.array_equal(gu.bits(fpts), gu.bits(ref_f))
+    got = h.align_batch(raw.init_xyt)
+    from srrg2_laser_slam_2d_b200._abi import reduction_threads
+    off_f = np.concatenate([[0], np.cumsum(cf)]).astype(np.int32)
+    off_m = np.concatenate([[0], np.cumsum(cm)]).astype(np.int32)
+    ref, _ = oracle.align_batch(oracle.default_params(**akw), ref_f, off_f, ref_m, off_m, raw.init_xyt,
+                                sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1081))
+    for f in ("status", "n_corr", "n_inliers", "n_kernelized"):
+        assert np.array_equal(got[f], ref[f]), f
+    for f in ("x", "y", "theta", "chi_inliers"):
+        assert np.array_equal(gu.bits(got[f]), gu.bits(ref[f])), f
+    err = np.abs(np.stack([got["x"], got["y"], got["theta"]], 1) - raw.gt_xyt).max()
+    assert err < 0.02

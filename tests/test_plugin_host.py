@@ -62,6 +62,10 @@ def test_reference_configurations_load_unchanged(exe):
             tr["with_sensor"], tr["slices"]) == (10, 0.5, 0.9, 0.01, 1, 2)
     assert (tr["range_min"], tr["range_max"], tr["damping"]) == (0.3, 20.0, 0.0)
     assert d["loop_detectors"][0]["min_inliers"] == 300 and d["loop_detectors"][0]["aligner"] == ld["id"]
+    pre = {x["name"]: x for x in d["preprocessors"]}          # RawDataPreprocessorProjective2D, L0.json:781-806
+    assert pre["ad_scan_0"] == {"name": "ad_scan_0", "scan_topic": "/diago_0/scan_0_0", "voxelize_resolution": 0.02,
+                                "range_min": 0.0, "range_max": 1000.0, "normal_point_distance": 0.3,
+                                "normal_min_points": 5, "num_ranges": 721}
     m = json.loads(run(exe, "parse", os.path.join(REF_CONFIGS, "stage_segway_double_config_MULTI.json")))
     assert m["objects"] == 56
     am = {x["name"]: x for x in m["aligners"]}
@@ -295,3 +299,28 @@ def test_plugin_multi_slice_aligner_with_odometry_prior(exe, tmp_path, handle_fa
     # the bound prior changes the answer and is one more inlier factor
     assert not np.array_equal(got[:, 0]["rec"]["x"], got[:, 1]["rec"]["x"])
     assert np.array_equal(got[:, 0]["rec"]["n_inliers"] + got[:, 0]["rec"]["n_kernelized"], got[:, 0]["rec"]["n_corr"] + 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res", [0.02, 0.0])
+def test_plugin_raw_data_preprocessor_matches_the_oracle(exe, tmp_path, oracle, res):
+    """RawDataPreprocessorProjective2D through the plugin class (the reference's call sequence,
+    tests/test_measurement_adaptor.cpp:12-33) vs the oracle, bit for bit; plus the reference's own fixture count."""
+    from srrg2_laser_slam_2d_b200.synthetic import make_raw_scans
+    raw = make_raw_scans(3, n_beams=721, seed=17)
+    scans = [raw.fixed_ranges[0], raw.moving_ranges[1], raw.fixed_ranges[2]]
+    inp, out = str(tmp_path / "scan.bin"), str(tmp_path / "scan_out.bin")
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<iiff", len(scans), 721, raw.angle_min, raw.angle_max))
+        for r in scans:
+            f.write(np.ascontiguousarray(r, np.float32).tobytes())
+    assert "SCAN OK" in run(exe, "scan", str(res), inp, out)
+    blob = open(out, "rb").read()
+    pos = 0
+    osp = oracle.default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=res)
+    for r in scans:
+        k = struct.unpack_from("<i", blob, pos)[0]
+        c = np.frombuffer(blob, np.float32, 4 * k, pos + 4).reshape(k, 4)
+        pos += 4 + 16 * k
+        ref = oracle.preprocess_scan(osp, r)
+        assert c.shape == ref.shape and k > 50 and np.array_equal(c.view(np.uint32), ref.view(np.uint32))
