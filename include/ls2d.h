@@ -289,6 +289,21 @@ int ls2d_preprocess_scans_to_set_dev(ls2d_handle* h, int which, const ls2d_scan_
 int ls2d_download_clouds(ls2d_handle* h, int which, float* points, int32_t* offsets, int32_t n_clouds,
                          int64_t capacity_points);
 
+/* device-resident clipper: same clip as ls2d_clip_scenes, but the clipped clouds become cloud set `out_set`
+ * (packed CSR, out_set != scene_set) without leaving the device -- the tracker's moving clouds */
+int ls2d_clip_scenes_to_set(ls2d_handle* h, int scene_set, const int32_t* cloud_ids,
+                            const float* robot_in_local_map_xyt, const float* sensor_in_robot_xyt, int32_t n,
+                            int out_set);
+/* replaces: one MultiTracker2D frame step, preprocessRawData -> clip -> align
+ * (apps/visual_test_tracker_2d.cpp:167-179), batched over n frames.  Frame f: ranges[f] is
+ * pre-processed into the measurement cloud (fixed), local map scene_ids[f] of resident set `scene_set` (>= 2) is
+ * clipped from robot_in_local_map[f] * sensor_in_robot (sensor_in_robot = the handle's params when with_sensor,
+ * else identity) into the moving cloud, and the aligner runs from init_xyt[f] (NULL: identity).  Only 4 B/beam,
+ * ids and poses go to the device, 64 B/frame come back.  Overwrites sets LS2D_FIXED and LS2D_MOVING. */
+int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges, int32_t n_beams, int32_t n,
+                     int scene_set, const int32_t* scene_ids, const float* robot_in_local_map_xyt,
+                     const float* init_xyt, ls2d_result* out);
+
 /* ---- introspection ---------------------------------------------------------------------------------*/
 /* threads per pair the fused kernel uses for clouds of up to max_points points: fixes the shape of its
  * H/b reduction tree (the oracle's ORC_SUM_TREE mode mirrors it) */

@@ -79,6 +79,7 @@ EXPORTS = [
     "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev", "ls2d_align_multi", "ls2d_align_multi_dev",
     "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
     "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
+    "ls2d_clip_scenes_to_set", "ls2d_track_batch",
 ]
 
 _lib = None
@@ -128,6 +129,8 @@ def load():
     L.ls2d_preprocess_scans_to_set.argtypes = [vp, C.c_int, SP, vp, i32, i32]
     L.ls2d_preprocess_scans_to_set_dev.argtypes = [vp, C.c_int, SP, vp, i32, i32]
     L.ls2d_download_clouds.argtypes = [vp, C.c_int, vp, vp, i32, i64]
+    L.ls2d_clip_scenes_to_set.argtypes = [vp, C.c_int, vp, vp, vp, i32, C.c_int]
+    L.ls2d_track_batch.argtypes = [vp, SP, vp, i32, i32, C.c_int, vp, vp, vp, vp]
     L.ls2d_reduction_threads.argtypes = [i32]
     L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
     _lib = L
@@ -373,6 +376,28 @@ class Handle:
         off = np.zeros(n_clouds + 1, np.int32)
         self._check(self._L.ls2d_download_clouds(self._h, which, _ptr(pts), _ptr(off), n_clouds, capacity_points))
         return pts[:off[-1]].copy(), off
+
+    def clip_scenes_to_set(self, scene_set: int, cloud_ids, robot_in_local_map_xyt, sensor_in_robot_xyt, out_set: int):
+        ids = _i32(cloud_ids)
+        rob = _f32(robot_in_local_map_xyt).reshape(-1, 3)
+        sen = _f32(sensor_in_robot_xyt)
+        self._check(self._L.ls2d_clip_scenes_to_set(self._h, scene_set, _ptr(ids), _ptr(rob), _ptr(sen), len(ids),
+                                                    out_set))
+        self.sync()
+
+    def track_batch(self, sp: ScanParams, ranges, scene_set: int, scene_ids, robot_in_local_map_xyt, init_xyt=None,
+                    out=None):
+        """MultiTracker2D frame step (pre-process -> clip -> align) for a batch of frames, from host buffers."""
+        ranges = _f32(ranges)
+        n, n_beams = ranges.shape
+        ids = _i32(scene_ids)
+        rob = _f32(robot_in_local_map_xyt).reshape(-1, 3)
+        init = None if init_xyt is None else _f32(init_xyt).reshape(-1, 3)
+        if out is None:
+            out = np.zeros(n, RESULT_DTYPE)
+        self._check(self._L.ls2d_track_batch(self._h, C.byref(sp), _ptr(ranges), n_beams, n, scene_set, _ptr(ids),
+                                             _ptr(rob), _ptr(init), _ptr(out)))
+        return out
 
     # ---- loop-closure verification
     def verify(self, query_id: int, candidate_ids, guesses_xyt, gates: Gates, candidate_base: int = 0,

@@ -42,7 +42,7 @@ struct ls2d_handle {
   ls2d_params prm;
   dev_params dp;
   cloud_set sets[LS2D_MAX_CLOUD_SETS];
-  scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior, d_ranges;
+  scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior, d_ranges, d_clip;
   int64_t launches = 0;
   int variant      = 0;  // LS2D_ICP_VARIANT: tuning knob for the 1081-point kernel shape
   // NCCL, resolved lazily
@@ -313,6 +313,7 @@ int ls2d_destroy(ls2d_handle* h) {
   release(h->d_best);
   release(h->d_misc);
   release(h->d_ranges);
+  release(h->d_clip);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->nccl_lib) dlclose(h->nccl_lib);
   delete h;
@@ -916,17 +917,14 @@ int ls2d_preprocess_scans(ls2d_handle* h, const ls2d_scan_params* sp, const floa
   return LS2D_OK;
 }
 
-static int scans_to_set_impl(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges_dev,
-                             int32_t n_beams, int32_t n_scans) {
-  int rc;
-  const size_t n_pts = (size_t) n_scans * n_beams;
-  if ((rc = reserve(h->d_misc, sizeof(float4) * n_pts + sizeof(int) * (size_t) n_scans))) return rc;
-  float4* d_tmp = (float4*) h->d_misc.p;
-  int* d_cnt    = (int*) ((char*) h->d_misc.p + sizeof(float4) * n_pts);
-  cloud_set& c  = h->sets[which];
+// strided kernel output (rows of `stride` points + counts) -> owned, packed cloud set
+static int pack_into_set(ls2d_handle* h, int which, const float4* d_strided, const int* d_cnt, int32_t stride,
+                         int32_t n) {
+  cloud_set& c = h->sets[which];
   if (!c.owned) c = cloud_set();
   c.owned            = true;
-  const size_t n_off = (size_t) n_scans + 1;
+  const size_t n_pts = (size_t) n * stride;
+  const size_t n_off = (size_t) n + 1;
   if (n_pts > c.cap_pts || !c.pts) {
     if (c.pts) cudaFree(c.pts);
     c.pts     = nullptr;
@@ -941,19 +939,29 @@ static int scans_to_set_impl(ls2d_handle* h, int which, const ls2d_scan_params* 
     CU(cudaMalloc((void**) &c.off, (n_off + 16) * sizeof(int)));
     c.cap_off = n_off + 16;
   }
-  if (n_scans > 0) {
-    if ((rc = preprocess_dev(h, sp, ranges_dev, n_beams, n_scans, d_tmp, d_cnt))) return rc;
-    scan_offsets_kernel<<<1, 1024, 0, h->stream>>>(d_cnt, n_scans, c.off);
+  if (n > 0) {
+    scan_offsets_kernel<<<1, 1024, 0, h->stream>>>(d_cnt, n, c.off);
     CU(cudaGetLastError());
-    scan_pack_kernel<<<n_scans, 128, 0, h->stream>>>(d_tmp, c.off, n_beams, c.pts);
+    scan_pack_kernel<<<n, 128, 0, h->stream>>>(d_strided, c.off, stride, c.pts);
     CU(cudaGetLastError());
     h->launches += 2;
   } else {
     CU(cudaMemsetAsync(c.off, 0, sizeof(int), h->stream));
   }
-  c.n_clouds   = n_scans;
-  c.max_points = n_beams;  // upper bound: the counts stay on the device
+  c.n_clouds   = n;
+  c.max_points = stride;  // upper bound: the counts stay on the device
   return LS2D_OK;
+}
+
+static int scans_to_set_impl(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges_dev,
+                             int32_t n_beams, int32_t n_scans) {
+  int rc;
+  const size_t n_pts = (size_t) n_scans * n_beams;
+  if ((rc = reserve(h->d_misc, sizeof(float4) * n_pts + sizeof(int) * (size_t) n_scans))) return rc;
+  float4* d_tmp = (float4*) h->d_misc.p;
+  int* d_cnt    = (int*) ((char*) h->d_misc.p + sizeof(float4) * n_pts);
+  if (n_scans > 0 && (rc = preprocess_dev(h, sp, ranges_dev, n_beams, n_scans, d_tmp, d_cnt))) return rc;
+  return pack_into_set(h, which, d_tmp, d_cnt, n_beams, n_scans);
 }
 
 int ls2d_preprocess_scans_to_set(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges,
@@ -990,6 +998,72 @@ int ls2d_download_clouds(ls2d_handle* h, int which, float* points, int32_t* offs
     CU(cudaStreamSynchronize(h->stream));
   }
   return LS2D_OK;
+}
+
+// clip_kernel into scratch `tmp` (strided rows of canvas_cols points + counts); ids / poses already on the device
+static int clip_dev(ls2d_handle* h, const cloud_set& c, const int* ids_dev, const float* robot_dev,
+                    const float* sensor_xyt, int32_t n, scratch& tmp, float4** out, int** counts) {
+  const int C = h->dp.cam.cols;
+  int rc;
+  const size_t out_bytes = sizeof(float4) * (size_t) n * C;
+  if ((rc = reserve(tmp, out_bytes + sizeof(int) * (size_t) n))) return rc;
+  clip_args a;
+  a.pts       = c.pts;
+  a.off       = c.off;
+  a.cloud_ids = ids_dev;
+  a.robot_xyt = robot_dev;
+  memcpy(a.sensor_xyt, sensor_xyt, sizeof(float) * 3);
+  a.out    = (float4*) tmp.p;
+  a.counts = (int*) ((char*) tmp.p + out_bytes);
+  const size_t smem = sizeof(unsigned) * 2 * (size_t) C;
+  CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  clip_kernel<<<n, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  *out    = a.out;
+  *counts = a.counts;
+  return LS2D_OK;
+}
+
+int ls2d_clip_scenes_to_set(ls2d_handle* h, int scene_set, const int32_t* cloud_ids, const float* robot_xyt,
+                            const float* sensor_xyt, int32_t n, int out_set) {
+  if (!h || scene_set < 0 || scene_set >= LS2D_MAX_CLOUD_SETS || out_set < 0 || out_set >= LS2D_MAX_CLOUD_SETS ||
+      out_set == scene_set || !cloud_ids || !robot_xyt || !sensor_xyt || n < 0)
+    return LS2D_ERR_INVALID;
+  const cloud_set& c = h->sets[scene_set];
+  if (!c.pts || !c.off) return LS2D_ERR_NOT_READY;
+  for (int i = 0; i < n; ++i)
+    if (cloud_ids[i] < 0 || cloud_ids[i] >= c.n_clouds) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  float4* d_out = nullptr;
+  int* d_cnt    = nullptr;
+  if (n > 0) {
+    if ((rc = h2d(h, h->d_mid, cloud_ids, sizeof(int) * (size_t) n))) return rc;
+    if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * 3 * (size_t) n))) return rc;
+    if ((rc = clip_dev(h, c, (const int*) h->d_mid.p, (const float*) h->d_init.p, sensor_xyt, n, h->d_clip, &d_out, &d_cnt)))
+      return rc;
+  }
+  return pack_into_set(h, out_set, d_out, d_cnt, h->dp.cam.cols, n);
+}
+
+// MultiTracker2D's frame step, batched: raw scan -> measurement cloud (fixed), local map seen from the predicted
+// pose -> clipped scene in the robot frame (moving), MultiAligner2D; only ranges, ids and poses cross the bus.
+int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges, int32_t n_beams, int32_t n,
+                     int scene_set, const int32_t* scene_ids, const float* robot_xyt, const float* init_xyt,
+                     ls2d_result* out) {
+  if (!h || !sp || n < 0 || n_beams < 1 || scene_set < 2 || scene_set >= LS2D_MAX_CLOUD_SETS || !out ||
+      (n > 0 && (!ranges || !scene_ids || !robot_xyt)))
+    return LS2D_ERR_INVALID;
+  if (n == 0) return LS2D_OK;
+  int rc;
+  const float identity[3] = {0.f, 0.f, 0.f};
+  const float* sensor     = h->prm.with_sensor ? h->prm.sensor_in_robot : identity;
+  if ((rc = ls2d_preprocess_scans_to_set(h, LS2D_FIXED, sp, ranges, n_beams, n))) return rc;
+  if ((rc = ls2d_clip_scenes_to_set(h, scene_set, scene_ids, robot_xyt, sensor, n, LS2D_MOVING))) return rc;
+  if (init_xyt) return align_host_impl(h, nullptr, nullptr, init_xyt, n, out, nullptr, 0);
+  std::vector<float> zeros((size_t) n * 3, 0.f);
+  return align_host_impl(h, nullptr, nullptr, zeros.data(), n, out, nullptr, 0);
 }
 
 int ls2d_reduction_threads(int32_t max_points) {

@@ -92,3 +92,47 @@ def test_raw_scans_to_resident_set_and_align(handle_factory, oracle):
         assert np.array_equal(gu.bits(got[f]), gu.bits(ref[f])), f
     err = np.abs(np.stack([got["x"], got["y"], got["theta"]], 1) - raw.gt_xyt).max()
     assert err < 0.02
+
+
+@pytest.mark.parametrize("res,sensor", [(0.02, None), (0.0, (0.1, -0.05, 0.2))])
+def test_track_batch_matches_the_oracle_chain(handle_factory, oracle, res, sensor):
+    """ls2d_track_batch = pre-process -> clip -> align with only ranges / ids / poses crossing the bus: identical to the
+    oracle's RawDataPreprocessorProjective2D -> SceneClipperProjective2D -> MultiAligner2D chain."""
+    from srrg2_laser_slam_2d_b200._abi import reduction_threads
+    n, nb = 12, 1081
+    raw = make_raw_scans(n, n_beams=nb, seed=23)
+    kw = dict(angle_min=raw.angle_min, angle_max=raw.angle_max)
+    sp, osp = both_params(oracle, voxelize_resolution=res, **kw)
+    _, osp_map = both_params(oracle, voxelize_resolution=0.0, **kw)
+    akw = dict(canvas_cols=1081, normal_cos=0.9, max_iterations=10)
+    if sensor is not None:
+        akw.update(with_sensor=1, sensor_in_robot=sensor)
+    # local maps: the full-resolution cloud of the scan taken at P * delta, in that pose's frame
+    maps, cm = oracle.preprocess_scans(osp_map, raw.moving_ranges)
+    scenes = [maps[k, :cm[k]] for k in range(n)]
+    off = np.concatenate([[0], np.cumsum(cm)]).astype(np.int32)
+    rng = np.random.default_rng(1)
+    ids = rng.permutation(n).astype(np.int32)
+    robots = rng.uniform(-0.02, 0.02, (n, 3)).astype(np.float32)       # predicted robot_in_local_map
+    ranges = raw.fixed_ranges[ids]
+    h = handle_factory(default_params(**akw))
+    h.upload_clouds(2, np.concatenate(scenes), off)
+    got = h.track_batch(sp, ranges, 2, ids, robots)
+    prm = oracle.default_params(**akw)
+    sen = sensor if sensor is not None else (0.0, 0.0, 0.0)
+    fix, mov = [], []
+    for f in range(n):
+        fix.append(oracle.preprocess_scan(osp, ranges[f]))
+        mov.append(oracle.clip_scene(prm, scenes[ids[f]], robots[f], sen))
+    foff = np.concatenate([[0], np.cumsum([len(c) for c in fix])]).astype(np.int32)
+    moff = np.concatenate([[0], np.cumsum([len(c) for c in mov])]).astype(np.int32)
+    mpts, moff_dev = h.download_clouds(LS2D_MOVING, n, n * 1081)
+    assert np.array_equal(moff_dev, moff) and np.array_equal(gu.bits(mpts), gu.bits(np.concatenate(mov)))
+    # the sets are sized by their upper bound (n_beams / canvas_cols): that fixes the kernel's reduction shape
+    ref, _ = oracle.align_batch(prm, np.concatenate(fix), foff, np.concatenate(mov), moff, np.zeros((n, 3), np.float32),
+                                sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1081))
+    for f in ("status", "n_corr", "n_inliers", "n_kernelized"):
+        assert np.array_equal(got[f], ref[f]), f
+    for f in ("x", "y", "theta", "chi_inliers"):
+        assert np.array_equal(gu.bits(got[f]), gu.bits(ref[f])), f
+    assert (got["status"] == 0).all()
