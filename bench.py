@@ -20,6 +20,7 @@ over +-3.14159 rad.  A "step" is one pass of the hot path over the whole batch.
 N > 1 (torchrun): one process per GPU, every rank aligns its own 4096-pair batch (independent pairs, no
 data-path collective: weak scaling); time = max over ranks.   --impl reference times the oracle only.
 --workload verify runs the sharded loop-closure verification (config 4 shape) instead.
+--workload track times the tracker's frame step from RAW scans (ls2d_track_batch: pre-process -> clip -> align).
 """
 from __future__ import annotations
 
@@ -374,17 +375,72 @@ def run_verify(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- tracker step
+def run_track(args):
+    """The tracker's frame step with raw scans as the wire format: per frame 1081 ranges
+    (4.3 KB) + a local-map id + the predicted pose go to the device, 64 B come back; the local maps are resident."""
+    import torch
+
+    from srrg2_laser_slam_2d_b200 import Handle, default_params
+    from srrg2_laser_slam_2d_b200._abi import RESULT_DTYPE, default_scan_params
+    from srrg2_laser_slam_2d_b200.synthetic import make_raw_scans
+
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    n = args.pairs
+    raw = make_raw_scans(n, seed=0xC0FFEE, device="cuda:%d" % local_rank)
+    sp_map = default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=0.0)
+    sp = default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=args.voxel)
+    h = Handle(local_rank, default_params(**TRACK))
+    # resident local maps: the full-resolution clouds of the scans taken at P * delta (set 2)
+    h.preprocess_scans_to_set(2, sp_map, raw.moving_ranges)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    ranges, ids = pin(raw.fixed_ranges), pin(np.arange(n, dtype=np.int32))
+    robots, init = pin(np.zeros((n, 3), np.float32)), pin(np.zeros((n, 3), np.float32))
+    out = torch.zeros(n * 64, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
+    for _ in range(args.warmup):
+        h.track_batch(sp, ranges, 2, ids, robots, init, out)
+    torch.cuda.synchronize()
+    l0 = h.launch_count
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.track_batch(sp, ranges, 2, ids, robots, init, out)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    err = np.abs(np.stack([out["x"], out["y"], out["theta"]], 1) - raw.gt_xyt)
+    print(json.dumps({
+        "metric": "tracked frames/sec (raw 1081-beam scan -> pose; pre-process + clip + 10 GN iters)",
+        "value": n * args.steps / dt, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "tracker frame step from raw scans: %d frames x 1081 beams, voxelize %.3f, resident "
+                               "local maps, tracking parameter set" % (n, args.voxel), "frames_per_step": n,
+                   "success_rate": float((out["status"] == 0).mean()),
+                   "median_abs_pose_error": [float(v) for v in np.median(err, 0)]},
+        "e2e": {"value": n * args.steps / dt, "unit": "frames/s",
+                "h2d_bytes_per_step": int(ranges.nbytes + ids.nbytes + robots.nbytes + init.nbytes),
+                "d2h_bytes_per_step": int(out.nbytes)},
+        "gpu_launches": int(h.launch_count - l0), "clocks": clk,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["align", "verify"], default="align")
+    ap.add_argument("--workload", choices=["align", "verify", "track"], default="align")
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--candidates", type=int, default=65536)
     ap.add_argument("--guesses", type=int, default=8)
     ap.add_argument("--unique", type=int, default=4096)
+    ap.add_argument("--voxel", type=float, default=0.02, help="track: voxelize_resolution of the pre-processor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -392,6 +448,8 @@ def main():
         run_reference(args)
     elif args.workload == "verify":
         run_verify(args)
+    elif args.workload == "track":
+        run_track(args)
     else:
         run_ours(args)
 

@@ -44,6 +44,10 @@ struct ls2d_handle {
   cloud_set sets[LS2D_MAX_CLOUD_SETS];
   scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior, d_ranges, d_clip;
   int64_t launches = 0;
+  // host pipeline of ls2d_align_pairs_host: uploads run on their own stream, one event per chunk
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready     = nullptr;
+  cudaEvent_t ev_chunk[8]  = {};
   int variant      = 0;  // LS2D_ICP_VARIANT: tuning knob for the 1081-point kernel shape
   // NCCL, resolved lazily
   void* nccl_lib                                                             = nullptr;
@@ -314,6 +318,10 @@ int ls2d_destroy(ls2d_handle* h) {
   release(h->d_misc);
   release(h->d_ranges);
   release(h->d_clip);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  for (cudaEvent_t e : h->ev_chunk)
+    if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->nccl_lib) dlclose(h->nccl_lib);
   delete h;
@@ -469,12 +477,81 @@ int ls2d_score_batch_dev(ls2d_handle* h, const int32_t* fid, const int32_t* mid,
   return align_dev_impl(h, fid, mid, xyt, n_pairs, out, nullptr, 1);
 }
 
+// grows an owned cloud set to hold `total` points / `n_off` offsets (no copies)
+static int reserve_set(cloud_set& c, size_t total, size_t n_off) {
+  if (!c.owned) c = cloud_set();
+  c.owned = true;
+  if (total > c.cap_pts || !c.pts) {
+    if (c.pts) cudaFree(c.pts);
+    c.pts     = nullptr;
+    c.cap_pts = 0;
+    CU(cudaMalloc((void**) &c.pts, (total + total / 8 + 16) * sizeof(float4)));
+    c.cap_pts = total + total / 8 + 16;
+  }
+  if (n_off > c.cap_off || !c.off) {
+    if (c.off) cudaFree(c.off);
+    c.off     = nullptr;
+    c.cap_off = 0;
+    CU(cudaMalloc((void**) &c.off, (n_off + n_off / 8 + 16) * sizeof(int)));
+    c.cap_off = n_off + n_off / 8 + 16;
+  }
+  return LS2D_OK;
+}
+
+// One call from host buffers.  The batch is cut into up to 8 chunks of whole pairs: chunk k+1's clouds cross
+// PCIe on the copy stream while chunk k aligns, so the call costs the upload plus one chunk's kernel.
 int ls2d_align_pairs_host(ls2d_handle* h, const float* fpts, const int32_t* foff, const float* mpts,
                           const int32_t* moff, const float* init, int32_t n_pairs, ls2d_result* out) {
+  if (!h || !foff || !moff || !init || !out || n_pairs < 0) return LS2D_ERR_INVALID;
+  if (n_pairs == 0) return LS2D_OK;
+  if (foff[0] != 0 || moff[0] != 0 || (!fpts && foff[n_pairs] > 0) || (!mpts && moff[n_pairs] > 0)) return LS2D_ERR_INVALID;
+  int maxf = 0, maxm = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    const int nf = foff[i + 1] - foff[i], nm = moff[i + 1] - moff[i];
+    if (nf < 0 || nm < 0) return LS2D_ERR_INVALID;
+    if (nf > maxf) maxf = nf;
+    if (nm > maxm) maxm = nm;
+  }
+  CU(cudaSetDevice(h->device));
   int rc;
-  if ((rc = ls2d_upload_clouds(h, LS2D_FIXED, fpts, foff, n_pairs))) return rc;
-  if ((rc = ls2d_upload_clouds(h, LS2D_MOVING, mpts, moff, n_pairs))) return rc;
-  return align_host_impl(h, nullptr, nullptr, init, n_pairs, out, nullptr, 0);
+  cloud_set& F = h->sets[LS2D_FIXED];
+  cloud_set& M = h->sets[LS2D_MOVING];
+  if ((rc = reserve_set(F, (size_t) foff[n_pairs], (size_t) n_pairs + 1))) return rc;
+  if ((rc = reserve_set(M, (size_t) moff[n_pairs], (size_t) n_pairs + 1))) return rc;
+  F.n_clouds = M.n_clouds = n_pairs;
+  F.max_points = maxf, M.max_points = maxm;
+  if ((rc = reserve(h->d_init, sizeof(float) * 3 * (size_t) n_pairs))) return rc;
+  if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) n_pairs))) return rc;
+  if (!h->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+    for (cudaEvent_t& e : h->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  // earlier work on the compute stream may still read the sets: the uploads wait for it
+  CU(cudaEventRecord(h->ev_ready, h->stream));
+  CU(cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+  CU(cudaMemcpyAsync(F.off, foff, sizeof(int) * ((size_t) n_pairs + 1), cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaMemcpyAsync(M.off, moff, sizeof(int) * ((size_t) n_pairs + 1), cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaMemcpyAsync(h->d_init.p, init, sizeof(float) * 3 * (size_t) n_pairs, cudaMemcpyHostToDevice, h->copy_stream));
+  int n_chunks = n_pairs / 888;  // >= two waves of 3 CTAs x 148 SMs per chunk
+  n_chunks     = n_chunks < 1 ? 1 : (n_chunks > 8 ? 8 : n_chunks);
+  for (int k = 0; k < n_chunks; ++k) {
+    const int p0 = (int) ((long long) n_pairs * k / n_chunks), p1 = (int) ((long long) n_pairs * (k + 1) / n_chunks);
+    const size_t nf = (size_t) (foff[p1] - foff[p0]), nm = (size_t) (moff[p1] - moff[p0]);
+    if (nf) CU(cudaMemcpyAsync(F.pts + foff[p0], fpts + 4 * (size_t) foff[p0], nf * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream));
+    if (nm) CU(cudaMemcpyAsync(M.pts + moff[p0], mpts + 4 * (size_t) moff[p0], nm * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream));
+    CU(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_chunk[k], 0));
+    align_args a = base_args(h);
+    a.init_xyt   = (const float*) h->d_init.p;
+    a.out        = (ls2d_result*) h->d_out.p;
+    a.n_pairs    = p1 - p0;
+    a.pair_base  = p0;
+    if ((rc = launch_icp(h, a))) return rc;
+  }
+  CU(cudaMemcpyAsync(out, h->d_out.p, sizeof(ls2d_result) * (size_t) n_pairs, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
 }
 
 // ---- multi-slice aligner ---------------------------------------------------------------------------

@@ -48,6 +48,7 @@ struct align_args {
   ls2d_iter_stats* iters;  // nullable
   int n_pairs;
   int score_only;  // 1: one linearisation, no update
+  int pair_base;   // first pair of this launch (chunked host pipeline); grid = n_pairs CTAs
 };
 
 constexpr unsigned Z_EMPTY_DEPTH = 0xFFFFFFFFu;
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
   pose_bc* bc      = reinterpret_cast<pose_bc*>(red + (T / 32) * RED_STRIDE);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pair = blockIdx.x;
+  const int pair = blockIdx.x + A.pair_base;
   const int fcl  = A.fixed_const >= 0 ? A.fixed_const : (A.fixed_id ? A.fixed_id[pair] : pair);
   const int mcl  = A.moving_id ? A.moving_id[pair / A.moving_div] : pair / A.moving_div;
   const int f0 = A.fixed_off[fcl], nf = A.fixed_off[fcl + 1] - f0;
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(T, MINB) icp_stream_kernel(const dev_params P,
   pose_bc* bc          = reinterpret_cast<pose_bc*>(red + (T / 32) * RED_STRIDE);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pair = blockIdx.x;
+  const int pair = blockIdx.x + A.pair_base;
   const int fcl  = A.fixed_const >= 0 ? A.fixed_const : (A.fixed_id ? A.fixed_id[pair] : pair);
   const int mcl  = A.moving_id ? A.moving_id[pair / A.moving_div] : pair / A.moving_div;
   const int f0 = A.fixed_off[fcl], nf = A.fixed_off[fcl + 1] - f0;

@@ -391,3 +391,32 @@ def test_streaming_kernel_variants_are_bit_exact(oracle, variant, monkeypatch):
                                    sp.moving_off, sp.init_xyt, sum_mode=oracle.SUM_TREE,
                                    tree_threads=reduction_threads(1081), n_threads=oracle.max_threads())
     assert_bit_exact(g, o, gi, oi)
+
+
+def test_chunked_host_pipeline_matches_the_resident_path(handle_factory):
+    """ls2d_align_pairs_host cuts a batch into chunks whose uploads overlap the previous chunk's kernel: results must
+    not depend on the chunking (ragged clouds, 2000 pairs -> two chunks)."""
+    base = make_scan_pairs(50, n_beams=600, seed=77)
+    rng = np.random.default_rng(2)
+    n = 2000
+    src = rng.integers(0, 50, n)
+    keep = rng.integers(300, 601, n)
+    f = base.fixed_pts.reshape(50, 600, 4)
+    m = base.moving_pts.reshape(50, 600, 4)
+    fixed = [f[s, :k] for s, k in zip(src, keep)]
+    moving = [m[s, :k2] for s, k2 in zip(src, keep[::-1])]
+    foff = np.concatenate([[0], np.cumsum([len(c) for c in fixed])]).astype(np.int32)
+    moff = np.concatenate([[0], np.cumsum([len(c) for c in moving])]).astype(np.int32)
+    fpts, mpts = np.concatenate(fixed), np.concatenate(moving)
+    init = base.init_xyt[src]
+    kw = dict(canvas_cols=721, normal_cos=0.9, max_iterations=6)
+    h = handle_factory(default_params(**kw))
+    h.upload_clouds(LS2D_FIXED, fpts, foff)
+    h.upload_clouds(LS2D_MOVING, mpts, moff)
+    ref = h.align_batch(init)
+    h2 = handle_factory(default_params(**kw))
+    one = h2.align_pairs_host(fpts, foff, mpts, moff, init)
+    assert h2.launch_count == 2
+    assert one.tobytes() == ref.tobytes()
+    two = h2.align_pairs_host(fpts[:foff[10]], foff[:11], mpts[:moff[10]], moff[:11], init[:10])   # shrink: one chunk
+    assert two.tobytes() == ref[:10].tobytes()
