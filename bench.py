@@ -20,6 +20,8 @@ over +-3.14159 rad.  A "step" is one pass of the hot path over the whole batch.
 N > 1 (torchrun): one process per GPU, every rank aligns its own 4096-pair batch (independent pairs, no
 data-path collective: weak scaling); time = max over ranks.   --impl reference times the oracle only.
 --workload verify runs the sharded loop-closure verification (config 4 shape) instead.
+--workload allpairs runs the large-map all-pairs loop-closure search (config 5 shape): candidate pairs grouped by query
+map, groups sharded over the ranks, one all-gather of the per-map best records.
 --workload track times the tracker's frame step from RAW scans (ls2d_track_batch: pre-process -> clip -> align).
 """
 from __future__ import annotations
@@ -375,6 +377,125 @@ def run_verify(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- all-pairs search
+def run_allpairs(args):
+    """Large-map all-pairs loop-closure search (BASELINE.json configs[4], "config 5" of SURVEY.md 8d): n_maps local
+    maps of map_points points each, all resident on every GPU; candidate pairs from a seeded radius query over the map
+    positions, grouped by query map; ranks own contiguous runs of groups with equal pair counts; the only exchange
+    is one all-gather of the per-map ls2d_best records (n_maps x 32 B per rank)."""
+    import torch
+    import torch.distributed as dist
+    from scipy.spatial import cKDTree
+
+    from srrg2_laser_slam_2d_b200 import Gates, Handle, default_params
+    from srrg2_laser_slam_2d_b200._abi import BEST_DTYPE, LS2D_FIXED, LS2D_MOVING
+    from srrg2_laser_slam_2d_b200.sharding import shard_groups
+    from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_maps, n_pts, uniq = args.maps, args.map_points, min(args.maps, args.unique)
+    # unique local maps: 360-degree scans of seeded rooms with n_pts beams; map m holds cloud m % uniq, materialised
+    # n_maps times so the working set is the real one (20,000 x 8192 x 16 B = 2.6 GB per GPU)
+    sp = make_scan_pairs(uniq, n_beams=n_pts, seed=0xA11, device=str(dev), fov=6.2, motion_xy=0.4, motion_theta=0.2)
+    reps = (n_maps + uniq - 1) // uniq
+    pts = torch.from_numpy(sp.moving_pts).to(dev).view(uniq, n_pts, 4).repeat(reps, 1, 1)[:n_maps].contiguous()
+    off = torch.arange(n_maps + 1, dtype=torch.int32, device=dev) * n_pts
+    fpts = torch.from_numpy(sp.fixed_pts).to(dev).view(uniq, n_pts, 4).repeat(reps, 1, 1)[:n_maps].contiguous()
+    # candidate pairs: maps sit on a seeded random walk; every earlier map within `radius` of a query map is a candidate
+    rng = np.random.default_rng(5)
+    pos = np.cumsum(rng.normal(0.0, 1.0, (n_maps, 2)), 0)
+    pairs = cKDTree(pos).query_pairs(args.radius, output_type="ndarray")          # (i < j)
+    pairs = pairs[pairs[:, 1] - pairs[:, 0] > 8]                                   # not the immediate predecessors
+    order = np.lexsort((pairs[:, 0], pairs[:, 1]))
+    fid_all, mid_all = pairs[order, 1].astype(np.int32), pairs[order, 0].astype(np.int32)
+    group_off = np.searchsorted(fid_all, np.arange(n_maps + 1)).astype(np.int32)   # one group per query map
+    g_lo, g_hi = shard_groups(group_off, rank, world)
+    p_lo, p_hi = int(group_off[g_lo]), int(group_off[g_hi])
+    n_local = p_hi - p_lo
+    guesses = (sp.gt_xyt[mid_all % uniq] + rng.uniform(-0.1, 0.1, (len(mid_all), 3))).astype(np.float32)
+    h = Handle(local_rank, default_params(**dict(LOOP, canvas_cols=args.canvas)))
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    h.set_stream(stream.cuda_stream)
+    h.set_clouds_dev(LS2D_FIXED, fpts.data_ptr(), off.data_ptr(), n_maps, n_pts)
+    h.set_clouds_dev(LS2D_MOVING, pts.data_ptr(), off.data_ptr(), n_maps, n_pts)
+    fid = torch.from_numpy(fid_all[p_lo:p_hi].copy()).to(dev)
+    mid = torch.from_numpy(mid_all[p_lo:p_hi].copy()).to(dev)
+    gs = torch.from_numpy(guesses[p_lo:p_hi].copy()).to(dev)
+    goff = torch.from_numpy((group_off[g_lo:g_hi + 1] - p_lo).astype(np.int32)).to(dev)
+    best = torch.zeros(n_maps * 8, dtype=torch.int32, device=dev)
+    best.view(n_maps, 8)[:, 6:] = -1                      # candidate / guess = -1 outside this rank's groups
+    gathered = torch.zeros(world * n_maps * 8, dtype=torch.int32, device=dev)
+    owner = torch.zeros(n_maps, dtype=torch.int64, device=dev)
+    for r in range(world):
+        lo, hi = shard_groups(group_off, r, world)
+        owner[lo:hi] = r
+    final = torch.zeros(n_maps, 8, dtype=torch.int32, device=dev)
+    gates = Gates(300, 0.1, 0.8)
+    rows = torch.arange(n_maps, device=dev)
+
+    def step():
+        h.verify_pairs_dev(fid.data_ptr(), mid.data_ptr(), gs.data_ptr(), n_local, goff.data_ptr(), g_hi - g_lo, gates,
+                           best.data_ptr() + 32 * g_lo)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, best)
+        else:
+            gathered.copy_(best)
+        final.copy_(gathered.view(world, n_maps, 8)[owner, rows])   # every group has exactly one owner
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clk = clocks.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    rec = np.frombuffer(final.cpu().numpy().tobytes(), dtype=BEST_DTYPE)
+    if rank == 0:
+        n_pairs = len(fid_all)
+        a_bytes = 16 * n_pts * n_pairs + 16 * n_pts * int((np.diff(group_off) > 0).sum()) + 80 * n_pairs
+        s_per_step = float(ms[0]) * 1e-3 / args.steps
+        peak, peak_src = hbm_peak()
+        print(json.dumps({
+            "metric": "verified candidate pairs/sec (%d-point local maps, 30 GN iters)" % n_pts,
+            "value": n_pairs / s_per_step, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "large-map all-pairs loop-closure search: %d local maps x %d points, %d candidate "
+                                   "pairs (radius %.1f), 30 GN iterations, loop-closure parameter set (config 5 shape)"
+                                   % (n_maps, n_pts, n_pairs, args.radius),
+                       "unique_map_clouds": uniq, "resident_bytes_per_gpu": int(2 * pts.numel() * 4),
+                       "canvas_cols": args.canvas, "collective": "all_gather of %d x %d x 32 B" % (world, n_maps)},
+            "accepted_maps": int((rec["candidate"] >= 0).sum()),
+            "checksum": int(np.bitwise_xor.reduce(rec.view(np.uint32).ravel())),
+            "roofline": {"bound": "hbm", "achieved": a_bytes / s_per_step / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": a_bytes / s_per_step / 1e9 / world / peak, "peak_source": peak_src,
+                         "kernel": "icp_stream_kernel", "traffic": None,
+                         "note": "per GPU; algorithmic bytes = 16*N per candidate map + 16*N per query map + 80 per pair"},
+            "gpu_launches": int(h.launch_count), "clocks": clk,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------- tracker step
 def run_track(args):
     """The tracker's frame step with raw scans as the wire format: per frame 1081 ranges
@@ -435,11 +556,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["align", "verify", "track"], default="align")
+    ap.add_argument("--workload", choices=["align", "verify", "track", "allpairs"], default="align")
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--candidates", type=int, default=65536)
     ap.add_argument("--guesses", type=int, default=8)
     ap.add_argument("--unique", type=int, default=4096)
+    ap.add_argument("--maps", type=int, default=20000, help="allpairs: local maps")
+    ap.add_argument("--map-points", type=int, default=8192, help="allpairs: points per local map")
+    ap.add_argument("--radius", type=float, default=2.0, help="allpairs: candidate radius over the map positions")
+    ap.add_argument("--canvas", type=int, default=1081, help="allpairs: projector canvas_cols")
     ap.add_argument("--voxel", type=float, default=0.02, help="track: voxelize_resolution of the pre-processor")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -448,6 +573,8 @@ def main():
         run_reference(args)
     elif args.workload == "verify":
         run_verify(args)
+    elif args.workload == "allpairs":
+        run_allpairs(args)
     elif args.workload == "track":
         run_track(args)
     else:

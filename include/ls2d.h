@@ -228,6 +228,18 @@ int ls2d_verify(ls2d_handle* h, int32_t query_id, const int32_t* candidate_ids, 
 int ls2d_verify_dev(ls2d_handle* h, int32_t query_id, const int32_t* candidate_ids_dev, int32_t n_cand,
                     const float* guesses_xyt_dev, int32_t n_guess, const ls2d_gates* gates,
                     int32_t candidate_base, ls2d_best* best_dev, ls2d_result* all_results_dev);
+/* all-pairs loop-closure search (BASELINE.json configs[4]): pair p aligns moving cloud moving_ids[p] onto fixed
+ * cloud fixed_ids[p] from guesses_xyt[p]; the pairs are grouped by group_offsets (CSR over pairs, n_groups + 1
+ * entries; one group per query local map) and best[g] is the best accepted pair of group g under the same gates
+ * and ordering (candidate = its moving cloud id, guess = its index inside the group; candidate -1: none accepted).
+ * Ranks own disjoint runs of groups; the records all-gather like ls2d_verify's. */
+int ls2d_verify_pairs(ls2d_handle* h, const int32_t* fixed_ids, const int32_t* moving_ids, const float* guesses_xyt,
+                      int32_t n_pairs, const int32_t* group_offsets, int32_t n_groups, const ls2d_gates* gates,
+                      ls2d_best* best, ls2d_result* all_results);
+int ls2d_verify_pairs_dev(ls2d_handle* h, const int32_t* fixed_ids_dev, const int32_t* moving_ids_dev,
+                          const float* guesses_xyt_dev, int32_t n_pairs, const int32_t* group_offsets_dev,
+                          int32_t n_groups, const ls2d_gates* gates, ls2d_best* best_dev,
+                          ls2d_result* all_results_dev);
 /* best-of over gathered shard records (host), same ordering rule */
 int ls2d_reduce_best(const ls2d_best* records, int32_t n, ls2d_best* out);
 /* ls2d_verify_dev + all-gather of the 32-byte records over an existing NCCL communicator

@@ -79,7 +79,7 @@ EXPORTS = [
     "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev", "ls2d_align_multi", "ls2d_align_multi_dev",
     "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
     "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
-    "ls2d_clip_scenes_to_set", "ls2d_track_batch",
+    "ls2d_clip_scenes_to_set", "ls2d_track_batch", "ls2d_verify_pairs", "ls2d_verify_pairs_dev",
 ]
 
 _lib = None
@@ -117,6 +117,8 @@ def load():
     L.ls2d_verify.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]
     L.ls2d_verify_dev.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]
     L.ls2d_reduce_best.argtypes = [vp, i32, vp]
+    L.ls2d_verify_pairs.argtypes = [vp, vp, vp, vp, i32, vp, i32, GP, vp, vp]
+    L.ls2d_verify_pairs_dev.argtypes = [vp, vp, vp, vp, i32, vp, i32, GP, vp, vp]
     L.ls2d_verify_sharded_nccl.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, i32, vp]
     L.ls2d_clip_scenes.argtypes = [vp, C.c_int, vp, vp, vp, i32, vp, vp]
     L.ls2d_merge_scene.argtypes = [vp, vp, C.POINTER(i32), i32, vp, i32, vp, f32, vp]
@@ -410,6 +412,23 @@ class Handle:
         self._check(self._L.ls2d_verify(self._h, query_id, _ptr(cand), n_cand, _ptr(g), n_guess, C.byref(gates),
                                         candidate_base, _ptr(best), _ptr(allr)))
         return (best[0], allr) if want_all else best[0]
+
+    def verify_pairs(self, fixed_ids, moving_ids, guesses_xyt, group_offsets, gates: Gates, want_all: bool = False):
+        """all-pairs search: one ls2d_best per group of consecutive pairs (group_offsets: CSR over the pairs)"""
+        fid, mid, off = _i32(fixed_ids), _i32(moving_ids), _i32(group_offsets)
+        g = _f32(guesses_xyt).reshape(-1, 3)
+        n, n_groups = len(g), len(off) - 1
+        best = np.zeros(n_groups, BEST_DTYPE)
+        allr = np.zeros(n, RESULT_DTYPE) if want_all else None
+        self._check(self._L.ls2d_verify_pairs(self._h, _ptr(fid), _ptr(mid), _ptr(g), n, _ptr(off), n_groups,
+                                              C.byref(gates), _ptr(best), _ptr(allr)))
+        return (best, allr) if want_all else best
+
+    def verify_pairs_dev(self, fid_ptr, mid_ptr, guesses_ptr: int, n_pairs: int, group_off_ptr: int, n_groups: int,
+                         gates: Gates, best_ptr: int, all_ptr: int | None = None):
+        self._check(self._L.ls2d_verify_pairs_dev(self._h, C.c_void_p(fid_ptr or 0), C.c_void_p(mid_ptr or 0),
+                                                  C.c_void_p(guesses_ptr), n_pairs, C.c_void_p(group_off_ptr), n_groups,
+                                                  C.byref(gates), C.c_void_p(best_ptr), C.c_void_p(all_ptr or 0)))
 
     def verify_dev(self, query_id: int, cand_ptr, n_cand: int, guesses_ptr: int, n_guess: int, gates: Gates,
                    candidate_base: int, best_ptr: int, all_ptr: int | None = None):

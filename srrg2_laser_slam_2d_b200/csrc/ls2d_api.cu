@@ -786,6 +786,61 @@ int ls2d_verify(ls2d_handle* h, int32_t query_id, const int32_t* cand, int32_t n
   return LS2D_OK;
 }
 
+int ls2d_verify_pairs_dev(ls2d_handle* h, const int32_t* fid_dev, const int32_t* mid_dev, const float* guesses_dev,
+                          int32_t n_pairs, const int32_t* group_off_dev, int32_t n_groups, const ls2d_gates* gates,
+                          ls2d_best* best_dev, ls2d_result* all_dev) {
+  if (!h || !guesses_dev || !gates || !best_dev || !group_off_dev || n_pairs < 0 || n_groups < 0) return LS2D_ERR_INVALID;
+  if (!ready(h)) return LS2D_ERR_NOT_READY;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if (!all_dev) {
+    if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) (n_pairs > 0 ? n_pairs : 1)))) return rc;
+    all_dev = (ls2d_result*) h->d_out.p;
+  }
+  align_args a = base_args(h);
+  a.fixed_id   = fid_dev;
+  a.moving_id  = mid_dev;
+  a.init_xyt   = guesses_dev;
+  a.out        = all_dev;
+  a.n_pairs    = n_pairs;
+  if ((rc = launch_icp(h, a))) return rc;
+  if (n_groups > 0) {
+    best_of_groups_kernel<<<(n_groups + 7) / 8, 256, 0, h->stream>>>(all_dev, group_off_dev, n_groups, mid_dev, *gates, best_dev);
+    CU(cudaGetLastError());
+    h->launches++;
+  }
+  return LS2D_OK;
+}
+
+int ls2d_verify_pairs(ls2d_handle* h, const int32_t* fid, const int32_t* mid, const float* guesses, int32_t n_pairs,
+                      const int32_t* group_off, int32_t n_groups, const ls2d_gates* gates, ls2d_best* best,
+                      ls2d_result* all) {
+  if (!h || !guesses || !gates || !best || !group_off || n_pairs < 0 || n_groups < 0) return LS2D_ERR_INVALID;
+  if (!ready(h)) return LS2D_ERR_NOT_READY;
+  if (group_off[0] != 0 || group_off[n_groups] != n_pairs) return LS2D_ERR_INVALID;
+  for (int g = 0; g < n_groups; ++g)
+    if (group_off[g + 1] < group_off[g]) return LS2D_ERR_INVALID;
+  int rc = check_ids(h, fid, mid, n_pairs);
+  if (rc) return rc;
+  if (n_groups == 0) return LS2D_OK;
+  CU(cudaSetDevice(h->device));
+  const size_t n = (size_t) n_pairs;
+  if (fid && n && (rc = h2d(h, h->d_fid, fid, sizeof(int) * n))) return rc;
+  if (mid && n && (rc = h2d(h, h->d_mid, mid, sizeof(int) * n))) return rc;
+  if ((rc = h2d(h, h->d_init, guesses, sizeof(float) * 3 * (n ? n : 1)))) return rc;
+  if ((rc = h2d(h, h->d_misc, group_off, sizeof(int) * ((size_t) n_groups + 1)))) return rc;
+  if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (n ? n : 1)))) return rc;
+  if ((rc = reserve(h->d_best, sizeof(ls2d_best) * (size_t) n_groups))) return rc;
+  rc = ls2d_verify_pairs_dev(h, fid ? (const int*) h->d_fid.p : nullptr, mid ? (const int*) h->d_mid.p : nullptr,
+                             (const float*) h->d_init.p, n_pairs, (const int*) h->d_misc.p, n_groups, gates,
+                             (ls2d_best*) h->d_best.p, (ls2d_result*) h->d_out.p);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(best, h->d_best.p, sizeof(ls2d_best) * (size_t) n_groups, cudaMemcpyDeviceToHost, h->stream));
+  if (all && n) CU(cudaMemcpyAsync(all, h->d_out.p, sizeof(ls2d_result) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
+}
+
 int ls2d_reduce_best(const ls2d_best* rec, int32_t n, ls2d_best* out) {
   if (!rec || !out || n < 0) return LS2D_ERR_INVALID;
   ls2d_best b;

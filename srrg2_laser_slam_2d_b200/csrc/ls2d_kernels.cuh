@@ -921,4 +921,45 @@ __global__ void best_of_kernel(const ls2d_result* res, int n, int n_guess, ls2d_
   }
 }
 
+// acceptance gates + best-of per GROUP of consecutive results (all-pairs search, BASELINE.json configs[4]: one group
+// per query local map); one warp per group.  The record names the winning pair: candidate = moving_id[pair] (the
+// pair index when moving_id is null), guess = index of the pair inside its group.  Ordering as above, ties by the
+// lower pair index, so any sharding of the groups over ranks gives the same records.
+__global__ void best_of_groups_kernel(const ls2d_result* res, const int* group_off, int n_groups, const int* moving_id,
+                                      ls2d_gates g, ls2d_best* out) {
+  const int lane = threadIdx.x & 31;
+  const int grp  = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (grp >= n_groups) return;
+  const int p0 = group_off[grp], p1 = group_off[grp + 1];
+  int bn = 0, bi = -1;
+  float bcpi = 0.f;
+  for (int i = p0 + lane; i < p1; i += 32) {
+    const ls2d_result r = res[i];
+    if (!accepts(r, g)) continue;
+    const float c = fdiv(r.chi_inliers, (float) r.n_inliers);
+    if (better(r.n_inliers, c, i, bn, bcpi, bi)) bn = r.n_inliers, bcpi = c, bi = i;
+  }
+  for (int off = 16; off >= 1; off >>= 1) {
+    const int on   = __shfl_xor_sync(0xffffffffu, bn, off);
+    const float oc = __shfl_xor_sync(0xffffffffu, bcpi, off);
+    const int oi   = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (better(on, oc, oi, bn, bcpi, bi)) bn = on, bcpi = oc, bi = oi;
+  }
+  if (lane == 0) {
+    ls2d_best b;
+    if (bi < 0) {
+      b.x = b.y = b.theta = b.chi_inliers = 0.f;
+      b.n_inliers = b.n_corr = 0;
+      b.candidate = -1, b.guess = -1;
+    } else {
+      const ls2d_result r = res[bi];
+      b.x = r.x, b.y = r.y, b.theta = r.theta, b.chi_inliers = r.chi_inliers;
+      b.n_inliers = r.n_inliers, b.n_corr = r.n_corr;
+      b.candidate = moving_id ? moving_id[bi] : bi;
+      b.guess     = bi - p0;
+    }
+    out[grp] = b;
+  }
+}
+
 }  // namespace ls2d

@@ -33,3 +33,49 @@ def all_gather_best(local_best: np.ndarray, group=None) -> np.ndarray:
     out = torch.zeros(8 * world, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(out, mine, group=group)
     return reduce_best(np.frombuffer(out.cpu().numpy().tobytes(), dtype=BEST_DTYPE))
+
+
+def shard_groups(group_offsets: np.ndarray, rank: int, world: int) -> tuple[int, int]:
+    """All-pairs search (BASELINE.json configs[4]): the candidate-pair list is grouped by query (fixed) map and the
+    ranks own contiguous runs of groups, cut so that every rank gets about the same number of PAIRS (a group is never
+    split: its fixed map stays on one rank).  Returns the rank's [g_lo, g_hi)."""
+    off = np.asarray(group_offsets, np.int64)
+    n_groups, total = len(off) - 1, int(off[-1])
+    cuts = [0]
+    for r in range(1, world):
+        # first group boundary at or after r/world of the pairs, never before the previous cut
+        g = int(np.searchsorted(off, (total * r + world - 1) // world, side="left"))
+        cuts.append(min(max(g, cuts[-1]), n_groups))
+    cuts.append(n_groups)
+    return cuts[rank], cuts[rank + 1]
+
+
+def combine_group_best(gathered: np.ndarray) -> np.ndarray:
+    """gathered: [world, n_groups] ls2d_best records, candidate = -1 where a rank does not own the group or accepted
+    nothing.  Groups are owned by exactly one rank, so the combination is a per-group reduce_best."""
+    gathered = np.asarray(gathered)
+    world, n_groups = gathered.shape
+    out = np.zeros(n_groups, BEST_DTYPE)
+    out["candidate"], out["guess"] = -1, -1
+    for g in range(n_groups):
+        col = np.ascontiguousarray(gathered[:, g])
+        if (col["candidate"] >= 0).any():
+            out[g] = reduce_best(col)
+    return out
+
+
+def all_gather_group_best(local: np.ndarray, group=None) -> np.ndarray:
+    """All-gather every rank's full-length per-group record array ([n_groups] BEST_DTYPE, -1 outside its own run)
+    and combine.  20,000 groups x 32 B = 640 KB per rank."""
+    import torch
+    import torch.distributed as dist
+
+    local = np.ascontiguousarray(local, dtype=BEST_DTYPE)
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.from_numpy(local.view(np.int32).copy()).to(dev)
+    out = torch.zeros(world * mine.numel(), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    rec = np.frombuffer(out.cpu().numpy().tobytes(), dtype=BEST_DTYPE).reshape(world, len(local))
+    return combine_group_best(rec)

@@ -420,3 +420,44 @@ def test_chunked_host_pipeline_matches_the_resident_path(handle_factory):
     assert one.tobytes() == ref.tobytes()
     two = h2.align_pairs_host(fpts[:foff[10]], foff[:11], mpts[:moff[10]], moff[:11], init[:10])   # shrink: one chunk
     assert two.tobytes() == ref[:10].tobytes()
+
+
+def test_verify_pairs_per_group_best_matches_the_oracle(handle_factory, oracle):
+    """all-pairs search (BASELINE.json configs[4]): grouped candidate pairs, one best record per query map; large
+    (3000-point) local maps go through the streaming kernel."""
+    n_maps, n_pts = 10, 3000
+    sp = make_scan_pairs(n_maps, n_beams=n_pts, seed=31, motion_xy=0.3, motion_theta=0.15, fov=6.2)
+    kw = dict(canvas_cols=721, point_distance=1.414, normal_cos=0.8, cauchy_chi_threshold=0.05, max_iterations=12)
+    h = handle_factory(default_params(**kw))
+    upload(h, sp)
+    rng = np.random.default_rng(8)
+    # query g (fixed cloud g) against a few candidate maps; the true match (moving cloud g) is among them for even g
+    fid, mid, groups = [], [], [0]
+    for g in range(n_maps):
+        cands = list(rng.choice(n_maps, 3, replace=False))
+        if g % 2 == 0 and g not in cands:
+            cands[0] = g
+        if g == 5:
+            cands = []                                             # a query with no candidate at all
+        for c in sorted(cands):
+            fid.append(g), mid.append(int(c))
+        groups.append(len(fid))
+    fid, mid, groups = np.array(fid, np.int32), np.array(mid, np.int32), np.array(groups, np.int32)
+    guesses = (sp.gt_xyt[mid] + rng.uniform(-0.05, 0.05, (len(mid), 3))).astype(np.float32)
+    gates = Gates(250, 0.1, 0.8)
+    best, allr = h.verify_pairs(fid, mid, guesses, groups, gates, want_all=True)
+    o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
+                              guesses, fid, mid, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(n_pts),
+                              n_threads=oracle.max_threads())
+    assert_bit_exact(allr, o)
+    hits = 0
+    for g in range(n_maps):
+        lo, hi = groups[g], groups[g + 1]
+        k = oracle.best_of(o[lo:hi], 250, 0.1, 0.8) if hi > lo else -1
+        if k < 0:
+            assert best[g]["candidate"] == -1 and best[g]["guess"] == -1
+            continue
+        assert best[g]["candidate"] == mid[lo + k] and best[g]["guess"] == k
+        assert best[g]["n_inliers"] == o["n_inliers"][lo + k] and best[g]["theta"] == o["theta"][lo + k]
+        hits += int(mid[lo + k] == g)
+    assert hits >= 4                                               # true matches are found where offered
