@@ -147,30 +147,41 @@ template <bool SENSOR>
 __device__ __forceinline__ void linearize_point(const dev_params& P, const pose_bc* bc, float fd, const float4 F,
                                                 const float4 M, float rho, float Xtx, float Xty, float Lc, float Ls,
                                                 float (&acc)[16], unsigned& cnt) {
+  // every product / sum below is one binary32 rounding, in the oracle's order; independent ones are issued in
+  // pairs (mul2 / add2, see ls2d_math.cuh for the no-contraction rule)
   do {
       if (fd < 0.f) break;  // fcell.source_idx < 0
       if (fabsf(fsub(fd, rho)) > P.point_distance) break;
-      const float nx = fadd(fmul(Lc, M.z), fmul(-Ls, M.w));  // transformed normal
-      const float ny = fadd(fmul(Ls, M.z), fmul(Lc, M.w));
-      if (fadd(fmul(nx, F.z), fmul(ny, F.w)) < P.normal_cos) break;
+      const f2 rc1 = mk2(Lc, Ls), rc2 = mk2(-Ls, Lc);  // columns of R(local_map_in_sensor)
+      const f2 na = mul2s(rc1, M.z), nb = mul2s(rc2, M.w);
+      const float nx = fadd(na.x, nb.x);  // transformed normal
+      const float ny = fadd(na.y, nb.y);
+      const f2 fn = mk2(F.z, F.w);
+      const f2 nd = mul2(mk2(nx, ny), fn);
+      if (fadd(nd.x, nd.y) < P.normal_cos) break;
       // SE2Plane2PlaneErrorFactor (R/registration/aligner_slice_processor_laser_2d.h:8,23)
-      float px, py;
+      f2 p;
       if (SENSOR) {
-        const float qx = fadd(fadd(fmul(bc->Xc, M.x), fmul(-bc->Xs, M.y)), Xtx);
-        const float qy = fadd(fadd(fmul(bc->Xs, M.x), fmul(bc->Xc, M.y)), Xty);
-        iso_apply(P.Sinv, qx, qy, px, py);
+        const f2 qa = mul2s(mk2(bc->Xc, bc->Xs), M.x), qb = mul2s(mk2(-bc->Xs, bc->Xc), M.y);
+        const float qx = fadd(fadd(qa.x, qb.x), Xtx);
+        const float qy = fadd(fadd(qa.y, qb.y), Xty);
+        iso_apply(P.Sinv, qx, qy, p.x, p.y);
       } else {
-        px = fadd(fadd(fmul(Lc, M.x), fmul(-Ls, M.y)), Xtx);
-        py = fadd(fadd(fmul(Ls, M.x), fmul(Lc, M.y)), Xty);
+        const f2 pa = mul2s(rc1, M.x), pb = mul2s(rc2, M.y);
+        p = add2(mk2(fadd(pa.x, pb.x), fadd(pa.y, pb.y)), mk2(Xtx, Xty));
       }
-      const float dx = fsub(px, F.x), dy = fsub(py, F.y);
-      const float e0 = fadd(fmul(dx, F.z), fmul(dy, F.w));
-      const float e1 = fsub(nx, F.z), e2 = fsub(ny, F.w);
-      const float Ja = fadd(fmul(F.z, Lc), fmul(F.w, Ls));
-      const float Jb = fadd(fmul(F.z, -Ls), fmul(F.w, Lc));
-      const float Jc = fadd(fmul(Ja, -M.y), fmul(Jb, M.x));
+      const f2 d  = add2(p, mk2(-F.x, -F.y));
+      const f2 de = mul2(d, fn);
+      const float e0 = fadd(de.x, de.y);
+      const f2 e12 = add2(mk2(nx, ny), mk2(-F.z, -F.w));  // e1, e2
+      const f2 ja = mul2s(mk2(Lc, -Ls), F.z), jb = mul2s(mk2(Ls, Lc), F.w);
+      const float Ja = fadd(ja.x, jb.x);
+      const float Jb = fadd(ja.y, jb.y);
+      const f2 jc = mul2(mk2(Ja, Jb), mk2(-M.y, M.x));
+      const float Jc = fadd(jc.x, jc.y);
       const float d0 = -ny, d1 = nx;  // R * (-n.y, n.x)^T, exact in binary32
-      const float chi = fadd(fadd(fmul(e0, e0), fmul(e1, e1)), fmul(e2, e2));
+      const f2 ee = mul2(e12, e12);
+      const float chi = fadd(fadd(fmul(e0, e0), ee.x), ee.y);
       float w = 1.f, chi_in = chi, chi_k = 0.f;
       if (P.tau > 0.f && !(chi < P.tau)) {  // RobustifierCauchy (L0.json:76-81)
         const float aux = fadd(fmul(chi, P.inv_tau), 1.f);
@@ -181,17 +192,24 @@ __device__ __forceinline__ void linearize_point(const dev_params& P, const pose_
       } else {
         cnt += 1u;
       }
-      const float wa = fmul(Ja, w), wb = fmul(Jb, w), wc = fmul(Jc, w);
-      const float wd0 = fmul(d0, w), wd1 = fmul(d1, w);
-      acc[0]  = fadd(acc[0], fmul(wa, Ja));
-      acc[1]  = fadd(acc[1], fmul(wa, Jb));
-      acc[2]  = fadd(acc[2], fmul(wa, Jc));
-      acc[3]  = fadd(acc[3], fmul(wb, Jb));
-      acc[4]  = fadd(acc[4], fmul(wb, Jc));
-      acc[5]  = fadd(acc[5], fadd(fadd(fmul(wc, Jc), fmul(wd0, d0)), fmul(wd1, d1)));
-      acc[6]  = fadd(acc[6], fmul(wa, e0));
-      acc[7]  = fadd(acc[7], fmul(wb, e0));
-      acc[8]  = fadd(acc[8], fadd(fadd(fmul(wc, e0), fmul(wd0, e1)), fmul(wd1, e2)));
+      const f2 wab = mul2s(mk2(Ja, Jb), w);  // wa, wb
+      const float wc = fmul(Jc, w);
+      const f2 wd = mul2s(mk2(d0, d1), w);   // wd0, wd1
+      const f2 h01 = mul2s(mk2(Ja, Jb), wab.x);            // wa*Ja, wa*Jb
+      const f2 h23 = mul2(wab, mk2(Jc, Jb));               // wa*Jc, wb*Jb
+      const f2 h4c = mul2(mk2(wab.y, wc), mk2(Jc, Jc));    // wb*Jc, wc*Jc
+      const f2 hdd = mul2(wd, mk2(d0, d1));                // wd0*d0, wd1*d1
+      const f2 b01 = mul2s(wab, e0);                       // wa*e0, wb*e0
+      const f2 bde = mul2(wd, e12);                        // wd0*e1, wd1*e2
+      acc[0]  = fadd(acc[0], h01.x);
+      acc[1]  = fadd(acc[1], h01.y);
+      acc[2]  = fadd(acc[2], h23.x);
+      acc[3]  = fadd(acc[3], h23.y);
+      acc[4]  = fadd(acc[4], h4c.x);
+      acc[5]  = fadd(acc[5], fadd(fadd(h4c.y, hdd.x), hdd.y));
+      acc[6]  = fadd(acc[6], b01.x);
+      acc[7]  = fadd(acc[7], b01.y);
+      acc[8]  = fadd(acc[8], fadd(fadd(fmul(wc, e0), bde.x), bde.y));
       acc[9]  = fadd(acc[9], chi_in);
       acc[10] = fadd(acc[10], chi_k);
   } while (false);
@@ -383,11 +401,11 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
       col[j] = -1;
       rb[j]  = 0;
       if (tid + j * T < nm) {
-        const float rx  = fadd(fmul(Lc, mp[j].x), fmul(-Ls, mp[j].y));
-        const float ry  = fadd(fmul(Ls, mp[j].x), fmul(Lc, mp[j].y));
-        const float px  = fadd(rx, Wtx);
-        const float py  = fadd(ry, Wty);
-        const float rho = fsqrt(fadd(fmul(px, px), fmul(py, py)));
+        const f2 ra = mul2s(mk2(Lc, Ls), mp[j].x), rb2 = mul2s(mk2(-Ls, Lc), mp[j].y);
+        const f2 pc = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
+        const f2 pq = mul2(pc, pc);
+        const float px = pc.x, py = pc.y;
+        const float rho = fsqrt(fadd(pq.x, pq.y));
         if (!(rho < P.range_min || rho > P.range_max)) {
           col[j] = polar_column(P.cam, py, px);
           rb[j]  = f2u(rho);
@@ -535,11 +553,11 @@ __global__ void __launch_bounds__(T, MINB) icp_stream_kernel(const dev_params P,
     if (exact) __syncthreads();
     for (int i = tid; i < nm; i += T) {
       const float4 M  = MP_SMEM ? smp[i] : ldg4(mpts + i);
-      const float rx  = fadd(fmul(Lc, M.x), fmul(-Ls, M.y));
-      const float ry  = fadd(fmul(Ls, M.x), fmul(Lc, M.y));
-      const float px  = fadd(rx, Wtx);
-      const float py  = fadd(ry, Wty);
-      const float rho = fsqrt(fadd(fmul(px, px), fmul(py, py)));
+      const f2 ra = mul2s(mk2(Lc, Ls), M.x), rb2 = mul2s(mk2(-Ls, Lc), M.y);
+      const f2 pc = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
+      const f2 pq = mul2(pc, pc);
+      const float px = pc.x, py = pc.y;
+      const float rho = fsqrt(fadd(pq.x, pq.y));
       int col         = -1;
       if (!(rho < P.range_min || rho > P.range_max)) col = polar_column(P.cam, py, px);
       scol[i] = (unsigned short) (col < 0 ? 0xFFFF : col);
