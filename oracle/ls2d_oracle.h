@@ -12,7 +12,10 @@
  * this path.  What is in-repo is followed line by line
  * (correspondence_finder_projective_2d.cpp:18-77); what lives in the un-vendored
  * dependencies is restated from their published behaviour, and every result-affecting
- * choice is a numbered decision point D1..D17 documented in ls2d_oracle.c.
+ * choice is a numbered decision point (D1..D17 aligner, P1..P8 raw-scan pre-processor) documented in
+ * ls2d_oracle.c.  The one number the reference's own tests pin on a restated row -- the Synthetic
+ * fixture pre-processes into exactly 100 points (tests/test_measurement_adaptor.cpp:36) -- is checked
+ * in tests/test_oracle_preprocess.py.
  *
  * Arithmetic contract: every floating-point operation below is ONE IEEE-754 binary32
  * operation (no FMA contraction; build with -ffp-contract=off), in the order Eigen
