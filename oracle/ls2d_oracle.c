@@ -916,7 +916,10 @@ int32_t orc_merge(const orc_params* prm, float merge_threshold, orc_point* scene
  *     with |p_j - p_i|^2 < normal_point_distance^2 (scan outwards from i, stop at the first violation).
  *  P3 fewer than normal_min_points points in the window (i included) => the point is Invalid (dropped by both
  *     branches of .cpp:37-48).
- *  P4 mean = sum / n; covariance = sum (p - mean)(p - mean)^T / n, sums sequential in ascending index.
+ *  P4 covariance from the first and second moments of d_j = p_j - p_i (relative to the query point, which keeps
+ *     binary32 accurate far from the origin): m = sum d / n, C = sum d d^T / n - m m^T; the sums accumulate in the
+ *     order the window walk visits the points (i-1 down to the window's start, then i+1 up to its end), so one
+ *     pass finds the window and the moments -- the "sliding window" accumulates as it slides.
  *  P5 normal = eigenvector of the smallest eigenvalue by Eigen's closed-form 2x2
  *     SelfAdjointEigenSolver::computeDirect (shift by trace/2, scale by max|coeff|, roots t1 -/+ t0, eigenvector of
  *     the larger root from the better-conditioned row, the other by unitOrthogonal()); degenerate (equal roots):
@@ -1028,37 +1031,37 @@ int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int3
   /* NormalComputator1DSlidingWindow::computeNormals (P2..P6) */
   const float d2 = sp->normal_point_distance * sp->normal_point_distance;
   for (int32_t i = 0; i < n; ++i) {
-    int32_t lo = i, hi = i;
-    while (lo > 0) {
-      const float dx = pts[lo - 1].x - pts[i].x, dy = pts[lo - 1].y - pts[i].y;
-      if (!(dx * dx + dy * dy < d2)) {
+    /* one walk over the window, first towards lower indices, then towards higher ones (P2); first and second
+     * moments of d_j = p_j - p_i accumulate in walking order (P4); p_i itself contributes d = 0 */
+    float sx = 0.f, sy = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f;
+    int32_t cnt = 1;
+    for (int32_t j = i - 1; j >= 0; --j) {
+      const float dx = pts[j].x - pts[i].x, dy = pts[j].y - pts[i].y;
+      const float dxx = dx * dx, dyy = dy * dy;
+      if (!(dxx + dyy < d2)) {
         break;
       }
-      --lo;
+      sx = sx + dx, sy = sy + dy;
+      sxx = sxx + dxx, sxy = sxy + dx * dy, syy = syy + dyy;
+      ++cnt;
     }
-    while (hi + 1 < n) {
-      const float dx = pts[hi + 1].x - pts[i].x, dy = pts[hi + 1].y - pts[i].y;
-      if (!(dx * dx + dy * dy < d2)) {
+    for (int32_t j = i + 1; j < n; ++j) {
+      const float dx = pts[j].x - pts[i].x, dy = pts[j].y - pts[i].y;
+      const float dxx = dx * dx, dyy = dy * dy;
+      if (!(dxx + dyy < d2)) {
         break;
       }
-      ++hi;
+      sx = sx + dx, sy = sy + dy;
+      sxx = sxx + dxx, sxy = sxy + dx * dy, syy = syy + dyy;
+      ++cnt;
     }
-    const int32_t cnt = hi - lo + 1;
     valid[i] = cnt >= sp->normal_min_points; /* P3 */
     if (!valid[i]) {
       continue;
     }
-    float sx = 0.f, sy = 0.f;
-    for (int32_t j = lo; j <= hi; ++j) {
-      sx = sx + pts[j].x, sy = sy + pts[j].y;
-    }
-    const float mx = sx / (float) cnt, my = sy / (float) cnt; /* P4 */
-    float cxx = 0.f, cxy = 0.f, cyy = 0.f;
-    for (int32_t j = lo; j <= hi; ++j) {
-      const float dx = pts[j].x - mx, dy = pts[j].y - my;
-      cxx = cxx + dx * dx, cxy = cxy + dx * dy, cyy = cyy + dy * dy;
-    }
-    cxx = cxx / (float) cnt, cxy = cxy / (float) cnt, cyy = cyy / (float) cnt;
+    const float fc = (float) cnt;
+    const float mx = sx / fc, my = sy / fc;
+    const float cxx = sxx / fc - mx * mx, cxy = sxy / fc - mx * my, cyy = syy / fc - my * my;
     float nx, ny;
     smallest_eigenvector_2x2(cxx, cxy, cyy, &nx, &ny); /* P5 */
     if (nx * pts[i].x + ny * pts[i].y > 0.f) {          /* P6 */

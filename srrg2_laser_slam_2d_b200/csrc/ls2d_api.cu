@@ -1013,8 +1013,9 @@ static int preprocess_dev(ls2d_handle* h, const ls2d_scan_params* sp, const floa
   P.n_beams              = n_beams;
   P.sort_cap             = 0;
   if (P.inv_res != 0.f) {
-    P.sort_cap = 1;
-    while (P.sort_cap < n_beams) P.sort_cap <<= 1;
+    P.sort_cap = (n_beams + 3) & ~3;
+    // the packed voxel key holds |coordinate / res| < 2^22 (coordinates are bounded by the range limit)
+    if (!(P.range_max * P.inv_res < 4194304.f)) return LS2D_ERR_UNSUPPORTED;
   }
   scan_args a;
   a.ranges  = ranges_dev;
@@ -1024,7 +1025,7 @@ static int preprocess_dev(ls2d_handle* h, const ls2d_scan_params* sp, const floa
   const size_t smem = scan_smem_bytes(n_beams, P.sort_cap);
   if (smem > 227 * 1024) return LS2D_ERR_UNSUPPORTED;
   CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  preprocess_kernel<<<n_scans, 256, smem, h->stream>>>(P, a);
+  preprocess_kernel<<<n_scans, SCAN_T, smem, h->stream>>>(P, a);
   CU(cudaGetLastError());
   h->launches++;
   return LS2D_OK;

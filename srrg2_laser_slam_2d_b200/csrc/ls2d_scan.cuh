@@ -3,8 +3,9 @@
 //
 //  preprocess_kernel   one CTA per scan: polar unprojection with an ordered compaction of the accepted beams,
 //                      sliding-window normals (every point sums its own window sequentially: the reference's
-//                      order), optional voxelisation = bitonic sort of the (voxel key, index) pairs in shared
-//                      memory + one sequential sum per run of equal keys, ordered output.
+//                      order), optional voxelisation = runs of consecutive points in one voxel ("segments"),
+//                      bitonic sort of the few hundred segments in shared memory, one sequential sum per voxel in
+//                      cloud order, ordered output.
 //  scan_offsets_kernel exclusive scan of the per-scan counts -> CSR offsets
 //  scan_pack_kernel    strided [n_scans][n_beams] -> packed CSR points
 //
@@ -27,7 +28,7 @@ struct scan_dev_params {
   float inv_res;               // 1 / voxelize_resolution, 0: valid-only copy (.cpp:44-48)
   int min_points;              // normal_min_points
   int n_beams;
-  int sort_cap;                // power of two >= n_beams (voxelisation on), else 0
+  int sort_cap;                // slots of the segment sort: n_beams (voxelisation on), else 0
 };
 
 struct scan_args {
@@ -38,7 +39,7 @@ struct scan_args {
 };
 
 constexpr size_t scan_smem_bytes(int n_beams, int sort_cap) {
-  return (size_t) n_beams * (8 + 8 + 4) + (size_t) sort_cap * (8 + 4) + 64;
+  return (size_t) n_beams * (8 + 8) + (size_t) ((n_beams + 3) & ~3) + (size_t) sort_cap * (8 + 2) + 64;
 }
 
 // Eigen 3.3 SelfAdjointEigenSolver<Matrix2f>::computeDirect: eigenvector of the smallest eigenvalue (P5)
@@ -81,156 +82,229 @@ __device__ __forceinline__ bool key_less(unsigned long long a1, unsigned a2, uns
   return a1 < b1 || (a1 == b1 && a2 < b2);
 }
 
-__global__ void __launch_bounds__(256) preprocess_kernel(const scan_dev_params P, const scan_args A) {
+// Ordered block-wide compaction in two barriers.  Thread `tid` owns element c * T + tid of chunk c and passes its
+// flags as a bit mask (bit c); slots come back through compact_slot().  cnt: n_chunks * (T / 32) ints of shared
+// memory, total: one int.  Element order = chunk, warp, lane = ascending element index.
+__device__ __forceinline__ void compact_count(unsigned mask, int n_chunks, int* cnt, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int c = 0; c < n_chunks; ++c) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
+    if (lane == 0) cnt[c * nwarp + warp] = __popc(ballot);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive prefix over the n_chunks * nwarp counts, in place
+    const int n = n_chunks * nwarp, per = (n + 31) >> 5;
+    int sum = 0;
+    for (int k = lane * per; k < min(n, (lane + 1) * per); ++k) sum += cnt[k];
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    int run = incl - sum;
+    for (int k = lane * per; k < min(n, (lane + 1) * per); ++k) {
+      const int v = cnt[k];
+      cnt[k]      = run;
+      run += v;
+    }
+    if (lane == 31) *total = incl;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ int compact_slot(unsigned mask, int c, const int* cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const unsigned ballot = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
+  return cnt[c * nwarp + warp] + __popc(ballot & ((1u << lane) - 1u));
+}
+
+// voxel key of a point (P7): trunc-toward-zero of (x, y, nx, ny) * (1/res, 1/res, 1, 1), packed so that unsigned
+// order = the oracle's lexicographic order: ix (23 bits, biased) | iy (23 bits, biased) | normal code (4 bits); the
+// low 14 bits are left for the first point of a segment.  |coordinate / res| < 2^22 is checked on the host.
+__device__ __forceinline__ unsigned long long voxel_key(const scan_dev_params& P, float2 p, float2 nv) {
+  const int ix = __float2int_rz(fmul(p.x, P.inv_res)), iy = __float2int_rz(fmul(p.y, P.inv_res));
+  const int inx = __float2int_rz(nv.x), iny = __float2int_rz(nv.y);  // in {-1, 0, 1}
+  const unsigned long long bx = (unsigned) (ix + (1 << 22)) & 0x7FFFFFu, by = (unsigned) (iy + (1 << 22)) & 0x7FFFFFu;
+  return (bx << 41) | (by << 18) | ((unsigned long long) ((inx + 1) * 3 + (iny + 1)) << 14);
+}
+constexpr unsigned long long VOXEL_MASK = ~0x3FFFull;  // everything but the point index
+
+constexpr int SCAN_T = 384;  // threads per scan; at most 32 chunks => n_beams <= 12288 (and < 2^14: key layout)
+
+__global__ void __launch_bounds__(SCAN_T) preprocess_kernel(const scan_dev_params P, const scan_args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NB = P.n_beams;
   float2* xy                = reinterpret_cast<float2*>(smem_raw);                 // accepted beams, beam order
   float2* nrm               = xy + NB;                                             // their normals
-  unsigned long long* key1  = reinterpret_cast<unsigned long long*>(nrm + NB);     // [sort_cap] (ix, iy), biased
-  unsigned* key2            = reinterpret_cast<unsigned*>(key1 + P.sort_cap);      // [sort_cap] (inx, iny, index)
-  unsigned* valid           = key2 + P.sort_cap;                                   // [NB]
-  __shared__ int warp_tot[32];
-  __shared__ int base;
-  const int T = blockDim.x, tid = threadIdx.x;
+  unsigned long long* key   = reinterpret_cast<unsigned long long*>(nrm + NB);     // [sort_cap] segment: voxel key | first point
+  unsigned char* valid      = reinterpret_cast<unsigned char*>(key + P.sort_cap);  // [NB]
+  unsigned short* segend    = reinterpret_cast<unsigned short*>(valid + ((NB + 3) & ~3));  // [sort_cap] one past the last point
+  __shared__ int cnt[32 * (SCAN_T / 32)];
+  __shared__ int total;
+  const int T = SCAN_T, tid = threadIdx.x;
   const float* ranges = A.ranges + (size_t) blockIdx.x * NB;
   float4* out         = A.out + (size_t) blockIdx.x * NB;
+  const int beam_chunks = (NB + T - 1) / T;
 
-  // ---- PointNormal2fUnprojectorPolar, accepted beams only, beam order (P1)
-  if (tid == 0) base = 0;
-  __syncthreads();
-  for (int c0 = 0; c0 < NB; c0 += T) {
-    const int c = c0 + tid;
-    bool ok     = false;
-    float x = 0.f, y = 0.f;
-    if (c < NB) {
-      const float r = __ldg(ranges + c);
-      ok            = !(r < P.range_min || r > P.range_max);
-      if (ok) {
-        const float az = fmul(P.ifx, fsub((float) c, P.cx));
-        x              = fmul(r, cosf_glibc(az));
-        y              = fmul(r, sinf_glibc(az));
+  // ---- PointNormal2fUnprojectorPolar, accepted beams only, beam order (P1); staged through `nrm`
+  unsigned mask = 0;
+  for (int c = 0; c < beam_chunks; ++c) {
+    const int b = c * T + tid;
+    if (b < NB) {
+      const float r = __ldg(ranges + b);
+      if (!(r < P.range_min || r > P.range_max)) {
+        const float az = fmul(P.ifx, fsub((float) b, P.cx));
+        nrm[b]         = make_float2(fmul(r, cosf_glibc(az)), fmul(r, sinf_glibc(az)));
+        mask |= 1u << c;
       }
     }
-    const int dst = ordered_slot(ok, warp_tot, &base);
-    if (ok) xy[dst] = make_float2(x, y);
   }
-  const int n = base;
+  compact_count(mask, beam_chunks, cnt, &total);
+  for (int c = 0; c < beam_chunks; ++c) {
+    const int dst = compact_slot(mask, c, cnt);
+    if ((mask >> c) & 1u) xy[dst] = nrm[c * T + tid];
+  }
+  const int n = total;
   __syncthreads();
 
-  // ---- NormalComputator1DSlidingWindow (P2..P6): every point scans its own window
+  // ---- NormalComputator1DSlidingWindow (P2..P6): every point walks its own window
   for (int i = tid; i < n; i += T) {
     const float2 p = xy[i];
-    int lo = i, hi = i;
-    while (lo > 0) {
-      const float2 q = xy[lo - 1];
-      const float dx = fsub(q.x, p.x), dy = fsub(q.y, p.y);
-      if (!(fadd(fmul(dx, dx), fmul(dy, dy)) < P.d2)) break;
-      --lo;
+    const f2 np    = mk2(-p.x, -p.y);
+    // one walk over the window (down, then up): moments of d = q - p in walking order (P2, P4); the independent
+    // operations go out in pairs (FADD2 / FMUL2: same roundings)
+    f2 s1 = mk2(0.f, 0.f);  // sum dx, sum dy
+    float sxx = 0.f, sxy = 0.f, syy = 0.f;
+    int wn = 1;
+    for (int j = i - 1; j >= 0; --j) {
+      const float2 q = xy[j];
+      const f2 d  = add2(mk2(q.x, q.y), np);
+      const f2 dd = mul2(d, d);
+      if (!(fadd(dd.x, dd.y) < P.d2)) break;
+      s1  = add2(s1, d);
+      sxx = fadd(sxx, dd.x), sxy = fadd(sxy, fmul(d.x, d.y)), syy = fadd(syy, dd.y);
+      ++wn;
     }
-    while (hi + 1 < n) {
-      const float2 q = xy[hi + 1];
-      const float dx = fsub(q.x, p.x), dy = fsub(q.y, p.y);
-      if (!(fadd(fmul(dx, dx), fmul(dy, dy)) < P.d2)) break;
-      ++hi;
+    for (int j = i + 1; j < n; ++j) {
+      const float2 q = xy[j];
+      const f2 d  = add2(mk2(q.x, q.y), np);
+      const f2 dd = mul2(d, d);
+      if (!(fadd(dd.x, dd.y) < P.d2)) break;
+      s1  = add2(s1, d);
+      sxx = fadd(sxx, dd.x), sxy = fadd(sxy, fmul(d.x, d.y)), syy = fadd(syy, dd.y);
+      ++wn;
     }
-    const int cnt = hi - lo + 1;
-    const bool ok = cnt >= P.min_points;
+    const bool ok = wn >= P.min_points;
     float nx = 0.f, ny = 0.f;
     if (ok) {
-      float sx = 0.f, sy = 0.f;
-      for (int j = lo; j <= hi; ++j) {
-        const float2 q = xy[j];
-        sx = fadd(sx, q.x), sy = fadd(sy, q.y);
-      }
-      const float fc = (float) cnt;
-      const float mx = fdiv(sx, fc), my = fdiv(sy, fc);
-      float cxx = 0.f, cxy = 0.f, cyy = 0.f;
-      for (int j = lo; j <= hi; ++j) {
-        const float2 q = xy[j];
-        const float dx = fsub(q.x, mx), dy = fsub(q.y, my);
-        cxx = fadd(cxx, fmul(dx, dx)), cxy = fadd(cxy, fmul(dx, dy)), cyy = fadd(cyy, fmul(dy, dy));
-      }
-      cxx = fdiv(cxx, fc), cxy = fdiv(cxy, fc), cyy = fdiv(cyy, fc);
+      const float fc = (float) wn;
+      const float mx = fdiv(s1.x, fc), my = fdiv(s1.y, fc);
+      const float cxx = fsub(fdiv(sxx, fc), fmul(mx, mx)), cxy = fsub(fdiv(sxy, fc), fmul(mx, my)),
+                  cyy = fsub(fdiv(syy, fc), fmul(my, my));
       smallest_eigenvector_2x2(cxx, cxy, cyy, nx, ny);
       if (fadd(fmul(nx, p.x), fmul(ny, p.y)) > 0.f) nx = -nx, ny = -ny;
     }
     nrm[i]   = make_float2(nx, ny);
     valid[i] = ok;
   }
-  if (tid == 0) base = 0;
   __syncthreads();
+  const int pt_chunks = (n + T - 1) / T;
 
   if (P.inv_res == 0.f) {  // ---- valid points in cloud order (.cpp:44-48, P8)
-    for (int i0 = 0; i0 < n; i0 += T) {
-      const int i   = i0 + tid;
-      const bool ok = i < n && valid[i];
-      const int dst = ordered_slot(ok, warp_tot, &base);
-      if (ok) out[dst] = make_float4(xy[i].x, xy[i].y, nrm[i].x, nrm[i].y);
+    mask = 0;
+    for (int c = 0; c < pt_chunks; ++c) {
+      const int i = c * T + tid;
+      if (i < n && valid[i]) mask |= 1u << c;
     }
-    if (tid == 0) A.counts[blockIdx.x] = base;
+    compact_count(mask, pt_chunks, cnt, &total);
+    for (int c = 0; c < pt_chunks; ++c) {
+      const int i = c * T + tid, dst = compact_slot(mask, c, cnt);
+      if ((mask >> c) & 1u) out[dst] = make_float4(xy[i].x, xy[i].y, nrm[i].x, nrm[i].y);
+    }
+    if (tid == 0) A.counts[blockIdx.x] = total;
     return;
   }
 
-  // ---- voxelize (.cpp:38-42, P7): keys of the valid points, compacted
-  for (int i0 = 0; i0 < n; i0 += T) {
-    const int i   = i0 + tid;
-    const bool ok = i < n && valid[i];
-    const int dst = ordered_slot(ok, warp_tot, &base);
-    if (ok) {
-      const int ix = __float2int_rz(fmul(xy[i].x, P.inv_res)), iy = __float2int_rz(fmul(xy[i].y, P.inv_res));
-      const int inx = __float2int_rz(nrm[i].x), iny = __float2int_rz(nrm[i].y);  // in {-1, 0, 1}
-      key1[dst] = ((unsigned long long) ((unsigned) ix ^ 0x80000000u) << 32) | ((unsigned) iy ^ 0x80000000u);
-      key2[dst] = ((unsigned) ((inx + 1) * 3 + (iny + 1)) << 16) | (unsigned) i;
+  // ---- voxelize (.cpp:38-42, P7).  Consecutive valid points that share a voxel form a SEGMENT (neighbouring
+  // beams hit neighbouring places, so a scan has few hundred segments for ~1000 points); only the segments are
+  // sorted, by (voxel key, first point), and a voxel's sum walks its segments in that order = cloud order.
+  mask = 0;
+  for (int c = 0; c < pt_chunks; ++c) {  // segment heads: valid points whose previous valid point has another key
+    const int i = c * T + tid;
+    if (i < n && valid[i]) {
+      int prev = i - 1;
+      while (prev >= 0 && !valid[prev]) --prev;
+      const bool head = prev < 0 || voxel_key(P, xy[i], nrm[i]) != voxel_key(P, xy[prev], nrm[prev]);
+      if (head) mask |= 1u << c;
     }
   }
-  const int m = base;
+  compact_count(mask, pt_chunks, cnt, &total);
+  const int S = total;
   int cap     = 1;
-  while (cap < m) cap <<= 1;
-  for (int i = m + tid; i < cap; i += T) key1[i] = ~0ull, key2[i] = ~0u;
+  while (cap < S) cap <<= 1;
+  for (int c = 0; c < pt_chunks; ++c) {
+    const int i = c * T + tid, dst = compact_slot(mask, c, cnt);
+    if ((mask >> c) & 1u) key[dst] = voxel_key(P, xy[i], nrm[i]) | (unsigned long long) i;
+  }
   __syncthreads();
-  // bitonic sort, ascending by (key1, key2); key2 carries the cloud index, so equal voxels keep cloud order
+  for (int sgm = tid; sgm < S; sgm += T) segend[sgm] = (unsigned short) (sgm + 1 < S ? (int) (key[sgm + 1] & 0x3FFF) : n);
+  __syncthreads();
+  // bitonic sort of the S segments, ascending, in the all-ascending formulation (every merge starts with a "flip"
+  // stage, then half-cleaners): elements beyond S are virtual +infinity that never move, so only S slots exist.
+  // A thread always owns the same pair slots, and for spans of at most 64 both elements of a pair live in its
+  // warp's 64-element block: those stages need no block barrier.
   for (int k = 2; k <= cap; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
+      const int lx = j == (k >> 1) ? k - 1 : j;  // flip: partner = i ^ (k - 1); half-cleaner: partner = i | j
       for (int t = tid; t < (cap >> 1); t += T) {
-        const int i   = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int l   = i | j;
-        const bool up = (i & k) == 0;
-        const unsigned long long a1 = key1[i], b1 = key1[l];
-        const unsigned a2 = key2[i], b2 = key2[l];
-        if (key_less(b1, b2, a1, a2) == up) {
-          key1[i] = b1, key2[i] = b2;
-          key1[l] = a1, key2[l] = a2;
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i ^ lx;
+        if (l >= S) continue;
+        const unsigned long long a = key[i], b2 = key[l];
+        if (b2 < a) {
+          const unsigned short ea = segend[i], eb = segend[l];
+          key[i] = b2, segend[i] = eb;
+          key[l] = a, segend[l] = ea;
         }
       }
-      __syncthreads();
+      // next stage: the flip of merge 2k (span 2k) after j == 1, else a half-cleaner of span j
+      const int span_now = lx == j ? 2 * j : k, span_next = j == 1 ? 2 * k : j;
+      if (span_now > 64 || span_next > 64)
+        __syncthreads();
+      else
+        __syncwarp();
     }
-  // one output point per run of equal keys: the run's head sums its members in sorted (= cloud) order
-  if (tid == 0) base = 0;
   __syncthreads();
-  for (int t0 = 0; t0 < m; t0 += T) {
-    const int t     = t0 + tid;
-    const bool head = t < m && (t == 0 || key1[t] != key1[t - 1] || (key2[t] >> 16) != (key2[t - 1] >> 16));
-    float4 o        = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (head) {
-      const unsigned long long k1 = key1[t];
-      const unsigned k2           = key2[t] >> 16;
-      int e = t;
-      for (; e < m && key1[e] == k1 && (key2[e] >> 16) == k2; ++e) {
-        const int i = key2[e] & 0xFFFF;
+  // one output point per run of equal voxel keys: the run's first segment sums all members in sorted (= cloud) order
+  const int seg_chunks = (S + T - 1) / T;
+  mask = 0;
+  for (int c = 0; c < seg_chunks; ++c) {
+    const int t = c * T + tid;
+    if (t < S && (t == 0 || ((key[t] ^ key[t - 1]) & VOXEL_MASK) != 0)) mask |= 1u << c;
+  }
+  compact_count(mask, seg_chunks, cnt, &total);
+  for (int c = 0; c < seg_chunks; ++c) {
+    const int t = c * T + tid, dst = compact_slot(mask, c, cnt);
+    if (!((mask >> c) & 1u)) continue;
+    const unsigned long long vk = key[t] & VOXEL_MASK;
+    float4 o  = make_float4(0.f, 0.f, 0.f, 0.f);
+    int count = 0;
+    for (int e = t; e < S && (key[e] & VOXEL_MASK) == vk; ++e) {
+      const int end = segend[e];
+      for (int i = (int) (key[e] & 0x3FFF); i < end; ++i) {
+        if (!valid[i]) continue;
         o.x = fadd(o.x, xy[i].x), o.y = fadd(o.y, xy[i].y), o.z = fadd(o.z, nrm[i].x), o.w = fadd(o.w, nrm[i].y);
-      }
-      const float w = fdiv(1.f, (float) (e - t));
-      o.x = fmul(o.x, w), o.y = fmul(o.y, w), o.z = fmul(o.z, w), o.w = fmul(o.w, w);
-      const float z = fadd(fmul(o.z, o.z), fmul(o.w, o.w));
-      if (z > 0.f) {
-        const float nn = fsqrt(z);
-        o.z = fdiv(o.z, nn), o.w = fdiv(o.w, nn);
+        ++count;
       }
     }
-    const int dst = ordered_slot(head, warp_tot, &base);
-    if (head) out[dst] = o;
+    const float w = fdiv(1.f, (float) count);
+    o.x = fmul(o.x, w), o.y = fmul(o.y, w), o.z = fmul(o.z, w), o.w = fmul(o.w, w);
+    const float z = fadd(fmul(o.z, o.z), fmul(o.w, o.w));
+    if (z > 0.f) {
+      const float nn = fsqrt(z);
+      o.z = fdiv(o.z, nn), o.w = fdiv(o.w, nn);
+    }
+    out[dst] = o;
   }
-  if (tid == 0) A.counts[blockIdx.x] = base;
+  if (tid == 0) A.counts[blockIdx.x] = total;
 }
 
 // exclusive scan of counts[n] -> off[n + 1]; one CTA, chunks of blockDim.x
