@@ -99,3 +99,29 @@ def test_merger_rejects_too_small_capacity(handle_factory):
     rc = h._L.ls2d_merge_scene(h._h, scene.ctypes.data_as(C.c_void_p), C.byref(size), 100, None, 0,
                                np.zeros(3, np.float32).ctypes.data_as(C.c_void_p), 0.2, None)
     assert rc == -1
+
+
+def test_tracker_rows_golden(handle_factory):
+    """frozen fixture of the rows around the aligner (tests/golden/tracker_721_l0.npz): raw scans -> pre-processor ->
+    clipper -> merger on the device, bit for bit"""
+    from srrg2_laser_slam_2d_b200._abi import default_scan_params
+    d = gu.load_raw("tracker_721_l0")
+    kw = dict(angle_min=float(d["angles"][0]), angle_max=float(d["angles"][1]))
+    h = handle_factory(default_params(canvas_cols=721))
+    meas, cm = h.preprocess_scans(default_scan_params(**kw), d["fixed_ranges"])
+    scene, cs = h.preprocess_scans(default_scan_params(voxelize_resolution=0.0, **kw), d["moving_ranges"])
+    scenes = [scene[k, :cs[k]] for k in range(3)]
+    off = np.concatenate([[0], np.cumsum(cs)]).astype(np.int32)
+    h.upload_clouds(2, np.concatenate(scenes), off)
+    clips = h.clip_scenes(2, [0, 1, 2], d["robot_in_local_map"], d["sensor_in_robot"])
+    for k in range(3):
+        assert np.array_equal(gu.bits(meas[k, :cm[k]]), gu.bits(d[f"meas_{k}"]))
+        assert np.array_equal(gu.bits(scenes[k]), gu.bits(d[f"scene_{k}"]))
+        assert np.array_equal(gu.bits(clips[k]), gu.bits(d[f"clip_{k}"]))
+        merged, counters = h.merge_scene(scenes[k], meas[k, :cm[k]], d["gt_xyt"][k], 0.2)
+        assert np.array_equal(gu.bits(merged), gu.bits(d[f"merged_{k}"]))
+        assert np.array_equal(counters, d[f"merge_counters_{k}"])
+    fx = default_scan_params(angle_min=-1.0, angle_max=1.0, msg_range_min=0.0, msg_range_max=1000.0, range_min=0.0,
+                             range_max=1000.0, voxelize_resolution=0.01)
+    cloud, n = h.preprocess_scans(fx, np.full((1, 100), 1.0, np.float32))
+    assert n[0] == 100 and np.array_equal(gu.bits(cloud[0, :100]), gu.bits(d["synthetic_fixture_cloud"]))

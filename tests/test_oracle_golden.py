@@ -64,3 +64,23 @@ def test_oracle_reproduces_multi_slice_golden(oracle):
     assert res.tobytes() == d["results_no_prior"].tobytes() and its.tobytes() == d["iters_no_prior"].tobytes()
     assert (d["results"]["status"] == 0).all()
     assert np.abs(np.stack([d["results"][k] for k in ("x", "y", "theta")], 1) - d["gt_xyt"]).max() < 5e-3
+
+
+def test_oracle_reproduces_tracker_rows_golden(oracle):
+    """pre-processor -> clipper -> merger fixture (tools/make_golden.py --mapping-only), LASER_0.json values"""
+    d = gu.load_raw("tracker_721_l0")
+    kw = dict(angle_min=float(d["angles"][0]), angle_max=float(d["angles"][1]))
+    sp_vox, sp_full = oracle.default_scan_params(**kw), oracle.default_scan_params(voxelize_resolution=0.0, **kw)
+    prm = oracle.default_params(canvas_cols=721)
+    for k in range(3):
+        meas = oracle.preprocess_scan(sp_vox, d["fixed_ranges"][k])
+        scene = oracle.preprocess_scan(sp_full, d["moving_ranges"][k])
+        assert np.array_equal(gu.bits(meas), gu.bits(d[f"meas_{k}"]))
+        assert np.array_equal(gu.bits(scene), gu.bits(d[f"scene_{k}"]))
+        clip = oracle.clip_scene(prm, scene, d["robot_in_local_map"][k], d["sensor_in_robot"])
+        assert np.array_equal(gu.bits(clip), gu.bits(d[f"clip_{k}"]))
+        merged, counters = oracle.merge(prm, 0.2, scene, meas, d["gt_xyt"][k])
+        assert np.array_equal(gu.bits(merged), gu.bits(d[f"merged_{k}"]))
+        assert np.array_equal(counters, d[f"merge_counters_{k}"])
+        assert 50 < len(meas) <= len(scene) <= 721 and counters[1] > 0       # voxelisation shrinks, merging merges
+    assert len(d["synthetic_fixture_cloud"]) == 100                        # the reference's own pinned count

@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_binding as ob  # noqa: E402
-from srrg2_laser_slam_2d_b200.synthetic import make_multi_sensor_pairs, make_scan_pairs, reference_demo_scene  # noqa: E402
+from srrg2_laser_slam_2d_b200.synthetic import (make_multi_sensor_pairs, make_raw_scans, make_scan_pairs,  # noqa: E402
+                                                reference_demo_scene)
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -73,11 +74,42 @@ def make_multi():
           "err", np.abs(np.stack([res["x"], res["y"], res["theta"]], 1) - msp.gt_xyt).max())
 
 
+def make_mapping():
+    """tracker_721_l0.npz: the rows around the aligner with the LASER_0.json values -- raw 721-beam
+    scans -> RawDataPreprocessorProjective2D (voxelize 0.02 and off) -> SceneClipperProjective2D of a local map ->
+    MergerProjective2D of the measurement into it; plus the reference's own Synthetic fixture (100 points)."""
+    raw = make_raw_scans(3, n_beams=721, seed=107)
+    kw = dict(angle_min=raw.angle_min, angle_max=raw.angle_max)
+    sp_vox, sp_full = ob.default_scan_params(**kw), ob.default_scan_params(voxelize_resolution=0.0, **kw)
+    prm = ob.default_params(canvas_cols=721)
+    out = dict(fixed_ranges=raw.fixed_ranges, moving_ranges=raw.moving_ranges,
+               angles=np.array([raw.angle_min, raw.angle_max], np.float32), gt_xyt=raw.gt_xyt,
+               robot_in_local_map=np.array([[0.01, -0.02, 0.015]] * 3, np.float32),
+               sensor_in_robot=np.array([0.2, 0.2, 0.1], np.float32))   # synthetic_scene_generator.cpp:77
+    for k in range(3):
+        meas = ob.preprocess_scan(sp_vox, raw.fixed_ranges[k])
+        scene = ob.preprocess_scan(sp_full, raw.moving_ranges[k])
+        clip = ob.clip_scene(prm, scene, out["robot_in_local_map"][k], out["sensor_in_robot"])
+        merged, counters = ob.merge(prm, 0.2, scene, meas, raw.gt_xyt[k])
+        out.update({f"meas_{k}": meas, f"scene_{k}": scene, f"clip_{k}": clip, f"merged_{k}": merged,
+                    f"merge_counters_{k}": counters})
+        print("tracker_721_l0[%d]: %d beams -> %d (voxel 0.02) / %d (full); clip %d; merge %s -> %d" %
+              (k, 721, len(meas), len(scene), len(clip), counters, len(merged)))
+    fx = ob.default_scan_params(angle_min=-1.0, angle_max=1.0, msg_range_min=0.0, msg_range_max=1000.0, range_min=0.0,
+                                range_max=1000.0, voxelize_resolution=0.01)  # tests/fixtures.hpp:38-47
+    out["synthetic_fixture_cloud"] = ob.preprocess_scan(fx, np.full(100, 1.0, np.float32))
+    assert len(out["synthetic_fixture_cloud"]) == 100                      # tests/test_measurement_adaptor.cpp:36
+    np.savez_compressed(os.path.join(OUT, "tracker_721_l0.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--mapping-only" in sys.argv:
+        return make_mapping()
     if "--multi-only" in sys.argv:
         return make_multi()
     make_multi()
+    make_mapping()
     for name, (gen, prm_kw) in CASES.items():
         sp = make_scan_pairs(**gen)
         prm = ob.default_params(**prm_kw)
