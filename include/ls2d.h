@@ -250,8 +250,8 @@ int ls2d_verify_sharded_nccl(ls2d_handle* h, int32_t query_id, const int32_t* ca
                              int32_t n_ranks, ls2d_best* best);
 
 /* ---- local-map maintenance around the aligner -------------------------------
- * replaces: SceneClipperProjective2D::compute with voxelize_resolution == 0, the value both shipped
- * configurations use (R/mapping/scene_clipper_projective_2d.cpp:11-65): for request r the scene cloud
+ * replaces: SceneClipperProjective2D::compute (R/mapping/scene_clipper_projective_2d.cpp:11-65) with
+ * voxelize_resolution == 0, the value both shipped configurations use: for request r the scene cloud
  * cloud_ids[r] of set `which` is seen from robot_in_local_map[r] * sensor_in_robot; the z-buffer winners, in
  * column order, come back as points in the ROBOT frame: out_points [n * canvas_cols * 4], out_counts [n]. */
 int ls2d_clip_scenes(ls2d_handle* h, int which, const int32_t* cloud_ids, const float* robot_in_local_map_xyt,
@@ -301,6 +301,12 @@ int ls2d_preprocess_scans_to_set_dev(ls2d_handle* h, int which, const ls2d_scan_
 int ls2d_download_clouds(ls2d_handle* h, int which, float* points, int32_t* offsets, int32_t n_clouds,
                          int64_t capacity_points);
 
+/* the clipper's voxelize branch (.cpp:36-48): the winners, as points in the sensor frame, are voxelized with
+ * res_coeffs (voxelize_resolution, voxelize_resolution, 0.1, 0.1) before the move to the robot frame;
+ * voxelize_resolution <= 0 behaves like ls2d_clip_scenes */
+int ls2d_clip_scenes_voxelized(ls2d_handle* h, int which, const int32_t* cloud_ids,
+                               const float* robot_in_local_map_xyt, const float* sensor_in_robot_xyt, int32_t n,
+                               float voxelize_resolution, float* out_points, int32_t* out_counts);
 /* device-resident clipper: same clip as ls2d_clip_scenes, but the clipped clouds become cloud set `out_set`
  * (packed CSR, out_set != scene_set) without leaving the device -- the tracker's moving clouds */
 int ls2d_clip_scenes_to_set(ls2d_handle* h, int scene_set, const int32_t* cloud_ids,

@@ -803,20 +803,24 @@ void orc_column_n(const orc_params* prm, const float* y, const float* x, int32_t
  *     four fields, normalize() renormalises the normal only, with Eigen's rule (divide by sqrt(squaredNorm)
  *     when squaredNorm > 0). */
 
+/* voxelize_cloud is defined with the pre-processor below */
+static int32_t voxelize_cloud(const orc_point* pts, const uint8_t* valid, int32_t n, const float* inv, orc_point* out);
+
 static int iso_is_identity(orc_iso T) {
   return T.c == 1.f && T.s == 0.f && T.tx == 0.f && T.ty == 0.f;
 }
 
-/* SceneClipperProjective2D::compute with voxelize_resolution == 0 (both shipped configurations)
- * R/mapping/scene_clipper_projective_2d.cpp:22-62.  out holds canvas_cols points; returns the count. */
-int32_t orc_clip_scene(const orc_params* prm, const orc_point* scene, int32_t n_scene,
-                       orc_iso robot_in_local_map, orc_iso sensor_in_robot, orc_point* out) {
+/* SceneClipperProjective2D::compute, R/mapping/scene_clipper_projective_2d.cpp:22-62 (both shipped configurations
+ * set voxelize_resolution 0).  out holds canvas_cols points; returns the count. */
+int32_t orc_clip_scene_voxelized(const orc_params* prm, const orc_point* scene, int32_t n_scene,
+                                 orc_iso robot_in_local_map, orc_iso sensor_in_robot, float voxelize_resolution,
+                                 orc_point* out) {
   const int32_t C = prm->canvas_cols;
   orc_cell* img   = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
   const orc_iso sensor_in_local_map = orc_compose(robot_in_local_map, sensor_in_robot); /* :29 */
   orc_project(prm, sensor_in_local_map, scene, n_scene, img);                             /* :31-32 */
   int32_t k = 0;
-  for (int32_t c = 0; c < C; ++c) { /* :50-56 */
+  for (int32_t c = 0; c < C; ++c) { /* :38-43 / :50-56 */
     if (img[c].source_idx < 0) {
       continue;
     }
@@ -825,6 +829,13 @@ int32_t orc_clip_scene(const orc_params* prm, const orc_point* scene, int32_t n_
     out[k].nx = img[c].nx;
     out[k].ny = img[c].ny;
     ++k;
+  }
+  if (voxelize_resolution > 0.f) { /* :36-48: voxelize(res_coeffs = (res, res, 0.1, 0.1)) of the points in the sensor */
+    orc_point* tmp = (orc_point*) malloc(sizeof(orc_point) * (size_t)(k > 0 ? k : 1));
+    memcpy(tmp, out, sizeof(orc_point) * (size_t) k);
+    const float inv[4] = {1.f / voxelize_resolution, 1.f / voxelize_resolution, 1.f / 0.1f, 1.f / 0.1f};
+    k = voxelize_cloud(tmp, NULL, k, inv, out);
+    free(tmp);
   }
   if (!iso_is_identity(sensor_in_robot)) { /* :60-62 move the local scene in robot's coords */
     for (int32_t i = 0; i < k; ++i) {
@@ -836,6 +847,11 @@ int32_t orc_clip_scene(const orc_params* prm, const orc_point* scene, int32_t n_
   }
   free(img);
   return k;
+}
+
+int32_t orc_clip_scene(const orc_params* prm, const orc_point* scene, int32_t n_scene,
+                       orc_iso robot_in_local_map, orc_iso sensor_in_robot, orc_point* out) {
+  return orc_clip_scene_voxelized(prm, scene, n_scene, robot_in_local_map, sensor_in_robot, 0.f, out);
 }
 
 /* MergerProjective2D::compute, R/mapping/merger_projective_2d.cpp:9-100.  `scene` must have room for
@@ -946,6 +962,48 @@ static int vox_cmp(const void* a, const void* b) {
     }
   }
   return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+/* PointCloud::voxelize(out, res_coeffs) (P7): valid points only; `valid` may be NULL (all valid).  inv[4] = the
+ * inverse scales of the plain vector (x, y, nx, ny).  Returns the number of points written to out. */
+static int32_t voxelize_cloud(const orc_point* pts, const uint8_t* valid, int32_t n, const float* inv, orc_point* out) {
+  vox_entry* e = (vox_entry*) malloc(sizeof(vox_entry) * (size_t)(n > 0 ? n : 1));
+  int32_t m = 0, k = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    if (valid && !valid[i]) {
+      continue;
+    }
+    e[m].k[0] = (int32_t)(pts[i].x * inv[0]);
+    e[m].k[1] = (int32_t)(pts[i].y * inv[1]);
+    e[m].k[2] = (int32_t)(pts[i].nx * inv[2]);
+    e[m].k[3] = (int32_t)(pts[i].ny * inv[3]);
+    e[m].idx  = i;
+    ++m;
+  }
+  qsort(e, (size_t) m, sizeof(vox_entry), vox_cmp);
+  int32_t s = 0;
+  while (s < m) {
+    int32_t t = s;
+    float ax = 0.f, ay = 0.f, anx = 0.f, any = 0.f;
+    while (t < m && e[t].k[0] == e[s].k[0] && e[t].k[1] == e[s].k[1] && e[t].k[2] == e[s].k[2] &&
+           e[t].k[3] == e[s].k[3]) {
+      const orc_point* p = &pts[e[t].idx];
+      ax = ax + p->x, ay = ay + p->y, anx = anx + p->nx, any = any + p->ny;
+      ++t;
+    }
+    const float w = 1.f / (float) (t - s);
+    ax = ax * w, ay = ay * w, anx = anx * w, any = any * w;
+    const float z = anx * anx + any * any;
+    if (z > 0.f) {
+      const float nrm = sqrtf(z);
+      anx = anx / nrm, any = any / nrm;
+    }
+    out[k].x = ax, out[k].y = ay, out[k].nx = anx, out[k].ny = any;
+    ++k;
+    s = t;
+  }
+  free(e);
+  return k;
 }
 
 void orc_default_scan_params(orc_scan_params* p) {
@@ -1070,44 +1128,9 @@ int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int3
     pts[i].nx = nx, pts[i].ny = ny;
   }
   int32_t k = 0;
-  if (sp->voxelize_resolution > 0.f) { /* .cpp:38-42, P7 */
-    const float inv = 1.f / sp->voxelize_resolution;
-    vox_entry* e    = (vox_entry*) malloc(sizeof(vox_entry) * (size_t)(n > 0 ? n : 1));
-    int32_t m = 0;
-    for (int32_t i = 0; i < n; ++i) {
-      if (!valid[i]) {
-        continue;
-      }
-      e[m].k[0] = (int32_t)(pts[i].x * inv);
-      e[m].k[1] = (int32_t)(pts[i].y * inv);
-      e[m].k[2] = (int32_t)(pts[i].nx * 1.f);
-      e[m].k[3] = (int32_t)(pts[i].ny * 1.f);
-      e[m].idx  = i;
-      ++m;
-    }
-    qsort(e, (size_t) m, sizeof(vox_entry), vox_cmp);
-    int32_t s = 0;
-    while (s < m) {
-      int32_t t = s;
-      float ax = 0.f, ay = 0.f, anx = 0.f, any = 0.f;
-      while (t < m && e[t].k[0] == e[s].k[0] && e[t].k[1] == e[s].k[1] && e[t].k[2] == e[s].k[2] &&
-             e[t].k[3] == e[s].k[3]) {
-        const orc_point* p = &pts[e[t].idx];
-        ax = ax + p->x, ay = ay + p->y, anx = anx + p->nx, any = any + p->ny;
-        ++t;
-      }
-      const float w = 1.f / (float) (t - s);
-      ax = ax * w, ay = ay * w, anx = anx * w, any = any * w;
-      const float z = anx * anx + any * any;
-      if (z > 0.f) {
-        const float nrm = sqrtf(z);
-        anx = anx / nrm, any = any / nrm;
-      }
-      out[k].x = ax, out[k].y = ay, out[k].nx = anx, out[k].ny = any;
-      ++k;
-      s = t;
-    }
-    free(e);
+  if (sp->voxelize_resolution > 0.f) { /* .cpp:38-42, P7: res_coeffs = (res, res, 1, 1) */
+    const float inv[4] = {1.f / sp->voxelize_resolution, 1.f / sp->voxelize_resolution, 1.f / 1.f, 1.f / 1.f};
+    k = voxelize_cloud(pts, valid, n, inv, out);
   } else { /* .cpp:44-48, P8 */
     for (int32_t i = 0; i < n; ++i) {
       if (valid[i]) {

@@ -186,6 +186,12 @@ int32_t orc_max_threads(void);
 int32_t orc_clip_scene(const orc_params* prm, const orc_point* scene, int32_t n_scene,
                        orc_iso robot_in_local_map, orc_iso sensor_in_robot, orc_point* out);
 
+/* the same with the clipper's voxelize branch (.cpp:36-48: res_coeffs (res, res, 0.1, 0.1), applied to the
+ * points in the sensor frame, before the move to the robot frame); voxelize_resolution <= 0: orc_clip_scene */
+int32_t orc_clip_scene_voxelized(const orc_params* prm, const orc_point* scene, int32_t n_scene,
+                                 orc_iso robot_in_local_map, orc_iso sensor_in_robot, float voxelize_resolution,
+                                 orc_point* out);
+
 /* MergerProjective2D::compute: merges `measurement` into `scene` (room for n_scene + canvas_cols points
  * required); counters = {new, merged, replaced} (nullable); returns the new scene size */
 int32_t orc_merge(const orc_params* prm, float merge_threshold, orc_point* scene, int32_t n_scene,

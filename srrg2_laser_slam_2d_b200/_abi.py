@@ -80,6 +80,7 @@ EXPORTS = [
     "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
     "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
     "ls2d_clip_scenes_to_set", "ls2d_track_batch", "ls2d_verify_pairs", "ls2d_verify_pairs_dev",
+    "ls2d_clip_scenes_voxelized",
 ]
 
 _lib = None
@@ -131,6 +132,7 @@ def load():
     L.ls2d_preprocess_scans_to_set.argtypes = [vp, C.c_int, SP, vp, i32, i32]
     L.ls2d_preprocess_scans_to_set_dev.argtypes = [vp, C.c_int, SP, vp, i32, i32]
     L.ls2d_download_clouds.argtypes = [vp, C.c_int, vp, vp, i32, i64]
+    L.ls2d_clip_scenes_voxelized.argtypes = [vp, C.c_int, vp, vp, vp, i32, f32, vp, vp]
     L.ls2d_clip_scenes_to_set.argtypes = [vp, C.c_int, vp, vp, vp, i32, C.c_int]
     L.ls2d_track_batch.argtypes = [vp, SP, vp, i32, i32, C.c_int, vp, vp, vp, vp]
     L.ls2d_reduction_threads.argtypes = [i32]
@@ -327,15 +329,20 @@ class Handle:
         return idx, depth
 
     # ---- local-map maintenance
-    def clip_scenes(self, which: int, cloud_ids, robot_in_local_map_xyt, sensor_in_robot_xyt=(0.0, 0.0, 0.0)):
-        """SceneClipperProjective2D (voxelize off): returns a list of clipped clouds [k_r, 4] in the robot frame."""
+    def clip_scenes(self, which: int, cloud_ids, robot_in_local_map_xyt, sensor_in_robot_xyt=(0.0, 0.0, 0.0),
+                    voxelize_resolution: float = 0.0):
+        """SceneClipperProjective2D: returns a list of clipped clouds [k_r, 4] in the robot frame."""
         ids = _i32(cloud_ids)
         rob = _f32(robot_in_local_map_xyt).reshape(-1, 3)
         sen = _f32(sensor_in_robot_xyt)
         n, cols = len(ids), self.params.canvas_cols
         out = np.zeros((n, cols, 4), np.float32)
         cnt = np.zeros(n, np.int32)
-        self._check(self._L.ls2d_clip_scenes(self._h, which, _ptr(ids), _ptr(rob), _ptr(sen), n, _ptr(out), _ptr(cnt)))
+        if voxelize_resolution > 0:
+            self._check(self._L.ls2d_clip_scenes_voxelized(self._h, which, _ptr(ids), _ptr(rob), _ptr(sen), n,
+                                                           voxelize_resolution, _ptr(out), _ptr(cnt)))
+        else:
+            self._check(self._L.ls2d_clip_scenes(self._h, which, _ptr(ids), _ptr(rob), _ptr(sen), n, _ptr(out), _ptr(cnt)))
         return [out[r, :cnt[r]].copy() for r in range(n)]
 
     def merge_scene(self, scene: np.ndarray, measurement: np.ndarray, measurement_in_scene_xyt, merge_threshold: float = 0.2):

@@ -1014,8 +1014,8 @@ static int preprocess_dev(ls2d_handle* h, const ls2d_scan_params* sp, const floa
   P.sort_cap             = 0;
   if (P.inv_res != 0.f) {
     P.sort_cap = (n_beams + 3) & ~3;
-    // the packed voxel key holds |coordinate / res| < 2^22 (coordinates are bounded by the range limit)
-    if (!(P.range_max * P.inv_res < 4194304.f)) return LS2D_ERR_UNSUPPORTED;
+    // the packed voxel key holds |coordinate / res| < 2^19 (coordinates are bounded by the range limit)
+    if (!(P.range_max * P.inv_res < 524288.f)) return LS2D_ERR_UNSUPPORTED;
   }
   scan_args a;
   a.ranges  = ranges_dev;
@@ -1135,7 +1135,8 @@ int ls2d_download_clouds(ls2d_handle* h, int which, float* points, int32_t* offs
 
 // clip_kernel into scratch `tmp` (strided rows of canvas_cols points + counts); ids / poses already on the device
 static int clip_dev(ls2d_handle* h, const cloud_set& c, const int* ids_dev, const float* robot_dev,
-                    const float* sensor_xyt, int32_t n, scratch& tmp, float4** out, int** counts) {
+                    const float* sensor_xyt, int32_t n, scratch& tmp, float4** out, int** counts,
+                    float voxelize_resolution = 0.f) {
   const int C = h->dp.cam.cols;
   int rc;
   const size_t out_bytes = sizeof(float4) * (size_t) n * C;
@@ -1148,13 +1149,47 @@ static int clip_dev(ls2d_handle* h, const cloud_set& c, const int* ids_dev, cons
   memcpy(a.sensor_xyt, sensor_xyt, sizeof(float) * 3);
   a.out    = (float4*) tmp.p;
   a.counts = (int*) ((char*) tmp.p + out_bytes);
-  const size_t smem = sizeof(unsigned) * 2 * (size_t) C;
-  CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  clip_kernel<<<n, 256, smem, h->stream>>>(h->dp, a);
+  if (voxelize_resolution > 0.f) {  // scene_clipper_projective_2d.cpp:36-48
+    const float inv_res = 1.f / voxelize_resolution;
+    // the packed voxel key holds |coordinate / res| < 2^19 (coordinates are bounded by the range limit)
+    if (!(h->dp.range_max * inv_res < 524288.f) || C > 32 * SCAN_T) return LS2D_ERR_UNSUPPORTED;
+    const size_t smem = clip_voxel_smem_bytes(C);
+    CU(cudaFuncSetAttribute(clip_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    clip_voxel_kernel<<<n, SCAN_T, smem, h->stream>>>(h->dp, a, inv_res);
+  } else {
+    const size_t smem = sizeof(unsigned) * 2 * (size_t) C;
+    CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    clip_kernel<<<n, 256, smem, h->stream>>>(h->dp, a);
+  }
   CU(cudaGetLastError());
   h->launches++;
   *out    = a.out;
   *counts = a.counts;
+  return LS2D_OK;
+}
+
+int ls2d_clip_scenes_voxelized(ls2d_handle* h, int which, const int32_t* cloud_ids, const float* robot_xyt,
+                               const float* sensor_xyt, int32_t n, float voxelize_resolution, float* out_points,
+                               int32_t* out_counts) {
+  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !cloud_ids || !robot_xyt || !sensor_xyt || !out_points || !out_counts || n < 0)
+    return LS2D_ERR_INVALID;
+  const cloud_set& c = h->sets[which];
+  if (!c.pts || !c.off) return LS2D_ERR_NOT_READY;
+  if (n == 0) return LS2D_OK;
+  for (int i = 0; i < n; ++i)
+    if (cloud_ids[i] < 0 || cloud_ids[i] >= c.n_clouds) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = h2d(h, h->d_mid, cloud_ids, sizeof(int) * (size_t) n))) return rc;
+  if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * 3 * (size_t) n))) return rc;
+  float4* d_out = nullptr;
+  int* d_cnt    = nullptr;
+  if ((rc = clip_dev(h, c, (const int*) h->d_mid.p, (const float*) h->d_init.p, sensor_xyt, n, h->d_clip, &d_out, &d_cnt,
+                     voxelize_resolution)))
+    return rc;
+  CU(cudaMemcpyAsync(out_points, d_out, sizeof(float4) * (size_t) n * h->dp.cam.cols, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(out_counts, d_cnt, sizeof(int) * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return LS2D_OK;
 }
 

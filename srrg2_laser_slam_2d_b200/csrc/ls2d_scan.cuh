@@ -39,7 +39,7 @@ struct scan_args {
 };
 
 constexpr size_t scan_smem_bytes(int n_beams, int sort_cap) {
-  return (size_t) n_beams * (8 + 8) + (size_t) ((n_beams + 3) & ~3) + (size_t) sort_cap * (8 + 2) + 64;
+  return (size_t) n_beams * (8 + 8) + (size_t) ((n_beams + 3) & ~3) + (size_t) sort_cap * 8 + 64;
 }
 
 // Eigen 3.3 SelfAdjointEigenSolver<Matrix2f>::computeDirect: eigenvector of the smallest eigenvalue (P5)
@@ -117,16 +117,111 @@ __device__ __forceinline__ int compact_slot(unsigned mask, int c, const int* cnt
   return cnt[c * nwarp + warp] + __popc(ballot & ((1u << lane) - 1u));
 }
 
-// voxel key of a point (P7): trunc-toward-zero of (x, y, nx, ny) * (1/res, 1/res, 1, 1), packed so that unsigned
-// order = the oracle's lexicographic order: ix (23 bits, biased) | iy (23 bits, biased) | normal code (4 bits); the
-// low 14 bits are left for the first point of a segment.  |coordinate / res| < 2^22 is checked on the host.
-__device__ __forceinline__ unsigned long long voxel_key(const scan_dev_params& P, float2 p, float2 nv) {
-  const int ix = __float2int_rz(fmul(p.x, P.inv_res)), iy = __float2int_rz(fmul(p.y, P.inv_res));
-  const int inx = __float2int_rz(nv.x), iny = __float2int_rz(nv.y);  // in {-1, 0, 1}
-  const unsigned long long bx = (unsigned) (ix + (1 << 22)) & 0x7FFFFFu, by = (unsigned) (iy + (1 << 22)) & 0x7FFFFFu;
-  return (bx << 41) | (by << 18) | ((unsigned long long) ((inx + 1) * 3 + (iny + 1)) << 14);
+// voxelize(res_coeffs) parameters: inverse scales of (x, y) and of the normal, nb = bound of |trunc(n * inv_n)|
+struct voxel_params {
+  float inv_res, inv_n;
+  int nb;
+};
+
+// voxel key of a point (P7): trunc-toward-zero of (x, y, nx, ny) * (1/res, 1/res, inv_n, inv_n), packed so that unsigned
+// order = the oracle's lexicographic order: ix (20 bits, biased) | iy (20 bits, biased) | normal code (10 bits); the
+// low 14 bits are left for the first point of a segment.  |coordinate / res| < 2^19 is checked on the host; normal
+// cells are clamped to +-nb (unit normals never leave that range).
+__device__ __forceinline__ unsigned long long voxel_key(const voxel_params& V, float2 p, float2 nv) {
+  const int ix = __float2int_rz(fmul(p.x, V.inv_res)), iy = __float2int_rz(fmul(p.y, V.inv_res));
+  const int inx = max(-V.nb, min(V.nb, __float2int_rz(fmul(nv.x, V.inv_n))));
+  const int iny = max(-V.nb, min(V.nb, __float2int_rz(fmul(nv.y, V.inv_n))));
+  const unsigned long long bx = (unsigned) (ix + (1 << 19)) & 0xFFFFFu, by = (unsigned) (iy + (1 << 19)) & 0xFFFFFu;
+  return (bx << 44) | (by << 24) | ((unsigned long long) ((inx + V.nb) * (2 * V.nb + 1) + (iny + V.nb)) << 14);
 }
 constexpr unsigned long long VOXEL_MASK = ~0x3FFFull;  // everything but the point index
+
+// Block-wide voxelize of the n points (xy, nrm) with flags valid (nullptr: all valid), in place in shared memory:
+// consecutive valid points that share a voxel form a SEGMENT (neighbouring beams hit neighbouring places); only the
+// segments are sorted, by (voxel key, first point), and a voxel's sum walks its segments in that order = cloud
+// order.  emit(slot, point) receives the output points in sorted order; returns their number (to every thread).
+// key: n slots of shared memory, cnt / total: the compaction scratch.  Needs n <= 32 * blockDim.x and n < 2^14.
+template <typename Emit>
+__device__ __forceinline__ int block_voxelize(const voxel_params& V, const float2* xy, const float2* nrm,
+                                              const unsigned char* valid, int n, unsigned long long* key, int* cnt,
+                                              int* total, Emit emit) {
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int pt_chunks = (n + T - 1) / T;
+  unsigned mask = 0;
+  for (int c = 0; c < pt_chunks; ++c) {  // segment heads: valid points whose previous valid point has another key
+    const int i = c * T + tid;
+    if (i < n && (!valid || valid[i])) {
+      int prev = i - 1;
+      while (valid && prev >= 0 && !valid[prev]) --prev;
+      const bool head = prev < 0 || voxel_key(V, xy[i], nrm[i]) != voxel_key(V, xy[prev], nrm[prev]);
+      if (head) mask |= 1u << c;
+    }
+  }
+  compact_count(mask, pt_chunks, cnt, total);
+  const int S = *total;
+  int cap     = 1;
+  while (cap < S) cap <<= 1;
+  for (int c = 0; c < pt_chunks; ++c) {
+    const int i = c * T + tid, dst = compact_slot(mask, c, cnt);
+    if ((mask >> c) & 1u) key[dst] = voxel_key(V, xy[i], nrm[i]) | (unsigned long long) i;
+  }
+  __syncthreads();
+  // bitonic sort of the S segments, ascending, in the all-ascending formulation (every merge starts with a "flip"
+  // stage, then half-cleaners): elements beyond S are virtual +infinity that never move, so only S slots exist.
+  // A thread always owns the same pair slots, and for spans of at most 64 both elements of a pair live in its
+  // warp's 64-element block: those stages need no block barrier.
+  for (int k = 2; k <= cap; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int lx = j == (k >> 1) ? k - 1 : j;  // flip: partner = i ^ (k - 1); half-cleaner: partner = i | j
+      for (int t = tid; t < (cap >> 1); t += T) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i ^ lx;
+        if (l >= S) continue;
+        const unsigned long long a = key[i], b2 = key[l];
+        if (b2 < a) key[i] = b2, key[l] = a;
+      }
+      // next stage: the flip of merge 2k (span 2k) after j == 1, else a half-cleaner of span j
+      const int span_now = lx == j ? 2 * j : k, span_next = j == 1 ? 2 * k : j;
+      if (span_now > 64 || span_next > 64)
+        __syncthreads();
+      else
+        __syncwarp();
+    }
+  __syncthreads();
+  // one output point per run of equal voxel keys: the run's first segment sums all members in sorted (= cloud) order;
+  // a segment's members are the valid points from its first point on that still carry its voxel key
+  const int seg_chunks = (S + T - 1) / T;
+  mask = 0;
+  for (int c = 0; c < seg_chunks; ++c) {
+    const int t = c * T + tid;
+    if (t < S && (t == 0 || ((key[t] ^ key[t - 1]) & VOXEL_MASK) != 0)) mask |= 1u << c;
+  }
+  compact_count(mask, seg_chunks, cnt, total);
+  for (int c = 0; c < seg_chunks; ++c) {
+    const int t = c * T + tid, dst = compact_slot(mask, c, cnt);
+    if (!((mask >> c) & 1u)) continue;
+    const unsigned long long vk = key[t] & VOXEL_MASK;
+    float4 o  = make_float4(0.f, 0.f, 0.f, 0.f);
+    int count = 0;
+    for (int e = t; e < S && (key[e] & VOXEL_MASK) == vk; ++e) {
+      const int first = (int) (key[e] & 0x3FFF);
+      for (int i = first; i < n; ++i) {
+        if (valid && !valid[i]) continue;
+        if (i != first && (voxel_key(V, xy[i], nrm[i]) & VOXEL_MASK) != vk) break;
+        o.x = fadd(o.x, xy[i].x), o.y = fadd(o.y, xy[i].y), o.z = fadd(o.z, nrm[i].x), o.w = fadd(o.w, nrm[i].y);
+        ++count;
+      }
+    }
+    const float w = fdiv(1.f, (float) count);
+    o.x = fmul(o.x, w), o.y = fmul(o.y, w), o.z = fmul(o.z, w), o.w = fmul(o.w, w);
+    const float z = fadd(fmul(o.z, o.z), fmul(o.w, o.w));
+    if (z > 0.f) {
+      const float nn = fsqrt(z);
+      o.z = fdiv(o.z, nn), o.w = fdiv(o.w, nn);
+    }
+    emit(dst, o);
+  }
+  return *total;
+}
 
 constexpr int SCAN_T = 384;  // threads per scan; at most 32 chunks => n_beams <= 12288 (and < 2^14: key layout)
 
@@ -137,7 +232,6 @@ __global__ void __launch_bounds__(SCAN_T) preprocess_kernel(const scan_dev_param
   float2* nrm               = xy + NB;                                             // their normals
   unsigned long long* key   = reinterpret_cast<unsigned long long*>(nrm + NB);     // [sort_cap] segment: voxel key | first point
   unsigned char* valid      = reinterpret_cast<unsigned char*>(key + P.sort_cap);  // [NB]
-  unsigned short* segend    = reinterpret_cast<unsigned short*>(valid + ((NB + 3) & ~3));  // [sort_cap] one past the last point
   __shared__ int cnt[32 * (SCAN_T / 32)];
   __shared__ int total;
   const int T = SCAN_T, tid = threadIdx.x;
@@ -224,87 +318,11 @@ __global__ void __launch_bounds__(SCAN_T) preprocess_kernel(const scan_dev_param
     return;
   }
 
-  // ---- voxelize (.cpp:38-42, P7).  Consecutive valid points that share a voxel form a SEGMENT (neighbouring
-  // beams hit neighbouring places, so a scan has few hundred segments for ~1000 points); only the segments are
-  // sorted, by (voxel key, first point), and a voxel's sum walks its segments in that order = cloud order.
-  mask = 0;
-  for (int c = 0; c < pt_chunks; ++c) {  // segment heads: valid points whose previous valid point has another key
-    const int i = c * T + tid;
-    if (i < n && valid[i]) {
-      int prev = i - 1;
-      while (prev >= 0 && !valid[prev]) --prev;
-      const bool head = prev < 0 || voxel_key(P, xy[i], nrm[i]) != voxel_key(P, xy[prev], nrm[prev]);
-      if (head) mask |= 1u << c;
-    }
-  }
-  compact_count(mask, pt_chunks, cnt, &total);
-  const int S = total;
-  int cap     = 1;
-  while (cap < S) cap <<= 1;
-  for (int c = 0; c < pt_chunks; ++c) {
-    const int i = c * T + tid, dst = compact_slot(mask, c, cnt);
-    if ((mask >> c) & 1u) key[dst] = voxel_key(P, xy[i], nrm[i]) | (unsigned long long) i;
-  }
-  __syncthreads();
-  for (int sgm = tid; sgm < S; sgm += T) segend[sgm] = (unsigned short) (sgm + 1 < S ? (int) (key[sgm + 1] & 0x3FFF) : n);
-  __syncthreads();
-  // bitonic sort of the S segments, ascending, in the all-ascending formulation (every merge starts with a "flip"
-  // stage, then half-cleaners): elements beyond S are virtual +infinity that never move, so only S slots exist.
-  // A thread always owns the same pair slots, and for spans of at most 64 both elements of a pair live in its
-  // warp's 64-element block: those stages need no block barrier.
-  for (int k = 2; k <= cap; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const int lx = j == (k >> 1) ? k - 1 : j;  // flip: partner = i ^ (k - 1); half-cleaner: partner = i | j
-      for (int t = tid; t < (cap >> 1); t += T) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i ^ lx;
-        if (l >= S) continue;
-        const unsigned long long a = key[i], b2 = key[l];
-        if (b2 < a) {
-          const unsigned short ea = segend[i], eb = segend[l];
-          key[i] = b2, segend[i] = eb;
-          key[l] = a, segend[l] = ea;
-        }
-      }
-      // next stage: the flip of merge 2k (span 2k) after j == 1, else a half-cleaner of span j
-      const int span_now = lx == j ? 2 * j : k, span_next = j == 1 ? 2 * k : j;
-      if (span_now > 64 || span_next > 64)
-        __syncthreads();
-      else
-        __syncwarp();
-    }
-  __syncthreads();
-  // one output point per run of equal voxel keys: the run's first segment sums all members in sorted (= cloud) order
-  const int seg_chunks = (S + T - 1) / T;
-  mask = 0;
-  for (int c = 0; c < seg_chunks; ++c) {
-    const int t = c * T + tid;
-    if (t < S && (t == 0 || ((key[t] ^ key[t - 1]) & VOXEL_MASK) != 0)) mask |= 1u << c;
-  }
-  compact_count(mask, seg_chunks, cnt, &total);
-  for (int c = 0; c < seg_chunks; ++c) {
-    const int t = c * T + tid, dst = compact_slot(mask, c, cnt);
-    if (!((mask >> c) & 1u)) continue;
-    const unsigned long long vk = key[t] & VOXEL_MASK;
-    float4 o  = make_float4(0.f, 0.f, 0.f, 0.f);
-    int count = 0;
-    for (int e = t; e < S && (key[e] & VOXEL_MASK) == vk; ++e) {
-      const int end = segend[e];
-      for (int i = (int) (key[e] & 0x3FFF); i < end; ++i) {
-        if (!valid[i]) continue;
-        o.x = fadd(o.x, xy[i].x), o.y = fadd(o.y, xy[i].y), o.z = fadd(o.z, nrm[i].x), o.w = fadd(o.w, nrm[i].y);
-        ++count;
-      }
-    }
-    const float w = fdiv(1.f, (float) count);
-    o.x = fmul(o.x, w), o.y = fmul(o.y, w), o.z = fmul(o.z, w), o.w = fmul(o.w, w);
-    const float z = fadd(fmul(o.z, o.z), fmul(o.w, o.w));
-    if (z > 0.f) {
-      const float nn = fsqrt(z);
-      o.z = fdiv(o.z, nn), o.w = fdiv(o.w, nn);
-    }
-    out[dst] = o;
-  }
-  if (tid == 0) A.counts[blockIdx.x] = total;
+  // ---- voxelize(res, res, 1, 1) (.cpp:38-42, P7)
+  voxel_params V;
+  V.inv_res = P.inv_res, V.inv_n = 1.f, V.nb = 1;
+  const int n_out = block_voxelize(V, xy, nrm, valid, n, key, cnt, &total, [&](int slot, float4 o) { out[slot] = o; });
+  if (tid == 0) A.counts[blockIdx.x] = n_out;
 }
 
 // exclusive scan of counts[n] -> off[n + 1]; one CTA, chunks of blockDim.x
@@ -343,6 +361,65 @@ __global__ void scan_pack_kernel(const float4* strided, const int* off, int n_be
   const int s = blockIdx.x;
   const int o = off[s], n = off[s + 1] - o;
   for (int i = threadIdx.x; i < n; i += blockDim.x) packed[o + i] = strided[(size_t) s * n_beams + i];
+}
+
+// SceneClipperProjective2D::compute with voxelize_resolution > 0 (R/mapping/scene_clipper_projective_2d.cpp:36-48):
+// the z-buffer winners in column order, as points in the sensor frame, voxelized with res_coeffs (res, res, 0.1,
+// 0.1), then moved into the robot frame.  One CTA per request; shared memory: clip_voxel_smem_bytes(canvas_cols).
+constexpr size_t clip_voxel_smem_bytes(int cols) { return (size_t) cols * (4 + 4 + 8 + 8 + 8) + 64; }
+
+__global__ void __launch_bounds__(SCAN_T) clip_voxel_kernel(const dev_params P, const clip_args A, float inv_res) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C             = P.cam.cols;
+  float2* xy              = reinterpret_cast<float2*>(smem_raw);
+  float2* nrm             = xy + C;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(nrm + C);
+  unsigned* zdepth        = reinterpret_cast<unsigned*>(key + C);
+  unsigned* zidx          = zdepth + C;
+  __shared__ int cnt[32 * (SCAN_T / 32)];
+  __shared__ int total;
+  const int T = SCAN_T, tid = threadIdx.x;
+  const int r     = blockIdx.x;
+  const int cloud = A.cloud_ids[r];
+  const int p0 = A.off[cloud], n = A.off[cloud + 1] - p0;
+  const iso S   = iso_v2t(A.sensor_xyt[0], A.sensor_xyt[1], A.sensor_xyt[2]);
+  const iso cam = iso_compose(iso_v2t(A.robot_xyt[3 * r], A.robot_xyt[3 * r + 1], A.robot_xyt[3 * r + 2]), S);
+  const iso W   = iso_inverse(cam);
+  const bool move = !(S.c == 1.f && S.s == 0.f && S.tx == 0.f && S.ty == 0.f);  // .cpp:60
+  zbuffer_project<false>(P, W, A.pts + p0, n, zdepth, zidx);
+  // winners in column order (.cpp:38-43), in the sensor frame
+  const int col_chunks = (C + T - 1) / T;
+  unsigned mask = 0;
+  for (int c = 0; c < col_chunks; ++c) {
+    const int k = c * T + tid;
+    if (k < C && zidx[k] != Z_EMPTY_IDX) mask |= 1u << c;
+  }
+  compact_count(mask, col_chunks, cnt, &total);
+  for (int c = 0; c < col_chunks; ++c) {
+    const int k = c * T + tid, dst = compact_slot(mask, c, cnt);
+    if ((mask >> c) & 1u) {
+      const float4 p = ldg4(A.pts + p0 + zidx[k]);
+      float2 q, nq;
+      iso_apply(W, p.x, p.y, q.x, q.y);
+      iso_rot(W, p.z, p.w, nq.x, nq.y);
+      xy[dst] = q, nrm[dst] = nq;
+    }
+  }
+  const int m = total;
+  __syncthreads();
+  voxel_params V;
+  V.inv_res = inv_res, V.inv_n = fdiv(1.f, 0.1f), V.nb = 10;
+  float4* out     = A.out + (size_t) r * C;
+  const int n_out = block_voxelize(V, xy, nrm, nullptr, m, key, cnt, &total, [&](int slot, float4 o) {
+    if (move) {  // .cpp:60-62
+      float x, y, nx, ny;
+      iso_apply(S, o.x, o.y, x, y);
+      iso_rot(S, o.z, o.w, nx, ny);
+      o = make_float4(x, y, nx, ny);
+    }
+    out[slot] = o;
+  });
+  if (tid == 0) A.counts[r] = n_out;
 }
 
 }  // namespace ls2d

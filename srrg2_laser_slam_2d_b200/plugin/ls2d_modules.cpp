@@ -167,9 +167,6 @@ namespace srrg2_laser_slam_2d {
       return;
     }
     if (!param_projector.value()) throw std::runtime_error("SceneClipperProjective2D::compute| Missing Projector");
-    if (param_voxelize_resolution.value() > 0)
-      throw std::runtime_error("SceneClipperProjective2D::compute| voxelize_resolution > 0 is not supported by the "
-                               "CUDA clipper (both shipped configurations set 0)");
     ls2d_params p;
     ls2d_default_params(&p);
     param_projector->fillParams(p);
@@ -184,8 +181,9 @@ namespace srrg2_laser_slam_2d {
     std::vector<float> out((size_t) p.canvas_cols * 4);
     int32_t n        = 0;
     const int32_t id = 0;
-    Ls2dDevice::check(ls2d_clip_scenes(h, LS2D_FIXED, &id, robot.v, sensor.v, 1, out.data(), &n),
-                      "SceneClipperProjective2D::compute");
+    Ls2dDevice::check(ls2d_clip_scenes_voxelized(h, LS2D_FIXED, &id, robot.v, sensor.v, 1,
+                                                 param_voxelize_resolution.value(), out.data(), &n),
+                      "SceneClipperProjective2D::compute");  // <= 0: the plain clip (.cpp:49-57)
     unflatten(out.data(), (size_t) n, *_clipped_scene_in_robot);
     _status = Successful;
   }

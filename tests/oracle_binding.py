@@ -85,6 +85,8 @@ def lib():
         L.orc_accept.restype = i32
         L.orc_max_threads.restype = i32
         L.orc_clip_scene.argtypes, L.orc_clip_scene.restype = [C.POINTER(OrcParams), vp, i32, OrcIso, OrcIso, vp], i32
+        L.orc_clip_scene_voxelized.argtypes = [C.POINTER(OrcParams), vp, i32, OrcIso, OrcIso, f32, vp]
+        L.orc_clip_scene_voxelized.restype = i32
         L.orc_merge.argtypes = [C.POINTER(OrcParams), f32, vp, i32, vp, i32, OrcIso, vp]
         L.orc_merge.restype = i32
         L.orc_default_scan_params.argtypes = [C.POINTER(OrcScanParams)]
@@ -253,12 +255,13 @@ def column(prm: OrcParams, y: np.ndarray, x: np.ndarray) -> np.ndarray:
     return col
 
 
-def clip_scene(prm: OrcParams, scene: np.ndarray, robot_in_local_map_xyt, sensor_in_robot_xyt) -> np.ndarray:
-    """SceneClipperProjective2D::compute (voxelize off): returns the clipped cloud [k, 4] in the robot frame."""
+def clip_scene(prm: OrcParams, scene: np.ndarray, robot_in_local_map_xyt, sensor_in_robot_xyt,
+               voxelize_resolution: float = 0.0) -> np.ndarray:
+    """SceneClipperProjective2D::compute: returns the clipped cloud [k, 4] in the robot frame."""
     scene = _f32(scene)
     out = np.zeros((prm.canvas_cols, 4), np.float32)
-    k = lib().orc_clip_scene(C.byref(prm), _ptr(scene), len(scene), v2t(*robot_in_local_map_xyt),
-                             v2t(*sensor_in_robot_xyt), _ptr(out))
+    k = lib().orc_clip_scene_voxelized(C.byref(prm), _ptr(scene), len(scene), v2t(*robot_in_local_map_xyt),
+                                       v2t(*sensor_in_robot_xyt), voxelize_resolution, _ptr(out))
     return out[:k].copy()
 
 

@@ -125,3 +125,26 @@ def test_tracker_rows_golden(handle_factory):
                              range_max=1000.0, voxelize_resolution=0.01)
     cloud, n = h.preprocess_scans(fx, np.full((1, 100), 1.0, np.float32))
     assert n[0] == 100 and np.array_equal(gu.bits(cloud[0, :100]), gu.bits(d["synthetic_fixture_cloud"]))
+
+
+@pytest.mark.parametrize("cols,res,sensor", [(721, 0.1, (0.2, 0.1, 0.3)), (1081, 0.05, (0.0, 0.0, 0.0)),
+                                             (361, 0.5, (0.1, -0.2, -0.4)), (721, 0.02, (0.0, 0.0, 0.0))])
+def test_scene_clipper_voxelize_branch_bit_exact(handle_factory, oracle, cols, res, sensor):
+    """SceneClipperProjective2D with voxelize_resolution > 0 (R/mapping/scene_clipper_projective_2d.cpp:36-48):
+    the winners are voxelized with res_coeffs (res, res, 0.1, 0.1) in the sensor frame, then moved to the robot"""
+    sp = make_scan_pairs(6, n_beams=900, seed=63)
+    scenes = [local_map(sp, k) for k in range(6)]
+    off = np.concatenate([[0], np.cumsum([len(s) for s in scenes])]).astype(np.int32)
+    kw = dict(canvas_cols=cols)
+    h = handle_factory(default_params(**kw))
+    h.upload_clouds(LS2D_FIXED, np.concatenate(scenes), off)
+    rng = np.random.default_rng(6)
+    ids = np.array([0, 5, 2, 2, 4], np.int32)
+    robots = rng.uniform(-0.3, 0.3, (len(ids), 3)).astype(np.float32)
+    got = h.clip_scenes(LS2D_FIXED, ids, robots, sensor, voxelize_resolution=res)
+    prm = oracle.default_params(**kw)
+    for r, cid in enumerate(ids):
+        ref = oracle.clip_scene(prm, scenes[cid], robots[r], sensor, res)
+        plain = oracle.clip_scene(prm, scenes[cid], robots[r], sensor)
+        assert got[r].shape == ref.shape and 10 < len(ref) <= len(plain)
+        assert np.array_equal(gu.bits(got[r]), gu.bits(ref))
