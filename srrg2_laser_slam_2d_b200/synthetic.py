@@ -249,6 +249,39 @@ def make_raw_scans(n_pairs: int, n_beams: int = HOKUYO_BEAMS, seed: int = 0xC0FF
                         np.zeros_like(delta, dtype=np.float32))
 
 
+@dataclass
+class ScanSequence:
+    """One robot driving through one world: raw scans and ground-truth poses (world frame)."""
+
+    ranges: np.ndarray     # [n_frames, n_beams] float32
+    poses: np.ndarray      # [n_frames, 3] float64 (x, y, theta) of the sensor = robot
+    angle_min: float
+    angle_max: float
+
+
+def make_scan_sequence(n_frames: int, n_beams: int = 721, seed: int = 1, fov: float = HOKUYO_FOV,
+                       step_xy: float = 0.04, step_theta: float = 0.02, range_noise: float = 0.005,
+                       dropout: float = 0.01, range_max: float = 20.0, no_return: float = 65.0) -> ScanSequence:
+    """A smooth random drive inside one seeded room (frame-to-frame motion of the size the reference's generator
+    uses, apps/synthetic_scene_generator.cpp:168-178), scanned at every pose: the input of a tracker run."""
+    rng = np.random.default_rng(seed)
+    segs_np, circ_np = _make_worlds(rng, 1)
+    poses = np.zeros((n_frames, 3))
+    poses[0] = (rng.uniform(-0.5, 0.5), rng.uniform(-0.5, 0.5), rng.uniform(-math.pi, math.pi))
+    vel = np.array([step_xy, 0.0, step_theta]) * rng.uniform(0.5, 1.0, 3)
+    for f in range(1, n_frames):
+        vel = 0.9 * vel + 0.1 * np.array([step_xy, 0.0, step_theta]) * rng.uniform(-1.0, 1.5, 3)
+        poses[f] = _t2v(_v2t(poses[f - 1]) @ _v2t(vel))
+    beam = (np.arange(n_beams) - 0.5 * n_beams) * (fov / n_beams)
+    segs = torch.from_numpy(np.repeat(segs_np, n_frames, 0))
+    circ = torch.from_numpy(np.repeat(circ_np, n_frames, 0))
+    r = _raycast(torch.from_numpy(poses), torch.from_numpy(beam), segs, circ)
+    r = r + torch.from_numpy(rng.normal(0.0, range_noise, (n_frames, n_beams)))
+    bad = ~torch.isfinite(r) | (r <= 0.05) | (r >= range_max) | torch.from_numpy(rng.uniform(0, 1, (n_frames, n_beams)) < dropout)
+    r = torch.where(bad, torch.full_like(r, no_return), r)
+    return ScanSequence(r.to(torch.float32).numpy(), poses, -0.5 * fov, 0.5 * fov)
+
+
 def reference_demo_scene(n_points: int = 1024) -> np.ndarray:
     """The deterministic world of apps/synthetic_scene_generator.cpp:36-56: a circle (r = 3.5 m,
     2*n_points points) plus a 2 m + 3 m corner placed at (2, 0, pi/4).  The reference leaves the
