@@ -22,6 +22,7 @@ data-path collective: weak scaling); time = max over ranks.   --impl reference t
 --workload verify runs the sharded loop-closure verification (config 4 shape) instead.
 --workload allpairs runs the large-map all-pairs loop-closure search (config 5 shape): candidate pairs grouped by query
 map, groups sharded over the ranks, one all-gather of the per-map best records.
+--workload multi times the MULTI.json-shaped aligner (two laser slices + odometry prior in one 3x3 system).
 --workload track times the tracker's frame step from RAW scans (ls2d_track_batch: pre-process -> clip -> align).
 """
 from __future__ import annotations
@@ -521,6 +522,76 @@ def run_allpairs(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------------------------- multi-slice aligner
+def run_multi(args):
+    """BASELINE.json configs[1] (stage_segway_double_config_MULTI.json:700-730): two rangefinders + wheel odometry
+    fused in one SE(2) aligner, batched: 721-beam scans, Cauchy 0.01 on laser_0, no robustifier on laser_1,
+    min_num_correspondences 5, 10 iterations, prior information diag(100, 100, 400)."""
+    import torch
+
+    from srrg2_laser_slam_2d_b200 import Handle, default_params
+    from srrg2_laser_slam_2d_b200._abi import RESULT_DTYPE, make_prior
+    from srrg2_laser_slam_2d_b200.synthetic import make_multi_sensor_pairs
+
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n = args.pairs
+    msp = make_multi_sensor_pairs(n, n_beams=721, seed=0xD0C, device=str(dev))
+    base = dict(canvas_cols=721, max_iterations=10, min_num_correspondences=5, with_sensor=1, point_distance=0.5)
+    sl = [default_params(normal_cos=0.9, cauchy_chi_threshold=0.01, sensor_in_robot=tuple(float(v) for v in msp.sensors[0]), **base),
+          default_params(normal_cos=0.8, cauchy_chi_threshold=-1.0, sensor_in_robot=tuple(float(v) for v in msp.sensors[1]), **base)]
+    prior = make_prior((100.0, 0.0, 0.0, 100.0, 0.0, 400.0))
+    h = Handle(local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
+    h.upload_clouds(0, msp.fixed_pts[0], msp.fixed_off[0])
+    h.upload_clouds(2, msp.fixed_pts[1], msp.fixed_off[1])
+    h.upload_clouds(1, msp.moving_pts, msp.moving_off)
+    init = torch.from_numpy(msp.init_xyt).to(dev)
+    z = torch.from_numpy(msp.odom_xyt).to(dev)
+    out = torch.zeros(n * 16, dtype=torch.int32, device=dev)
+
+    def step():
+        h.align_multi_dev(sl, [0, 2], [1, 1], init.data_ptr(), n, out.data_ptr(), prior=prior, prior_z_ptr=z.data_ptr())
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = h.launch_count
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    res = np.frombuffer(out.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+    err = np.abs(np.stack([res["x"], res["y"], res["theta"]], 1) - msp.gt_xyt)
+    bytes_per_pair = 16 * (int(msp.fixed_off[0][1]) + int(msp.fixed_off[1][1]) + int(msp.moving_off[1])) + 12 + 12 + 64
+    peak, peak_src = hbm_peak()
+    print(json.dumps({
+        "metric": "aligned multi-sensor pairs/sec (2 x 721 beams + odometry prior, 10 GN iters)",
+        "value": n / (ms * 1e-3), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "multi-slice registration (MULTI.json tracking aligner shape): %d pairs, two laser slices of "
+                               "721 beams with their own sensor_in_robot + odometry prior" % n,
+                   "success_rate": float((res["status"] == 0).mean()),
+                   "median_abs_pose_error": [float(v) for v in np.median(err, 0)]},
+        "roofline": {"bound": "hbm", "achieved": bytes_per_pair * n / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": bytes_per_pair * n / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                     "kernel": "icp_multi_kernel", "traffic": None, "algorithmic_bytes_per_pair": bytes_per_pair},
+        "gpu_launches": int(h.launch_count - l0), "clocks": clk,
+    }))
+
+
 # ----------------------------------------------------------------------------------------------- tracker step
 def run_track(args):
     """The tracker's frame step with raw scans as the wire format: per frame 1081 ranges
@@ -581,7 +652,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["align", "verify", "track", "allpairs"], default="align")
+    ap.add_argument("--workload", choices=["align", "verify", "track", "allpairs", "multi"], default="align")
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--candidates", type=int, default=65536)
     ap.add_argument("--guesses", type=int, default=8)
@@ -600,6 +671,8 @@ def main():
         run_verify(args)
     elif args.workload == "allpairs":
         run_allpairs(args)
+    elif args.workload == "multi":
+        run_multi(args)
     elif args.workload == "track":
         run_track(args)
     else:
