@@ -159,7 +159,7 @@ shape pick_shape(int max_points, int variant) {
 
 template <int T, int PPT, bool SENSOR, int MINB>
 int launch_icp_k(ls2d_handle* h, const align_args& a) {
-  const size_t smem = icp_smem_bytes(h->dp.cam.cols, T);
+  const size_t smem = icp_smem_bytes(h->dp.cam.cols, T, PPT);
   auto kern         = icp_fused_kernel<T, PPT, SENSOR, MINB>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   // the kernel keeps its working set in shared memory and registers; give it the whole carve-out

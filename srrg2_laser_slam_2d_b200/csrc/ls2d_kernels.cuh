@@ -295,8 +295,9 @@ __device__ __forceinline__ void write_result(const dev_params& P, const align_ar
   }
 }
 
-constexpr size_t icp_smem_bytes(int cols, int threads) {
-  return (size_t) cols * (16 + 4 + 4 + 4) + (size_t)(threads / 32) * RED_STRIDE * 4 + sizeof(pose_bc) + 16;
+constexpr size_t icp_smem_bytes(int cols, int threads, int ppt) {
+  return (size_t) cols * (16 + 4 + 4 + 4) + (size_t) threads * ppt * 8 + (size_t)(threads / 32) * RED_STRIDE * 4 +
+         sizeof(pose_bc) + 16;
 }
 
 template <int T, int PPT, bool SENSOR, int MINB>
@@ -307,7 +308,8 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
   float* fdepth    = reinterpret_cast<float*>(fimg + C);            // fixed image: rho, < 0 = empty
   unsigned* zdepth = reinterpret_cast<unsigned*>(fdepth + C);       // z-buffer pass 1: min rho bits
   unsigned* zidx   = zdepth + C;                                    // z-buffer pass 2: min index among ties
-  float* red       = reinterpret_cast<float*>(zidx + C);            // [T/32][RED_STRIDE]
+  float2* mnrm     = reinterpret_cast<float2*>(zidx + C + (C & 1)); // [T * PPT] moving normals (phase 2 only)
+  float* red       = reinterpret_cast<float*>(mnrm + T * PPT);      // [T/32][RED_STRIDE]
   pose_bc* bc      = reinterpret_cast<pose_bc*>(red + (T / 32) * RED_STRIDE);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -322,12 +324,16 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
     zdepth[k] = Z_EMPTY_DEPTH;
     zidx[k]   = Z_EMPTY_IDX;
   }
-  // moving cloud -> registers (issued early; consumed after the fixed image is built)
-  float4 mp[PPT];
+  // moving cloud (issued early; consumed after the fixed image is built): coordinates -> registers for all
+  // iterations, normals -> shared memory (only winners read them; the register allocator would spill them to
+  // local memory otherwise)
+  float2 mp[PPT];
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
-    const int i = tid + j * T;
-    mp[j]       = i < nm ? ldg4(A.moving_pts + m0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int i    = tid + j * T;
+    const float4 m = i < nm ? ldg4(A.moving_pts + m0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    mp[j]          = make_float2(m.x, m.y);
+    mnrm[i]        = make_float2(m.z, m.w);
   }
   if (tid == 0) {
     const iso X = iso_v2t(A.init_xyt[3 * pair], A.init_xyt[3 * pair + 1], A.init_xyt[3 * pair + 2]);
@@ -391,11 +397,12 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
   // index tie-break pass (one more barrier).  `exact` is uniform over the CTA.
   bool exact = false;
   for (; it < max_it; ++it) {
-    const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
     if (exact) __syncthreads();  // redo pass: tie flag cleared and all cells handed back
     int col[PPT];
     unsigned rb[PPT];
     // phase 1: project the moving cloud (camera = local_map_in_sensor^-1, .cpp:47-48), z-buffer pass 1
+    {
+    const float Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;  // phase-1 copies die at the barrier
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       col[j] = -1;
@@ -413,7 +420,9 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
         }
       }
     }
+    }
     __syncthreads();
+    const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls;  // re-read: shorter live ranges than 6 registers
     if (exact) {  // z-buffer pass 2: lowest index among equal depths
 #pragma unroll
       for (int j = 0; j < PPT; ++j)
@@ -435,7 +444,9 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
         bc->tie = 1;  // two points of equal minimal rho in one column: redo this iteration exactly
         continue;
       }
-      linearize_point<SENSOR>(P, bc, fdepth[c], fimg[c], mp[j], u2f(rb[j]), Xtx, Xty, Lc, Ls, acc, cnt);
+      const float2 mn = mnrm[tid + j * T];
+      linearize_point<SENSOR>(P, bc, fdepth[c], fimg[c], make_float4(mp[j].x, mp[j].y, mn.x, mn.y), u2f(rb[j]), Xtx,
+                              Xty, Lc, Ls, acc, cnt);
     }
     store_partials(acc, cnt, red, lane, warp);
     __syncthreads();
