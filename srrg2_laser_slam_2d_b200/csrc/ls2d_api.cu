@@ -143,6 +143,8 @@ shape pick_shape(int max_points, int variant) {
       case 5: return {256, 5, 4, 0};
       case 6: return {192, 6, 4, 0};
       case 7: return {128, 9, 5, 0};
+      case 8: return {288, 4, 4, 0};
+      case 9: return {288, 4, 3, 0};
       case 10: return {384, 0, 4, 2};
       case 11: return {384, 0, 4, 1};
       case 12: return {256, 0, 6, 2};
@@ -216,6 +218,8 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   LS2D_CASE(192, 6, 5)
   LS2D_CASE(256, 5, 4)
   LS2D_CASE(384, 3, 3)
+  LS2D_CASE(288, 4, 4)
+  LS2D_CASE(288, 4, 3)
   LS2D_CASE(128, 9, 5)
   LS2D_CASE(256, 6, 2)
   LS2D_CASE(256, 8, 2)

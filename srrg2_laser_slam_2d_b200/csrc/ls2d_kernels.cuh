@@ -403,22 +403,34 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
     // phase 1: project the moving cloud (camera = local_map_in_sensor^-1, .cpp:47-48), z-buffer pass 1
     {
     const float Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;  // phase-1 copies die at the barrier
+    // the three points of a thread run as independent straight-line chains (transform, rho, fast column); the rare
+    // points whose column only the exact atan2 may decide are visited afterwards
+    f2 pc[PPT];
+    bool near[PPT];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      col[j] = -1;
-      rb[j]  = 0;
-      if (tid + j * T < nm) {
-        const f2 ra = mul2s(mk2(Lc, Ls), mp[j].x), rb2 = mul2s(mk2(-Ls, Lc), mp[j].y);
-        const f2 pc = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
-        const f2 pq = mul2(pc, pc);
-        const float px = pc.x, py = pc.y;
-        const float rho = fsqrt(fadd(pq.x, pq.y));
-        if (!(rho < P.range_min || rho > P.range_max)) {
-          col[j] = polar_column(P.cam, py, px);
-          rb[j]  = f2u(rho);
-          if (col[j] >= 0) atomicMin(&zdepth[col[j]], rb[j]);
-        }
-      }
+      const f2 ra = mul2s(mk2(Lc, Ls), mp[j].x), rb2 = mul2s(mk2(-Ls, Lc), mp[j].y);
+      pc[j]       = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
+      const f2 pq = mul2(pc[j], pc[j]);
+      const float rho = fsqrt(fadd(pq.x, pq.y));
+      rb[j]       = f2u(rho);
+      col[j]      = polar_column_fast(P.cam, pc[j].y, pc[j].x, near[j]);
+      near[j]     = near[j] && !(rho < P.range_min || rho > P.range_max);
+    }
+    bool any_near = false;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) any_near |= near[j];
+    if (any_near) {
+#pragma unroll
+      for (int j = 0; j < PPT; ++j)
+        if (near[j]) col[j] = polar_column_exact(P.cam, pc[j].y, pc[j].x);
+    }
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      const float rho = u2f(rb[j]);
+      const bool ok   = tid + j * T < nm && !(rho < P.range_min || rho > P.range_max) && col[j] >= 0 && col[j] < C;
+      col[j]          = ok ? col[j] : -1;
+      if (ok) atomicMin(&zdepth[col[j]], rb[j]);
     }
     }
     __syncthreads();
