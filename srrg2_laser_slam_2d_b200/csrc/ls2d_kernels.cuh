@@ -572,20 +572,46 @@ __global__ void __launch_bounds__(T, MINB) icp_stream_kernel(const dev_params P,
   unsigned tot_cnt = 0;
   bool exact       = false;
   for (; it < max_it; ++it) {
-    const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
     if (exact) __syncthreads();
-    for (int i = tid; i < nm; i += T) {
-      const float4 M  = MP_SMEM ? smp[i] : ldg4(mpts + i);
-      const f2 ra = mul2s(mk2(Lc, Ls), M.x), rb2 = mul2s(mk2(-Ls, Lc), M.y);
-      const f2 pc = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
-      const f2 pq = mul2(pc, pc);
-      const float px = pc.x, py = pc.y;
-      const float rho = fsqrt(fadd(pq.x, pq.y));
-      int col         = -1;
-      if (!(rho < P.range_min || rho > P.range_max)) col = polar_column(P.cam, py, px);
-      scol[i] = (unsigned short) (col < 0 ? 0xFFFF : col);
-      srho[i] = f2u(rho);
-      if (col >= 0) atomicMin(&zdepth[col], f2u(rho));
+    {  // phase 1: four points of a thread at a time as straight-line chains; the rare exact-atan2 points afterwards
+      const float Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
+      constexpr int U = 4;
+      for (int i0 = tid; i0 < nm; i0 += U * T) {
+        f2 pc[U];
+        unsigned rbv[U];
+        int colv[U];
+        bool near[U];
+        bool any_near = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i    = i0 + u * T;
+          const float4 M = i < nm ? (MP_SMEM ? smp[i] : ldg4(mpts + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const f2 ra = mul2s(mk2(Lc, Ls), M.x), rb2 = mul2s(mk2(-Ls, Lc), M.y);
+          pc[u]       = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
+          const f2 pq = mul2(pc[u], pc[u]);
+          const float rho = fsqrt(fadd(pq.x, pq.y));
+          rbv[u]      = f2u(rho);
+          colv[u]     = polar_column_fast(P.cam, pc[u].y, pc[u].x, near[u]);
+          near[u]     = near[u] && i < nm && !(rho < P.range_min || rho > P.range_max);
+          any_near |= near[u];
+        }
+        if (any_near) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (near[u]) colv[u] = polar_column_exact(P.cam, pc[u].y, pc[u].x);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * T;
+          if (i < nm) {
+            const float rho = u2f(rbv[u]);
+            const bool ok   = !(rho < P.range_min || rho > P.range_max) && colv[u] >= 0 && colv[u] < C;
+            scol[i]         = (unsigned short) (ok ? colv[u] : 0xFFFF);
+            srho[i]         = rbv[u];
+            if (ok) atomicMin(&zdepth[colv[u]], rbv[u]);
+          }
+        }
+      }
     }
     __syncthreads();
     if (exact) {
@@ -595,28 +621,42 @@ __global__ void __launch_bounds__(T, MINB) icp_stream_kernel(const dev_params P,
       }
       __syncthreads();
     }
+    const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls;
     float acc[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) acc[s] = 0.f;
     unsigned cnt = 0;
-    for (int i = tid; i < nm; i += T) {
-      const unsigned c = scol[i];
-      if (c == 0xFFFF || zdepth[c] != srho[i]) continue;
-      if (exact) {
-        if (zidx[c] != (unsigned) i) continue;
-      } else if (atomicCAS(&zidx[c], Z_EMPTY_IDX, (unsigned) i) != Z_EMPTY_IDX) {
-        bc->tie = 1;
-        continue;
+    // phase 2: a thread first finds the z-buffer winners among its next 32 points (cheap scan), then linearises only
+    // those, in ascending order: with far more points than columns most points lose, and a warp now runs the heavy
+    // path max-winners-per-lane times instead of once per scanned point
+    for (int k0 = 0; tid + k0 * T < nm; k0 += 32) {
+      unsigned wmask = 0;
+#pragma unroll 4
+      for (int k = 0; k < 32; ++k) {
+        const int i = tid + (k0 + k) * T;
+        if (i >= nm) break;
+        const unsigned c = scol[i];
+        if (c == 0xFFFF || zdepth[c] != srho[i]) continue;
+        if (exact) {
+          if (zidx[c] != (unsigned) i) continue;
+        } else if (atomicCAS(&zidx[c], Z_EMPTY_IDX, (unsigned) i) != Z_EMPTY_IDX) {
+          bc->tie = 1;
+          continue;
+        }
+        wmask |= 1u << k;
       }
-      const float4 M = MP_SMEM ? smp[i] : ldg4(mpts + i);
-      linearize_point<SENSOR>(P, bc, fdepth[c], fimg[c], M, u2f(srho[i]), Xtx, Xty, Lc, Ls, acc, cnt);
+      while (wmask) {
+        const int k = __ffs(wmask) - 1;
+        wmask &= wmask - 1;
+        const int i      = tid + (k0 + k) * T;
+        const unsigned c = scol[i];
+        const float4 M   = MP_SMEM ? smp[i] : ldg4(mpts + i);
+        linearize_point<SENSOR>(P, bc, fdepth[c], fimg[c], M, u2f(srho[i]), Xtx, Xty, Lc, Ls, acc, cnt);
+      }
     }
     store_partials(acc, cnt, red, lane, warp);
     __syncthreads();
-    for (int i = tid; i < nm; i += T) {
-      const unsigned c = scol[i];
-      if (c != 0xFFFF) zdepth[c] = Z_EMPTY_DEPTH, zidx[c] = Z_EMPTY_IDX;
-    }
+    for (int k = tid; k < C; k += T) zdepth[k] = Z_EMPTY_DEPTH, zidx[k] = Z_EMPTY_IDX;  // wholesale: C <= points
     if (!exact && bc->tie) {
       __syncthreads();
       if (tid == 0) bc->tie = 0;
