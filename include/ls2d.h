@@ -326,6 +326,8 @@ int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ra
 /* threads per pair the fused kernel uses for clouds of up to max_points points: fixes the shape of its
  * H/b reduction tree (the oracle's ORC_SUM_TREE mode mirrors it) */
 int ls2d_reduction_threads(int32_t max_points);
+/* the same for the multi-slice aligner (ls2d_align_multi), whatever the cloud sizes */
+int ls2d_multi_reduction_threads(void);
 /* kernels launched by this handle since creation */
 int64_t ls2d_launch_count(const ls2d_handle* h);
 

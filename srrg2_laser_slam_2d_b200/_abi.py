@@ -80,7 +80,7 @@ EXPORTS = [
     "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
     "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
     "ls2d_clip_scenes_to_set", "ls2d_track_batch", "ls2d_verify_pairs", "ls2d_verify_pairs_dev",
-    "ls2d_clip_scenes_voxelized",
+    "ls2d_clip_scenes_voxelized", "ls2d_multi_reduction_threads",
 ]
 
 _lib = None
@@ -178,6 +178,10 @@ def _i32(a):
 
 def reduction_threads(max_points: int) -> int:
     return load().ls2d_reduction_threads(max_points)
+
+
+def multi_reduction_threads() -> int:
+    return load().ls2d_multi_reduction_threads()
 
 
 def reduce_best(records: np.ndarray) -> np.ndarray:

@@ -488,6 +488,53 @@ __global__ void __launch_bounds__(T, MINB) icp_fused_kernel(const dev_params P, 
   if (tid < 32) write_result(P, A, bc, pair, it, status, tot, tot_cnt);
 }
 
+// Phase 1 of the streaming kernels: every moving point is seen from the camera (W = inverse(inverse(
+// local_map_in_sensor)), decision D13), its rho and column are stashed in shared memory and its rho fights for the
+// column's z-buffer cell.  U points of a thread at a time run as straight-line chains; the rare points whose
+// column only the exact atan2 may decide are visited afterwards.
+template <int T, int U, typename Load>
+__device__ __forceinline__ void project_and_stash(const dev_params& P, const pose_bc* bc, int nm, Load load,
+                                                  unsigned short* scol, unsigned* srho, unsigned* zdepth) {
+  const float Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
+  const int C = P.cam.cols;
+  for (int i0 = threadIdx.x; i0 < nm; i0 += U * T) {
+    f2 pc[U];
+    unsigned rbv[U];
+    int colv[U];
+    bool near[U];
+    bool any_near = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i    = i0 + u * T;
+      const float4 M = i < nm ? load(i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const f2 ra = mul2s(mk2(Lc, Ls), M.x), rb2 = mul2s(mk2(-Ls, Lc), M.y);
+      pc[u]       = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
+      const f2 pq = mul2(pc[u], pc[u]);
+      const float rho = fsqrt(fadd(pq.x, pq.y));
+      rbv[u]      = f2u(rho);
+      colv[u]     = polar_column_fast(P.cam, pc[u].y, pc[u].x, near[u]);
+      near[u]     = near[u] && i < nm && !(rho < P.range_min || rho > P.range_max);
+      any_near |= near[u];
+    }
+    if (any_near) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (near[u]) colv[u] = polar_column_exact(P.cam, pc[u].y, pc[u].x);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * T;
+      if (i < nm) {
+        const float rho = u2f(rbv[u]);
+        const bool ok   = !(rho < P.range_min || rho > P.range_max) && colv[u] >= 0 && colv[u] < C;
+        scol[i]         = (unsigned short) (ok ? colv[u] : 0xFFFF);
+        srho[i]         = rbv[u];
+        if (ok) atomicMin(&zdepth[colv[u]], rbv[u]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // icp_stream_kernel: same algorithm and the same reduction shape (thread t owns points t, t+T, ...; ascending) for
 // clouds of any size.  Per-point state does not live in registers: column and rho of every point are stashed in
@@ -573,46 +620,7 @@ __global__ void __launch_bounds__(T, MINB) icp_stream_kernel(const dev_params P,
   bool exact       = false;
   for (; it < max_it; ++it) {
     if (exact) __syncthreads();
-    {  // phase 1: four points of a thread at a time as straight-line chains; the rare exact-atan2 points afterwards
-      const float Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
-      constexpr int U = 4;
-      for (int i0 = tid; i0 < nm; i0 += U * T) {
-        f2 pc[U];
-        unsigned rbv[U];
-        int colv[U];
-        bool near[U];
-        bool any_near = false;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i    = i0 + u * T;
-          const float4 M = i < nm ? (MP_SMEM ? smp[i] : ldg4(mpts + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const f2 ra = mul2s(mk2(Lc, Ls), M.x), rb2 = mul2s(mk2(-Ls, Lc), M.y);
-          pc[u]       = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
-          const f2 pq = mul2(pc[u], pc[u]);
-          const float rho = fsqrt(fadd(pq.x, pq.y));
-          rbv[u]      = f2u(rho);
-          colv[u]     = polar_column_fast(P.cam, pc[u].y, pc[u].x, near[u]);
-          near[u]     = near[u] && i < nm && !(rho < P.range_min || rho > P.range_max);
-          any_near |= near[u];
-        }
-        if (any_near) {
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (near[u]) colv[u] = polar_column_exact(P.cam, pc[u].y, pc[u].x);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * T;
-          if (i < nm) {
-            const float rho = u2f(rbv[u]);
-            const bool ok   = !(rho < P.range_min || rho > P.range_max) && colv[u] >= 0 && colv[u] < C;
-            scol[i]         = (unsigned short) (ok ? colv[u] : 0xFFFF);
-            srho[i]         = rbv[u];
-            if (ok) atomicMin(&zdepth[colv[u]], rbv[u]);
-          }
-        }
-      }
-    }
+    project_and_stash<T, 4>(P, bc, nm, [&](int i) { return MP_SMEM ? smp[i] : ldg4(mpts + i); }, scol, srho, zdepth);
     __syncthreads();
     if (exact) {
       for (int i = tid; i < nm; i += T) {

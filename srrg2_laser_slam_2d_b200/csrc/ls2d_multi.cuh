@@ -11,7 +11,8 @@
 
 namespace ls2d {
 
-constexpr int MAX_SLICES = LS2D_MAX_SLICES;
+constexpr int MAX_SLICES    = LS2D_MAX_SLICES;
+constexpr int MULTI_THREADS = 256;  // threads per pair: the shape of the per-slice reduction tree
 
 struct dev_slice {
   dev_params P;
@@ -195,22 +196,10 @@ __global__ void __launch_bounds__(T, MINB) icp_multi_kernel(const multi_args A) 
       const pose_bc* bc   = &sh->bc[s];
       const int m0 = A.sl[s].moving_off[mcl], nm = A.sl[s].moving_off[mcl + 1] - m0;
       const float4* mpts = A.sl[s].moving_pts + m0;
-      const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls, Wtx = bc->Wtx, Wty = bc->Wty;
+      const float Xtx = bc->Xtx, Xty = bc->Xty, Lc = bc->Lc, Ls = bc->Ls;
       bool exact = false;
       for (;;) {  // optimistic z-buffer pass, redone exactly on a tie (see icp_fused_kernel)
-        for (int i = tid; i < nm; i += T) {
-          const float4 M  = ldg4(mpts + i);
-          const float rx  = fadd(fmul(Lc, M.x), fmul(-Ls, M.y));
-          const float ry  = fadd(fmul(Ls, M.x), fmul(Lc, M.y));
-          const float px  = fadd(rx, Wtx);
-          const float py  = fadd(ry, Wty);
-          const float rho = fsqrt(fadd(fmul(px, px), fmul(py, py)));
-          int col         = -1;
-          if (!(rho < P.range_min || rho > P.range_max)) col = polar_column(P.cam, py, px);
-          scol[i] = (unsigned short) (col < 0 ? 0xFFFF : col);
-          srho[i] = f2u(rho);
-          if (col >= 0) atomicMin(&zdepth[col], f2u(rho));
-        }
+        project_and_stash<T, 1>(P, bc, nm, [&](int i) { return ldg4(mpts + i); }, scol, srho, zdepth);
         __syncthreads();
         if (exact) {
           for (int i = tid; i < nm; i += T) {

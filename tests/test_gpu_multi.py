@@ -13,7 +13,9 @@ from test_gpu_parity import INT_FIELDS, assert_bit_exact, tolerance_rate
 
 pytestmark = pytest.mark.gpu
 
-MULTI_T = 512       # threads per pair of icp_multi_kernel: the shape of its per-slice reduction tree
+from srrg2_laser_slam_2d_b200._abi import multi_reduction_threads  # noqa: E402
+
+MULTI_T = multi_reduction_threads()   # threads per pair of icp_multi_kernel: the shape of its per-slice reduction tree
 SENSORS = ((0.2, 0.05, 0.1), (-0.2, 0.0, math.pi))
 
 

@@ -239,7 +239,7 @@ def test_plugin_multi_slice_aligner_with_odometry_prior(exe, tmp_path, handle_fa
     classes: scenes carry "points_0" / "points_1" / "points" clouds and "odom" poses; compared with the C ABI called
     directly and with the oracle (kernel summation order), bit for bit."""
     from srrg2_laser_slam_2d_b200 import default_params
-    from srrg2_laser_slam_2d_b200._abi import make_prior
+    from srrg2_laser_slam_2d_b200._abi import make_prior, multi_reduction_threads
     from srrg2_laser_slam_2d_b200.synthetic import make_multi_sensor_pairs
     n = 4
     sensors = ((0.2, 0.05, 0.1), (-0.2, 0.0, 3.0))
@@ -286,7 +286,7 @@ def test_plugin_multi_slice_aligner_with_odometry_prior(exe, tmp_path, handle_fa
                            (1, {}, {})):
         g = h.align_multi(mk(default_params), [0, 2], [1, 1], msp.init_xyt, **kw)
         o, _ = oracle.align_multi_batch(mk(oracle.default_params), fixed, moving, msp.init_xyt, sum_mode=oracle.SUM_TREE,
-                                        tree_threads=512, **okw)
+                                        tree_threads=multi_reduction_threads(), **okw)
         rec = got[:, pass_]["rec"]
         assert same(rec[exact], g[exact]) is None
         assert np.abs(rec["theta"] - g["theta"]).max() <= 2.4e-7     # movingInFixed() is an Isometry2f: v2t -> t2v
