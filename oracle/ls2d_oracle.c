@@ -323,8 +323,12 @@ static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
     }
     return;
   }
-  /* ORC_SUM_TREE: the CUDA kernel's fixed reduction shape (D10) */
-  const int32_t T = tree_threads;
+  /* ORC_SUM_TREE: the CUDA kernels' fixed reduction shapes (D10).  tree_threads = threads per pair (bits 0..15);
+   * bit 16 selects how a warp's 32 lane partials are combined:
+   *   0  xor-butterfly (offsets 16, 8, 4, 2, 1)                      -- icp_fused_kernel / stream / multi
+   *   1  lanes 0..15 and 16..31 summed in ascending order, then added -- icp_fused2_kernel (transposed tile) */
+  const int32_t T        = tree_threads & 0xFFFF;
+  const int32_t half_seq = (tree_threads >> 16) & 1;
   float* part     = (float*) calloc((size_t) T * NSLOT, sizeof(float));
   int32_t* fx_of  = (int32_t*) malloc(sizeof(int32_t) * (size_t)(n_moving > 0 ? n_moving : 1));
   for (int32_t i = 0; i < n_moving; ++i) {
@@ -348,16 +352,29 @@ static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
   }
   for (int32_t w = 0; w < T / 32; ++w) {
     float* lane = part + (size_t) w * 32 * NSLOT;
-    for (int off = 16; off >= 1; off >>= 1) { /* v[l] = v[l] + v[l ^ off] on all lanes */
-      for (int l = 0; l < 32; ++l) {
-        if (l & off) {
-          continue;
+    if (half_seq) {
+      for (int s = 0; s < NSLOT; ++s) {
+        float half[2];
+        for (int h = 0; h < 2; ++h) {
+          half[h] = lane[(h * 16) * NSLOT + s];
+          for (int l = 1; l < 16; ++l) {
+            half[h] = half[h] + lane[(h * 16 + l) * NSLOT + s];
+          }
         }
-        for (int s = 0; s < NSLOT; ++s) {
-          const float a             = lane[l * NSLOT + s];
-          const float b             = lane[(l ^ off) * NSLOT + s];
-          lane[l * NSLOT + s]         = a + b;
-          lane[(l ^ off) * NSLOT + s] = b + a;
+        lane[s] = half[0] + half[1];
+      }
+    } else {
+      for (int off = 16; off >= 1; off >>= 1) { /* v[l] = v[l] + v[l ^ off] on all lanes */
+        for (int l = 0; l < 32; ++l) {
+          if (l & off) {
+            continue;
+          }
+          for (int s = 0; s < NSLOT; ++s) {
+            const float a             = lane[l * NSLOT + s];
+            const float b             = lane[(l ^ off) * NSLOT + s];
+            lane[l * NSLOT + s]         = a + b;
+            lane[(l ^ off) * NSLOT + s] = b + a;
+          }
         }
       }
     }

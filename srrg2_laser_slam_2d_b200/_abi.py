@@ -75,7 +75,7 @@ EXPORTS = [
     "ls2d_default_params", "ls2d_set_params", "ls2d_get_params", "ls2d_upload_clouds", "ls2d_set_clouds_dev",
     "ls2d_align_batch", "ls2d_align_batch_dev", "ls2d_align_pairs_host", "ls2d_score_batch",
     "ls2d_score_batch_dev", "ls2d_find_correspondences", "ls2d_project", "ls2d_verify", "ls2d_verify_dev",
-    "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_threads", "ls2d_launch_count",
+    "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_threads", "ls2d_reduction_shape", "ls2d_launch_count",
     "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev", "ls2d_align_multi", "ls2d_align_multi_dev",
     "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
     "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
@@ -136,6 +136,7 @@ def load():
     L.ls2d_clip_scenes_to_set.argtypes = [vp, C.c_int, vp, vp, vp, i32, C.c_int]
     L.ls2d_track_batch.argtypes = [vp, SP, vp, i32, i32, C.c_int, vp, vp, vp, vp]
     L.ls2d_reduction_threads.argtypes = [i32]
+    L.ls2d_reduction_shape.argtypes = [i32, i32]
     L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
     _lib = L
     return L
@@ -176,8 +177,10 @@ def _i32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
 
 
-def reduction_threads(max_points: int) -> int:
-    return load().ls2d_reduction_threads(max_points)
+def reduction_threads(max_points: int, canvas_cols: int = 1081) -> int:
+    """shape of the aligner kernel's H/b reduction (threads per pair | warp-combine flag << 16): the value the
+    oracle's SUM_TREE mode takes as tree_threads"""
+    return load().ls2d_reduction_shape(max_points, canvas_cols)
 
 
 def multi_reduction_threads() -> int:

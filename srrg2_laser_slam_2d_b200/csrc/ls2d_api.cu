@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ls2d_kernels.cuh"
+#include "ls2d_icp2.cuh"
 #include "ls2d_multi.cuh"
 #include "ls2d_scan.cuh"
 
@@ -127,8 +128,11 @@ dev_params translate(const ls2d_params& p) {
 // ---- kernel table: (threads, points per thread) by cloud size -------------------------------------
 struct shape {
   int threads, ppt, minb;
-  int kind;  // 0: points in registers (icp_fused_kernel); 1: streamed from global/L2; 2: staged in shared memory
+  int kind;  // 0: points in registers (icp_fused_kernel); 1: streamed from global/L2; 2: staged in shared memory;
+             // 3: points in registers, icp_fused2_kernel (compile-time column stride ICP2_CS; needs cols < ICP2_CS)
 };
+
+constexpr int ICP2_CS = 1152;  // column stride of icp_fused2_kernel: covers the 721- and 1081-column canvases
 
 shape pick_shape(int max_points, int variant) {
   if (max_points <= 256) return {128, 2, 6, 0};
@@ -149,7 +153,8 @@ shape pick_shape(int max_points, int variant) {
       case 11: return {384, 0, 4, 1};
       case 12: return {256, 0, 6, 2};
       case 13: return {512, 0, 3, 2};
-      default: return {384, 3, 3, 0};  // measured best on B200 (profiles/r01_variant_sweep.md)
+      case 20: return {384, 3, 3, 0};  // the generic-pointer kernel (before icp_fused2_kernel)
+      default: return {384, 3, 3, 3};  // measured best on B200 (profiles/r01_variant_sweep.md)
     }
   }
   if (max_points <= 1536) return {256, 6, 2, 0};
@@ -165,6 +170,18 @@ int launch_icp_k(ls2d_handle* h, const align_args& a) {
   auto kern         = icp_fused_kernel<T, PPT, SENSOR, MINB>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   // the kernel keeps its working set in shared memory and registers; give it the whole carve-out
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+template <int T, int PPT, bool SENSOR, int MINB>
+int launch_icp2_k(ls2d_handle* h, const align_args& a) {
+  constexpr size_t smem = icp2_map<T, PPT, ICP2_CS>::BYTES;
+  auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, ICP2_CS>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
@@ -200,7 +217,10 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   if (a.n_pairs <= 0) return LS2D_OK;
   const int maxp = h->sets[0].max_points > h->sets[1].max_points ? h->sets[0].max_points
                                                                   : h->sets[1].max_points;
-  const shape s = pick_shape(maxp, h->variant);
+  shape s = pick_shape(maxp, h->variant);
+  if (s.kind == 3 && h->dp.cam.cols >= ICP2_CS) s.kind = 0;  // wider canvases: the run-time-stride kernel
+  if (s.kind == 3 && s.threads == 384 && s.ppt == 3 && s.minb == 3)
+    return h->dp.with_sensor ? launch_icp2_k<384, 3, true, 3>(h, a) : launch_icp2_k<384, 3, false, 3>(h, a);
   if (s.kind == 1 && s.threads == 512) return launch_stream_t<512, false, 2>(h, a, maxp);
   if (s.kind == 1 && s.threads == 384) return launch_stream_t<384, false, 4>(h, a, maxp);
   if (s.kind == 2 && s.threads == 384) return launch_stream_t<384, true, 4>(h, a, maxp);
@@ -1244,6 +1264,13 @@ int ls2d_reduction_threads(int32_t max_points) {
   int variant = 0;
   if (const char* v = getenv("LS2D_ICP_VARIANT")) variant = atoi(v);
   return pick_shape(max_points, variant).threads;
+}
+
+int ls2d_reduction_shape(int32_t max_points, int32_t canvas_cols) {
+  int variant = 0;
+  if (const char* v = getenv("LS2D_ICP_VARIANT")) variant = atoi(v);
+  const shape s = pick_shape(max_points, variant);
+  return s.threads | ((s.kind == 3 && canvas_cols < ICP2_CS) ? 1 << 16 : 0);
 }
 
 int64_t ls2d_launch_count(const ls2d_handle* h) { return h ? h->launches : 0; }

@@ -226,13 +226,16 @@ __device__ __forceinline__ void store_partials(float (&acc)[16], unsigned cnt, f
 // reduction stage 2 + Gauss-Newton step, executed by warp 0 after the barrier: lanes 0..10 add the warps' partials in
 // warp order, lane 0 checks the correspondence gate, solves the 3x3 system in binary64, applies X <- X * v2t(dx)
 // (VariableSE2Right) and publishes the next pose.
-template <int T, bool SENSOR>
+// CANON: add +0.0f to the totals (a kernel whose threads ASSIGN their first contribution can produce -0 where the
+// oracle's 0 + x gives +0; the sum with +0 maps both to the same bits and changes nothing else).
+template <int T, bool SENSOR, bool CANON = false>
 __device__ __forceinline__ void warp0_update(const dev_params& P, const align_args& A, pose_bc* bc, const float* red,
                                              int pair, int it, int lane, float& tot, unsigned& tot_cnt) {
   if (lane < NSUM) {
     tot = red[lane];
 #pragma unroll
     for (int w = 1; w < T / 32; ++w) tot = fadd(tot, red[w * RED_STRIDE + lane]);
+    if (CANON) tot = fadd(tot, 0.f);
   } else if (lane == NSUM) {
     tot_cnt = 0;
 #pragma unroll
