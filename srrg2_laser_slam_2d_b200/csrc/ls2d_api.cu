@@ -44,6 +44,7 @@ struct ls2d_handle {
   dev_params dp;
   cloud_set sets[LS2D_MAX_CLOUD_SETS];
   scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior, d_ranges, d_clip;
+  scratch d_edge;  // rounding-edge directions of the projector (polar_cam::edge), rebuilt by ls2d_set_params
   int64_t launches = 0;
   // host pipeline of ls2d_align_pairs_host: uploads run on their own stream, one event per chunk
   cudaStream_t copy_stream = nullptr;
@@ -154,7 +155,11 @@ shape pick_shape(int max_points, int variant) {
       case 12: return {256, 0, 6, 2};
       case 13: return {512, 0, 3, 2};
       case 20: return {384, 3, 3, 0};  // the generic-pointer kernel (before icp_fused2_kernel)
-      default: return {384, 3, 3, 3};  // measured best on B200 (profiles/r01_variant_sweep.md)
+      case 21: return {288, 4, 4, 3};
+      case 22: return {256, 5, 4, 3};
+      case 23: return {192, 6, 5, 3};
+      case 24: return {384, 3, 3, 3};
+      default: return {288, 4, 4, 3};  // measured best on B200 (profiles/r01_variant_sweep.md)
     }
   }
   if (max_points <= 1536) return {256, 6, 2, 0};
@@ -219,8 +224,14 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
                                                                   : h->sets[1].max_points;
   shape s = pick_shape(maxp, h->variant);
   if (s.kind == 3 && h->dp.cam.cols >= ICP2_CS) s.kind = 0;  // wider canvases: the run-time-stride kernel
-  if (s.kind == 3 && s.threads == 384 && s.ppt == 3 && s.minb == 3)
-    return h->dp.with_sensor ? launch_icp2_k<384, 3, true, 3>(h, a) : launch_icp2_k<384, 3, false, 3>(h, a);
+#define LS2D_CASE2(T, P, B)                                              \
+  if (s.kind == 3 && s.threads == T && s.ppt == P && s.minb == B)         \
+    return h->dp.with_sensor ? launch_icp2_k<T, P, true, B>(h, a) : launch_icp2_k<T, P, false, B>(h, a);
+  LS2D_CASE2(384, 3, 3)
+  LS2D_CASE2(288, 4, 4)
+  LS2D_CASE2(256, 5, 4)
+  LS2D_CASE2(192, 6, 5)
+#undef LS2D_CASE2
   if (s.kind == 1 && s.threads == 512) return launch_stream_t<512, false, 2>(h, a, maxp);
   if (s.kind == 1 && s.threads == 384) return launch_stream_t<384, false, 4>(h, a, maxp);
   if (s.kind == 2 && s.threads == 384) return launch_stream_t<384, true, 4>(h, a, maxp);
@@ -246,6 +257,20 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   LS2D_CASE(512, 8, 1)
 #undef LS2D_CASE
   return LS2D_ERR_UNSUPPORTED;
+}
+
+// device copy of the projector's rounding edges (second tier of the column decision, ls2d_math.cuh)
+int upload_edges(ls2d_handle* h) {
+  std::vector<polar_edge> edges((size_t) h->dp.cam.cols + 1);
+  fill_polar_edges(h->dp.cam, edges.data());
+  const size_t bytes = edges.size() * sizeof(polar_edge);
+  h->dp.cam.edge = nullptr;
+  int rc = reserve(h->d_edge, bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->d_edge.p, edges.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));  // `edges` is pageable and dies here
+  h->dp.cam.edge = static_cast<const polar_edge*>(h->d_edge.p);
+  return LS2D_OK;
 }
 
 bool ready(const ls2d_handle* h) { return h->sets[0].pts && h->sets[1].pts && h->sets[0].off && h->sets[1].off; }
@@ -322,6 +347,11 @@ int ls2d_create(ls2d_handle** out, int device) {
   h->stream = h->own_stream;
   ls2d_default_params(&h->prm);
   h->dp = translate(h->prm);
+  if (upload_edges(h) != LS2D_OK) {
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return LS2D_ERR_CUDA;
+  }
   if (const char* v = getenv("LS2D_ICP_VARIANT")) h->variant = atoi(v);
   *out = h;
   return LS2D_OK;
@@ -342,6 +372,7 @@ int ls2d_destroy(ls2d_handle* h) {
   release(h->d_misc);
   release(h->d_ranges);
   release(h->d_clip);
+  release(h->d_edge);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   for (cudaEvent_t e : h->ev_chunk)
@@ -369,7 +400,8 @@ int ls2d_set_params(ls2d_handle* h, const ls2d_params* p) {
   if (!h || !p || !params_valid(*p)) return LS2D_ERR_INVALID;
   h->prm = *p;
   h->dp  = translate(*p);
-  return LS2D_OK;
+  CU(cudaSetDevice(h->device));
+  return upload_edges(h);
 }
 
 int ls2d_get_params(const ls2d_handle* h, ls2d_params* p) {

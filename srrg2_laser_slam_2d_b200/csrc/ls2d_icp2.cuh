@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
       const float Wtx = sm::ld_f32<BC_WTX>(bca), Wty = sm::ld_f32<BC_WTY>(bca);
       f2 pc[PPT];
       int col[PPT];
-      bool near[PPT];
+      bool near[PPT], up[PPT];
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         const f2 ra = mul2s(mk2(Lc, Ls), mp[j].x), rb2 = mul2s(mk2(-Ls, Lc), mp[j].y);
@@ -337,16 +337,20 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
         const f2 pq = mul2(pc[j], pc[j]);
         const float rho = fsqrt(fadd(pq.x, pq.y));
         rb[j]       = f2u(rho);
-        col[j]      = polar_column_fast(P.cam, pc[j].y, pc[j].x, near[j]);
+        col[j]      = polar_column_fast2(P.cam, pc[j].y, pc[j].x, near[j], up[j]);
         near[j]     = near[j] && !(rho < P.range_min || rho > P.range_max);
       }
       bool any_near = false;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) any_near |= near[j];
-      if (any_near) {
+      if (any_near) {  // rare: second tier (side of the rounding edge), then the exact atan2f
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
-          if (near[j]) col[j] = polar_column_exact(P.cam, pc[j].y, pc[j].x);
+          if (near[j]) {
+            bool undecided;
+            const int c2 = polar_column_edge(P.cam, pc[j].y, pc[j].x, u2f(rb[j]), col[j] + (up[j] ? 1 : 0), undecided);
+            col[j]       = undecided ? polar_column_exact(P.cam, pc[j].y, pc[j].x) : c2;
+          }
       }
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {

@@ -26,6 +26,8 @@ def mc():
     L.ls2d_host_atan2f_n.argtypes = [vp, vp, vp, C.c_long]
     L.ls2d_host_sincosf_n.argtypes = [vp, vp, vp, C.c_long]
     L.ls2d_host_polar_column_n.argtypes = [C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, C.c_long]
+    L.ls2d_host_polar_column_tiered_n.argtypes = [C.c_int, C.c_float, C.c_float, vp, vp, vp, vp, C.c_long]
+    L.ls2d_host_edge_tol.argtypes, L.ls2d_host_edge_tol.restype = [C.c_int, C.c_float, C.c_float], C.c_float
     L.ls2d_host_margin.argtypes, L.ls2d_host_margin.restype = [C.c_int, C.c_float, C.c_float], C.c_float
     L.ls2d_host_atan2f_fast.argtypes, L.ls2d_host_atan2f_fast.restype = [C.c_float, C.c_float], C.c_float
     return L
@@ -96,3 +98,32 @@ def test_fast_atan2_error_budget(mc):
                                                                             np.float32(x).astype(np.float64))))
     assert worst < 1.2e-6
     assert mc.ls2d_host_margin(1081, -3.14159, 3.14159) < 1e-3
+
+
+@pytest.mark.parametrize("cols,amin,amax", [(1081, -3.14159, 3.14159), (721, -3.14159, 3.14159),
+                                            (1081, -2.35619, 2.35619), (1024, -1.2566371, 1.2566371),
+                                            (361, -3.14159, 3.14159)])
+def test_tiered_column_never_disagrees_with_exact(mc, cols, amin, amax):
+    """icp_fused2_kernel's three tiers (fast proposal -> side of the rounding edge's ray in binary64 -> exact
+    atan2f) against the exact path alone, with most samples packed tightly around the rounding edges"""
+    rng = np.random.default_rng(cols + 17)
+    n = 4_000_000
+    r = rng.uniform(0.05, 25, n)
+    a = rng.uniform(-np.pi, np.pi, n)
+    k00 = np.float32(cols) / (np.float32(amax) - np.float32(amin))
+    k01 = np.float32(cols) * np.float32(0.5)
+    m = 3 * n // 4
+    spread = np.repeat([3e-6, 1e-6, 3e-7, 5e-8], m // 4)          # down to well inside edge_tol
+    edge = (rng.integers(-2, cols + 2, m) + 0.5 - float(k01)) / float(k00) + rng.normal(0, 1, m) * spread
+    a[:m] = np.clip(edge, -np.pi, np.pi)
+    x, y = (r * np.cos(a)).astype(np.float32), (r * np.sin(a)).astype(np.float32)
+    col, tier = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    fast, exact = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    mc.ls2d_host_polar_column_tiered_n(cols, amin, amax, _p(y), _p(x), _p(col), _p(tier), n)
+    mc.ls2d_host_polar_column_n(cols, amin, amax, _p(y), _p(x), _p(fast), _p(exact), n)
+    assert np.array_equal(col, exact)
+    # the second tier does take work off the exact path, even on this edge-packed sample
+    n2, n3 = int((tier == 2).sum()), int((tier == 3).sum())
+    assert n2 > 0 and n3 > 0
+    assert 5e-7 < mc.ls2d_host_edge_tol(cols, amin, amax) < 5e-6
+    print("cols %d: tier 2 decided %d, tier 3 (exact) %d of %d near points" % (cols, n2, n3, n2 + n3))
