@@ -42,7 +42,7 @@ def test_host_side_helpers_need_no_gpu():
     lib = _abi.load()
     assert lib.ls2d_version() == 100
     assert lib.ls2d_strerror(0) == b"ok"
-    assert _abi.reduction_threads(1081) & 0xFFFF in (128, 192, 256, 384)
+    assert _abi.reduction_threads(1081) & 0xFFFF in (128, 192, 256, 288, 384)
     assert lib.ls2d_reduction_threads(1081) == _abi.reduction_threads(1081) & 0xFFFF
     assert _abi.reduction_threads(100000) == 0
     rec = np.zeros(4, _abi.BEST_DTYPE)
