@@ -45,6 +45,8 @@ struct ls2d_handle {
   cloud_set sets[LS2D_MAX_CLOUD_SETS];
   scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior, d_ranges, d_clip;
   scratch d_edge;  // rounding-edge directions of the projector (polar_cam::edge), rebuilt by ls2d_set_params
+  scratch d_edge_slice[LS2D_MAX_SLICES];  // the same for the slices of ls2d_align_multi, cached by camera
+  polar_cam edge_slice_key[LS2D_MAX_SLICES] = {};
   int64_t launches = 0;
   // host pipeline of ls2d_align_pairs_host: uploads run on their own stream, one event per chunk
   cudaStream_t copy_stream = nullptr;
@@ -273,6 +275,24 @@ int upload_edges(ls2d_handle* h) {
   return LS2D_OK;
 }
 
+// edge table of slice `slot` of the multi-slice aligner: uploaded when the slice's camera changes
+int slice_edges(ls2d_handle* h, int slot, polar_cam& cam) {
+  polar_cam& key = h->edge_slice_key[slot];
+  if (!(h->d_edge_slice[slot].p && key.cols == cam.cols && key.K00 == cam.K00 && key.K01 == cam.K01)) {
+    std::vector<polar_edge> edges((size_t) cam.cols + 1);
+    fill_polar_edges(cam, edges.data());
+    const size_t bytes = edges.size() * sizeof(polar_edge);
+    key.cols = 0;
+    int rc = reserve(h->d_edge_slice[slot], bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->d_edge_slice[slot].p, edges.data(), bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    key = cam;
+  }
+  cam.edge = static_cast<const polar_edge*>(h->d_edge_slice[slot].p);
+  return LS2D_OK;
+}
+
 bool ready(const ls2d_handle* h) { return h->sets[0].pts && h->sets[1].pts && h->sets[0].off && h->sets[1].off; }
 
 int h2d(ls2d_handle* h, scratch& s, const void* src, size_t bytes) {
@@ -373,6 +393,7 @@ int ls2d_destroy(ls2d_handle* h) {
   release(h->d_ranges);
   release(h->d_clip);
   release(h->d_edge);
+  for (scratch& e : h->d_edge_slice) release(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   for (cudaEvent_t e : h->ev_chunk)
@@ -629,6 +650,7 @@ static int multi_dev_impl(ls2d_handle* h, const ls2d_params* slices, const int32
     const cloud_set& m = h->sets[mset[s]];
     if (!f.pts || !f.off || !m.pts || !m.off) return LS2D_ERR_NOT_READY;
     a.sl[s].P          = translate(slices[s]);
+    if (int rc = slice_edges(h, s, a.sl[s].P.cam)) return rc;
     a.sl[s].fixed_pts  = f.pts;
     a.sl[s].fixed_off  = f.off;
     a.sl[s].moving_pts = m.pts;

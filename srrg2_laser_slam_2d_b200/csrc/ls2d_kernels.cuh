@@ -504,7 +504,7 @@ __device__ __forceinline__ void project_and_stash(const dev_params& P, const pos
     f2 pc[U];
     unsigned rbv[U];
     int colv[U];
-    bool near[U];
+    bool near[U], up[U];
     bool any_near = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -515,14 +515,18 @@ __device__ __forceinline__ void project_and_stash(const dev_params& P, const pos
       const f2 pq = mul2(pc[u], pc[u]);
       const float rho = fsqrt(fadd(pq.x, pq.y));
       rbv[u]      = f2u(rho);
-      colv[u]     = polar_column_fast(P.cam, pc[u].y, pc[u].x, near[u]);
+      colv[u]     = polar_column_fast2(P.cam, pc[u].y, pc[u].x, near[u], up[u]);
       near[u]     = near[u] && i < nm && !(rho < P.range_min || rho > P.range_max);
       any_near |= near[u];
     }
-    if (any_near) {
+    if (any_near) {  // rare: side of the rounding edge's ray (when the camera carries an edge table), then exact atan2f
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (near[u]) colv[u] = polar_column_exact(P.cam, pc[u].y, pc[u].x);
+        if (near[u]) {
+          bool undecided;
+          const int c2 = polar_column_edge(P.cam, pc[u].y, pc[u].x, u2f(rbv[u]), colv[u] + (up[u] ? 1 : 0), undecided);
+          colv[u]      = undecided ? polar_column_exact(P.cam, pc[u].y, pc[u].x) : c2;
+        }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
