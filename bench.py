@@ -270,15 +270,15 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(hout.nbytes), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),  # timed region of `value`; the scoring pass adds its own
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic("icp_fused_kernel"), "peak_source": peak_src,
-                         "kernel": "icp_fused_kernel", "algorithmic_bytes_per_launch": A_PAIR_BYTES * n_pairs,
+                         "traffic": recorded_traffic("icp_fused2_kernel"), "peak_source": peak_src,
+                         "kernel": "icp_fused2_kernel", "algorithmic_bytes_per_launch": A_PAIR_BYTES * n_pairs,
                          "mean_launch_ms": mean_launch_s * 1e3,
                          "note": "10 fused iterations per pair make this kernel issue-bound, not HBM-bound "
                                  "(SURVEY.md 8d); see DESIGN.md for the instruction-issue roofline"},
             "clocks": clk,
             "e2e_gpu_launches": int(e2e_launches),
         }
-        inst = recorded_traffic("icp_fused_kernel_warp_instructions")
+        inst = recorded_traffic("icp_fused2_kernel_warp_instructions")
         if inst and clk and clk.get("sm_mhz"):
             issue_peak = 148 * 4 * clk["sm_mhz"] * 1e6          # warp instructions / s: 4 schedulers per SM
             line["roofline_issue"] = {"bound": "issue", "achieved": inst / mean_launch_s, "peak": issue_peak,
