@@ -113,12 +113,15 @@ def dist_env():
     return rank, int(os.environ.get("LOCAL_RANK", rank)), world
 
 
+N_BEAMS = 1081  # --beams (align workload only): 721 = the scan shape of the shipped configurations
+
+
 def make_workload(n_pairs: int, seed: int, device: str, loop: bool = False):
     from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
     if loop:
         return make_scan_pairs(n_pairs, seed=seed, device=device, motion_xy=0.4, motion_theta=0.2,
                                init_noise_xy=0.2, init_noise_theta=0.08)
-    return make_scan_pairs(n_pairs, seed=seed, device=device)
+    return make_scan_pairs(n_pairs, n_beams=N_BEAMS, seed=seed, device=device)
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -189,8 +192,8 @@ def run_ours(args):
     mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
     init = torch.from_numpy(sp.init_xyt).to(dev)
     out = torch.zeros(n_pairs * 16, dtype=torch.int32, device=dev)
-    h.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), n_pairs, 1081)
-    h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), n_pairs, 1081)
+    h.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), n_pairs, N_BEAMS)
+    h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), n_pairs, N_BEAMS)
 
     def step():
         h.align_batch_dev(None, None, init.data_ptr(), n_pairs, out.data_ptr())
@@ -259,7 +262,7 @@ def run_ours(args):
         achieved = A_PAIR_BYTES * n_pairs / mean_launch_s / 1e9
         h2d = hfp.nbytes + hfo.nbytes + hmp.nbytes + hmo.nbytes + hin.nbytes
         line = {
-            "metric": "aligned scan-pairs/sec (1081 beams, 10 GN iters)", "value": value, "unit": "pairs/s",
+            "metric": "aligned scan-pairs/sec (%d beams, 10 GN iters)" % N_BEAMS, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "batched scan-to-local-map registration: %d pairs x 1081 beams, 10 GN iterations, "
@@ -654,6 +657,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["align", "verify", "track", "allpairs", "multi"], default="align")
     ap.add_argument("--pairs", type=int, default=4096)
+    ap.add_argument("--beams", type=int, default=1081, help="align: beams per scan = canvas columns (headline: 1081)")
     ap.add_argument("--candidates", type=int, default=65536)
     ap.add_argument("--guesses", type=int, default=8)
     ap.add_argument("--unique", type=int, default=4096)
@@ -665,6 +669,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.beams != 1081:  # side measurement on another scan shape; the headline stays 1081 beams
+        global N_BEAMS, A_PAIR_BYTES
+        N_BEAMS, A_PAIR_BYTES = args.beams, 16 * args.beams + 16 * args.beams + 16 + 64
+        TRACK["canvas_cols"] = args.beams
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "verify":

@@ -132,15 +132,22 @@ dev_params translate(const ls2d_params& p) {
 struct shape {
   int threads, ppt, minb;
   int kind;  // 0: points in registers (icp_fused_kernel); 1: streamed from global/L2; 2: staged in shared memory;
-             // 3: points in registers, icp_fused2_kernel (compile-time column stride ICP2_CS; needs cols < ICP2_CS)
+             // 3: points in registers, icp_fused2_kernel (compile-time column stride cs; needs cols < cs)
+  int cs;    // kind 3: column stride (768 covers the 721-column canvas of the shipped configurations, 1152 the
+             // 1081-column one); wider canvases fall back to kind 0
 };
-
-constexpr int ICP2_CS = 1152;  // column stride of icp_fused2_kernel: covers the 721- and 1081-column canvases
 
 shape pick_shape(int max_points, int variant) {
   if (max_points <= 256) return {128, 2, 6, 0};
   if (max_points <= 512) return {128, 4, 6, 0};
-  if (max_points <= 768) return {256, 3, 3, 0};
+  if (max_points <= 768) {
+    switch (variant) {
+      case 40: return {256, 3, 3, 0};  // the generic-pointer kernel
+      case 41: return {256, 3, 4, 3, 768};
+      case 42: return {192, 4, 5, 3, 768};
+      default: return {256, 3, 5, 3, 768};  // 721 beams: 0.276 ms per 4096 pairs (192 x 4 x 5: 0.285, kind 0: 0.358)
+    }
+  }
   if (max_points <= 1152) {
     switch (variant) {  // LS2D_ICP_VARIANT: tuning knob, see profiles/r01_variant_sweep.md
       case 1: return {128, 9, 4, 0};
@@ -157,11 +164,11 @@ shape pick_shape(int max_points, int variant) {
       case 12: return {256, 0, 6, 2};
       case 13: return {512, 0, 3, 2};
       case 20: return {384, 3, 3, 0};  // the generic-pointer kernel (before icp_fused2_kernel)
-      case 21: return {288, 4, 4, 3};
-      case 22: return {256, 5, 4, 3};
-      case 23: return {192, 6, 5, 3};
-      case 24: return {384, 3, 3, 3};
-      default: return {288, 4, 4, 3};  // measured best on B200 (profiles/r01_variant_sweep.md)
+      case 21: return {288, 4, 4, 3, 1152};
+      case 22: return {256, 5, 4, 3, 1152};
+      case 23: return {192, 6, 5, 3, 1152};
+      case 24: return {384, 3, 3, 3, 1152};
+      default: return {288, 4, 4, 3, 1152};  // measured best on B200 (profiles/r01_variant_sweep.md)
     }
   }
   if (max_points <= 1536) return {256, 6, 2, 0};
@@ -184,10 +191,10 @@ int launch_icp_k(ls2d_handle* h, const align_args& a) {
   return LS2D_OK;
 }
 
-template <int T, int PPT, bool SENSOR, int MINB>
+template <int T, int PPT, bool SENSOR, int MINB, int CS>
 int launch_icp2_k(ls2d_handle* h, const align_args& a) {
-  constexpr size_t smem = icp2_map<T, PPT, ICP2_CS>::BYTES;
-  auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, ICP2_CS>;
+  constexpr size_t smem = icp2_map<T, PPT, CS>::BYTES;
+  auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, CS>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
@@ -225,14 +232,21 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   const int maxp = h->sets[0].max_points > h->sets[1].max_points ? h->sets[0].max_points
                                                                   : h->sets[1].max_points;
   shape s = pick_shape(maxp, h->variant);
-  if (s.kind == 3 && h->dp.cam.cols >= ICP2_CS) s.kind = 0;  // wider canvases: the run-time-stride kernel
-#define LS2D_CASE2(T, P, B)                                              \
-  if (s.kind == 3 && s.threads == T && s.ppt == P && s.minb == B)         \
-    return h->dp.with_sensor ? launch_icp2_k<T, P, true, B>(h, a) : launch_icp2_k<T, P, false, B>(h, a);
-  LS2D_CASE2(384, 3, 3)
-  LS2D_CASE2(288, 4, 4)
-  LS2D_CASE2(256, 5, 4)
-  LS2D_CASE2(192, 6, 5)
+  if (s.kind == 3 && h->dp.cam.cols >= s.cs) {  // wider canvases: the run-time-stride kernel
+    s.kind = 0;
+    if (s.threads == 192 && s.ppt == 4) s = {256, 3, 3, 0, 0};
+    if (s.threads == 256 && s.ppt == 3) s.minb = 3;
+  }
+#define LS2D_CASE2(T, P, B, CS)                                                        \
+  if (s.kind == 3 && s.threads == T && s.ppt == P && s.minb == B && s.cs == CS)         \
+    return h->dp.with_sensor ? launch_icp2_k<T, P, true, B, CS>(h, a) : launch_icp2_k<T, P, false, B, CS>(h, a);
+  LS2D_CASE2(384, 3, 3, 1152)
+  LS2D_CASE2(288, 4, 4, 1152)
+  LS2D_CASE2(256, 5, 4, 1152)
+  LS2D_CASE2(192, 6, 5, 1152)
+  LS2D_CASE2(192, 4, 5, 768)
+  LS2D_CASE2(256, 3, 4, 768)
+  LS2D_CASE2(256, 3, 5, 768)
 #undef LS2D_CASE2
   if (s.kind == 1 && s.threads == 512) return launch_stream_t<512, false, 2>(h, a, maxp);
   if (s.kind == 1 && s.threads == 384) return launch_stream_t<384, false, 4>(h, a, maxp);
@@ -1323,8 +1337,12 @@ int ls2d_reduction_threads(int32_t max_points) {
 int ls2d_reduction_shape(int32_t max_points, int32_t canvas_cols) {
   int variant = 0;
   if (const char* v = getenv("LS2D_ICP_VARIANT")) variant = atoi(v);
-  const shape s = pick_shape(max_points, variant);
-  return s.threads | ((s.kind == 3 && canvas_cols < ICP2_CS) ? 1 << 16 : 0);
+  shape s = pick_shape(max_points, variant);
+  if (s.kind == 3 && canvas_cols >= s.cs) {  // launch_icp()'s fallback
+    if (s.threads == 192 && s.ppt == 4) s.threads = 256;
+    s.kind = 0;
+  }
+  return s.threads | (s.kind == 3 ? 1 << 16 : 0);
 }
 
 int64_t ls2d_launch_count(const ls2d_handle* h) { return h ? h->launches : 0; }

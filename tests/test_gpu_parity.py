@@ -66,7 +66,7 @@ def test_golden_alignment(handle_factory, oracle, name):
     # (1) bit-exact against the oracle run in the kernel's summation order
     prm = gu.make_params(oracle.default_params, d)
     o, oi = oracle.align_batch(prm, d["fixed_pts"], d["fixed_off"], d["moving_pts"], d["moving_off"], d["init_xyt"],
-                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(max_points(d)))
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(max_points(d), int(prm.canvas_cols)))
     assert_bit_exact(g, o, gi, oi)
     # (2) within tolerance of the frozen fixture (the reference's sequential summation order)
     ref = d["results"]
@@ -127,7 +127,7 @@ def test_seeded_batch_tree_bit_exact_and_sequential_tolerance(handle_factory, or
     prm = oracle.default_params(**kw)
     nt = oracle.max_threads()
     o, oi = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
-                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(n_beams), n_threads=nt)
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(n_beams, kw["canvas_cols"]), n_threads=nt)
     assert_bit_exact(g, o, gi, oi)
     s, _ = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt, n_threads=nt)
     rate, int_rate = tolerance_rate(g, s)
@@ -153,7 +153,7 @@ def test_loop_closure_parameters_30_iterations(handle_factory, oracle):
     upload(h, sp)
     g, gi = h.align_batch(sp.init_xyt, want_iters=True)
     o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
-                               sp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1081),
+                               sp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1081, kw["canvas_cols"]),
                                n_threads=oracle.max_threads())
     assert_bit_exact(g, o, gi, oi)
 
@@ -167,7 +167,7 @@ def test_sensor_offset_and_no_robustifier(handle_factory, oracle, with_sensor, t
     upload(h, sp)
     g, gi = h.align_batch(sp.init_xyt, want_iters=True)
     o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
-                               sp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(721))
+                               sp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(721, kw["canvas_cols"]))
     assert_bit_exact(g, o, gi, oi)
 
 
@@ -193,7 +193,7 @@ def test_ragged_empty_and_degenerate_clouds(handle_factory, oracle):
     h.upload_clouds(LS2D_MOVING, m_pts, m_off)
     g, gi = h.align_batch(init, fid, mid, want_iters=True)
     o, oi = oracle.align_batch(oracle.default_params(**kw), f_pts, f_off, m_pts, m_off, init, fid, mid,
-                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(500))
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(500, kw["canvas_cols"]))
     assert_bit_exact(g, o, gi, oi)
     assert (g["status"][:5] != 0).all() and g["status"][5] == 0
     for p in (0, 1, 3, 4):
@@ -230,7 +230,7 @@ def test_status_codes_match_the_oracle(handle_factory, oracle):
         g = h.align_batch(sp.init_xyt)
         o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts,
                                   sp.moving_off, sp.init_xyt, sum_mode=oracle.SUM_TREE,
-                                  tree_threads=reduction_threads(361))
+                                  tree_threads=reduction_threads(361, kw["canvas_cols"]))
         assert_bit_exact(g, o)
         assert (g["status"] != 0).all()
     # zero normals -> H has an empty diagonal -> SINGULAR, pose untouched
@@ -252,7 +252,7 @@ def test_score_batch_is_the_first_linearisation(handle_factory, oracle):
     s = h.score_batch(sp.gt_xyt)
     prm = oracle.default_params(max_iterations=1, **kw)
     o, oi = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.gt_xyt,
-                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(721))
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(721, kw["canvas_cols"]))
     for f in ("n_corr", "n_inliers", "n_kernelized"):
         assert np.array_equal(s[f], o[f])
     assert np.array_equal(gu.bits(s["chi_inliers"]), gu.bits(o["chi_inliers"]))
@@ -278,7 +278,7 @@ def test_verify_gates_and_best_of_match_the_oracle(handle_factory, oracle):
     mid = np.repeat(cand, n_guess)
     o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
                               guesses.reshape(-1, 3), fid, mid, sum_mode=oracle.SUM_TREE,
-                              tree_threads=reduction_threads(721), n_threads=oracle.max_threads())
+                              tree_threads=reduction_threads(721, kw["canvas_cols"]), n_threads=oracle.max_threads())
     assert_bit_exact(allr, o)
     ob = oracle.best_of(o, 300, 0.1, 0.8)
     assert ob >= 0 and cand[ob // n_guess] == 0                  # the true match wins
@@ -320,7 +320,7 @@ def test_full_size_batch_properties(handle_factory, oracle):
     sample = rng.choice(n, 64, replace=False)
     o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
                               init[sample], ids[sample], ids[sample], sum_mode=oracle.SUM_TREE,
-                              tree_threads=reduction_threads(1081), n_threads=oracle.max_threads())
+                              tree_threads=reduction_threads(1081, kw["canvas_cols"]), n_threads=oracle.max_threads())
     assert_bit_exact(a[sample], o)
 
 
@@ -367,7 +367,7 @@ def test_zbuffer_ties_first_index_wins(handle_factory, oracle):
     g, gi = h.align_batch(sp.init_xyt, want_iters=True)
     prm = oracle.default_params(**kw)
     o, oi = oracle.align_batch(prm, fixed.reshape(-1, 4), off, moving.reshape(-1, 4), off, sp.init_xyt,
-                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1000))
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1000, kw["canvas_cols"]))
     assert_bit_exact(g, o, gi, oi)
     for p in range(3):
         fi, mi, _, _ = oracle.find_correspondences(prm, fixed[p], moving[p], sp.init_xyt[p])
@@ -389,7 +389,7 @@ def test_streaming_kernel_variants_are_bit_exact(oracle, variant, monkeypatch):
         g, gi = h.align_batch(sp.init_xyt, want_iters=True)
         o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts,
                                    sp.moving_off, sp.init_xyt, sum_mode=oracle.SUM_TREE,
-                                   tree_threads=reduction_threads(1081), n_threads=oracle.max_threads())
+                                   tree_threads=reduction_threads(1081, kw["canvas_cols"]), n_threads=oracle.max_threads())
     assert_bit_exact(g, o, gi, oi)
 
 
@@ -447,7 +447,7 @@ def test_verify_pairs_per_group_best_matches_the_oracle(handle_factory, oracle):
     gates = Gates(250, 0.1, 0.8)
     best, allr = h.verify_pairs(fid, mid, guesses, groups, gates, want_all=True)
     o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
-                              guesses, fid, mid, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(n_pts),
+                              guesses, fid, mid, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(n_pts, kw["canvas_cols"]),
                               n_threads=oracle.max_threads())
     assert_bit_exact(allr, o)
     hits = 0

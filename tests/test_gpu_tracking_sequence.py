@@ -59,7 +59,7 @@ def test_tracker_chain_is_bit_identical_and_follows_ground_truth(handle_factory,
             else:
                 clip = oracle.clip_scene(prm, scene, guess, (0.0, 0.0, 0.0))
                 res, _ = oracle.align(prm, meas, clip, zero[0], sum_mode=oracle.SUM_TREE,
-                                      tree_threads=reduction_threads(max(len(meas), len(clip))))
+                                      tree_threads=reduction_threads(max(len(meas), len(clip)), cols))
             assert res["status"] == 0
             # X maps the clipped scene (robot frame at the guess) onto the measurement (true robot frame)
             X = v2t(np.array([res["x"], res["y"], res["theta"]], np.float64))
