@@ -17,6 +17,14 @@
  * fixture pre-processes into exactly 100 points (tests/test_measurement_adaptor.cpp:36) -- is checked
  * in tests/test_oracle_preprocess.py.
  *
+ * PARTLY PINNED AGAINST THE REFERENCE'S OWN SOURCES: three in-repo files -- correspondence_finder_projective_2d.cpp,
+ * merger_projective_2d.cpp, scene_clipper_projective_2d.cpp -- are compiled where they lie under /root/reference,
+ * unmodified, against stand-in headers for the absent libraries (oracle/ref_shim/, oracle/ref_harness.cpp ->
+ * oracle/_ref/libls2d_ref.so, built by oracle/Makefile) and orc_find_correspondences / orc_merge / orc_clip_scene
+ * must agree with them bit for bit (tests/test_oracle_vs_reference_sources.py).  That pins the control flow the
+ * reference itself owns (gates, strictness, ordering, caching, the merger's decision tree); the upstream arithmetic
+ * (projector, factor, robustifier, solver) is the oracle's own in both arms and stays unpinned.
+ *
  * Arithmetic contract: every floating-point operation below is ONE IEEE-754 binary32
  * operation (no FMA contraction; build with -ffp-contract=off), in the order Eigen
  * evaluates the reference's expressions; transcendental functions are glibc's

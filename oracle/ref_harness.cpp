@@ -1,0 +1,110 @@
+// ref_harness.cpp -- TEST INFRASTRUCTURE.  C entry points over the reference's OWN classes, compiled from the
+// reference's own sources where they lie under /root/reference (see oracle/Makefile, target _ref/libls2d_ref.so) against
+// the stand-in headers of oracle/ref_shim/.  Drives them the way the reference's apps do
+// (apps/visual_test_correspondence_finder_projective_2d.cpp:73-79, apps/visual_test_merger_projective_2d.cpp:100-125).
+#include "srrg2_laser_slam_2d/mapping/merger_projective_2d.h"
+#include "srrg2_laser_slam_2d/mapping/scene_clipper_projective_2d.h"
+#include "srrg2_laser_slam_2d/registration/correspondence_finder_projective_2d.h"
+
+using namespace srrg2_core;
+using namespace srrg2_laser_slam_2d;
+
+namespace {
+  void to_cloud(const orc_point* p, int32_t n, PointNormal2fVectorCloud& c) {
+    c.resize((size_t) n);
+    for (int32_t i = 0; i < n; ++i) {
+      c[(size_t) i].coordinates() = Vector2f(p[i].x, p[i].y);
+      c[(size_t) i].normal()      = Vector2f(p[i].nx, p[i].ny);
+    }
+  }
+  void from_cloud(const PointNormal2fVectorCloud& c, orc_point* p) {
+    for (size_t i = 0; i < c.size(); ++i) {
+      p[i].x = c[i].coordinates().x(), p[i].y = c[i].coordinates().y();
+      p[i].nx = c[i].normal().x(), p[i].ny = c[i].normal().y();
+    }
+  }
+  void configure(PointNormal2fProjectorPolar& pr, const orc_params* prm) {
+    pr.param_canvas_cols.setValue(prm->canvas_cols);
+    pr.param_angle_col_min.setValue(prm->angle_col_min);
+    pr.param_angle_col_max.setValue(prm->angle_col_max);
+    pr.param_range_min.setValue(prm->range_min);
+    pr.param_range_max.setValue(prm->range_max);
+  }
+  Isometry2f iso(const float* xyt) { return Isometry2f(orc_v2t(xyt[0], xyt[1], xyt[2])); }
+}  // namespace
+
+extern "C" {
+
+// CorrespondenceFinderProjective2f::compute(); n_calls > 1 repeats compute() on the same object with the poses
+// xyt[3 * k] (exercises the _fixed_changed_flag caching, .cpp:37-44); the LAST call's list is returned
+int32_t ref_find_correspondences(const orc_params* prm, const orc_point* fixed, int32_t n_fixed, const orc_point* moving,
+                                 int32_t n_moving, const float* xyt, int32_t n_calls, int32_t* fixed_idx,
+                                 int32_t* moving_idx) {
+  PointNormal2fVectorCloud f, m;
+  to_cloud(fixed, n_fixed, f);
+  to_cloud(moving, n_moving, m);
+  CorrespondenceFinderProjective2f cf;
+  configure(*cf.param_projector.value(), prm);
+  cf.param_point_distance.setValue(prm->point_distance);
+  cf.param_normal_cos.setValue(prm->normal_cos);
+  CorrespondenceVector corr;
+  cf.setFixed(&f);
+  cf.setMoving(&m);
+  cf.setCorrespondences(&corr);
+  for (int32_t k = 0; k < n_calls; ++k) {
+    cf.setLocalMapInSensor(iso(xyt + 3 * k));
+    cf.compute();
+  }
+  for (size_t i = 0; i < corr.size(); ++i) {
+    fixed_idx[i]  = corr[i].fixed_idx;
+    moving_idx[i] = corr[i].moving_idx;
+  }
+  return (int32_t) corr.size();
+}
+
+// MergerProjective2D::compute(): scene must have room for n_scene + canvas_cols points; returns the new size
+int32_t ref_merge(const orc_params* prm, float merge_threshold, orc_point* scene, int32_t n_scene,
+                  const orc_point* measurement, int32_t n_measurement, const float* measurement_in_scene_xyt) {
+  PointNormal2fVectorCloud s, m;
+  to_cloud(scene, n_scene, s);
+  to_cloud(measurement, n_measurement, m);
+  MergerProjective2D mg;
+  configure(*mg.param_projector.value(), prm);
+  mg.param_merge_threshold.setValue(merge_threshold);
+  mg.setScene(&s);
+  mg.setMeasurement(&m);
+  mg.setMeasurementInScene(iso(measurement_in_scene_xyt));
+  mg.compute();
+  from_cloud(s, scene);
+  return (int32_t) s.size();
+}
+
+// SceneClipperProjective2D::compute() with voxelize_resolution 0 (both shipped configurations); out holds
+// canvas_cols points; returns the count, or -1 when the module reports Error
+int32_t ref_clip(const orc_params* prm, const orc_point* scene, int32_t n_scene, const float* robot_in_local_map_xyt,
+                 const float* sensor_in_robot_xyt, orc_point* out) {
+  PointNormal2fVectorCloud full, clipped;
+  to_cloud(scene, n_scene, full);
+  SceneClipperProjective2D cl;
+  configure(*cl.param_projector.value(), prm);
+  cl.param_voxelize_resolution.setValue(0.f);
+  cl.setFullScene(&full);
+  cl.setClippedSceneInRobot(&clipped);
+  cl.setRobotInLocalMap(iso(robot_in_local_map_xyt));
+  cl.setSensorInRobot(iso(sensor_in_robot_xyt));
+  cl.compute();
+  from_cloud(clipped, out);
+  return (int32_t) clipped.size();
+}
+
+// mis-wiring must throw std::runtime_error (correspondence_finder_projective_2d.cpp:20-31): 1 = it did
+int32_t ref_finder_throws_without_inputs(void) {
+  CorrespondenceFinderProjective2f cf;
+  try {
+    cf.compute();
+  } catch (const std::runtime_error&) {
+    return 1;
+  }
+  return 0;
+}
+}
