@@ -1078,20 +1078,16 @@ static void smallest_eigenvector_2x2(float m00, float m10, float m11, float* vx,
   }
 }
 
-int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int32_t n_beams, orc_point* out) {
-  if (n_beams <= 0) {
-    return 0;
-  }
-  /* _processLaserMessage, .cpp:83-90 */
-  const float range_max  = sp->msg_range_max < sp->range_max ? sp->msg_range_max : sp->range_max;
-  const float range_min  = sp->msg_range_min > sp->range_min ? sp->msg_range_min : sp->range_min;
-  const float sensor_res = (sp->angle_max - sp->angle_min) / (float) n_beams;
-  const float fx = 1.f / sensor_res, cx = (float) n_beams / 2.f;
+/* the three upstream stages of the pre-processor, separately callable so that the reference's own in-repo source
+ * (compiled against oracle/ref_shim/) can run on top of the very same restatement (tests/test_oracle_vs_reference_sources.py) */
+
+/* PointNormal2fUnprojectorPolar::compute (P1): fx = K(0,0), cx = K(0,1) of the sensor matrix; returns the number of
+ * accepted beams, written to pts in beam order with zero normals */
+int32_t orc_unproject(float range_min, float range_max, float fx, float cx, const float* ranges, int32_t n_beams,
+                      orc_point* pts) {
   const float ifx = 1.f / fx; /* P1 */
-  orc_point* pts   = (orc_point*) malloc(sizeof(orc_point) * (size_t) n_beams);
-  uint8_t* valid   = (uint8_t*) malloc((size_t) n_beams);
   int32_t n = 0;
-  for (int32_t c = 0; c < n_beams; ++c) { /* unprojector, P1 */
+  for (int32_t c = 0; c < n_beams; ++c) {
     const float r = ranges[c];
     if (r < range_min || r > range_max) {
       continue;
@@ -1103,8 +1099,14 @@ int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int3
     pts[n].ny = 0.f;
     ++n;
   }
-  /* NormalComputator1DSlidingWindow::computeNormals (P2..P6) */
-  const float d2 = sp->normal_point_distance * sp->normal_point_distance;
+  return n;
+}
+
+/* NormalComputator1DSlidingWindow::computeNormals (P2..P6): fills the normals of pts in place and valid[i] = 0 for
+ * the points that become Invalid (P3) */
+void orc_sliding_window_normals(orc_point* pts, int32_t n, float normal_point_distance, int32_t normal_min_points,
+                                uint8_t* valid) {
+  const float d2 = normal_point_distance * normal_point_distance;
   for (int32_t i = 0; i < n; ++i) {
     /* one walk over the window, first towards lower indices, then towards higher ones (P2); first and second
      * moments of d_j = p_j - p_i accumulate in walking order (P4); p_i itself contributes d = 0 */
@@ -1130,7 +1132,7 @@ int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int3
       sxx = sxx + dxx, sxy = sxy + dx * dy, syy = syy + dyy;
       ++cnt;
     }
-    valid[i] = cnt >= sp->normal_min_points; /* P3 */
+    valid[i] = cnt >= normal_min_points; /* P3 */
     if (!valid[i]) {
       continue;
     }
@@ -1144,10 +1146,32 @@ int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int3
     }
     pts[i].nx = nx, pts[i].ny = ny;
   }
+}
+
+/* PointCloud::voxelize(out, res_coeffs) (P7): res_coeffs = the four resolutions as the reference's sources write them
+ * ((res, res, 1, 1) in the pre-processor, (res, res, 0.1, 0.1) in the clipper); valid == NULL: all points valid */
+int32_t orc_voxelize(const orc_point* pts, const uint8_t* valid, int32_t n, const float* res_coeffs, orc_point* out) {
+  const float inv[4] = {1.f / res_coeffs[0], 1.f / res_coeffs[1], 1.f / res_coeffs[2], 1.f / res_coeffs[3]};
+  return voxelize_cloud(pts, valid, n, inv, out);
+}
+
+int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int32_t n_beams, orc_point* out) {
+  if (n_beams <= 0) {
+    return 0;
+  }
+  /* _processLaserMessage, .cpp:83-90 */
+  const float range_max  = sp->msg_range_max < sp->range_max ? sp->msg_range_max : sp->range_max;
+  const float range_min  = sp->msg_range_min > sp->range_min ? sp->msg_range_min : sp->range_min;
+  const float sensor_res = (sp->angle_max - sp->angle_min) / (float) n_beams;
+  const float fx = 1.f / sensor_res, cx = (float) n_beams / 2.f;
+  orc_point* pts   = (orc_point*) malloc(sizeof(orc_point) * (size_t) n_beams);
+  uint8_t* valid   = (uint8_t*) malloc((size_t) n_beams);
+  const int32_t n  = orc_unproject(range_min, range_max, fx, cx, ranges, n_beams, pts);               /* .cpp:29-31 */
+  orc_sliding_window_normals(pts, n, sp->normal_point_distance, sp->normal_min_points, valid);       /* .cpp:32 */
   int32_t k = 0;
   if (sp->voxelize_resolution > 0.f) { /* .cpp:38-42, P7: res_coeffs = (res, res, 1, 1) */
-    const float inv[4] = {1.f / sp->voxelize_resolution, 1.f / sp->voxelize_resolution, 1.f / 1.f, 1.f / 1.f};
-    k = voxelize_cloud(pts, valid, n, inv, out);
+    const float res_coeffs[4] = {sp->voxelize_resolution, sp->voxelize_resolution, 1.f, 1.f};
+    k = orc_voxelize(pts, valid, n, res_coeffs, out);
   } else { /* .cpp:44-48, P8 */
     for (int32_t i = 0; i < n; ++i) {
       if (valid[i]) {

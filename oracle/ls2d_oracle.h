@@ -17,11 +17,11 @@
  * fixture pre-processes into exactly 100 points (tests/test_measurement_adaptor.cpp:36) -- is checked
  * in tests/test_oracle_preprocess.py.
  *
- * PARTLY PINNED AGAINST THE REFERENCE'S OWN SOURCES: three in-repo files -- correspondence_finder_projective_2d.cpp,
- * merger_projective_2d.cpp, scene_clipper_projective_2d.cpp -- are compiled where they lie under /root/reference,
+ * PARTLY PINNED AGAINST THE REFERENCE'S OWN SOURCES: four in-repo files -- correspondence_finder_projective_2d.cpp,
+ * merger_projective_2d.cpp, scene_clipper_projective_2d.cpp, raw_data_preprocessor_projective_2d.cpp -- are compiled where they lie under /root/reference,
  * unmodified, against stand-in headers for the absent libraries (oracle/ref_shim/, oracle/ref_harness.cpp ->
- * oracle/_ref/libls2d_ref.so, built by oracle/Makefile) and orc_find_correspondences / orc_merge / orc_clip_scene
- * must agree with them bit for bit (tests/test_oracle_vs_reference_sources.py).  That pins the control flow the
+ * oracle/_ref/libls2d_ref.so, built by oracle/Makefile) and orc_find_correspondences / orc_merge / orc_clip_scene /
+ * orc_preprocess_scan must agree with them bit for bit (tests/test_oracle_vs_reference_sources.py).  That pins the control flow the
  * reference itself owns (gates, strictness, ordering, caching, the merger's decision tree); the upstream arithmetic
  * (projector, factor, robustifier, solver) is the oracle's own in both arms and stays unpinned.
  *
@@ -218,6 +218,14 @@ typedef struct {
 } orc_scan_params;
 
 void orc_default_scan_params(orc_scan_params* p);
+
+/* the pre-processor's three upstream stages (P1, P2..P6, P7), separately callable: orc_preprocess_scan is their
+ * composition by the in-repo logic of raw_data_preprocessor_projective_2d.cpp */
+int32_t orc_unproject(float range_min, float range_max, float fx, float cx, const float* ranges, int32_t n_beams,
+                      orc_point* pts);
+void orc_sliding_window_normals(orc_point* pts, int32_t n, float normal_point_distance, int32_t normal_min_points,
+                                uint8_t* valid);
+int32_t orc_voxelize(const orc_point* pts, const uint8_t* valid, int32_t n, const float* res_coeffs, orc_point* out);
 
 /* one scan; `out` holds n_beams points; returns the number of points produced */
 int32_t orc_preprocess_scan(const orc_scan_params* sp, const float* ranges, int32_t n_beams, orc_point* out);

@@ -5,6 +5,7 @@
 #include "srrg2_laser_slam_2d/mapping/merger_projective_2d.h"
 #include "srrg2_laser_slam_2d/mapping/scene_clipper_projective_2d.h"
 #include "srrg2_laser_slam_2d/registration/correspondence_finder_projective_2d.h"
+#include "srrg2_laser_slam_2d/sensor_processing/raw_data_preprocessor_projective_2d.h"
 
 using namespace srrg2_core;
 using namespace srrg2_laser_slam_2d;
@@ -79,15 +80,15 @@ int32_t ref_merge(const orc_params* prm, float merge_threshold, orc_point* scene
   return (int32_t) s.size();
 }
 
-// SceneClipperProjective2D::compute() with voxelize_resolution 0 (both shipped configurations); out holds
-// canvas_cols points; returns the count, or -1 when the module reports Error
+// SceneClipperProjective2D::compute() (voxelize_resolution 0 in both shipped configurations; > 0 takes the
+// voxelize branch, .cpp:36-48); out holds canvas_cols points; returns the count
 int32_t ref_clip(const orc_params* prm, const orc_point* scene, int32_t n_scene, const float* robot_in_local_map_xyt,
-                 const float* sensor_in_robot_xyt, orc_point* out) {
+                 const float* sensor_in_robot_xyt, float voxelize_resolution, orc_point* out) {
   PointNormal2fVectorCloud full, clipped;
   to_cloud(scene, n_scene, full);
   SceneClipperProjective2D cl;
   configure(*cl.param_projector.value(), prm);
-  cl.param_voxelize_resolution.setValue(0.f);
+  cl.param_voxelize_resolution.setValue(voxelize_resolution);
   cl.setFullScene(&full);
   cl.setClippedSceneInRobot(&clipped);
   cl.setRobotInLocalMap(iso(robot_in_local_map_xyt));
@@ -95,6 +96,32 @@ int32_t ref_clip(const orc_params* prm, const orc_point* scene, int32_t n_scene,
   cl.compute();
   from_cloud(clipped, out);
   return (int32_t) clipped.size();
+}
+
+// RawDataPreprocessorProjective2D: setRawData(LaserMessage) + compute(), driven as
+// apps/visual_test_correspondence_finder_projective_2d.cpp:62-66 does; out holds n_beams points; returns the count
+int32_t ref_preprocess_scan(const orc_scan_params* sp, const float* ranges, int32_t n_beams, orc_point* out) {
+  LaserMessagePtr msg(new LaserMessage);
+  msg->topic = "/scan";
+  msg->ranges.value().assign(ranges, ranges + n_beams);
+  msg->range_min.setValue(sp->msg_range_min);
+  msg->range_max.setValue(sp->msg_range_max);
+  msg->angle_min.setValue(sp->angle_min);
+  msg->angle_max.setValue(sp->angle_max);
+  RawDataPreprocessorProjective2D pre;
+  pre.param_range_min.setValue(sp->range_min);
+  pre.param_range_max.setValue(sp->range_max);
+  pre.param_voxelize_resolution.setValue(sp->voxelize_resolution);
+  pre.param_normal_computator_sliding->param_normal_point_distance.setValue(sp->normal_point_distance);
+  pre.param_normal_computator_sliding->param_normal_min_points.setValue(sp->normal_min_points);
+  RawDataPreprocessorProjective2D::MeasurementType cloud;
+  pre.setMeas(&cloud);
+  if (!pre.setRawData(msg)) {
+    return -1;
+  }
+  pre.compute();
+  from_cloud(cloud, out);
+  return (int32_t) cloud.size();
 }
 
 // mis-wiring must throw std::runtime_error (correspondence_finder_projective_2d.cpp:20-31): 1 = it did

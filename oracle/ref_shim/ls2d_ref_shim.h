@@ -4,16 +4,19 @@
 //     src/srrg2_laser_slam_2d/registration/correspondence_finder_projective_2d.cpp
 //     src/srrg2_laser_slam_2d/mapping/merger_projective_2d.cpp
 //     src/srrg2_laser_slam_2d/mapping/scene_clipper_projective_2d.cpp
+//     src/srrg2_laser_slam_2d/sensor_processing/raw_data_preprocessor_projective_2d.cpp
 // so that the oracle's line-by-line restatement of those files (ls2d_oracle.c: orc_find_correspondences, orc_merge,
-// orc_clip_scene) can be checked against the reference's own compiled control flow (oracle/_ref/libls2d_ref.so,
+// orc_clip_scene[_voxelized], orc_preprocess_scan) can be checked against the reference's own compiled control flow (oracle/_ref/libls2d_ref.so,
 // tests/test_oracle_vs_reference_sources.py).
 //
 // What this does NOT pin: everything that lives upstream.  The polar projector, the isometry algebra and the point
 // arithmetic below are supplied by the oracle's own restatement (orc_project, orc_inverse, orc_compose, decision
-// points D1-D4, D13, D14 of ls2d_oracle.c), because the real ones are absent.  Names, members and call signatures
+// points D1-D4, D13, D14 of ls2d_oracle.c; the unprojector, the sliding-window normals and PointCloud::voxelize by
+// orc_unproject, orc_sliding_window_normals, orc_voxelize, P1-P7), because the real ones are absent.  Names, members and call signatures
 // follow the way the reference's sources and apps use them (cited per item); nothing here is copied from upstream.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <iostream>
@@ -44,7 +47,21 @@ namespace srrg2_core {
   };
 
   struct Matrix2f {
-    float m[4] = {1.f, 0.f, 0.f, 1.f};
+    float m[4] = {1.f, 0.f, 0.f, 1.f};  // row-major
+    static Matrix2f Identity() { return Matrix2f(); }
+    float operator()(int r, int c) const { return m[2 * r + c]; }
+    struct Comma {  // "sensor_matrix << a, b, c, d;"  raw_data_preprocessor_projective_2d.cpp:89-90
+      Matrix2f* t;
+      int k;
+      Comma operator,(double x) {
+        t->m[k] = (float) x;
+        return Comma{t, k + 1};
+      }
+    };
+    Comma operator<<(double x) {
+      m[0] = (float) x;
+      return Comma{this, 1};
+    }
   };
   inline std::ostream& operator<<(std::ostream& os, const Matrix2f& M) {  // printInfo(), finder .cpp:13-14
     return os << M.m[0] << " " << M.m[1] << "\n" << M.m[2] << " " << M.m[3];
@@ -88,6 +105,7 @@ namespace srrg2_core {
   struct Property_ {
     Property_(const char*, const char*, V def, bool* changed_flag) : _value(def), _flag(changed_flag) {}
     const V& value() const { return _value; }
+    V& value() { return _value; }  // "&laser_message->ranges.value()", raw_data_preprocessor_projective_2d.cpp:78
     void setValue(const V& v_) {
       _value = v_;
       if (_flag) {
@@ -99,6 +117,7 @@ namespace srrg2_core {
   };
   using PropertyFloat = Property_<float>;
   using PropertyInt   = Property_<int>;
+  using PropertyString = Property_<std::string>;
 
   template <typename C>
   struct PropertyConfigurable_ {
@@ -182,17 +201,34 @@ namespace srrg2_core {
         p._normal.v[1]      = T.s * nx + T.c * ny;
       }
     }
+    // PointCloud::voxelize(out, res_coeffs): the oracle's restatement (orc_voxelize, P7); Invalid points are skipped
     template <typename OutIt>
-    void voxelize(OutIt, const PlainVectorType&) const {
-      throw std::runtime_error("ls2d_ref_shim| PointCloud::voxelize is not provided (both shipped configurations "
-                               "run the clipper with voxelize_resolution 0)");
+    void voxelize(OutIt out, const PlainVectorType& res_coeffs) const {
+      std::vector<orc_point> in(size()), res(size() ? size() : 1);
+      std::vector<uint8_t> valid(size() ? size() : 1);
+      for (size_t i = 0; i < size(); ++i) {
+        const PointNormal2f& p = (*this)[i];
+        in[i].x = p._coordinates.v[0], in[i].y = p._coordinates.v[1], in[i].nx = p._normal.v[0], in[i].ny = p._normal.v[1];
+        valid[i] = p.status == Valid;
+      }
+      const int32_t k = orc_voxelize(in.data(), valid.data(), (int32_t) size(), res_coeffs.v, res.data());
+      for (int32_t i = 0; i < k; ++i) {
+        PointNormal2f p;
+        p._coordinates = Vector2f(res[(size_t) i].x, res[(size_t) i].y);
+        p._normal      = Vector2f(res[(size_t) i].nx, res[(size_t) i].ny);
+        *out++ = p;
+      }
     }
   };
 
   template <typename E>
   struct Matrix_ {
-    void resize(size_t rows, size_t cols) { _d.assign(rows * cols, E()); }
+    void resize(size_t rows, size_t cols) { _cols = cols, _d.assign(rows * cols, E()); }
     size_t size() const { return _d.size(); }
+    size_t cols() const { return _cols; }
+    E& at(size_t r, size_t c) { return _d[r * _cols + c]; }  // raw_data_preprocessor_projective_2d.cpp:26
+    const E& at(size_t r, size_t c) const { return _d[r * _cols + c]; }
+    size_t _cols = 0;
     typename std::vector<E>::iterator begin() { return _d.begin(); }
     typename std::vector<E>::iterator end() { return _d.end(); }
     typename std::vector<E>::const_iterator begin() const { return _d.begin(); }
@@ -254,6 +290,69 @@ namespace srrg2_core {
   };
   using PointNormal2fProjectorPolarPtr = std::shared_ptr<PointNormal2fProjectorPolar>;
 
+  // PointNormal2fUnprojectorPolar (parameters as LASER_0.json:405-430 names them): compute<WithNormals>() is the
+  // oracle's orc_unproject (P1: reads K(0,0) and K(0,1) of the sensor matrix the in-repo code builds)
+  enum { WithNormals = 1, WithoutNormals = 0 };  // raw_data_preprocessor_projective_2d.cpp:31
+  struct PointNormal2fUnprojectorPolar : public Configurable {
+    PARAM(PropertyFloat, range_min, "min laser range [m]", 0.f, nullptr);
+    PARAM(PropertyFloat, range_max, "max laser range [m]", 1000.f, nullptr);
+    PARAM(PropertyFloat, angle_min, "start angle [rad]", -3.14159f, nullptr);
+    PARAM(PropertyFloat, angle_max, "end angle [rad]", 3.14159f, nullptr);
+    void setCameraMatrix(const Matrix2f& K) { _K = K; }
+    template <int Mode, typename OutIt>
+    void compute(OutIt out, const Matrix_<float>& ranges) {
+      const int32_t n = (int32_t) ranges.size();
+      std::vector<orc_point> pts((size_t)(n > 0 ? n : 1));
+      const int32_t k = orc_unproject(param_range_min.value(), param_range_max.value(), _K(0, 0), _K(0, 1),
+                                      ranges._d.data(), n, pts.data());
+      for (int32_t i = 0; i < k; ++i) {
+        PointNormal2f p;
+        p._coordinates = Vector2f(pts[(size_t) i].x, pts[(size_t) i].y);
+        p._normal      = Vector2f(pts[(size_t) i].nx, pts[(size_t) i].ny);
+        *out++ = p;
+      }
+    }
+    Matrix2f _K;
+  };
+  using PointNormal2fUnprojectorPolarPtr = std::shared_ptr<PointNormal2fUnprojectorPolar>;
+
+  // NormalComputator1DSlidingWindow (LASER_0.json:711-719): the oracle's orc_sliding_window_normals (P2-P6)
+  template <typename CloudType_, int idx_>
+  struct NormalComputator1DSlidingWindow : public Configurable {
+    PARAM(PropertyInt, normal_min_points, "min number of points to compute a normal", 5, nullptr);
+    PARAM(PropertyFloat, normal_point_distance, "max normal point distance", 0.3f, nullptr);
+    void computeNormals(CloudType_& cloud) {
+      const int32_t n = (int32_t) cloud.size();
+      std::vector<orc_point> pts((size_t)(n > 0 ? n : 1));
+      std::vector<uint8_t> valid((size_t)(n > 0 ? n : 1));
+      for (int32_t i = 0; i < n; ++i) {
+        const PointNormal2f& p = cloud[(size_t) i];
+        pts[(size_t) i].x = p._coordinates.v[0], pts[(size_t) i].y = p._coordinates.v[1];
+        pts[(size_t) i].nx = p._normal.v[0], pts[(size_t) i].ny = p._normal.v[1];
+      }
+      orc_sliding_window_normals(pts.data(), n, param_normal_point_distance.value(), param_normal_min_points.value(),
+                                 valid.data());
+      for (int32_t i = 0; i < n; ++i) {
+        PointNormal2f& p = cloud[(size_t) i];
+        p._normal        = Vector2f(pts[(size_t) i].nx, pts[(size_t) i].ny);
+        p.status         = valid[(size_t) i] ? Valid : Invalid;
+      }
+    }
+  };
+
+  // srrg_messages: the fields raw_data_preprocessor_projective_2d.cpp:78-87 reads
+  struct BaseSensorMessage {
+    virtual ~BaseSensorMessage() {}
+    std::string topic;
+  };
+  using BaseSensorMessagePtr = std::shared_ptr<BaseSensorMessage>;
+  struct LaserMessage : public BaseSensorMessage {
+    Property_<std::vector<float>> ranges{"ranges", "", std::vector<float>(), nullptr};
+    PropertyFloat range_min{"range_min", "", 0.f, nullptr}, range_max{"range_max", "", 0.f, nullptr};
+    PropertyFloat angle_min{"angle_min", "", 0.f, nullptr}, angle_max{"angle_max", "", 0.f, nullptr};
+  };
+  using LaserMessagePtr = std::shared_ptr<LaserMessage>;
+
   // srrg_data_structures/correspondence.h
   struct Correspondence {
     int fixed_idx = -1, moving_idx = -1;
@@ -314,6 +413,31 @@ namespace srrg2_slam_interfaces {
     SceneType_* _full_scene              = nullptr;
     SceneType_* _clipped_scene_in_robot = nullptr;
     EstimateType_ _robot_in_local_map, _sensor_in_robot;
+    Status _status = Error;
+  };
+
+  // srrg2_slam_interfaces/raw_data_preprocessors/raw_data_preprocessor.h: members and calls as the in-repo
+  // source and apps/visual_test_correspondence_finder_projective_2d.cpp:62-66 use them
+  template <typename MessageType_>
+  std::shared_ptr<MessageType_> extractMessage(srrg2_core::BaseSensorMessagePtr msg, const std::string& topic) {
+    std::shared_ptr<MessageType_> m = std::dynamic_pointer_cast<MessageType_>(msg);
+    if (m && !topic.empty() && !m->topic.empty() && m->topic != topic) {
+      return nullptr;
+    }
+    return m;
+  }
+  template <typename MeasurementType_>
+  struct RawDataPreprocessor_ : public srrg2_core::Configurable {
+    using MeasurementType = MeasurementType_;
+    enum Status { Error = 0, Ready = 1 };
+    void setMeas(MeasurementType_* m) { _meas = m; }
+    virtual bool setRawData(srrg2_core::BaseSensorMessagePtr msg) {
+      _raw_data = msg;
+      return true;
+    }
+    virtual void compute() = 0;
+    MeasurementType_* _meas = nullptr;
+    srrg2_core::BaseSensorMessagePtr _raw_data;
     Status _status = Error;
   };
 

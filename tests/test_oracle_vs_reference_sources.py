@@ -2,11 +2,12 @@
 
 oracle/_ref/libls2d_ref.so is built by oracle/Makefile from three reference files compiled where they lie under
 /root/reference, unmodified -- correspondence_finder_projective_2d.cpp, merger_projective_2d.cpp,
-scene_clipper_projective_2d.cpp -- against stand-in headers (oracle/ref_shim/) for the absent upstream libraries.
+scene_clipper_projective_2d.cpp, raw_data_preprocessor_projective_2d.cpp -- against stand-in headers (oracle/ref_shim/) for the absent upstream libraries.
 The upstream pieces (polar projector, isometry algebra, point arithmetic) are the oracle's own restatement in both
 arms, so what these tests pin is exactly what lives in the reference repository: the finder's gates, their
 strictness, ordering and caching (.cpp:18-77), the merger's per-column decision tree and its ordered appends
-(.cpp:9-100), the clipper's collection and its move to the robot frame (.cpp:11-65).  The projector / factor / solver
+(.cpp:9-100), the clipper's collection, voxelize branch and move to the robot frame (.cpp:11-65), the pre-processor's
+range limits, sensor matrix, voxelize / valid-only branches and message handling (.cpp:13-51, 53-104).  The projector / factor / solver
 arithmetic stays unpinned."""
 import ctypes as C
 import os
@@ -15,7 +16,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
+from srrg2_laser_slam_2d_b200.synthetic import make_raw_scans, make_scan_pairs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libls2d_ref.so")
@@ -35,8 +36,10 @@ def ref(oracle):
     L.ref_find_correspondences.restype = i32
     L.ref_merge.argtypes = [vp, f32, vp, i32, vp, i32, vp]
     L.ref_merge.restype = i32
-    L.ref_clip.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.ref_clip.argtypes = [vp, vp, i32, vp, vp, f32, vp]
     L.ref_clip.restype = i32
+    L.ref_preprocess_scan.argtypes = [vp, vp, i32, vp]
+    L.ref_preprocess_scan.restype = i32
     L.ref_finder_throws_without_inputs.restype = i32
     return L
 
@@ -102,8 +105,10 @@ def test_merger_decision_tree_and_appends(oracle, ref, cols, thr):
     assert n_changed > 0
 
 
-@pytest.mark.parametrize("cols,sensor", [(721, (0.0, 0.0, 0.0)), (1081, (0.2, 0.2, 0.1)), (361, (-0.1, 0.05, -0.3))])
-def test_clipper_collects_and_moves_to_the_robot_frame(oracle, ref, cols, sensor):
+@pytest.mark.parametrize("cols,sensor,voxel", [(721, (0.0, 0.0, 0.0), 0.0), (1081, (0.2, 0.2, 0.1), 0.0),
+                                               (361, (-0.1, 0.05, -0.3), 0.0), (1081, (0.0, 0.0, 0.0), 0.1),
+                                               (721, (0.2, 0.2, 0.1), 0.05)])
+def test_clipper_collects_voxelizes_and_moves_to_the_robot_frame(oracle, ref, cols, sensor, voxel):
     prm = oracle.default_params(canvas_cols=cols)
     sp = make_scan_pairs(12, n_beams=1081, seed=77 + cols)
     for p in range(12):
@@ -111,8 +116,42 @@ def test_clipper_collects_and_moves_to_the_robot_frame(oracle, ref, cols, sensor
                                 sp.moving_pts[sp.moving_off[p]:sp.moving_off[p + 1]]])   # a denser "local map"
         robot = np.ascontiguousarray(sp.gt_xyt[p] * 3, np.float32)
         sens = np.float32(sensor)
-        want = oracle.clip_scene(prm, scene, robot, sens)
+        want = oracle.clip_scene(prm, scene, robot, sens, voxel)
         out = np.zeros((cols, 4), np.float32)
-        k = ref.ref_clip(C.byref(prm), _p(scene), len(scene), _p(robot), _p(sens), _p(out))
+        k = ref.ref_clip(C.byref(prm), _p(scene), len(scene), _p(robot), _p(sens), voxel, _p(out))
         assert k == len(want) and k > 0
         assert np.array_equal(_bits(out[:k]), _bits(want))
+
+
+def _ref_preprocess(ref, sp, ranges):
+    ranges = np.ascontiguousarray(ranges, np.float32)
+    out = np.zeros((len(ranges), 4), np.float32)
+    k = ref.ref_preprocess_scan(C.byref(sp), _p(ranges), len(ranges), _p(out))
+    return out[:k]
+
+
+def test_preprocessor_synthetic_fixture_of_the_reference_tests(oracle, ref):
+    """tests/fixtures.hpp:38-47 through the reference's own RawDataPreprocessorProjective2D::setRawData + compute:
+    100 points (tests/test_measurement_adaptor.cpp:36), the oracle's cloud bit for bit"""
+    from test_oracle_preprocess import synthetic_fixture
+    sp, ranges = synthetic_fixture()
+    got = _ref_preprocess(ref, sp, ranges)
+    assert len(got) == 100
+    assert np.array_equal(_bits(got), _bits(oracle.preprocess_scan(sp, ranges)))
+
+
+@pytest.mark.parametrize("voxel", [0.0, 0.02, 0.1])
+@pytest.mark.parametrize("limits", [dict(msg_range_min=0.1, msg_range_max=30.0, range_min=0.3, range_max=20.0),
+                                    dict(msg_range_min=0.5, msg_range_max=8.0, range_min=0.0, range_max=1000.0)])
+def test_preprocessor_range_limits_sensor_matrix_and_branches(oracle, ref, voxel, limits):
+    raw = make_raw_scans(6, n_beams=1081, seed=4242)
+    sp = oracle.default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=voxel,
+                                    **limits)
+    n_pts = 0
+    for ranges in np.concatenate([raw.fixed_ranges, raw.moving_ranges]):
+        want = oracle.preprocess_scan(sp, ranges)
+        got = _ref_preprocess(ref, sp, ranges)
+        assert len(got) == len(want)
+        assert np.array_equal(_bits(got), _bits(want))
+        n_pts += len(want)
+    assert n_pts > 12 * 100
