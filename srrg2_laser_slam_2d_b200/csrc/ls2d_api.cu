@@ -12,6 +12,7 @@
 
 #include "ls2d_kernels.cuh"
 #include "ls2d_icp2.cuh"
+#include "ls2d_icp3.cuh"
 #include "ls2d_multi.cuh"
 #include "ls2d_scan.cuh"
 
@@ -168,6 +169,7 @@ shape pick_shape(int max_points, int variant) {
       case 22: return {256, 5, 4, 3, 1152};
       case 23: return {192, 6, 5, 3, 1152};
       case 24: return {384, 3, 3, 3, 1152};
+      case 30: return {544, 2, 2, 4, 1088};  // icp_duo_kernel: two pairs per CTA + solver warp
       default: return {288, 4, 4, 3, 1152};  // measured best on B200 (profiles/r01_variant_sweep.md)
     }
   }
@@ -198,6 +200,18 @@ int launch_icp2_k(ls2d_handle* h, const align_args& a) {
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+template <int TC, bool SENSOR, int CS>
+int launch_duo_k(ls2d_handle* h, const align_args& a) {
+  constexpr size_t smem = duo_map<TC, CS>::BYTES;
+  auto kern             = icp_duo_kernel<TC, SENSOR, CS>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<(a.n_pairs + 1) / 2, TC + 32, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
   return LS2D_OK;
@@ -237,6 +251,8 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
     if (s.threads == 192 && s.ppt == 4) s = {256, 3, 3, 0, 0};
     if (s.threads == 256 && s.ppt == 3) s.minb = 3;
   }
+  if (s.kind == 4 && h->dp.cam.cols >= s.cs) s = {288, 4, 4, 0, 0};
+  if (s.kind == 4) return h->dp.with_sensor ? launch_duo_k<544, true, 1088>(h, a) : launch_duo_k<544, false, 1088>(h, a);
 #define LS2D_CASE2(T, P, B, CS)                                                        \
   if (s.kind == 3 && s.threads == T && s.ppt == P && s.minb == B && s.cs == CS)         \
     return h->dp.with_sensor ? launch_icp2_k<T, P, true, B, CS>(h, a) : launch_icp2_k<T, P, false, B, CS>(h, a);
@@ -1342,7 +1358,8 @@ int ls2d_reduction_shape(int32_t max_points, int32_t canvas_cols) {
     if (s.threads == 192 && s.ppt == 4) s.threads = 256;
     s.kind = 0;
   }
-  return s.threads | (s.kind == 3 ? 1 << 16 : 0);
+  if (s.kind == 4 && canvas_cols >= s.cs) s = {288, 4, 4, 0, 0};
+  return s.threads | (s.kind >= 3 ? 1 << 16 : 0);
 }
 
 int64_t ls2d_launch_count(const ls2d_handle* h) { return h ? h->launches : 0; }

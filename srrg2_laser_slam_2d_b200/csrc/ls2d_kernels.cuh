@@ -273,12 +273,12 @@ __device__ __forceinline__ void warp0_update(const dev_params& P, const align_ar
 
 // final record of a pair, written by thread 0 (called by the whole warp 0)
 __device__ __forceinline__ void write_result(const dev_params& P, const align_args& A, const pose_bc* bc, int pair,
-                                             int it, int status, float tot, unsigned tot_cnt) {
+                                             int it, int status, float tot, unsigned tot_cnt, int writer_tid = 0) {
   float v[NSUM];
 #pragma unroll
   for (int s = 0; s < NSUM; ++s) v[s] = __shfl_sync(0xffffffffu, tot, s);
   const unsigned c2 = __shfl_sync(0xffffffffu, tot_cnt, NSUM);
-  if (threadIdx.x == 0) {
+  if ((int) threadIdx.x == writer_tid) {
     int n_in = c2 & 0xffff, n_k = c2 >> 16;
     const int n_corr = n_in + n_k;
     if (status == LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES) {  // the oracle reports empty sums here
