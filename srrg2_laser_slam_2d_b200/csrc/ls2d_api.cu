@@ -170,6 +170,7 @@ shape pick_shape(int max_points, int variant) {
       case 23: return {192, 6, 5, 3, 1152};
       case 24: return {384, 3, 3, 3, 1152};
       case 30: return {544, 2, 2, 4, 1088};  // icp_duo_kernel: two pairs per CTA + solver warp
+      case 31: return {544, 2, 2, 5, 1088};  // icp_joint_kernel: two pairs per CTA, shared barriers
       default: return {288, 4, 4, 3, 1152};  // measured best on B200 (profiles/r01_variant_sweep.md)
     }
   }
@@ -217,6 +218,18 @@ int launch_duo_k(ls2d_handle* h, const align_args& a) {
   return LS2D_OK;
 }
 
+template <int TC, bool SENSOR, int CS>
+int launch_joint_k(ls2d_handle* h, const align_args& a) {
+  constexpr size_t smem = duo_map<TC, CS>::BYTES;
+  auto kern             = icp_joint_kernel<TC, SENSOR, CS>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  kern<<<(a.n_pairs + 1) / 2, TC, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
 template <int T, int PPT, int MINB>
 int launch_icp_t(ls2d_handle* h, const align_args& a) {
   return h->dp.with_sensor ? launch_icp_k<T, PPT, true, MINB>(h, a) : launch_icp_k<T, PPT, false, MINB>(h, a);
@@ -251,7 +264,8 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
     if (s.threads == 192 && s.ppt == 4) s = {256, 3, 3, 0, 0};
     if (s.threads == 256 && s.ppt == 3) s.minb = 3;
   }
-  if (s.kind == 4 && h->dp.cam.cols >= s.cs) s = {288, 4, 4, 0, 0};
+  if (s.kind >= 4 && h->dp.cam.cols >= s.cs) s = {288, 4, 4, 0, 0};
+  if (s.kind == 5) return h->dp.with_sensor ? launch_joint_k<544, true, 1088>(h, a) : launch_joint_k<544, false, 1088>(h, a);
   if (s.kind == 4) return h->dp.with_sensor ? launch_duo_k<544, true, 1088>(h, a) : launch_duo_k<544, false, 1088>(h, a);
 #define LS2D_CASE2(T, P, B, CS)                                                        \
   if (s.kind == 3 && s.threads == T && s.ppt == P && s.minb == B && s.cs == CS)         \
@@ -1358,7 +1372,7 @@ int ls2d_reduction_shape(int32_t max_points, int32_t canvas_cols) {
     if (s.threads == 192 && s.ppt == 4) s.threads = 256;
     s.kind = 0;
   }
-  if (s.kind == 4 && canvas_cols >= s.cs) s = {288, 4, 4, 0, 0};
+  if (s.kind >= 4 && canvas_cols >= s.cs) s = {288, 4, 4, 0, 0};
   return s.threads | (s.kind >= 3 ? 1 << 16 : 0);
 }
 

@@ -282,4 +282,211 @@ __global__ void __launch_bounds__(TC + 32, 2) icp_duo_kernel(const dev_params P,
   }
 }
 
+// icp_joint_kernel: two pairs per CTA WITHOUT a solver warp -- the four projection chains of a thread (two points of
+// pair A, two of pair B) run interleaved as in icp_fused2_kernel<288, 4>, both pairs share every barrier (3 per
+// iteration for two pairs), and the two Gauss-Newton steps run side by side on warps 0 and 1.  TC threads own points
+// t and t + TC of either pair (no all-invalid slot at 1081 points); same summation shape as icp_duo_kernel.
+template <int TC, bool SENSOR, int CS>
+__global__ void __launch_bounds__(TC, 2) icp_joint_kernel(const dev_params P, const align_args A) {
+  using M = duo_map<TC, CS>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned sb = sm::addr(smem_raw);
+  const int C       = P.cam.cols;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pair0  = 2 * blockIdx.x + A.pair_base;
+  const int n_here = (pair0 + 1 < A.pair_base + A.n_pairs) ? 2 : 1;
+  const int max_it = A.score_only ? 1 : P.max_iterations;
+
+  float2 mp[4];          // [2 X + J]
+  unsigned za[4], rb[4];
+  // ---- prologue per pair (as icp_duo_kernel, whole CTA)
+  static_for<0, 2>([&](auto xc) {
+    constexpr int X = decltype(xc)::value;
+    pose_bc* bc = reinterpret_cast<pose_bc*>(smem_raw + M::BC + X * 48);
+    if (X >= n_here) {  // absent pair: never alive, its points never valid
+      mp[2 * X] = mp[2 * X + 1] = make_float2(1e30f, 0.f);
+      if (tid == 0) {
+        publish_pose(bc, P, iso_identity(), SENSOR, 1 + LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES);
+        bc->tie = 0;
+      }
+      return;
+    }
+    const int pair = pair0 + X;
+    const unsigned zb = sb + M::Z + X * M::PAIR_Z;
+    const unsigned fk = 3u * zb - M::FI;
+    const int fcl  = A.fixed_const >= 0 ? A.fixed_const : (A.fixed_id ? A.fixed_id[pair] : pair);
+    const int mcl  = A.moving_id ? A.moving_id[pair / A.moving_div] : pair / A.moving_div;
+    const int f0 = A.fixed_off[fcl], nf = A.fixed_off[fcl + 1] - f0;
+    const int m0 = A.moving_off[mcl], nm = A.moving_off[mcl + 1] - m0;
+    for (int k = tid; k <= C; k += TC) {
+      const unsigned a = zb + 4u * k;
+      sm::st_f32<M::FD>(a, -1.f);
+      sm::st_u32<0>(a, Z_EMPTY_DEPTH);
+      sm::st_u32<M::ZI>(a, Z_EMPTY_IDX);
+    }
+    const unsigned mna = sb + X * M::PAIR_MN + 8u * tid;
+    static_for<0, 2>([&](auto jc) {
+      constexpr int J = decltype(jc)::value;
+      const int i     = tid + J * TC;
+      const float4 m  = i < nm ? ldg4(A.moving_pts + m0 + i) : make_float4(1e30f, 0.f, 0.f, 0.f);
+      mp[2 * X + J]   = make_float2(m.x, m.y);
+      sm::st_f32x2<J * TC * 8>(mna, m.z, m.w);
+    });
+    if (tid == 0) {
+      const iso Xi = iso_v2t(A.init_xyt[3 * pair], A.init_xyt[3 * pair + 1], A.init_xyt[3 * pair + 2]);
+      publish_pose(bc, P, Xi, SENSOR, 0);
+      bc->tie = 0;
+    }
+    __syncthreads();
+    float4 fp[2];
+    unsigned fza[2], frb[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int i = tid + j * TC;
+      int col     = C;
+      frb[j]      = 0;
+      if (i < nf) {
+        fp[j]           = ldg4(A.fixed_pts + f0 + i);
+        const float rho = fsqrt(fadd(fmul(fp[j].x, fp[j].x), fmul(fp[j].y, fp[j].y)));
+        if (!(rho < P.range_min || rho > P.range_max)) {
+          const int c = polar_column(P.cam, fp[j].y, fp[j].x);
+          if (c >= 0) col = c, frb[j] = f2u(rho);
+        }
+      }
+      fza[j] = zb + 4u * col;
+      if (col != C) sm::atom_min_u32<0>(fza[j], frb[j]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (sm::ld_u32<0>(fza[j]) == frb[j]) sm::atom_min_u32<M::ZI>(fza[j], (unsigned) (tid + j * TC));
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (sm::ld_u32<0>(fza[j]) == frb[j] && sm::ld_u32<M::ZI>(fza[j]) == (unsigned) (tid + j * TC)) {
+        sm::st_f32x4<0>(4u * fza[j] - fk, fp[j]);
+        sm::st_f32<M::FD>(fza[j], u2f(frb[j]));
+      }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      sm::st_u32<0>(fza[j], Z_EMPTY_DEPTH);
+      sm::st_u32<M::ZI>(fza[j], Z_EMPTY_IDX);
+    }
+  });
+  __syncthreads();
+
+  const unsigned wt = sb + M::WRED + (unsigned) warp * M::WTILE;
+  float tot        = 0.f;  // warp X, lane s: total of slot s of pair X
+  unsigned tot_cnt = 0;
+  int its[2]       = {0, 0};  // iterations run per pair (uniform)
+  bool alive[2]    = {true, n_here > 1};
+  for (int it = 0; it < max_it && (alive[0] || alive[1]); ++it) {
+    // phase 1: the four chains of the thread, interleaved
+    {
+      f2 pc[4];
+      int col[4];
+      bool near[4], up[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned bca = sb + M::BC + (q >> 1) * 48;
+        const float Lc = sm::ld_f32<BC_LC>(bca), Ls = sm::ld_f32<BC_LS>(bca);
+        const float Wtx = sm::ld_f32<BC_WTX>(bca), Wty = sm::ld_f32<BC_WTY>(bca);
+        const f2 ra = mul2s(mk2(Lc, Ls), mp[q].x), rb2 = mul2s(mk2(-Ls, Lc), mp[q].y);
+        pc[q]       = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
+        const f2 pq = mul2(pc[q], pc[q]);
+        const float rho = fsqrt(fadd(pq.x, pq.y));
+        rb[q]       = f2u(rho);
+        col[q]      = polar_column_fast2(P.cam, pc[q].y, pc[q].x, near[q], up[q]);
+        near[q]     = near[q] && alive[q >> 1] && !(rho < P.range_min || rho > P.range_max);
+      }
+      if (near[0] || near[1] || near[2] || near[3]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (near[q]) {
+            bool undecided;
+            const int c2 = polar_column_edge(P.cam, pc[q].y, pc[q].x, u2f(rb[q]), col[q] + (up[q] ? 1 : 0), undecided);
+            col[q]       = undecided ? polar_column_exact(P.cam, pc[q].y, pc[q].x) : c2;
+          }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned zb  = sb + M::Z + (q >> 1) * M::PAIR_Z;
+        const unsigned bca = sb + M::BC + (q >> 1) * 48;
+        const float rho = u2f(rb[q]);
+        const bool ok   = alive[q >> 1] && !(rho < P.range_min || rho > P.range_max) && (unsigned) col[q] < (unsigned) C;
+        za[q]           = zb + 4u * (ok ? col[q] : C);
+        rb[q]           = ok ? rb[q] : 0u;
+        if (ok && sm::atom_min_u32<0>(za[q], rb[q]) == rb[q]) sm::st_u32<BC_TIE>(bca, 1u);
+      }
+    }
+    __syncthreads();
+    const bool tie0 = sm::ld_u32<BC_TIE>(sb + M::BC) != 0, tie1 = sm::ld_u32<BC_TIE>(sb + M::BC + 48) != 0;
+    if (tie0 || tie1) {  // exact pass on the pair(s) that saw equal minimal depths
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (((q >> 1) ? tie1 : tie0) && sm::ld_u32<0>(za[q]) == rb[q])
+          sm::atom_min_u32<M::ZI>(za[q], (unsigned) (tid + (q & 1) * TC));
+      __syncthreads();
+    }
+    // phase 2 + per-warp reduction, pair by pair
+    static_for<0, 2>([&](auto xc) {
+      constexpr int X = decltype(xc)::value;
+      if (!alive[X]) return;
+      const unsigned zb  = sb + M::Z + X * M::PAIR_Z;
+      const unsigned fk  = 3u * zb - M::FI;
+      const unsigned bca = sb + M::BC + X * 48;
+      const unsigned mna = sb + X * M::PAIR_MN + 8u * tid;
+      const bool tie     = X ? tie1 : tie0;
+      const float Xtx = sm::ld_f32<BC_XTX>(bca), Xty = sm::ld_f32<BC_XTY>(bca);
+      const float Lc = sm::ld_f32<BC_LC>(bca), Ls = sm::ld_f32<BC_LS>(bca);
+      float Xc = 0.f, Xs = 0.f;
+      if (SENSOR) Xc = sm::ld_f32<BC_XC>(bca), Xs = sm::ld_f32<BC_XS>(bca);
+      float acc[NSUM];
+#pragma unroll
+      for (int s = 0; s < NSUM; ++s) acc[s] = 0.f;
+      unsigned cnt = 0;
+      static_for<0, 2>([&](auto jc) {
+        constexpr int J = decltype(jc)::value;
+        constexpr int Q = 2 * X + J;
+        bool win        = sm::ld_u32<0>(za[Q]) == rb[Q];
+        if (tie) win = win && sm::ld_u32<M::ZI>(za[Q]) == (unsigned) (tid + J * TC);
+        if (win) {
+          const float fd  = sm::ld_f32<M::FD>(za[Q]);
+          const float4 F  = sm::ld_f32x4<0>(4u * za[Q] - fk);
+          const float2 Mn = sm::ld_f32x2<J * TC * 8>(mna);
+          linearize2<SENSOR, J == 0>(P, fd, F, mp[Q].x, mp[Q].y, Mn, u2f(rb[Q]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+        }
+      });
+      store_partials2(acc, cnt, wt, sb + M::RED + X * M::PAIR_RED + (unsigned) warp * (RED_STRIDE * 4), lane);
+      __syncwarp();  // the warp's tile is reused by the next pair
+    });
+    __syncthreads();
+    // hand-back, then the two Gauss-Newton steps side by side: warp X updates pair X
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      sm::st_u32<0>(za[q], Z_EMPTY_DEPTH);
+      if ((q >> 1) ? tie1 : tie0) sm::st_u32<M::ZI>(za[q], Z_EMPTY_IDX);
+    }
+    if (warp < 2 && alive[warp]) {
+      pose_bc* bc      = reinterpret_cast<pose_bc*>(smem_raw + M::BC + warp * 48);
+      const float* red = reinterpret_cast<const float*>(smem_raw + M::RED + warp * M::PAIR_RED);
+      if (lane == 0) bc->tie = 0;
+      warp0_update<TC, SENSOR, true>(P, A, bc, red, pair0 + warp, it, lane, tot, tot_cnt);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+      if (alive[x]) {
+        its[x] = it + 1;
+        if (sm::ld_u32<BC_STOP>(sb + M::BC + x * 48)) alive[x] = false, its[x] = it;
+      }
+  }
+  if (warp < n_here) {
+    const pose_bc* bc = reinterpret_cast<const pose_bc*>(smem_raw + M::BC + warp * 48);
+    const int stop    = bc->stop;
+    write_result(P, A, bc, pair0 + warp, its[warp], stop ? stop - 1 : -1, tot, tot_cnt, warp * 32);
+  }
+}
+
 }  // namespace ls2d

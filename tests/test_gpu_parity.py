@@ -376,11 +376,11 @@ def test_zbuffer_ties_first_index_wins(handle_factory, oracle):
         assert (mi < 500).all()                                     # of each duplicated pair the first copy wins
 
 
-@pytest.mark.parametrize("variant", ["10", "11", "12", "13", "20", "24", "30"])
+@pytest.mark.parametrize("variant", ["10", "11", "12", "13", "20", "24", "30", "31"])
 def test_streaming_kernel_variants_are_bit_exact(oracle, variant, monkeypatch):
     """The shared-memory / L2-streaming kernel (the path of clouds > 4096 points) forced onto 1081-point clouds, the
     generic-pointer kernel (20), the 384 x 3 shape of icp_fused2_kernel (24) and the two-pairs-per-CTA kernel with its
-    solver warp (30; 47 pairs: the last CTA owns a single pair): same algorithm, each with its own fixed reduction
+    solver warp (30; 47 pairs: the last CTA owns a single pair) or with shared barriers (31): same algorithm, each with its own fixed reduction
     shape, so the same bit-exact parity bar."""
     from srrg2_laser_slam_2d_b200 import Handle
     monkeypatch.setenv("LS2D_ICP_VARIANT", variant)
