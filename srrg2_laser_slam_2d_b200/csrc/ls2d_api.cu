@@ -46,6 +46,7 @@ struct ls2d_handle {
   cloud_set sets[LS2D_MAX_CLOUD_SETS];
   scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior, d_ranges, d_clip;
   scratch d_edge;  // rounding-edge directions of the projector (polar_cam::edge), rebuilt by ls2d_set_params
+  polar_cam edge_key = {};  // camera the table in d_edge was built for
   scratch d_edge_slice[LS2D_MAX_SLICES];  // the same for the slices of ls2d_align_multi, cached by camera
   polar_cam edge_slice_key[LS2D_MAX_SLICES] = {};
   int64_t launches = 0;
@@ -307,6 +308,12 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
 
 // device copy of the projector's rounding edges (second tier of the column decision, ls2d_math.cuh)
 int upload_edges(ls2d_handle* h) {
+  const polar_cam& key = h->edge_key;  // the table depends on the camera constants only: re-use it across set_params
+  if (h->d_edge.p && key.cols == h->dp.cam.cols && key.K00 == h->dp.cam.K00 && key.K01 == h->dp.cam.K01) {
+    h->dp.cam.edge = static_cast<const polar_edge*>(h->d_edge.p);
+    return LS2D_OK;
+  }
+  h->edge_key.cols = 0;
   std::vector<polar_edge> edges((size_t) h->dp.cam.cols + 1);
   fill_polar_edges(h->dp.cam, edges.data());
   const size_t bytes = edges.size() * sizeof(polar_edge);
@@ -316,6 +323,7 @@ int upload_edges(ls2d_handle* h) {
   CU(cudaMemcpyAsync(h->d_edge.p, edges.data(), bytes, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));  // `edges` is pageable and dies here
   h->dp.cam.edge = static_cast<const polar_edge*>(h->d_edge.p);
+  h->edge_key    = h->dp.cam;
   return LS2D_OK;
 }
 
