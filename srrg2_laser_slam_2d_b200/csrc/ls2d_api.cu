@@ -662,7 +662,8 @@ int ls2d_align_pairs_host(ls2d_handle* h, const float* fpts, const int32_t* foff
   CU(cudaMemcpyAsync(F.off, foff, sizeof(int) * ((size_t) n_pairs + 1), cudaMemcpyHostToDevice, h->copy_stream));
   CU(cudaMemcpyAsync(M.off, moff, sizeof(int) * ((size_t) n_pairs + 1), cudaMemcpyHostToDevice, h->copy_stream));
   CU(cudaMemcpyAsync(h->d_init.p, init, sizeof(float) * 3 * (size_t) n_pairs, cudaMemcpyHostToDevice, h->copy_stream));
-  int n_chunks = n_pairs / 888;  // >= two waves of 3 CTAs x 148 SMs per chunk
+  int n_chunks = n_pairs / 512;  // a chunk's upload (~0.3 ms) is far longer than its kernel: the more chunks, the
+                                 // shorter the tail left after the last upload (~one wave of 4 CTAs x 148 SMs)
   n_chunks     = n_chunks < 1 ? 1 : (n_chunks > 8 ? 8 : n_chunks);
   for (int k = 0; k < n_chunks; ++k) {
     const int p0 = (int) ((long long) n_pairs * k / n_chunks), p1 = (int) ((long long) n_pairs * (k + 1) / n_chunks);

@@ -397,7 +397,7 @@ def test_streaming_kernel_variants_are_bit_exact(oracle, variant, monkeypatch):
 
 def test_chunked_host_pipeline_matches_the_resident_path(handle_factory):
     """ls2d_align_pairs_host cuts a batch into chunks whose uploads overlap the previous chunk's kernel: results must
-    not depend on the chunking (ragged clouds, 2000 pairs -> two chunks)."""
+    not depend on the chunking (ragged clouds, 2000 pairs -> three chunks of the host pipeline)."""
     base = make_scan_pairs(50, n_beams=600, seed=77)
     rng = np.random.default_rng(2)
     n = 2000
@@ -418,7 +418,7 @@ def test_chunked_host_pipeline_matches_the_resident_path(handle_factory):
     ref = h.align_batch(init)
     h2 = handle_factory(default_params(**kw))
     one = h2.align_pairs_host(fpts, foff, mpts, moff, init)
-    assert h2.launch_count == 2
+    assert h2.launch_count == min(8, 2000 // 512)   # ls2d_align_pairs_host: one launch per chunk
     assert one.tobytes() == ref.tobytes()
     two = h2.align_pairs_host(fpts[:foff[10]], foff[:11], mpts[:moff[10]], moff[:11], init[:10])   # shrink: one chunk
     assert two.tobytes() == ref[:10].tobytes()
