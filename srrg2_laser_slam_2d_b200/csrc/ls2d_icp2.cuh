@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
   static_for<0, PPT>([&](auto jc) {
     constexpr int J = decltype(jc)::value;
     const int i     = tid + J * T;
-    const float4 m  = i < nm ? ldg4(A.moving_pts + m0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // lanes past the end of the cloud hold a point no pose brings inside the range gates (rho overflows to inf)
+    const float4 m  = i < nm ? ldg4(A.moving_pts + m0 + i) : make_float4(1e30f, 0.f, 0.f, 0.f);
     mp[J]           = make_float2(m.x, m.y);
     sm::st_f32x2<J * T * 8>(mna, m.z, m.w);
   });
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         const float rho = u2f(rb[j]);
-        const bool ok   = tid + j * T < nm && !(rho < P.range_min || rho > P.range_max) && col[j] >= 0 && col[j] < C;
+        const bool ok   = !(rho < P.range_min || rho > P.range_max) && (unsigned) col[j] < (unsigned) C;
         za[j]           = zb + 4u * (ok ? col[j] : C);
         rb[j]           = ok ? rb[j] : 0u;  // never equals the dummy cell's EMPTY
         if (ok && sm::atom_min_u32<0>(za[j], rb[j]) == rb[j]) sm::st_u32<BC_TIE>(bca, 1u);  // an equal rho was there
