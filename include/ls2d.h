@@ -328,7 +328,8 @@ int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ra
 int ls2d_reduction_threads(int32_t max_points);
 /* the full shape of that reduction for clouds of up to max_points points on a canvas of canvas_cols columns:
  * bits 0..15 = threads per pair, bit 16 = how a warp combines its 32 lane partials (0: xor-butterfly, 1: lanes
- * 0..15 and 16..31 in ascending order, then the two halves).  This is the value ORC_SUM_TREE takes as tree_threads. */
+ * 0..15 and 16..31 in ascending order, then the two halves), bit 17 = the contributions are accumulated with fused
+ * multiply-adds (oracle decision D18).  This is the value ORC_SUM_TREE takes as tree_threads. */
 int ls2d_reduction_shape(int32_t max_points, int32_t canvas_cols);
 /* the same for the multi-slice aligner (ls2d_align_multi), whatever the cloud sizes */
 int ls2d_multi_reduction_threads(void);

@@ -300,6 +300,57 @@ static inline int contribution(const orc_params* prm, const factor_ctx* f, orc_p
   return inlier;
 }
 
+/* D18 -- the same contribution with the kernel's FUSED arithmetic (ORC_SUM_TREE with bit 17 of tree_threads set;
+ * icp_fused2_kernel): every gate and everything that decides a pixel index stays single binary32 operations, but the
+ * error / Jacobian entries and the accumulation into the thread's partial sums p[] use fused multiply-adds, in
+ * exactly this association.  (The reference's own builds are not uniquely defined here either: GCC's default
+ * -ffp-contract=fast contracts Eigen's expressions wherever the target has FMA.)  Returns 1 if inlier. */
+static inline int contribution_fused(const orc_params* prm, const factor_ctx* f, orc_point pf, orc_point pm, float* p) {
+  const float c = f->RX.c, s = f->RX.s;
+  float px, py, nx, ny;
+  if (f->with_sensor) { /* D9: unfused, as factor_eval */
+    float qx, qy;
+    apply(f->X, pm.x, pm.y, &qx, &qy);
+    apply(f->Sinv, qx, qy, &px, &py);
+  } else {
+    px = fmaf(c, pm.x, fmaf(-s, pm.y, f->X.tx));
+    py = fmaf(s, pm.x, fmaf(c, pm.y, f->X.ty));
+  }
+  rot(f->RX, pm.nx, pm.ny, &nx, &ny); /* the finder's gate used this very value */
+  const float dx = px - pf.x, dy = py - pf.y;
+  const float e0 = fmaf(dx, pf.nx, dy * pf.ny);
+  const float e1 = nx - pf.nx, e2 = ny - pf.ny;
+  const float Ja = fmaf(pf.nx, c, pf.ny * s);
+  const float Jb = fmaf(pf.ny, c, pf.nx * (-s));
+  const float Jc = fmaf(Ja, -pm.y, Jb * pm.x);
+  const float d0 = -ny, d1 = nx;
+  const float chi = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
+  float w = 1.f, chi_in = chi, chi_k = 0.f;
+  int inlier      = 1;
+  const float tau = prm->cauchy_chi_threshold;
+  if (tau > 0.f && !(chi < tau)) { /* D6 */
+    const float inv_tau = 1.f / tau;
+    const float aux     = chi * inv_tau + 1.f;
+    chi_k               = tau * logf(aux);
+    w                   = 1.f / aux;
+    chi_in              = 0.f;
+    inlier              = 0;
+  }
+  const float wa = Ja * w, wb = Jb * w, wc = Jc * w, wd0 = d0 * w, wd1 = d1 * w;
+  p[0]  = fmaf(wa, Ja, p[0]);
+  p[1]  = fmaf(wa, Jb, p[1]);
+  p[2]  = fmaf(wa, Jc, p[2]);
+  p[3]  = fmaf(wb, Jb, p[3]);
+  p[4]  = fmaf(wb, Jc, p[4]);
+  p[5]  = fmaf(wd1, d1, fmaf(wd0, d0, fmaf(wc, Jc, p[5])));
+  p[6]  = fmaf(wa, e0, p[6]);
+  p[7]  = fmaf(wb, e0, p[7]);
+  p[8]  = fmaf(wd1, e2, fmaf(wd0, e1, fmaf(wc, e0, p[8])));
+  p[9]  = p[9] + chi_in;
+  p[10] = p[10] + chi_k;
+  return inlier;
+}
+
 typedef struct {
   float v[NSLOT];
   int32_t n_inliers, n_kernelized;
@@ -326,9 +377,11 @@ static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
   /* ORC_SUM_TREE: the CUDA kernels' fixed reduction shapes (D10).  tree_threads = threads per pair (bits 0..15);
    * bit 16 selects how a warp's 32 lane partials are combined:
    *   0  xor-butterfly (offsets 16, 8, 4, 2, 1)                      -- icp_fused_kernel / stream / multi
-   *   1  lanes 0..15 and 16..31 summed in ascending order, then added -- icp_fused2_kernel (transposed tile) */
+   *   1  lanes 0..15 and 16..31 summed in ascending order, then added -- icp_fused2_kernel (transposed tile)
+   * bit 17: the contributions and their accumulation into the thread's partial use the fused arithmetic of D18 */
   const int32_t T        = tree_threads & 0xFFFF;
   const int32_t half_seq = (tree_threads >> 16) & 1;
+  const int32_t fused    = (tree_threads >> 17) & 1;
   float* part     = (float*) calloc((size_t) T * NSLOT, sizeof(float));
   int32_t* fx_of  = (int32_t*) malloc(sizeof(int32_t) * (size_t)(n_moving > 0 ? n_moving : 1));
   for (int32_t i = 0; i < n_moving; ++i) {
@@ -341,11 +394,16 @@ static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
     if (fx_of[i] < 0) {
       continue;
     }
-    float v[NSLOT];
-    const int inl = contribution(prm, &f, fixed[fx_of[i]], moving[i], v);
-    float* p      = part + (size_t)(i % T) * NSLOT;
-    for (int s = 0; s < NSLOT; ++s) {
-      p[s] = p[s] + v[s];
+    float* p = part + (size_t)(i % T) * NSLOT;
+    int inl;
+    if (fused) {
+      inl = contribution_fused(prm, &f, fixed[fx_of[i]], moving[i], p);
+    } else {
+      float v[NSLOT];
+      inl = contribution(prm, &f, fixed[fx_of[i]], moving[i], v);
+      for (int s = 0; s < NSLOT; ++s) {
+        p[s] = p[s] + v[s];
+      }
     }
     out->n_inliers += inl;
     out->n_kernelized += !inl;

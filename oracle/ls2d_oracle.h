@@ -108,6 +108,9 @@ typedef struct {
  * fixed-shape tree of the CUDA kernel: thread t owns moving points t, t+T, ...; per-thread
  * sequential, xor-butterfly inside each 32-lane warp, then sequential over warps. */
 enum { ORC_SUM_SEQUENTIAL = 0, ORC_SUM_TREE = 1 };
+/* ORC_SUM_TREE reads tree_threads as: bits 0..15 threads per pair; bit 16 how a warp combines its lanes (0 xor-
+ * butterfly, 1 two ascending 16-lane halves); bit 17 fused accumulation arithmetic (decision D18: gates and pixel
+ * indices single-rounding, error / Jacobian entries and the sums with fmaf in the kernel's association) */
 
 void orc_default_params(orc_params* p);
 

@@ -139,6 +139,9 @@ struct shape {
              // 1081-column one); wider canvases fall back to kind 0
 };
 
+// LS2D_ICP_UNFUSED=1: icp_fused2_kernel<288, 4> with linearize2() instead of linearize2f() (measurement knob)
+bool unfused_requested() { return getenv("LS2D_ICP_UNFUSED") != nullptr; }
+
 shape pick_shape(int max_points, int variant) {
   if (max_points <= 256) return {128, 2, 6, 0};
   if (max_points <= 512) return {128, 4, 6, 0};
@@ -195,10 +198,10 @@ int launch_icp_k(ls2d_handle* h, const align_args& a) {
   return LS2D_OK;
 }
 
-template <int T, int PPT, bool SENSOR, int MINB, int CS>
+template <int T, int PPT, bool SENSOR, int MINB, int CS, bool FUSED = true>
 int launch_icp2_k(ls2d_handle* h, const align_args& a) {
   constexpr size_t smem = icp2_map<T, PPT, CS>::BYTES;
-  auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, CS>;
+  auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, CS, FUSED>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
@@ -268,9 +271,12 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   if (s.kind >= 4 && h->dp.cam.cols >= s.cs) s = {288, 4, 4, 0, 0};
   if (s.kind == 5) return h->dp.with_sensor ? launch_joint_k<544, true, 1088>(h, a) : launch_joint_k<544, false, 1088>(h, a);
   if (s.kind == 4) return h->dp.with_sensor ? launch_duo_k<544, true, 1088>(h, a) : launch_duo_k<544, false, 1088>(h, a);
+  if (s.kind == 3 && unfused_requested() && s.threads == 288 && s.ppt == 4 && s.minb == 4 && !h->dp.with_sensor)
+    return launch_icp2_k<288, 4, false, 4, 1152, false>(h, a);  // A/B: single-rounding accumulation arithmetic
 #define LS2D_CASE2(T, P, B, CS)                                                        \
   if (s.kind == 3 && s.threads == T && s.ppt == P && s.minb == B && s.cs == CS)         \
-    return h->dp.with_sensor ? launch_icp2_k<T, P, true, B, CS>(h, a) : launch_icp2_k<T, P, false, B, CS>(h, a);
+    return h->dp.with_sensor ? launch_icp2_k<T, P, true, B, CS, (CS == 1152)>(h, a)     \
+                             : launch_icp2_k<T, P, false, B, CS, (CS == 1152)>(h, a);
   LS2D_CASE2(384, 3, 3, 1152)
   LS2D_CASE2(288, 4, 4, 1152)
   LS2D_CASE2(256, 5, 4, 1152)
@@ -1382,7 +1388,9 @@ int ls2d_reduction_shape(int32_t max_points, int32_t canvas_cols) {
     s.kind = 0;
   }
   if (s.kind >= 4 && canvas_cols >= s.cs) s = {288, 4, 4, 0, 0};
-  return s.threads | (s.kind >= 3 ? 1 << 16 : 0);
+  // linearize2f (oracle decision D18): the 1152-stride shapes; the 768-stride ones measured faster unfused
+  const bool fused = s.kind == 3 && s.cs == 1152 && !(unfused_requested() && s.threads == 288);
+  return s.threads | (s.kind >= 3 ? 1 << 16 : 0) | (fused ? 1 << 17 : 0);
 }
 
 int64_t ls2d_launch_count(const ls2d_handle* h) { return h ? h->launches : 0; }

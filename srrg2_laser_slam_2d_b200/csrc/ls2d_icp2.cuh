@@ -190,6 +190,76 @@ __device__ __forceinline__ void linearize2(const dev_params& P, float fd, const 
   }
 }
 
+// The same winner with FUSED accumulation arithmetic (decision D18 of oracle/ls2d_oracle.c, ORC_SUM_TREE bit 17): the
+// gates -- everything that decides a correspondence -- are the single-rounding operations of linearize2(); the error /
+// Jacobian entries and the sums use fused multiply-adds in exactly the oracle's association.  ~15 instructions fewer
+// per winner.
+template <bool SENSOR, bool FIRST>
+__device__ __forceinline__ void linearize2f(const dev_params& P, float fd, const float4 F, float Mx, float My,
+                                            float2 Mn, float rho, float Xtx, float Xty, float Xc, float Xs, float Lc,
+                                            float Ls, float (&acc)[NSUM], unsigned& cnt) {
+  if (fd < 0.f || fabsf(fsub(fd, rho)) > P.point_distance) return;
+  const f2 rc1 = mk2(Lc, Ls), rc2 = mk2(-Ls, Lc);  // columns of R(local_map_in_sensor)
+  const f2 na = mul2s(rc1, Mn.x), nb = mul2s(rc2, Mn.y);
+  const float nx = fadd(na.x, nb.x);  // transformed normal (unfused: the gate below reads it)
+  const float ny = fadd(na.y, nb.y);
+  const f2 nd = mul2(mk2(nx, ny), mk2(F.z, F.w));
+  if (fadd(nd.x, nd.y) < P.normal_cos) return;
+  f2 p;
+  if (SENSOR) {
+    const f2 qa = mul2s(mk2(Xc, Xs), Mx), qb = mul2s(mk2(-Xs, Xc), My);
+    const float qx = fadd(fadd(qa.x, qb.x), Xtx);
+    const float qy = fadd(fadd(qa.y, qb.y), Xty);
+    iso_apply(P.Sinv, qx, qy, p.x, p.y);
+  } else {  // px = fma(Lc, Mx, fma(-Ls, My, Xtx)), py = fma(Ls, Mx, fma(Lc, My, Xty))
+    p = fma2(rc1, mk2(Mx, Mx), fma2(rc2, mk2(My, My), mk2(Xtx, Xty)));
+  }
+  const f2 d     = add2(p, mk2(-F.x, -F.y));
+  const float e0 = ffma(d.x, F.z, fmul(d.y, F.w));
+  const f2 e12   = add2(mk2(nx, ny), mk2(-F.z, -F.w));  // e1, e2
+  // Ja = fma(F.z, Lc, F.w * Ls), Jb = fma(F.w, Lc, F.z * -Ls)
+  const f2 Jab   = fma2(mk2(F.z, F.w), mk2(Lc, Lc), mul2(mk2(F.w, F.z), mk2(Ls, -Ls)));
+  const float Ja = Jab.x, Jb = Jab.y;
+  const float Jc = ffma(Ja, -My, fmul(Jb, Mx));
+  const float d0 = -ny, d1 = nx;
+  const float chi = ffma(e12.y, e12.y, ffma(e12.x, e12.x, fmul(e0, e0)));
+  float w = 1.f, chi_in = chi, chi_k = 0.f;
+  if (P.tau > 0.f && !(chi < P.tau)) {  // RobustifierCauchy (L0.json:76-81)
+    const float aux = fadd(fmul(chi, P.inv_tau), 1.f);
+    chi_k           = fmul(P.tau, __logf(aux));  // statistics only (tolerance parity)
+    w               = frcp(aux);
+    chi_in          = 0.f;
+    cnt += 1u << 16;
+  } else {
+    cnt += 1u;
+  }
+  const f2 wab   = mul2s(Jab, w);  // wa, wb
+  const float wc = fmul(Jc, w);
+  const f2 wd    = mul2s(mk2(d0, d1), w);  // wd0, wd1
+  if (FIRST) {
+    const f2 a01 = mul2s(Jab, wab.x);                      // wa Ja, wa Jb
+    const f2 a23 = mul2(wab, mk2(Jc, Jb));                 // wa Jc, wb Jb
+    const f2 a67 = mul2s(wab, e0);                         // wa e0, wb e0
+    f2 a58       = mul2s(mk2(Jc, e0), wc);                 // wc Jc, wc e0
+    a58          = fma2(mk2(wd.x, wd.x), mk2(d0, e12.x), a58);
+    a58          = fma2(mk2(wd.y, wd.y), mk2(d1, e12.y), a58);
+    acc[0] = a01.x, acc[1] = a01.y, acc[2] = a23.x, acc[3] = a23.y, acc[4] = fmul(wab.y, Jc), acc[5] = a58.x;
+    acc[6] = a67.x, acc[7] = a67.y, acc[8] = a58.y, acc[9] = chi_in, acc[10] = chi_k;
+  } else {
+    const f2 a01 = fma2(mk2(wab.x, wab.x), Jab, mk2(acc[0], acc[1]));
+    const f2 a23 = fma2(wab, mk2(Jc, Jb), mk2(acc[2], acc[3]));
+    const f2 a67 = fma2(wab, mk2(e0, e0), mk2(acc[6], acc[7]));
+    f2 a58       = fma2(mk2(wc, wc), mk2(Jc, e0), mk2(acc[5], acc[8]));
+    a58          = fma2(mk2(wd.x, wd.x), mk2(d0, e12.x), a58);
+    a58          = fma2(mk2(wd.y, wd.y), mk2(d1, e12.y), a58);
+    acc[0] = a01.x, acc[1] = a01.y, acc[2] = a23.x, acc[3] = a23.y, acc[5] = a58.x, acc[8] = a58.y;
+    acc[6] = a67.x, acc[7] = a67.y;
+    acc[4]  = ffma(wab.y, Jc, acc[4]);
+    acc[9]  = fadd(acc[9], chi_in);
+    acc[10] = fadd(acc[10], chi_k);
+  }
+}
+
 // per-warp reduction through the warp's transposed tile; the total of slot s ends on lane 2s and goes to the warp's
 // row of `red` (same row format as store_partials()).  wt = shared address of the warp's tile, rrow = of its row.
 __device__ __forceinline__ void store_partials2(const float (&acc)[NSUM], unsigned cnt, unsigned wt, unsigned rrow,
@@ -226,7 +296,7 @@ __device__ __forceinline__ void store_partials2(const float (&acc)[NSUM], unsign
   if (lane == 0) sm::st_u32<NSUM * 4>(rrow, wcnt);
 }
 
-template <int T, int PPT, bool SENSOR, int MINB, int CS>
+template <int T, int PPT, bool SENSOR, int MINB, int CS, bool FUSED = true>
 __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P, const align_args A) {
   using M = icp2_map<T, PPT, CS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -387,7 +457,10 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
         const float fd  = sm::ld_f32<M::FD>(za[J]);
         const float4 F  = sm::ld_f32x4<0>(4u * za[J] - fk);
         const float2 Mn = sm::ld_f32x2<J * T * 8>(mna);
-        linearize2<SENSOR, J == 0>(P, fd, F, mp[J].x, mp[J].y, Mn, u2f(rb[J]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+        if (FUSED)
+          linearize2f<SENSOR, J == 0>(P, fd, F, mp[J].x, mp[J].y, Mn, u2f(rb[J]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+        else
+          linearize2<SENSOR, J == 0>(P, fd, F, mp[J].x, mp[J].y, Mn, u2f(rb[J]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
       }
     });
     store_partials2(acc, cnt, wt, rrow, lane);
