@@ -152,7 +152,8 @@ def run_reference(args):
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "batched scan-to-local-map registration: %d pairs x 1081 beams, 10 GN iterations, "
-                               "tracking parameter set" % sample_pairs, "pairs_per_step": sample_pairs},
+                               "tracking parameter set (config 3)" % sample_pairs, "pairs_per_step": sample_pairs,
+                   "canvas_cols": 1081},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": "%d pairs per step, OpenMP over pairs on %d threads" % (sample_pairs, cores)},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -265,9 +266,9 @@ def run_ours(args):
             "metric": "aligned scan-pairs/sec (%d beams, 10 GN iters)" % N_BEAMS, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "batched scan-to-local-map registration: %d pairs x 1081 beams, 10 GN iterations, "
-                                   "tracking parameter set (config 3)" % n_pairs,
-                       "pairs_per_gpu_per_step": n_pairs, "canvas_cols": 1081, "l2": "inputs_larger_than_l2 (142 MB)",
+            "config": {"workload": "batched scan-to-local-map registration: %d pairs x %d beams, 10 GN iterations, "
+                                   "tracking parameter set (config 3)" % (n_pairs, N_BEAMS),
+                       "pairs_per_gpu_per_step": n_pairs, "canvas_cols": N_BEAMS, "l2": "inputs_larger_than_l2 (142 MB)",
                        "success_rate": ok_rate},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(hout.nbytes), "ms_per_step": e2e_ms / args.steps},
