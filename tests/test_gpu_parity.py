@@ -117,7 +117,10 @@ def test_demo_scene_projection(handle_factory):
 # ------------------------------------------------------------------ seeded batches vs the oracle
 @pytest.mark.parametrize("n_beams,cols,n_pairs", [(1081, 1081, 192), (721, 721, 96), (361, 361, 64), (181, 90, 32),
                                                   (1500, 1081, 24), (2000, 721, 16), (4000, 1081, 8),
-                                                  (6000, 1081, 6), (8192, 721, 6)])
+                                                  (6000, 1081, 6), (8192, 721, 6),
+                                                  # canvases wider than the compile-time column stride of
+                                                  # icp_fused2_kernel: the run-time-stride kernel takes over
+                                                  (600, 1081, 32), (1000, 1200, 32)])
 def test_seeded_batch_tree_bit_exact_and_sequential_tolerance(handle_factory, oracle, n_beams, cols, n_pairs):
     sp = make_scan_pairs(n_pairs, n_beams=n_beams, seed=1000 + n_beams)
     kw = dict(canvas_cols=cols, normal_cos=0.9)
