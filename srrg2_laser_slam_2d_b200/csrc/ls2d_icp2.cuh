@@ -1,5 +1,5 @@
 // ls2d_icp2.cuh -- icp_fused2_kernel: the instruction-diet version of icp_fused_kernel (same algorithm, same
-// arithmetic, same results; see ls2d_kernels.cuh for the algorithm and the reference citations).
+// decisions; see ls2d_kernels.cuh for the algorithm and the reference citations).
 //
 // What changed, all of it aimed at the issue slots the ncu source view showed being spent on bookkeeping
 // (profiles/r01_icp_ncu_summary.md: phase 2 + reduction = 65 % of the executed warp instructions):
@@ -17,9 +17,16 @@
 //     4 x 128-bit loads and 15 adds on 22 lanes, one shuffle) instead of the 16-shuffle recursive-halving tree with
 //     its ~30 selects.  This is a different -- equally fixed -- summation shape: lanes 0..15 and 16..31 of a warp are
 //     summed in ascending order, the two halves added, the warps added in ascending order; the oracle offers it as
-//     ORC_SUM_TREE with bit 16 of tree_threads set (ls2d_reduction_threads() reports it).
+//     ORC_SUM_TREE with bit 16 of tree_threads set (ls2d_reduction_shape() reports it).
 //   * the first of a thread's points assigns its contribution instead of adding it to zero (the totals are
 //     canonicalised with +0.0f in warp 0, so even an all-minus-zero sum matches the oracle's 0 + x).
+//   * the column of a moving point is decided in three tiers (ls2d_math.cuh): fast proposal, side of the rounding
+//     edge's ray in binary64, exact atan2f -- the single-lane exact path in front of the CTA barrier is 3 x rarer.
+//   * FUSED (default at the 1152-column stride): the error / Jacobian entries of an accepted correspondence and their
+//     accumulation use fused multiply-adds (linearize2f, oracle decision D18, ORC_SUM_TREE bit 17); every gate and
+//     everything that decides a pixel index stays single-rounding arithmetic.
+//   * lanes past the end of the cloud hold a far point (1e30, 0): its rho overflows to inf, no range gate accepts it,
+//     and the iteration loop never compares point indices.
 #pragma once
 
 #include <type_traits>
