@@ -120,7 +120,10 @@ def test_demo_scene_projection(handle_factory):
                                                   (6000, 1081, 6), (8192, 721, 6),
                                                   # canvases wider than the compile-time column stride of
                                                   # icp_fused2_kernel: the run-time-stride kernel takes over
-                                                  (600, 1081, 32), (1000, 1200, 32)])
+                                                  (600, 1081, 32), (1000, 1200, 32), (1081, 7680, 4),
+                                                  # the widest canvases the compile-time strides hold (the dummy
+                                                  # column is the stride's last cell)
+                                                  (1081, 1151, 16), (721, 767, 16), (1081, 1152, 8)])
 def test_seeded_batch_tree_bit_exact_and_sequential_tolerance(handle_factory, oracle, n_beams, cols, n_pairs):
     sp = make_scan_pairs(n_pairs, n_beams=n_beams, seed=1000 + n_beams)
     kw = dict(canvas_cols=cols, normal_cos=0.9)
