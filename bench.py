@@ -124,6 +124,31 @@ def make_workload(n_pairs: int, seed: int, device: str, loop: bool = False):
     return make_scan_pairs(n_pairs, n_beams=N_BEAMS, seed=seed, device=device)
 
 
+def bind_to_gpu_numa_node(torch, local_rank: int) -> str:
+    """N > 1: run this rank on the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function), so that the
+    pinned host buffers it allocates are first-touched on that NUMA node and eight uploads do not share one
+    socket's memory controllers.  Returns what it did; never fails the bench."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        addr = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % addr) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "unchanged (no local cpus in the affinity mask)"
+        os.sched_setaffinity(0, cpus)
+        return "cpus %s of %s" % (spec, addr)
+    except (OSError, AttributeError, ValueError) as e:
+        return "unchanged (%s)" % type(e).__name__
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's own CPU implementation of the path.  It cannot be compiled here (needs Eigen3 and three
@@ -172,6 +197,7 @@ def run_ours(args):
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else "unchanged (one rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -269,7 +295,7 @@ def run_ours(args):
             "config": {"workload": "batched scan-to-local-map registration: %d pairs x %d beams, 10 GN iterations, "
                                    "tracking parameter set (config 3)" % (n_pairs, N_BEAMS),
                        "pairs_per_gpu_per_step": n_pairs, "canvas_cols": N_BEAMS, "l2": "inputs_larger_than_l2 (142 MB)",
-                       "success_rate": ok_rate},
+                       "success_rate": ok_rate, "host_binding_rank0": numa},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(hout.nbytes), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),  # timed region of `value`; the scoring pass adds its own
