@@ -258,6 +258,26 @@ def test_tree_and_sequential_sums_agree_within_tolerance(oracle):
     assert np.allclose(seq["chi_inliers"], tree["chi_inliers"], rtol=1e-3)
 
 
+@pytest.mark.parametrize("shape", [288 | 1 << 16, 288 | 1 << 16 | 1 << 17, 544 | 1 << 16, 256 | 1 << 17])
+def test_kernel_shaped_sum_modes_agree_with_the_reference_order(oracle, shape):
+    """every ORC_SUM_TREE variant the kernels use (warp-combine flag bit 16, fused accumulation arithmetic of decision
+    D18 bit 17) against the reference's sequential order: same integer outcomes at the first linearisation, poses and
+    chi2 inside BASELINE.json's tolerances; the fused mode really is a different arithmetic (some bits differ)"""
+    sp = make_scan_pairs(16, n_beams=1081, seed=21)
+    prm = oracle.default_params(canvas_cols=1081, normal_cos=0.9)
+    seq, sit = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt)
+    tree, tit = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
+                                   sum_mode=oracle.SUM_TREE, tree_threads=shape)
+    assert np.array_equal(sit["n_corr"][:, 0], tit["n_corr"][:, 0])
+    assert np.abs(seq["x"] - tree["x"]).max() < 1e-5 and np.abs(seq["y"] - tree["y"]).max() < 1e-5
+    assert np.abs(seq["theta"] - tree["theta"]).max() < 2e-6
+    assert np.allclose(seq["chi_inliers"], tree["chi_inliers"], rtol=1e-3)
+    if shape >> 17 & 1:
+        unfused, _ = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
+                                        sum_mode=oracle.SUM_TREE, tree_threads=shape & ~(1 << 17))
+        assert not np.array_equal(unfused["chi_inliers"].view(np.uint32), tree["chi_inliers"].view(np.uint32))
+
+
 def test_synthetic_pairs_converge_near_ground_truth(oracle):
     sp = make_scan_pairs(6, seed=9)
     prm = oracle.default_params(canvas_cols=1081, normal_cos=0.9)
