@@ -267,14 +267,15 @@ def test_score_batch_is_the_first_linearisation(handle_factory, oracle):
 
 
 # ------------------------------------------------------------------ loop-closure verification
-def test_verify_gates_and_best_of_match_the_oracle(handle_factory, oracle):
+@pytest.mark.parametrize("n_beams", [721, 1081])
+def test_verify_gates_and_best_of_match_the_oracle(handle_factory, oracle, n_beams):
     n_cand, n_guess = 24, 4
-    sp = make_scan_pairs(n_cand, n_beams=721, seed=21, motion_xy=0.3, motion_theta=0.15)
+    sp = make_scan_pairs(n_cand, n_beams=n_beams, seed=21, motion_xy=0.3, motion_theta=0.15)
     # one query (fixed cloud 0) against candidates; candidate 0's moving cloud is the true match, others are
     # scans of other rooms; guesses are perturbations of candidate 0's ground truth
     rng = np.random.default_rng(4)
     guesses = (sp.gt_xyt[0][None, None, :] + rng.uniform(-0.1, 0.1, (n_cand, n_guess, 3))).astype(np.float32)
-    kw = dict(canvas_cols=721, point_distance=1.414, normal_cos=0.8, cauchy_chi_threshold=0.05, max_iterations=30)
+    kw = dict(canvas_cols=n_beams, point_distance=1.414, normal_cos=0.8, cauchy_chi_threshold=0.05, max_iterations=30)
     h = handle_factory(default_params(**kw))
     upload(h, sp)
     gates = Gates(300, 0.1, 0.8)
@@ -284,7 +285,7 @@ def test_verify_gates_and_best_of_match_the_oracle(handle_factory, oracle):
     mid = np.repeat(cand, n_guess)
     o, _ = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
                               guesses.reshape(-1, 3), fid, mid, sum_mode=oracle.SUM_TREE,
-                              tree_threads=reduction_threads(721, kw["canvas_cols"]), n_threads=oracle.max_threads())
+                              tree_threads=reduction_threads(n_beams, kw["canvas_cols"]), n_threads=oracle.max_threads())
     assert_bit_exact(allr, o)
     ob = oracle.best_of(o, 300, 0.1, 0.8)
     assert ob >= 0 and cand[ob // n_guess] == 0                  # the true match wins
