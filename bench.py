@@ -218,7 +218,7 @@ def run_ours(args):
     fp, fo = torch.from_numpy(sp.fixed_pts).to(dev), torch.from_numpy(sp.fixed_off).to(dev)
     mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
     init = torch.from_numpy(sp.init_xyt).to(dev)
-    out = torch.zeros(n_pairs * 16, dtype=torch.int32, device=dev)
+    out = torch.zeros(n_pairs * (RESULT_DTYPE.itemsize // 4), dtype=torch.int32, device=dev)
     h.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), n_pairs, N_BEAMS)
     h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), n_pairs, N_BEAMS)
 
@@ -245,7 +245,7 @@ def run_ours(args):
     ok_rate = float((res["status"] == 0).mean())
 
     # ---- the single-linearisation scoring pass (ls2d_score_batch): the regime closest to the HBM roofline
-    out_s = torch.zeros(n_pairs * 16, dtype=torch.int32, device=dev)
+    out_s = torch.zeros(n_pairs * (RESULT_DTYPE.itemsize // 4), dtype=torch.int32, device=dev)
     for _ in range(args.warmup):
         h.score_batch_dev(None, None, init.data_ptr(), n_pairs, out_s.data_ptr())
     barrier()
@@ -260,7 +260,7 @@ def run_ours(args):
     # ---- end to end: host buffers (pinned) -> C ABI -> host results
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     hfp, hfo, hmp, hmo, hin = pin(sp.fixed_pts), pin(sp.fixed_off), pin(sp.moving_pts), pin(sp.moving_off), pin(sp.init_xyt)
-    hout = torch.zeros(n_pairs * 64, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
+    hout = torch.zeros(n_pairs * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
     he = Handle(local_rank, default_params(**TRACK))
     for _ in range(args.warmup):
         he.align_pairs_host(hfp, hfo, hmp, hmo, hin, hout)
@@ -407,8 +407,9 @@ def run_verify(args):
     h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), uniq, 1081)
     cand = torch.from_numpy(cand_ids[lo:hi].copy()).to(dev)
     gs = torch.from_numpy(guesses[lo:hi].copy()).to(dev)
-    best = torch.zeros(8, dtype=torch.int32, device=dev)
-    gathered = torch.zeros(8 * world, dtype=torch.int32, device=dev)
+    BW = BEST_DTYPE.itemsize // 4
+    best = torch.zeros(BW, dtype=torch.int32, device=dev)
+    gathered = torch.zeros(BW * world, dtype=torch.int32, device=dev)
     gates = Gates(300, 0.1, 0.8)
 
     def step():
@@ -445,7 +446,7 @@ def run_verify(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "loop-closure verification: 1 query x %d candidates x %d guesses, 30 GN iterations, "
                                    "loop-closure parameter set (config 4 shape)" % (n_cand, n_guess),
-                       "unique_candidate_clouds": uniq, "collective": "all_gather of %d x 32 B" % world},
+                       "unique_candidate_clouds": uniq, "collective": "all_gather of %d x 48 B" % world},
             "winner": {"candidate": int(winner["candidate"]), "guess": int(winner["guess"]),
                        "n_inliers": int(winner["n_inliers"])},
             "gpu_launches": int(h.launch_count),
@@ -459,7 +460,7 @@ def run_allpairs(args):
     """Large-map all-pairs loop-closure search (BASELINE.json configs[4], "config 5" of SURVEY.md 8d): n_maps local
     maps of map_points points each, all resident on every GPU; candidate pairs from a seeded radius query over the map
     positions, grouped by query map; ranks own contiguous runs of groups with equal pair counts; the only exchange
-    is one all-gather of the per-map ls2d_best records (n_maps x 32 B per rank)."""
+    is one all-gather of the per-map ls2d_best records (n_maps x 48 B per rank)."""
     import torch
     import torch.distributed as dist
     from scipy.spatial import cKDTree
@@ -505,25 +506,26 @@ def run_allpairs(args):
     mid = torch.from_numpy(mid_all[p_lo:p_hi].copy()).to(dev)
     gs = torch.from_numpy(guesses[p_lo:p_hi].copy()).to(dev)
     goff = torch.from_numpy((group_off[g_lo:g_hi + 1] - p_lo).astype(np.int32)).to(dev)
-    best = torch.zeros(n_maps * 8, dtype=torch.int32, device=dev)
-    best.view(n_maps, 8)[:, 6:] = -1                      # candidate / guess = -1 outside this rank's groups
-    gathered = torch.zeros(world * n_maps * 8, dtype=torch.int32, device=dev)
+    BW = BEST_DTYPE.itemsize // 4
+    best = torch.zeros(n_maps * BW, dtype=torch.int32, device=dev)
+    best.view(n_maps, BW)[:, 6:8] = -1                    # candidate / guess = -1 outside this rank's groups
+    gathered = torch.zeros(world * n_maps * BW, dtype=torch.int32, device=dev)
     owner = torch.zeros(n_maps, dtype=torch.int64, device=dev)
     for r in range(world):
         lo, hi = shard_groups(group_off, r, world)
         owner[lo:hi] = r
-    final = torch.zeros(n_maps, 8, dtype=torch.int32, device=dev)
+    final = torch.zeros(n_maps, BW, dtype=torch.int32, device=dev)
     gates = Gates(300, 0.1, 0.8)
     rows = torch.arange(n_maps, device=dev)
 
     def step():
         h.verify_pairs_dev(fid.data_ptr(), mid.data_ptr(), gs.data_ptr(), n_local, goff.data_ptr(), g_hi - g_lo, gates,
-                           best.data_ptr() + 32 * g_lo)
+                           best.data_ptr() + BEST_DTYPE.itemsize * g_lo)
         if world > 1:
             dist.all_gather_into_tensor(gathered, best)
         else:
             gathered.copy_(best)
-        final.copy_(gathered.view(world, n_maps, 8)[owner, rows])   # every group has exactly one owner
+        final.copy_(gathered.view(world, n_maps, BW)[owner, rows])   # every group has exactly one owner
 
     for _ in range(args.warmup):
         step()
@@ -560,7 +562,7 @@ def run_allpairs(args):
                                    "pairs (radius %.1f), 30 GN iterations, loop-closure parameter set (config 5 shape)"
                                    % (n_maps, n_pts, n_pairs, args.radius),
                        "unique_map_clouds": uniq, "resident_bytes_per_gpu": int(2 * pts.numel() * 4),
-                       "canvas_cols": args.canvas, "collective": "all_gather of %d x %d x 32 B" % (world, n_maps)},
+                       "canvas_cols": args.canvas, "collective": "all_gather of %d x %d x 48 B" % (world, n_maps)},
             "accepted_maps": int((rec["candidate"] >= 0).sum()),
             "checksum": int(np.bitwise_xor.reduce(rec.view(np.uint32).ravel())),
             "roofline": {"bound": "hbm", "achieved": a_bytes / s_per_step / 1e9 / world, "peak": peak, "unit": "GB/s",
@@ -604,7 +606,7 @@ def run_multi(args):
     h.upload_clouds(1, msp.moving_pts, msp.moving_off)
     init = torch.from_numpy(msp.init_xyt).to(dev)
     z = torch.from_numpy(msp.odom_xyt).to(dev)
-    out = torch.zeros(n * 16, dtype=torch.int32, device=dev)
+    out = torch.zeros(n * (RESULT_DTYPE.itemsize // 4), dtype=torch.int32, device=dev)
 
     def step():
         h.align_multi_dev(sl, [0, 2], [1, 1], init.data_ptr(), n, out.data_ptr(), prior=prior, prior_z_ptr=z.data_ptr())
@@ -646,7 +648,7 @@ def run_multi(args):
 # ----------------------------------------------------------------------------------------------- tracker step
 def run_track(args):
     """The tracker's frame step with raw scans as the wire format: per frame 1081 ranges
-    (4.3 KB) + a local-map id + the predicted pose go to the device, 64 B come back; the local maps are resident."""
+    (4.3 KB) + a local-map id + the predicted pose go to the device, 80 B come back; the local maps are resident."""
     import torch
 
     from srrg2_laser_slam_2d_b200 import Handle, default_params
@@ -667,7 +669,7 @@ def run_track(args):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     ranges, ids = pin(raw.fixed_ranges), pin(np.arange(n, dtype=np.int32))
     robots, init = pin(np.zeros((n, 3), np.float32)), pin(np.zeros((n, 3), np.float32))
-    out = torch.zeros(n * 64, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
+    out = torch.zeros(n * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
     for _ in range(args.warmup):
         h.track_batch(sp, ranges, 2, ids, robots, init, out)
     torch.cuda.synchronize()

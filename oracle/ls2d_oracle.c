@@ -43,6 +43,31 @@
  *      correspondence.
  *  D16 H and b are the binary32 sums of the slices' totals in slice order, the prior last.
  *  D17 max_iterations, min_num_inliers and damping are aligner-level (read from slice 0's record).
+ *  D18 fused accumulation arithmetic of the 1152-stride kernel (see contribution_fused below).
+ *  Options north_star names but the shipped configurations never switch on (all UNPINNED restatements):
+ *  D19 factor POINT2POINT = SE2Point2PointErrorFactor[WithSensor] on VariableSE2Right: e = X p_m - p_f
+ *      (S^-1 (X p_m) - p_f), J = [R | R (-y, x)^T] with R the rotation of X (of S^-1 X), Omega = I2,
+ *      chi = e0^2 + e1^2; the finder and its normal gate are unchanged.
+ *  L1  algorithm LM = IterationAlgorithmLM (the Levenberg-Marquardt of g2o / srrg2_solver, Nielsen's update):
+ *      per round, H, b and chi0 = chi_inliers + chi_kernelized are built at X with the round's correspondences.
+ *  L2  lambda is initialised in the first round (user_lambda_init if > 0, else tau * max diag H) and carried
+ *      across the rounds of one compute(); nu = 2 at every round's start.
+ *  L3  trial: solve (H + lambda D) dx = -b, D = diag H (variable_damping) or I, binary64 LDL^T as D11; a system
+ *      that is not positive definite counts as a rejected trial.
+ *  L4  chi1 = robustified chi of the SAME correspondences at X * v2t(dx) (computeActiveErrors: no new association;
+ *      a factor's inlier / kernelized decision is re-taken at the trial pose), binary32, summed in the selected
+ *      order.
+ *  L5  scale = sum_j dx_j (lambda D_j dx_j - b_j) + 1e-3, rho = (chi0 - chi1) / scale, binary64.
+ *  L6  rho > 0 and chi1 finite: accept (X <- X * v2t(dx)), lambda *= max(step_low, min(1 - (2 rho - 1)^3,
+ *      step_high)), round done.  Else lambda *= nu, nu *= 2, next trial (at most lm_iterations_max per round).
+ *  L7  no accepted trial: X stays; the round still counts as an iteration.  `damping` is not used by LM.
+ *  L8  lambda, nu, rho, scale live in binary64.
+ *  I1  enable_inlier_only_runs: after the main rounds, if they did not fail and n_inliers >= min_num_inliers, up
+ *      to max_iterations more rounds run in which kernelized factors get weight 0 (they still count in the
+ *      statistics); their iteration records follow the main ones.
+ *  T1  termination_epsilon > 0: after a round (not the first of its phase) with
+ *      chi_prev - chi < epsilon * chi_prev, chi = chi_inliers + chi_kernelized of the round's linearisation, the
+ *      phase stops.
  */
 #include "ls2d_oracle.h"
 
@@ -69,6 +94,36 @@ void orc_default_params(orc_params* p) {
   p->min_num_correspondences = 0;        /* L0.json:134 */
   p->min_num_inliers         = 10;       /* L0.json:501 */
   p->with_sensor             = 0;
+  p->factor                  = ORC_FACTOR_PLANE2PLANE;
+  p->algorithm               = ORC_ALGORITHM_GN;
+  p->lm_user_lambda_init     = 0.f;
+  p->lm_tau                  = 1e-5f;
+  p->lm_step_low             = 1.f / 3.f;
+  p->lm_step_high            = 2.f / 3.f;
+  p->lm_iterations_max       = 10;
+  p->lm_variable_damping     = 1;
+}
+
+/* sensor_in_robot of a WithSensor slice in either form (with_sensor 1: x, y, theta; 2: the isometry itself) */
+static orc_iso orc_v2t_fwd(float x, float y, float theta);
+static orc_iso sensor_iso(const orc_params* prm) {
+  if (prm->with_sensor == 2) {
+    orc_iso S;
+    S.tx = prm->sensor_in_robot[0], S.ty = prm->sensor_in_robot[1];
+    S.c = prm->sensor_in_robot_cs[0], S.s = prm->sensor_in_robot_cs[1];
+    return S;
+  }
+  return orc_v2t_fwd(prm->sensor_in_robot[0], prm->sensor_in_robot[1], prm->sensor_in_robot[2]);
+}
+
+static orc_iso pose_at(const float* poses, size_t k, int32_t stride) {
+  const float* p = poses + k * (size_t) stride;
+  if (stride == 4) {
+    orc_iso T;
+    T.tx = p[0], T.ty = p[1], T.c = p[2], T.s = p[3];
+    return T;
+  }
+  return orc_v2t_fwd(p[0], p[1], p[2]);
 }
 
 /* ---------------------------------------------------------------- A.0 geometry helpers */
@@ -82,6 +137,7 @@ orc_iso orc_v2t(float x, float y, float theta) {
   T.s  = sinf(theta);
   return T;
 }
+static orc_iso orc_v2t_fwd(float x, float y, float theta) { return orc_v2t(x, y, theta); }
 
 /* geometry2d::t2v [used at apps/visual_test_aligner_2d.cpp:145]: theta = atan2(R10, R00) */
 void orc_t2v(orc_iso T, float* xyt) {
@@ -238,8 +294,7 @@ static factor_ctx make_factor(const orc_params* prm, orc_iso X) {
   f.RX          = X;
   f.Sinv        = orc_v2t(0.f, 0.f, 0.f);
   if (prm->with_sensor) {
-    f.Sinv = orc_inverse(
-      orc_v2t(prm->sensor_in_robot[0], prm->sensor_in_robot[1], prm->sensor_in_robot[2]));
+    f.Sinv = orc_inverse(sensor_iso(prm));
     f.RX = orc_compose(f.Sinv, X); /* only its rotation is used */
   }
   return f;
@@ -351,23 +406,111 @@ static inline int contribution_fused(const orc_params* prm, const factor_ctx* f,
   return inlier;
 }
 
+/* D19 -- SE2Point2PointErrorFactor[WithSensor]: e = p_pred - p_fixed, J = [R | R (-y, x)^T], Omega = I2.
+ * returns 1 if inlier, 0 if kernelized */
+static inline int contribution_p2p(const orc_params* prm, const factor_ctx* f, orc_point pf, orc_point pm, float* v) {
+  float px, py, jc0, jc1;
+  apply(f->X, pm.x, pm.y, &px, &py);
+  if (f->with_sensor) { /* D9 */
+    float qx, qy;
+    apply(f->Sinv, px, py, &qx, &qy);
+    px = qx;
+    py = qy;
+  }
+  const float e0 = px - pf.x, e1 = py - pf.y;
+  const float c = f->RX.c, s = f->RX.s;
+  rot(f->RX, -pm.y, pm.x, &jc0, &jc1);
+  const float chi = e0 * e0 + e1 * e1;
+  float w         = 1.f;
+  int inlier      = 1;
+  float chi_in = chi, chi_k = 0.f;
+  const float tau = prm->cauchy_chi_threshold;
+  if (tau > 0.f && !(chi < tau)) { /* D6 */
+    const float inv_tau = 1.f / tau;
+    const float aux     = chi * inv_tau + 1.f;
+    chi_k               = tau * logf(aux);
+    w                   = 1.f / aux;
+    chi_in              = 0.f;
+    inlier              = 0;
+  }
+  const float wc = c * w, ws = s * w, wms = (-s) * w, wj0 = jc0 * w, wj1 = jc1 * w;
+  v[0]  = wc * c + ws * s;
+  v[1]  = wc * (-s) + ws * c;
+  v[2]  = wc * jc0 + ws * jc1;
+  v[3]  = wms * (-s) + wc * c;
+  v[4]  = wms * jc0 + wc * jc1;
+  v[5]  = wj0 * jc0 + wj1 * jc1;
+  v[6]  = wc * e0 + ws * e1;
+  v[7]  = wms * e0 + wc * e1;
+  v[8]  = wj0 * e0 + wj1 * e1;
+  v[9]  = chi_in;
+  v[10] = chi_k;
+  return inlier;
+}
+
+/* robustified squared error of one correspondence at the factor's pose (L4): the error half of contribution() */
+static inline float correspondence_chi(const orc_params* prm, const factor_ctx* f, orc_point pf, orc_point pm) {
+  float px, py;
+  apply(f->X, pm.x, pm.y, &px, &py);
+  if (f->with_sensor) {
+    float qx, qy;
+    apply(f->Sinv, px, py, &qx, &qy);
+    px = qx;
+    py = qy;
+  }
+  const float dx = px - pf.x, dy = py - pf.y;
+  float chi;
+  if (prm->factor == ORC_FACTOR_POINT2POINT) {
+    chi = dx * dx + dy * dy;
+  } else {
+    float nx, ny;
+    rot(f->RX, pm.nx, pm.ny, &nx, &ny);
+    const float e0 = dx * pf.nx + dy * pf.ny, e1 = nx - pf.nx, e2 = ny - pf.ny;
+    chi = (e0 * e0 + e1 * e1) + e2 * e2;
+  }
+  const float tau = prm->cauchy_chi_threshold;
+  if (tau > 0.f && !(chi < tau)) {
+    chi = tau * logf(chi * (1.f / tau) + 1.f);
+  }
+  return chi;
+}
+
 typedef struct {
   float v[NSLOT];
   int32_t n_inliers, n_kernelized;
 } lin_sums;
 
+/* one correspondence through the slice's factor (D19); inlier_only (I1): a kernelized factor keeps its statistics
+ * but adds nothing to H and b */
+static inline int contribution_any(const orc_params* prm, const factor_ctx* f, orc_point pf, orc_point pm,
+                                   int inlier_only, float* v, int* n_slots) {
+  const int inl = prm->factor == ORC_FACTOR_POINT2POINT ? contribution_p2p(prm, f, pf, pm, v)
+                                                        : contribution(prm, f, pf, pm, v);
+  *n_slots = NSLOT;
+  if (inlier_only && !inl) {
+    v[0] = v[9], v[1] = v[10]; /* caller adds them to slots 9, 10 only */
+    *n_slots = 0;
+  }
+  return inl;
+}
+
 static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
                       const orc_point* moving, int32_t n_moving, const int32_t* fixed_idx,
                       const int32_t* moving_idx, int32_t n_corr, int32_t sum_mode,
-                      int32_t tree_threads, lin_sums* out) {
+                      int32_t tree_threads, int inlier_only, lin_sums* out) {
   const factor_ctx f = make_factor(prm, X);
   memset(out, 0, sizeof(*out));
   if (sum_mode == ORC_SUM_SEQUENTIAL) {
     for (int32_t k = 0; k < n_corr; ++k) {
       float v[NSLOT];
-      const int inl = contribution(prm, &f, fixed[fixed_idx[k]], moving[moving_idx[k]], v);
-      for (int s = 0; s < NSLOT; ++s) {
-        out->v[s] = out->v[s] + v[s];
+      int ns;
+      const int inl = contribution_any(prm, &f, fixed[fixed_idx[k]], moving[moving_idx[k]], inlier_only, v, &ns);
+      if (ns) {
+        for (int s = 0; s < NSLOT; ++s) {
+          out->v[s] = out->v[s] + v[s];
+        }
+      } else {
+        out->v[9] = out->v[9] + v[0], out->v[10] = out->v[10] + v[1];
       }
       out->n_inliers += inl;
       out->n_kernelized += !inl;
@@ -396,13 +539,18 @@ static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
     }
     float* p = part + (size_t)(i % T) * NSLOT;
     int inl;
-    if (fused) {
+    if (fused) { /* D18: the plane-to-plane factor of the 1152-stride kernel only */
       inl = contribution_fused(prm, &f, fixed[fx_of[i]], moving[i], p);
     } else {
       float v[NSLOT];
-      inl = contribution(prm, &f, fixed[fx_of[i]], moving[i], v);
-      for (int s = 0; s < NSLOT; ++s) {
-        p[s] = p[s] + v[s];
+      int ns;
+      inl = contribution_any(prm, &f, fixed[fx_of[i]], moving[i], inlier_only, v, &ns);
+      if (ns) {
+        for (int s = 0; s < NSLOT; ++s) {
+          p[s] = p[s] + v[s];
+        }
+      } else {
+        p[9] = p[9] + v[0], p[10] = p[10] + v[1];
       }
     }
     out->n_inliers += inl;
@@ -446,11 +594,58 @@ static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
 
 /* ---------------------------------------------------------------- A.6 GN step */
 
-/* IterationAlgorithmGN + 3x3 LDL^T (D11). returns 0 on success, -1 if not positive definite */
-static int solve3(const float* v, float damping, float* dx) {
-  const double H00 = (double) v[0] + (double) damping, H01 = v[1], H02 = v[2];
-  const double H11 = (double) v[3] + (double) damping, H12 = v[4];
-  const double H22 = (double) v[5] + (double) damping;
+/* L4: chi1 of the trial pose over the round's correspondences, summed sequentially in correspondence order or in
+ * the general kernel's shape (thread t owns moving points t, t + T, ...; xor-butterfly inside a warp; warps in
+ * order) */
+static float total_chi(const orc_params* prm, orc_iso X, const orc_point* fixed, const orc_point* moving,
+                       int32_t n_moving, const int32_t* fixed_idx, const int32_t* moving_idx, int32_t n_corr,
+                       int32_t sum_mode, int32_t tree_threads) {
+  const factor_ctx f = make_factor(prm, X);
+  if (sum_mode == ORC_SUM_SEQUENTIAL) {
+    float t = 0.f;
+    for (int32_t k = 0; k < n_corr; ++k) {
+      t = t + correspondence_chi(prm, &f, fixed[fixed_idx[k]], moving[moving_idx[k]]);
+    }
+    return t;
+  }
+  const int32_t T = tree_threads & 0xFFFF;
+  float* part     = (float*) calloc((size_t) T, sizeof(float));
+  int32_t* fx_of  = (int32_t*) malloc(sizeof(int32_t) * (size_t)(n_moving > 0 ? n_moving : 1));
+  for (int32_t i = 0; i < n_moving; ++i) {
+    fx_of[i] = -1;
+  }
+  for (int32_t k = 0; k < n_corr; ++k) {
+    fx_of[moving_idx[k]] = fixed_idx[k];
+  }
+  for (int32_t i = 0; i < n_moving; ++i) {
+    if (fx_of[i] >= 0) {
+      part[i % T] = part[i % T] + correspondence_chi(prm, &f, fixed[fx_of[i]], moving[i]);
+    }
+  }
+  float total = 0.f;
+  for (int32_t w = 0; w < T / 32; ++w) {
+    float* lane = part + (size_t) w * 32;
+    for (int off = 16; off >= 1; off >>= 1) {
+      for (int l = 0; l < 32; ++l) {
+        if (!(l & off)) {
+          const float a = lane[l], b = lane[l ^ off];
+          lane[l] = a + b, lane[l ^ off] = b + a;
+        }
+      }
+    }
+    total = (w == 0) ? lane[0] : total + lane[0];
+  }
+  free(part);
+  free(fx_of);
+  return total;
+}
+
+/* IterationAlgorithmGN + 3x3 LDL^T (D11), D[j] added to the diagonal (GN: the damping; LM: lambda * D_j).
+ * returns 0 on success, -1 if not positive definite */
+static int solve3d(const float* v, const double* D, float* dx) {
+  const double H00 = (double) v[0] + D[0], H01 = v[1], H02 = v[2];
+  const double H11 = (double) v[3] + D[1], H12 = v[4];
+  const double H22 = (double) v[5] + D[2];
   const double r0 = -(double) v[6], r1 = -(double) v[7], r2 = -(double) v[8];
   if (!(H00 > 0.0)) { /* d0 */
     return -1;
@@ -484,12 +679,83 @@ static int solve3(const float* v, float damping, float* dx) {
   return 0;
 }
 
+static int solve3(const float* v, float damping, float* dx) {
+  const double D[3] = {(double) damping, (double) damping, (double) damping};
+  return solve3d(v, D, dx);
+}
+
+/* Levenberg-Marquardt state of one compute() (L2, L8) */
+typedef struct {
+  double lambda;
+  int started;
+  int32_t rejected;
+} lm_state;
+
+/* one LM round (L3..L7) on the quadratic form `sums` built at X; returns the new estimate */
+static orc_iso lm_round(const orc_params* prm, lm_state* lm, const lin_sums* sums, orc_iso X, const orc_point* fixed,
+                        const orc_point* moving, int32_t n_moving, const int32_t* fidx, const int32_t* midx,
+                        int32_t n_corr, int32_t sum_mode, int32_t tree_threads) {
+  const float* v       = sums->v;
+  const double diag[3] = {(double) v[0], (double) v[3], (double) v[5]};
+  if (!lm->started) { /* L2 */
+    double mx = diag[0] > diag[1] ? diag[0] : diag[1];
+    mx        = mx > diag[2] ? mx : diag[2];
+    lm->lambda  = prm->lm_user_lambda_init > 0.f ? (double) prm->lm_user_lambda_init : (double) prm->lm_tau * mx;
+    lm->started = 1;
+  }
+  const float chi0 = v[9] + v[10];
+  double nu        = 2.0;
+  for (int32_t t = 0; t < prm->lm_iterations_max; ++t) {
+    double D[3];
+    for (int j = 0; j < 3; ++j) {
+      D[j] = prm->lm_variable_damping ? lm->lambda * diag[j] : lm->lambda;
+    }
+    float dx[3];
+    if (solve3d(v, D, dx) == 0) {
+      const orc_iso Xt = orc_compose(X, orc_v2t(dx[0], dx[1], dx[2]));
+      const float chi1 = total_chi(prm, Xt, fixed, moving, n_moving, fidx, midx, n_corr, sum_mode, tree_threads);
+      double scale     = 0.0;
+      for (int j = 0; j < 3; ++j) { /* L5 */
+        scale = scale + (double) dx[j] * (D[j] * (double) dx[j] - (double) v[6 + j]);
+      }
+      scale            = scale + 1e-3;
+      const double rho = ((double) chi0 - (double) chi1) / scale;
+      if (rho > 0.0 && isfinite(chi1)) { /* L6 */
+        const double q = 2.0 * rho - 1.0;
+        double alpha   = 1.0 - (q * q) * q;
+        alpha          = alpha < (double) prm->lm_step_high ? alpha : (double) prm->lm_step_high;
+        const double g = alpha > (double) prm->lm_step_low ? alpha : (double) prm->lm_step_low;
+        lm->lambda     = lm->lambda * g;
+        return Xt;
+      }
+    }
+    lm->lambda = lm->lambda * nu;
+    nu         = nu * 2.0;
+    lm->rejected++;
+  }
+  return X; /* L7 */
+}
+
 /* ---------------------------------------------------------------- A.7 outer loop */
 
-void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
-               const orc_point* moving, int32_t n_moving, const float* init_xyt,
-               int32_t sum_mode, int32_t tree_threads, orc_result* out,
-               orc_iter_stats* iter_stats) {
+static void fill_iter(orc_iter_stats* st, orc_iso X, const lin_sums* sums, int32_t n_corr) {
+  float xyt[3];
+  orc_t2v(X, xyt);
+  st->x              = xyt[0];
+  st->y              = xyt[1];
+  st->theta          = xyt[2];
+  st->c              = X.c;
+  st->s              = X.s;
+  st->chi_inliers    = sums->v[9];
+  st->chi_kernelized = sums->v[10];
+  st->n_inliers      = sums->n_inliers;
+  st->n_kernelized   = sums->n_kernelized;
+  st->n_corr         = n_corr;
+}
+
+void orc_align_iso(const orc_params* prm, const orc_point* fixed, int32_t n_fixed, const orc_point* moving,
+                   int32_t n_moving, orc_iso init, int32_t sum_mode, int32_t tree_threads, orc_result* out,
+                   orc_iter_stats* iter_stats) {
   const int32_t C      = prm->canvas_cols;
   orc_cell* fixed_img  = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
   orc_cell* moving_img = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) C);
@@ -499,49 +765,57 @@ void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
   /* correspondence_finder_projective_2d.cpp:37-44: fixed projected once, identity camera */
   orc_project(prm, orc_v2t(0.f, 0.f, 0.f), fixed, n_fixed, fixed_img);
 
-  orc_iso X = orc_v2t(init_xyt[0], init_xyt[1], init_xyt[2]); /* setMovingInFixed */
+  orc_iso X    = init; /* setMovingInFixed */
   orc_iso Sinv = orc_v2t(0.f, 0.f, 0.f);
   if (prm->with_sensor) {
-    Sinv = orc_inverse(
-      orc_v2t(prm->sensor_in_robot[0], prm->sensor_in_robot[1], prm->sensor_in_robot[2]));
+    Sinv = orc_inverse(sensor_iso(prm));
   }
+  const int32_t n_phases = prm->enable_inlier_only_runs ? 2 : 1;
   memset(out, 0, sizeof(*out));
   if (iter_stats) {
-    memset(iter_stats, 0, sizeof(orc_iter_stats) * (size_t) prm->max_iterations);
+    memset(iter_stats, 0, sizeof(orc_iter_stats) * (size_t) prm->max_iterations * (size_t) n_phases);
   }
   lin_sums sums;
   memset(&sums, 0, sizeof(sums));
+  lm_state lm;
+  memset(&lm, 0, sizeof(lm));
   int32_t n_corr = 0;
   int32_t status = -1;
-  int32_t it     = 0;
-  for (; it < prm->max_iterations; ++it) {
-    /* slice->findCorrespondences(): local_map_in_sensor = sensor_in_robot^-1 * moving_in_fixed */
-    const orc_iso L = prm->with_sensor ? orc_compose(Sinv, X) : X;
-    n_corr = orc_find_correspondences(prm, fixed_img, moving, n_moving, L, moving_img, fidx, midx);
-    memset(&sums, 0, sizeof(sums));
-    if (n_corr <= prm->min_num_correspondences) {
-      status = ORC_STATUS_NOT_ENOUGH_CORRESPONDENCES;
+  int32_t it     = 0; /* rounds executed over both phases */
+  for (int32_t phase = 0; phase < n_phases && status < 0; ++phase) {
+    if (phase == 1 && sums.n_inliers < prm->min_num_inliers) { /* I1: "if sufficient inliers are available" */
       break;
     }
-    linearize(prm, X, fixed, moving, n_moving, fidx, midx, n_corr, sum_mode, tree_threads, &sums);
-    float dx[3];
-    if (solve3(sums.v, prm->damping, dx) != 0) {
-      status = ORC_STATUS_SINGULAR;
-      break;
-    }
-    X = orc_compose(X, orc_v2t(dx[0], dx[1], dx[2])); /* VariableSE2Right: X <- X * v2t(dx) */
-    if (iter_stats) {
-      orc_iter_stats* st = &iter_stats[it];
-      float xyt[3];
-      orc_t2v(X, xyt);
-      st->x              = xyt[0];
-      st->y              = xyt[1];
-      st->theta          = xyt[2];
-      st->chi_inliers    = sums.v[9];
-      st->chi_kernelized = sums.v[10];
-      st->n_inliers      = sums.n_inliers;
-      st->n_kernelized   = sums.n_kernelized;
-      st->n_corr         = n_corr;
+    float chi_prev = 0.f;
+    for (int32_t k = 0; k < prm->max_iterations; ++k) {
+      /* slice->findCorrespondences(): local_map_in_sensor = sensor_in_robot^-1 * moving_in_fixed */
+      const orc_iso L = prm->with_sensor ? orc_compose(Sinv, X) : X;
+      n_corr = orc_find_correspondences(prm, fixed_img, moving, n_moving, L, moving_img, fidx, midx);
+      memset(&sums, 0, sizeof(sums));
+      if (n_corr <= prm->min_num_correspondences) {
+        status = ORC_STATUS_NOT_ENOUGH_CORRESPONDENCES;
+        break;
+      }
+      linearize(prm, X, fixed, moving, n_moving, fidx, midx, n_corr, sum_mode, tree_threads, phase == 1, &sums);
+      if (prm->algorithm == ORC_ALGORITHM_LM) {
+        X = lm_round(prm, &lm, &sums, X, fixed, moving, n_moving, fidx, midx, n_corr, sum_mode, tree_threads);
+      } else {
+        float dx[3];
+        if (solve3(sums.v, prm->damping, dx) != 0) {
+          status = ORC_STATUS_SINGULAR;
+          break;
+        }
+        X = orc_compose(X, orc_v2t(dx[0], dx[1], dx[2])); /* VariableSE2Right: X <- X * v2t(dx) */
+      }
+      if (iter_stats) {
+        fill_iter(&iter_stats[it], X, &sums, n_corr);
+      }
+      ++it;
+      const float chi = sums.v[9] + sums.v[10];
+      if (prm->termination_epsilon > 0.f && k > 0 && chi_prev - chi < prm->termination_epsilon * chi_prev) { /* T1 */
+        break;
+      }
+      chi_prev = chi;
     }
   }
   if (status < 0) {
@@ -553,6 +827,8 @@ void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
   out->x              = xyt[0];
   out->y              = xyt[1];
   out->theta          = xyt[2];
+  out->c              = X.c;
+  out->s              = X.s;
   out->chi_inliers    = sums.v[9];
   out->chi_kernelized = sums.v[10];
   out->n_inliers      = sums.n_inliers;
@@ -560,6 +836,7 @@ void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
   out->n_corr         = n_corr;
   out->status         = status;
   out->iterations     = it;
+  out->lm_rejected    = lm.rejected;
   for (int s = 0; s < 6; ++s) {
     out->H[s] = sums.v[s];
   }
@@ -569,21 +846,29 @@ void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
   free(midx);
 }
 
+void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
+               const orc_point* moving, int32_t n_moving, const float* init_xyt,
+               int32_t sum_mode, int32_t tree_threads, orc_result* out,
+               orc_iter_stats* iter_stats) {
+  orc_align_iso(prm, fixed, n_fixed, moving, n_moving, orc_v2t(init_xyt[0], init_xyt[1], init_xyt[2]), sum_mode,
+                tree_threads, out, iter_stats);
+}
+
 void orc_align_batch(const orc_params* prm, const orc_point* fixed_pts, const int32_t* fixed_off,
                      const orc_point* moving_pts, const int32_t* moving_off,
-                     const int32_t* fixed_id, const int32_t* moving_id, const float* init_xyt,
-                     int32_t n_pairs, int32_t sum_mode, int32_t tree_threads, int32_t n_threads,
-                     orc_result* out, orc_iter_stats* iter_stats) {
+                     const int32_t* fixed_id, const int32_t* moving_id, const float* init_pose,
+                     int32_t pose_stride, int32_t n_pairs, int32_t sum_mode, int32_t tree_threads,
+                     int32_t n_threads, orc_result* out, orc_iter_stats* iter_stats) {
+  const size_t n_iter = (size_t) prm->max_iterations * (prm->enable_inlier_only_runs ? 2 : 1);
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 8) num_threads(n_threads > 1 ? n_threads : 1)
 #endif
   for (int32_t p = 0; p < n_pairs; ++p) {
     const int32_t f = fixed_id ? fixed_id[p] : p;
     const int32_t m = moving_id ? moving_id[p] : p;
-    orc_align(prm, fixed_pts + fixed_off[f], fixed_off[f + 1] - fixed_off[f],
-              moving_pts + moving_off[m], moving_off[m + 1] - moving_off[m], init_xyt + 3 * p,
-              sum_mode, tree_threads, out + p,
-              iter_stats ? iter_stats + (size_t) p * prm->max_iterations : NULL);
+    orc_align_iso(prm, fixed_pts + fixed_off[f], fixed_off[f + 1] - fixed_off[f], moving_pts + moving_off[m],
+                  moving_off[m + 1] - moving_off[m], pose_at(init_pose, (size_t) p, pose_stride), sum_mode,
+                  tree_threads, out + p, iter_stats ? iter_stats + (size_t) p * n_iter : NULL);
   }
 }
 
@@ -593,7 +878,7 @@ void orc_align_batch(const orc_params* prm, const orc_point* fixed_pts, const in
 /* SE2PriorErrorFactor [srrg2_solver types_2d/se2_prior_error_factor; slice class named at
  * L0.json:291-310, MULTI.json:400-422] -- D15 */
 static void prior_eval(const orc_prior* pr, orc_iso X, float* e, orc_iso* P_out) {
-  const orc_iso Zinv = orc_inverse(orc_v2t(pr->z[0], pr->z[1], pr->z[2]));
+  const orc_iso Zinv = orc_inverse(pose_at(pr->z, 0, pr->z_is_iso ? 4 : 3));
   const orc_iso P    = orc_compose(Zinv, X);
   e[0]               = P.tx;
   e[1]               = P.ty;
@@ -654,7 +939,7 @@ static int prior_contribution(const orc_prior* pr, orc_iso X, float* v) {
 
 void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point* const* fixed,
                      const int32_t* n_fixed, const orc_point* const* moving, const int32_t* n_moving,
-                     const orc_prior* prior, const float* init_xyt, int32_t sum_mode, int32_t tree_threads,
+                     const orc_prior* prior, orc_iso init, int32_t sum_mode, int32_t tree_threads,
                      orc_result* out, orc_iter_stats* iter_stats) {
   const int32_t max_it = slices[0].max_iterations; /* D17 */
   orc_cell* fixed_img[ORC_MAX_SLICES];
@@ -667,14 +952,13 @@ void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point
     orc_project(&slices[s], orc_v2t(0.f, 0.f, 0.f), fixed[s], n_fixed[s], fixed_img[s]);
     Sinv[s] = orc_v2t(0.f, 0.f, 0.f);
     if (slices[s].with_sensor) {
-      Sinv[s] = orc_inverse(orc_v2t(slices[s].sensor_in_robot[0], slices[s].sensor_in_robot[1],
-                                    slices[s].sensor_in_robot[2]));
+      Sinv[s] = orc_inverse(sensor_iso(&slices[s]));
     }
   }
   orc_cell* moving_img = (orc_cell*) malloc(sizeof(orc_cell) * (size_t) Cmax);
   int32_t* fidx        = (int32_t*) malloc(sizeof(int32_t) * (size_t) Cmax);
   int32_t* midx        = (int32_t*) malloc(sizeof(int32_t) * (size_t) Cmax);
-  orc_iso X            = orc_v2t(init_xyt[0], init_xyt[1], init_xyt[2]);
+  orc_iso X            = init;
   memset(out, 0, sizeof(*out));
   if (iter_stats) {
     memset(iter_stats, 0, sizeof(orc_iter_stats) * (size_t) max_it);
@@ -696,7 +980,7 @@ void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point
         continue;
       }
       lin_sums ss;
-      linearize(&slices[s], X, fixed[s], moving[s], n_moving[s], fidx, midx, nc, sum_mode, tree_threads, &ss);
+      linearize(&slices[s], X, fixed[s], moving[s], n_moving[s], fidx, midx, nc, sum_mode, tree_threads, 0, &ss);
       for (int k = 0; k < NSLOT; ++k) { /* D16 */
         tot.v[k] = contributed ? tot.v[k] + ss.v[k] : ss.v[k];
       }
@@ -727,15 +1011,7 @@ void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point
     }
     X = orc_compose(X, orc_v2t(dx[0], dx[1], dx[2]));
     if (iter_stats) {
-      orc_iter_stats* st = &iter_stats[it];
-      float xyt[3];
-      orc_t2v(X, xyt);
-      st->x = xyt[0], st->y = xyt[1], st->theta = xyt[2];
-      st->chi_inliers    = tot.v[9];
-      st->chi_kernelized = tot.v[10];
-      st->n_inliers      = tot.n_inliers;
-      st->n_kernelized   = tot.n_kernelized;
-      st->n_corr         = n_corr;
+      fill_iter(&iter_stats[it], X, &tot, n_corr);
     }
   }
   if (status < 0) {
@@ -744,6 +1020,7 @@ void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point
   float xyt[3];
   orc_t2v(X, xyt);
   out->x = xyt[0], out->y = xyt[1], out->theta = xyt[2];
+  out->c = X.c, out->s = X.s;
   out->chi_inliers    = tot.v[9];
   out->chi_kernelized = tot.v[10];
   out->n_inliers      = tot.n_inliers;
@@ -765,9 +1042,9 @@ void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point
 void orc_align_multi_batch(const orc_params* slices, int32_t n_slices, const orc_point* const* fixed_pts,
                            const int32_t* const* fixed_off, const orc_point* const* moving_pts,
                            const int32_t* const* moving_off, const int32_t* fixed_id, const int32_t* moving_id,
-                           const orc_prior* prior, const float* prior_z, const float* init_xyt, int32_t n_pairs,
-                           int32_t sum_mode, int32_t tree_threads, int32_t n_threads, orc_result* out,
-                           orc_iter_stats* iter_stats) {
+                           const orc_prior* prior, const float* prior_z, const float* init_pose, int32_t pose_stride,
+                           int32_t n_pairs, int32_t sum_mode, int32_t tree_threads, int32_t n_threads,
+                           orc_result* out, orc_iter_stats* iter_stats) {
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 8) num_threads(n_threads > 1 ? n_threads : 1)
 #endif
@@ -786,10 +1063,12 @@ void orc_align_multi_batch(const orc_params* slices, int32_t n_slices, const orc
     orc_prior pr;
     if (prior && prior_z) {
       pr = *prior;
-      memcpy(pr.z, prior_z + 3 * (size_t) p, sizeof(float) * 3);
+      memcpy(pr.z, prior_z + (size_t) pose_stride * (size_t) p, sizeof(float) * (size_t) pose_stride);
+      pr.z_is_iso = pose_stride == 4;
     }
-    orc_align_multi(slices, n_slices, fx, nf, mv, nm, (prior && prior_z) ? &pr : NULL, init_xyt + 3 * p, sum_mode,
-                    tree_threads, out + p, iter_stats ? iter_stats + (size_t) p * slices[0].max_iterations : NULL);
+    orc_align_multi(slices, n_slices, fx, nf, mv, nm, (prior && prior_z) ? &pr : NULL,
+                    pose_at(init_pose, (size_t) p, pose_stride), sum_mode, tree_threads, out + p,
+                    iter_stats ? iter_stats + (size_t) p * slices[0].max_iterations : NULL);
   }
 }
 
@@ -850,6 +1129,12 @@ int32_t orc_max_threads(void) {
 void orc_libm_atan2f_n(const float* y, const float* x, float* out, long n) {
   for (long i = 0; i < n; ++i) {
     out[i] = atan2f(y[i], x[i]);
+  }
+}
+
+void orc_libm_logf_n(const float* x, float* out, long n) {
+  for (long i = 0; i < n; ++i) {
+    out[i] = logf(x[i]);
   }
 }
 

@@ -12,7 +12,7 @@
  * this path.  What is in-repo is followed line by line
  * (correspondence_finder_projective_2d.cpp:18-77); what lives in the un-vendored
  * dependencies is restated from their published behaviour, and every result-affecting
- * choice is a numbered decision point (D1..D17 aligner, P1..P8 raw-scan pre-processor) documented in
+ * choice is a numbered decision point (D1..D19 aligner, L1..L8 Levenberg-Marquardt, I1 / T1 aligner options, P1..P8 raw-scan pre-processor) documented in
  * ls2d_oracle.c.  The one number the reference's own tests pin on a restated row -- the Synthetic
  * fixture pre-processes into exactly 100 points (tests/test_measurement_adaptor.cpp:36) -- is checked
  * in tests/test_oracle_preprocess.py.
@@ -72,10 +72,24 @@ typedef struct {
   int32_t max_iterations;
   int32_t min_num_correspondences;
   int32_t min_num_inliers;
-  /* AlignerSliceProcessorLaser2DWithSensor: sensor_in_robot (x, y, theta) */
+  /* AlignerSliceProcessorLaser2DWithSensor: 1 = sensor_in_robot as (x, y, theta); 2 = as the isometry
+   * (tx, ty) = sensor_in_robot[0..1], (c, s) = sensor_in_robot_cs */
   int32_t with_sensor;
   float sensor_in_robot[3];
+  float sensor_in_robot_cs[2];
+  /* the rest mirrors ls2d_params (include/ls2d.h) field for field */
+  int32_t factor;                  /* ORC_FACTOR_PLANE2PLANE | ORC_FACTOR_POINT2POINT (D19) */
+  int32_t algorithm;               /* ORC_ALGORITHM_GN | ORC_ALGORITHM_LM (L1..L8) */
+  float lm_user_lambda_init, lm_tau, lm_step_low, lm_step_high;
+  int32_t lm_iterations_max, lm_variable_damping;
+  int32_t single_rounding_accumulation; /* kernel selection only; the oracle's arithmetic follows tree_threads */
+  int32_t enable_inlier_only_runs;      /* I1 */
+  int32_t keep_only_inlier_correspondences;
+  float termination_epsilon;            /* T1; <= 0: none */
 } orc_params;
+
+enum { ORC_FACTOR_PLANE2PLANE = 0, ORC_FACTOR_POINT2POINT = 1 };
+enum { ORC_ALGORITHM_GN = 0, ORC_ALGORITHM_LM = 1 };
 
 enum {
   ORC_STATUS_SUCCESS = 0,
@@ -84,7 +98,7 @@ enum {
   ORC_STATUS_SINGULAR = 3
 };
 
-/* 64-byte result record; same field order as ls2d_result in include/ls2d.h */
+/* 80-byte result record; same field order as ls2d_result in include/ls2d.h */
 typedef struct {
   float x, y, theta;     /* movingInFixed() as t2v */
   float chi_inliers;     /* last iteration's stats (linearisation point of that iteration) */
@@ -95,13 +109,17 @@ typedef struct {
   int32_t status;
   int32_t iterations;    /* iterations actually run */
   float H[6];            /* H00 H01 H02 H11 H12 H22 of the last linearisation */
+  float c, s;            /* rotation of movingInFixed() as the state holds it (D12) */
+  int32_t lm_rejected;   /* rejected Levenberg-Marquardt trial steps, all rounds */
+  int32_t reserved;
 } orc_result;
 
-/* per-iteration record (32 B); pose is the estimate AFTER that iteration's update */
+/* per-iteration record (40 B); pose is the estimate AFTER that iteration's update */
 typedef struct {
   float x, y, theta;
   float chi_inliers, chi_kernelized;
   int32_t n_inliers, n_kernelized, n_corr;
+  float c, s;
 } orc_iter_stats;
 
 /* accumulation order (D10): sequential in correspondence order (the reference's), or the
@@ -135,19 +153,24 @@ int32_t orc_find_correspondences(const orc_params* prm, const orc_cell* fixed_im
 void orc_error_and_jacobian(const orc_params* prm, orc_iso X, orc_point fixed, orc_point moving,
                             float* e, float* J);
 
-/* MultiAligner2D::compute() for one pair */
+/* MultiAligner2D::compute() for one pair; iter_stats holds max_iterations records (2 * max_iterations with
+ * enable_inlier_only_runs).  orc_align takes the initial guess as (x, y, theta), orc_align_iso as the isometry. */
+void orc_align_iso(const orc_params* prm, const orc_point* fixed, int32_t n_fixed, const orc_point* moving,
+                   int32_t n_moving, orc_iso init, int32_t sum_mode, int32_t tree_threads, orc_result* out,
+                   orc_iter_stats* iter_stats);
 void orc_align(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
                const orc_point* moving, int32_t n_moving, const float* init_xyt,
                int32_t sum_mode, int32_t tree_threads, orc_result* out,
                orc_iter_stats* iter_stats /* max_iterations records or NULL */);
 
 /* batch over CSR clouds; n_threads <= 1 runs the reference's single-threaded model,
- * otherwise an OpenMP parallel-for over the independent pairs */
+ * otherwise an OpenMP parallel-for over the independent pairs.  init_pose: pose_stride floats per pair
+ * (3: x, y, theta; 4: tx, ty, c, s) */
 void orc_align_batch(const orc_params* prm, const orc_point* fixed_pts, const int32_t* fixed_off,
                      const orc_point* moving_pts, const int32_t* moving_off,
-                     const int32_t* fixed_id, const int32_t* moving_id, const float* init_xyt,
-                     int32_t n_pairs, int32_t sum_mode, int32_t tree_threads, int32_t n_threads,
-                     orc_result* out, orc_iter_stats* iter_stats);
+                     const int32_t* fixed_id, const int32_t* moving_id, const float* init_pose,
+                     int32_t pose_stride, int32_t n_pairs, int32_t sum_mode, int32_t tree_threads,
+                     int32_t n_threads, orc_result* out, orc_iter_stats* iter_stats);
 
 
 /* ---- multi-slice aligner (MULTI.json:700-730: laser_0 + odometry prior + laser_1 in one 3x3 system) ----
@@ -159,7 +182,8 @@ void orc_align_batch(const orc_params* prm, const orc_point* fixed_pts, const in
  * prediction z of moving_in_fixed with information matrix Omega (upper triangle O00 O01 O02 O11 O12 O22);
  * cauchy_chi_threshold <= 0: no robustifier (both configurations: "#pointer" -1) */
 typedef struct {
-  float z[3];
+  float z[4];          /* z_is_iso == 0: (x, y, theta); 1: (tx, ty, c, s) */
+  int32_t z_is_iso;
   float information[6];
   float cauchy_chi_threshold;
 } orc_prior;
@@ -171,17 +195,17 @@ void orc_prior_error_and_jacobian(const orc_prior* prior, orc_iso X, float* e, f
  * optional prior (NULL: none) */
 void orc_align_multi(const orc_params* slices, int32_t n_slices, const orc_point* const* fixed,
                      const int32_t* n_fixed, const orc_point* const* moving, const int32_t* n_moving,
-                     const orc_prior* prior, const float* init_xyt, int32_t sum_mode, int32_t tree_threads,
+                     const orc_prior* prior, orc_iso init, int32_t sum_mode, int32_t tree_threads,
                      orc_result* out, orc_iter_stats* iter_stats);
 
-/* batch: slice s reads clouds fixed_id[p] / moving_id[p] (NULL: p) of its own CSR sets; prior_z [n_pairs * 3]
- * (NULL: no prior) shares information / threshold of `prior` */
+/* batch: slice s reads clouds fixed_id[p] / moving_id[p] (NULL: p) of its own CSR sets; prior_z [n_pairs * pose_stride]
+ * (NULL: no prior) shares information / threshold of `prior`; init_pose / prior_z: pose_stride floats per pair */
 void orc_align_multi_batch(const orc_params* slices, int32_t n_slices, const orc_point* const* fixed_pts,
                            const int32_t* const* fixed_off, const orc_point* const* moving_pts,
                            const int32_t* const* moving_off, const int32_t* fixed_id, const int32_t* moving_id,
-                           const orc_prior* prior, const float* prior_z, const float* init_xyt, int32_t n_pairs,
-                           int32_t sum_mode, int32_t tree_threads, int32_t n_threads, orc_result* out,
-                           orc_iter_stats* iter_stats);
+                           const orc_prior* prior, const float* prior_z, const float* init_pose, int32_t pose_stride,
+                           int32_t n_pairs, int32_t sum_mode, int32_t tree_threads, int32_t n_threads,
+                           orc_result* out, orc_iter_stats* iter_stats);
 
 /* loop-closure acceptance gates (MultiLoopDetectorBruteForce2D, LASER_0.json:627-634) and the
  * deterministic best-of rule. Returns index of the best accepted result or -1. */
@@ -240,6 +264,7 @@ void orc_preprocess_scans(const orc_scan_params* sp, const float* ranges, int32_
 /* host libm bulk drivers for tests/test_math_host.py */
 void orc_libm_atan2f_n(const float* y, const float* x, float* out, long n);
 void orc_libm_sincosf_n(const float* x, float* s, float* c, long n);
+void orc_libm_logf_n(const float* x, float* out, long n);
 void orc_column_n(const orc_params* prm, const float* y, const float* x, int32_t* col, long n);
 
 #ifdef __cplusplus

@@ -31,16 +31,25 @@ namespace {
     pr.param_range_min.setValue(prm->range_min);
     pr.param_range_max.setValue(prm->range_max);
   }
-  Isometry2f iso(const float* xyt) { return Isometry2f(orc_v2t(xyt[0], xyt[1], xyt[2])); }
+  // a pose in either wire format: stride 3 = (x, y, theta) through geometry2d::v2t, stride 4 = the Isometry2f content
+  // (tx, ty, c, s) itself -- what a caller of the reference holds (e.g. an accumulated product of increments)
+  Isometry2f iso(const float* p, int32_t stride = 3) {
+    if (stride == 4) {
+      orc_iso T;
+      T.tx = p[0], T.ty = p[1], T.c = p[2], T.s = p[3];
+      return Isometry2f(T);
+    }
+    return Isometry2f(orc_v2t(p[0], p[1], p[2]));
+  }
 }  // namespace
 
 extern "C" {
 
 // CorrespondenceFinderProjective2f::compute(); n_calls > 1 repeats compute() on the same object with the poses
 // xyt[3 * k] (exercises the _fixed_changed_flag caching, .cpp:37-44); the LAST call's list is returned
-int32_t ref_find_correspondences(const orc_params* prm, const orc_point* fixed, int32_t n_fixed, const orc_point* moving,
-                                 int32_t n_moving, const float* xyt, int32_t n_calls, int32_t* fixed_idx,
-                                 int32_t* moving_idx) {
+static int32_t find_impl(const orc_params* prm, const orc_point* fixed, int32_t n_fixed, const orc_point* moving,
+                         int32_t n_moving, const float* xyt, int32_t stride, int32_t n_calls, int32_t* fixed_idx,
+                         int32_t* moving_idx) {
   PointNormal2fVectorCloud f, m;
   to_cloud(fixed, n_fixed, f);
   to_cloud(moving, n_moving, m);
@@ -53,7 +62,7 @@ int32_t ref_find_correspondences(const orc_params* prm, const orc_point* fixed, 
   cf.setMoving(&m);
   cf.setCorrespondences(&corr);
   for (int32_t k = 0; k < n_calls; ++k) {
-    cf.setLocalMapInSensor(iso(xyt + 3 * k));
+    cf.setLocalMapInSensor(iso(xyt + stride * k, stride));
     cf.compute();
   }
   for (size_t i = 0; i < corr.size(); ++i) {
@@ -63,9 +72,22 @@ int32_t ref_find_correspondences(const orc_params* prm, const orc_point* fixed, 
   return (int32_t) corr.size();
 }
 
+int32_t ref_find_correspondences(const orc_params* prm, const orc_point* fixed, int32_t n_fixed, const orc_point* moving,
+                                 int32_t n_moving, const float* xyt, int32_t n_calls, int32_t* fixed_idx,
+                                 int32_t* moving_idx) {
+  return find_impl(prm, fixed, n_fixed, moving, n_moving, xyt, 3, n_calls, fixed_idx, moving_idx);
+}
+// the same with local_map_in_sensor handed over as the Isometry2f itself (4 floats per pose: tx, ty, c, s)
+int32_t ref_find_correspondences_iso(const orc_params* prm, const orc_point* fixed, int32_t n_fixed,
+                                     const orc_point* moving, int32_t n_moving, const float* iso4, int32_t n_calls,
+                                     int32_t* fixed_idx, int32_t* moving_idx) {
+  return find_impl(prm, fixed, n_fixed, moving, n_moving, iso4, 4, n_calls, fixed_idx, moving_idx);
+}
+
 // MergerProjective2D::compute(): scene must have room for n_scene + canvas_cols points; returns the new size
-int32_t ref_merge(const orc_params* prm, float merge_threshold, orc_point* scene, int32_t n_scene,
-                  const orc_point* measurement, int32_t n_measurement, const float* measurement_in_scene_xyt) {
+static int32_t merge_impl(const orc_params* prm, float merge_threshold, orc_point* scene, int32_t n_scene,
+                          const orc_point* measurement, int32_t n_measurement, const float* measurement_in_scene_xyt,
+                          int32_t stride) {
   PointNormal2fVectorCloud s, m;
   to_cloud(scene, n_scene, s);
   to_cloud(measurement, n_measurement, m);
@@ -74,16 +96,24 @@ int32_t ref_merge(const orc_params* prm, float merge_threshold, orc_point* scene
   mg.param_merge_threshold.setValue(merge_threshold);
   mg.setScene(&s);
   mg.setMeasurement(&m);
-  mg.setMeasurementInScene(iso(measurement_in_scene_xyt));
+  mg.setMeasurementInScene(iso(measurement_in_scene_xyt, stride));
   mg.compute();
   from_cloud(s, scene);
   return (int32_t) s.size();
 }
+int32_t ref_merge(const orc_params* prm, float merge_threshold, orc_point* scene, int32_t n_scene,
+                  const orc_point* measurement, int32_t n_measurement, const float* measurement_in_scene_xyt) {
+  return merge_impl(prm, merge_threshold, scene, n_scene, measurement, n_measurement, measurement_in_scene_xyt, 3);
+}
+int32_t ref_merge_iso(const orc_params* prm, float merge_threshold, orc_point* scene, int32_t n_scene,
+                      const orc_point* measurement, int32_t n_measurement, const float* measurement_in_scene_iso4) {
+  return merge_impl(prm, merge_threshold, scene, n_scene, measurement, n_measurement, measurement_in_scene_iso4, 4);
+}
 
 // SceneClipperProjective2D::compute() (voxelize_resolution 0 in both shipped configurations; > 0 takes the
 // voxelize branch, .cpp:36-48); out holds canvas_cols points; returns the count
-int32_t ref_clip(const orc_params* prm, const orc_point* scene, int32_t n_scene, const float* robot_in_local_map_xyt,
-                 const float* sensor_in_robot_xyt, float voxelize_resolution, orc_point* out) {
+static int32_t clip_impl(const orc_params* prm, const orc_point* scene, int32_t n_scene, const float* robot_in_local_map_xyt,
+                         const float* sensor_in_robot_xyt, int32_t stride, float voxelize_resolution, orc_point* out) {
   PointNormal2fVectorCloud full, clipped;
   to_cloud(scene, n_scene, full);
   SceneClipperProjective2D cl;
@@ -91,11 +121,19 @@ int32_t ref_clip(const orc_params* prm, const orc_point* scene, int32_t n_scene,
   cl.param_voxelize_resolution.setValue(voxelize_resolution);
   cl.setFullScene(&full);
   cl.setClippedSceneInRobot(&clipped);
-  cl.setRobotInLocalMap(iso(robot_in_local_map_xyt));
-  cl.setSensorInRobot(iso(sensor_in_robot_xyt));
+  cl.setRobotInLocalMap(iso(robot_in_local_map_xyt, stride));
+  cl.setSensorInRobot(iso(sensor_in_robot_xyt, stride));
   cl.compute();
   from_cloud(clipped, out);
   return (int32_t) clipped.size();
+}
+int32_t ref_clip(const orc_params* prm, const orc_point* scene, int32_t n_scene, const float* robot_in_local_map_xyt,
+                 const float* sensor_in_robot_xyt, float voxelize_resolution, orc_point* out) {
+  return clip_impl(prm, scene, n_scene, robot_in_local_map_xyt, sensor_in_robot_xyt, 3, voxelize_resolution, out);
+}
+int32_t ref_clip_iso(const orc_params* prm, const orc_point* scene, int32_t n_scene, const float* robot_in_local_map_iso4,
+                     const float* sensor_in_robot_iso4, float voxelize_resolution, orc_point* out) {
+  return clip_impl(prm, scene, n_scene, robot_in_local_map_iso4, sensor_in_robot_iso4, 4, voxelize_resolution, out);
 }
 
 // RawDataPreprocessorProjective2D: setRawData(LaserMessage) + compute(), driven as

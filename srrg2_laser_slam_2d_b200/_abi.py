@@ -29,7 +29,17 @@ class Params(C.Structure):
                 ("normal_cos", C.c_float), ("cauchy_chi_threshold", C.c_float), ("damping", C.c_float),
                 ("max_iterations", C.c_int32), ("min_num_correspondences", C.c_int32),
                 ("min_num_inliers", C.c_int32), ("with_sensor", C.c_int32),
-                ("sensor_in_robot", C.c_float * 3)]
+                ("sensor_in_robot", C.c_float * 3), ("sensor_in_robot_cs", C.c_float * 2),
+                ("factor", C.c_int32), ("algorithm", C.c_int32), ("lm_user_lambda_init", C.c_float),
+                ("lm_tau", C.c_float), ("lm_step_low", C.c_float), ("lm_step_high", C.c_float),
+                ("lm_iterations_max", C.c_int32), ("lm_variable_damping", C.c_int32),
+                ("single_rounding_accumulation", C.c_int32), ("enable_inlier_only_runs", C.c_int32),
+                ("keep_only_inlier_correspondences", C.c_int32), ("termination_epsilon", C.c_float)]
+
+
+FACTOR_PLANE2PLANE, FACTOR_POINT2POINT = 0, 1
+ALGORITHM_GN, ALGORITHM_LM = 0, 1
+POSE_XYT, POSE_ISO = 0, 1
 
 
 class Prior(C.Structure):
@@ -61,26 +71,29 @@ class Gates(C.Structure):
 
 RESULT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
                          ("chi_kernelized", "<f4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"),
-                         ("n_corr", "<i4"), ("status", "<i4"), ("iterations", "<i4"), ("H", "<f4", (6,))])
+                         ("n_corr", "<i4"), ("status", "<i4"), ("iterations", "<i4"), ("H", "<f4", (6,)),
+                         ("c", "<f4"), ("s", "<f4"), ("lm_rejected", "<i4"), ("reserved", "<i4")])
 ITER_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
                        ("chi_kernelized", "<f4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"),
-                       ("n_corr", "<i4")])
+                       ("n_corr", "<i4"), ("c", "<f4"), ("s", "<f4")])
 BEST_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
-                       ("n_inliers", "<i4"), ("n_corr", "<i4"), ("candidate", "<i4"), ("guess", "<i4")])
-assert RESULT_DTYPE.itemsize == 64 and ITER_DTYPE.itemsize == 32 and BEST_DTYPE.itemsize == 32
+                       ("n_inliers", "<i4"), ("n_corr", "<i4"), ("candidate", "<i4"), ("guess", "<i4"),
+                       ("c", "<f4"), ("s", "<f4"), ("iterations", "<i4"), ("reserved", "<i4")])
+assert RESULT_DTYPE.itemsize == 80 and ITER_DTYPE.itemsize == 40 and BEST_DTYPE.itemsize == 48
 
 # every symbol include/ls2d.h declares (tests/test_abi_symbols.py checks the library exports them all)
 EXPORTS = [
     "ls2d_create", "ls2d_destroy", "ls2d_set_stream", "ls2d_sync", "ls2d_strerror", "ls2d_version",
-    "ls2d_default_params", "ls2d_set_params", "ls2d_get_params", "ls2d_upload_clouds", "ls2d_set_clouds_dev",
+    "ls2d_default_params", "ls2d_set_params", "ls2d_get_params", "ls2d_set_pose_format", "ls2d_get_pose_format",
+    "ls2d_upload_clouds", "ls2d_set_clouds_dev",
     "ls2d_align_batch", "ls2d_align_batch_dev", "ls2d_align_pairs_host", "ls2d_score_batch",
     "ls2d_score_batch_dev", "ls2d_find_correspondences", "ls2d_project", "ls2d_verify", "ls2d_verify_dev",
-    "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_threads", "ls2d_reduction_shape", "ls2d_launch_count",
+    "ls2d_reduce_best", "ls2d_verify_sharded_nccl", "ls2d_reduction_shape", "ls2d_launch_count",
     "ls2d_clip_scenes", "ls2d_merge_scene", "ls2d_merge_scene_dev", "ls2d_align_multi", "ls2d_align_multi_dev",
     "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
     "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
     "ls2d_clip_scenes_to_set", "ls2d_track_batch", "ls2d_verify_pairs", "ls2d_verify_pairs_dev",
-    "ls2d_clip_scenes_voxelized", "ls2d_multi_reduction_threads",
+    "ls2d_clip_scenes_voxelized", "ls2d_multi_reduction_threads", "ls2d_classify_correspondences",
 ]
 
 _lib = None
@@ -105,6 +118,8 @@ def load():
     L.ls2d_default_params.argtypes, L.ls2d_default_params.restype = [PP], None
     L.ls2d_set_params.argtypes = [vp, PP]
     L.ls2d_get_params.argtypes = [vp, PP]
+    L.ls2d_set_pose_format.argtypes = [vp, C.c_int]
+    L.ls2d_get_pose_format.argtypes = [vp]
     L.ls2d_upload_clouds.argtypes = [vp, C.c_int, vp, vp, i32]
     L.ls2d_set_clouds_dev.argtypes = [vp, C.c_int, vp, vp, i32, i32]
     L.ls2d_align_batch.argtypes = [vp, vp, vp, vp, i32, vp, vp]
@@ -115,6 +130,7 @@ def load():
     L.ls2d_find_correspondences.argtypes = [vp, i32, i32, vp, vp, vp, C.POINTER(i32)]
     L.ls2d_find_correspondences_in.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, C.POINTER(i32)]
     L.ls2d_project.argtypes = [vp, C.c_int, i32, vp, vp, vp]
+    L.ls2d_classify_correspondences.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     L.ls2d_verify.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]
     L.ls2d_verify_dev.argtypes = [vp, i32, vp, i32, vp, i32, GP, i32, vp, vp]
     L.ls2d_reduce_best.argtypes = [vp, i32, vp]
@@ -135,8 +151,7 @@ def load():
     L.ls2d_clip_scenes_voxelized.argtypes = [vp, C.c_int, vp, vp, vp, i32, f32, vp, vp]
     L.ls2d_clip_scenes_to_set.argtypes = [vp, C.c_int, vp, vp, vp, i32, C.c_int]
     L.ls2d_track_batch.argtypes = [vp, SP, vp, i32, i32, C.c_int, vp, vp, vp, vp]
-    L.ls2d_reduction_threads.argtypes = [i32]
-    L.ls2d_reduction_shape.argtypes = [i32, i32]
+    L.ls2d_reduction_shape.argtypes = [PP, i32]
     L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
     _lib = L
     return L
@@ -147,10 +162,25 @@ def default_params(**kw) -> Params:
     load().ls2d_default_params(C.byref(p))
     for k, v in kw.items():
         if k == "sensor_in_robot":
-            p.sensor_in_robot = (C.c_float * 3)(*v)
+            set_sensor(p, v)
+        elif k == "sensor_in_robot_cs":
+            p.sensor_in_robot_cs = (C.c_float * 2)(*[float(x) for x in v])
         else:
             setattr(p, k, v)
     return p
+
+
+def set_sensor(p: Params, v):
+    """sensor_in_robot of a params record: 3 values = (x, y, theta), 4 values = the isometry (tx, ty, c, s), which
+    switches a WithSensor slice to with_sensor = 2"""
+    v = [float(x) for x in v]
+    if len(v) == 4:
+        p.sensor_in_robot = (C.c_float * 3)(v[0], v[1], 0.0)
+        p.sensor_in_robot_cs = (C.c_float * 2)(v[2], v[3])
+        if p.with_sensor:
+            p.with_sensor = 2
+    else:
+        p.sensor_in_robot = (C.c_float * 3)(*v)
 
 
 def default_scan_params(**kw) -> ScanParams:
@@ -177,10 +207,14 @@ def _i32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
 
 
-def reduction_threads(max_points: int, canvas_cols: int = 1081) -> int:
-    """shape of the aligner kernel's H/b reduction (threads per pair | warp-combine flag << 16): the value the
-    oracle's SUM_TREE mode takes as tree_threads"""
-    return load().ls2d_reduction_shape(max_points, canvas_cols)
+def reduction_threads(max_points: int, canvas_cols: int = 1081, params: Params | None = None) -> int:
+    """shape of the H/b reduction the aligner runs for these parameters and cloud size (threads per pair | warp-combine
+    flag << 16 | fused-accumulation flag << 17): the value the oracle's SUM_TREE mode takes as tree_threads"""
+    p = params if params is not None else default_params(canvas_cols=canvas_cols)
+    shape = load().ls2d_reduction_shape(C.byref(p), max_points)
+    if shape < 0:
+        raise Ls2dError(f"ls2d_reduction_shape: {shape}")
+    return shape
 
 
 def multi_reduction_threads() -> int:
@@ -239,6 +273,28 @@ class Handle:
     def sync(self):
         self._check(self._L.ls2d_sync(self._h))
 
+    def set_pose_format(self, fmt: int):
+        self._check(self._L.ls2d_set_pose_format(self._h, fmt))
+
+    @property
+    def pose_format(self) -> int:
+        return int(self._L.ls2d_get_pose_format(self._h))
+
+    def _poses(self, a, lead=None):
+        """host poses as a contiguous float32 array [..., 3] (x, y, theta) or [..., 4] (tx, ty, c, s); the handle's
+        pose format follows the array (every pose argument of ONE call must use the same format)"""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        k = a.shape[-1]
+        assert k in (3, 4), "a pose is (x, y, theta) or (tx, ty, c, s)"
+        want = POSE_ISO if k == 4 else POSE_XYT
+        if self.pose_format != want:
+            self.set_pose_format(want)
+        return a if lead is None else a.reshape(lead + (k,))
+
+    @property
+    def iters_per_pair(self) -> int:
+        return self.params.max_iterations * (2 if self.params.enable_inlier_only_runs else 1)
+
     @property
     def launch_count(self) -> int:
         return int(self._L.ls2d_launch_count(self._h))
@@ -256,11 +312,12 @@ class Handle:
 
     # ---- registration
     def align_batch(self, init_xyt, fixed_id=None, moving_id=None, want_iters: bool = False):
-        init = _f32(init_xyt).reshape(-1, 3)
+        init = self._poses(init_xyt)
+        init = init.reshape(-1, init.shape[-1])
         fid, mid = _i32(fixed_id), _i32(moving_id)
         n = len(init)
         out = np.zeros(n, RESULT_DTYPE)
-        its = np.zeros((n, self.params.max_iterations), ITER_DTYPE) if want_iters else None
+        its = np.zeros((n, self.iters_per_pair), ITER_DTYPE) if want_iters else None
         self._check(self._L.ls2d_align_batch(self._h, _ptr(fid), _ptr(mid), _ptr(init), n, _ptr(out), _ptr(its)))
         return (out, its) if want_iters else out
 
@@ -275,6 +332,7 @@ class Handle:
         n = len(fixed_off) - 1
         if out is None:
             out = np.zeros(n, RESULT_DTYPE)
+        init_xyt = self._poses(init_xyt)  # no copy when the caller hands a contiguous float32 (e.g. pinned) array
         self._check(self._L.ls2d_align_pairs_host(self._h, _ptr(fixed_pts), _ptr(fixed_off), _ptr(moving_pts),
                                                   _ptr(moving_off), _ptr(init_xyt), n, _ptr(out)))
         return out
@@ -286,8 +344,10 @@ class Handle:
         n_s = len(slices)
         arr = (Params * n_s)(*slices)
         fs, ms = _i32(fixed_sets), _i32(moving_sets)
-        init = _f32(init_xyt).reshape(-1, 3)
-        pz = None if prior_z is None else _f32(prior_z).reshape(-1, 3)
+        init = self._poses(init_xyt)
+        init = init.reshape(-1, init.shape[-1])
+        pz = None if prior_z is None else self._poses(prior_z).reshape(len(init), -1)
+        assert pz is None or pz.shape[1] == init.shape[1], "init and prior_z share one pose format"
         fid, mid = _i32(fixed_id), _i32(moving_id)
         n = len(init)
         out = np.zeros(n, RESULT_DTYPE)
@@ -308,7 +368,8 @@ class Handle:
                                                  n_pairs, C.c_void_p(out_ptr), C.c_void_p(iters_ptr or 0)))
 
     def score_batch(self, xyt, fixed_id=None, moving_id=None):
-        xyt = _f32(xyt).reshape(-1, 3)
+        xyt = self._poses(xyt)
+        xyt = xyt.reshape(-1, xyt.shape[-1])
         fid, mid = _i32(fixed_id), _i32(moving_id)
         out = np.zeros(len(xyt), RESULT_DTYPE)
         self._check(self._L.ls2d_score_batch(self._h, _ptr(fid), _ptr(mid), _ptr(xyt), len(xyt), _ptr(out)))
@@ -320,7 +381,7 @@ class Handle:
 
     # ---- finder / projector
     def find_correspondences(self, fixed_id: int, moving_id: int, local_map_in_sensor_xyt):
-        xyt = _f32(local_map_in_sensor_xyt)
+        xyt = self._poses(local_map_in_sensor_xyt)
         cols = self.params.canvas_cols
         fi, mi = np.zeros(cols, np.int32), np.zeros(cols, np.int32)
         n = C.c_int32(0)
@@ -328,8 +389,18 @@ class Handle:
                                                       C.byref(n)))
         return fi[:n.value].copy(), mi[:n.value].copy()
 
+    def classify_correspondences(self, fixed_id: int, moving_id: int, moving_in_fixed, fixed_idx, moving_idx,
+                                 fixed_set: int = LS2D_FIXED, moving_set: int = LS2D_MOVING):
+        """inlier flags (chi < cauchy_chi_threshold at the estimate) of given correspondences"""
+        X = self._poses(moving_in_fixed)
+        fi, mi = _i32(fixed_idx), _i32(moving_idx)
+        out = np.zeros(len(fi), np.uint8)
+        self._check(self._L.ls2d_classify_correspondences(self._h, fixed_set, moving_set, fixed_id, moving_id, _ptr(X),
+                                                          _ptr(fi), _ptr(mi), len(fi), _ptr(out)))
+        return out.astype(bool)
+
     def project(self, which: int, cloud_id: int, camera_pose_xyt):
-        xyt = _f32(camera_pose_xyt)
+        xyt = self._poses(camera_pose_xyt)
         cols = self.params.canvas_cols
         idx, depth = np.zeros(cols, np.int32), np.zeros(cols, np.float32)
         self._check(self._L.ls2d_project(self._h, which, cloud_id, _ptr(xyt), _ptr(idx), _ptr(depth)))
@@ -340,8 +411,8 @@ class Handle:
                     voxelize_resolution: float = 0.0):
         """SceneClipperProjective2D: returns a list of clipped clouds [k_r, 4] in the robot frame."""
         ids = _i32(cloud_ids)
-        rob = _f32(robot_in_local_map_xyt).reshape(-1, 3)
-        sen = _f32(sensor_in_robot_xyt)
+        sen = self._poses(sensor_in_robot_xyt)
+        rob = self._poses(robot_in_local_map_xyt).reshape(-1, len(sen))
         n, cols = len(ids), self.params.canvas_cols
         out = np.zeros((n, cols, 4), np.float32)
         cnt = np.zeros(n, np.int32)
@@ -360,7 +431,7 @@ class Handle:
         buf[:len(scene)] = scene
         size = C.c_int32(len(scene))
         counters = np.zeros(3, np.int32)
-        xyt = _f32(measurement_in_scene_xyt)
+        xyt = self._poses(measurement_in_scene_xyt)
         self._check(self._L.ls2d_merge_scene(self._h, _ptr(buf), C.byref(size), cap, _ptr(measurement), len(measurement),
                                              _ptr(xyt), merge_threshold, _ptr(counters)))
         return buf[:size.value].copy(), counters
@@ -395,8 +466,8 @@ class Handle:
 
     def clip_scenes_to_set(self, scene_set: int, cloud_ids, robot_in_local_map_xyt, sensor_in_robot_xyt, out_set: int):
         ids = _i32(cloud_ids)
-        rob = _f32(robot_in_local_map_xyt).reshape(-1, 3)
-        sen = _f32(sensor_in_robot_xyt)
+        sen = self._poses(sensor_in_robot_xyt)
+        rob = self._poses(robot_in_local_map_xyt).reshape(-1, len(sen))
         self._check(self._L.ls2d_clip_scenes_to_set(self._h, scene_set, _ptr(ids), _ptr(rob), _ptr(sen), len(ids),
                                                     out_set))
         self.sync()
@@ -407,8 +478,10 @@ class Handle:
         ranges = _f32(ranges)
         n, n_beams = ranges.shape
         ids = _i32(scene_ids)
-        rob = _f32(robot_in_local_map_xyt).reshape(-1, 3)
-        init = None if init_xyt is None else _f32(init_xyt).reshape(-1, 3)
+        rob = self._poses(robot_in_local_map_xyt)
+        rob = rob.reshape(-1, rob.shape[-1])
+        init = None if init_xyt is None else self._poses(init_xyt).reshape(len(rob), -1)
+        assert init is None or init.shape[1] == rob.shape[1], "robot poses and initial guesses share one pose format"
         if out is None:
             out = np.zeros(n, RESULT_DTYPE)
         self._check(self._L.ls2d_track_batch(self._h, C.byref(sp), _ptr(ranges), n_beams, n, scene_set, _ptr(ids),
@@ -418,7 +491,7 @@ class Handle:
     # ---- loop-closure verification
     def verify(self, query_id: int, candidate_ids, guesses_xyt, gates: Gates, candidate_base: int = 0,
                want_all: bool = False):
-        g = _f32(guesses_xyt)
+        g = self._poses(guesses_xyt)
         n_cand, n_guess = g.shape[0], g.shape[1]
         cand = _i32(candidate_ids)
         best = np.zeros(1, BEST_DTYPE)
@@ -430,7 +503,8 @@ class Handle:
     def verify_pairs(self, fixed_ids, moving_ids, guesses_xyt, group_offsets, gates: Gates, want_all: bool = False):
         """all-pairs search: one ls2d_best per group of consecutive pairs (group_offsets: CSR over the pairs)"""
         fid, mid, off = _i32(fixed_ids), _i32(moving_ids), _i32(group_offsets)
-        g = _f32(guesses_xyt).reshape(-1, 3)
+        g = self._poses(guesses_xyt)
+        g = g.reshape(-1, g.shape[-1])
         n, n_groups = len(g), len(off) - 1
         best = np.zeros(n_groups, BEST_DTYPE)
         allr = np.zeros(n, RESULT_DTYPE) if want_all else None

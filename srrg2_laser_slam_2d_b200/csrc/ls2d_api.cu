@@ -10,72 +10,21 @@
 #include <new>
 #include <vector>
 
-#include "ls2d_kernels.cuh"
-#include "ls2d_icp2.cuh"
-#include "ls2d_icp3.cuh"
-#include "ls2d_multi.cuh"
-#include "ls2d_scan.cuh"
+#include "ls2d_internal.h"
 
 using namespace ls2d;
 
 namespace {
-
-struct cloud_set {
-  float4* pts     = nullptr;
-  int* off        = nullptr;
-  bool owned      = false;
-  size_t cap_pts  = 0;  // points
-  size_t cap_off  = 0;  // ints
-  int n_clouds    = 0;
-  int max_points  = 0;
-};
-
-struct scratch {
-  void* p    = nullptr;
-  size_t cap = 0;
-};
-
-}  // namespace
-
-struct ls2d_handle {
-  int device               = 0;
-  cudaStream_t own_stream  = nullptr;
-  cudaStream_t stream      = nullptr;
-  ls2d_params prm;
-  dev_params dp;
-  cloud_set sets[LS2D_MAX_CLOUD_SETS];
-  scratch d_fid, d_mid, d_init, d_out, d_iters, d_best, d_misc, d_prior, d_ranges, d_clip;
-  scratch d_edge;  // rounding-edge directions of the projector (polar_cam::edge), rebuilt by ls2d_set_params
-  polar_cam edge_key = {};  // camera the table in d_edge was built for
-  scratch d_edge_slice[LS2D_MAX_SLICES];  // the same for the slices of ls2d_align_multi, cached by camera
-  polar_cam edge_slice_key[LS2D_MAX_SLICES] = {};
-  int64_t launches = 0;
-  // host pipeline of ls2d_align_pairs_host: uploads run on their own stream, one event per chunk
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_ready     = nullptr;
-  cudaEvent_t ev_chunk[8]  = {};
-  int variant      = 0;  // LS2D_ICP_VARIANT: tuning knob for the 1081-point kernel shape
-  // NCCL, resolved lazily
-  void* nccl_lib                                                             = nullptr;
-  int (*nccl_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
-};
-
-#define CU(call)                                                        \
-  do {                                                                  \
-    cudaError_t e__ = (call);                                           \
-    if (e__ != cudaSuccess) {                                           \
-      set_last_cuda_error(e__, #call);                                  \
-      return LS2D_ERR_CUDA;                                             \
-    }                                                                   \
-  } while (0)
-
-namespace {
-
 thread_local char g_last_cuda[256] = "";
+}
+
+namespace ls2d {
 
 void set_last_cuda_error(cudaError_t e, const char* what) {
   snprintf(g_last_cuda, sizeof(g_last_cuda), "CUDA error: %s (%s)", cudaGetErrorString(e), what);
 }
+
+int pose_stride(const ls2d_handle* h) { return h->pose_format == LS2D_POSE_ISO ? 4 : 3; }
 
 int reserve(scratch& s, size_t bytes) {
   if (bytes <= s.cap) return LS2D_OK;
@@ -87,6 +36,10 @@ int reserve(scratch& s, size_t bytes) {
   s.cap = want;
   return LS2D_OK;
 }
+
+}  // namespace ls2d
+
+namespace {
 
 void release(scratch& s) {
   if (s.p) cudaFree(s.p);
@@ -106,8 +59,23 @@ bool params_valid(const ls2d_params& p) {
   if (p.canvas_cols < 1 || p.canvas_cols > 7680) return false;
   if (!(p.angle_col_max > p.angle_col_min)) return false;
   if (!(p.range_max > p.range_min)) return false;
+  if (!(p.range_max <= 1.0e5f)) return false;  // invalid beams travel as points at 1e6 m: beyond every legal range_max
   if (p.max_iterations < 0 || p.max_iterations > 100000) return false;
+  if (p.with_sensor < 0 || p.with_sensor > 2) return false;
+  if (p.factor != LS2D_FACTOR_PLANE2PLANE && p.factor != LS2D_FACTOR_POINT2POINT) return false;
+  if (p.algorithm != LS2D_ALGORITHM_GN && p.algorithm != LS2D_ALGORITHM_LM) return false;
+  if (p.algorithm == LS2D_ALGORITHM_LM && (p.lm_iterations_max < 1 || p.lm_iterations_max > 1000)) return false;
   return true;
+}
+
+// sensor_in_robot of a WithSensor slice in either form (include/ls2d.h: with_sensor 1 / 2)
+iso sensor_iso(const ls2d_params& p) {
+  if (p.with_sensor == 2) {
+    iso S;
+    S.tx = p.sensor_in_robot[0], S.ty = p.sensor_in_robot[1], S.c = p.sensor_in_robot_cs[0], S.s = p.sensor_in_robot_cs[1];
+    return S;
+  }
+  return iso_v2t(p.sensor_in_robot[0], p.sensor_in_robot[1], p.sensor_in_robot[2]);
 }
 
 dev_params translate(const ls2d_params& p) {
@@ -123,194 +91,24 @@ dev_params translate(const ls2d_params& p) {
   d.max_iterations          = p.max_iterations;
   d.min_num_correspondences = p.min_num_correspondences;
   d.min_num_inliers         = p.min_num_inliers;
-  d.with_sensor             = p.with_sensor;
+  d.with_sensor             = p.with_sensor ? 1 : 0;
   d.Sinv                    = iso_identity();
-  if (p.with_sensor)
-    d.Sinv = iso_inverse(iso_v2t(p.sensor_in_robot[0], p.sensor_in_robot[1], p.sensor_in_robot[2]));
+  if (p.with_sensor) d.Sinv = iso_inverse(sensor_iso(p));
+  d.factor                  = p.factor;
+  d.algorithm               = p.algorithm;
+  d.lm_user_lambda_init     = p.lm_user_lambda_init;
+  d.lm_tau                  = p.lm_tau;
+  d.lm_step_low             = p.lm_step_low;
+  d.lm_step_high            = p.lm_step_high;
+  d.lm_iterations_max       = p.lm_iterations_max;
+  d.lm_variable_damping     = p.lm_variable_damping;
+  d.inlier_only_runs        = p.enable_inlier_only_runs;
+  d.termination_epsilon     = p.termination_epsilon;
   return d;
 }
 
-// ---- kernel table: (threads, points per thread) by cloud size -------------------------------------
-struct shape {
-  int threads, ppt, minb;
-  int kind;  // 0: points in registers (icp_fused_kernel); 1: streamed from global/L2; 2: staged in shared memory;
-             // 3: points in registers, icp_fused2_kernel (compile-time column stride cs; needs cols < cs)
-  int cs;    // kind 3: column stride (768 covers the 721-column canvas of the shipped configurations, 1152 the
-             // 1081-column one); wider canvases fall back to kind 0
-};
-
-// LS2D_ICP_UNFUSED=1: icp_fused2_kernel<288, 4> with linearize2() instead of linearize2f() (measurement knob)
-bool unfused_requested() { return getenv("LS2D_ICP_UNFUSED") != nullptr; }
-
-shape pick_shape(int max_points, int variant) {
-  if (max_points <= 256) return {128, 2, 6, 0};
-  if (max_points <= 512) return {128, 4, 6, 0};
-  if (max_points <= 768) {
-    switch (variant) {
-      case 40: return {256, 3, 3, 0};  // the generic-pointer kernel
-      case 41: return {256, 3, 4, 3, 768};
-      case 42: return {192, 4, 5, 3, 768};
-      default: return {256, 3, 5, 3, 768};  // 721 beams: 0.276 ms per 4096 pairs (192 x 4 x 5: 0.285, kind 0: 0.358)
-    }
-  }
-  if (max_points <= 1152) {
-    switch (variant) {  // LS2D_ICP_VARIANT: tuning knob, see profiles/r01_variant_sweep.md
-      case 1: return {128, 9, 4, 0};
-      case 2: return {384, 3, 2, 0};
-      case 3: return {256, 5, 3, 0};
-      case 4: return {192, 6, 5, 0};
-      case 5: return {256, 5, 4, 0};
-      case 6: return {192, 6, 4, 0};
-      case 7: return {128, 9, 5, 0};
-      case 8: return {288, 4, 4, 0};
-      case 9: return {288, 4, 3, 0};
-      case 10: return {384, 0, 4, 2};
-      case 11: return {384, 0, 4, 1};
-      case 12: return {256, 0, 6, 2};
-      case 13: return {512, 0, 3, 2};
-      case 20: return {384, 3, 3, 0};  // the generic-pointer kernel (before icp_fused2_kernel)
-      case 21: return {288, 4, 4, 3, 1152};
-      case 22: return {256, 5, 4, 3, 1152};
-      case 23: return {192, 6, 5, 3, 1152};
-      case 24: return {384, 3, 3, 3, 1152};
-      case 30: return {544, 2, 2, 4, 1088};  // icp_duo_kernel: two pairs per CTA + solver warp
-      case 31: return {544, 2, 2, 5, 1088};  // icp_joint_kernel: two pairs per CTA, shared barriers
-      default: return {288, 4, 4, 3, 1152};  // measured best on B200 (profiles/r01_variant_sweep.md)
-    }
-  }
-  if (max_points <= 1536) return {256, 6, 2, 0};
-  if (max_points <= 2048) return {256, 8, 2, 0};
-  if (max_points <= 4096) return {512, 8, 1, 0};
-  if (max_points <= 65535) return {512, 0, 2, 1};  // streaming kernel, any size the shared-memory stash can hold
-  return {0, 0, 0, 0};
-}
-
-template <int T, int PPT, bool SENSOR, int MINB>
-int launch_icp_k(ls2d_handle* h, const align_args& a) {
-  const size_t smem = icp_smem_bytes(h->dp.cam.cols, T, PPT);
-  auto kern         = icp_fused_kernel<T, PPT, SENSOR, MINB>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  // the kernel keeps its working set in shared memory and registers; give it the whole carve-out
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
-}
-
-template <int T, int PPT, bool SENSOR, int MINB, int CS, bool FUSED = true>
-int launch_icp2_k(ls2d_handle* h, const align_args& a) {
-  constexpr size_t smem = icp2_map<T, PPT, CS>::BYTES;
-  auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, CS, FUSED>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
-}
-
-template <int TC, bool SENSOR, int CS>
-int launch_duo_k(ls2d_handle* h, const align_args& a) {
-  constexpr size_t smem = duo_map<TC, CS>::BYTES;
-  auto kern             = icp_duo_kernel<TC, SENSOR, CS>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<(a.n_pairs + 1) / 2, TC + 32, smem, h->stream>>>(h->dp, a);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
-}
-
-template <int TC, bool SENSOR, int CS>
-int launch_joint_k(ls2d_handle* h, const align_args& a) {
-  constexpr size_t smem = duo_map<TC, CS>::BYTES;
-  auto kern             = icp_joint_kernel<TC, SENSOR, CS>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<(a.n_pairs + 1) / 2, TC, smem, h->stream>>>(h->dp, a);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
-}
-
-template <int T, int PPT, int MINB>
-int launch_icp_t(ls2d_handle* h, const align_args& a) {
-  return h->dp.with_sensor ? launch_icp_k<T, PPT, true, MINB>(h, a) : launch_icp_k<T, PPT, false, MINB>(h, a);
-}
-
-template <int T, bool SENSOR, bool MP_SMEM, int MINB>
-int launch_stream_k(ls2d_handle* h, const align_args& a, int maxp) {
-  const size_t smem = icp_stream_smem_bytes(h->dp.cam.cols, T, maxp, MP_SMEM);
-  if (smem > 227 * 1024) return LS2D_ERR_UNSUPPORTED;
-  auto kern = icp_stream_kernel<T, SENSOR, MP_SMEM, MINB>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a, maxp);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
-}
-
-template <int T, bool MP_SMEM, int MINB>
-int launch_stream_t(ls2d_handle* h, const align_args& a, int maxp) {
-  return h->dp.with_sensor ? launch_stream_k<T, true, MP_SMEM, MINB>(h, a, maxp)
-                           : launch_stream_k<T, false, MP_SMEM, MINB>(h, a, maxp);
-}
-
-int launch_icp(ls2d_handle* h, const align_args& a) {
-  if (a.n_pairs <= 0) return LS2D_OK;
-  const int maxp = h->sets[0].max_points > h->sets[1].max_points ? h->sets[0].max_points
-                                                                  : h->sets[1].max_points;
-  shape s = pick_shape(maxp, h->variant);
-  if (s.kind == 3 && h->dp.cam.cols >= s.cs) {  // wider canvases: the run-time-stride kernel
-    s.kind = 0;
-    if (s.threads == 192 && s.ppt == 4) s = {256, 3, 3, 0, 0};
-    if (s.threads == 256 && s.ppt == 3) s.minb = 3;
-  }
-  if (s.kind >= 4 && h->dp.cam.cols >= s.cs) s = {288, 4, 4, 0, 0};
-  if (s.kind == 5) return h->dp.with_sensor ? launch_joint_k<544, true, 1088>(h, a) : launch_joint_k<544, false, 1088>(h, a);
-  if (s.kind == 4) return h->dp.with_sensor ? launch_duo_k<544, true, 1088>(h, a) : launch_duo_k<544, false, 1088>(h, a);
-  if (s.kind == 3 && unfused_requested() && s.threads == 288 && s.ppt == 4 && s.minb == 4 && !h->dp.with_sensor)
-    return launch_icp2_k<288, 4, false, 4, 1152, false>(h, a);  // A/B: single-rounding accumulation arithmetic
-#define LS2D_CASE2(T, P, B, CS)                                                        \
-  if (s.kind == 3 && s.threads == T && s.ppt == P && s.minb == B && s.cs == CS)         \
-    return h->dp.with_sensor ? launch_icp2_k<T, P, true, B, CS, (CS == 1152)>(h, a)     \
-                             : launch_icp2_k<T, P, false, B, CS, (CS == 1152)>(h, a);
-  LS2D_CASE2(384, 3, 3, 1152)
-  LS2D_CASE2(288, 4, 4, 1152)
-  LS2D_CASE2(256, 5, 4, 1152)
-  LS2D_CASE2(192, 6, 5, 1152)
-  LS2D_CASE2(192, 4, 5, 768)
-  LS2D_CASE2(256, 3, 4, 768)
-  LS2D_CASE2(256, 3, 5, 768)
-#undef LS2D_CASE2
-  if (s.kind == 1 && s.threads == 512) return launch_stream_t<512, false, 2>(h, a, maxp);
-  if (s.kind == 1 && s.threads == 384) return launch_stream_t<384, false, 4>(h, a, maxp);
-  if (s.kind == 2 && s.threads == 384) return launch_stream_t<384, true, 4>(h, a, maxp);
-  if (s.kind == 2 && s.threads == 256) return launch_stream_t<256, true, 6>(h, a, maxp);
-  if (s.kind == 2 && s.threads == 512) return launch_stream_t<512, true, 3>(h, a, maxp);
-#define LS2D_CASE(T, P, B) \
-  if (s.kind == 0 && s.threads == T && s.ppt == P && s.minb == B) return launch_icp_t<T, P, B>(h, a);
-  LS2D_CASE(128, 2, 6)
-  LS2D_CASE(128, 4, 6)
-  LS2D_CASE(256, 3, 3)
-  LS2D_CASE(192, 6, 4)
-  LS2D_CASE(128, 9, 4)
-  LS2D_CASE(384, 3, 2)
-  LS2D_CASE(256, 5, 3)
-  LS2D_CASE(192, 6, 5)
-  LS2D_CASE(256, 5, 4)
-  LS2D_CASE(384, 3, 3)
-  LS2D_CASE(288, 4, 4)
-  LS2D_CASE(288, 4, 3)
-  LS2D_CASE(128, 9, 5)
-  LS2D_CASE(256, 6, 2)
-  LS2D_CASE(256, 8, 2)
-  LS2D_CASE(512, 8, 1)
-#undef LS2D_CASE
-  return LS2D_ERR_UNSUPPORTED;
-}
+// iteration records one alignment may write (include/ls2d.h: iter_stats)
+int iters_per_pair(const ls2d_params& p) { return p.max_iterations * (p.enable_inlier_only_runs ? 2 : 1); }
 
 // device copy of the projector's rounding edges (second tier of the column decision, ls2d_math.cuh)
 int upload_edges(ls2d_handle* h) {
@@ -363,6 +161,8 @@ int h2d(ls2d_handle* h, scratch& s, const void* src, size_t bytes) {
 align_args base_args(const ls2d_handle* h) {
   align_args a;
   memset(&a, 0, sizeof(a));
+  a.pose_stride  = pose_stride(h);
+  a.iters_stride = iters_per_pair(h->prm);
   a.fixed_pts   = h->sets[0].pts;
   a.fixed_off   = h->sets[0].off;
   a.moving_pts  = h->sets[1].pts;
@@ -406,6 +206,14 @@ void ls2d_default_params(ls2d_params* p) {
   p->min_num_correspondences = 0;
   p->min_num_inliers         = 10;
   p->with_sensor             = 0;
+  p->factor                  = LS2D_FACTOR_PLANE2PLANE;
+  p->algorithm               = LS2D_ALGORITHM_GN;
+  p->lm_user_lambda_init     = 0.f;
+  p->lm_tau                  = 1e-5f;
+  p->lm_step_low             = 1.f / 3.f;
+  p->lm_step_high            = 2.f / 3.f;
+  p->lm_iterations_max       = 10;
+  p->lm_variable_damping     = 1;
 }
 
 int ls2d_create(ls2d_handle** out, int device) {
@@ -430,7 +238,7 @@ int ls2d_create(ls2d_handle** out, int device) {
     delete h;
     return LS2D_ERR_CUDA;
   }
-  if (const char* v = getenv("LS2D_ICP_VARIANT")) h->variant = atoi(v);
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = h;
   return LS2D_OK;
 }
@@ -452,6 +260,7 @@ int ls2d_destroy(ls2d_handle* h) {
   release(h->d_clip);
   release(h->d_edge);
   for (scratch& e : h->d_edge_slice) release(e);
+  if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   for (cudaEvent_t e : h->ev_chunk)
@@ -488,6 +297,14 @@ int ls2d_get_params(const ls2d_handle* h, ls2d_params* p) {
   *p = h->prm;
   return LS2D_OK;
 }
+
+int ls2d_set_pose_format(ls2d_handle* h, int format) {
+  if (!h || (format != LS2D_POSE_XYT && format != LS2D_POSE_ISO)) return LS2D_ERR_INVALID;
+  h->pose_format = format;
+  return LS2D_OK;
+}
+
+int ls2d_get_pose_format(const ls2d_handle* h) { return h ? h->pose_format : LS2D_ERR_INVALID; }
 
 int ls2d_upload_clouds(ls2d_handle* h, int which, const float* pts, const int32_t* off, int32_t n_clouds) {
   if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !off || n_clouds < 0 || (!pts && n_clouds > 0 && off[n_clouds] > 0))
@@ -549,12 +366,12 @@ static int align_dev_impl(ls2d_handle* h, const int32_t* fid, const int32_t* mid
   align_args a = base_args(h);
   a.fixed_id   = fid;
   a.moving_id  = mid;
-  a.init_xyt   = init;
+  a.init_pose  = init;
   a.out        = out;
   a.iters      = iters;
   a.n_pairs    = n_pairs;
   a.score_only = score_only;
-  return launch_icp(h, a);
+  return score_only ? launch_score(h, a) : launch_icp(h, a);
 }
 
 static int check_ids(const ls2d_handle* h, const int32_t* fid, const int32_t* mid, int32_t n) {
@@ -575,9 +392,9 @@ static int align_host_impl(ls2d_handle* h, const int32_t* fid, const int32_t* mi
   CU(cudaSetDevice(h->device));
   if (fid && (rc = h2d(h, h->d_fid, fid, sizeof(int) * (size_t) n_pairs))) return rc;
   if (mid && (rc = h2d(h, h->d_mid, mid, sizeof(int) * (size_t) n_pairs))) return rc;
-  if ((rc = h2d(h, h->d_init, init, sizeof(float) * 3 * (size_t) n_pairs))) return rc;
+  if ((rc = h2d(h, h->d_init, init, sizeof(float) * pose_stride(h) * (size_t) n_pairs))) return rc;
   if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) n_pairs))) return rc;
-  const size_t iter_bytes = sizeof(ls2d_iter_stats) * (size_t) n_pairs * (size_t) h->prm.max_iterations;
+  const size_t iter_bytes = sizeof(ls2d_iter_stats) * (size_t) n_pairs * (size_t) iters_per_pair(h->prm);
   if (iters && iter_bytes) {
     if ((rc = reserve(h->d_iters, iter_bytes))) return rc;
     CU(cudaMemsetAsync(h->d_iters.p, 0, iter_bytes, h->stream));
@@ -655,7 +472,7 @@ int ls2d_align_pairs_host(ls2d_handle* h, const float* fpts, const int32_t* foff
   if ((rc = reserve_set(M, (size_t) moff[n_pairs], (size_t) n_pairs + 1))) return rc;
   F.n_clouds = M.n_clouds = n_pairs;
   F.max_points = maxf, M.max_points = maxm;
-  if ((rc = reserve(h->d_init, sizeof(float) * 3 * (size_t) n_pairs))) return rc;
+  if ((rc = reserve(h->d_init, sizeof(float) * pose_stride(h) * (size_t) n_pairs))) return rc;
   if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) n_pairs))) return rc;
   if (!h->copy_stream) {
     CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -667,7 +484,7 @@ int ls2d_align_pairs_host(ls2d_handle* h, const float* fpts, const int32_t* foff
   CU(cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
   CU(cudaMemcpyAsync(F.off, foff, sizeof(int) * ((size_t) n_pairs + 1), cudaMemcpyHostToDevice, h->copy_stream));
   CU(cudaMemcpyAsync(M.off, moff, sizeof(int) * ((size_t) n_pairs + 1), cudaMemcpyHostToDevice, h->copy_stream));
-  CU(cudaMemcpyAsync(h->d_init.p, init, sizeof(float) * 3 * (size_t) n_pairs, cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaMemcpyAsync(h->d_init.p, init, sizeof(float) * pose_stride(h) * (size_t) n_pairs, cudaMemcpyHostToDevice, h->copy_stream));
   int n_chunks = n_pairs / 512;  // a chunk's upload (~0.3 ms) is far longer than its kernel: the more chunks, the
                                  // shorter the tail left after the last upload (~one wave of 4 CTAs x 148 SMs)
   n_chunks     = n_chunks < 1 ? 1 : (n_chunks > 8 ? 8 : n_chunks);
@@ -679,7 +496,7 @@ int ls2d_align_pairs_host(ls2d_handle* h, const float* fpts, const int32_t* foff
     CU(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
     CU(cudaStreamWaitEvent(h->stream, h->ev_chunk[k], 0));
     align_args a = base_args(h);
-    a.init_xyt   = (const float*) h->d_init.p;
+    a.init_pose  = (const float*) h->d_init.p;
     a.out        = (ls2d_result*) h->d_out.p;
     a.n_pairs    = p1 - p0;
     a.pair_base  = p0;
@@ -720,11 +537,12 @@ static int multi_dev_impl(ls2d_handle* h, const ls2d_params* slices, const int32
     if (m.max_points > a.max_points) a.max_points = m.max_points;
   }
   if (a.max_cols > 0xFFFE) return LS2D_ERR_UNSUPPORTED;
-  a.n_slices   = n_slices;
-  a.fixed_id   = fid;
-  a.moving_id  = mid;
-  a.init_xyt   = init;
-  a.prior_z    = prior_z;
+  a.n_slices    = n_slices;
+  a.fixed_id    = fid;
+  a.moving_id   = mid;
+  a.init_pose   = init;
+  a.pose_stride = pose_stride(h);
+  a.prior_z     = prior_z;
   if (prior) {
     memcpy(a.prior_info, prior->information, sizeof(float) * 6);
     a.prior_tau     = prior->cauchy_chi_threshold;
@@ -735,17 +553,11 @@ static int multi_dev_impl(ls2d_handle* h, const ls2d_params* slices, const int32
   a.n_pairs    = n_pairs;
   a.score_only = 0;
   if (n_pairs == 0) return LS2D_OK;
+  for (int s = 0; s < n_slices; ++s)  // the multi-slice kernels run Gauss-Newton rounds only
+    if (slices[s].algorithm != LS2D_ALGORITHM_GN || slices[s].enable_inlier_only_runs || slices[s].termination_epsilon > 0.f)
+      return LS2D_ERR_UNSUPPORTED;
   CU(cudaSetDevice(h->device));
-  constexpr int T   = MULTI_THREADS;  // 4 CTAs of 8 warps per SM measured best (512 x 2: +28 % time, 384 x 3: +16 %)
-  const size_t smem = multi_smem_bytes(cols, n_slices, a.max_cols, a.max_points, T);
-  if (smem > 227 * 1024) return LS2D_ERR_UNSUPPORTED;
-  auto kern = icp_multi_kernel<T, 4>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  kern<<<n_pairs, T, smem, h->stream>>>(a);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
+  return launch_multi(h, a, cols);
 }
 
 int ls2d_align_multi_dev(ls2d_handle* h, const ls2d_params* slices, const int32_t* fset, const int32_t* mset,
@@ -774,8 +586,8 @@ int ls2d_align_multi(ls2d_handle* h, const ls2d_params* slices, const int32_t* f
   int rc;
   if (fid && (rc = h2d(h, h->d_fid, fid, sizeof(int) * (size_t) n_pairs))) return rc;
   if (mid && (rc = h2d(h, h->d_mid, mid, sizeof(int) * (size_t) n_pairs))) return rc;
-  if ((rc = h2d(h, h->d_init, init, sizeof(float) * 3 * (size_t) n_pairs))) return rc;
-  if (prior_z && (rc = h2d(h, h->d_prior, prior_z, sizeof(float) * 3 * (size_t) n_pairs))) return rc;
+  if ((rc = h2d(h, h->d_init, init, sizeof(float) * pose_stride(h) * (size_t) n_pairs))) return rc;
+  if (prior_z && (rc = h2d(h, h->d_prior, prior_z, sizeof(float) * pose_stride(h) * (size_t) n_pairs))) return rc;
   if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) n_pairs))) return rc;
   const size_t iter_bytes = sizeof(ls2d_iter_stats) * (size_t) n_pairs * (size_t) slices[0].max_iterations;
   if (iters && iter_bytes) {
@@ -819,15 +631,13 @@ int ls2d_find_correspondences_in(ls2d_handle* h, int32_t fixed_set, int32_t movi
   a.moving_off   = ms.off;
   a.fixed_cloud  = fixed_id;
   a.moving_cloud = moving_id;
-  memcpy(a.lmis_xyt, xyt, sizeof(float) * 3);
+  a.pose_stride = pose_stride(h);
+  memset(a.lmis_pose, 0, sizeof(a.lmis_pose));
+  memcpy(a.lmis_pose, xyt, sizeof(float) * a.pose_stride);
   a.fixed_idx  = (int*) h->d_misc.p;
   a.moving_idx = a.fixed_idx + C;
   a.count      = a.moving_idx + C;
-  const size_t smem = sizeof(unsigned) * 4 * (size_t) C;
-  CU(cudaFuncSetAttribute(correspond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  correspond_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
-  CU(cudaGetLastError());
-  h->launches++;
+  if ((rc = launch_correspond(h, a))) return rc;
   int n = 0;
   CU(cudaMemcpyAsync(&n, a.count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -838,6 +648,41 @@ int ls2d_find_correspondences_in(ls2d_handle* h, int32_t fixed_set, int32_t movi
     CU(cudaStreamSynchronize(h->stream));
   }
   *n_out = n;
+  return LS2D_OK;
+}
+
+int ls2d_classify_correspondences(ls2d_handle* h, int32_t fixed_set, int32_t moving_set, int32_t fixed_id,
+                                  int32_t moving_id, const float* X_pose, const int32_t* fixed_idx,
+                                  const int32_t* moving_idx, int32_t n, uint8_t* is_inlier) {
+  if (!h || !X_pose || n < 0 || (n > 0 && (!fixed_idx || !moving_idx || !is_inlier))) return LS2D_ERR_INVALID;
+  if (fixed_set < 0 || fixed_set >= LS2D_MAX_CLOUD_SETS || moving_set < 0 || moving_set >= LS2D_MAX_CLOUD_SETS)
+    return LS2D_ERR_INVALID;
+  const cloud_set& fs = h->sets[fixed_set];
+  const cloud_set& ms = h->sets[moving_set];
+  if (!fs.pts || !fs.off || !ms.pts || !ms.off) return LS2D_ERR_NOT_READY;
+  if (fixed_id < 0 || fixed_id >= fs.n_clouds || moving_id < 0 || moving_id >= ms.n_clouds) return LS2D_ERR_INVALID;
+  if (n == 0) return LS2D_OK;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = reserve(h->d_misc, (sizeof(int) * 2 + 1) * (size_t) n + 16))) return rc;
+  int* d_fi          = (int*) h->d_misc.p;
+  int* d_mi          = d_fi + n;
+  unsigned char* d_o = (unsigned char*) (d_mi + n);
+  CU(cudaMemcpyAsync(d_fi, fixed_idx, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(d_mi, moving_idx, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, h->stream));
+  classify_args a;
+  memset(&a, 0, sizeof(a));
+  a.fixed_pts   = fs.pts;
+  a.moving_pts  = ms.pts;
+  a.pose_stride = pose_stride(h);
+  memcpy(a.X_pose, X_pose, sizeof(float) * a.pose_stride);
+  a.fixed_idx  = d_fi;
+  a.moving_idx = d_mi;
+  a.n          = n;
+  a.is_inlier  = d_o;
+  if ((rc = launch_classify(h, a, fs.off, fixed_id, ms.off, moving_id))) return rc;
+  CU(cudaMemcpyAsync(is_inlier, d_o, (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return LS2D_OK;
 }
 
@@ -855,14 +700,12 @@ int ls2d_project(ls2d_handle* h, int which, int32_t cloud_id, const float* cam_x
   a.pts   = c.pts;
   a.off   = c.off;
   a.cloud = cloud_id;
-  memcpy(a.cam_xyt, cam_xyt, sizeof(float) * 3);
+  a.pose_stride = pose_stride(h);
+  memset(a.cam_pose, 0, sizeof(a.cam_pose));
+  memcpy(a.cam_pose, cam_xyt, sizeof(float) * a.pose_stride);
   a.source_idx = (int*) h->d_misc.p;
   a.depth      = (float*) (a.source_idx + C);
-  const size_t smem = sizeof(unsigned) * 2 * (size_t) C;
-  CU(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  project_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
-  CU(cudaGetLastError());
-  h->launches++;
+  if ((rc = launch_project(h, a))) return rc;
   CU(cudaMemcpyAsync(source_idx, a.source_idx, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(depth, a.depth, sizeof(float) * C, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -887,14 +730,11 @@ int ls2d_verify_dev(ls2d_handle* h, int32_t query_id, const int32_t* cand_dev, i
   a.fixed_const = query_id;
   a.moving_id   = cand_dev;
   a.moving_div  = n_guess;
-  a.init_xyt    = guesses_dev;
+  a.init_pose   = guesses_dev;
   a.out         = all_dev;
   a.n_pairs     = n;
   if ((rc = launch_icp(h, a))) return rc;
-  best_of_kernel<<<1, 1024, 0, h->stream>>>(all_dev, n, n_guess, *gates, cand_base, best_dev);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
+  return launch_best_of(h, all_dev, n, n_guess, *gates, cand_base, best_dev);
 }
 
 int ls2d_verify(ls2d_handle* h, int32_t query_id, const int32_t* cand, int32_t n_cand, const float* guesses,
@@ -911,7 +751,7 @@ int ls2d_verify(ls2d_handle* h, int32_t query_id, const int32_t* cand, int32_t n
   const size_t n = (size_t) n_cand * n_guess;
   int rc;
   if (cand && n_cand && (rc = h2d(h, h->d_mid, cand, sizeof(int) * (size_t) n_cand))) return rc;
-  if ((rc = h2d(h, h->d_init, guesses, sizeof(float) * 3 * (n ? n : 1)))) return rc;
+  if ((rc = h2d(h, h->d_init, guesses, sizeof(float) * pose_stride(h) * (n ? n : 1)))) return rc;
   if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (n ? n : 1)))) return rc;
   if ((rc = reserve(h->d_best, sizeof(ls2d_best)))) return rc;
   rc = ls2d_verify_dev(h, query_id, cand ? (const int*) h->d_mid.p : nullptr, n_cand, (const float*) h->d_init.p,
@@ -937,16 +777,11 @@ int ls2d_verify_pairs_dev(ls2d_handle* h, const int32_t* fid_dev, const int32_t*
   align_args a = base_args(h);
   a.fixed_id   = fid_dev;
   a.moving_id  = mid_dev;
-  a.init_xyt   = guesses_dev;
+  a.init_pose  = guesses_dev;
   a.out        = all_dev;
   a.n_pairs    = n_pairs;
   if ((rc = launch_icp(h, a))) return rc;
-  if (n_groups > 0) {
-    best_of_groups_kernel<<<(n_groups + 7) / 8, 256, 0, h->stream>>>(all_dev, group_off_dev, n_groups, mid_dev, *gates, best_dev);
-    CU(cudaGetLastError());
-    h->launches++;
-  }
-  return LS2D_OK;
+  return launch_best_of_groups(h, all_dev, group_off_dev, n_groups, mid_dev, *gates, best_dev);
 }
 
 int ls2d_verify_pairs(ls2d_handle* h, const int32_t* fid, const int32_t* mid, const float* guesses, int32_t n_pairs,
@@ -964,7 +799,7 @@ int ls2d_verify_pairs(ls2d_handle* h, const int32_t* fid, const int32_t* mid, co
   const size_t n = (size_t) n_pairs;
   if (fid && n && (rc = h2d(h, h->d_fid, fid, sizeof(int) * n))) return rc;
   if (mid && n && (rc = h2d(h, h->d_mid, mid, sizeof(int) * n))) return rc;
-  if ((rc = h2d(h, h->d_init, guesses, sizeof(float) * 3 * (n ? n : 1)))) return rc;
+  if ((rc = h2d(h, h->d_init, guesses, sizeof(float) * pose_stride(h) * (n ? n : 1)))) return rc;
   if ((rc = h2d(h, h->d_misc, group_off, sizeof(int) * ((size_t) n_groups + 1)))) return rc;
   if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (n ? n : 1)))) return rc;
   if ((rc = reserve(h->d_best, sizeof(ls2d_best) * (size_t) n_groups))) return rc;
@@ -1011,59 +846,38 @@ int ls2d_verify_sharded_nccl(ls2d_handle* h, int32_t query_id, const int32_t* ca
                              const float* guesses_dev, int32_t n_guess, const ls2d_gates* gates,
                              int32_t cand_base, void* comm, int32_t n_ranks, ls2d_best* best) {
   if (!h || !comm || !best || n_ranks < 1) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));  // before any allocation: the gather buffer must live on the handle's device
   if (!h->nccl_all_gather) {
-    h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h->nccl_lib) h->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!h->nccl_lib) return LS2D_ERR_NCCL;
-    h->nccl_all_gather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t)) dlsym(h->nccl_lib, "ncclAllGather");
-    if (!h->nccl_all_gather) return LS2D_ERR_NCCL;
+    // the NCCL the process already runs (torch bundles its own) before any system copy: a communicator only makes
+    // sense to the library that created it
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+    void* cnt = dlsym(RTLD_DEFAULT, "ncclCommCount");
+    if (!sym || !cnt) {
+      h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (!h->nccl_lib) h->nccl_lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+      if (!h->nccl_lib) return LS2D_ERR_NCCL;
+      sym = dlsym(h->nccl_lib, "ncclAllGather");
+      cnt = dlsym(h->nccl_lib, "ncclCommCount");
+    }
+    if (!sym || !cnt) return LS2D_ERR_NCCL;
+    h->nccl_all_gather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t)) sym;
+    h->nccl_comm_count = (int (*)(void*, int*)) cnt;
   }
+  int comm_size = 0;
+  if (h->nccl_comm_count(comm, &comm_size) != 0) return LS2D_ERR_NCCL;
+  if (comm_size != n_ranks) return LS2D_ERR_INVALID;  // the all-gather writes comm_size records
   int rc;
   if ((rc = reserve(h->d_best, sizeof(ls2d_best) * (size_t) (n_ranks + 1)))) return rc;
   ls2d_best* mine   = (ls2d_best*) h->d_best.p;
   ls2d_best* gather = mine + 1;
   if ((rc = ls2d_verify_dev(h, query_id, cand_dev, n_cand, guesses_dev, n_guess, gates, cand_base, mine, nullptr)))
     return rc;
-  if (h->nccl_all_gather(mine, gather, sizeof(ls2d_best), /*ncclInt8*/ 0, comm, h->stream) != 0) return LS2D_ERR_NCCL;
+  constexpr int kNcclInt8 = 0;  // ncclDataType_t::ncclInt8 (nccl.h); the records travel as bytes
+  if (h->nccl_all_gather(mine, gather, sizeof(ls2d_best), kNcclInt8, comm, h->stream) != 0) return LS2D_ERR_NCCL;
   std::vector<ls2d_best> host((size_t) n_ranks);
   CU(cudaMemcpyAsync(host.data(), gather, sizeof(ls2d_best) * (size_t) n_ranks, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return ls2d_reduce_best(host.data(), n_ranks, best);
-}
-
-int ls2d_clip_scenes(ls2d_handle* h, int which, const int32_t* cloud_ids, const float* robot_xyt,
-                     const float* sensor_xyt, int32_t n, float* out_points, int32_t* out_counts) {
-  if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !cloud_ids || !robot_xyt || !sensor_xyt || !out_points || !out_counts || n < 0)
-    return LS2D_ERR_INVALID;
-  const cloud_set& c = h->sets[which];
-  if (!c.pts || !c.off) return LS2D_ERR_NOT_READY;
-  if (n == 0) return LS2D_OK;
-  for (int i = 0; i < n; ++i)
-    if (cloud_ids[i] < 0 || cloud_ids[i] >= c.n_clouds) return LS2D_ERR_INVALID;
-  CU(cudaSetDevice(h->device));
-  const int C = h->dp.cam.cols;
-  int rc;
-  if ((rc = h2d(h, h->d_mid, cloud_ids, sizeof(int) * (size_t) n))) return rc;
-  if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * 3 * (size_t) n))) return rc;
-  const size_t out_bytes = sizeof(float4) * (size_t) n * C;
-  if ((rc = reserve(h->d_misc, out_bytes + sizeof(int) * (size_t) n))) return rc;
-  clip_args a;
-  a.pts       = c.pts;
-  a.off       = c.off;
-  a.cloud_ids = (const int*) h->d_mid.p;
-  a.robot_xyt = (const float*) h->d_init.p;
-  memcpy(a.sensor_xyt, sensor_xyt, sizeof(float) * 3);
-  a.out    = (float4*) h->d_misc.p;
-  a.counts = (int*) ((char*) h->d_misc.p + out_bytes);
-  const size_t smem = sizeof(unsigned) * 2 * (size_t) C;
-  CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  clip_kernel<<<n, 256, smem, h->stream>>>(h->dp, a);
-  CU(cudaGetLastError());
-  h->launches++;
-  CU(cudaMemcpyAsync(out_points, a.out, out_bytes, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaMemcpyAsync(out_counts, a.counts, sizeof(int) * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
-  return LS2D_OK;
 }
 
 int ls2d_merge_scene_dev(ls2d_handle* h, void* scene_dev, int32_t* scene_size_dev, int32_t capacity,
@@ -1078,15 +892,12 @@ int ls2d_merge_scene_dev(ls2d_handle* h, void* scene_dev, int32_t* scene_size_de
   a.capacity   = capacity;
   a.meas       = (const float4*) meas_dev;
   a.n_meas     = n_meas;
-  memcpy(a.mis_xyt, mis_xyt, sizeof(float) * 3);
+  a.pose_stride = pose_stride(h);
+  memset(a.mis_pose, 0, sizeof(a.mis_pose));
+  memcpy(a.mis_pose, mis_xyt, sizeof(float) * a.pose_stride);
   a.merge_threshold = merge_threshold;
   a.counters        = counters_dev;
-  const size_t smem = sizeof(unsigned) * 4 * (size_t) h->dp.cam.cols;
-  CU(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  merge_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
+  return launch_merge(h, a);
 }
 
 int ls2d_merge_scene(ls2d_handle* h, float* scene, int32_t* scene_size, int32_t capacity, const float* meas,
@@ -1159,13 +970,7 @@ static int preprocess_dev(ls2d_handle* h, const ls2d_scan_params* sp, const floa
   a.out     = out_dev;
   a.counts  = counts_dev;
   a.n_scans = n_scans;
-  const size_t smem = scan_smem_bytes(n_beams, P.sort_cap);
-  if (smem > 227 * 1024) return LS2D_ERR_UNSUPPORTED;
-  CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  preprocess_kernel<<<n_scans, SCAN_T, smem, h->stream>>>(P, a);
-  CU(cudaGetLastError());
-  h->launches++;
-  return LS2D_OK;
+  return launch_preprocess(h, P, a, n_scans);
 }
 
 int ls2d_preprocess_scans(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges, int32_t n_beams,
@@ -1210,11 +1015,7 @@ static int pack_into_set(ls2d_handle* h, int which, const float4* d_strided, con
     c.cap_off = n_off + 16;
   }
   if (n > 0) {
-    scan_offsets_kernel<<<1, 1024, 0, h->stream>>>(d_cnt, n, c.off);
-    CU(cudaGetLastError());
-    scan_pack_kernel<<<n, 128, 0, h->stream>>>(d_strided, c.off, stride, c.pts);
-    CU(cudaGetLastError());
-    h->launches += 2;
+    if (int rc = launch_scan_pack(h, d_strided, d_cnt, stride, n, c.off, c.pts)) return rc;
   } else {
     CU(cudaMemsetAsync(c.off, 0, sizeof(int), h->stream));
   }
@@ -1282,24 +1083,20 @@ static int clip_dev(ls2d_handle* h, const cloud_set& c, const int* ids_dev, cons
   a.pts       = c.pts;
   a.off       = c.off;
   a.cloud_ids = ids_dev;
-  a.robot_xyt = robot_dev;
-  memcpy(a.sensor_xyt, sensor_xyt, sizeof(float) * 3);
+  a.robot_pose  = robot_dev;
+  a.pose_stride = pose_stride(h);
+  memset(a.sensor_pose, 0, sizeof(a.sensor_pose));
+  memcpy(a.sensor_pose, sensor_xyt, sizeof(float) * a.pose_stride);
   a.out    = (float4*) tmp.p;
   a.counts = (int*) ((char*) tmp.p + out_bytes);
   if (voxelize_resolution > 0.f) {  // scene_clipper_projective_2d.cpp:36-48
     const float inv_res = 1.f / voxelize_resolution;
     // the packed voxel key holds |coordinate / res| < 2^19 (coordinates are bounded by the range limit)
-    if (!(h->dp.range_max * inv_res < 524288.f) || C > 32 * SCAN_T) return LS2D_ERR_UNSUPPORTED;
-    const size_t smem = clip_voxel_smem_bytes(C);
-    CU(cudaFuncSetAttribute(clip_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    clip_voxel_kernel<<<n, SCAN_T, smem, h->stream>>>(h->dp, a, inv_res);
+    if (!(h->dp.range_max * inv_res < 524288.f)) return LS2D_ERR_UNSUPPORTED;
+    if ((rc = launch_clip_voxel(h, a, n, inv_res))) return rc;
   } else {
-    const size_t smem = sizeof(unsigned) * 2 * (size_t) C;
-    CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    clip_kernel<<<n, 256, smem, h->stream>>>(h->dp, a);
+    if ((rc = launch_clip(h, a, n))) return rc;
   }
-  CU(cudaGetLastError());
-  h->launches++;
   *out    = a.out;
   *counts = a.counts;
   return LS2D_OK;
@@ -1318,7 +1115,7 @@ int ls2d_clip_scenes_voxelized(ls2d_handle* h, int which, const int32_t* cloud_i
   CU(cudaSetDevice(h->device));
   int rc;
   if ((rc = h2d(h, h->d_mid, cloud_ids, sizeof(int) * (size_t) n))) return rc;
-  if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * 3 * (size_t) n))) return rc;
+  if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * pose_stride(h) * (size_t) n))) return rc;
   float4* d_out = nullptr;
   int* d_cnt    = nullptr;
   if ((rc = clip_dev(h, c, (const int*) h->d_mid.p, (const float*) h->d_init.p, sensor_xyt, n, h->d_clip, &d_out, &d_cnt,
@@ -1328,6 +1125,11 @@ int ls2d_clip_scenes_voxelized(ls2d_handle* h, int which, const int32_t* cloud_i
   CU(cudaMemcpyAsync(out_counts, d_cnt, sizeof(int) * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return LS2D_OK;
+}
+
+int ls2d_clip_scenes(ls2d_handle* h, int which, const int32_t* cloud_ids, const float* robot_pose,
+                     const float* sensor_pose, int32_t n, float* out_points, int32_t* out_counts) {
+  return ls2d_clip_scenes_voxelized(h, which, cloud_ids, robot_pose, sensor_pose, n, 0.f, out_points, out_counts);
 }
 
 int ls2d_clip_scenes_to_set(ls2d_handle* h, int scene_set, const int32_t* cloud_ids, const float* robot_xyt,
@@ -1345,7 +1147,7 @@ int ls2d_clip_scenes_to_set(ls2d_handle* h, int scene_set, const int32_t* cloud_
   int* d_cnt    = nullptr;
   if (n > 0) {
     if ((rc = h2d(h, h->d_mid, cloud_ids, sizeof(int) * (size_t) n))) return rc;
-    if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * 3 * (size_t) n))) return rc;
+    if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * pose_stride(h) * (size_t) n))) return rc;
     if ((rc = clip_dev(h, c, (const int*) h->d_mid.p, (const float*) h->d_init.p, sensor_xyt, n, h->d_clip, &d_out, &d_cnt)))
       return rc;
   }
@@ -1362,35 +1164,28 @@ int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ra
     return LS2D_ERR_INVALID;
   if (n == 0) return LS2D_OK;
   int rc;
-  const float identity[3] = {0.f, 0.f, 0.f};
-  const float* sensor     = h->prm.with_sensor ? h->prm.sensor_in_robot : identity;
+  // sensor_in_robot in the handle's pose format (the parameter record may hold either form)
+  const int stride = pose_stride(h);
+  const iso S      = h->prm.with_sensor ? sensor_iso(h->prm) : iso_identity();
+  float sensor[4]  = {S.tx, S.ty, S.c, S.s};
+  if (stride == 3) {
+    if (h->prm.with_sensor == 2) return LS2D_ERR_INVALID;  // an isometry cannot be handed on as (x, y, theta) bit for bit
+    sensor[2] = h->prm.with_sensor ? h->prm.sensor_in_robot[2] : 0.f;
+  }
   if ((rc = ls2d_preprocess_scans_to_set(h, LS2D_FIXED, sp, ranges, n_beams, n))) return rc;
   if ((rc = ls2d_clip_scenes_to_set(h, scene_set, scene_ids, robot_xyt, sensor, n, LS2D_MOVING))) return rc;
   if (init_xyt) return align_host_impl(h, nullptr, nullptr, init_xyt, n, out, nullptr, 0);
-  std::vector<float> zeros((size_t) n * 3, 0.f);
-  return align_host_impl(h, nullptr, nullptr, zeros.data(), n, out, nullptr, 0);
+  std::vector<float> ident((size_t) n * stride, 0.f);
+  if (stride == 4)
+    for (int i = 0; i < n; ++i) ident[(size_t) i * 4 + 2] = 1.f;
+  return align_host_impl(h, nullptr, nullptr, ident.data(), n, out, nullptr, 0);
 }
 
-int ls2d_multi_reduction_threads(void) { return MULTI_THREADS; }
+int ls2d_multi_reduction_threads(void) { return multi_reduction_threads(); }
 
-int ls2d_reduction_threads(int32_t max_points) {
-  int variant = 0;
-  if (const char* v = getenv("LS2D_ICP_VARIANT")) variant = atoi(v);
-  return pick_shape(max_points, variant).threads;
-}
-
-int ls2d_reduction_shape(int32_t max_points, int32_t canvas_cols) {
-  int variant = 0;
-  if (const char* v = getenv("LS2D_ICP_VARIANT")) variant = atoi(v);
-  shape s = pick_shape(max_points, variant);
-  if (s.kind == 3 && canvas_cols >= s.cs) {  // launch_icp()'s fallback
-    if (s.threads == 192 && s.ppt == 4) s.threads = 256;
-    s.kind = 0;
-  }
-  if (s.kind >= 4 && canvas_cols >= s.cs) s = {288, 4, 4, 0, 0};
-  // linearize2f (oracle decision D18): the 1152-stride shapes; the 768-stride ones measured faster unfused
-  const bool fused = s.kind == 3 && s.cs == 1152 && !(unfused_requested() && s.threads == 288);
-  return s.threads | (s.kind >= 3 ? 1 << 16 : 0) | (fused ? 1 << 17 : 0);
+int ls2d_reduction_shape(const ls2d_params* p, int32_t max_points) {
+  if (!p || !params_valid(*p) || max_points < 0) return LS2D_ERR_INVALID;
+  return icp_reduction_shape(translate(*p), p->single_rounding_accumulation != 0, max_points);
 }
 
 int64_t ls2d_launch_count(const ls2d_handle* h) { return h ? h->launches : 0; }

@@ -31,7 +31,7 @@
 
 #include <type_traits>
 
-#include "ls2d_kernels.cuh"
+#include "ls2d_icp.cuh"
 
 namespace ls2d {
 
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
     sm::st_f32x2<J * T * 8>(mna, m.z, m.w);
   });
   if (tid == 0) {
-    const iso X = iso_v2t(A.init_xyt[3 * pair], A.init_xyt[3 * pair + 1], A.init_xyt[3 * pair + 2]);
+    const iso X = load_pose(A.init_pose, (size_t) pair, A.pose_stride);
     publish_pose(bc, P, X, SENSOR, 0);
     bc->tie = 0;
   }

@@ -23,6 +23,9 @@ void ls2d_host_atan2f_n(const float* y, const float* x, float* out, long n) {
 void ls2d_host_sincosf_n(const float* x, float* s, float* c, long n) {
   for (long i = 0; i < n; ++i) s[i] = ls2d::sinf_glibc(x[i]), c[i] = ls2d::cosf_glibc(x[i]);
 }
+void ls2d_host_logf_n(const float* x, float* out, long n) {
+  for (long i = 0; i < n; ++i) out[i] = ls2d::logf_glibc(x[i]);
+}
 void ls2d_host_polar_column_n(int cols, float amin, float amax, const float* y, const float* x, int* fast,
                               int* exact, long n) {
   const ls2d::polar_cam k = ls2d::make_polar_cam(cols, amin, amax);

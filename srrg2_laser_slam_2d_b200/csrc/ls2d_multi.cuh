@@ -7,36 +7,13 @@
 // added in slice order, the prior last (oracle decisions D14-D17).
 #pragma once
 
-#include "ls2d_kernels.cuh"
+#include "ls2d_icp.cuh"
 
 namespace ls2d {
 
-constexpr int MAX_SLICES    = LS2D_MAX_SLICES;
 constexpr int MULTI_THREADS = 256;  // threads per pair: the shape of the per-slice reduction tree
 
-struct dev_slice {
-  dev_params P;
-  const float4* fixed_pts;
-  const int* fixed_off;
-  const float4* moving_pts;
-  const int* moving_off;
-};
 
-struct multi_args {
-  dev_slice sl[MAX_SLICES];
-  int n_slices;
-  int max_cols, max_points;  // capacity of the shared z-buffer / stash
-  const int* fixed_id;       // nullable: pair index
-  const int* moving_id;      // nullable: pair index
-  const float* init_xyt;
-  const float* prior_z;      // nullable: [n_pairs * 3], the prior slice's measurement
-  float prior_info[6];       // O00 O01 O02 O11 O12 O22
-  float prior_tau, prior_inv_tau;
-  ls2d_result* out;
-  ls2d_iter_stats* iters;  // nullable
-  int n_pairs;
-  int score_only;
-};
 
 struct multi_shared {
   pose_bc bc[MAX_SLICES];
@@ -140,13 +117,12 @@ __global__ void __launch_bounds__(T, MINB) icp_multi_kernel(const multi_args A) 
     zidx[k]   = Z_EMPTY_IDX;
   }
   if (tid == 0) {
-    const iso X = iso_v2t(A.init_xyt[3 * pair], A.init_xyt[3 * pair + 1], A.init_xyt[3 * pair + 2]);
+    const iso X = load_pose(A.init_pose, (size_t) pair, A.pose_stride);
     for (int s = 0; s < S; ++s) {
       publish_pose(&sh->bc[s], A.sl[s].P, X, A.sl[s].P.with_sensor != 0, 0);
       sh->bc[s].tie = 0;
     }
-    if (A.prior_z)
-      sh->Zinv = iso_inverse(iso_v2t(A.prior_z[3 * pair], A.prior_z[3 * pair + 1], A.prior_z[3 * pair + 2]));
+    if (A.prior_z) sh->Zinv = iso_inverse(load_pose(A.prior_z, (size_t) pair, A.pose_stride));
     for (int k = 0; k < NSUM; ++k) sh->tot[k] = 0.f;
     sh->n_in = sh->n_k = sh->n_corr = 0;
   }
@@ -299,6 +275,7 @@ __global__ void __launch_bounds__(T, MINB) icp_multi_kernel(const multi_args A) 
                 st.x = X.tx, st.y = X.ty, st.theta = atan2f_fdlibm(X.s, X.c);
                 st.chi_inliers = v[9], st.chi_kernelized = v[10];
                 st.n_inliers = n_in, st.n_kernelized = n_k, st.n_corr = n_corr;
+                st.c = X.c, st.s = X.s;
                 A.iters[(size_t) pair * A.sl[0].P.max_iterations + it] = st;
               }
             }
@@ -326,6 +303,8 @@ __global__ void __launch_bounds__(T, MINB) icp_multi_kernel(const multi_args A) 
     r.status = status, r.iterations = it;
 #pragma unroll
     for (int k = 0; k < 6; ++k) r.H[k] = sh->tot[k];
+    r.c = sh->bc[0].Xc, r.s = sh->bc[0].Xs;
+    r.lm_rejected = 0, r.reserved = 0;
     A.out[pair] = r;
   }
 }

@@ -17,26 +17,11 @@
 #include <cuda_runtime.h>
 #include <float.h>
 
-#include "ls2d_kernels.cuh"
+#include "ls2d_service.cuh"
 
 namespace ls2d {
 
-struct scan_dev_params {
-  float range_min, range_max;  // the tighter of message and PARAM limits (.cpp:83-84)
-  float ifx, cx;               // azimuth = ifx * (c - cx), sensor matrix [1/res, n/2] (.cpp:87-90)
-  float d2;                    // normal_point_distance^2
-  float inv_res;               // 1 / voxelize_resolution, 0: valid-only copy (.cpp:44-48)
-  int min_points;              // normal_min_points
-  int n_beams;
-  int sort_cap;                // slots of the segment sort: n_beams (voxelisation on), else 0
-};
 
-struct scan_args {
-  const float* ranges;  // [n_scans][n_beams]
-  float4* out;          // [n_scans][n_beams]
-  int* counts;          // [n_scans]
-  int n_scans;
-};
 
 constexpr size_t scan_smem_bytes(int n_beams, int sort_cap) {
   return (size_t) n_beams * (8 + 8) + (size_t) ((n_beams + 3) & ~3) + (size_t) sort_cap * 8 + 64;
@@ -382,8 +367,8 @@ __global__ void __launch_bounds__(SCAN_T) clip_voxel_kernel(const dev_params P, 
   const int r     = blockIdx.x;
   const int cloud = A.cloud_ids[r];
   const int p0 = A.off[cloud], n = A.off[cloud + 1] - p0;
-  const iso S   = iso_v2t(A.sensor_xyt[0], A.sensor_xyt[1], A.sensor_xyt[2]);
-  const iso cam = iso_compose(iso_v2t(A.robot_xyt[3 * r], A.robot_xyt[3 * r + 1], A.robot_xyt[3 * r + 2]), S);
+  const iso S   = load_pose(A.sensor_pose, 0, A.pose_stride);
+  const iso cam = iso_compose(load_pose(A.robot_pose, (size_t) r, A.pose_stride), S);
   const iso W   = iso_inverse(cam);
   const bool move = !(S.c == 1.f && S.s == 0.f && S.tx == 0.f && S.ty == 0.f);  // .cpp:60
   zbuffer_project<false>(P, W, A.pts + p0, n, zdepth, zidx);

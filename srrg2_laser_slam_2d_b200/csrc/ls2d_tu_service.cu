@@ -1,0 +1,106 @@
+// ls2d_tu_service.cu -- projector / finder / clipper / merger / best-of kernels (ls2d_service.cuh) and the raw-scan
+// pre-processor, voxelizing clipper and CSR packing built on the same z-buffer helpers (ls2d_scan.cuh)
+#include "ls2d_internal.h"
+#include "ls2d_scan.cuh"
+
+namespace ls2d {
+
+int launch_project(ls2d_handle* h, const project_args& a) {
+  const size_t smem = sizeof(unsigned) * 2 * (size_t) h->dp.cam.cols;
+  CU(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  project_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_correspond(ls2d_handle* h, const correspond_args& a) {
+  const size_t smem = sizeof(unsigned) * 4 * (size_t) h->dp.cam.cols;
+  CU(cudaFuncSetAttribute(correspond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  correspond_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_clip(ls2d_handle* h, const clip_args& a, int n) {
+  if (n <= 0) return LS2D_OK;
+  const size_t smem = sizeof(unsigned) * 2 * (size_t) h->dp.cam.cols;
+  CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  clip_kernel<<<n, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_merge(ls2d_handle* h, const merge_args& a) {
+  const size_t smem = sizeof(unsigned) * 4 * (size_t) h->dp.cam.cols;
+  CU(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  merge_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_classify(ls2d_handle* h, const classify_args& a, const int* off_f, int cloud_f, const int* off_m, int cloud_m) {
+  if (a.n <= 0) return LS2D_OK;
+  classify_dev d;
+  d.off_f = off_f, d.off_m = off_m, d.cloud_f = cloud_f, d.cloud_m = cloud_m;
+  classify_kernel<<<(a.n + 127) / 128, 128, 0, h->stream>>>(h->dp, a, d);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_best_of(ls2d_handle* h, const ls2d_result* res, int n, int n_guess, const ls2d_gates& g, int candidate_base,
+                   ls2d_best* out) {
+  best_of_kernel<<<1, 1024, 0, h->stream>>>(res, n, n_guess, g, candidate_base, out);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_best_of_groups(ls2d_handle* h, const ls2d_result* res, const int* group_off, int n_groups,
+                          const int* moving_id, const ls2d_gates& g, ls2d_best* out) {
+  if (n_groups <= 0) return LS2D_OK;
+  best_of_groups_kernel<<<(n_groups + 7) / 8, 256, 0, h->stream>>>(res, group_off, n_groups, moving_id, g, out);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+
+int launch_preprocess(ls2d_handle* h, const scan_dev_params& P, const scan_args& a, int n_scans) {
+  if (n_scans <= 0) return LS2D_OK;
+  const size_t smem = scan_smem_bytes(P.n_beams, P.sort_cap);
+  if (smem > SMEM_LIMIT) return LS2D_ERR_UNSUPPORTED;
+  CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  preprocess_kernel<<<n_scans, SCAN_T, smem, h->stream>>>(P, a);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_clip_voxel(ls2d_handle* h, const clip_args& a, int n, float inv_res) {
+  if (n <= 0) return LS2D_OK;
+  const int C = h->dp.cam.cols;
+  if (C > 32 * SCAN_T) return LS2D_ERR_UNSUPPORTED;
+  const size_t smem = clip_voxel_smem_bytes(C);
+  CU(cudaFuncSetAttribute(clip_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  clip_voxel_kernel<<<n, SCAN_T, smem, h->stream>>>(h->dp, a, inv_res);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
+int launch_scan_pack(ls2d_handle* h, const float4* strided, const int* counts, int stride, int n, int* off, float4* packed) {
+  if (n <= 0) return LS2D_OK;
+  scan_offsets_kernel<<<1, 1024, 0, h->stream>>>(counts, n, off);
+  CU(cudaGetLastError());
+  scan_pack_kernel<<<n, 128, 0, h->stream>>>(strided, off, stride, packed);
+  CU(cudaGetLastError());
+  h->launches += 2;
+  return LS2D_OK;
+}
+
+}  // namespace ls2d

@@ -23,8 +23,15 @@ namespace srrg2_core {
       int device = 0;
       if (const char* d = std::getenv("LS2D_DEVICE")) device = std::atoi(d);
       check(ls2d_create(&_h, device), "Ls2dDevice::handle");
+      // every pose crosses the C ABI as the Isometry2f itself (tx, ty, c, s): no t2v / v2t round trip, the device
+      // sees the bits the caller holds (the reference hands Isometry2f objects to its modules)
+      check(ls2d_set_pose_format(_h, LS2D_POSE_ISO), "Ls2dDevice::handle");
     }
     return _h;
+  }
+
+  void isoFloats(const Isometry2f& T, float* out) {
+    out[0] = T.raw().tx, out[1] = T.raw().ty, out[2] = T.raw().c, out[3] = T.raw().s;
   }
 
   void flattenCloud(const PointNormal2fVectorCloud& cloud, std::vector<float>& out) {
@@ -71,14 +78,15 @@ namespace srrg2_core {
     flattenCloud(cloud, flat);
     const int32_t off[2] = {0, (int32_t) n};
     Ls2dDevice::check(ls2d_upload_clouds(h, LS2D_FIXED, flat.data(), off, 1), "PointNormal2fProjectorPolar::compute");
-    const Vector3f cam = geometry2d::t2v(_camera_pose);
+    float cam[4];
+    isoFloats(_camera_pose, cam);
     std::vector<int32_t> idx(cols);
     std::vector<float> depth(cols);
-    Ls2dDevice::check(ls2d_project(h, LS2D_FIXED, 0, cam.v, idx.data(), depth.data()),
+    Ls2dDevice::check(ls2d_project(h, LS2D_FIXED, 0, cam, idx.data(), depth.data()),
                       "PointNormal2fProjectorPolar::compute");
     target.resize(1, cols);
     // `transformed` of the winners: same isometry, same single-rounding arithmetic as the device
-    const Isometry2f W = geometry2d::v2t(cam).inverse();
+    const Isometry2f W = _camera_pose.inverse();
     size_t filled      = 0;
     for (size_t c = 0; c < cols; ++c) {
       ProjectedEntry& e = target.at(0, c);
@@ -142,9 +150,10 @@ namespace srrg2_laser_slam_2d {
     Ls2dDevice::check(ls2d_upload_clouds(h, LS2D_MOVING, _staging.data(), off, 1),
                       "CorrespondenceFinderProjective2f::compute");
     std::vector<int32_t> fi(num_beams), mi(num_beams);
-    int32_t n          = 0;
-    const Vector3f xyt = geometry2d::t2v(_local_map_in_sensor);
-    Ls2dDevice::check(ls2d_find_correspondences(h, 0, 0, xyt.v, fi.data(), mi.data(), &n),
+    int32_t n = 0;
+    float lmis[4];
+    isoFloats(_local_map_in_sensor, lmis);  // .cpp:47: the isometry as the caller set it, bit for bit
+    Ls2dDevice::check(ls2d_find_correspondences(h, 0, 0, lmis, fi.data(), mi.data(), &n),
                       "CorrespondenceFinderProjective2f::compute");
     _correspondences->resize(n);
     for (int k = 0; k < n; ++k) (*_correspondences)[k] = Correspondence(fi[k], mi[k]);
@@ -177,11 +186,13 @@ namespace srrg2_laser_slam_2d {
     const int32_t off[2] = {0, (int32_t) _full_scene->size()};
     Ls2dDevice::check(ls2d_upload_clouds(h, LS2D_FIXED, flat.data(), off, 1), "SceneClipperProjective2D::compute");
     param_projector->setCameraPose(_robot_in_local_map * _sensor_in_robot);  // .cpp:29-31, visible to sharers
-    const Vector3f robot = geometry2d::t2v(_robot_in_local_map), sensor = geometry2d::t2v(_sensor_in_robot);
+    float robot[4], sensor[4];
+    isoFloats(_robot_in_local_map, robot);  // .cpp:22-32: both isometries verbatim
+    isoFloats(_sensor_in_robot, sensor);
     std::vector<float> out((size_t) p.canvas_cols * 4);
     int32_t n        = 0;
     const int32_t id = 0;
-    Ls2dDevice::check(ls2d_clip_scenes_voxelized(h, LS2D_FIXED, &id, robot.v, sensor.v, 1,
+    Ls2dDevice::check(ls2d_clip_scenes_voxelized(h, LS2D_FIXED, &id, robot, sensor, 1,
                                                  param_voxelize_resolution.value(), out.data(), &n),
                       "SceneClipperProjective2D::compute");  // <= 0: the plain clip (.cpp:49-57)
     unflatten(out.data(), (size_t) n, *_clipped_scene_in_robot);
@@ -198,17 +209,38 @@ namespace srrg2_laser_slam_2d {
     ls2d_handle* h = _device.handle();
     Ls2dDevice::check(ls2d_set_params(h, &p), "MergerProjective2D::compute");
     param_projector->setCameraPose(_measurement_in_scene);  // .cpp:19
+    // only Valid scene points take part (projector and merger skip the others by status): they are compacted for the
+    // device and written back through the index map, so a non-Valid point keeps its status, coordinates and slot
+    std::vector<size_t> slot;
     std::vector<float> scene, meas;
-    flattenCloud(*_scene, scene);
+    slot.reserve(_scene->size());
+    scene.reserve((_scene->size() + p.canvas_cols) * 4);
+    for (size_t i = 0; i < _scene->size(); ++i) {
+      const PointNormal2f& q = (*_scene)[i];
+      if (q.status != Valid) continue;
+      slot.push_back(i);
+      scene.insert(scene.end(), {q.coordinates().x(), q.coordinates().y(), q.normal().x(), q.normal().y()});
+    }
     flattenCloud(*_measurement, meas);
-    int32_t size           = (int32_t) _scene->size();
+    const int32_t n_valid  = (int32_t) slot.size();
+    int32_t size           = n_valid;
     const int32_t capacity = size + p.canvas_cols;  // .cpp:31
     scene.resize((size_t) capacity * 4);
-    const Vector3f xyt = geometry2d::t2v(_measurement_in_scene);
+    float mis[4];
+    isoFloats(_measurement_in_scene, mis);  // .cpp:19-22: the isometry verbatim
     Ls2dDevice::check(ls2d_merge_scene(h, scene.data(), &size, capacity, meas.data(), (int32_t) _measurement->size(),
-                                       xyt.v, param_merge_threshold.value(), nullptr),
+                                       mis, param_merge_threshold.value(), nullptr),
                       "MergerProjective2D::compute");
-    unflatten(scene.data(), (size_t) size, *_scene);
+    for (int32_t k = 0; k < size; ++k) {
+      PointNormal2f q;
+      q.coordinates() = Vector2f(scene[4 * (size_t) k], scene[4 * (size_t) k + 1]);
+      q.normal()      = Vector2f(scene[4 * (size_t) k + 2], scene[4 * (size_t) k + 3]);
+      q.status        = Valid;
+      if (k < n_valid)
+        (*_scene)[slot[k]] = q;   // merged / replaced in place (.cpp:72-84)
+      else
+        _scene->push_back(q);     // ordered append (.cpp:57-62, 87-88)
+    }
     _status = Success;
   }
 
@@ -303,6 +335,7 @@ namespace srrg2_laser_slam_2d {
     BOSS_REGISTER_CLASS(PointNormal2fProjectorPolar);
     BOSS_REGISTER_CLASS(RobustifierCauchy);
     BOSS_REGISTER_CLASS(IterationAlgorithmGN);
+    BOSS_REGISTER_CLASS(IterationAlgorithmLM);
     BOSS_REGISTER_CLASS(SparseBlockLinearSolverCholmodFull);
     BOSS_REGISTER_CLASS(SparseBlockLinearSolverCholeskyCSparse);
     BOSS_REGISTER_CLASS(SimpleTerminationCriteria);
@@ -326,6 +359,9 @@ namespace srrg2_laser_slam_2d {
     BOSS_REGISTER_CLASS_AS(AlignerSliceProcessorLaser2D, "AlignerSliceProcessorLaser2DCUDA");
     BOSS_REGISTER_CLASS_AS(AlignerSliceProcessorLaser2DWithSensor, "AlignerSliceProcessorLaser2DWithSensorCUDA");
     BOSS_REGISTER_CLASS_AS(MultiAligner2D, "MultiAligner2DCUDA");
+    // slices that bind the point-to-point factor (not in the reference, which binds plane-to-plane only)
+    BOSS_REGISTER_CLASS(AlignerSliceProcessorLaser2DPoint2Point);
+    BOSS_REGISTER_CLASS(AlignerSliceProcessorLaser2DPoint2PointWithSensor);
   }
 
 }  // namespace srrg2_laser_slam_2d
@@ -394,26 +430,38 @@ namespace srrg2_slam_interfaces {
     p.max_iterations          = param_max_iterations.value();
     p.min_num_inliers         = param_min_num_inliers.value();
     p.damping                 = 0.f;
+    p.factor                  = slice->pointToPoint() ? LS2D_FACTOR_POINT2POINT : LS2D_FACTOR_PLANE2PLANE;
     if (auto solver = param_solver.value()) {
       if (solver->param_max_iterations.size() && solver->param_max_iterations.value(0) != 1)
         throw std::runtime_error("MultiAligner2D::compute| the inner solver must run 1 iteration per ICP round "
                                  "(both shipped configurations do)");
-      if (auto gn = std::dynamic_pointer_cast<srrg2_solver::IterationAlgorithmGN>(solver->param_algorithm.value()))
+      if (auto gn = std::dynamic_pointer_cast<srrg2_solver::IterationAlgorithmGN>(solver->param_algorithm.value())) {
         p.damping = gn->param_damping.value();
-      else if (solver->param_algorithm.value())
-        throw std::runtime_error("MultiAligner2D::compute| only IterationAlgorithmGN is supported");
+      } else if (auto lm = std::dynamic_pointer_cast<srrg2_solver::IterationAlgorithmLM>(solver->param_algorithm.value())) {
+        p.algorithm           = LS2D_ALGORITHM_LM;
+        p.lm_user_lambda_init = lm->param_user_lambda_init.value();
+        p.lm_tau              = lm->param_tau.value();
+        p.lm_step_low         = lm->param_step_low.value();
+        p.lm_step_high        = lm->param_step_high.value();
+        p.lm_iterations_max   = lm->param_lm_iterations_max.value();
+        p.lm_variable_damping = lm->param_variable_damping.value() ? 1 : 0;
+      } else if (solver->param_algorithm.value()) {
+        throw std::runtime_error("MultiAligner2D::compute| only IterationAlgorithmGN / IterationAlgorithmLM are supported");
+      }
     }
-    if (param_enable_inlier_only_runs.value() || param_keep_only_inlier_correspondences.value())
-      throw std::runtime_error("MultiAligner2D::compute| inlier-only runs are not supported (both shipped "
-                               "configurations disable them)");
-    if (param_termination_criteria.value())
-      throw std::runtime_error("MultiAligner2D::compute| aligner termination criteria are not supported (both "
-                               "shipped configurations leave them unset)");
-    p.with_sensor = slice->withSensor() ? 1 : 0;
+    p.enable_inlier_only_runs          = param_enable_inlier_only_runs.value() ? 1 : 0;
+    p.keep_only_inlier_correspondences = param_keep_only_inlier_correspondences.value() ? 1 : 0;
+    if (auto tc = param_termination_criteria.value()) {
+      auto simple = std::dynamic_pointer_cast<srrg2_solver::SimpleTerminationCriteria>(tc);
+      if (!simple) throw std::runtime_error("MultiAligner2D::compute| only SimpleTerminationCriteria is supported");
+      p.termination_epsilon = simple->param_epsilon.value();
+    }
+    p.with_sensor = slice->withSensor() ? 2 : 0;  // 2: sensor_in_robot handed over as the isometry itself
     if (p.with_sensor) {
       slice->setupFactor();
-      const Vector3f s = geometry2d::t2v(slice->sensorInRobot());
-      std::memcpy(p.sensor_in_robot, s.v, sizeof(float) * 3);
+      const Isometry2f S = slice->sensorInRobot();
+      p.sensor_in_robot[0] = S.raw().tx, p.sensor_in_robot[1] = S.raw().ty, p.sensor_in_robot[2] = 0.f;
+      p.sensor_in_robot_cs[0] = S.raw().c, p.sensor_in_robot_cs[1] = S.raw().s;
     }
   }
 
@@ -425,10 +473,16 @@ namespace srrg2_slam_interfaces {
     for (size_t i = 0; i < slices.size(); ++i) fillOne(p[i], slices[i]);
   }
 
+  static Isometry2f isoOf(float tx, float ty, float c, float s) {
+    ls2d::iso T;
+    T.tx = tx, T.ty = ty, T.c = c, T.s = s;
+    return Isometry2f(T);
+  }
+
   static AlignmentResult toResult(const ls2d_result& r) {
     AlignmentResult a;
     a.estimate        = Vector3f(r.x, r.y, r.theta);
-    a.moving_in_fixed = geometry2d::v2t(a.estimate);
+    a.moving_in_fixed = isoOf(r.x, r.y, r.c, r.s);  // the isometry the kernel holds, not v2t(t2v(.))
     a.status          = r.status;
     a.iterations      = r.iterations;
     a.last.iteration           = r.iterations - 1;
@@ -479,6 +533,42 @@ namespace srrg2_slam_interfaces {
     }
   }
 
+  // the estimate the LAST executed finder pass ran at: a completed run linearised its last round at the estimate
+  // after round iterations - 2; a run that stopped early in round k (NotEnoughCorrespondences / singular system)
+  // completed k = iterations rounds and its failing finder pass ran at the estimate after round k - 1
+  static Isometry2f lastFinderEstimate(const ls2d_result& r, const std::vector<ls2d_iter_stats>& its,
+                                       const Isometry2f& init) {
+    const bool early = r.status == LS2D_STATUS_NOT_ENOUGH_CORRESPONDENCES || r.status == LS2D_STATUS_SINGULAR;
+    const int k      = early ? r.iterations - 1 : r.iterations - 2;
+    if (k < 0) return init;
+    return isoOf(its[k].x, its[k].y, its[k].c, its[k].s);
+  }
+
+  // slice->correspondences() after compute(): the last finder pass, re-run at the very isometry the kernel used
+  // (sensor_in_robot^-1 * estimate composed with the same binary32 sequence); keep_only_inlier_correspondences
+  // drops the pairs whose factor was kernelized
+  void MultiAligner2D::exportCorrespondences(ls2d_handle* h, const ls2d_params& p, int fixed_set, int moving_set,
+                                             const std::shared_ptr<AlignerSliceProcessorLaserBase>& slice,
+                                             const Isometry2f& estimate) {
+    Isometry2f lmis = estimate;
+    if (p.with_sensor) lmis = slice->sensorInRobot().inverse() * lmis;
+    float lv[4], ev[4];
+    isoFloats(lmis, lv);
+    isoFloats(estimate, ev);
+    std::vector<int32_t> fi(p.canvas_cols), mi(p.canvas_cols);
+    int32_t n = 0;
+    Ls2dDevice::check(ls2d_find_correspondences_in(h, fixed_set, moving_set, 0, 0, lv, fi.data(), mi.data(), &n),
+                      "MultiAligner2D::compute");
+    std::vector<uint8_t> inlier((size_t) (n > 0 ? n : 1), 1);
+    if (p.keep_only_inlier_correspondences && n > 0)
+      Ls2dDevice::check(ls2d_classify_correspondences(h, fixed_set, moving_set, 0, 0, ev, fi.data(), mi.data(), n,
+                                                      inlier.data()),
+                        "MultiAligner2D::compute");
+    slice->_correspondences.clear();
+    for (int k = 0; k < n; ++k)
+      if (inlier[k]) slice->_correspondences.push_back(Correspondence(fi[k], mi[k]));
+  }
+
   static PointNormal2fVectorCloud* sliceCloud(PropertyContainerDynamic* scene, const std::string& name, const char* which) {
     PointNormal2fVectorCloud* c = scene->cloud(name);
     if (!c) throw std::runtime_error(std::string("MultiAligner2D::compute| ") + which + " scene has no slice \"" + name + "\"");
@@ -504,22 +594,15 @@ namespace srrg2_slam_interfaces {
     Ls2dDevice::check(ls2d_set_params(h, &p), "MultiAligner2D::compute");
     uploadSet(h, LS2D_FIXED, {fixed}, "MultiAligner2D::compute");
     uploadSet(h, LS2D_MOVING, {moving}, "MultiAligner2D::compute");
-    const Vector3f init = geometry2d::t2v(_moving_in_fixed);
+    const Isometry2f init = _moving_in_fixed;
+    float iv[4];
+    isoFloats(init, iv);  // apps/visual_test_aligner_2d.cpp:123-128: setMovingInFixed(Isometry2f), verbatim
     ls2d_result r;
-    std::vector<ls2d_iter_stats> its((size_t) (p.max_iterations > 0 ? p.max_iterations : 1));
-    Ls2dDevice::check(ls2d_align_batch(h, nullptr, nullptr, init.v, 1, &r, its.data()), "MultiAligner2D::compute");
+    const int n_its = p.max_iterations * (p.enable_inlier_only_runs ? 2 : 1);
+    std::vector<ls2d_iter_stats> its((size_t) (n_its > 0 ? n_its : 1));
+    Ls2dDevice::check(ls2d_align_batch(h, nullptr, nullptr, iv, 1, &r, its.data()), "MultiAligner2D::compute");
     storeOutcome(r, its);
-    // slice->correspondences(): those of the last iteration, i.e. found at the estimate before its update
-    Vector3f before = init;
-    if (r.iterations >= 2) before = _iteration_stats[r.iterations - 2].estimate;
-    Isometry2f lmis = geometry2d::v2t(before);
-    if (p.with_sensor) lmis = slice->sensorInRobot().inverse() * lmis;
-    const Vector3f lv = geometry2d::t2v(lmis);
-    std::vector<int32_t> fi(p.canvas_cols), mi(p.canvas_cols);
-    int32_t n = 0;
-    Ls2dDevice::check(ls2d_find_correspondences(h, 0, 0, lv.v, fi.data(), mi.data(), &n), "MultiAligner2D::compute");
-    slice->_correspondences.resize(n);
-    for (int k = 0; k < n; ++k) slice->_correspondences[k] = Correspondence(fi[k], mi[k]);
+    exportCorrespondences(h, p, LS2D_FIXED, LS2D_MOVING, slice, lastFinderEstimate(r, its, init));
   }
 
   // several laser slices and / or a bound odometry prior: one fused 3x3 system per iteration (MULTI.json:700-730,
@@ -543,7 +626,7 @@ namespace srrg2_slam_interfaces {
       if (!shared) uploadSet(h, mset[s], {slices[s]->_moving}, "MultiAligner2D::compute");
     }
     ls2d_prior pr;
-    Vector3f z;
+    float z[4];
     if (prior) {
       const Matrix3f& O = prior->informationMatrix();
       const float info[6] = {O.m[0][0], O.m[0][1], O.m[0][2], O.m[1][1], O.m[1][2], O.m[2][2]};
@@ -552,29 +635,22 @@ namespace srrg2_slam_interfaces {
       if (prior->param_robustifier.value() && !cauchy)
         throw std::runtime_error("MultiAligner2D::compute| only RobustifierCauchy is supported");
       pr.cauchy_chi_threshold = cauchy ? cauchy->param_chi_threshold.value() : -1.f;
-      z = geometry2d::t2v(prior->measurement(_fixed_scene, _moving_scene));
+      isoFloats(prior->measurement(_fixed_scene, _moving_scene), z);
     }
-    const Vector3f init = geometry2d::t2v(_moving_in_fixed);
+    const Isometry2f init = _moving_in_fixed;
+    float iv[4];
+    isoFloats(init, iv);
     ls2d_result r;
     std::vector<ls2d_iter_stats> its((size_t) (p[0].max_iterations > 0 ? p[0].max_iterations : 1));
     Ls2dDevice::check(ls2d_align_multi(h, p.data(), fset.data(), mset.data(), (int32_t) slices.size(), prior ? &pr : nullptr,
-                                       prior ? z.v : nullptr, nullptr, nullptr, init.v, 1, &r, its.data()),
+                                       prior ? z : nullptr, nullptr, nullptr, iv, 1, &r, its.data()),
                       "MultiAligner2D::compute");
     storeOutcome(r, its);
-    // every slice's correspondences(): found at the estimate before the last iteration's update
-    Vector3f before = init;
-    if (r.iterations >= 2) before = _iteration_stats[r.iterations - 2].estimate;
+    // every slice's correspondences(): the last finder pass
+    const Isometry2f before = lastFinderEstimate(r, its, init);
     for (size_t s = 0; s < slices.size(); ++s) {
-      Isometry2f lmis = geometry2d::v2t(before);
-      if (p[s].with_sensor) lmis = slices[s]->sensorInRobot().inverse() * lmis;
-      const Vector3f lv = geometry2d::t2v(lmis);
       Ls2dDevice::check(ls2d_set_params(h, &p[s]), "MultiAligner2D::compute");
-      std::vector<int32_t> fi(p[s].canvas_cols), mi(p[s].canvas_cols);
-      int32_t n = 0;
-      Ls2dDevice::check(ls2d_find_correspondences_in(h, fset[s], mset[s], 0, 0, lv.v, fi.data(), mi.data(), &n),
-                        "MultiAligner2D::compute");
-      slices[s]->_correspondences.resize(n);
-      for (int k = 0; k < n; ++k) slices[s]->_correspondences[k] = Correspondence(fi[k], mi[k]);
+      exportCorrespondences(h, p[s], fset[s], mset[s], slices[s], before);
     }
   }
 
@@ -589,11 +665,8 @@ namespace srrg2_slam_interfaces {
     Ls2dDevice::check(ls2d_set_params(h, &p), "MultiAligner2D::computeBatch");
     uploadSet(h, LS2D_FIXED, fixed, "MultiAligner2D::computeBatch");
     uploadSet(h, LS2D_MOVING, moving, "MultiAligner2D::computeBatch");
-    std::vector<float> init(guesses.size() * 3);
-    for (size_t i = 0; i < guesses.size(); ++i) {
-      const Vector3f v = geometry2d::t2v(guesses[i]);
-      std::memcpy(&init[3 * i], v.v, sizeof(float) * 3);
-    }
+    std::vector<float> init(guesses.size() * 4);
+    for (size_t i = 0; i < guesses.size(); ++i) isoFloats(guesses[i], &init[4 * i]);
     std::vector<ls2d_result> out(guesses.size());
     Ls2dDevice::check(ls2d_align_batch(h, nullptr, nullptr, init.data(), (int32_t) guesses.size(), out.data(), nullptr),
                       "MultiAligner2D::computeBatch");
@@ -620,12 +693,9 @@ namespace srrg2_slam_interfaces {
     Ls2dDevice::check(ls2d_set_params(h, &p), "MultiLoopDetectorBruteForce2D::compute");
     uploadSet(h, LS2D_FIXED, {&query}, "MultiLoopDetectorBruteForce2D::compute");
     uploadSet(h, LS2D_MOVING, candidates, "MultiLoopDetectorBruteForce2D::compute");
-    std::vector<float> init(candidates.size() * n_guess * 3);
+    std::vector<float> init(candidates.size() * n_guess * 4);
     for (size_t c = 0; c < candidates.size(); ++c)
-      for (size_t g = 0; g < n_guess; ++g) {
-        const Vector3f v = geometry2d::t2v(guesses[c][g]);
-        std::memcpy(&init[3 * (c * n_guess + g)], v.v, sizeof(float) * 3);
-      }
+      for (size_t g = 0; g < n_guess; ++g) isoFloats(guesses[c][g], &init[4 * (c * n_guess + g)]);
     ls2d_gates gates;
     gates.min_inliers        = param_relocalize_min_inliers.value();
     gates.max_chi_per_inlier = param_relocalize_max_chi_inliers.value();
@@ -643,7 +713,7 @@ namespace srrg2_slam_interfaces {
     lc.candidate = best.candidate;
     lc.guess     = best.guess;
     if (best.candidate >= 0) {
-      lc.moving_in_fixed     = geometry2d::v2t(Vector3f(best.x, best.y, best.theta));
+      lc.moving_in_fixed     = isoOf(best.x, best.y, best.c, best.s);
       lc.chi_inliers         = best.chi_inliers;
       lc.num_inliers         = best.n_inliers;
       lc.num_correspondences = best.n_corr;

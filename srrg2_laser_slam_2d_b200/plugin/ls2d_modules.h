@@ -39,6 +39,8 @@ namespace srrg2_core {
 
   // flat (x, y, nx, ny) staging of a cloud for ls2d_upload_clouds
   void flattenCloud(const PointNormal2fVectorCloud& cloud, std::vector<float>& out);
+  // (tx, ty, c, s): an Isometry2f in the LS2D_POSE_ISO wire format of include/ls2d.h -- the bits the caller holds
+  void isoFloats(const Isometry2f& T, float* out);
 
   // 1 x cols image of {source_idx, depth, transformed}  (PointNormal2fProjectorPolar::TargetMatrixType)
   struct ProjectedEntry {
@@ -169,6 +171,18 @@ namespace srrg2_solver {
   public:
     PARAM(PropertyFloat, damping, "damping factor, the higher the closer to gradient descend. Default:0", 0.f, 0);
     IterationAlgorithmGN() { _class_name = "IterationAlgorithmGN"; }
+  };
+  // IterationAlgorithmLM of srrg2_solver (not instantiated by the shipped configurations; BASELINE.json's north_star
+  // names the LM update): parameter holder, run by icp_general_kernel (oracle decisions L1..L8)
+  class IterationAlgorithmLM : public IterationAlgorithmBase {
+  public:
+    PARAM(PropertyFloat, user_lambda_init, "initial lm lambda, if 0 is computed by system", 0.f, 0);
+    PARAM(PropertyFloat, step_high, "upper clamp for lambda if things go well", 2.f / 3.f, 0);
+    PARAM(PropertyFloat, step_low, "lower clamp for lambda if things go well", 1.f / 3.f, 0);
+    PARAM(PropertyInt, lm_iterations_max, "max lm iterations", 10, 0);
+    PARAM(PropertyBool, variable_damping, "set to true uses lambda*diag(H), otherwise uses lambda*I", true, 0);
+    PARAM(PropertyFloat, tau, "scale factor for the lambda computed by the system", 1e-5f, 0);
+    IterationAlgorithmLM() { _class_name = "IterationAlgorithmLM"; }
   };
   class SparseBlockLinearSolver : public Configurable {};
   class SparseBlockLinearSolverCholmodFull : public SparseBlockLinearSolver {
@@ -310,6 +324,7 @@ namespace srrg2_slam_interfaces {
     PARAM(PropertyInt, min_num_correspondences, "minimum number of correspondences in this slice", 0, 0);
     bool isLaserSlice() const override { return true; }
     virtual bool withSensor() const { return false; }
+    virtual bool pointToPoint() const { return false; }  // SE2Point2PointErrorFactor instead of plane-to-plane
     // sensor_in_robot of this slice (identity unless WithSensor); throws if the tf lookup fails
     Isometry2f sensorInRobot() const;
     const CorrespondenceVector& correspondences() const { return _correspondences; }
@@ -377,6 +392,8 @@ namespace srrg2_slam_interfaces {
     void computeMulti(const std::vector<std::shared_ptr<AlignerSliceProcessorLaserBase>>& slices,
                       const std::shared_ptr<AlignerSliceOdom2DPrior>& prior);
     void storeOutcome(const ls2d_result& r, const std::vector<ls2d_iter_stats>& its);
+    void exportCorrespondences(ls2d_handle* h, const ls2d_params& p, int fixed_set, int moving_set,
+                               const std::shared_ptr<AlignerSliceProcessorLaserBase>& slice, const Isometry2f& estimate);
     PropertyContainerDynamic* _fixed_scene  = nullptr;
     PropertyContainerDynamic* _moving_scene = nullptr;
     Isometry2f _moving_in_fixed;
@@ -441,6 +458,19 @@ namespace srrg2_laser_slam_2d {
     void setupFactor() override;  // R/registration/aligner_slice_processor_laser_2d_impl.cpp:7-10
   };
   using AlignerSliceProcessorLaser2DWithSensorPtr = std::shared_ptr<AlignerSliceProcessorLaser2DWithSensor>;
+
+  // the same slices bound to SE2Point2PointErrorFactor[WithSensor] (BASELINE.json north_star: "point-to-line (and
+  // point-to-point)"); the reference itself binds only the plane-to-plane factor (aligner_slice_processor_laser_2d.h:8,23)
+  class AlignerSliceProcessorLaser2DPoint2Point : public AlignerSliceProcessorLaser2D {
+  public:
+    AlignerSliceProcessorLaser2DPoint2Point() { _class_name = "AlignerSliceProcessorLaser2DPoint2Point"; }
+    bool pointToPoint() const override { return true; }
+  };
+  class AlignerSliceProcessorLaser2DPoint2PointWithSensor : public AlignerSliceProcessorLaser2DWithSensor {
+  public:
+    AlignerSliceProcessorLaser2DPoint2PointWithSensor() { _class_name = "AlignerSliceProcessorLaser2DPoint2PointWithSensor"; }
+    bool pointToPoint() const override { return true; }
+  };
 
   // R/mapping/scene_clipper_projective_2d.{h,cpp}: visibility clip of the local map (the tracker's moving cloud).
   // Driven as apps/visual_test_scene_clipper_projective_2d.cpp:103-114.

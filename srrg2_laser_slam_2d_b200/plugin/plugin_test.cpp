@@ -114,7 +114,11 @@ static int selftest() {
   platform->addTransform("scan", "base_frame", geometry2d::v2t(Vector3f(0.2f, 0.2f, 0.1f)));
   ls2d_params q;
   a3->fillParams(q);
-  REQUIRE(q.with_sensor == 1 && q.sensor_in_robot[0] == 0.2f && std::fabs(q.sensor_in_robot[2] - 0.1f) < 1e-6f);
+  // sensor_in_robot crosses the ABI as the isometry the platform holds (tx, ty, c, s), not as t2v of it
+  const Isometry2f S3 = geometry2d::v2t(Vector3f(0.2f, 0.2f, 0.1f));
+  REQUIRE(q.with_sensor == 2 && q.sensor_in_robot[0] == 0.2f && q.sensor_in_robot_cs[0] == S3.raw().c &&
+          q.sensor_in_robot_cs[1] == S3.raw().s);
+  REQUIRE(q.factor == LS2D_FACTOR_PLANE2PLANE && q.algorithm == LS2D_ALGORITHM_GN && q.enable_inlier_only_runs == 0);
   REQUIRE(q.cauchy_chi_threshold < 0.f);  // no robustifier on the slice
 
   // mis-wiring throws std::runtime_error with the reference's messages (correspondence_finder_projective_2d.cpp:20-31)
@@ -198,14 +202,14 @@ static int parse(const std::string& file) {
                 first ? "" : ", ", m.idOf(a.get()), a->name().c_str(), a->param_slice_processors.size(), p.canvas_cols,
                 p.angle_col_min, p.angle_col_max, p.range_min, p.range_max, p.point_distance, p.normal_cos,
                 p.cauchy_chi_threshold, p.damping, p.max_iterations, p.min_num_correspondences, p.min_num_inliers,
-                p.with_sensor);
+                p.with_sensor ? 1 : 0);
     std::vector<ls2d_params> all;
     a->fillSliceParams(all);  // every laser slice of the aligner (MULTI.json: two rangefinders)
     for (size_t k = 0; k < all.size(); ++k)
       std::printf("%s{\"point_distance\": %.4f, \"normal_cos\": %.4f, \"cauchy_chi_threshold\": %.4f, "
                   "\"min_num_correspondences\": %d, \"with_sensor\": %d, \"canvas_cols\": %d}",
                   k ? ", " : "", all[k].point_distance, all[k].normal_cos, all[k].cauchy_chi_threshold,
-                  all[k].min_num_correspondences, all[k].with_sensor, all[k].canvas_cols);
+                  all[k].min_num_correspondences, all[k].with_sensor ? 1 : 0, all[k].canvas_cols);
     int priors = 0;
     for (size_t k = 0; k < a->param_slice_processors.size(); ++k)
       if (std::dynamic_pointer_cast<AlignerSliceOdom2DPrior>(a->param_slice_processors.value(k))) ++priors;

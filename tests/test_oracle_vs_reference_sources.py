@@ -18,30 +18,6 @@ import pytest
 
 from srrg2_laser_slam_2d_b200.synthetic import make_raw_scans, make_scan_pairs
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_SO = os.path.join(ROOT, "oracle", "_ref", "libls2d_ref.so")
-REF_SRC = "/root/reference/srrg2_laser_slam_2d/src"
-
-
-@pytest.fixture(scope="module")
-def ref(oracle):
-    if os.path.isdir(REF_SRC):
-        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
-    if not os.path.exists(REF_SO):
-        pytest.skip("oracle/_ref/libls2d_ref.so not built and /root/reference absent")
-    oracle.lib()  # libls2d_oracle.so first: the reference library resolves the upstream stand-ins from it
-    L = C.CDLL(REF_SO)
-    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
-    L.ref_find_correspondences.argtypes = [vp, vp, i32, vp, i32, vp, i32, vp, vp]
-    L.ref_find_correspondences.restype = i32
-    L.ref_merge.argtypes = [vp, f32, vp, i32, vp, i32, vp]
-    L.ref_merge.restype = i32
-    L.ref_clip.argtypes = [vp, vp, i32, vp, vp, f32, vp]
-    L.ref_clip.restype = i32
-    L.ref_preprocess_scan.argtypes = [vp, vp, i32, vp]
-    L.ref_preprocess_scan.restype = i32
-    L.ref_finder_throws_without_inputs.restype = i32
-    return L
 
 
 def _p(a):

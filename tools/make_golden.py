@@ -36,13 +36,40 @@ CASES = {
     "norobust_361": (dict(n_pairs=6, n_beams=361, seed=105),
                      dict(canvas_cols=361, normal_cos=0.8, cauchy_chi_threshold=-1.0, max_iterations=6,
                           min_num_correspondences=5)),              # MULTI.json laser_1 slice: no robustifier
+    # poses handed over as Isometry2f content (tx, ty, c, s): initial guesses and sensor_in_robot are PRODUCTS of
+    # increments, the way a tracker accumulates them -- their (c, s) are not the cosf / sinf of any angle
+    "iso_721": (dict(n_pairs=6, n_beams=721, seed=108),
+                dict(canvas_cols=721, normal_cos=0.9, max_iterations=10, with_sensor=2, sensor_in_robot="accumulated")),
+    # options north_star names and the shipped configurations leave off (oracle decisions D19, L1-L8, I1, T1)
+    "p2p_721": (dict(n_pairs=6, n_beams=721, seed=109),
+                dict(canvas_cols=721, normal_cos=0.9, max_iterations=10, factor=1)),
+    "lm_721": (dict(n_pairs=6, n_beams=721, seed=110, motion_xy=0.3, motion_theta=0.15, init_noise_xy=0.15,
+                    init_noise_theta=0.05),
+               dict(canvas_cols=721, normal_cos=0.8, point_distance=1.414, cauchy_chi_threshold=0.05, max_iterations=15,
+                    algorithm=1)),
+    "lm_p2p_sensor_361": (dict(n_pairs=6, n_beams=361, seed=111),
+                          dict(canvas_cols=361, normal_cos=0.9, max_iterations=8, with_sensor=1,
+                               sensor_in_robot=(0.2, 0.2, 0.1), algorithm=1, factor=1, lm_variable_damping=0,
+                               lm_user_lambda_init=0.5)),
+    "options_361": (dict(n_pairs=6, n_beams=361, seed=112),
+                    dict(canvas_cols=361, normal_cos=0.9, max_iterations=8, enable_inlier_only_runs=1,
+                         termination_epsilon=1e-3)),
 }
 
 
 def params_dict(p):
-    d = {k: getattr(p, k) for k, _ in p._fields_ if k != "sensor_in_robot"}
-    d["sensor_in_robot"] = list(p.sensor_in_robot)
+    d = {}
+    for k, _ in p._fields_:
+        v = getattr(p, k)
+        d[k] = list(v) if hasattr(v, "__len__") else v
     return d
+
+
+def accumulated_pose(seed, xyt, steps=20):
+    """an Isometry2f close to v2t(xyt) built as a product of `steps` increments (tests/oracle_binding.accumulate)"""
+    rng = np.random.default_rng(seed)
+    inc = np.tile(np.asarray(xyt, np.float64) / steps, (steps, 1)) + rng.normal(0.0, 2e-3, (steps, 3))
+    return ob.accumulate(inc.astype(np.float32))
 
 
 # MULTI.json tracking aligner (:700-730): al_sl_laser_0 (Cauchy 0.01, finder 0.5 / 0.9), ad_sl_odom, al_sl_laser_1
@@ -112,19 +139,26 @@ def main():
     make_mapping()
     for name, (gen, prm_kw) in CASES.items():
         sp = make_scan_pairs(**gen)
+        prm_kw = dict(prm_kw)
+        iso_case = prm_kw.get("sensor_in_robot") == "accumulated"
+        if iso_case:
+            prm_kw["sensor_in_robot"] = ob.iso_array([accumulated_pose(7, (0.2, 0.2, 0.1))])[0]
         prm = ob.default_params(**prm_kw)
-        res, its = ob.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt)
+        init = sp.init_xyt
+        if iso_case:
+            init = ob.iso_array([accumulated_pose(100 + p, sp.init_xyt[p] + np.float32([0.02, -0.01, 0.01]))
+                                 for p in range(sp.n_pairs)])
+        res, its = ob.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, init)
         fidx, midx, ncorr, f_src, f_depth, m_src, m_depth = [], [], [], [], [], [], []
         for p in range(sp.n_pairs):
             f = sp.fixed_pts[sp.fixed_off[p]:sp.fixed_off[p + 1]]
             m = sp.moving_pts[sp.moving_off[p]:sp.moving_off[p + 1]]
-            lmis = sp.init_xyt[p]
-            if prm.with_sensor:
-                S = ob.lib().orc_inverse(ob.v2t(*prm.sensor_in_robot))
-                L = ob.lib().orc_compose(S, ob.v2t(*lmis))
-                xyt = np.zeros(3, np.float32)
-                ob.lib().orc_t2v(L, xyt.ctypes.data)
-                lmis = xyt
+            lmis = ob.as_iso(init[p])
+            if prm.with_sensor == 2:
+                S = ob.OrcIso(prm.sensor_in_robot[0], prm.sensor_in_robot[1], *prm.sensor_in_robot_cs)
+                lmis = ob.compose(ob.inverse(S), lmis)
+            elif prm.with_sensor:
+                lmis = ob.compose(ob.inverse(ob.v2t(*prm.sensor_in_robot)), lmis)
             fi, mi, fimg, mimg = ob.find_correspondences(prm, f, m, lmis)
             pad = np.full(prm.canvas_cols, -1, np.int32)
             a, b = pad.copy(), pad.copy()
@@ -134,12 +168,14 @@ def main():
             m_src.append(mimg["source_idx"]), m_depth.append(mimg["depth"])
         np.savez_compressed(
             os.path.join(OUT, name + ".npz"), fixed_pts=sp.fixed_pts, fixed_off=sp.fixed_off,
-            moving_pts=sp.moving_pts, moving_off=sp.moving_off, init_xyt=sp.init_xyt, gt_xyt=sp.gt_xyt,
+            moving_pts=sp.moving_pts, moving_off=sp.moving_off, init_xyt=init, gt_xyt=sp.gt_xyt,
             params=np.array(repr(params_dict(prm))), results=res, iters=its,
             corr_fixed_idx=np.stack(fidx), corr_moving_idx=np.stack(midx), corr_n=np.array(ncorr, np.int32),
             fixed_source_idx=np.stack(f_src), fixed_depth=np.stack(f_depth),
             moving_source_idx=np.stack(m_src), moving_depth=np.stack(m_depth), lmis_is_init=np.array(1))
-        print(name, "status", res["status"], "n_corr", res["n_corr"], "n_inl", res["n_inliers"])
+        print(name, "status", res["status"], "n_corr", res["n_corr"], "n_inl", res["n_inliers"], "it", res["iterations"],
+              "lm_rej", res["lm_rejected"], "err",
+              np.abs(np.stack([res["x"], res["y"], res["theta"]], 1) - sp.gt_xyt).max(0))
 
     # the reference's own deterministic demo world (apps/synthetic_scene_generator.cpp:36-88):
     # 1024 bins over +-0.4 pi, range_min 0.01, projector at (0.2, 0.2, 0.1) in the robot, robot at identity
