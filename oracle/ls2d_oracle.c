@@ -304,6 +304,22 @@ void orc_error_and_jacobian(const orc_params* prm, orc_iso X, orc_point fixed, o
                             float* e, float* J) {
   factor_ctx f = make_factor(prm, X);
   float Ja, Jb, Jc, d0, d1;
+  if (prm->factor == ORC_FACTOR_POINT2POINT) { /* D19: e = p_pred - p_fixed (2 rows, the third is zero), J = [R | R (-y, x)^T] */
+    float px, py, jc0, jc1;
+    apply(f.X, moving.x, moving.y, &px, &py);
+    if (f.with_sensor) {
+      float qx, qy;
+      apply(f.Sinv, px, py, &qx, &qy);
+      px = qx;
+      py = qy;
+    }
+    rot(f.RX, -moving.y, moving.x, &jc0, &jc1);
+    e[0] = px - fixed.x, e[1] = py - fixed.y, e[2] = 0.f;
+    J[0] = f.RX.c, J[1] = -f.RX.s, J[2] = jc0;
+    J[3] = f.RX.s, J[4] = f.RX.c, J[5] = jc1;
+    J[6] = J[7] = J[8] = 0.f;
+    return;
+  }
   factor_eval(&f, fixed, moving, e, &Ja, &Jb, &Jc, &d0, &d1);
   J[0] = Ja;
   J[1] = Jb;

@@ -145,10 +145,12 @@ def test_finder_empty_inputs(oracle):
 
 
 # ------------------------------------------------------------------ factor (A.3)
+@pytest.mark.parametrize("factor", [0, 1])
 @pytest.mark.parametrize("with_sensor", [0, 1])
-def test_jacobian_matches_finite_differences(oracle, with_sensor):
-    """J is the derivative of e for the post-multiplied increment X <- X * v2t(dx) (nicp_post.m:96)."""
-    prm = oracle.default_params(with_sensor=with_sensor, sensor_in_robot=(0.2, -0.1, 0.3))
+def test_jacobian_matches_finite_differences(oracle, with_sensor, factor):
+    """J is the derivative of e for the post-multiplied increment X <- X * v2t(dx) (nicp_post.m:96); factor 1 = the
+    point-to-point factor (decision D19)."""
+    prm = oracle.default_params(with_sensor=with_sensor, sensor_in_robot=(0.2, -0.1, 0.3), factor=factor)
     rng = np.random.default_rng(3)
     for _ in range(20):
         X = rng.uniform(-1, 1, 3)

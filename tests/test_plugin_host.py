@@ -140,10 +140,7 @@ def test_plugin_aligner_matches_abi_and_oracle(exe, tmp_path, handle_factory, or
     k = struct.unpack_from("<i", raw, pos)[0]
     finder_corr = np.frombuffer(raw, np.int32, 2 * k, pos + 4).reshape(k, 2)
     track = aligner == "aligner_tracking"
-    # the slice reads sensor_in_robot from the tf tree as an isometry; it crosses the C ABI as t2v(isometry)
-    srt = np.zeros(3, np.float32)
-    oracle.lib().orc_t2v(oracle.v2t(*sensor), srt.ctypes.data)
-    sensor = tuple(float(v) for v in srt)
+    # the slice reads sensor_in_robot from the tf tree as an isometry (v2t of this triple) and hands it over verbatim
     kw = dict(canvas_cols=1081, point_distance=0.5 if track else 1.414, normal_cos=0.9 if track else 0.8,
               cauchy_chi_threshold=0.01 if track else 0.05, max_iterations=10 if track else 30,
               with_sensor=1 if track else 0, sensor_in_robot=sensor)
@@ -153,10 +150,8 @@ def test_plugin_aligner_matches_abi_and_oracle(exe, tmp_path, handle_factory, or
     h.upload_clouds(LS2D_MOVING, sp.moving_pts, sp.moving_off)
     g, gi = h.align_batch(sp.init_xyt, want_iters=True)
     assert same(batch, g) is None
-    # compute() hands the estimate back as an Isometry2f (movingInFixed()): theta makes a v2t -> t2v round trip
-    exact = [f for f in REC.names if f != "theta"]
-    assert same(single[exact], g[exact]) is None
-    assert np.abs(single["theta"] - g["theta"]).max() <= 2.4e-7
+    # compute() hands the estimate back as the Isometry2f the kernel holds (movingInFixed()): no round trip anywhere
+    assert same(single, g) is None
     # ... and therefore bit-identical to the oracle in the kernel's summation order
     o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off,
                                sp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(1081))
@@ -189,11 +184,9 @@ def test_plugin_loop_detector_verification(exe, tmp_path, handle_factory, oracle
     h = handle_factory(default_params(**kw))
     h.upload_clouds(LS2D_FIXED, sp.fixed_pts, sp.fixed_off)
     h.upload_clouds(LS2D_MOVING, sp.moving_pts, sp.moving_off)
-    # the detector takes its initial guesses as Isometry2f; they cross the C ABI as t2v(isometry)
-    rt = guesses.copy().reshape(-1, 3)
-    for k in range(len(rt)):
-        oracle.lib().orc_t2v(oracle.v2t(*rt[k]), rt[k:k + 1].ctypes.data)
-    best, ref = h.verify(0, None, rt.reshape(guesses.shape), Gates(300, 0.1, 0.8), want_all=True)
+    # the detector takes its initial guesses as Isometry2f (here v2t of the file's triples) and hands them to the C ABI
+    # verbatim (tx, ty, c, s): the same poses as the triples themselves
+    best, ref = h.verify(0, None, guesses, Gates(300, 0.1, 0.8), want_all=True)
     assert same(allr, ref) is None
     assert (cand, guess, n_inl) == (int(best["candidate"]), int(best["guess"]), int(best["n_inliers"]))
     assert cand == 0                                       # the true match
@@ -221,11 +214,10 @@ def test_plugin_clipper_and_merger_match_the_oracle(exe, tmp_path, oracle):
         return c
 
     prm = oracle.default_params(canvas_cols=cols)
-    rt = lambda v: (lambda a: (oracle.lib().orc_t2v(oracle.v2t(*v), a.ctypes.data), a)[1])(np.zeros(3, np.float32))
     for p in range(n):
         scene = sp.fixed_pts[sp.fixed_off[p]:sp.fixed_off[p + 1]]
         meas = sp.moving_pts[sp.moving_off[p]:sp.moving_off[p + 1]]
-        pose, sen = rt(poses[p]), rt(sensor)          # isometries cross the C ABI as t2v(isometry)
+        pose, sen = poses[p], np.float32(sensor)      # the plugin holds v2t of these and hands the isometries over verbatim
         clipped, merged = cloud(), cloud()
         ref_c = oracle.clip_scene(prm, scene, pose, sen)
         ref_m, _ = oracle.merge(prm, 0.2, scene, meas, pose)
@@ -248,16 +240,15 @@ def test_plugin_multi_slice_aligner_with_odometry_prior(exe, tmp_path, handle_fa
     rng = np.random.default_rng(5)
     odom_fixed = rng.uniform(-2, 2, (n, 3)).astype(np.float32)       # robot pose in the odometry frame now ...
     inp, out = str(tmp_path / "multi.bin"), str(tmp_path / "multi_out.bin")
-    rt = lambda v: (lambda a: (oracle.lib().orc_t2v(oracle.v2t(*v), a.ctypes.data), a)[1])(np.zeros(3, np.float32))
     odom_moving = np.zeros((n, 3), np.float32)
-    z = np.zeros((n, 3), np.float32)
+    z = np.zeros((n, 4), np.float32)
     L = oracle.lib()
     for p in range(n):                                               # ... and the moving scene's: fixed * odometry delta
         M = L.orc_compose(oracle.v2t(*odom_fixed[p]), oracle.v2t(*msp.odom_xyt[p]))
         L.orc_t2v(M, odom_moving[p:p + 1].ctypes.data)
-        # what the slice computes: Z = fixed^-1 * moving, handed to the C ABI as t2v(Z)
+        # what the slice computes: Z = fixed^-1 * moving, handed to the C ABI as the isometry itself
         Z = L.orc_compose(L.orc_inverse(oracle.v2t(*odom_fixed[p])), oracle.v2t(*odom_moving[p]))
-        L.orc_t2v(Z, z[p:p + 1].ctypes.data)
+        z[p] = oracle.iso_array([Z])[0]
     with open(inp, "wb") as f:
         f.write(struct.pack("<i6f6f", n, *sensors[0], *sensors[1], *info))
         for p in range(n):
@@ -271,10 +262,11 @@ def test_plugin_multi_slice_aligner_with_odometry_prior(exe, tmp_path, handle_fa
     assert "MULTI OK" in run(exe, "multi", MULTI_CONFIG, "multi_aligner", inp, out)
     item = np.dtype([("rec", REC), ("nc", "<i4", (2,)), ("H", "<f4", (6,))])
     got = np.frombuffer(open(out, "rb").read(), item).reshape(n, 2)
-    # reference run: the C ABI directly, sensor_in_robot as t2v(isometry)
+    # reference run: the C ABI directly; every pose is the isometry the plugin holds (v2t of the file's triples)
     base = dict(canvas_cols=721, max_iterations=10, min_num_correspondences=5, with_sensor=1, point_distance=0.5)
-    mk = lambda fac: [fac(normal_cos=0.9, cauchy_chi_threshold=0.01, sensor_in_robot=tuple(map(float, rt(sensors[0]))), **base),
-                      fac(normal_cos=0.8, cauchy_chi_threshold=-1.0, sensor_in_robot=tuple(map(float, rt(sensors[1]))), **base)]
+    mk = lambda fac: [fac(normal_cos=0.9, cauchy_chi_threshold=0.01, sensor_in_robot=tuple(map(float, sensors[0])), **base),
+                      fac(normal_cos=0.8, cauchy_chi_threshold=-1.0, sensor_in_robot=tuple(map(float, sensors[1])), **base)]
+    init_iso = oracle.iso_array([oracle.v2t(*[float(v) for v in x]) for x in msp.init_xyt])
     h = handle_factory()
     h.upload_clouds(0, msp.fixed_pts[0], msp.fixed_off[0])
     h.upload_clouds(2, msp.fixed_pts[1], msp.fixed_off[1])
@@ -284,12 +276,12 @@ def test_plugin_multi_slice_aligner_with_odometry_prior(exe, tmp_path, handle_fa
     exact = [f for f in REC.names if f != "theta"]
     for pass_, kw, okw in ((0, dict(prior=make_prior(info), prior_z=z), dict(prior=oracle.make_prior(info), prior_z=z)),
                            (1, {}, {})):
-        g = h.align_multi(mk(default_params), [0, 2], [1, 1], msp.init_xyt, **kw)
-        o, _ = oracle.align_multi_batch(mk(oracle.default_params), fixed, moving, msp.init_xyt, sum_mode=oracle.SUM_TREE,
+        g = h.align_multi(mk(default_params), [0, 2], [1, 1], init_iso, **kw)
+        o, _ = oracle.align_multi_batch(mk(oracle.default_params), fixed, moving, init_iso, sum_mode=oracle.SUM_TREE,
                                         tree_threads=multi_reduction_threads(), **okw)
         rec = got[:, pass_]["rec"]
         assert same(rec[exact], g[exact]) is None
-        assert np.abs(rec["theta"] - g["theta"]).max() <= 2.4e-7     # movingInFixed() is an Isometry2f: v2t -> t2v
+        assert np.array_equal(rec["theta"], g["theta"])              # movingInFixed() is the kernel's isometry itself
         assert np.array_equal(got[:, pass_]["H"].view(np.uint32), g["H"].view(np.uint32))   # informationMatrix()
         for f in ("x", "y", "theta", "chi_inliers", "status", "n_inliers", "n_corr", "iterations"):
             assert np.array_equal(g[f], o[f]), f
