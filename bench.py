@@ -149,6 +149,15 @@ def bind_to_gpu_numa_node(torch, local_rank: int) -> str:
         return "unchanged (%s)" % type(e).__name__
 
 
+def bench_config(n_pairs: int) -> dict:
+    """the `config` object of the JSON line -- the SAME keys and values in both arms (ours / --impl reference)"""
+    return {"workload": "batched scan-to-local-map registration: %d pairs x %d beams, 10 GN iterations, tracking "
+                        "parameter set (config 3)" % (n_pairs, N_BEAMS),
+            "pairs_per_step": n_pairs, "beams": N_BEAMS, "canvas_cols": N_BEAMS, "iterations": 10,
+            "parameters": "point_distance 0.5, normal_cos 0.9, Cauchy 0.01 (LASER_0.json:598-611,76-81,498)",
+            "seed": "0xC0FFEE + rank", "l2": "inputs_larger_than_l2 (142 MB of clouds per step vs 126 MB)"}
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's own CPU implementation of the path.  It cannot be compiled here (needs Eigen3 and three
@@ -160,8 +169,8 @@ def run_reference(args):
     import oracle_binding as ob
     prm = ob.default_params(**TRACK)
     cores = host_cores()  # not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
-    sample_pairs = min(args.pairs, 4096)
-    sp = make_workload(sample_pairs, 0xC0FFEE, "cpu")
+    n_pairs = args.pairs
+    sp = make_workload(n_pairs, 0xC0FFEE, "cpu")
     run = lambda: ob.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt,
                                  n_threads=cores, want_iters=False)
     for _ in range(args.warmup):
@@ -170,23 +179,126 @@ def run_reference(args):
     for _ in range(args.steps):
         run()
     dt = time.perf_counter() - t0
-    value = sample_pairs * args.steps / dt
+    value = n_pairs * args.steps / dt
     print(json.dumps({
-        "impl": "reference", "metric": "aligned scan-pairs/sec (1081 beams, 10 GN iters)", "value": value,
+        "impl": "reference", "metric": "aligned scan-pairs/sec (%d beams, 10 GN iters)" % N_BEAMS, "value": value,
         "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "batched scan-to-local-map registration: %d pairs x 1081 beams, 10 GN iterations, "
-                               "tracking parameter set (config 3)" % sample_pairs, "pairs_per_step": sample_pairs,
-                   "canvas_cols": 1081},
+        "dtype": "f32", "data": "synthetic", "config": bench_config(n_pairs),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": "%d pairs per step, OpenMP over pairs on %d threads" % (sample_pairs, cores)},
+                         "sample": "%d pairs per step (the whole config-3 batch), OpenMP over pairs on %d threads; the "
+                                   "reference itself cannot be built here (no Eigen / srrg2_*): in-repo oracle port"
+                                   % (n_pairs, cores)},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def timed_steps(torch, stream, step, n, barrier):
+    """n calls of step() on `stream`, bracketed by barrier + synchronize; returns (total ms, per-call ms list)"""
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record(stream)
+    for i in range(n):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    return ev[0].elapsed_time(ev[-1]), [ev[i].elapsed_time(ev[i + 1]) for i in range(n)]
+
+
+def measure_e2e(torch, he, bufs, hout, args, barrier, pinned: bool):
+    fp, fo, mp_, mo, init = bufs
+    for _ in range(args.warmup):
+        he.align_pairs_host(fp, fo, mp_, mo, init, hout)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        he.align_pairs_host(fp, fo, mp_, mo, init, hout)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    barrier()
+    return dt
+
+
+def measure_track(torch, local_rank, n, args):
+    """the tracker's frame step with RAW scans as the wire format (ls2d_track_batch: pre-process -> clip -> align):
+    4 B/beam + ids + poses up, 80 B/frame down; the local maps are resident"""
+    from srrg2_laser_slam_2d_b200 import Handle, default_params
+    from srrg2_laser_slam_2d_b200._abi import RESULT_DTYPE, default_scan_params
+    from srrg2_laser_slam_2d_b200.synthetic import make_raw_scans
+    raw = make_raw_scans(n, seed=0xC0FFEE, device="cuda:%d" % local_rank)
+    sp_map = default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=0.0)
+    sp = default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=args.voxel)
+    h = Handle(local_rank, default_params(**TRACK))
+    h.preprocess_scans_to_set(2, sp_map, raw.moving_ranges)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    ranges, ids = pin(raw.fixed_ranges), pin(np.arange(n, dtype=np.int32))
+    robots, init = pin(np.zeros((n, 3), np.float32)), pin(np.zeros((n, 3), np.float32))
+    out = torch.zeros(n * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
+    for _ in range(args.warmup):
+        h.track_batch(sp, ranges, 2, ids, robots, init, out)
+    torch.cuda.synchronize()
+    l0 = h.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h.track_batch(sp, ranges, 2, ids, robots, init, out)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    err = np.abs(np.stack([out["x"], out["y"], out["theta"]], 1) - raw.gt_xyt)
+    rec = {"value": n * args.steps / dt, "unit": "frames/s", "ms_per_step": 1e3 * dt / args.steps,
+           "h2d_bytes_per_step": int(ranges.nbytes + ids.nbytes + robots.nbytes + init.nbytes),
+           "d2h_bytes_per_step": int(out.nbytes), "frames_per_step": n, "voxelize_resolution": args.voxel,
+           "gpu_launches_per_step": int(h.launch_count - l0) // args.steps,
+           "success_rate": float((out["status"] == 0).mean()),
+           "median_abs_pose_error": [float(v) for v in np.median(err, 0)],
+           "note": "ls2d_track_batch: raw 1081-beam scans (4 B/beam) -> pre-process -> clip of the resident local map -> "
+                   "10 GN iterations; the same metric with the raw-range wire format instead of 16 B/point clouds"}
+    h.close()
+    return rec
+
+
+def measure_latency(sp, n_calls=200):
+    """single-pair latency of MultiAligner2D::compute() through the C++ shim (plugin_test latency), the reference's
+    real tracker use (apps/visual_test_tracker_2d.cpp:167-179), next to the 1-thread oracle on the same pairs"""
+    import struct
+    import tempfile
+    exe = os.path.join(ROOT, "srrg2_laser_slam_2d_b200", "plugin_test")
+    cfg = os.path.join(ROOT, "configs", "laser_aligner_b200.json")
+    if not (os.path.exists(exe) and os.path.exists(cfg)):
+        return {"unavailable": "plugin_test not built"}
+    n = 16
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        f.write(struct.pack("<ii3f", n, 1, 0.0, 0.0, 0.0))
+        for p in range(n):
+            fx = sp.fixed_pts[sp.fixed_off[p]:sp.fixed_off[p + 1]]
+            mv = sp.moving_pts[sp.moving_off[p]:sp.moving_off[p + 1]]
+            f.write(struct.pack("<ii", len(fx), len(mv)))
+            f.write(np.ascontiguousarray(fx, np.float32).tobytes())
+            f.write(np.ascontiguousarray(mv, np.float32).tobytes())
+            f.write(np.ascontiguousarray(sp.init_xyt[p], np.float32).tobytes())
+        path = f.name
+    try:
+        r = subprocess.run([exe, "latency", cfg, "aligner_tracking", path, str(n_calls)], capture_output=True, text=True,
+                           timeout=300)
+        if r.returncode != 0:
+            return {"unavailable": "plugin_test latency failed: " + r.stderr.strip()[-200:]}
+        rec = json.loads(r.stdout.strip().splitlines()[-1])
+    finally:
+        os.unlink(path)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    prm = ob.default_params(**dict(TRACK, with_sensor=1))
+    t0 = time.perf_counter()
+    ob.align_batch(prm, sp.fixed_pts, sp.fixed_off[:n + 1], sp.moving_pts, sp.moving_off[:n + 1], sp.init_xyt[:n],
+                   n_threads=1, want_iters=False)
+    rec["oracle_1_thread_us"] = 1e6 * (time.perf_counter() - t0) / n
+    rec["note"] = ("one MultiAligner2D::compute() per call through the plugin class: stage + upload 2 x 1081 points, "
+                   "aligner, download result and iteration records, re-run the finder for slice->correspondences(); "
+                   "pageable host memory, nothing batched")
+    return rec
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -213,12 +325,13 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
+    words = RESULT_DTYPE.itemsize // 4
 
     # ---- device-resident: clouds live in HBM, one launch per step
     fp, fo = torch.from_numpy(sp.fixed_pts).to(dev), torch.from_numpy(sp.fixed_off).to(dev)
     mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
     init = torch.from_numpy(sp.init_xyt).to(dev)
-    out = torch.zeros(n_pairs * (RESULT_DTYPE.itemsize // 4), dtype=torch.int32, device=dev)
+    out = torch.zeros(n_pairs * words, dtype=torch.int32, device=dev)
     h.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), n_pairs, N_BEAMS)
     h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), n_pairs, N_BEAMS)
 
@@ -227,53 +340,52 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
-    barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     launches0 = h.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record(stream)
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record(stream)
-    barrier()
+    total_ms, per_launch_ms = timed_steps(torch, stream, step, args.steps, barrier)
     launches = h.launch_count - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     res = np.frombuffer(out.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
     ok_rate = float((res["status"] == 0).mean())
 
     # ---- the single-linearisation scoring pass (ls2d_score_batch): the regime closest to the HBM roofline
-    out_s = torch.zeros(n_pairs * (RESULT_DTYPE.itemsize // 4), dtype=torch.int32, device=dev)
+    out_s = torch.zeros(n_pairs * words, dtype=torch.int32, device=dev)
+    score = lambda: h.score_batch_dev(None, None, init.data_ptr(), n_pairs, out_s.data_ptr())
     for _ in range(args.warmup):
-        h.score_batch_dev(None, None, init.data_ptr(), n_pairs, out_s.data_ptr())
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record(stream)
-    for _ in range(args.steps):
-        h.score_batch_dev(None, None, init.data_ptr(), n_pairs, out_s.data_ptr())
-    s1.record(stream)
-    barrier()
-    score_ms = s0.elapsed_time(s1) / args.steps
+        score()
+    score_total, _ = timed_steps(torch, stream, score, args.steps, barrier)
+    score_ms = score_total / args.steps
 
-    # ---- end to end: host buffers (pinned) -> C ABI -> host results
+    # ---- sustained: the same step back to back for >= args.sustain seconds (the timed region above is a few ms of
+    # burst clock; an issue-bound kernel slows down when the SM clock settles under load)
+    sustained = None
+    if args.sustain > 0:
+        reps = max(args.steps, int(args.sustain * 1e3 / (total_ms / args.steps)) + 1)
+        sclk = ClockSampler(local_rank)
+        if rank == 0:
+            sclk.start()
+        sus_ms, _ = timed_steps(torch, stream, step, reps, barrier)
+        sc = sclk.stop() if rank == 0 else None
+        sustained = {"launches": reps, "seconds": sus_ms * 1e-3, "ms_per_launch": sus_ms / reps,
+                     "pairs_per_s_per_gpu": n_pairs * reps / (sus_ms * 1e-3), "clocks": sc}
+
+    # ---- end to end: host buffers -> C ABI -> host results (pinned = the headline e2e; pageable = what a caller that
+    # never pinned anything gets)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    hfp, hfo, hmp, hmo, hin = pin(sp.fixed_pts), pin(sp.fixed_off), pin(sp.moving_pts), pin(sp.moving_off), pin(sp.init_xyt)
+    host = (sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt)
+    pinned = tuple(pin(a) for a in host)
     hout = torch.zeros(n_pairs * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
     he = Handle(local_rank, default_params(**TRACK))
-    for _ in range(args.warmup):
-        he.align_pairs_host(hfp, hfo, hmp, hmo, hin, hout)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        he.align_pairs_host(hfp, hfo, hmp, hmo, hin, hout)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = measure_e2e(torch, he, pinned, hout, args, barrier, True)
     e2e_launches = he.launch_count
-    barrier()
-    clk = clocks.stop() if rank == 0 else None
     assert hout.tobytes() == res.tobytes(), "end-to-end results differ from the device-resident run"
+    pageable_s = None
+    if rank == 0 and world == 1:
+        pout = np.zeros(n_pairs, RESULT_DTYPE)
+        pageable_s = measure_e2e(torch, he, host, pout, args, barrier, False)
+        assert pout.tobytes() == res.tobytes()
+    clk = clocks.stop() if rank == 0 else None
 
     # ---- max over ranks
     t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -281,32 +393,33 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
 
+    # ---- the path that shards: loop-closure verification (config 4), strong scaling over the ranks
+    verify = measure_verify(args, torch, dist, rank, local_rank, world) if args.verify_candidates > 0 else None
+
     if rank == 0:
         value = world * n_pairs * args.steps / (total_ms * 1e-3)
         e2e_value = world * n_pairs * args.steps / (e2e_ms * 1e-3)
         peak, peak_src = hbm_peak()
         mean_launch_s = float(np.mean(per_launch_ms)) * 1e-3
         achieved = A_PAIR_BYTES * n_pairs / mean_launch_s / 1e9
-        h2d = hfp.nbytes + hfo.nbytes + hmp.nbytes + hmo.nbytes + hin.nbytes
+        h2d = sum(a.nbytes for a in pinned)
         line = {
             "metric": "aligned scan-pairs/sec (%d beams, 10 GN iters)" % N_BEAMS, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "batched scan-to-local-map registration: %d pairs x %d beams, 10 GN iterations, "
-                                   "tracking parameter set (config 3)" % (n_pairs, N_BEAMS),
-                       "pairs_per_gpu_per_step": n_pairs, "canvas_cols": N_BEAMS, "l2": "inputs_larger_than_l2 (142 MB)",
-                       "success_rate": ok_rate, "host_binding_rank0": numa},
+            "config": bench_config(n_pairs),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(hout.nbytes), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches),  # timed region of `value`; the scoring pass adds its own
+                    "d2h_bytes_per_step": int(hout.nbytes), "ms_per_step": e2e_ms / args.steps,
+                    "host_memory": "pinned (caller-provided)", "gpu_launches": int(e2e_launches)},
+            "gpu_launches": int(launches),  # timed region of `value`; the sub-records count their own
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic("icp_fused2_kernel"), "peak_source": peak_src,
                          "kernel": "icp_fused2_kernel", "algorithmic_bytes_per_launch": A_PAIR_BYTES * n_pairs,
                          "mean_launch_ms": mean_launch_s * 1e3,
                          "note": "10 fused iterations per pair make this kernel issue-bound, not HBM-bound "
-                                 "(SURVEY.md 8d); see DESIGN.md for the instruction-issue roofline"},
+                                 "(SURVEY.md 8d); see roofline_issue and DESIGN.md; the HBM-bound regime is score_pass"},
             "clocks": clk,
-            "e2e_gpu_launches": int(e2e_launches),
+            "info": {"success_rate": ok_rate, "host_binding_rank0": numa},
         }
         inst = recorded_traffic("icp_fused2_kernel_warp_instructions")
         if inst and clk and clk.get("sm_mhz"):
@@ -316,15 +429,137 @@ def run_ours(args):
                                       "warp_instructions_per_launch": inst,
                                       "note": "the bound that actually limits the 10-iteration kernel; instruction count "
                                               "from the committed ncu capture (profiles/)"}
+        score_gbs = A_PAIR_BYTES * n_pairs / (score_ms * 1e-3) / 1e9
         line["score_pass"] = {"ms_per_launch": score_ms, "pairs_per_s": n_pairs / (score_ms * 1e-3),
-                              "achieved_gbs": A_PAIR_BYTES * n_pairs / (score_ms * 1e-3) / 1e9,
-                              "frac_of_hbm_peak": A_PAIR_BYTES * n_pairs / (score_ms * 1e-3) / 1e9 / peak,
-                              "note": "ls2d_score_batch: fixed image + one projection/linearisation per pair, same bytes"}
+                              "roofline": {"bound": "hbm", "achieved": score_gbs, "peak": peak, "unit": "GB/s",
+                                           "frac": score_gbs / peak, "traffic": recorded_traffic("score_kernel"),
+                                           "kernel": "score_kernel"},
+                              "frac_of_hbm_peak": score_gbs / peak,
+                              "note": "ls2d_score_batch: fixed image + one projection / linearisation per pair, same bytes"}
+        if sustained:
+            line["sustained"] = sustained
+        if pageable_s is not None:
+            line["e2e_pageable"] = {"value": n_pairs * args.steps / pageable_s, "unit": "pairs/s",
+                                    "ms_per_step": 1e3 * pageable_s / args.steps,
+                                    "note": "the same call from pageable numpy buffers"}
+        if world == 1:
+            line["e2e_track"] = measure_track(torch, local_rank, n_pairs, args)
+            line["latency_single_pair"] = measure_latency(sp)
+        if verify:
+            line["verify"] = verify
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sp, res)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def candidate_block(block: int, device: str):
+    """candidates [block * 4096, (block + 1) * 4096) of the verification workload: every block has its own seed, so any
+    sharding of the candidate list over ranks sees the same clouds"""
+    return make_workload(4096, 0xBEEF + block, device, loop=True)
+
+
+def measure_verify(args, torch, dist, rank, local_rank, world):
+    """Sharded loop-closure verification (BASELINE.json configs[3], "config 4"): one query local map against n_cand
+    DISTINCT candidate local maps x n_guess initial guesses, 30 GN iterations, loop-closure parameter set; the
+    candidates are split contiguously over the ranks (strong scaling: the total is fixed), the only exchange is the
+    all-gather of the ranks' 48-byte ls2d_best records inside ls2d_verify_sharded_nccl (the C ABI's collective, over a
+    raw ncclComm_t), then the same deterministic best-of on every rank."""
+    from srrg2_laser_slam_2d_b200 import Gates, Handle, default_params
+    from srrg2_laser_slam_2d_b200._abi import LS2D_FIXED, LS2D_MOVING, RESULT_DTYPE
+    from srrg2_laser_slam_2d_b200.nccl_comm import NcclComm
+    from srrg2_laser_slam_2d_b200.sharding import shard_range
+
+    dev = torch.device("cuda", local_rank)
+    n_cand, n_guess = args.verify_candidates, args.guesses
+    lo, hi = shard_range(n_cand, rank, world)
+    t_gen = time.perf_counter()
+    blocks = range(lo // 4096, (max(hi, lo + 1) - 1) // 4096 + 1)
+    parts, query = [], None
+    b0 = candidate_block(0, str(dev))               # the query = fixed cloud 0 of block 0; candidate 0 is its match
+    query = torch.from_numpy(b0.fixed_pts[:1081].copy()).to(dev)
+    gt0 = b0.gt_xyt[0]
+    for b in blocks:
+        blk = b0 if b == 0 else candidate_block(b, str(dev))
+        a, z = max(lo, b * 4096) - b * 4096, min(hi, (b + 1) * 4096) - b * 4096
+        parts.append(torch.from_numpy(blk.moving_pts[a * 1081:z * 1081].copy()).to(dev))
+    cands = torch.cat(parts) if parts else torch.zeros((0, 4), dtype=torch.float32, device=dev)
+    del parts
+    n_local = hi - lo
+    off = torch.arange(n_local + 1, dtype=torch.int32, device=dev) * 1081
+    qoff = torch.tensor([0, 1081], dtype=torch.int32, device=dev)
+    rng = np.random.default_rng(1)
+    guesses = (gt0[None, None, :] + rng.uniform(-0.15, 0.15, (n_cand, n_guess, 3))).astype(np.float32)
+    gs = torch.from_numpy(guesses[lo:hi].copy()).to(dev)
+    gen_s = time.perf_counter() - t_gen
+    h = Handle(local_rank, default_params(**LOOP))
+    stream = torch.cuda.current_stream(dev)
+    h.set_stream(stream.cuda_stream)
+    h.set_clouds_dev(LS2D_FIXED, query.data_ptr(), qoff.data_ptr(), 1, 1081)
+    h.set_clouds_dev(LS2D_MOVING, cands.data_ptr(), off.data_ptr(), n_local, 1081)
+    gates = Gates(300, 0.1, 0.8)
+    comm, how = None, "ls2d_verify_sharded_nccl (raw ncclComm_t, all-gather of %d x 48 B)" % world
+    try:
+        comm = NcclComm(rank, world, local_rank)
+    except Exception as e:                                   # a box without a usable NCCL: single rank only
+        if world > 1:
+            raise
+        how = "ls2d_verify_dev (NCCL unavailable: %s)" % type(e).__name__
+    best_dev = torch.zeros(12, dtype=torch.int32, device=dev)
+    winner = {}
+
+    def step():
+        if comm is not None:
+            b = h.verify_sharded_nccl(0, None, n_local, gs.data_ptr(), n_guess, gates, lo, comm.ptr, world)
+            winner.update(candidate=int(b["candidate"]), guess=int(b["guess"]), n_inliers=int(b["n_inliers"]))
+        else:
+            h.verify_dev(0, None, n_local, gs.data_ptr(), n_guess, gates, lo, best_dev.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(args.steps, 20)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    l0 = h.launch_count
+    ms, _ = timed_steps(torch, stream, step, steps, barrier)
+    launches = h.launch_count - l0
+    # executed iterations (the kernel leaves early on a failure status): one untimed pass that keeps every result
+    allr = torch.zeros(max(n_local * n_guess, 1) * (RESULT_DTYPE.itemsize // 4), dtype=torch.int32, device=dev)
+    h.verify_dev(0, None, n_local, gs.data_ptr(), n_guess, gates, lo, best_dev.data_ptr(), allr.data_ptr())
+    torch.cuda.synchronize()
+    r = np.frombuffer(allr.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)[:n_local * n_guess]
+    stats = torch.tensor([ms, float(r["iterations"].sum()), float((r["status"] == 0).sum()), gen_s], dtype=torch.float64,
+                         device=dev)
+    mx = stats.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    if comm is not None:
+        comm.close()
+    h.close()
+    n_align = n_cand * n_guess
+    ms = float(mx[0])
+    peak, _ = hbm_peak()
+    a_bytes = 16 * 1081 + n_cand * 16 * 1081 + n_align * (16 + 80)     # SURVEY.md 8d: the query is counted once
+    return {"metric": "verified candidate alignments/sec (1081 beams, 30 GN iters)",
+            "value": n_align * steps / (ms * 1e-3), "unit": "alignments/s", "n_gpus": world, "steps": steps,
+            "ms_per_step": ms / steps, "scaling": "strong",
+            "config": {"workload": "loop-closure verification: 1 query x %d candidates x %d guesses, 30 GN iterations, "
+                                   "loop-closure parameter set (config 4)" % (n_cand, n_guess),
+                       "distinct_candidate_clouds": n_cand, "candidate_bytes": int(n_cand * 1081 * 16),
+                       "collective": how},
+            "mean_executed_iterations": float(stats[1]) / n_align, "success_rate": float(stats[2]) / n_align,
+            "winner": winner, "gpu_launches": int(launches),
+            "fixed_part": "per step and rank: 1 aligner launch + best_of_kernel (1 CTA) + the %d x 48 B all-gather + one "
+                          "stream synchronize and a %d-byte D2H of the gathered records" % (world, 48 * world),
+            "roofline": {"bound": "hbm", "achieved": a_bytes / (ms / steps * 1e-3) / 1e9 / world, "peak": peak,
+                         "unit": "GB/s", "frac": a_bytes / (ms / steps * 1e-3) / 1e9 / world / peak, "traffic": None,
+                         "kernel": "icp_fused2_kernel", "note": "per GPU; 30 iterations per alignment: issue-bound"},
+            "generation_seconds_max_rank": float(mx[3])}
 
 
 def parity_against_cpu(gpu, cpu):
@@ -372,85 +607,18 @@ def cpu_baseline(sp, gpu_results=None):
 
 # ----------------------------------------------------------------------------------------------- verification
 def run_verify(args):
-    """Sharded loop-closure verification (config 4 shape): one query local map against n_cand candidate local
-    maps x n_guess initial guesses, candidates split contiguously over the ranks, one all-gather of the 32-byte
-    per-shard best records (torch.distributed / NCCL), deterministic best-of on every rank."""
+    """--workload verify: the sharded loop-closure verification alone (the `verify` sub-record of the default line)"""
     import torch
     import torch.distributed as dist
-
-    from srrg2_laser_slam_2d_b200 import Gates, Handle, default_params
-    from srrg2_laser_slam_2d_b200._abi import BEST_DTYPE, LS2D_FIXED, LS2D_MOVING, reduce_best
-    from srrg2_laser_slam_2d_b200.sharding import shard_range
-
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n_cand, n_guess = args.candidates, args.guesses
-    lo, hi = shard_range(n_cand, rank, world)
-    # every rank builds the same candidate set from the same seed and keeps its slice (a real deployment
-    # would hold its shard of the local maps resident); unique clouds are tiled to reach n_cand
-    uniq = min(n_cand, args.unique)
-    sp = make_workload(uniq, 0xBEEF, str(dev), loop=True)
-    rng = np.random.default_rng(1)
-    guesses = (sp.gt_xyt[0][None, None, :] + rng.uniform(-0.15, 0.15, (n_cand, n_guess, 3))).astype(np.float32)
-    cand_ids = (np.arange(n_cand) % uniq).astype(np.int32)
-    h = Handle(local_rank, default_params(**LOOP))
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    h.set_stream(stream.cuda_stream)
-    fp, fo = torch.from_numpy(sp.fixed_pts).to(dev), torch.from_numpy(sp.fixed_off).to(dev)
-    mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
-    h.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), uniq, 1081)
-    h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), uniq, 1081)
-    cand = torch.from_numpy(cand_ids[lo:hi].copy()).to(dev)
-    gs = torch.from_numpy(guesses[lo:hi].copy()).to(dev)
-    BW = BEST_DTYPE.itemsize // 4
-    best = torch.zeros(BW, dtype=torch.int32, device=dev)
-    gathered = torch.zeros(BW * world, dtype=torch.int32, device=dev)
-    gates = Gates(300, 0.1, 0.8)
-
-    def step():
-        h.verify_dev(0, cand.data_ptr(), hi - lo, gs.data_ptr(), n_guess, gates, lo, best.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, best)
-        else:
-            gathered.copy_(best)
-
-    for _ in range(args.warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    rec = np.frombuffer(gathered.cpu().numpy().tobytes(), dtype=BEST_DTYPE)
-    winner = reduce_best(rec)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rec = measure_verify(args, torch, dist, rank, local_rank, world)
     if rank == 0:
-        n_align = n_cand * n_guess
-        print(json.dumps({
-            "metric": "verified candidate alignments/sec (1081 beams, 30 GN iters)",
-            "value": n_align * args.steps / (float(ms[0]) * 1e-3), "unit": "alignments/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms[0]) / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "loop-closure verification: 1 query x %d candidates x %d guesses, 30 GN iterations, "
-                                   "loop-closure parameter set (config 4 shape)" % (n_cand, n_guess),
-                       "unique_candidate_clouds": uniq, "collective": "all_gather of %d x 48 B" % world},
-            "winner": {"candidate": int(winner["candidate"]), "guess": int(winner["guess"]),
-                       "n_inliers": int(winner["n_inliers"])},
-            "gpu_launches": int(h.launch_count),
-        }))
+        rec.update({"warmup": max(args.warmup, 3), "higher_is_better": True, "vs_baseline": None, "dtype": "f32",
+                    "data": "synthetic"})
+        print(json.dumps(rec))
     if world > 1:
         dist.destroy_process_group()
 
@@ -647,56 +815,17 @@ def run_multi(args):
 
 # ----------------------------------------------------------------------------------------------- tracker step
 def run_track(args):
-    """The tracker's frame step with raw scans as the wire format: per frame 1081 ranges
-    (4.3 KB) + a local-map id + the predicted pose go to the device, 80 B come back; the local maps are resident."""
+    """--workload track: the tracker's frame step from RAW scans alone (the `e2e_track` sub-record of the default line)"""
     import torch
-
-    from srrg2_laser_slam_2d_b200 import Handle, default_params
-    from srrg2_laser_slam_2d_b200._abi import RESULT_DTYPE, default_scan_params
-    from srrg2_laser_slam_2d_b200.synthetic import make_raw_scans
-
     rank, local_rank, world = dist_env()
     if rank != 0:
         return
     torch.cuda.set_device(local_rank)
-    n = args.pairs
-    raw = make_raw_scans(n, seed=0xC0FFEE, device="cuda:%d" % local_rank)
-    sp_map = default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=0.0)
-    sp = default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=args.voxel)
-    h = Handle(local_rank, default_params(**TRACK))
-    # resident local maps: the full-resolution clouds of the scans taken at P * delta (set 2)
-    h.preprocess_scans_to_set(2, sp_map, raw.moving_ranges)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-    ranges, ids = pin(raw.fixed_ranges), pin(np.arange(n, dtype=np.int32))
-    robots, init = pin(np.zeros((n, 3), np.float32)), pin(np.zeros((n, 3), np.float32))
-    out = torch.zeros(n * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(RESULT_DTYPE)
-    for _ in range(args.warmup):
-        h.track_batch(sp, ranges, 2, ids, robots, init, out)
-    torch.cuda.synchronize()
-    l0 = h.launch_count
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        h.track_batch(sp, ranges, 2, ids, robots, init, out)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    clk = clocks.stop()
-    err = np.abs(np.stack([out["x"], out["y"], out["theta"]], 1) - raw.gt_xyt)
-    print(json.dumps({
-        "metric": "tracked frames/sec (raw 1081-beam scan -> pose; pre-process + clip + 10 GN iters)",
-        "value": n * args.steps / dt, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "tracker frame step from raw scans: %d frames x 1081 beams, voxelize %.3f, resident "
-                               "local maps, tracking parameter set" % (n, args.voxel), "frames_per_step": n,
-                   "success_rate": float((out["status"] == 0).mean()),
-                   "median_abs_pose_error": [float(v) for v in np.median(err, 0)]},
-        "e2e": {"value": n * args.steps / dt, "unit": "frames/s",
-                "h2d_bytes_per_step": int(ranges.nbytes + ids.nbytes + robots.nbytes + init.nbytes),
-                "d2h_bytes_per_step": int(out.nbytes)},
-        "gpu_launches": int(h.launch_count - l0), "clocks": clk,
-    }))
+    rec = measure_track(torch, local_rank, args.pairs, args)
+    rec.update({"metric": "tracked frames/sec (raw 1081-beam scan -> pose; pre-process + clip + 10 GN iters)", "n_gpus": 1,
+                "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic"})
+    print(json.dumps(rec))
 
 
 def main():
@@ -708,9 +837,11 @@ def main():
     ap.add_argument("--workload", choices=["align", "verify", "track", "allpairs", "multi"], default="align")
     ap.add_argument("--pairs", type=int, default=4096)
     ap.add_argument("--beams", type=int, default=1081, help="align: beams per scan = canvas columns (headline: 1081)")
-    ap.add_argument("--candidates", type=int, default=65536)
+    ap.add_argument("--verify-candidates", type=int, default=65536,
+                    help="candidates of the sharded verification sub-record (0: skip it)")
     ap.add_argument("--guesses", type=int, default=8)
-    ap.add_argument("--unique", type=int, default=4096)
+    ap.add_argument("--unique", type=int, default=4096, help="allpairs: distinct map clouds")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back launches for the sustained sub-record")
     ap.add_argument("--maps", type=int, default=20000, help="allpairs: local maps")
     ap.add_argument("--map-points", type=int, default=8192, help="allpairs: points per local map")
     ap.add_argument("--radius", type=float, default=2.0, help="allpairs: candidate radius over the map positions")

@@ -500,6 +500,16 @@ class Handle:
                                         candidate_base, _ptr(best), _ptr(allr)))
         return (best[0], allr) if want_all else best[0]
 
+    def verify_sharded_nccl(self, query_id: int, cand_ptr, n_cand: int, guesses_ptr: int, n_guess: int, gates: Gates,
+                            candidate_base: int, nccl_comm_ptr: int, n_ranks: int):
+        """ls2d_verify_dev on this rank's shard + all-gather of the 48-byte records over the caller's ncclComm_t +
+        the deterministic best-of: every rank returns the same global winner (device-resident inputs)"""
+        best = np.zeros(1, BEST_DTYPE)
+        self._check(self._L.ls2d_verify_sharded_nccl(self._h, query_id, C.c_void_p(cand_ptr or 0), n_cand,
+                                                     C.c_void_p(guesses_ptr), n_guess, C.byref(gates), candidate_base,
+                                                     C.c_void_p(nccl_comm_ptr), n_ranks, _ptr(best)))
+        return best[0]
+
     def verify_pairs(self, fixed_ids, moving_ids, guesses_xyt, group_offsets, gates: Gates, want_all: bool = False):
         """all-pairs search: one ls2d_best per group of consecutive pairs (group_offsets: CSR over the pairs)"""
         fid, mid, off = _i32(fixed_ids), _i32(moving_ids), _i32(group_offsets)

@@ -819,6 +819,7 @@ int ls2d_reduce_best(const ls2d_best* rec, int32_t n, ls2d_best* out) {
   memset(&b, 0, sizeof(b));
   b.candidate = -1;
   b.guess     = -1;
+  b.c         = 1.f;  // "nothing accepted" carries the identity, like best_of_kernel's empty record
   for (int i = 0; i < n; ++i) {
     const ls2d_best& r = rec[i];
     if (r.candidate < 0 || r.n_inliers <= 0) continue;

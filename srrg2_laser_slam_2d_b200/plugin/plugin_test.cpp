@@ -8,6 +8,7 @@
 //                                                 n_scans, n_beams; float angle_min, angle_max; float ranges[]
 // Binary layout of <in.bin>: int32 n_pairs, int32 n_guess, float sensor_in_robot[3]; then per pair:
 //   int32 n_fixed, n_moving; float fixed[n_fixed*4]; float moving[n_moving*4]; float init[n_guess*3].
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -291,6 +292,44 @@ static void writeResult(std::ofstream& os, const Vector3f& est, int status, floa
   os.write((const char*) i, sizeof(i));
 }
 
+// (GPU) single-pair latency of MultiAligner2D::compute() -- the reference's real tracker use: one compute() per frame
+// (apps/visual_test_tracker_2d.cpp:167-179).  Every call stages the two clouds, uploads them, runs the aligner and
+// reads the result and the last correspondence list back; prints one JSON line (microseconds per call).
+static int latency(const std::string& config, const std::string& name, const std::string& in, int reps) {
+  ConfigurableManager m;
+  m.read(config);
+  PairsFile f = readPairs(in);
+  identityPlatformFor(m, geometry2d::v2t(Vector3f(f.sensor[0], f.sensor[1], f.sensor[2])));
+  MultiAligner2DPtr aligner = m.getByName<MultiAligner2D>(name);
+  if (!aligner) throw std::runtime_error("no MultiAligner2D named " + name);
+  std::vector<double> us;
+  int ok = 0;
+  for (int r = -3; r < reps; ++r) {  // three untimed warm-up calls (context, kernel load, buffer growth)
+    const int p = ((r % f.n_pairs) + f.n_pairs) % f.n_pairs;
+    PropertyContainerDynamic fixed_scene, moving_scene;
+    fixed_scene.setCloud("points", &f.fixed[p]);
+    moving_scene.setCloud("points", &f.moving[p]);
+    const auto t0 = std::chrono::steady_clock::now();
+    aligner->setFixed(&fixed_scene);
+    aligner->setMoving(&moving_scene);
+    aligner->setMovingInFixed(f.guesses[p][0]);
+    aligner->compute();
+    const auto t1 = std::chrono::steady_clock::now();
+    if (r >= 0) {
+      us.push_back(std::chrono::duration<double, std::micro>(t1 - t0).count());
+      ok += aligner->status() == MultiAligner2D::Success;
+    }
+  }
+  std::sort(us.begin(), us.end());
+  double mean = 0;
+  for (double v : us) mean += v;
+  mean /= (double) us.size();
+  std::printf("{\"calls\": %d, \"success\": %d, \"us_median\": %.1f, \"us_mean\": %.1f, \"us_min\": %.1f, \"us_p90\": %.1f, "
+              "\"points\": %zu}\n",
+              reps, ok, us[us.size() / 2], mean, us.front(), us[us.size() * 9 / 10], f.fixed[0].size());
+  return 0;
+}
+
 static int align(const std::string& config, const std::string& name, const std::string& in, const std::string& out) {
   ConfigurableManager m;
   m.read(config);
@@ -526,13 +565,14 @@ int main(int argc, char** argv) {
   try {
     const std::string cmd = argc > 1 ? argv[1] : "";
     if (cmd == "selftest") return selftest();
+    if (cmd == "latency" && argc == 6) return latency(argv[2], argv[3], argv[4], std::atoi(argv[5]));
     if (cmd == "parse" && argc == 3) return parse(argv[2]);
     if (cmd == "align" && argc == 6) return align(argv[2], argv[3], argv[4], argv[5]);
     if (cmd == "verify" && argc == 6) return verify(argv[2], argv[3], argv[4], argv[5]);
     if (cmd == "multi" && argc == 6) return multi(argv[2], argv[3], argv[4], argv[5]);
     if (cmd == "map" && argc == 5) return map(std::atoi(argv[2]), argv[3], argv[4]);
     if (cmd == "scan" && argc == 5) return scan((float) std::atof(argv[2]), argv[3], argv[4]);
-    std::fprintf(stderr, "usage: plugin_test selftest | parse <config> | align|verify <config> <name> <in> <out>\n");
+    std::fprintf(stderr, "usage: plugin_test selftest | parse <config> | align|verify <config> <name> <in> <out> | latency <config> <name> <in> <reps>\n");
     return 2;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "plugin_test: %s\n", e.what());
