@@ -388,8 +388,14 @@ int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ra
  * halves), bit 17 = the contributions are accumulated with fused multiply-adds (oracle decision D18).  This is
  * the value ORC_SUM_TREE takes as tree_threads.  Negative: ls2d_error. */
 int ls2d_reduction_shape(const ls2d_params* p, int32_t max_points);
+/* the same for the scoring pass (ls2d_score_batch), which has a kernel of its own for clouds of up to 1152 points */
+int ls2d_score_reduction_shape(const ls2d_params* p, int32_t max_points);
 /* the same for the multi-slice aligner (ls2d_align_multi), whatever the cloud sizes */
 int ls2d_multi_reduction_threads(void);
+/* device self-test: the kernels evaluate sqrtf on range-gated operands with the five-instruction core of __fsqrt_rn
+ * (no operand-class test; csrc/ls2d_math.cuh fsqrt_gated); compares it with __fsqrt_rn on EVERY binary32 value in
+ * [lo, hi] (lo > 2^-100) and reports how many were checked and how many differ (must be 0) */
+int ls2d_selftest_gated_sqrt(ls2d_handle* h, float lo, float hi, int64_t* n_checked, int64_t* n_mismatch);
 /* kernels launched by this handle since creation */
 int64_t ls2d_launch_count(const ls2d_handle* h);
 

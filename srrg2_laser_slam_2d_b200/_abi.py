@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libls2d.so")
+LIB_PATH = os.environ.get("LS2D_LIB") or os.path.join(_HERE, "libls2d.so")  # LS2D_LIB: A/B builds (bench plumbing)
 MATHCHECK_PATH = os.path.join(_HERE, "libls2d_mathcheck.so")
 
 LS2D_FIXED, LS2D_MOVING = 0, 1
@@ -93,7 +93,7 @@ EXPORTS = [
     "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
     "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
     "ls2d_clip_scenes_to_set", "ls2d_track_batch", "ls2d_verify_pairs", "ls2d_verify_pairs_dev",
-    "ls2d_clip_scenes_voxelized", "ls2d_multi_reduction_threads", "ls2d_classify_correspondences",
+    "ls2d_clip_scenes_voxelized", "ls2d_multi_reduction_threads", "ls2d_classify_correspondences", "ls2d_score_reduction_shape", "ls2d_selftest_gated_sqrt",
 ]
 
 _lib = None
@@ -152,6 +152,8 @@ def load():
     L.ls2d_clip_scenes_to_set.argtypes = [vp, C.c_int, vp, vp, vp, i32, C.c_int]
     L.ls2d_track_batch.argtypes = [vp, SP, vp, i32, i32, C.c_int, vp, vp, vp, vp]
     L.ls2d_reduction_shape.argtypes = [PP, i32]
+    L.ls2d_score_reduction_shape.argtypes = [PP, i32]
+    L.ls2d_selftest_gated_sqrt.argtypes = [vp, f32, f32, C.POINTER(i64), C.POINTER(i64)]
     L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
     _lib = L
     return L
@@ -214,6 +216,15 @@ def reduction_threads(max_points: int, canvas_cols: int = 1081, params: Params |
     shape = load().ls2d_reduction_shape(C.byref(p), max_points)
     if shape < 0:
         raise Ls2dError(f"ls2d_reduction_shape: {shape}")
+    return shape
+
+
+def score_reduction_threads(max_points: int, canvas_cols: int = 1081, params: Params | None = None) -> int:
+    """the same for the scoring pass (ls2d_score_batch)"""
+    p = params if params is not None else default_params(canvas_cols=canvas_cols)
+    shape = load().ls2d_score_reduction_shape(C.byref(p), max_points)
+    if shape < 0:
+        raise Ls2dError(f"ls2d_score_reduction_shape: {shape}")
     return shape
 
 
@@ -388,6 +399,12 @@ class Handle:
         self._check(self._L.ls2d_find_correspondences(self._h, fixed_id, moving_id, _ptr(xyt), _ptr(fi), _ptr(mi),
                                                       C.byref(n)))
         return fi[:n.value].copy(), mi[:n.value].copy()
+
+    def selftest_gated_sqrt(self, lo: float, hi: float):
+        """(values checked, mismatches) of the kernels' gated square root against __fsqrt_rn over [lo, hi]"""
+        n, bad = C.c_int64(0), C.c_int64(0)
+        self._check(self._L.ls2d_selftest_gated_sqrt(self._h, lo, hi, C.byref(n), C.byref(bad)))
+        return n.value, bad.value
 
     def classify_correspondences(self, fixed_id: int, moving_id: int, moving_in_fixed, fixed_idx, moving_idx,
                                  fixed_set: int = LS2D_FIXED, moving_set: int = LS2D_MOVING):

@@ -83,6 +83,7 @@ dev_params translate(const ls2d_params& p) {
   d.cam                     = make_polar_cam(p.canvas_cols, p.angle_col_min, p.angle_col_max);
   d.range_min               = p.range_min;
   d.range_max               = p.range_max;
+  d.gate2                   = make_range_gate2(p.range_min, p.range_max);
   d.point_distance          = p.point_distance;
   d.normal_cos              = p.normal_cos;
   d.tau                     = p.cauchy_chi_threshold;
@@ -110,43 +111,37 @@ dev_params translate(const ls2d_params& p) {
 // iteration records one alignment may write (include/ls2d.h: iter_stats)
 int iters_per_pair(const ls2d_params& p) { return p.max_iterations * (p.enable_inlier_only_runs ? 2 : 1); }
 
-// device copy of the projector's rounding edges (second tier of the column decision, ls2d_math.cuh)
-int upload_edges(ls2d_handle* h) {
-  const polar_cam& key = h->edge_key;  // the table depends on the camera constants only: re-use it across set_params
-  if (h->d_edge.p && key.cols == h->dp.cam.cols && key.K00 == h->dp.cam.K00 && key.K01 == h->dp.cam.K01) {
-    h->dp.cam.edge = static_cast<const polar_edge*>(h->d_edge.p);
-    return LS2D_OK;
+// table of a camera's rounding edges as the kernels read it: [cols + 1] polar_edge (binary64 directions, second tier
+// of the aligner kernels) followed by [cols + 1] polar_edge_f (binary32, the scoring kernel stages it in shared memory)
+size_t edge_table_bytes(const polar_cam& cam) { return ((size_t) cam.cols + 1) * (sizeof(polar_edge) + sizeof(polar_edge_f)); }
+
+int upload_edge_table(ls2d_handle* h, scratch& buf, polar_cam& key, polar_cam& cam) {
+  if (!(buf.p && key.cols == cam.cols && key.K00 == cam.K00 && key.K01 == cam.K01)) {
+    const size_t n = (size_t) cam.cols + 1;
+    std::vector<unsigned char> host(edge_table_bytes(cam));
+    fill_polar_edges(cam, reinterpret_cast<polar_edge*>(host.data()));
+    fill_polar_edges_f(cam, reinterpret_cast<polar_edge_f*>(host.data() + n * sizeof(polar_edge)));
+    key.cols = 0;
+    int rc   = reserve(buf, host.size());
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(buf.p, host.data(), host.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));  // `host` is pageable and dies here
+    key = cam;
   }
-  h->edge_key.cols = 0;
-  std::vector<polar_edge> edges((size_t) h->dp.cam.cols + 1);
-  fill_polar_edges(h->dp.cam, edges.data());
-  const size_t bytes = edges.size() * sizeof(polar_edge);
-  h->dp.cam.edge = nullptr;
-  int rc = reserve(h->d_edge, bytes);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(h->d_edge.p, edges.data(), bytes, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));  // `edges` is pageable and dies here
-  h->dp.cam.edge = static_cast<const polar_edge*>(h->d_edge.p);
-  h->edge_key    = h->dp.cam;
+  cam.edge = static_cast<const polar_edge*>(buf.p);
   return LS2D_OK;
+}
+
+// device copy of the projector's rounding edges (second tier of the column decision, ls2d_math.cuh); the table depends
+// on the camera constants only and is re-used across ls2d_set_params
+int upload_edges(ls2d_handle* h) {
+  h->dp.cam.edge = nullptr;
+  return upload_edge_table(h, h->d_edge, h->edge_key, h->dp.cam);
 }
 
 // edge table of slice `slot` of the multi-slice aligner: uploaded when the slice's camera changes
 int slice_edges(ls2d_handle* h, int slot, polar_cam& cam) {
-  polar_cam& key = h->edge_slice_key[slot];
-  if (!(h->d_edge_slice[slot].p && key.cols == cam.cols && key.K00 == cam.K00 && key.K01 == cam.K01)) {
-    std::vector<polar_edge> edges((size_t) cam.cols + 1);
-    fill_polar_edges(cam, edges.data());
-    const size_t bytes = edges.size() * sizeof(polar_edge);
-    key.cols = 0;
-    int rc = reserve(h->d_edge_slice[slot], bytes);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h->d_edge_slice[slot].p, edges.data(), bytes, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    key = cam;
-  }
-  cam.edge = static_cast<const polar_edge*>(h->d_edge_slice[slot].p);
-  return LS2D_OK;
+  return upload_edge_table(h, h->d_edge_slice[slot], h->edge_slice_key[slot], cam);
 }
 
 bool ready(const ls2d_handle* h) { return h->sets[0].pts && h->sets[1].pts && h->sets[0].off && h->sets[1].off; }
@@ -1187,6 +1182,33 @@ int ls2d_multi_reduction_threads(void) { return multi_reduction_threads(); }
 int ls2d_reduction_shape(const ls2d_params* p, int32_t max_points) {
   if (!p || !params_valid(*p) || max_points < 0) return LS2D_ERR_INVALID;
   return icp_reduction_shape(translate(*p), p->single_rounding_accumulation != 0, max_points);
+}
+
+int ls2d_score_reduction_shape(const ls2d_params* p, int32_t max_points) {
+  if (!p || !params_valid(*p) || max_points < 0) return LS2D_ERR_INVALID;
+  const dev_params dp = translate(*p);
+  const int shape     = score_reduction_shape(nullptr, dp, p->single_rounding_accumulation != 0, max_points);
+  if (shape >= 0) return shape;
+  dev_params gn = dp;  // the scoring pass never runs the general kernel: one linearisation of the size's aligner kernel
+  gn.algorithm = LS2D_ALGORITHM_GN, gn.inlier_only_runs = 0, gn.termination_epsilon = 0.f;
+  return icp_reduction_shape(gn, p->single_rounding_accumulation != 0, max_points);
+}
+
+int ls2d_selftest_gated_sqrt(ls2d_handle* h, float lo, float hi, int64_t* n_checked, int64_t* n_mismatch) {
+  if (!h || !n_checked || !n_mismatch || !(lo > 0x1p-100f) || !(hi >= lo) || !(hi <= 3.0e38f)) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = reserve(h->d_misc, 8))) return rc;
+  CU(cudaMemsetAsync(h->d_misc.p, 0, 8, h->stream));
+  unsigned lo_bits, hi_bits;
+  memcpy(&lo_bits, &lo, 4), memcpy(&hi_bits, &hi, 4);
+  if ((rc = launch_selftest_sqrt(h, lo_bits, hi_bits, (unsigned long long*) h->d_misc.p))) return rc;
+  unsigned long long bad = 0;
+  CU(cudaMemcpyAsync(&bad, h->d_misc.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *n_checked  = (int64_t) hi_bits - (int64_t) lo_bits + 1;
+  *n_mismatch = (int64_t) bad;
+  return LS2D_OK;
 }
 
 int64_t ls2d_launch_count(const ls2d_handle* h) { return h ? h->launches : 0; }

@@ -14,6 +14,7 @@ constexpr int MAX_SLICES = LS2D_MAX_SLICES;
 struct dev_params {
   polar_cam cam;
   float range_min, range_max;
+  range_gate2 gate2;  // the same gate on the squared range (ls2d_math.cuh)
   float point_distance, normal_cos;
   float tau, inv_tau;  // Cauchy threshold (<= 0: none) and 1/tau
   float damping;

@@ -87,6 +87,8 @@ int launch_icp(ls2d_handle* h, const align_args& a);
 int icp_reduction_shape(const dev_params& dp, bool single_rounding, int max_points);
 int launch_general(ls2d_handle* h, const align_args& a, int max_points);
 int launch_score(ls2d_handle* h, const align_args& a);
+// shape of the scoring pass's reduction when score_kernel serves these parameters, else -1 (the aligner's shape)
+int score_reduction_shape(const ls2d_handle* h_or_null, const dev_params& dp, bool single_rounding, int max_points);
 
 int launch_multi(ls2d_handle* h, const multi_args& a, const int* cols);
 int multi_reduction_threads();
@@ -96,6 +98,7 @@ int launch_correspond(ls2d_handle* h, const correspond_args& a);
 int launch_clip(ls2d_handle* h, const clip_args& a, int n);
 int launch_merge(ls2d_handle* h, const merge_args& a);
 int launch_classify(ls2d_handle* h, const classify_args& a, const int* off_f, int cloud_f, const int* off_m, int cloud_m);
+int launch_selftest_sqrt(ls2d_handle* h, unsigned lo_bits, unsigned hi_bits, unsigned long long* n_mismatch_dev);
 int launch_best_of(ls2d_handle* h, const ls2d_result* res, int n, int n_guess, const ls2d_gates& g, int candidate_base,
                    ls2d_best* out);
 int launch_best_of_groups(ls2d_handle* h, const ls2d_result* res, const int* group_off, int n_groups,

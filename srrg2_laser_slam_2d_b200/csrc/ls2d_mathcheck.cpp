@@ -54,6 +54,10 @@ void ls2d_host_polar_column_tiered_n(int cols, float amin, float amax, const flo
     col[i] = (c < 0 || c >= cols) ? -1 : c;
   }
 }
+void ls2d_host_range_gate2(float range_min, float range_max, float* lo, float* hi) {
+  const ls2d::range_gate2 g = ls2d::make_range_gate2(range_min, range_max);
+  *lo = g.lo, *hi = g.hi;
+}
 float ls2d_host_edge_tol(int cols, float amin, float amax) { return ls2d::make_polar_cam(cols, amin, amax).edge_tol; }
 float ls2d_host_margin(int cols, float amin, float amax) { return ls2d::make_polar_cam(cols, amin, amax).margin; }
 }

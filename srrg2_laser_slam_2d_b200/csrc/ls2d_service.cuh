@@ -275,6 +275,20 @@ __global__ void classify_kernel(const dev_params P, const classify_args A, const
 }
 
 // ---------------------------------------------------------------------------------------------------
+// self-test of fsqrt_gated (ls2d_math.cuh) against __fsqrt_rn over every binary32 value in [lo_bits, hi_bits]
+__global__ void selftest_sqrt_kernel(unsigned lo_bits, unsigned hi_bits, unsigned long long* n_mismatch) {
+  unsigned long long bad = 0;
+  const unsigned long long n = (unsigned long long) hi_bits - lo_bits + 1ull;
+  for (unsigned long long k = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; k < n;
+       k += (unsigned long long) gridDim.x * blockDim.x) {
+    const float a = u2f(lo_bits + (unsigned) k);
+    bad += f2u(fsqrt_gated(a)) != f2u(__fsqrt_rn(a));
+  }
+  bad = __reduce_add_sync(0xffffffffu, (unsigned) bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_mismatch, bad);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // acceptance gates (L0.json:627-634) + deterministic best-of, one CTA.
 __device__ __forceinline__ bool accepts(const ls2d_result& r, const ls2d_gates& g) {
   if (r.status != LS2D_STATUS_SUCCESS) return false;

@@ -126,7 +126,4 @@ int icp_reduction_shape(const dev_params& dp, bool single_rounding, int max_poin
   return s.threads | (s.kind == 3 ? 1 << 16 : 0) | (fused_accumulation(s, single_rounding) ? 1 << 17 : 0);
 }
 
-// until the TMA-fed scoring kernel takes over (ls2d_tu_score.cu), the scoring pass is one linearisation of the aligner
-int launch_score(ls2d_handle* h, const align_args& a) { return launch_icp(h, a); }
-
 }  // namespace ls2d

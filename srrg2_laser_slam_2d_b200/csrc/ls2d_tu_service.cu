@@ -52,6 +52,13 @@ int launch_classify(ls2d_handle* h, const classify_args& a, const int* off_f, in
   return LS2D_OK;
 }
 
+int launch_selftest_sqrt(ls2d_handle* h, unsigned lo_bits, unsigned hi_bits, unsigned long long* n_mismatch_dev) {
+  selftest_sqrt_kernel<<<h->sm_count * 8, 256, 0, h->stream>>>(lo_bits, hi_bits, n_mismatch_dev);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
 int launch_best_of(ls2d_handle* h, const ls2d_result* res, int n, int n_guess, const ls2d_gates& g, int candidate_base,
                    ls2d_best* out) {
   best_of_kernel<<<1, 1024, 0, h->stream>>>(res, n, n_guess, g, candidate_base, out);

@@ -275,22 +275,6 @@ def test_status_codes_match_the_oracle(handle_factory, oracle):
     assert (g["status"] == 3).all() and (g["iterations"] == 0).all() and (g["x"] == 0).all()
 
 
-def test_score_batch_is_the_first_linearisation(handle_factory, oracle):
-    sp = make_scan_pairs(16, n_beams=721, seed=12)
-    kw = dict(canvas_cols=721, normal_cos=0.9)
-    h = handle_factory(default_params(**kw))
-    upload(h, sp)
-    s = h.score_batch(sp.gt_xyt)
-    prm = oracle.default_params(max_iterations=1, **kw)
-    o, oi = oracle.align_batch(prm, sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.gt_xyt,
-                               sum_mode=oracle.SUM_TREE, tree_threads=reduction_threads(721, kw["canvas_cols"]))
-    for f in ("n_corr", "n_inliers", "n_kernelized"):
-        assert np.array_equal(s[f], o[f])
-    assert np.array_equal(gu.bits(s["chi_inliers"]), gu.bits(o["chi_inliers"]))
-    assert np.array_equal(gu.bits(s["H"]), gu.bits(o["H"]))
-    assert np.array_equal(s["x"], sp.gt_xyt[:, 0]) and np.array_equal(s["y"], sp.gt_xyt[:, 1])   # pose untouched
-
-
 # ------------------------------------------------------------------ loop-closure verification
 @pytest.mark.parametrize("n_beams", [721, 1081])
 def test_verify_gates_and_best_of_match_the_oracle(handle_factory, oracle, n_beams):
