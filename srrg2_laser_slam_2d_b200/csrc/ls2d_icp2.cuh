@@ -407,33 +407,40 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
       const float Wtx = sm::ld_f32<BC_WTX>(bca), Wty = sm::ld_f32<BC_WTY>(bca);
       f2 pc[PPT];
       int col[PPT];
-      bool near[PPT], up[PPT];
+      bool near[PPT], up[PPT], in[PPT];
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
         const f2 ra = mul2s(mk2(Lc, Ls), mp[j].x), rb2 = mul2s(mk2(-Ls, Lc), mp[j].y);
         pc[j]       = add2(mk2(fadd(ra.x, rb2.x), fadd(ra.y, rb2.y)), mk2(Wtx, Wty));
         const f2 pq = mul2(pc[j], pc[j]);
-        const float rho = fsqrt(fadd(pq.x, pq.y));
-        rb[j]       = f2u(rho);
+        const float a = fadd(pq.x, pq.y);
+        in[j]       = a >= P.gate2.lo && a <= P.gate2.hi;  // the range gate, taken on the squared range (ls2d_math.cuh)
+        rb[j]       = f2u(fsqrt_gated(a));                 // exact wherever the gate is open
         col[j]      = polar_column_fast2(P.cam, pc[j].y, pc[j].x, near[j], up[j]);
-        near[j]     = near[j] && !(rho < P.range_min || rho > P.range_max);
+        near[j]     = near[j] && in[j];
       }
       bool any_near = false;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) any_near |= near[j];
-      if (any_near) {  // rare: second tier (side of the rounding edge), then the exact atan2f
+      if (any_near) {  // rare: second tier (side of the rounding edge, binary32), then the exact atan2f
+        const polar_edge_f* edges = reinterpret_cast<const polar_edge_f*>(P.cam.edge + C + 1);
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
           if (near[j]) {
-            bool undecided;
-            const int c2 = polar_column_edge(P.cam, pc[j].y, pc[j].x, u2f(rb[j]), col[j] + (up[j] ? 1 : 0), undecided);
-            col[j]       = undecided ? polar_column_exact(P.cam, pc[j].y, pc[j].x) : c2;
+            bool undecided = true;
+            const int kb   = col[j] + (up[j] ? 1 : 0);
+            int c2         = -1;
+            if ((unsigned) kb <= (unsigned) C) {
+              polar_edge_f ef;
+              ef.c = __ldg(&edges[kb].c), ef.s = __ldg(&edges[kb].s);
+              c2   = polar_column_edge_f(P.cam, pc[j].y, pc[j].x, u2f(rb[j]), kb, ef, undecided);
+            }
+            col[j] = undecided ? polar_column_exact(P.cam, pc[j].y, pc[j].x) : c2;
           }
       }
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {
-        const float rho = u2f(rb[j]);
-        const bool ok   = !(rho < P.range_min || rho > P.range_max) && (unsigned) col[j] < (unsigned) C;
+        const bool ok   = in[j] && (unsigned) col[j] < (unsigned) C;
         za[j]           = zb + 4u * (ok ? col[j] : C);
         rb[j]           = ok ? rb[j] : 0u;  // never equals the dummy cell's EMPTY
         if (ok && sm::atom_min_u32<0>(za[j], rb[j]) == rb[j]) sm::st_u32<BC_TIE>(bca, 1u);  // an equal rho was there

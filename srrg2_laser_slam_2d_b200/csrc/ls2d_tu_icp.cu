@@ -31,7 +31,8 @@ shape pick_shape(int max_points) {
 // on canvases narrower than its stride; everything else runs the run-time-shaped kernels
 shape resolve_shape(const dev_params& dp, int max_points) {
   shape s = pick_shape(max_points);
-  if (s.kind == 3 && (dp.cam.cols >= s.cs || dp.factor != LS2D_FACTOR_PLANE2PLANE)) {
+  // (its projection takes the range gate on the squared range and a square root that is exact above 1e-30 m^2)
+  if (s.kind == 3 && (dp.cam.cols >= s.cs || dp.factor != LS2D_FACTOR_PLANE2PLANE || dp.gate2.lo < 1.0e-30f)) {
     s = s.cs == 768 ? shape{256, 3, 3, 0, 0} : shape{288, 4, 4, 0, 0};
   }
   if (s.kind == 0 && icp_smem_bytes(dp.cam.cols, s.threads, s.ppt) > SMEM_LIMIT) s = {512, 0, 2, 1, 0};
