@@ -22,6 +22,15 @@ constexpr int NSUM               = 11;  // H00 H01 H02 H11 H12 H22 b0 b1 b2 chi_
 constexpr int RED_STRIDE         = 12;  // + packed counts
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+// a point that is read exactly once by the kernel: do not let the stream of clouds evict the small tables (rounding
+// edges of the projector) that live in the few KB of L1 left beside the shared-memory carve-out
+__device__ __forceinline__ float4 ldg4_once(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
 
 // pose k of an array in the handle's pose format (include/ls2d.h): stride 3 = (x, y, theta) rebuilt with the glibc
 // cosf / sinf copies, stride 4 = the caller's Isometry2f content, used verbatim

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
     constexpr int J = decltype(jc)::value;
     const int i     = tid + J * T;
     // lanes past the end of the cloud hold a point no pose brings inside the range gates (rho overflows to inf)
-    const float4 m  = i < nm ? ldg4(A.moving_pts + m0 + i) : make_float4(1e30f, 0.f, 0.f, 0.f);
+    const float4 m  = i < nm ? ldg4_once(A.moving_pts + m0 + i) : make_float4(1e30f, 0.f, 0.f, 0.f);
     mp[J]           = make_float2(m.x, m.y);
     sm::st_f32x2<J * T * 8>(mna, m.z, m.w);
   });
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
       int col     = C;
       rb[j]       = 0;
       if (i < nf) {
-        fp[j]           = ldg4(A.fixed_pts + f0 + i);
+        fp[j]           = ldg4_once(A.fixed_pts + f0 + i);
         const float rho = fsqrt(fadd(fmul(fp[j].x, fp[j].x), fmul(fp[j].y, fp[j].y)));
         if (!(rho < P.range_min || rho > P.range_max)) {
           const int c = polar_column(P.cam, fp[j].y, fp[j].x);
