@@ -390,8 +390,13 @@ int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ra
 int ls2d_reduction_shape(const ls2d_params* p, int32_t max_points);
 /* the same for the scoring pass (ls2d_score_batch), which has a kernel of its own for clouds of up to 1152 points */
 int ls2d_score_reduction_shape(const ls2d_params* p, int32_t max_points);
-/* the same for the multi-slice aligner (ls2d_align_multi), whatever the cloud sizes */
+/* the same for the multi-slice aligner (ls2d_align_multi): the general kernel's shape, whatever the cloud sizes ... */
 int ls2d_multi_reduction_threads(void);
+/* ... and the shape ls2d_align_multi runs for these slices: two slices whose fixed clouds hold up to 768 points, on
+ * canvases below 768 columns, that share ONE moving cloud set of up to 1536 points (the MULTI.json aligner: fixed
+ * "points_0" / "points_1", moving "points") have a register-resident kernel with a shape of its own */
+int ls2d_multi_reduction_shape(const ls2d_params* slices, int32_t n_slices, int32_t max_fixed_points,
+                               int32_t max_moving_points, int32_t shared_moving);
 /* device self-test: the kernels evaluate sqrtf on range-gated operands with the five-instruction core of __fsqrt_rn
  * (no operand-class test; csrc/ls2d_math.cuh fsqrt_gated); compares it with __fsqrt_rn on EVERY binary32 value in
  * [lo, hi] (lo > 2^-100) and reports how many were checked and how many differ (must be 0) */

@@ -93,7 +93,7 @@ EXPORTS = [
     "ls2d_find_correspondences_in", "ls2d_default_scan_params", "ls2d_preprocess_scans",
     "ls2d_preprocess_scans_to_set", "ls2d_preprocess_scans_to_set_dev", "ls2d_download_clouds",
     "ls2d_clip_scenes_to_set", "ls2d_track_batch", "ls2d_verify_pairs", "ls2d_verify_pairs_dev",
-    "ls2d_clip_scenes_voxelized", "ls2d_multi_reduction_threads", "ls2d_classify_correspondences", "ls2d_score_reduction_shape", "ls2d_selftest_gated_sqrt",
+    "ls2d_clip_scenes_voxelized", "ls2d_multi_reduction_threads", "ls2d_classify_correspondences", "ls2d_score_reduction_shape", "ls2d_selftest_gated_sqrt", "ls2d_multi_reduction_shape",
 ]
 
 _lib = None
@@ -153,6 +153,7 @@ def load():
     L.ls2d_track_batch.argtypes = [vp, SP, vp, i32, i32, C.c_int, vp, vp, vp, vp]
     L.ls2d_reduction_shape.argtypes = [PP, i32]
     L.ls2d_score_reduction_shape.argtypes = [PP, i32]
+    L.ls2d_multi_reduction_shape.argtypes = [vp, i32, i32, i32, i32]
     L.ls2d_selftest_gated_sqrt.argtypes = [vp, f32, f32, C.POINTER(i64), C.POINTER(i64)]
     L.ls2d_launch_count.argtypes, L.ls2d_launch_count.restype = [vp], i64
     _lib = L
@@ -228,8 +229,18 @@ def score_reduction_threads(max_points: int, canvas_cols: int = 1081, params: Pa
     return shape
 
 
-def multi_reduction_threads() -> int:
-    return load().ls2d_multi_reduction_threads()
+def multi_reduction_threads(slices=None, max_fixed_points: int = 0, max_moving_points: int = 0,
+                            shared_moving: bool = True) -> int:
+    """shape of the multi-slice aligner's per-slice reduction: the general kernel's (no arguments), or the one
+    ls2d_align_multi runs for these slices (list of Params), cloud sizes and moving-set sharing"""
+    if slices is None:
+        return load().ls2d_multi_reduction_threads()
+    arr = (Params * len(slices))(*slices)
+    shape = load().ls2d_multi_reduction_shape(C.cast(arr, C.c_void_p), len(slices), max_fixed_points,
+                                              max_moving_points, 1 if shared_moving else 0)
+    if shape < 0:
+        raise Ls2dError(f"ls2d_multi_reduction_shape: {shape}")
+    return shape
 
 
 def reduce_best(records: np.ndarray) -> np.ndarray:

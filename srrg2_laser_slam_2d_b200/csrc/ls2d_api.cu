@@ -530,6 +530,7 @@ static int multi_dev_impl(ls2d_handle* h, const ls2d_params* slices, const int32
     if (cols[s] > a.max_cols) a.max_cols = cols[s];
     if (f.max_points > a.max_points) a.max_points = f.max_points;
     if (m.max_points > a.max_points) a.max_points = m.max_points;
+    if (f.max_points > a.max_fixed_points) a.max_fixed_points = f.max_points;
   }
   if (a.max_cols > 0xFFFE) return LS2D_ERR_UNSUPPORTED;
   a.n_slices    = n_slices;
@@ -1178,6 +1179,27 @@ int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ra
 }
 
 int ls2d_multi_reduction_threads(void) { return multi_reduction_threads(); }
+
+int ls2d_multi_reduction_shape(const ls2d_params* slices, int32_t n_slices, int32_t max_fixed_points,
+                               int32_t max_moving_points, int32_t shared_moving) {
+  if (!slices || n_slices < 1 || n_slices > LS2D_MAX_SLICES || max_fixed_points < 0 || max_moving_points < 0)
+    return LS2D_ERR_INVALID;
+  multi_args a;
+  memset(&a, 0, sizeof(a));
+  static const polar_edge some_table = {1.0, 0.0};  // the kernel choice only asks whether a slice HAS an edge table
+  for (int s = 0; s < n_slices; ++s) {
+    if (!params_valid(slices[s])) return LS2D_ERR_INVALID;
+    a.sl[s].P          = translate(slices[s]);
+    a.sl[s].P.cam.edge = &some_table;
+    if (slices[s].canvas_cols > a.max_cols) a.max_cols = slices[s].canvas_cols;
+  }
+  a.n_slices         = n_slices;
+  a.max_points       = max_fixed_points > max_moving_points ? max_fixed_points : max_moving_points;
+  a.max_fixed_points = max_fixed_points;
+  if (!shared_moving)
+    for (int s = 1; s < n_slices; ++s) a.sl[s].moving_off = reinterpret_cast<const int*>(&some_table);  // "another set"
+  return multi_reduction_shape(a);
+}
 
 int ls2d_reduction_shape(const ls2d_params* p, int32_t max_points) {
   if (!p || !params_valid(*p) || max_points < 0) return LS2D_ERR_INVALID;

@@ -121,6 +121,7 @@ struct multi_args {
   dev_slice sl[MAX_SLICES];
   int n_slices;
   int max_cols, max_points;  // capacity of the shared z-buffer / stash
+  int max_fixed_points;      // the largest fixed cloud alone (kernel selection)
   const int* fixed_id;       // nullable: pair index
   const int* moving_id;      // nullable: pair index
   const float* init_pose;    // pose_stride floats per pair

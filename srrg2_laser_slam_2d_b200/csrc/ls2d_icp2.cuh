@@ -422,21 +422,10 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
       bool any_near = false;
 #pragma unroll
       for (int j = 0; j < PPT; ++j) any_near |= near[j];
-      if (any_near) {  // rare: second tier (side of the rounding edge, binary32), then the exact atan2f
-        const polar_edge_f* edges = reinterpret_cast<const polar_edge_f*>(P.cam.edge + C + 1);
+      if (any_near) {  // rare, out of line: second tier (side of the rounding edge, binary32), then the exact atan2f
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
-          if (near[j]) {
-            bool undecided = true;
-            const int kb   = col[j] + (up[j] ? 1 : 0);
-            int c2         = -1;
-            if ((unsigned) kb <= (unsigned) C) {
-              polar_edge_f ef;
-              ef.c = __ldg(&edges[kb].c), ef.s = __ldg(&edges[kb].s);
-              c2   = polar_column_edge_f(P.cam, pc[j].y, pc[j].x, u2f(rb[j]), kb, ef, undecided);
-            }
-            col[j] = undecided ? polar_column_exact(P.cam, pc[j].y, pc[j].x) : c2;
-          }
+          if (near[j]) col[j] = polar_column_resolve(P.cam, pc[j].y, pc[j].x, u2f(rb[j]), col[j], up[j]);
       }
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {

@@ -92,6 +92,7 @@ int score_reduction_shape(const ls2d_handle* h_or_null, const dev_params& dp, bo
 
 int launch_multi(ls2d_handle* h, const multi_args& a, const int* cols);
 int multi_reduction_threads();
+int multi_reduction_shape(const multi_args& a);  // shape launch_multi() runs for these slices (ls2d_multi_reduction_shape)
 
 int launch_project(ls2d_handle* h, const project_args& a);
 int launch_correspond(ls2d_handle* h, const correspond_args& a);

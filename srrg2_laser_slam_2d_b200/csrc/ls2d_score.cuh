@@ -113,18 +113,9 @@ __device__ __forceinline__ score_eval project_fast(const dev_params& P, float x,
   e.near        = e.near && e.in;
   return e;
 }
-// the rare proposals: side of the rounding edge's ray in binary32 against the float copy of the edge table (global,
-// L1-resident: 8.7 KB), and only inside its tolerance the operation-for-operation fdlibm atan2f
-__device__ __forceinline__ void project_slow(const dev_params& P, score_eval& e, const polar_edge_f* edges) {
-  bool undecided = true;
-  const int kb   = e.col + (e.up ? 1 : 0);
-  int c2         = -1;
-  if ((unsigned) kb <= (unsigned) P.cam.cols) {
-    polar_edge_f ef;
-    ef.c = __ldg(&edges[kb].c), ef.s = __ldg(&edges[kb].s);
-    c2   = polar_column_edge_f(P.cam, e.y, e.x, e.rho, kb, ef, undecided);
-  }
-  e.col = undecided ? polar_column_exact(P.cam, e.y, e.x) : c2;
+// the rare proposals, out of line (ls2d_math.cuh: polar_column_resolve)
+__device__ __forceinline__ void project_slow(const dev_params& P, score_eval& e) {
+  e.col = polar_column_resolve(P.cam, e.y, e.x, e.rho, e.col, e.up);
 }
 
 template <int T, int PPT, bool SENSOR, bool FUSED, int MINB>
@@ -139,7 +130,6 @@ __global__ void __launch_bounds__(T, MINB) score_kernel(const dev_params P, cons
   const unsigned zdm = sb + M.zdm();
   const unsigned tie = sb + M.tie();
   const unsigned stM = sb + M.moving();
-  const polar_edge_f* edges = reinterpret_cast<const polar_edge_f*>(P.cam.edge + C + 1);  // ls2d_api.cu: upload_edge_table
 
   // ---- one-time set-up: empty z-buffers, barriers, tie flags
   for (int k = tid; k < 3 * M.CS; k += T) sm::st_u32<0>(sb + M.zdf(0) + 4u * k, Z_EMPTY_DEPTH);  // zdf[0] | zdf[1] | zdm
@@ -201,7 +191,7 @@ __global__ void __launch_bounds__(T, MINB) score_kernel(const dev_params P, cons
     if (any_near) {
 #pragma unroll
       for (int j = 0; j < PPT; ++j)
-        if (e[j].near) project_slow(P, e[j], edges);
+        if (e[j].near) project_slow(P, e[j]);
     }
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
@@ -255,7 +245,7 @@ __global__ void __launch_bounds__(T, MINB) score_kernel(const dev_params P, cons
       if (any_near) {
 #pragma unroll
         for (int j = 0; j < PPT; ++j)
-          if (e[j].near) project_slow(P, e[j], edges);
+          if (e[j].near) project_slow(P, e[j]);
       }
 #pragma unroll
       for (int j = 0; j < PPT; ++j) {

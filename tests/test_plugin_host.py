@@ -278,7 +278,7 @@ def test_plugin_multi_slice_aligner_with_odometry_prior(exe, tmp_path, handle_fa
                            (1, {}, {})):
         g = h.align_multi(mk(default_params), [0, 2], [1, 1], init_iso, **kw)
         o, _ = oracle.align_multi_batch(mk(oracle.default_params), fixed, moving, init_iso, sum_mode=oracle.SUM_TREE,
-                                        tree_threads=multi_reduction_threads(), **okw)
+                                        tree_threads=multi_reduction_threads(mk(default_params), 721, 1442, True), **okw)
         rec = got[:, pass_]["rec"]
         assert same(rec[exact], g[exact]) is None
         assert np.array_equal(rec["theta"], g["theta"])              # movingInFixed() is the kernel's isometry itself
