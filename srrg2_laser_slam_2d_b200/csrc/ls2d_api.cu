@@ -253,10 +253,16 @@ int ls2d_destroy(ls2d_handle* h) {
   release(h->d_misc);
   release(h->d_ranges);
   release(h->d_clip);
+  release(h->d_look);
+  release(h->d_ticket);
+  release(h->d_beam);
   release(h->d_edge);
   for (scratch& e : h->d_edge_slice) release(e);
   if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  for (cudaEvent_t e : h->ev_packed)
+    if (e) cudaEventDestroy(e);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   for (cudaEvent_t e : h->ev_chunk)
     if (e) cudaEventDestroy(e);
@@ -942,7 +948,7 @@ void ls2d_default_scan_params(ls2d_scan_params* p) {
 
 // ranges_dev -> strided points + counts on the device (asynchronous)
 static int preprocess_dev(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges_dev, int32_t n_beams,
-                          int32_t n_scans, float4* out_dev, int* counts_dev) {
+                          int32_t n_scans, float4* out_dev, int* counts_dev, int* off_dev, int continues = 0) {
   if (n_beams < 1 || n_beams > 8192 || !(sp->angle_max > sp->angle_min)) return LS2D_ERR_INVALID;
   scan_dev_params P;
   // _processLaserMessage, raw_data_preprocessor_projective_2d.cpp:83-90 (single binary32 operations)
@@ -956,17 +962,19 @@ static int preprocess_dev(ls2d_handle* h, const ls2d_scan_params* sp, const floa
   P.inv_res              = sp->voxelize_resolution > 0.f ? 1.f / sp->voxelize_resolution : 0.f;
   P.min_points           = sp->normal_min_points;
   P.n_beams              = n_beams;
-  P.sort_cap             = 0;
   if (P.inv_res != 0.f) {
-    P.sort_cap = (n_beams + 3) & ~3;
     // the packed voxel key holds |coordinate / res| < 2^19 (coordinates are bounded by the range limit)
     if (!(P.range_max * P.inv_res < 524288.f)) return LS2D_ERR_UNSUPPORTED;
   }
   scan_args a;
   a.ranges  = ranges_dev;
+  a.beam_cs = nullptr;  // launch_preprocess: the handle's table
   a.out     = out_dev;
   a.counts  = counts_dev;
   a.n_scans = n_scans;
+  a.off       = off_dev;
+  a.continues = continues;
+  a.ticket    = nullptr;  // launch_preprocess: the handle's counter
   return launch_preprocess(h, P, a, n_scans);
 }
 
@@ -982,16 +990,15 @@ int ls2d_preprocess_scans(ls2d_handle* h, const ls2d_scan_params* sp, const floa
   if ((rc = reserve(h->d_misc, sizeof(float4) * n_pts + sizeof(int) * (size_t) n_scans))) return rc;
   float4* d_out = (float4*) h->d_misc.p;
   int* d_cnt    = (int*) ((char*) h->d_misc.p + sizeof(float4) * n_pts);
-  if ((rc = preprocess_dev(h, sp, (const float*) h->d_ranges.p, n_beams, n_scans, d_out, d_cnt))) return rc;
+  if ((rc = preprocess_dev(h, sp, (const float*) h->d_ranges.p, n_beams, n_scans, d_out, d_cnt, nullptr))) return rc;
   CU(cudaMemcpyAsync(out_points, d_out, sizeof(float4) * n_pts, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(out_counts, d_cnt, sizeof(int) * (size_t) n_scans, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return LS2D_OK;
 }
 
-// strided kernel output (rows of `stride` points + counts) -> owned, packed cloud set
-static int pack_into_set(ls2d_handle* h, int which, const float4* d_strided, const int* d_cnt, int32_t stride,
-                         int32_t n) {
+// an owned cloud set with room for n clouds of at most `stride` points
+static int sized_set(ls2d_handle* h, int which, int32_t stride, int32_t n) {
   cloud_set& c = h->sets[which];
   if (!c.owned) c = cloud_set();
   c.owned            = true;
@@ -1011,25 +1018,45 @@ static int pack_into_set(ls2d_handle* h, int which, const float4* d_strided, con
     CU(cudaMalloc((void**) &c.off, (n_off + 16) * sizeof(int)));
     c.cap_off = n_off + 16;
   }
-  if (n > 0) {
-    if (int rc = launch_scan_pack(h, d_strided, d_cnt, stride, n, c.off, c.pts)) return rc;
-  } else {
-    CU(cudaMemsetAsync(c.off, 0, sizeof(int), h->stream));
-  }
   c.n_clouds   = n;
   c.max_points = stride;  // upper bound: the counts stay on the device
+  if (n == 0) CU(cudaMemsetAsync(c.off, 0, sizeof(int), h->stream));
+  return LS2D_OK;
+}
+
+// ... and the look-back words with which the n CTAs of the producing kernel agree on the CSR offsets
+// (ls2d_service.cuh: lookback_exclusive)
+static int packed_set(ls2d_handle* h, int which, int32_t stride, int32_t n, pack_target* pack) {
+  int rc;
+  if ((rc = sized_set(h, which, stride, n))) return rc;
+  if (n == 0) return LS2D_OK;
+  cloud_set& c = h->sets[which];
+  const size_t words = sizeof(unsigned long long) * (size_t) n;
+  const bool wrap    = h->pack_epoch >= 0x3FFFFFFEu;
+  if (words > h->d_look.cap || wrap) {  // fresh words must not look like this or a later launch's
+    if ((rc = reserve(h->d_look, words))) return rc;
+    CU(cudaMemsetAsync(h->d_look.p, 0, h->d_look.cap, h->stream));
+    if (wrap) h->pack_epoch = 0;
+  }
+  pack->packed = c.pts;
+  pack->off    = c.off;
+  pack->state  = (unsigned long long*) h->d_look.p;
+  pack->epoch  = ++h->pack_epoch;
   return LS2D_OK;
 }
 
 static int scans_to_set_impl(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges_dev,
                              int32_t n_beams, int32_t n_scans) {
   int rc;
+  if ((rc = sized_set(h, which, n_beams, n_scans))) return rc;
+  if (n_scans == 0) return LS2D_OK;
   const size_t n_pts = (size_t) n_scans * n_beams;
   if ((rc = reserve(h->d_misc, sizeof(float4) * n_pts + sizeof(int) * (size_t) n_scans))) return rc;
-  float4* d_tmp = (float4*) h->d_misc.p;
-  int* d_cnt    = (int*) ((char*) h->d_misc.p + sizeof(float4) * n_pts);
-  if (n_scans > 0 && (rc = preprocess_dev(h, sp, ranges_dev, n_beams, n_scans, d_tmp, d_cnt))) return rc;
-  return pack_into_set(h, which, d_tmp, d_cnt, n_beams, n_scans);
+  float4* d_rows = (float4*) h->d_misc.p;
+  int* d_cnt     = (int*) ((char*) h->d_misc.p + sizeof(float4) * n_pts);
+  cloud_set& c   = h->sets[which];
+  if ((rc = preprocess_dev(h, sp, ranges_dev, n_beams, n_scans, d_rows, d_cnt, c.off))) return rc;
+  return launch_scan_pack(h, d_rows, c.off, n_beams, n_scans, c.pts);
 }
 
 int ls2d_preprocess_scans_to_set(ls2d_handle* h, int which, const ls2d_scan_params* sp, const float* ranges,
@@ -1069,13 +1096,14 @@ int ls2d_download_clouds(ls2d_handle* h, int which, float* points, int32_t* offs
 }
 
 // clip_kernel into scratch `tmp` (strided rows of canvas_cols points + counts); ids / poses already on the device
+// (strided rows of canvas_cols points + counts), or straight into a packed set when `pack` names one
 static int clip_dev(ls2d_handle* h, const cloud_set& c, const int* ids_dev, const float* robot_dev,
                     const float* sensor_xyt, int32_t n, scratch& tmp, float4** out, int** counts,
-                    float voxelize_resolution = 0.f) {
+                    float voxelize_resolution = 0.f, const pack_target* pack = nullptr) {
   const int C = h->dp.cam.cols;
   int rc;
-  const size_t out_bytes = sizeof(float4) * (size_t) n * C;
-  if ((rc = reserve(tmp, out_bytes + sizeof(int) * (size_t) n))) return rc;
+  const size_t out_bytes = pack ? 0 : sizeof(float4) * (size_t) n * C;
+  if (!pack && (rc = reserve(tmp, out_bytes + sizeof(int) * (size_t) n))) return rc;
   clip_args a;
   a.pts       = c.pts;
   a.off       = c.off;
@@ -1084,8 +1112,10 @@ static int clip_dev(ls2d_handle* h, const cloud_set& c, const int* ids_dev, cons
   a.pose_stride = pose_stride(h);
   memset(a.sensor_pose, 0, sizeof(a.sensor_pose));
   memcpy(a.sensor_pose, sensor_xyt, sizeof(float) * a.pose_stride);
-  a.out    = (float4*) tmp.p;
-  a.counts = (int*) ((char*) tmp.p + out_bytes);
+  a.out    = pack ? nullptr : (float4*) tmp.p;
+  a.counts = pack ? nullptr : (int*) ((char*) tmp.p + out_bytes);
+  a.base   = 0;
+  a.pack   = pack ? *pack : pack_target{};
   if (voxelize_resolution > 0.f) {  // scene_clipper_projective_2d.cpp:36-48
     const float inv_res = 1.f / voxelize_resolution;
     // the packed voxel key holds |coordinate / res| < 2^19 (coordinates are bounded by the range limit)
@@ -1142,13 +1172,14 @@ int ls2d_clip_scenes_to_set(ls2d_handle* h, int scene_set, const int32_t* cloud_
   int rc;
   float4* d_out = nullptr;
   int* d_cnt    = nullptr;
-  if (n > 0) {
-    if ((rc = h2d(h, h->d_mid, cloud_ids, sizeof(int) * (size_t) n))) return rc;
-    if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * pose_stride(h) * (size_t) n))) return rc;
-    if ((rc = clip_dev(h, c, (const int*) h->d_mid.p, (const float*) h->d_init.p, sensor_xyt, n, h->d_clip, &d_out, &d_cnt)))
-      return rc;
-  }
-  return pack_into_set(h, out_set, d_out, d_cnt, h->dp.cam.cols, n);
+  const float4* src_pts = c.pts;  // packed_set() may touch h->sets[out_set] only: out_set != scene_set
+  pack_target pack = {};
+  if ((rc = packed_set(h, out_set, h->dp.cam.cols, n, &pack))) return rc;
+  if (n == 0 || !src_pts) return LS2D_OK;
+  if ((rc = h2d(h, h->d_mid, cloud_ids, sizeof(int) * (size_t) n))) return rc;
+  if ((rc = h2d(h, h->d_init, robot_xyt, sizeof(float) * pose_stride(h) * (size_t) n))) return rc;
+  return clip_dev(h, h->sets[scene_set], (const int*) h->d_mid.p, (const float*) h->d_init.p, sensor_xyt, n, h->d_clip,
+                  &d_out, &d_cnt, 0.f, &pack);
 }
 
 // MultiTracker2D's frame step, batched: raw scan -> measurement cloud (fixed), local map seen from the predicted
@@ -1169,13 +1200,97 @@ int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ra
     if (h->prm.with_sensor == 2) return LS2D_ERR_INVALID;  // an isometry cannot be handed on as (x, y, theta) bit for bit
     sensor[2] = h->prm.with_sensor ? h->prm.sensor_in_robot[2] : 0.f;
   }
-  if ((rc = ls2d_preprocess_scans_to_set(h, LS2D_FIXED, sp, ranges, n_beams, n))) return rc;
-  if ((rc = ls2d_clip_scenes_to_set(h, scene_set, scene_ids, robot_xyt, sensor, n, LS2D_MOVING))) return rc;
-  if (init_xyt) return align_host_impl(h, nullptr, nullptr, init_xyt, n, out, nullptr, 0);
-  std::vector<float> ident((size_t) n * stride, 0.f);
-  if (stride == 4)
-    for (int i = 0; i < n; ++i) ident[(size_t) i * 4 + 2] = 1.f;
-  return align_host_impl(h, nullptr, nullptr, ident.data(), n, out, nullptr, 0);
+  const cloud_set& scene = h->sets[scene_set];
+  if (!scene.pts || !scene.off) return LS2D_ERR_NOT_READY;
+  for (int i = 0; i < n; ++i)
+    if (scene_ids[i] < 0 || scene_ids[i] >= scene.n_clouds) return LS2D_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  // The batch is cut into chunks of whole frames: chunk k + 1's ranges cross PCIe on the copy stream while chunk k
+  // runs pre-processor -> clipper -> aligner on the compute stream.  The two cloud sets end up holding the whole
+  // batch: the chunks' CSR offsets continue each other (scan_args::continues, the clipper's look-back words).
+  const int C = h->dp.cam.cols;
+  pack_target pack = {};
+  if ((rc = sized_set(h, LS2D_FIXED, n_beams, n))) return rc;
+  if ((rc = packed_set(h, LS2D_MOVING, C, n, &pack))) return rc;
+  cloud_set& F = h->sets[LS2D_FIXED];
+  const int wave    = 8 * (h->sm_count > 0 ? h->sm_count : 148);  // two rounds of 4 CTAs per SM (measured: 3 and 7 chunks lose)
+  int n_chunks      = (n + wave - 1) / wave;
+  n_chunks          = n_chunks > 8 ? 8 : n_chunks;
+  const int chunk   = (n + n_chunks - 1) / n_chunks;
+  const size_t pose_bytes = sizeof(float) * stride * (size_t) n;
+  if ((rc = reserve(h->d_ranges, sizeof(float) * (size_t) n * n_beams))) return rc;
+  if ((rc = reserve(h->d_mid, sizeof(int) * (size_t) n))) return rc;
+  if ((rc = reserve(h->d_clip, pose_bytes))) return rc;
+  if ((rc = reserve(h->d_init, pose_bytes))) return rc;
+  if ((rc = reserve(h->d_out, sizeof(ls2d_result) * (size_t) n))) return rc;
+  if ((rc = reserve(h->d_misc, sizeof(float4) * (size_t) chunk * n_beams + sizeof(int) * (size_t) n))) return rc;
+  float4* d_rows = (float4*) h->d_misc.p;
+  int* d_cnt     = (int*) ((char*) h->d_misc.p + sizeof(float4) * (size_t) chunk * n_beams);
+  if (!h->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+    for (cudaEvent_t& e : h->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (!h->aux_stream) {
+    CU(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : h->ev_packed) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  // Two compute lanes: the pre-processor of chunk k + 1 (aux stream) shares the GPU with the clipper and aligner of
+  // chunk k (the handle's stream), so the partly filled last wave of one kernel is topped up by the other's CTAs.
+  // Earlier work on the handle's stream may still read the buffers: uploads and the aux lane wait for it.
+  cudaStream_t const main_stream = h->stream;
+  CU(cudaEventRecord(h->ev_ready, main_stream));
+  CU(cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+  CU(cudaStreamWaitEvent(h->aux_stream, h->ev_ready, 0));
+  CU(cudaMemcpyAsync(h->d_mid.p, scene_ids, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, h->copy_stream));
+  CU(cudaMemcpyAsync(h->d_clip.p, robot_xyt, pose_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  if (init_xyt) {
+    CU(cudaMemcpyAsync(h->d_init.p, init_xyt, pose_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  } else {
+    h->h_ident.assign((size_t) n * stride, 0.f);
+    if (stride == 4)
+      for (int i = 0; i < n; ++i) h->h_ident[(size_t) i * 4 + 2] = 1.f;
+    CU(cudaMemcpyAsync(h->d_init.p, h->h_ident.data(), pose_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  }
+  for (int k = 0; k < n_chunks; ++k) {
+    const int p0 = k * chunk, p1 = (k + 1) * chunk < n ? (k + 1) * chunk : n;
+    if (p1 <= p0) break;
+    CU(cudaMemcpyAsync((float*) h->d_ranges.p + (size_t) p0 * n_beams, ranges + (size_t) p0 * n_beams,
+                       sizeof(float) * (size_t) (p1 - p0) * n_beams, cudaMemcpyHostToDevice, h->copy_stream));
+    CU(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
+    CU(cudaStreamWaitEvent(h->aux_stream, h->ev_chunk[k], 0));
+    if (k == 0) CU(cudaStreamWaitEvent(main_stream, h->ev_chunk[0], 0));  // ids and poses
+    h->stream = h->aux_stream;  // the launchers work on the handle's stream
+    rc        = preprocess_dev(h, sp, (const float*) h->d_ranges.p + (size_t) p0 * n_beams, n_beams, p1 - p0, d_rows,
+                               d_cnt + p0, F.off + p0, p0 > 0);
+    if (!rc) rc = launch_scan_pack(h, d_rows, F.off + p0, n_beams, p1 - p0, F.pts);
+    h->stream = main_stream;
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev_packed[k], h->aux_stream));
+    clip_args c;
+    c.pts         = scene.pts;
+    c.off         = scene.off;
+    c.cloud_ids   = (const int*) h->d_mid.p;
+    c.robot_pose  = (const float*) h->d_clip.p;
+    c.pose_stride = stride;
+    memset(c.sensor_pose, 0, sizeof(c.sensor_pose));
+    memcpy(c.sensor_pose, sensor, sizeof(float) * stride);
+    c.out    = nullptr;
+    c.counts = nullptr;
+    c.base   = p0;
+    c.pack   = pack;
+    if ((rc = launch_clip(h, c, p1 - p0))) return rc;
+    CU(cudaStreamWaitEvent(main_stream, h->ev_packed[k], 0));
+    align_args a = base_args(h);
+    a.init_pose  = (const float*) h->d_init.p;
+    a.out        = (ls2d_result*) h->d_out.p;
+    a.n_pairs    = p1 - p0;
+    a.pair_base  = p0;
+    if ((rc = launch_icp(h, a))) return rc;
+  }
+  CU(cudaMemcpyAsync(out, h->d_out.p, sizeof(ls2d_result) * (size_t) n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LS2D_OK;
 }
 
 int ls2d_multi_reduction_threads(void) { return multi_reduction_threads(); }

@@ -73,6 +73,15 @@ struct correspond_args {
   int* count;
 };
 
+// where a one-CTA-per-request kernel puts its rows: packed CSR (offsets agreed by a decoupled look-back, see
+// lookback_exclusive in ls2d_service.cuh) or strided
+struct pack_target {
+  float4* packed;              // CSR points, nullptr: strided rows (out + b * stride) and no look-back
+  int* off;                    // [n + 1] CSR offsets
+  unsigned long long* state;   // [n] look-back words
+  unsigned epoch;              // 1 .. 2^30 - 1
+};
+
 struct clip_args {
   const float4* pts;
   const int* off;
@@ -80,8 +89,10 @@ struct clip_args {
   const float* robot_pose;  // [n * pose_stride] robot_in_local_map
   float sensor_pose[4];     // sensor_in_robot, pose_stride floats valid
   int pose_stride;
-  float4* out;              // [n * C]
-  int* counts;              // [n]
+  float4* out;              // [n * C] strided rows (pack.packed == nullptr)
+  int* counts;              // [n], may be nullptr with packed rows
+  int base;                 // index of this launch's first request in cloud_ids / robot_pose / out / counts / pack
+  pack_target pack;
 };
 
 struct merge_args {
@@ -143,14 +154,17 @@ struct scan_dev_params {
   float inv_res;               // 1 / voxelize_resolution, 0: valid-only copy (.cpp:44-48)
   int min_points;              // normal_min_points
   int n_beams;
-  int sort_cap;                // slots of the segment sort: n_beams (voxelisation on), else 0
 };
 
 struct scan_args {
   const float* ranges;  // [n_scans][n_beams]
-  float4* out;          // [n_scans][n_beams]
+  const float2* beam_cs;  // [n_beams] (cos, sin) of the beams' azimuths (beam_table_kernel)
+  float4* out;          // [n_scans][n_beams] strided rows
   int* counts;          // [n_scans]
   int n_scans;
+  int* off;             // [n_scans + 1] CSR offsets of the packed copy, written by the last CTA to finish; or nullptr
+  int continues;        // off[0] already holds the offset of scan 0 (a job cut into several launches), else it is 0
+  int* ticket;          // zero between launches: CTAs that have finished
 };
 
 }  // namespace ls2d

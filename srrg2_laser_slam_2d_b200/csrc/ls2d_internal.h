@@ -11,6 +11,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+
+#include <vector>
 #include <stdint.h>
 
 #include "../../include/ls2d.h"
@@ -53,12 +55,24 @@ struct ls2d_handle {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_ready     = nullptr;
   cudaEvent_t ev_chunk[8]  = {};
+  // second compute lane of ls2d_track_batch (pre-processor), one "packed" event per chunk
+  cudaStream_t aux_stream  = nullptr;
+  cudaEvent_t ev_packed[8] = {};
+  std::vector<float> h_ident;  // identity initial guesses of ls2d_track_batch (must outlive the asynchronous upload)
   ls2d::scratch h_stage;  // pinned staging of pageable caller buffers (ls2d_align_pairs_host)
   // NCCL, resolved lazily
   void* nccl_lib                                                               = nullptr;
   int (*nccl_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*nccl_comm_count)(void*, int*)                                          = nullptr;
   int sm_count = 0;
+  // producers of packed cloud sets (pre-processor, clipper): look-back words and the launch epoch they carry
+  ls2d::scratch d_look;
+  unsigned pack_epoch = 0;
+  ls2d::scratch d_ticket;  // finished-CTA counter of the pre-processor (zero between launches)
+  // (cos, sin) per beam of the pre-processor, cached by (n_beams, sensor matrix)
+  ls2d::scratch d_beam;
+  int beam_n     = 0;
+  float beam_ifx = 0.f, beam_cx = 0.f;
 };
 
 namespace ls2d {
@@ -107,6 +121,6 @@ int launch_best_of_groups(ls2d_handle* h, const ls2d_result* res, const int* gro
 
 int launch_preprocess(ls2d_handle* h, const scan_dev_params& P, const scan_args& a, int n_scans);
 int launch_clip_voxel(ls2d_handle* h, const clip_args& a, int n, float inv_res);
-int launch_scan_pack(ls2d_handle* h, const float4* strided, const int* counts, int stride, int n, int* off, float4* packed);
+int launch_scan_pack(ls2d_handle* h, const float4* strided, const int* off, int stride, int n, float4* packed);
 
 }  // namespace ls2d

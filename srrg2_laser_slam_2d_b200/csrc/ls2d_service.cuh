@@ -34,6 +34,101 @@ __device__ __forceinline__ int ordered_slot(bool ok, int* warp_tot, int* base) {
   return dst;
 }
 
+// Ordered block-wide compaction in two barriers.  Thread `tid` owns element c * T + tid of chunk c and passes its
+// flags as a bit mask (bit c); slots come back through compact_slot().  cnt: n_chunks * (T / 32) ints of shared
+// memory, total: one int.  Element order = chunk, warp, lane = ascending element index.
+__device__ __forceinline__ void compact_count(unsigned mask, int n_chunks, int* cnt, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int c = 0; c < n_chunks; ++c) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
+    if (lane == 0) cnt[c * nwarp + warp] = __popc(ballot);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive prefix over the n_chunks * nwarp counts, in place
+    const int n = n_chunks * nwarp, per = (n + 31) >> 5;
+    int sum = 0;
+    for (int k = lane * per; k < min(n, (lane + 1) * per); ++k) sum += cnt[k];
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    int run = incl - sum;
+    for (int k = lane * per; k < min(n, (lane + 1) * per); ++k) {
+      const int v = cnt[k];
+      cnt[k]      = run;
+      run += v;
+    }
+    if (lane == 31) *total = incl;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ int compact_slot(unsigned mask, int c, const int* cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const unsigned ballot = __ballot_sync(0xffffffffu, (mask >> c) & 1u);
+  return cnt[c * nwarp + warp] + __popc(ballot & ((1u << lane) - 1u));
+}
+
+
+// ---- ordered packing without a second pass: decoupled look-back over one 64-bit word per CTA --------------------
+// word = (epoch << 2 | flag) << 32 | value; flag 1: value = this CTA's count, flag 2: value = the inclusive prefix up
+// to and including this CTA.  The epoch (one per launch, kept by the handle) makes words of earlier launches read
+// as "not there yet", so the array is never cleared.  CTAs wait only for lower block indices, which the hardware
+// dispatches first.  Called by warp 0; returns the exclusive prefix of CTA b to all its lanes.
+
+__device__ __forceinline__ int lookback_exclusive(unsigned long long* state, unsigned epoch, int b, int count) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long tag_count = (unsigned long long) (epoch << 2 | 1u) << 32;
+  const unsigned long long tag_incl  = (unsigned long long) (epoch << 2 | 2u) << 32;
+  volatile unsigned long long* st = state;
+  if (b == 0) {
+    if (lane == 0) st[0] = tag_incl | (unsigned) count;
+    return 0;
+  }
+  if (lane == 0) st[b] = tag_count | (unsigned) count;
+  int excl = 0;
+  for (int base = b - 1;; base -= 32) {
+    const int idx        = base - lane;  // lane 0 reads the nearest predecessor
+    unsigned long long v = tag_incl;     // before the first CTA: an inclusive prefix of 0
+    if (idx >= 0) {
+      v = st[idx];
+      while ((unsigned) (v >> 34) != epoch || ((unsigned) (v >> 32) & 3u) == 0u) {
+        __nanosleep(32);
+        v = st[idx];
+      }
+    }
+    const unsigned incl = __ballot_sync(0xffffffffu, ((unsigned) (v >> 32) & 3u) == 2u);
+    const int last      = incl ? __ffs(incl) - 1 : 31;  // sum up to and including the nearest inclusive prefix
+    excl += __reduce_add_sync(0xffffffffu, lane <= last ? (int) (unsigned) v : 0);
+    if (incl) break;
+  }
+  if (lane == 0) st[b] = tag_incl | (unsigned) (excl + count);
+  return excl;
+}
+
+// Output rows of a CTA: `count` points from slot 0.  Every thread calls it (two barriers) once the count is known;
+// returns where slot 0 goes.  `base_smem`: one int of shared memory.
+// b: the request's index in the whole job (a job may be cut into several launches with one epoch: the look-back
+// crosses the launches).
+__device__ __forceinline__ float4* output_rows(const pack_target& T, float4* strided, size_t stride, int b, int count,
+                                               int* counts, int* base_smem) {
+  if (threadIdx.x == 0 && counts) counts[b] = count;
+  if (!T.packed) return strided + (size_t) b * stride;
+  if (threadIdx.x < 32) {
+    const int excl = lookback_exclusive(T.state, T.epoch, b, count);
+    if (threadIdx.x == 0) {
+      *base_smem = excl;
+      if (b == 0) T.off[0] = 0;
+      T.off[b + 1] = excl + count;
+    }
+  }
+  __syncthreads();
+  float4* rows = T.packed + *base_smem;
+  __syncthreads();  // base_smem may be reused
+  return rows;
+}
+
+
 // ---------------------------------------------------------------------------------------------------
 // z-buffer projection of an arbitrary-size cloud with strided loops (API / parity kernels).
 // W = world -> camera isometry.  On return (after the trailing barrier) zidx[c] holds the winner of
@@ -135,14 +230,17 @@ __global__ void correspond_kernel(const dev_params P, const correspond_args A) {
 // the z-buffer winners of the scene seen from robot_in_local_map * sensor_in_robot, in column order, as points in
 // the sensor frame, then moved into the robot frame.  One CTA per request.
 
-__global__ void clip_kernel(const dev_params P, const clip_args A) {
+constexpr int CLIP_T = 256;  // at most 32 column chunks => canvas_cols <= 8192
+
+__global__ void __launch_bounds__(CLIP_T) clip_kernel(const dev_params P, const clip_args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C      = P.cam.cols;
   unsigned* zdepth = reinterpret_cast<unsigned*>(smem_raw);
   unsigned* zidx   = zdepth + C;
-  __shared__ int warp_tot[32];
-  __shared__ int base;
-  const int r      = blockIdx.x;
+  __shared__ int cnt[32 * (CLIP_T / 32)];
+  __shared__ int misc[2];
+  const int T = CLIP_T, tid = threadIdx.x;
+  const int r      = blockIdx.x + A.base;
   const int cloud  = A.cloud_ids[r];
   const int p0 = A.off[cloud], n = A.off[cloud + 1] - p0;
   const iso S   = load_pose(A.sensor_pose, 0, A.pose_stride);
@@ -150,27 +248,29 @@ __global__ void clip_kernel(const dev_params P, const clip_args A) {
   const iso W   = iso_inverse(cam);
   const bool move = !(S.c == 1.f && S.s == 0.f && S.tx == 0.f && S.ty == 0.f);  // .cpp:60
   zbuffer_project<false>(P, W, A.pts + p0, n, zdepth, zidx);
-  if (threadIdx.x == 0) base = 0;
-  __syncthreads();
-  for (int k0 = 0; k0 < C; k0 += blockDim.x) {
-    const int k   = k0 + threadIdx.x;
-    const bool ok = k < C && zidx[k] != Z_EMPTY_IDX;
-    float4 o      = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) {
-      const float4 p = ldg4(A.pts + p0 + zidx[k]);
-      iso_apply(W, p.x, p.y, o.x, o.y);
-      iso_rot(W, p.z, p.w, o.z, o.w);
-      if (move) {
-        float x, y, nx, ny;
-        iso_apply(S, o.x, o.y, x, y);
-        iso_rot(S, o.z, o.w, nx, ny);
-        o = make_float4(x, y, nx, ny);
-      }
-    }
-    const int dst = ordered_slot(ok, warp_tot, &base);
-    if (ok) A.out[(size_t) r * C + dst] = o;
+  const int col_chunks = (C + T - 1) / T;
+  unsigned mask = 0;
+  for (int c = 0; c < col_chunks; ++c) {
+    const int k = c * T + tid;
+    if (k < C && zidx[k] != Z_EMPTY_IDX) mask |= 1u << c;
   }
-  if (threadIdx.x == 0) A.counts[r] = base;
+  compact_count(mask, col_chunks, cnt, &misc[0]);
+  float4* out = output_rows(A.pack, A.out, (size_t) C, r, misc[0], A.counts, &misc[1]);
+  for (int c = 0; c < col_chunks; ++c) {
+    const int k = c * T + tid, dst = compact_slot(mask, c, cnt);
+    if (!((mask >> c) & 1u)) continue;
+    const float4 p = ldg4(A.pts + p0 + zidx[k]);
+    float4 o;
+    iso_apply(W, p.x, p.y, o.x, o.y);
+    iso_rot(W, p.z, p.w, o.z, o.w);
+    if (move) {
+      float x, y, nx, ny;
+      iso_apply(S, o.x, o.y, x, y);
+      iso_rot(S, o.z, o.w, nx, ny);
+      o = make_float4(x, y, nx, ny);
+    }
+    out[dst] = o;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -1,5 +1,7 @@
 // ls2d_tu_service.cu -- projector / finder / clipper / merger / best-of kernels (ls2d_service.cuh) and the raw-scan
 // pre-processor, voxelizing clipper and CSR packing built on the same z-buffer helpers (ls2d_scan.cuh)
+#include <algorithm>
+
 #include "ls2d_internal.h"
 #include "ls2d_scan.cuh"
 
@@ -25,9 +27,10 @@ int launch_correspond(ls2d_handle* h, const correspond_args& a) {
 
 int launch_clip(ls2d_handle* h, const clip_args& a, int n) {
   if (n <= 0) return LS2D_OK;
+  if (h->dp.cam.cols > 32 * CLIP_T) return LS2D_ERR_UNSUPPORTED;
   const size_t smem = sizeof(unsigned) * 2 * (size_t) h->dp.cam.cols;
   CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  clip_kernel<<<n, 256, smem, h->stream>>>(h->dp, a);
+  clip_kernel<<<n, CLIP_T, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
   return LS2D_OK;
@@ -77,11 +80,27 @@ int launch_best_of_groups(ls2d_handle* h, const ls2d_result* res, const int* gro
 }
 
 
-int launch_preprocess(ls2d_handle* h, const scan_dev_params& P, const scan_args& a, int n_scans) {
+int launch_preprocess(ls2d_handle* h, const scan_dev_params& P, const scan_args& a_in, int n_scans) {
   if (n_scans <= 0) return LS2D_OK;
-  const size_t smem = scan_smem_bytes(P.n_beams, P.sort_cap);
+  if (P.n_beams > 32 * SCAN_T || P.n_beams >= (1 << 14)) return LS2D_ERR_UNSUPPORTED;
+  const size_t smem = scan_smem_bytes(P.n_beams, P.inv_res != 0.f);
   if (smem > SMEM_LIMIT) return LS2D_ERR_UNSUPPORTED;
+  int rc;
+  if (!h->d_beam.p || h->beam_n != P.n_beams || memcmp(&h->beam_ifx, &P.ifx, 4) || memcmp(&h->beam_cx, &P.cx, 4)) {
+    if ((rc = reserve(h->d_beam, sizeof(float2) * (size_t) P.n_beams))) return rc;
+    beam_table_kernel<<<(P.n_beams + 255) / 256, 256, 0, h->stream>>>(P.ifx, P.cx, P.n_beams, (float2*) h->d_beam.p);
+    CU(cudaGetLastError());
+    h->launches++;
+    h->beam_n = P.n_beams, h->beam_ifx = P.ifx, h->beam_cx = P.cx;
+  }
+  scan_args a = a_in;
+  a.beam_cs   = (const float2*) h->d_beam.p;
   CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (!h->d_ticket.p) {
+    if ((rc = reserve(h->d_ticket, sizeof(int)))) return rc;
+    CU(cudaMemsetAsync(h->d_ticket.p, 0, sizeof(int), h->stream));
+  }
+  a.ticket = (int*) h->d_ticket.p;
   preprocess_kernel<<<n_scans, SCAN_T, smem, h->stream>>>(P, a);
   CU(cudaGetLastError());
   h->launches++;
@@ -91,8 +110,9 @@ int launch_preprocess(ls2d_handle* h, const scan_dev_params& P, const scan_args&
 int launch_clip_voxel(ls2d_handle* h, const clip_args& a, int n, float inv_res) {
   if (n <= 0) return LS2D_OK;
   const int C = h->dp.cam.cols;
-  if (C > 32 * SCAN_T) return LS2D_ERR_UNSUPPORTED;
+  if (C > 32 * SCAN_T || C >= (1 << 14)) return LS2D_ERR_UNSUPPORTED;
   const size_t smem = clip_voxel_smem_bytes(C);
+  if (smem > SMEM_LIMIT) return LS2D_ERR_UNSUPPORTED;
   CU(cudaFuncSetAttribute(clip_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   clip_voxel_kernel<<<n, SCAN_T, smem, h->stream>>>(h->dp, a, inv_res);
   CU(cudaGetLastError());
@@ -100,13 +120,11 @@ int launch_clip_voxel(ls2d_handle* h, const clip_args& a, int n, float inv_res) 
   return LS2D_OK;
 }
 
-int launch_scan_pack(ls2d_handle* h, const float4* strided, const int* counts, int stride, int n, int* off, float4* packed) {
+int launch_scan_pack(ls2d_handle* h, const float4* strided, const int* off, int stride, int n, float4* packed) {
   if (n <= 0) return LS2D_OK;
-  scan_offsets_kernel<<<1, 1024, 0, h->stream>>>(counts, n, off);
-  CU(cudaGetLastError());
   scan_pack_kernel<<<n, 128, 0, h->stream>>>(strided, off, stride, packed);
   CU(cudaGetLastError());
-  h->launches += 2;
+  h->launches++;
   return LS2D_OK;
 }
 

@@ -67,3 +67,24 @@ def test_host_side_helpers_need_no_gpu():
 def test_no_cpu_fallback_without_a_device():
     with pytest.raises(_abi.Ls2dError):
         _abi.Handle(0)
+
+
+def test_preprocessor_sums_are_not_contracted():
+    """ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (a single rounding) when the product has no other use;
+    the pre-processor's window walk relies on the product ALSO feeding the distance test (ls2d_scan.cuh).  Its SASS
+    must hold packed multiplies and adds but no packed fused multiply-add."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    body, inside = [], False
+    for line in sass.splitlines():
+        if "Function : " in line:
+            inside = "preprocess_kernel" in line
+        elif inside:
+            body.append(line)
+    text = "\n".join(body)
+    assert "FMUL2" in text and "FADD2" in text
+    assert "FFMA2" not in text

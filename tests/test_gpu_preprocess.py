@@ -136,3 +136,54 @@ def test_track_batch_matches_the_oracle_chain(handle_factory, oracle, res, senso
     for f in ("x", "y", "theta", "chi_inliers"):
         assert np.array_equal(gu.bits(got[f]), gu.bits(ref[f])), f
     assert (got["status"] == 0).all()
+
+
+def test_track_batch_in_chunks_equals_the_three_calls(handle_factory):
+    """2600 frames: ls2d_track_batch cuts the batch into chunks (uploads overlap the kernels, two compute lanes);
+    results and the two cloud sets it leaves behind are those of pre-process -> clip -> align called one after the
+    other on the whole batch."""
+    n, nb = 2600, 721
+    raw = make_raw_scans(64, n_beams=nb, seed=5)
+    rng = np.random.default_rng(9)
+    pick = rng.integers(0, 64, n)
+    ranges = np.ascontiguousarray(raw.fixed_ranges[pick])
+    ids = pick.astype(np.int32)                               # the local map of the pose the frame was taken near
+    robots = rng.uniform(-0.02, 0.02, (n, 3)).astype(np.float32)
+    init = rng.uniform(-0.01, 0.01, (n, 3)).astype(np.float32)
+    kw = dict(angle_min=raw.angle_min, angle_max=raw.angle_max)
+    sp = default_scan_params(voxelize_resolution=0.02, **kw)
+    sp_map = default_scan_params(voxelize_resolution=0.0, **kw)
+    h = handle_factory(default_params(canvas_cols=721, max_iterations=6))
+    h.preprocess_scans_to_set(2, sp_map, raw.moving_ranges)
+    got = h.track_batch(sp, ranges, 2, ids, robots, init).copy()
+    fpts, foff = h.download_clouds(LS2D_FIXED, n, n * nb)
+    mpts, moff = h.download_clouds(LS2D_MOVING, n, n * 721)
+    h.preprocess_scans_to_set(LS2D_FIXED, sp, ranges)
+    h.clip_scenes_to_set(2, ids, robots, np.zeros(3, np.float32), LS2D_MOVING)
+    fpts2, foff2 = h.download_clouds(LS2D_FIXED, n, n * nb)
+    mpts2, moff2 = h.download_clouds(LS2D_MOVING, n, n * 721)
+    want = h.align_batch(init)
+    assert np.array_equal(foff, foff2) and np.array_equal(moff, moff2)
+    assert np.array_equal(gu.bits(fpts), gu.bits(fpts2)) and np.array_equal(gu.bits(mpts), gu.bits(mpts2))
+    assert got.tobytes() == want.tobytes()
+    assert (got["status"] == 0).mean() > 0.9
+
+
+def test_voxelize_with_uneven_buckets_takes_the_sort(handle_factory, oracle):
+    """a wall at x = const seen square on: hundreds of voxels share one ix, the buckets of the counting sort are too
+    uneven and the segments go through the bitonic sort instead -- same cloud, bit for bit"""
+    nb = 1081
+    kw = dict(angle_min=-1.2, angle_max=1.2)
+    az = np.linspace(-1.2, 1.2, nb, dtype=np.float64)
+    rng = np.random.default_rng(2)
+    scans = []
+    for d in (2.0, 3.5, 1.2):
+        r = d / np.cos(az)                                    # the wall x = d
+        r[::97] = 0.0                                         # a few dropped beams
+        r[520:560] = 29.0 + 0.01 * np.arange(40)              # a doorway: far returns stretch the x extent, so the
+                                                              # 2048 buckets cannot also split the wall along y
+        scans.append((r + rng.normal(0, 1e-4, nb)).astype(np.float32))
+    ranges = np.stack(scans)
+    h = handle_factory()
+    for res in (0.02, 0.05):
+        check(h, oracle, dict(voxelize_resolution=res, **kw), ranges)
