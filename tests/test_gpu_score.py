@@ -126,3 +126,28 @@ def test_squared_range_gate_is_the_reference_gate(oracle):
             if t >= 0:
                 assert (np.sqrt(np.float32(t)) >= rmin32) == inside
         assert np.sqrt(np.float32(hi.value)) <= rmax32 < np.sqrt(np.nextafter(np.float32(hi.value), np.float32(np.inf)))
+
+
+@gpu
+def test_lock_free_cell_hand_back_is_deterministic(handle_factory):
+    """score_kernel and icp_multi2_kernel let the winner of a column hand the z-buffer cells back inside the interval
+    in which the losers still test them (losers only ever see the winner's rho or EMPTY; racecheck reports these
+    accesses, profiles/r02/sanitizer.md).  40 repetitions on 4096 pairs, with ties in the clouds, must be one result."""
+    from srrg2_laser_slam_2d_b200._abi import multi_reduction_threads
+    sp = make_scan_pairs(4096, n_beams=721, seed=404, chunk=512)
+    fixed = sp.fixed_pts.copy()
+    fixed[1::7] = fixed[0::7][:len(fixed[1::7])]                 # duplicated points: equal rho in a column (decision D3)
+    gp = default_params(canvas_cols=721, normal_cos=0.8, max_iterations=4)
+    h = handle_factory(gp)
+    h.upload_clouds(LS2D_FIXED, fixed, sp.fixed_off)
+    h.upload_clouds(LS2D_MOVING, sp.moving_pts, sp.moving_off)
+    h.upload_clouds(2, sp.fixed_pts, sp.fixed_off)
+    poses = (sp.gt_xyt + np.float32([0.01, -0.01, 0.005])).astype(np.float32)
+    first_s = h.score_batch(poses).tobytes()
+    sl = [default_params(canvas_cols=721, normal_cos=0.8, max_iterations=4, with_sensor=1, sensor_in_robot=(0.1, 0.0, 0.0)),
+          default_params(canvas_cols=721, normal_cos=0.8, max_iterations=4, with_sensor=1, sensor_in_robot=(-0.1, 0.0, 0.1))]
+    assert multi_reduction_threads(sl, 721, 721, True) == 256 | 1 << 16       # icp_multi2_kernel serves this shape
+    first_m = h.align_multi(sl, [LS2D_FIXED, 2], [LS2D_MOVING, LS2D_MOVING], poses).tobytes()
+    for _ in range(40):
+        assert h.score_batch(poses).tobytes() == first_s
+        assert h.align_multi(sl, [LS2D_FIXED, 2], [LS2D_MOVING, LS2D_MOVING], poses).tobytes() == first_m

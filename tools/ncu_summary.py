@@ -39,7 +39,16 @@ def main():
     lines = ["# ncu summary of `%s`" % rep.split("/")[-1], "",
              "Captured with `ncu --set full --clock-control none --import-source on` (one launch, replayed passes);",
              "times under the profiler are not bench values.", ""]
-    for r in data[:1]:
+    want = sys.argv[3] if len(sys.argv) > 3 else None
+    seen = set()
+    picked = []
+    for r in data:  # one table per distinct kernel (the first launch of each), or only the ones matching argv[3]
+        name = r[hdr.index("Kernel Name")]
+        if name in seen or (want and want not in name):
+            continue
+        seen.add(name)
+        picked.append(r)
+    for r in picked:
         lines += ["## %s" % r[hdr.index("Kernel Name")], "", "| metric | value | unit |", "|---|---|---|"]
         for m in RAW:
             if m in hdr:
