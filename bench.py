@@ -10,12 +10,21 @@ over +-3.14159 rad.  A "step" is one pass of the hot path over the whole batch.
              on the launching stream.  The 142 MB of clouds exceed the 126 MB L2, so every step re-reads
              them from HBM (config.l2: "inputs_larger_than_l2").
   e2e        the same metric through the C ABI with HOST buffers (ls2d_align_pairs_host): pinned-memory
-             H2D of both cloud sets and the initial guesses, the kernel, D2H of the 64-byte results, all
+             H2D of both cloud sets and the initial guesses, the kernel, D2H of the 80-byte results, all
              inside the timed region.
   roofline   achieved = 34,672 algorithmic bytes per pair (16*1081 + 16*1081 + 16 + 64) x pairs
              per launch / mean launch duration, against the measured HBM copy bandwidth.
   cpu_baseline  the CPU oracle (oracle/ls2d_oracle.c, the restatement of the reference's aligner -- the
              reference itself cannot be built here) on the box's host cores.
+  sub-records of the default line (each a measurement of its own, same batch unless it says otherwise):
+    roofline_issue       the bound that limits the 10-iteration kernel: warp instructions (committed ncu capture) / s
+    score_pass           ls2d_score_batch, the single-linearisation pass (score_kernel): HBM and issue rooflines
+    sustained            --sustain seconds of back-to-back launches: time per launch and clocks under load
+    e2e_pageable         e2e from pageable numpy buffers (what a caller without pinned staging sees)
+    e2e_track            ls2d_track_batch: RAW scans (4 B/beam) -> pre-process -> clip -> align, pinned host buffers
+    latency_single_pair  one MultiAligner2D::compute() per call through the C++ plugin class vs the 1-thread oracle
+    verify               config 4 through ls2d_verify_sharded_nccl: 65,536 distinct candidate clouds x 8 guesses x 30
+                         iterations, strong scaling over the ranks, mean executed iterations, winner
 
 N > 1 (torchrun): one process per GPU, every rank aligns its own 4096-pair batch (independent pairs, no
 data-path collective: weak scaling); time = max over ranks.   --impl reference times the oracle only.
@@ -436,6 +445,13 @@ def run_ours(args):
                                            "kernel": "score_kernel"},
                               "frac_of_hbm_peak": score_gbs / peak,
                               "note": "ls2d_score_batch: fixed image + one projection / linearisation per pair, same bytes"}
+        s_inst = recorded_traffic("score_kernel_warp_instructions")
+        if s_inst and clk and clk.get("sm_mhz"):
+            issue_peak = 148 * 4 * clk["sm_mhz"] * 1e6
+            line["score_pass"]["roofline_issue"] = {"bound": "issue", "achieved": s_inst / (score_ms * 1e-3),
+                                                    "peak": issue_peak, "unit": "warp-inst/s",
+                                                    "frac": s_inst / (score_ms * 1e-3) / issue_peak,
+                                                    "warp_instructions_per_launch": s_inst}
         if sustained:
             line["sustained"] = sustained
         if pageable_s is not None:
