@@ -38,7 +38,7 @@ constexpr size_t icp_general_smem_bytes(int cols, int threads, int max_points) {
 }
 
 template <int T, bool SENSOR>
-__global__ void __launch_bounds__(T, 1) icp_general_kernel(const dev_params P, const align_args A, int max_points) {
+__global__ void __launch_bounds__(T, 2) icp_general_kernel(const dev_params P, const align_args A, int max_points) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C          = P.cam.cols;
   float4* fimg         = reinterpret_cast<float4*>(smem_raw);
