@@ -341,6 +341,7 @@ def run_ours(args):
     mp, mo = torch.from_numpy(sp.moving_pts).to(dev), torch.from_numpy(sp.moving_off).to(dev)
     init = torch.from_numpy(sp.init_xyt).to(dev)
     out = torch.zeros(n_pairs * words, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()  # ls2d_set_clouds_dev reads the offsets: they must be complete
     h.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), n_pairs, N_BEAMS)
     h.set_clouds_dev(LS2D_MOVING, mp.data_ptr(), mo.data_ptr(), n_pairs, N_BEAMS)
 
@@ -512,6 +513,7 @@ def measure_verify(args, torch, dist, rank, local_rank, world):
     h = Handle(local_rank, default_params(**LOOP))
     stream = torch.cuda.current_stream(dev)
     h.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
     h.set_clouds_dev(LS2D_FIXED, query.data_ptr(), qoff.data_ptr(), 1, 1081)
     h.set_clouds_dev(LS2D_MOVING, cands.data_ptr(), off.data_ptr(), n_local, 1081)
     gates = Gates(300, 0.1, 0.8)
@@ -684,6 +686,7 @@ def run_allpairs(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
     h.set_clouds_dev(LS2D_FIXED, fpts.data_ptr(), off.data_ptr(), n_maps, n_pts)
     h.set_clouds_dev(LS2D_MOVING, pts.data_ptr(), off.data_ptr(), n_maps, n_pts)
     fid = torch.from_numpy(fid_all[p_lo:p_hi].copy()).to(dev)

@@ -200,7 +200,9 @@ int ls2d_get_pose_format(const ls2d_handle* h);
  * (apps/visual_test_aligner_2d.cpp:108-126, apps/visual_test_correspondence_finder_projective_2d.cpp:73-79) */
 int ls2d_upload_clouds(ls2d_handle* h, int which /* set id */, const float* points_xynn, const int32_t* offsets,
                        int32_t n_clouds);
-/* borrow device-resident clouds (no copy); max_points = largest cloud in the set */
+/* borrow device-resident clouds (no copy); max_points >= the largest cloud in the set: it picks the kernel and its
+ * capacity, so the offsets -- which must be complete on the device when this is called -- are checked against it
+ * here (one small kernel and a 4-byte read back); LS2D_ERR_INVALID when a cloud is larger or the offsets descend */
 int ls2d_set_clouds_dev(ls2d_handle* h, int which, const void* points_dev, const int32_t* offsets_dev,
                         int32_t n_clouds, int32_t max_points);
 

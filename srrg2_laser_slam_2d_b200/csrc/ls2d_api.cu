@@ -349,6 +349,17 @@ int ls2d_set_clouds_dev(ls2d_handle* h, int which, const void* pts_dev, const in
   if (!h || which < 0 || which >= LS2D_MAX_CLOUD_SETS || !pts_dev || !off_dev || n_clouds < 0 || max_points < 0)
     return LS2D_ERR_INVALID;
   if (((uintptr_t) pts_dev) & 15) return LS2D_ERR_INVALID;
+  // max_points picks the kernel and its capacity: an understated value would silently drop points, so the offsets
+  // (which must be complete when this is called) are checked against it once, here
+  if (n_clouds > 0) {
+    CU(cudaSetDevice(h->device));
+    int rc, largest = 0;
+    if ((rc = reserve(h->d_misc, sizeof(int)))) return rc;
+    if ((rc = launch_largest_cloud(h, off_dev, n_clouds, (int*) h->d_misc.p))) return rc;
+    CU(cudaMemcpyAsync(&largest, h->d_misc.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (largest < 0 || largest > max_points) return LS2D_ERR_INVALID;  // < 0: offsets not ascending
+  }
   release(h->sets[which]);
   cloud_set& c = h->sets[which];
   c.pts        = (float4*) pts_dev;

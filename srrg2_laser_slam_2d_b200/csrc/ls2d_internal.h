@@ -121,6 +121,8 @@ int launch_best_of_groups(ls2d_handle* h, const ls2d_result* res, const int* gro
 
 int launch_preprocess(ls2d_handle* h, const scan_dev_params& P, const scan_args& a, int n_scans);
 int launch_clip_voxel(ls2d_handle* h, const clip_args& a, int n, float inv_res);
+// *out = the largest off[i + 1] - off[i], or -1 when a difference is negative
+int launch_largest_cloud(ls2d_handle* h, const int* off, int n, int* out);
 int launch_scan_pack(ls2d_handle* h, const float4* strided, const int* off, int stride, int n, float4* packed);
 
 }  // namespace ls2d

@@ -230,6 +230,26 @@ __global__ void correspond_kernel(const dev_params P, const correspond_args A) {
 // the z-buffer winners of the scene seen from robot_in_local_map * sensor_in_robot, in column order, as points in
 // the sensor frame, then moved into the robot frame.  One CTA per request.
 
+// ls2d_set_clouds_dev: the largest cloud of a borrowed CSR set (an int, zeroed before the launch); a negative size
+// anywhere makes it negative for good
+__global__ void largest_cloud_kernel(const int* off, int n, int* out) {
+  int best = 0;
+  bool bad = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int m = off[i + 1] - off[i];
+    bad |= m < 0;
+    best = max(best, m);
+  }
+  best = __reduce_max_sync(0xffffffffu, best);
+  bad  = __any_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (bad)
+      atomicMin(out, -0x7fffffff);
+    else if (atomicMax(out, best) < 0)
+      atomicMin(out, -0x7fffffff);
+  }
+}
+
 constexpr int CLIP_T = 256;  // at most 32 column chunks => canvas_cols <= 8192
 
 __global__ void __launch_bounds__(CLIP_T) clip_kernel(const dev_params P, const clip_args A) {

@@ -120,6 +120,14 @@ int launch_clip_voxel(ls2d_handle* h, const clip_args& a, int n, float inv_res) 
   return LS2D_OK;
 }
 
+int launch_largest_cloud(ls2d_handle* h, const int* off, int n, int* out) {
+  CU(cudaMemsetAsync(out, 0, sizeof(int), h->stream));
+  largest_cloud_kernel<<<(n + 1023) / 1024 > 1024 ? 1024 : (n + 1023) / 1024, 1024, 0, h->stream>>>(off, n, out);
+  CU(cudaGetLastError());
+  h->launches++;
+  return LS2D_OK;
+}
+
 int launch_scan_pack(ls2d_handle* h, const float4* strided, const int* off, int stride, int n, float4* packed) {
   if (n <= 0) return LS2D_OK;
   scan_pack_kernel<<<n, 128, 0, h->stream>>>(strided, off, stride, packed);

@@ -421,6 +421,13 @@ def test_device_resident_path_matches_host_path(handle_factory):
     assert got.tobytes() == ref.tobytes()
     one = h2.align_pairs_host(sp.fixed_pts, sp.fixed_off, sp.moving_pts, sp.moving_off, sp.init_xyt)
     assert one.tobytes() == ref.tobytes()
+    # a borrowed set whose max_points understates its largest cloud is refused (it would silently drop points)
+    from srrg2_laser_slam_2d_b200._abi import Ls2dError
+    with pytest.raises(Ls2dError):
+        h2.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), fo.data_ptr(), 64, int(np.diff(sp.fixed_off).max()) - 1)
+    bad = torch.from_numpy(sp.fixed_off[::-1].copy()).to(dev)
+    with pytest.raises(Ls2dError):
+        h2.set_clouds_dev(LS2D_FIXED, fp.data_ptr(), bad.data_ptr(), 64, 1081)
 
 
 def test_zbuffer_ties_first_index_wins(handle_factory, oracle):
