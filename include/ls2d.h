@@ -348,7 +348,8 @@ typedef struct ls2d_scan_params {
 void ls2d_default_scan_params(ls2d_scan_params* p);
 /* n_scans scans of n_beams ranges each (host, row-major) -> out_points [n_scans * n_beams * 4] (scan s starts at
  * s * n_beams * 4; out_counts[s] points are valid), the cloud each RawDataPreprocessorProjective2D::compute would
- * hand to setMeas().  n_beams <= 8192. */
+ * hand to setMeas().  n_beams <= 8192; with voxelize_resolution > 0 a scan's working set must fit one CTA's shared
+ * memory: n_beams <= 6000 (LS2D_ERR_UNSUPPORTED beyond). */
 int ls2d_preprocess_scans(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges, int32_t n_beams,
                           int32_t n_scans, float* out_points, int32_t* out_counts);
 /* same, but the clouds stay on the device as cloud set `which` (packed CSR), ready for ls2d_align_batch & co.;

@@ -187,3 +187,17 @@ def test_voxelize_with_uneven_buckets_takes_the_sort(handle_factory, oracle):
     h = handle_factory()
     for res in (0.02, 0.05):
         check(h, oracle, dict(voxelize_resolution=res, **kw), ranges)
+
+
+def test_beam_count_limits(handle_factory, oracle):
+    """n_beams <= 8192 without voxelisation; with it the scan has to fit one CTA's shared memory (<= 6000 beams),
+    beyond that the call says so instead of falling back to anything"""
+    from srrg2_laser_slam_2d_b200._abi import Ls2dError
+    h = handle_factory()
+    for nb, res in ((6000, 0.02), (8192, 0.0)):
+        raw = make_raw_scans(3, n_beams=nb, seed=nb)
+        check(h, oracle, dict(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=res), raw.fixed_ranges)
+    raw = make_raw_scans(1, n_beams=8192, seed=1)
+    sp = default_scan_params(angle_min=raw.angle_min, angle_max=raw.angle_max, voxelize_resolution=0.02)
+    with pytest.raises(Ls2dError):
+        h.preprocess_scans(sp, raw.fixed_ranges)
