@@ -258,7 +258,6 @@ int ls2d_destroy(ls2d_handle* h) {
   release(h->d_beam);
   release(h->d_edge);
   for (scratch& e : h->d_edge_slice) release(e);
-  if (h->h_stage.p) cudaFreeHost(h->h_stage.p);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   for (cudaEvent_t e : h->ev_packed)
@@ -503,8 +502,9 @@ int ls2d_align_pairs_host(ls2d_handle* h, const float* fpts, const int32_t* foff
   for (int k = 0; k < n_chunks; ++k) {
     const int p0 = (int) ((long long) n_pairs * k / n_chunks), p1 = (int) ((long long) n_pairs * (k + 1) / n_chunks);
     const size_t nf = (size_t) (foff[p1] - foff[p0]), nm = (size_t) (moff[p1] - moff[p0]);
-    if (nf) CU(cudaMemcpyAsync(F.pts + foff[p0], fpts + 4 * (size_t) foff[p0], nf * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream));
-    if (nm) CU(cudaMemcpyAsync(M.pts + moff[p0], mpts + 4 * (size_t) moff[p0], nm * sizeof(float4), cudaMemcpyHostToDevice, h->copy_stream));
+    // (pageable caller buffers go through the handle's pinned ring with a few copy threads, ls2d_stage.h)
+    if (nf) CU(h->stage.upload(F.pts + foff[p0], fpts + 4 * (size_t) foff[p0], nf * sizeof(float4), h->copy_stream));
+    if (nm) CU(h->stage.upload(M.pts + moff[p0], mpts + 4 * (size_t) moff[p0], nm * sizeof(float4), h->copy_stream));
     CU(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
     CU(cudaStreamWaitEvent(h->stream, h->ev_chunk[k], 0));
     align_args a = base_args(h);
@@ -1266,8 +1266,8 @@ int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ra
   for (int k = 0; k < n_chunks; ++k) {
     const int p0 = k * chunk, p1 = (k + 1) * chunk < n ? (k + 1) * chunk : n;
     if (p1 <= p0) break;
-    CU(cudaMemcpyAsync((float*) h->d_ranges.p + (size_t) p0 * n_beams, ranges + (size_t) p0 * n_beams,
-                       sizeof(float) * (size_t) (p1 - p0) * n_beams, cudaMemcpyHostToDevice, h->copy_stream));
+    CU(h->stage.upload((float*) h->d_ranges.p + (size_t) p0 * n_beams, ranges + (size_t) p0 * n_beams,
+                       sizeof(float) * (size_t) (p1 - p0) * n_beams, h->copy_stream));
     CU(cudaEventRecord(h->ev_chunk[k], h->copy_stream));
     CU(cudaStreamWaitEvent(h->aux_stream, h->ev_chunk[k], 0));
     if (k == 0) CU(cudaStreamWaitEvent(main_stream, h->ev_chunk[0], 0));  // ids and poses

@@ -17,6 +17,7 @@
 
 #include "../../include/ls2d.h"
 #include "ls2d_args.h"
+#include "ls2d_stage.h"
 
 namespace ls2d {
 
@@ -59,7 +60,7 @@ struct ls2d_handle {
   cudaStream_t aux_stream  = nullptr;
   cudaEvent_t ev_packed[8] = {};
   std::vector<float> h_ident;  // identity initial guesses of ls2d_track_batch (must outlive the asynchronous upload)
-  ls2d::scratch h_stage;  // pinned staging of pageable caller buffers (ls2d_align_pairs_host)
+  ls2d::stage_pool stage;  // uploads from pageable caller buffers (ls2d_align_pairs_host, ls2d_track_batch)
   // NCCL, resolved lazily
   void* nccl_lib                                                               = nullptr;
   int (*nccl_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;

@@ -544,3 +544,18 @@ def test_verify_pairs_per_group_best_matches_the_oracle(handle_factory, oracle):
         assert best[g]["n_inliers"] == o["n_inliers"][lo + k] and best[g]["theta"] == o["theta"][lo + k]
         hits += int(mid[lo + k] == g)
     assert hits >= 4                                               # true matches are found where offered
+
+
+def test_pageable_host_buffers_go_through_the_staging_ring(handle_factory):
+    """ls2d_align_pairs_host from plain (pageable) numpy buffers: 17.7 MB per cloud set, more than the handle's 16 MB
+    ring of pinned slots (csrc/ls2d_stage.h), so every slot is reused; same bytes out as from pinned buffers and as
+    from resident clouds"""
+    import torch
+    sp = make_scan_pairs(1024, n_beams=1081, seed=31, chunk=256)
+    h = handle_factory(default_params(canvas_cols=1081, normal_cos=0.9, max_iterations=3))
+    upload(h, sp)
+    ref = h.align_batch(sp.init_xyt)
+    pageable = h.align_pairs_host(sp.fixed_pts.copy(), sp.fixed_off, sp.moving_pts.copy(), sp.moving_off, sp.init_xyt)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    pinned = h.align_pairs_host(pin(sp.fixed_pts), sp.fixed_off, pin(sp.moving_pts), sp.moving_off, sp.init_xyt)
+    assert pageable.tobytes() == ref.tobytes() and pinned.tobytes() == ref.tobytes()
