@@ -552,21 +552,27 @@ namespace srrg2_slam_interfaces {
                                              const Isometry2f& estimate) {
     Isometry2f lmis = estimate;
     if (p.with_sensor) lmis = slice->sensorInRobot().inverse() * lmis;
-    float lv[4], ev[4];
-    isoFloats(lmis, lv);
-    isoFloats(estimate, ev);
-    std::vector<int32_t> fi(p.canvas_cols), mi(p.canvas_cols);
-    int32_t n = 0;
-    Ls2dDevice::check(ls2d_find_correspondences_in(h, fixed_set, moving_set, 0, 0, lv, fi.data(), mi.data(), &n),
-                      "MultiAligner2D::compute");
-    std::vector<uint8_t> inlier((size_t) (n > 0 ? n : 1), 1);
-    if (p.keep_only_inlier_correspondences && n > 0)
-      Ls2dDevice::check(ls2d_classify_correspondences(h, fixed_set, moving_set, 0, 0, ev, fi.data(), mi.data(), n,
-                                                      inlier.data()),
+    AlignerSliceProcessorLaserBase* s = slice.get();  // the closure lives in the slice: no owning pointer back to it
+    s->_correspondences.clear();
+    const std::weak_ptr<int> alive = _alive;  // the handle is this aligner's: a fetch after its death finds nothing
+    s->_fetch_correspondences = [h, p, fixed_set, moving_set, s, lmis, estimate, alive]() {
+      if (alive.expired()) return;
+      float lv[4], ev[4];
+      isoFloats(lmis, lv);
+      isoFloats(estimate, ev);
+      Ls2dDevice::check(ls2d_set_params(h, &p), "MultiAligner2D::compute");  // a multi-slice aligner leaves the last slice's
+      std::vector<int32_t> fi(p.canvas_cols), mi(p.canvas_cols);
+      int32_t n = 0;
+      Ls2dDevice::check(ls2d_find_correspondences_in(h, fixed_set, moving_set, 0, 0, lv, fi.data(), mi.data(), &n),
                         "MultiAligner2D::compute");
-    slice->_correspondences.clear();
-    for (int k = 0; k < n; ++k)
-      if (inlier[k]) slice->_correspondences.push_back(Correspondence(fi[k], mi[k]));
+      std::vector<uint8_t> inlier((size_t) (n > 0 ? n : 1), 1);
+      if (p.keep_only_inlier_correspondences && n > 0)
+        Ls2dDevice::check(ls2d_classify_correspondences(h, fixed_set, moving_set, 0, 0, ev, fi.data(), mi.data(), n,
+                                                        inlier.data()),
+                          "MultiAligner2D::compute");
+      for (int k = 0; k < n; ++k)
+        if (inlier[k]) s->_correspondences.push_back(Correspondence(fi[k], mi[k]));
+    };
   }
 
   static PointNormal2fVectorCloud* sliceCloud(PropertyContainerDynamic* scene, const std::string& name, const char* which) {
@@ -648,10 +654,7 @@ namespace srrg2_slam_interfaces {
     storeOutcome(r, its);
     // every slice's correspondences(): the last finder pass
     const Isometry2f before = lastFinderEstimate(r, its, init);
-    for (size_t s = 0; s < slices.size(); ++s) {
-      Ls2dDevice::check(ls2d_set_params(h, &p[s]), "MultiAligner2D::compute");
-      exportCorrespondences(h, p[s], fset[s], mset[s], slices[s], before);
-    }
+    for (size_t s = 0; s < slices.size(); ++s) exportCorrespondences(h, p[s], fset[s], mset[s], slices[s], before);
   }
 
   void MultiAligner2D::computeBatch(const std::vector<const PointNormal2fVectorCloud*>& fixed,

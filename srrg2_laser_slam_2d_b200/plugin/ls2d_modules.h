@@ -12,6 +12,7 @@
 //   MultiLoopDetectorBruteForce2D          gates L0.json:613-635
 #pragma once
 
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -327,14 +328,24 @@ namespace srrg2_slam_interfaces {
     virtual bool pointToPoint() const { return false; }  // SE2Point2PointErrorFactor instead of plane-to-plane
     // sensor_in_robot of this slice (identity unless WithSensor); throws if the tf lookup fails
     Isometry2f sensorInRobot() const;
-    const CorrespondenceVector& correspondences() const { return _correspondences; }
+    // the last finder pass of the aligner's compute().  The list is fetched from the device on first access (the
+    // clouds are still resident there): a tracker that never looks at it does not pay a launch and a download per frame
+    const CorrespondenceVector& correspondences() const {
+      if (_fetch_correspondences) {
+        std::function<void()> fetch;
+        fetch.swap(_fetch_correspondences);
+        fetch();
+      }
+      return _correspondences;
+    }
     const PointNormal2fVectorCloud* fixed() const { return _fixed; }
     const PointNormal2fVectorCloud* moving() const { return _moving; }
 
   protected:
     friend class MultiAligner2D;
     virtual void setupFactor() {}
-    CorrespondenceVector _correspondences;
+    mutable CorrespondenceVector _correspondences;
+    mutable std::function<void()> _fetch_correspondences;  // set by MultiAligner2D::compute
     const PointNormal2fVectorCloud* _fixed  = nullptr;
     const PointNormal2fVectorCloud* _moving = nullptr;
   };
@@ -401,6 +412,7 @@ namespace srrg2_slam_interfaces {
     srrg2_solver::IterationStatsVector _iteration_stats;
     Matrix3f _information_matrix;
     Ls2dDevice _device;
+    std::shared_ptr<int> _alive = std::make_shared<int>(0);  // what the slices' pending correspondence fetches watch
   };
   using MultiAligner2DPtr = std::shared_ptr<MultiAligner2D>;
 
