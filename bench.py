@@ -303,7 +303,8 @@ def measure_latency(sp, n_calls=200):
                    n_threads=1, want_iters=False)
     rec["oracle_1_thread_us"] = 1e6 * (time.perf_counter() - t0) / n
     rec["note"] = ("one MultiAligner2D::compute() per call through the plugin class: stage + upload 2 x 1081 points, "
-                   "aligner, download result and iteration records, re-run the finder for slice->correspondences(); "
+                   "aligner, download result and iteration records (slice->correspondences() is fetched from the device on first "
+                   "access, which the timed call does not make); "
                    "pageable host memory, nothing batched")
     return rec
 
