@@ -1001,6 +1001,7 @@ int ls2d_preprocess_scans(ls2d_handle* h, const ls2d_scan_params* sp, const floa
   if ((rc = reserve(h->d_misc, sizeof(float4) * n_pts + sizeof(int) * (size_t) n_scans))) return rc;
   float4* d_out = (float4*) h->d_misc.p;
   int* d_cnt    = (int*) ((char*) h->d_misc.p + sizeof(float4) * n_pts);
+  CU(cudaMemsetAsync(d_out, 0, sizeof(float4) * n_pts, h->stream));  // rows are copied out whole: zeros past the counts
   if ((rc = preprocess_dev(h, sp, (const float*) h->d_ranges.p, n_beams, n_scans, d_out, d_cnt, nullptr))) return rc;
   CU(cudaMemcpyAsync(out_points, d_out, sizeof(float4) * n_pts, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaMemcpyAsync(out_counts, d_cnt, sizeof(int) * (size_t) n_scans, cudaMemcpyDeviceToHost, h->stream));
@@ -1125,6 +1126,7 @@ static int clip_dev(ls2d_handle* h, const cloud_set& c, const int* ids_dev, cons
   memcpy(a.sensor_pose, sensor_xyt, sizeof(float) * a.pose_stride);
   a.out    = pack ? nullptr : (float4*) tmp.p;
   a.counts = pack ? nullptr : (int*) ((char*) tmp.p + out_bytes);
+  if (!pack) CU(cudaMemsetAsync(tmp.p, 0, out_bytes, h->stream));  // rows are copied out whole: zeros past the counts
   a.base   = 0;
   a.pack   = pack ? *pack : pack_target{};
   if (voxelize_resolution > 0.f) {  // scene_clipper_projective_2d.cpp:36-48
