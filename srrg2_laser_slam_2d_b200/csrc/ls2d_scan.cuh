@@ -8,9 +8,12 @@
 //                      order), optional voxelisation = runs of consecutive points in one voxel ("segments"),
 //                      segments ordered by a counting sort over 2048 order-preserving buckets of (ix, iy) plus a
 //                      rank inside the bucket (bitonic sort in shared memory when the buckets are too uneven), one
-//                      sequential sum per voxel in cloud order, ordered output.  The output goes straight into the
-//                      packed (CSR) cloud set: the CTAs agree on their offsets with a decoupled look-back over a
-//                      64-bit state word per scan, so there is no offsets pass and no second copy of the points.
+//                      sequential sum per voxel in cloud order, ordered output into the scan's strided row.  The
+//                      last CTA to finish turns the counts into CSR offsets (no offsets pass); a look-back inside
+//                      this kernel was measured and dropped: scans differ 3x in run time, and CTAs that wait for a
+//                      slow predecessor hold their SM slots (437 vs 294 us per 4096 scans)
+//  scan_pack_kernel    strided rows -> packed CSR points
+//  clip_voxel_kernel   the clipper's voxelize branch (same block_voxelize), rows placed by look-back
 //
 // Reference: R/sensor_processing/raw_data_preprocessor_projective_2d.cpp:13-51,77-104 (R/ =
 // /root/reference/srrg2_laser_slam_2d/src/srrg2_laser_slam_2d/); the upstream pieces (unprojector, normal
