@@ -87,7 +87,7 @@ __device__ __forceinline__ unsigned long long voxel_key(const voxel_params& V, f
 constexpr unsigned long long VOXEL_MASK = ~0x3FFFull;  // everything but the segment index
 constexpr unsigned long long NO_KEY     = ~0ull;      // per-point key of an invalid point
 
-constexpr int SCAN_T      = 384;  // threads per scan; at most 32 chunks => n_beams <= 12288 (and < 2^14: key layout)
+constexpr int SCAN_T      = 512;  // threads per scan; at most 32 chunks => n_beams <= 12288 (and < 2^14: key layout)
 constexpr int VOX_BUCKETS = 2048;
 // the rank inside the buckets costs sum(m_b^2) comparisons, the bitonic sort about S * log2(S)^2 / 2 compare-exchanges
 // of twice the price: above this many comparisons per segment the buckets are too uneven (a long wall at x = const)
