@@ -138,7 +138,8 @@ def test_track_batch_matches_the_oracle_chain(handle_factory, oracle, res, senso
     assert (got["status"] == 0).all()
 
 
-def test_track_batch_in_chunks_equals_the_three_calls(handle_factory):
+@pytest.mark.parametrize("iso,sensor", [(False, None), (True, (0.15, -0.05, 0.1))])
+def test_track_batch_in_chunks_equals_the_three_calls(handle_factory, iso, sensor):
     """2600 frames: ls2d_track_batch cuts the batch into chunks (uploads overlap the kernels, two compute lanes);
     results and the two cloud sets it leaves behind are those of pre-process -> clip -> align called one after the
     other on the whole batch."""
@@ -153,13 +154,21 @@ def test_track_batch_in_chunks_equals_the_three_calls(handle_factory):
     kw = dict(angle_min=raw.angle_min, angle_max=raw.angle_max)
     sp = default_scan_params(voxelize_resolution=0.02, **kw)
     sp_map = default_scan_params(voxelize_resolution=0.0, **kw)
-    h = handle_factory(default_params(canvas_cols=721, max_iterations=6))
+    akw = dict(canvas_cols=721, max_iterations=6)
+    sen = np.zeros(3, np.float32)
+    if sensor is not None:
+        akw.update(with_sensor=1, sensor_in_robot=sensor)
+        sen = np.float32(sensor)
+    if iso:  # poses as (tx, ty, c, s): the handle takes the format from the arrays' last dimension
+        to_iso = lambda p: np.stack([p[..., 0], p[..., 1], np.cos(p[..., 2]), np.sin(p[..., 2])], -1).astype(np.float32)
+        robots, init, sen = to_iso(robots), to_iso(init), to_iso(sen)
+    h = handle_factory(default_params(**akw))
     h.preprocess_scans_to_set(2, sp_map, raw.moving_ranges)
     got = h.track_batch(sp, ranges, 2, ids, robots, init).copy()
     fpts, foff = h.download_clouds(LS2D_FIXED, n, n * nb)
     mpts, moff = h.download_clouds(LS2D_MOVING, n, n * 721)
     h.preprocess_scans_to_set(LS2D_FIXED, sp, ranges)
-    h.clip_scenes_to_set(2, ids, robots, np.zeros(3, np.float32), LS2D_MOVING)
+    h.clip_scenes_to_set(2, ids, robots, sen, LS2D_MOVING)
     fpts2, foff2 = h.download_clouds(LS2D_FIXED, n, n * nb)
     mpts2, moff2 = h.download_clouds(LS2D_MOVING, n, n * 721)
     want = h.align_batch(init)
