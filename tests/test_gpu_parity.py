@@ -457,25 +457,6 @@ def test_zbuffer_ties_first_index_wins(handle_factory, oracle):
         assert (mi < 500).all()                                     # of each duplicated pair the first copy wins
 
 
-@pytest.mark.parametrize("variant", ["10", "11", "12", "13", "20", "24", "30", "31"])
-def test_streaming_kernel_variants_are_bit_exact(oracle, variant, monkeypatch):
-    """The shared-memory / L2-streaming kernel (the path of clouds > 4096 points) forced onto 1081-point clouds, the
-    generic-pointer kernel (20), the 384 x 3 shape of icp_fused2_kernel (24) and the two-pairs-per-CTA kernel with its
-    solver warp (30; 47 pairs: the last CTA owns a single pair) or with shared barriers (31): same algorithm, each with its own fixed reduction
-    shape, so the same bit-exact parity bar."""
-    from srrg2_laser_slam_2d_b200 import Handle
-    monkeypatch.setenv("LS2D_ICP_VARIANT", variant)
-    sp = make_scan_pairs(47, n_beams=1081, seed=404)
-    kw = dict(canvas_cols=1081, normal_cos=0.9)
-    with Handle(0, default_params(**kw)) as h:
-        upload(h, sp)
-        g, gi = h.align_batch(sp.init_xyt, want_iters=True)
-        o, oi = oracle.align_batch(oracle.default_params(**kw), sp.fixed_pts, sp.fixed_off, sp.moving_pts,
-                                   sp.moving_off, sp.init_xyt, sum_mode=oracle.SUM_TREE,
-                                   tree_threads=reduction_threads(1081, kw["canvas_cols"]), n_threads=oracle.max_threads())
-    assert_bit_exact(g, o, gi, oi)
-
-
 def test_chunked_host_pipeline_matches_the_resident_path(handle_factory):
     """ls2d_align_pairs_host cuts a batch into chunks whose uploads overlap the previous chunk's kernel: results must
     not depend on the chunking (ragged clouds, 2000 pairs -> three chunks of the host pipeline)."""
