@@ -1,5 +1,5 @@
 // ls2d_icp2.cuh -- icp_fused2_kernel: the instruction-diet version of icp_fused_kernel (same algorithm, same
-// decisions; see ls2d_kernels.cuh for the algorithm and the reference citations).
+// decisions; see ls2d_icp.cuh and ls2d_common.cuh for the algorithm and the reference citations).
 //
 // What changed, all of it aimed at the issue slots the ncu source view showed being spent on bookkeeping
 // (profiles/r01_icp_ncu_summary.md: phase 2 + reduction = 65 % of the executed warp instructions):
@@ -122,7 +122,7 @@ constexpr int BC_XTX = 0, BC_XTY = 4, BC_XC = 8, BC_XS = 12, BC_LC = 16, BC_LS =
 static_assert(sizeof(pose_bc) == 40, "pose_bc layout is addressed by byte offsets");
 
 // One winner against its fixed cell: gates of CorrespondenceFinderProjective2f (.cpp:61-73), SE2Plane2PlaneErrorFactor,
-// Cauchy, H/b terms -- operation for operation the arithmetic of linearize_point() (ls2d_kernels.cuh).  FIRST: the
+// Cauchy, H/b terms -- operation for operation the arithmetic of linearize_point() (ls2d_common.cuh).  FIRST: the
 // thread's sums are still zero, assign instead of add.
 template <bool SENSOR, bool FIRST>
 __device__ __forceinline__ void linearize2(const dev_params& P, float fd, const float4 F, float Mx, float My,

@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the sharded-verification host logic (CPU only): contiguous candidate split,
-all-gather of the 32-byte best records, identical deterministic winner on every rank."""
+all-gather of the 48-byte best records, identical deterministic winner on every rank."""
 import os
 import sys
 
