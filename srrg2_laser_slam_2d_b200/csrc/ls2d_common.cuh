@@ -121,13 +121,17 @@ struct pose_bc {
   int tie;                 // set by a failed optimistic z-buffer claim
 };
 
-__device__ __forceinline__ void publish_pose(pose_bc* bc, const dev_params& P, const iso& X,
-                                             bool with_sensor, int stop) {
+// the pose fields only (a Levenberg-Marquardt trial pose: the other threads may still be reading bc->stop)
+__device__ __forceinline__ void publish_trial_pose(pose_bc* bc, const dev_params& P, const iso& X, bool with_sensor) {
   const iso L = with_sensor ? iso_compose(P.Sinv, X) : X;
   const iso W = iso_inverse(iso_inverse(L));
   bc->Xtx = X.tx, bc->Xty = X.ty, bc->Xc = X.c, bc->Xs = X.s;
   bc->Lc = W.c, bc->Ls = W.s;
   bc->Wtx = W.tx, bc->Wty = W.ty;
+}
+__device__ __forceinline__ void publish_pose(pose_bc* bc, const dev_params& P, const iso& X,
+                                             bool with_sensor, int stop) {
+  publish_trial_pose(bc, P, X, with_sensor);
   bc->stop = stop;
 }
 

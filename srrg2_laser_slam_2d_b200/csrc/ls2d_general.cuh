@@ -31,6 +31,8 @@ struct general_shared {
   int lm_started, lm_trial, lm_pending, lm_done, lm_rejected;
   float chi_prev;
   int n_corr_last;
+  int phase_done;        // the termination criterion ended the phase: written by thread 0 between the round's last two
+                         // barriers and read after the last one (bc->stop is written before them and read between them)
 };
 
 constexpr size_t icp_general_smem_bytes(int cols, int threads, int max_points) {
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(T, 2) icp_general_kernel(const dev_params P, c
     bc->tie = 0;
     for (int k = 0; k < NSUM; ++k) gs->v[k] = 0.f;
     gs->n_in = gs->n_k = 0;
+    gs->phase_done = 0;
     gs->lm_started = 0, gs->lm_rejected = 0;
     gs->lambda = 0.0;
     gs->n_corr_last = 0;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(T, 2) icp_general_kernel(const dev_params P, c
               if (solve3d(v, gs->D[0], gs->D[1], gs->D[2], dx)) {
                 gs->dx[0] = dx[0], gs->dx[1] = dx[1], gs->dx[2] = dx[2];
                 gs->Xt    = iso_compose(gs->X, iso_v2t(dx[0], dx[1], dx[2]));
-                publish_pose(bc, P, gs->Xt, SENSOR, 0);
+                publish_trial_pose(bc, P, gs->Xt, SENSOR);  // bc->stop is 0 and stays
                 gs->lm_pending = 1;
                 break;
               }
@@ -286,10 +289,11 @@ __global__ void __launch_bounds__(T, 2) icp_general_kernel(const dev_params P, c
         if (P.termination_epsilon > 0.f && k > 0 && fsub(gs->chi_prev, chi) < fmul(P.termination_epsilon, gs->chi_prev))
           stop = STOP_PHASE_DONE;  // T1
         gs->chi_prev = chi;
-        publish_pose(bc, P, X, SENSOR, stop);
+        publish_trial_pose(bc, P, X, SENSOR);  // bc->stop stays 0: other threads may still be reading it
+        gs->phase_done = stop;
       }
       __syncthreads();
-      const int stop = bc->stop;
+      const int stop = bc->stop ? bc->stop : gs->phase_done;
       if (stop && stop != STOP_PHASE_DONE) {
         status = stop - 1;
         break;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(T, 2) icp_general_kernel(const dev_params P, c
       if (stop == STOP_PHASE_DONE) break;
     }
     __syncthreads();  // everybody has read bc->stop before thread 0 of the next phase clears it
-    if (tid == 0) bc->stop = 0;
+    if (tid == 0) bc->stop = 0, gs->phase_done = 0;
     __syncthreads();
   }
 
