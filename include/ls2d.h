@@ -218,7 +218,9 @@ int ls2d_align_batch(ls2d_handle* h, const int32_t* fixed_id, const int32_t* mov
 int ls2d_align_batch_dev(ls2d_handle* h, const int32_t* fixed_id_dev, const int32_t* moving_id_dev,
                          const float* init_pose_dev, int32_t n_pairs, ls2d_result* out_dev,
                          ls2d_iter_stats* iter_stats_dev);
-/* one call from host buffers: upload both cloud sets, align pair p = (fixed p, moving p), download */
+/* one call from host buffers: upload both cloud sets, align pair p = (fixed p, moving p), download.  The batch is
+ * cut into chunks whose uploads overlap the previous chunk's kernel; pinned (or registered) buffers go to the copy
+ * engine directly, pageable ones through the handle's pinned ring filled by a few copy threads */
 int ls2d_align_pairs_host(ls2d_handle* h, const float* fixed_points, const int32_t* fixed_offsets,
                           const float* moving_points, const int32_t* moving_offsets,
                           const float* init_pose, int32_t n_pairs, ls2d_result* out);
@@ -379,7 +381,10 @@ int ls2d_clip_scenes_to_set(ls2d_handle* h, int scene_set, const int32_t* cloud_
  * pre-processed into the measurement cloud (fixed), local map scene_ids[f] of resident set `scene_set` (>= 2) is
  * clipped from robot_in_local_map[f] * sensor_in_robot (sensor_in_robot = the handle's params when with_sensor,
  * else identity) into the moving cloud, and the aligner runs from init_pose[f] (NULL: identity).  Only 4 B/beam,
- * ids and poses go to the device, 80 B/frame come back.  Overwrites sets LS2D_FIXED and LS2D_MOVING. */
+ * ids and poses go to the device, 80 B/frame come back.  Overwrites sets LS2D_FIXED and LS2D_MOVING (they hold the
+ * whole batch afterwards).  Large batches are pipelined in chunks: the next chunk's ranges upload while the current one
+ * runs, the pre-processor shares the GPU with the previous chunk's clipper and aligner.  Pageable `ranges` are staged
+ * through the handle's pinned ring. */
 int ls2d_track_batch(ls2d_handle* h, const ls2d_scan_params* sp, const float* ranges, int32_t n_beams, int32_t n,
                      int scene_set, const int32_t* scene_ids, const float* robot_in_local_map_pose,
                      const float* init_pose, ls2d_result* out);
