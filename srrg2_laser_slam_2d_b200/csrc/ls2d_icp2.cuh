@@ -124,7 +124,7 @@ static_assert(sizeof(pose_bc) == 40, "pose_bc layout is addressed by byte offset
 // One winner against its fixed cell: gates of CorrespondenceFinderProjective2f (.cpp:61-73), SE2Plane2PlaneErrorFactor,
 // Cauchy, H/b terms -- operation for operation the arithmetic of linearize_point() (ls2d_common.cuh).  FIRST: the
 // thread's sums are still zero, assign instead of add.
-template <bool SENSOR, bool FIRST>
+template <bool SENSOR, bool FIRST, bool P2P = false>
 __device__ __forceinline__ void linearize2(const dev_params& P, float fd, const float4 F, float Mx, float My,
                                            float2 Mn, float rho, float Xtx, float Xty, float Xc, float Xs, float Lc,
                                            float Ls, float (&acc)[NSUM], unsigned& cnt) {
@@ -147,6 +147,34 @@ __device__ __forceinline__ void linearize2(const dev_params& P, float fd, const 
     p = add2(mk2(fadd(pa.x, pb.x), fadd(pa.y, pb.y)), mk2(Xtx, Xty));
   }
   const f2 d  = add2(p, mk2(-F.x, -F.y));
+  if (P2P) {
+    // SE2Point2PointErrorFactor[WithSensor] (oracle decision D19): e = p - p_fixed, J = [R | R (-y, x)^T], Omega = I2;
+    // operation for operation the point-to-point arm of linearize_point() (ls2d_common.cuh)
+    const float jc0 = fadd(fmul(Lc, -My), fmul(-Ls, Mx));
+    const float jc1 = fadd(fmul(Ls, -My), fmul(Lc, Mx));
+    const float chi = fadd(fmul(d.x, d.x), fmul(d.y, d.y));
+    float w = 1.f, chi_in = chi, chi_k = 0.f;
+    if (P.tau > 0.f && !(chi < P.tau)) {  // RobustifierCauchy
+      const float aux = fadd(fmul(chi, P.inv_tau), 1.f);
+      chi_k           = fmul(P.tau, __logf(aux));  // statistics only (tolerance parity)
+      w               = frcp(aux);
+      chi_in          = 0.f;
+      cnt += 1u << 16;
+    } else {
+      cnt += 1u;
+    }
+    const float wc = fmul(Lc, w), ws = fmul(Ls, w), wms = fmul(-Ls, w), wj0 = fmul(jc0, w), wj1 = fmul(jc1, w);
+    const float t[9] = {fadd(fmul(wc, Lc), fmul(ws, Ls)),    fadd(fmul(wc, -Ls), fmul(ws, Lc)),
+                        fadd(fmul(wc, jc0), fmul(ws, jc1)),  fadd(fmul(wms, -Ls), fmul(wc, Lc)),
+                        fadd(fmul(wms, jc0), fmul(wc, jc1)), fadd(fmul(wj0, jc0), fmul(wj1, jc1)),
+                        fadd(fmul(wc, d.x), fmul(ws, d.y)),  fadd(fmul(wms, d.x), fmul(wc, d.y)),
+                        fadd(fmul(wj0, d.x), fmul(wj1, d.y))};
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = FIRST ? t[q] : fadd(acc[q], t[q]);
+    acc[9]  = FIRST ? chi_in : fadd(acc[9], chi_in);
+    acc[10] = FIRST ? chi_k : fadd(acc[10], chi_k);
+    return;
+  }
   const f2 de = mul2(d, fn);
   const float e0 = fadd(de.x, de.y);
   const f2 e12 = add2(mk2(nx, ny), mk2(-F.z, -F.w));  // e1, e2
@@ -303,8 +331,9 @@ __device__ __forceinline__ void store_partials2(const float (&acc)[NSUM], unsign
   if (lane == 0) sm::st_u32<NSUM * 4>(rrow, wcnt);
 }
 
-template <int T, int PPT, bool SENSOR, int MINB, int CS, bool FUSED = true>
+template <int T, int PPT, bool SENSOR, int MINB, int CS, bool FUSED = true, bool P2P = false>
 __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P, const align_args A) {
+  static_assert(!(FUSED && P2P), "the fused accumulation arithmetic (D18) is the plane-to-plane factor's");
   using M = icp2_map<T, PPT, CS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned sb = sm::addr(smem_raw);
@@ -463,7 +492,7 @@ __global__ void __launch_bounds__(T, MINB) icp_fused2_kernel(const dev_params P,
         if (FUSED)
           linearize2f<SENSOR, J == 0>(P, fd, F, mp[J].x, mp[J].y, Mn, u2f(rb[J]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
         else
-          linearize2<SENSOR, J == 0>(P, fd, F, mp[J].x, mp[J].y, Mn, u2f(rb[J]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+          linearize2<SENSOR, J == 0, P2P>(P, fd, F, mp[J].x, mp[J].y, Mn, u2f(rb[J]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
       }
     });
     store_partials2(acc, cnt, wt, rrow, lane);

@@ -32,7 +32,7 @@ shape pick_shape(int max_points) {
 shape resolve_shape(const dev_params& dp, int max_points) {
   shape s = pick_shape(max_points);
   // (its projection takes the range gate on the squared range and a square root that is exact above 1e-30 m^2)
-  if (s.kind == 3 && (dp.cam.cols >= s.cs || dp.factor != LS2D_FACTOR_PLANE2PLANE || dp.gate2.lo < 1.0e-30f)) {
+  if (s.kind == 3 && (dp.cam.cols >= s.cs || dp.gate2.lo < 1.0e-30f)) {
     s = s.cs == 768 ? shape{256, 3, 3, 0, 0} : shape{288, 4, 4, 0, 0};
   }
   if (s.kind == 0 && icp_smem_bytes(dp.cam.cols, s.threads, s.ppt) > SMEM_LIMIT) s = {512, 0, 2, 1, 0};
@@ -57,10 +57,10 @@ int launch_icp_t(ls2d_handle* h, const align_args& a) {
   return h->dp.with_sensor ? launch_icp_k<T, PPT, true, MINB>(h, a) : launch_icp_k<T, PPT, false, MINB>(h, a);
 }
 
-template <int T, int PPT, bool SENSOR, int MINB, int CS, bool FUSED>
+template <int T, int PPT, bool SENSOR, int MINB, int CS, bool FUSED, bool P2P>
 int launch_icp2_k(ls2d_handle* h, const align_args& a) {
   constexpr size_t smem = icp2_map<T, PPT, CS>::BYTES;
-  auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, CS, FUSED>;
+  auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, CS, FUSED, P2P>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
@@ -69,10 +69,10 @@ int launch_icp2_k(ls2d_handle* h, const align_args& a) {
   return LS2D_OK;
 }
 
-template <int T, int PPT, int MINB, int CS, bool FUSED>
+template <int T, int PPT, int MINB, int CS, bool FUSED, bool P2P = false>
 int launch_icp2_t(ls2d_handle* h, const align_args& a) {
-  return h->dp.with_sensor ? launch_icp2_k<T, PPT, true, MINB, CS, FUSED>(h, a)
-                           : launch_icp2_k<T, PPT, false, MINB, CS, FUSED>(h, a);
+  return h->dp.with_sensor ? launch_icp2_k<T, PPT, true, MINB, CS, FUSED, P2P>(h, a)
+                           : launch_icp2_k<T, PPT, false, MINB, CS, FUSED, P2P>(h, a);
 }
 
 template <int T, bool SENSOR, int MINB>
@@ -93,7 +93,10 @@ bool needs_general(const dev_params& dp) {
 }
 
 // the 1152-stride kernel accumulates with fused multiply-adds unless the caller asked for single-rounding sums
-bool fused_accumulation(const shape& s, bool single_rounding) { return s.kind == 3 && s.cs == 1152 && !single_rounding; }
+// (plane-to-plane only: D18 restates that factor's arithmetic)
+bool fused_accumulation(const shape& s, const dev_params& dp, bool single_rounding) {
+  return s.kind == 3 && s.cs == 1152 && !single_rounding && dp.factor == LS2D_FACTOR_PLANE2PLANE;
+}
 
 }  // namespace
 
@@ -102,9 +105,12 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   const int maxp = h->sets[0].max_points > h->sets[1].max_points ? h->sets[0].max_points : h->sets[1].max_points;
   if (needs_general(h->dp) && !a.score_only) return launch_general(h, a, maxp);
   const shape s = resolve_shape(h->dp, maxp);
+  const bool p2p = h->dp.factor == LS2D_FACTOR_POINT2POINT;  // the factor is a template switch of the kernel
+  if (s.kind == 3 && s.cs == 1152 && p2p) return launch_icp2_t<288, 4, 4, 1152, false, true>(h, a);
+  if (s.kind == 3 && s.cs == 768 && p2p) return launch_icp2_t<256, 3, 5, 768, false, true>(h, a);
   if (s.kind == 3 && s.cs == 1152)
-    return fused_accumulation(s, h->prm.single_rounding_accumulation != 0) ? launch_icp2_t<288, 4, 4, 1152, true>(h, a)
-                                                                           : launch_icp2_t<288, 4, 4, 1152, false>(h, a);
+    return fused_accumulation(s, h->dp, h->prm.single_rounding_accumulation != 0) ? launch_icp2_t<288, 4, 4, 1152, true>(h, a)
+                                                                                  : launch_icp2_t<288, 4, 4, 1152, false>(h, a);
   if (s.kind == 3 && s.cs == 768) return launch_icp2_t<256, 3, 5, 768, false>(h, a);  // measured faster unfused
   if (s.kind == 1) return h->dp.with_sensor ? launch_stream_k<512, true, 2>(h, a, maxp) : launch_stream_k<512, false, 2>(h, a, maxp);
 #define LS2D_CASE(T, P, B) \
@@ -124,7 +130,7 @@ int icp_reduction_shape(const dev_params& dp, bool single_rounding, int max_poin
   if (needs_general(dp)) return 512;  // icp_general_kernel: xor-butterfly, single-rounding
   const shape s = resolve_shape(dp, max_points);
   if (s.kind < 0) return LS2D_ERR_UNSUPPORTED;
-  return s.threads | (s.kind == 3 ? 1 << 16 : 0) | (fused_accumulation(s, single_rounding) ? 1 << 17 : 0);
+  return s.threads | (s.kind == 3 ? 1 << 16 : 0) | (fused_accumulation(s, dp, single_rounding) ? 1 << 17 : 0);
 }
 
 }  // namespace ls2d

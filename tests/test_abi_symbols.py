@@ -43,10 +43,11 @@ def test_host_side_helpers_need_no_gpu():
     assert lib.ls2d_version() == 200
     assert lib.ls2d_strerror(0) == b"ok"
     # the 1081-beam shape: 288 threads, two-half warp combine, fused accumulation -- unless the caller asks for
-    # single-rounding sums, the point-to-point factor (run-time-shaped kernel) or an option only the general kernel has
+    # single-rounding sums, the point-to-point factor or an option only the general kernel has
     assert _abi.reduction_threads(1081) == 288 | 1 << 16 | 1 << 17
     assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, single_rounding_accumulation=1)) == 288 | 1 << 16
-    assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, factor=_abi.FACTOR_POINT2POINT)) == 288
+    # the point-to-point factor is a template switch of the same kernel: its shape, single-rounding sums
+    assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, factor=_abi.FACTOR_POINT2POINT)) == 288 | 1 << 16
     assert _abi.reduction_threads(721, 721) == 256 | 1 << 16
     assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, algorithm=_abi.ALGORITHM_LM)) == 512
     assert _abi.reduction_threads(1081, 4000) == 288                      # canvas wider than the compile-time stride
