@@ -860,7 +860,7 @@ def main():
     ap.add_argument("--verify-candidates", type=int, default=65536,
                     help="candidates of the sharded verification sub-record (0: skip it)")
     ap.add_argument("--guesses", type=int, default=8)
-    ap.add_argument("--unique", type=int, default=4096, help="allpairs: distinct map clouds")
+    ap.add_argument("--unique", type=int, default=20000, help="allpairs: distinct map clouds (default: every map its own)")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back launches for the sustained sub-record")
     ap.add_argument("--maps", type=int, default=20000, help="allpairs: local maps")
     ap.add_argument("--map-points", type=int, default=8192, help="allpairs: points per local map")
