@@ -43,7 +43,7 @@
  *      correspondence.
  *  D16 H and b are the binary32 sums of the slices' totals in slice order, the prior last.
  *  D17 max_iterations, min_num_inliers and damping are aligner-level (read from slice 0's record).
- *  D18 fused accumulation arithmetic of the 1152-stride kernel (see contribution_fused below).
+ *  D18 fused accumulation arithmetic of the compile-time-stride kernels (see contribution_fused below).
  *  Options north_star names but the shipped configurations never switch on (all UNPINNED restatements):
  *  D19 factor POINT2POINT = SE2Point2PointErrorFactor[WithSensor] on VariableSE2Right: e = X p_m - p_f
  *      (S^-1 (X p_m) - p_f), J = [R | R (-y, x)^T] with R the rotation of X (of S^-1 X), Omega = I2,
@@ -555,7 +555,7 @@ static void linearize(const orc_params* prm, orc_iso X, const orc_point* fixed,
     }
     float* p = part + (size_t)(i % T) * NSLOT;
     int inl;
-    if (fused) { /* D18: the plane-to-plane factor of the 1152-stride kernel only */
+    if (fused) { /* D18: the plane-to-plane factor of the compile-time-stride kernels only */
       inl = contribution_fused(prm, &f, fixed[fx_of[i]], moving[i], p);
     } else {
       float v[NSLOT];

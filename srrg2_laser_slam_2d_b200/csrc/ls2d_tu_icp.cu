@@ -18,7 +18,7 @@ struct shape {
 shape pick_shape(int max_points) {
   if (max_points <= 256) return {128, 2, 6, 0, 0};
   if (max_points <= 512) return {128, 4, 6, 0, 0};
-  if (max_points <= 768) return {256, 3, 5, 3, 768};    // 721 beams: 0.276 ms per 4096 pairs
+  if (max_points <= 768) return {256, 3, 5, 3, 768};    // 721 beams: 0.246 ms per 4096 pairs
   if (max_points <= 1152) return {288, 4, 4, 3, 1152};  // 1081 beams: the headline shape
   if (max_points <= 1536) return {256, 6, 2, 0, 0};
   if (max_points <= 2048) return {256, 8, 2, 0, 0};
@@ -92,10 +92,11 @@ bool needs_general(const dev_params& dp) {
   return dp.algorithm != LS2D_ALGORITHM_GN || dp.inlier_only_runs || dp.termination_epsilon > 0.f;
 }
 
-// the 1152-stride kernel accumulates with fused multiply-adds unless the caller asked for single-rounding sums
+// the compile-time-stride kernels accumulate with fused multiply-adds unless the caller asked for single-rounding
+// sums (721-beam shape: 0.2553 -> 0.2457 ms per 4096 pairs)
 // (plane-to-plane only: D18 restates that factor's arithmetic)
 bool fused_accumulation(const shape& s, const dev_params& dp, bool single_rounding) {
-  return s.kind == 3 && s.cs == 1152 && !single_rounding && dp.factor == LS2D_FACTOR_PLANE2PLANE;
+  return s.kind == 3 && !single_rounding && dp.factor == LS2D_FACTOR_PLANE2PLANE;
 }
 
 }  // namespace
@@ -111,7 +112,9 @@ int launch_icp(ls2d_handle* h, const align_args& a) {
   if (s.kind == 3 && s.cs == 1152)
     return fused_accumulation(s, h->dp, h->prm.single_rounding_accumulation != 0) ? launch_icp2_t<288, 4, 4, 1152, true>(h, a)
                                                                                   : launch_icp2_t<288, 4, 4, 1152, false>(h, a);
-  if (s.kind == 3 && s.cs == 768) return launch_icp2_t<256, 3, 5, 768, false>(h, a);  // measured faster unfused
+  if (s.kind == 3 && s.cs == 768)
+    return fused_accumulation(s, h->dp, h->prm.single_rounding_accumulation != 0) ? launch_icp2_t<256, 3, 5, 768, true>(h, a)
+                                                                                  : launch_icp2_t<256, 3, 5, 768, false>(h, a);
   if (s.kind == 1) return h->dp.with_sensor ? launch_stream_k<512, true, 2>(h, a, maxp) : launch_stream_k<512, false, 2>(h, a, maxp);
 #define LS2D_CASE(T, P, B) \
   if (s.kind == 0 && s.threads == T && s.ppt == P && s.minb == B) return launch_icp_t<T, P, B>(h, a);

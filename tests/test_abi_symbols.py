@@ -48,7 +48,7 @@ def test_host_side_helpers_need_no_gpu():
     assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, single_rounding_accumulation=1)) == 288 | 1 << 16
     # the point-to-point factor is a template switch of the same kernel: its shape, single-rounding sums
     assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, factor=_abi.FACTOR_POINT2POINT)) == 288 | 1 << 16
-    assert _abi.reduction_threads(721, 721) == 256 | 1 << 16
+    assert _abi.reduction_threads(721, 721) == 256 | 1 << 16 | 1 << 17
     assert _abi.reduction_threads(1081, params=_abi.default_params(canvas_cols=1081, algorithm=_abi.ALGORITHM_LM)) == 512
     assert _abi.reduction_threads(1081, 4000) == 288                      # canvas wider than the compile-time stride
     assert _abi.reduction_threads(4096, 7680) == 512                      # 247 KB in the register kernel: falls back to streaming
