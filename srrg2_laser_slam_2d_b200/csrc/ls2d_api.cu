@@ -551,6 +551,9 @@ static int multi_dev_impl(ls2d_handle* h, const ls2d_params* slices, const int32
   }
   if (a.max_cols > 0xFFFE) return LS2D_ERR_UNSUPPORTED;
   a.n_slices    = n_slices;
+  a.fused       = 1;
+  for (int s = 0; s < n_slices; ++s)
+    if (slices[s].single_rounding_accumulation) a.fused = 0;
   a.fixed_id    = fid;
   a.moving_id   = mid;
   a.init_pose   = init;
@@ -1322,6 +1325,9 @@ int ls2d_multi_reduction_shape(const ls2d_params* slices, int32_t n_slices, int3
     if (slices[s].canvas_cols > a.max_cols) a.max_cols = slices[s].canvas_cols;
   }
   a.n_slices         = n_slices;
+  a.fused            = 1;
+  for (int s = 0; s < n_slices; ++s)
+    if (slices[s].single_rounding_accumulation) a.fused = 0;
   a.max_points       = max_fixed_points > max_moving_points ? max_fixed_points : max_moving_points;
   a.max_fixed_points = max_fixed_points;
   if (!shared_moving)

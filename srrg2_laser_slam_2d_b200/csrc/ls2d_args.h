@@ -133,6 +133,8 @@ struct multi_args {
   int n_slices;
   int max_cols, max_points;  // capacity of the shared z-buffer / stash
   int max_fixed_points;      // the largest fixed cloud alone (kernel selection)
+  int fused;                 // icp_multi2_kernel: the fused accumulation arithmetic (D18) unless a slice asks for
+                             // single-rounding sums
   const int* fixed_id;       // nullable: pair index
   const int* moving_id;      // nullable: pair index
   const float* init_pose;    // pose_stride floats per pair

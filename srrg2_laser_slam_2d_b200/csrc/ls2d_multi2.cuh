@@ -34,7 +34,7 @@ struct multi2_map {
   static_assert(CS % 4 == 0, "column stride keeps the float4 images 16-byte aligned");
 };
 
-template <int T, int PPF, int PPM, int CS>
+template <int T, int PPF, int PPM, int CS, bool FUSED>
 __global__ void __launch_bounds__(T, 3) icp_multi2_kernel(const multi_args A) {
   using M = multi2_map<T, PPF, PPM, CS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -207,10 +207,18 @@ __global__ void __launch_bounds__(T, 3) icp_multi2_kernel(const multi_args A) {
         const float fd  = sm::ld_f32<M::FD>(za[j]);
         const float4 F  = sm::ld_f32x4<0>(4u * za[j] - fk);
         const float2 Mn = sm::ld_f32x2<0>(sb + M::MNRM + 8u * (unsigned) (j * T + tid));
-        if (P.with_sensor)
-          linearize2<true, false>(P, fd, F, mp[j].x, mp[j].y, Mn, u2f(rb[j]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
-        else
-          linearize2<false, false>(P, fd, F, mp[j].x, mp[j].y, Mn, u2f(rb[j]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+        // FUSED: the accumulation arithmetic of decision D18 (ls2d_icp2.cuh: linearize2f), else single-rounding sums
+        if (P.with_sensor) {
+          if (FUSED)
+            linearize2f<true, false>(P, fd, F, mp[j].x, mp[j].y, Mn, u2f(rb[j]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+          else
+            linearize2<true, false>(P, fd, F, mp[j].x, mp[j].y, Mn, u2f(rb[j]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+        } else {
+          if (FUSED)
+            linearize2f<false, false>(P, fd, F, mp[j].x, mp[j].y, Mn, u2f(rb[j]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+          else
+            linearize2<false, false>(P, fd, F, mp[j].x, mp[j].y, Mn, u2f(rb[j]), Xtx, Xty, Xc, Xs, Lc, Ls, acc, cnt);
+        }
         sm::st_u32<0>(za[j], Z_EMPTY_DEPTH);
         if (tied) sm::st_u32<M::ZI>(za[j], Z_EMPTY_IDX);
       }

@@ -22,13 +22,15 @@ bool multi2_serves(const multi_args& a) {
 
 int multi_reduction_threads() { return MULTI_THREADS; }
 
-int multi_reduction_shape(const multi_args& a) { return multi2_serves(a) ? (M2_T | 1 << 16) : MULTI_THREADS; }
+int multi_reduction_shape(const multi_args& a) {
+  return multi2_serves(a) ? (M2_T | 1 << 16 | (a.fused ? 1 << 17 : 0)) : MULTI_THREADS;
+}
 
 int launch_multi(ls2d_handle* h, const multi_args& a, const int* cols) {
   if (a.n_pairs <= 0) return LS2D_OK;
   if (multi2_serves(a)) {
     using map = multi2_map<M2_T, M2_PPF, M2_PPM, M2_CS>;
-    auto kern = icp_multi2_kernel<M2_T, M2_PPF, M2_PPM, M2_CS>;
+    auto kern = a.fused ? icp_multi2_kernel<M2_T, M2_PPF, M2_PPM, M2_CS, true> : icp_multi2_kernel<M2_T, M2_PPF, M2_PPM, M2_CS, false>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, map::BYTES));
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<a.n_pairs, M2_T, map::BYTES, h->stream>>>(a);

@@ -52,7 +52,7 @@ def test_golden_multi_slice_with_prior(handle_factory, oracle):
         kw = dict(prior=make_prior(d["prior_info"]), prior_z=d["odom_xyt"]) if with_prior else {}
         okw = dict(prior=oracle.make_prior(d["prior_info"]), prior_z=d["odom_xyt"]) if with_prior else {}
         g, gi = h.align_multi(sl, [0, 2], [1, 1], d["init_xyt"], want_iters=True, **kw)
-        assert shape_of(sl, 721) == 256 | 1 << 16           # the MULTI.json shape runs icp_multi2_kernel
+        assert shape_of(sl, 721) == 256 | 1 << 16 | 1 << 17  # the MULTI.json shape runs icp_multi2_kernel (fused sums)
         o, oi = oracle.align_multi_batch(osl, fixed, moving, d["init_xyt"], sum_mode=oracle.SUM_TREE,
                                          tree_threads=shape_of(sl, 721), **okw)
         assert_bit_exact(g, o, gi, oi)                      # kernel's summation order: every bit
@@ -174,7 +174,7 @@ def test_two_slices_with_moving_sets_of_their_own_run_the_general_kernel(handle_
     osl = slices_for(oracle.default_params, msp.sensors, cols=541)
     fixed = [(msp.fixed_pts[s], msp.fixed_off[s]) for s in range(2)]
     moving = [(msp.moving_pts, msp.moving_off)] * 2
-    assert shape_of(sl, 541, shared=False) == MULTI_T and shape_of(sl, 541) == 256 | 1 << 16
+    assert shape_of(sl, 541, shared=False) == MULTI_T and shape_of(sl, 541) == 256 | 1 << 16 | 1 << 17
     g, gi = h.align_multi(sl, [0, 2], [1, 3], msp.init_xyt, want_iters=True)
     o, oi = oracle.align_multi_batch(osl, fixed, moving, msp.init_xyt, sum_mode=oracle.SUM_TREE, tree_threads=MULTI_T)
     assert_bit_exact(g, o, gi, oi)

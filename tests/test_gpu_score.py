@@ -146,7 +146,7 @@ def test_lock_free_cell_hand_back_is_deterministic(handle_factory):
     first_s = h.score_batch(poses).tobytes()
     sl = [default_params(canvas_cols=721, normal_cos=0.8, max_iterations=4, with_sensor=1, sensor_in_robot=(0.1, 0.0, 0.0)),
           default_params(canvas_cols=721, normal_cos=0.8, max_iterations=4, with_sensor=1, sensor_in_robot=(-0.1, 0.0, 0.1))]
-    assert multi_reduction_threads(sl, 721, 721, True) == 256 | 1 << 16       # icp_multi2_kernel serves this shape
+    assert multi_reduction_threads(sl, 721, 721, True) == 256 | 1 << 16 | 1 << 17   # icp_multi2_kernel serves this shape
     first_m = h.align_multi(sl, [LS2D_FIXED, 2], [LS2D_MOVING, LS2D_MOVING], poses).tobytes()
     for _ in range(40):
         assert h.score_batch(poses).tobytes() == first_s
