@@ -10,6 +10,10 @@
 #include <new>
 #include <vector>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "ls2d_internal.h"
 
 using namespace ls2d;
@@ -25,6 +29,18 @@ void set_last_cuda_error(cudaError_t e, const char* what) {
 }
 
 int pose_stride(const ls2d_handle* h) { return h->pose_format == LS2D_POSE_ISO ? 4 : 3; }
+
+int grant_shared_memory(int device, const void* kernel, size_t bytes, bool max_carveout) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& have = granted[{device, kernel}];
+  if (have >= bytes && have != 0) return LS2D_OK;
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
+  if (max_carveout) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  have = bytes > 0 ? bytes : 1;
+  return LS2D_OK;
+}
 
 int reserve(scratch& s, size_t bytes) {
   if (bytes <= s.cap) return LS2D_OK;

@@ -91,6 +91,15 @@ void set_last_cuda_error(cudaError_t e, const char* what);
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;  // dynamic shared memory a CTA can opt into on sm_100a
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize [, PreferredSharedMemoryCarveout]) only when a kernel asks for more
+// than it was ever granted on this device: the attribute is an upper bound, and two driver calls per launch are
+// measurable on the single-pair path.  (ls2d_api.cu; process-wide, per device and kernel)
+int grant_shared_memory(int device, const void* kernel, size_t bytes, bool max_carveout);
+template <typename K>
+int configure_kernel(const ls2d_handle* h, K kernel, size_t bytes, bool max_carveout = true) {
+  return grant_shared_memory(h->device, reinterpret_cast<const void*>(kernel), bytes, max_carveout);
+}
+
 int reserve(scratch& s, size_t bytes);
 int pose_stride(const ls2d_handle* h);
 

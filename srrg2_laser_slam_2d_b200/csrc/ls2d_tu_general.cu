@@ -11,11 +11,11 @@ int launch_general(ls2d_handle* h, const align_args& a, int max_points) {
   if (max_points > 65535 || smem > SMEM_LIMIT) return LS2D_ERR_UNSUPPORTED;
   if (h->dp.with_sensor) {
     auto kern = icp_general_kernel<T, true>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (int rc = configure_kernel(h, kern, (size_t) ((int) smem), false)) return rc;
     kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a, max_points);
   } else {
     auto kern = icp_general_kernel<T, false>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (int rc = configure_kernel(h, kern, (size_t) ((int) smem), false)) return rc;
     kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a, max_points);
   }
   CU(cudaGetLastError());

@@ -43,9 +43,7 @@ template <int T, int PPT, bool SENSOR, int MINB>
 int launch_icp_k(ls2d_handle* h, const align_args& a) {
   const size_t smem = icp_smem_bytes(h->dp.cam.cols, T, PPT);
   auto kern         = icp_fused_kernel<T, PPT, SENSOR, MINB>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  // the kernel keeps its working set in shared memory and registers; give it the whole carve-out
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (int rc = configure_kernel(h, kern, (size_t) ((int) smem))) return rc;
   kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
@@ -61,8 +59,7 @@ template <int T, int PPT, bool SENSOR, int MINB, int CS, bool FUSED, bool P2P>
 int launch_icp2_k(ls2d_handle* h, const align_args& a) {
   constexpr size_t smem = icp2_map<T, PPT, CS>::BYTES;
   auto kern             = icp_fused2_kernel<T, PPT, SENSOR, MINB, CS, FUSED, P2P>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (int rc = configure_kernel(h, kern, (size_t) ((int) smem))) return rc;
   kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
@@ -80,8 +77,7 @@ int launch_stream_k(ls2d_handle* h, const align_args& a, int maxp) {
   const size_t smem = icp_stream_smem_bytes(h->dp.cam.cols, T, maxp, false);
   if (smem > SMEM_LIMIT) return LS2D_ERR_UNSUPPORTED;
   auto kern = icp_stream_kernel<T, SENSOR, false, MINB>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (int rc = configure_kernel(h, kern, (size_t) ((int) smem))) return rc;
   kern<<<a.n_pairs, T, smem, h->stream>>>(h->dp, a, maxp);
   CU(cudaGetLastError());
   h->launches++;

@@ -31,8 +31,7 @@ int launch_multi(ls2d_handle* h, const multi_args& a, const int* cols) {
   if (multi2_serves(a)) {
     using map = multi2_map<M2_T, M2_PPF, M2_PPM, M2_CS>;
     auto kern = a.fused ? icp_multi2_kernel<M2_T, M2_PPF, M2_PPM, M2_CS, true> : icp_multi2_kernel<M2_T, M2_PPF, M2_PPM, M2_CS, false>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, map::BYTES));
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (int rc = configure_kernel(h, kern, (size_t) (map::BYTES))) return rc;
     kern<<<a.n_pairs, M2_T, map::BYTES, h->stream>>>(a);
     CU(cudaGetLastError());
     h->launches++;
@@ -42,8 +41,7 @@ int launch_multi(ls2d_handle* h, const multi_args& a, const int* cols) {
   const size_t smem = multi_smem_bytes(cols, a.n_slices, a.max_cols, a.max_points, T);
   if (smem > SMEM_LIMIT) return LS2D_ERR_UNSUPPORTED;
   auto kern = icp_multi_kernel<T, 4>;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (int rc = configure_kernel(h, kern, (size_t) ((int) smem))) return rc;
   kern<<<a.n_pairs, T, smem, h->stream>>>(a);
   CU(cudaGetLastError());
   h->launches++;

@@ -24,8 +24,7 @@ template <bool SENSOR, bool FUSED>
 int launch_score_k(ls2d_handle* h, const align_args& a, int maxp) {
   auto kern        = score_kernel<SCORE_T, SCORE_PPT, SENSOR, FUSED, SCORE_MINB>;
   const int smem   = score_map(maxp, h->dp.cam.cols, SCORE_T, SCORE_PPT).bytes();
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (int rc = configure_kernel(h, kern, (size_t) (smem))) return rc;
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SCORE_T, (size_t) smem));
   if (per_sm < 1) return LS2D_ERR_UNSUPPORTED;

@@ -9,7 +9,7 @@ namespace ls2d {
 
 int launch_project(ls2d_handle* h, const project_args& a) {
   const size_t smem = sizeof(unsigned) * 2 * (size_t) h->dp.cam.cols;
-  CU(cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (int rc = configure_kernel(h, project_kernel, (size_t) ((int) smem), false)) return rc;
   project_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
@@ -18,7 +18,7 @@ int launch_project(ls2d_handle* h, const project_args& a) {
 
 int launch_correspond(ls2d_handle* h, const correspond_args& a) {
   const size_t smem = sizeof(unsigned) * 4 * (size_t) h->dp.cam.cols;
-  CU(cudaFuncSetAttribute(correspond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (int rc = configure_kernel(h, correspond_kernel, (size_t) ((int) smem), false)) return rc;
   correspond_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
@@ -29,7 +29,7 @@ int launch_clip(ls2d_handle* h, const clip_args& a, int n) {
   if (n <= 0) return LS2D_OK;
   if (h->dp.cam.cols > 32 * CLIP_T) return LS2D_ERR_UNSUPPORTED;
   const size_t smem = sizeof(unsigned) * 2 * (size_t) h->dp.cam.cols;
-  CU(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (int rc = configure_kernel(h, clip_kernel, (size_t) ((int) smem), false)) return rc;
   clip_kernel<<<n, CLIP_T, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
@@ -38,7 +38,7 @@ int launch_clip(ls2d_handle* h, const clip_args& a, int n) {
 
 int launch_merge(ls2d_handle* h, const merge_args& a) {
   const size_t smem = sizeof(unsigned) * 4 * (size_t) h->dp.cam.cols;
-  CU(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (int rc = configure_kernel(h, merge_kernel, (size_t) ((int) smem), false)) return rc;
   merge_kernel<<<1, 256, smem, h->stream>>>(h->dp, a);
   CU(cudaGetLastError());
   h->launches++;
@@ -95,7 +95,7 @@ int launch_preprocess(ls2d_handle* h, const scan_dev_params& P, const scan_args&
   }
   scan_args a = a_in;
   a.beam_cs   = (const float2*) h->d_beam.p;
-  CU(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (int rc = configure_kernel(h, preprocess_kernel, (size_t) ((int) smem), false)) return rc;
   if (!h->d_ticket.p) {
     if ((rc = reserve(h->d_ticket, sizeof(int)))) return rc;
     CU(cudaMemsetAsync(h->d_ticket.p, 0, sizeof(int), h->stream));
@@ -113,7 +113,7 @@ int launch_clip_voxel(ls2d_handle* h, const clip_args& a, int n, float inv_res) 
   if (C > 32 * SCAN_T || C >= (1 << 14)) return LS2D_ERR_UNSUPPORTED;
   const size_t smem = clip_voxel_smem_bytes(C);
   if (smem > SMEM_LIMIT) return LS2D_ERR_UNSUPPORTED;
-  CU(cudaFuncSetAttribute(clip_voxel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  if (int rc = configure_kernel(h, clip_voxel_kernel, (size_t) ((int) smem), false)) return rc;
   clip_voxel_kernel<<<n, SCAN_T, smem, h->stream>>>(h->dp, a, inv_res);
   CU(cudaGetLastError());
   h->launches++;
